@@ -1,0 +1,119 @@
+/*
+ * sassy_gpu.h -- entry points of libsassy_b200.so beyond the reference's C ABI
+ * (include/sassy.h).  The reference's C ABI (src/c.rs) only exposes
+ * Searcher::search without CIGARs; these functions expose the rest of the Rust
+ * surface of the hot path so that a Rust/Python/C host can bind all of it:
+ *
+ *   reference Rust item (file:line)                      this header
+ *   ---------------------------------------------------  ---------------------------------
+ *   Searcher::search            src/search.rs:510        sassy_gpu_search(all=0)
+ *   Searcher::search_all        src/search.rs:685        sassy_gpu_search(all=1)
+ *   CachedRev (text reused)     src/search.rs:144-166    sassy_gpu_text_upload + *_text calls
+ *   Searcher::encode_patterns   src/search.rs:404        sassy_gpu_encode_patterns
+ *   search_encoded_patterns     src/search.rs:415        sassy_gpu_search_encoded(all=0)
+ *   search_all_encoded_patterns src/search.rs:426        sassy_gpu_search_encoded(all=1)
+ *   Match{.., cigar}            src/search.rs:35-62      sassy_gpu_Match + sassy_gpu_result_ops
+ *   Cigar::to_string (pa-types) src/lib.rs:83,107        sassy_gpu_cigar
+ *
+ * Error handling: functions returning a pointer return NULL on error and
+ * functions returning int return non-zero; sassy_gpu_last_error() then holds a
+ * message (thread-local).  Nothing here falls back to the CPU.
+ */
+#ifndef SASSY_GPU_H
+#define SASSY_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "sassy.h"
+
+typedef struct sassy_gpu_Text sassy_gpu_Text;         /* a text resident in HBM */
+typedef struct sassy_gpu_Patterns sassy_gpu_Patterns; /* EncodedPatterns */
+typedef struct sassy_gpu_Result sassy_gpu_Result;     /* Vec<Match> incl. CIGAR ops */
+
+/* One match; same fields as the reference's Match (src/search.rs:35-62).
+ * The CIGAR ops of match i are the ops_len bytes at sassy_gpu_result_ops() + ops_off,
+ * one char per op out of "=XID", in pattern direction. 64 bytes. */
+typedef struct sassy_gpu_Match {
+  uint64_t pattern_idx;
+  uint64_t text_idx;
+  uint64_t text_start;
+  uint64_t text_end;
+  uint64_t pattern_start;
+  uint64_t pattern_end;
+  int32_t cost;
+  uint8_t strand; /* 0 = Fwd, 1 = Rc */
+  uint8_t reserved[3];
+  uint32_t ops_len;
+  uint32_t reserved2;
+  uint64_t ops_off;
+} sassy_gpu_Match;
+
+/* Timing/shape of the last search of a searcher (CUDA events on its stream). */
+typedef struct sassy_gpu_Stats {
+  float scan_ms;          /* scan kernel(s) only */
+  float total_ms;         /* tables + scan + sort + minima + traceback + result copy */
+  uint32_t scan_launches; /* our scan kernel launches */
+  uint32_t aux_launches;  /* our minima + traceback launches */
+  uint64_t candidates;    /* end positions with cost <= k seen by the scan */
+  uint64_t matches;
+  uint32_t row_bytes;     /* bytes of text per thread */
+  uint32_t rows;
+  uint32_t words;         /* 32-bit words per pattern bit-vector */
+  uint32_t blocks_per_sm;
+  uint32_t retries;       /* re-scans after a candidate-buffer overflow */
+  uint32_t reserved;
+} sassy_gpu_Stats;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int sassy_gpu_device_count(void);
+const char *sassy_gpu_last_error(void);
+
+/* Like sassy_searcher (src/c.rs:51-70) with an explicit CUDA device; NULL on error. */
+sassy_SearcherType *sassy_gpu_searcher(const char *alphabet, bool rc, float alpha, int device);
+
+/* Scan kernel data path: 0 = TMA-staged (default), 1 = per-thread global loads (A/B baseline). */
+int sassy_gpu_set_variant(sassy_SearcherType *searcher, int variant);
+int sassy_gpu_stats(const sassy_SearcherType *searcher, sassy_gpu_Stats *out);
+
+/* Pinned host memory for texts that are searched through the host-pointer entry points. */
+void *sassy_gpu_host_alloc(size_t bytes);
+void sassy_gpu_host_free(void *ptr);
+
+sassy_gpu_Text *sassy_gpu_text_upload(sassy_SearcherType *searcher, const uint8_t *text, size_t text_len);
+sassy_gpu_Text *sassy_gpu_text_from_device(sassy_SearcherType *searcher, const void *device_ptr, size_t text_len);
+size_t sassy_gpu_text_len(const sassy_gpu_Text *text);
+void sassy_gpu_text_free(sassy_SearcherType *searcher, sassy_gpu_Text *text);
+
+/* Searcher::search (all = 0) / search_all (all = 1) with CIGARs. */
+sassy_gpu_Result *sassy_gpu_search(sassy_SearcherType *searcher, const uint8_t *pattern, size_t pattern_len,
+                                   const uint8_t *text, size_t text_len, size_t k, int all);
+sassy_gpu_Result *sassy_gpu_search_text(sassy_SearcherType *searcher, const uint8_t *pattern, size_t pattern_len,
+                                        const sassy_gpu_Text *text, size_t k, int all);
+
+/* Searcher::encode_patterns: n_patterns patterns of equal length pattern_len, back to back. */
+sassy_gpu_Patterns *sassy_gpu_encode_patterns(sassy_SearcherType *searcher, const uint8_t *patterns,
+                                              size_t n_patterns, size_t pattern_len);
+void sassy_gpu_patterns_free(sassy_gpu_Patterns *patterns);
+/* search_encoded_patterns (all = 0) / search_all_encoded_patterns (all = 1). */
+sassy_gpu_Result *sassy_gpu_search_encoded(sassy_SearcherType *searcher, const sassy_gpu_Patterns *patterns,
+                                           const sassy_gpu_Text *text, size_t k, int all);
+sassy_gpu_Result *sassy_gpu_search_encoded_host(sassy_SearcherType *searcher, const sassy_gpu_Patterns *patterns,
+                                                const uint8_t *text, size_t text_len, size_t k, int all);
+
+size_t sassy_gpu_result_len(const sassy_gpu_Result *result);
+const sassy_gpu_Match *sassy_gpu_result_matches(const sassy_gpu_Result *result);
+const char *sassy_gpu_result_ops(const sassy_gpu_Result *result);
+/* Writes the run-length CIGAR of match i ("3=1X") NUL-terminated into buf; returns its length
+ * (excluding the NUL) even if it did not fit. */
+size_t sassy_gpu_cigar(const sassy_gpu_Result *result, size_t i, char *buf, size_t cap);
+void sassy_gpu_result_free(sassy_gpu_Result *result);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SASSY_GPU_H */

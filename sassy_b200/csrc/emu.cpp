@@ -1,0 +1,209 @@
+// CPU-only emulation of the GPU pipeline for the `-m "not gpu"` tests.
+//
+// This is NOT a CPU fallback and is not part of libsassy_b200.so: it is a test
+// harness (libsassy_b200_emu.so) that executes the very same per-thread code
+// the CUDA kernels run (scan_core.cuh: process16 / is_local_minimum /
+// trace_one) and the same host logic (host_logic.h: equality tables, row
+// tiling), one "thread" after the other, so that tiling, warm-up, restart,
+// candidate, minima and traceback logic can be checked against the oracle on
+// a machine without a GPU.  What it cannot check is the TMA/mbarrier staging.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "host_logic.h"
+
+using namespace sb;
+
+namespace {
+
+template <int W, bool REV>
+void scan_rows(const ScanArgs& a, const uint32_t* eq_q, uint32_t qs) {
+  EqTab eqt;
+  eqt.p = eq_q;
+  eqt.saddr = 0;
+  eqt.rowbytes = (uint32_t)W * 4u;
+  const uint32_t total = a.g.nwarm + a.g.nstage;
+  const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
+  for (uint64_t row = 0; row < tiles * kScanThreads; row++) {  // includes the idle threads of the last tile
+    Lane<W> s;
+    lane_reset<W>(s, a.m);
+    for (uint32_t it = 0; it < total; it++) {
+      int64_t r;
+      uint32_t col;
+      bool own;
+      stage_coord<REV>(a.g, it, (int64_t)row, r, col, own);
+      const uint64_t stage_idx = (uint64_t)(r * (int64_t)a.g.ltot + (int64_t)col);
+      const bool special = stage_is_special(a, stage_idx);
+      const bool valid = r >= 0 && r < (int64_t)a.g.rows;
+      for (int cc = 0; cc < kStageBytes / 16; cc++) {
+        const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
+        uint32_t x[4] = {0, 0, 0, 0};
+        if (valid) memcpy(x, a.text + stage_idx + 16u * c, 16);
+        if (special)
+          process16<W, REV, true>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+        else
+          process16<W, REV, false>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+      }
+    }
+  }
+}
+
+template <bool REV>
+void scan_dispatch(int W, const ScanArgs& a, const uint32_t* eq_q, uint32_t qs) {
+  switch (W) {
+    case 1: scan_rows<1, REV>(a, eq_q, qs); break;
+    case 2: scan_rows<2, REV>(a, eq_q, qs); break;
+    case 3: scan_rows<3, REV>(a, eq_q, qs); break;
+    case 4: scan_rows<4, REV>(a, eq_q, qs); break;
+    case 6: scan_rows<6, REV>(a, eq_q, qs); break;
+    case 8: scan_rows<8, REV>(a, eq_q, qs); break;
+    case 16: scan_rows<16, REV>(a, eq_q, qs); break;
+    case 32: scan_rows<32, REV>(a, eq_q, qs); break;
+    default: abort();
+  }
+}
+
+}  // namespace
+
+struct EmuResult {
+  std::vector<GpuMatch> m;
+  std::vector<uint32_t> ops;
+  uint32_t ops_words;
+  uint64_t candidates;
+  ScanGeom g;
+};
+
+extern "C" {
+
+// queries: nq * m bytes; rev[q] = 1 scans the reversed text.  ltot_override > 0
+// forces the row length (to exercise row boundaries on tiny texts); bpw plays
+// the part of "resident blocks per wave" in the tiling heuristic.
+EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, uint32_t nq, int m,
+                      const uint8_t* text, uint64_t n, int k, int all_minima, int include_pos0,
+                      uint32_t ltot_override, int bpw) {
+  ProfileParams pp;
+  if (!profile_params(profile, pp) || m <= 0) return nullptr;
+  const int W = round_words((m + 31) / 32);
+  if (W < 0) return nullptr;
+  EmuResult* res = new EmuResult;
+  res->ops_words = (uint32_t)((m + k + 1 + 15) / 16);
+  res->candidates = 0;
+
+  std::vector<uint32_t> eq((size_t)nq * pp.nrows * W);
+  for (uint32_t q = 0; q < nq; q++) build_eq_table(profile, queries + (size_t)q * m, m, W, pp.nrows, &eq[(size_t)q * pp.nrows * W]);
+
+  ScanGeom g = choose_geom(n, m, k, nq, bpw > 0 ? bpw : 444);
+  if (ltot_override) {
+    g.ltot = std::max<uint32_t>(ltot_override / kStageBytes * kStageBytes, g.nwarm * kStageBytes);
+    g.rows = (uint32_t)((n + g.ltot - 1) / g.ltot);
+    g.nstage = g.ltot / kStageBytes;
+  }
+  res->g = g;
+  std::vector<uint8_t> padded(std::max<size_t>(padded_alloc(n), (size_t)g.rows * g.ltot + 256), 0);
+  if (n) memcpy(padded.data(), text, n);
+
+  const uint64_t cap = (uint64_t)nq * (n + 2) + 16;
+  std::vector<uint64_t> keys(cap);
+  std::vector<uint32_t> cost(cap);
+  unsigned long long count = 0;
+  if (include_pos0 && m <= k && n > 0)
+    for (uint32_t q = 0; q < nq; q++) {
+      keys[count] = cand_key(q, 0);
+      cost[count] = (uint32_t)m;
+      count++;
+    }
+
+  ScanArgs a;
+  memset(&a, 0, sizeof a);
+  a.text = padded.data();
+  a.n = n;
+  a.g = g;
+  a.sh0 = pp.sh0;
+  a.msk0 = pp.msk0;
+  a.nrows = pp.nrows;
+  a.rowbytes = (uint32_t)W * 4u;
+  a.m = m;
+  a.k = k;
+  a.cand_keys = keys.data();
+  a.cand_cost = cost.data();
+  a.cand_count = &count;
+  a.cand_cap = cap;
+  if (n > 0) {
+    for (uint32_t q = 0; q < nq; q++) {
+      const uint32_t* eq_q = &eq[(size_t)q * pp.nrows * W];
+      if (rev[q]) {
+        a.reset_idx = n - 1;
+        scan_dispatch<true>(W, a, eq_q, q);
+      } else {
+        a.reset_idx = 0;
+        scan_dispatch<false>(W, a, eq_q, q);
+      }
+    }
+  }
+  res->candidates = count;
+
+  // sort by key (the GPU path uses a device radix sort)
+  std::vector<uint64_t> order(count);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return keys[x] < keys[y]; });
+  std::vector<uint64_t> skeys(count);
+  std::vector<uint32_t> scost(count);
+  for (uint64_t i = 0; i < count; i++) skeys[i] = keys[order[i]], scost[i] = cost[order[i]];
+
+  std::vector<uint64_t> sel;
+  for (uint64_t i = 0; i < count; i++)
+    if (all_minima || is_local_minimum(skeys.data(), scost.data(), i, count)) sel.push_back(skeys[i]);
+
+  res->m.resize(sel.size());
+  res->ops.assign(sel.size() * res->ops_words, 0);
+  std::vector<uint32_t> scratch((size_t)(m + k + 1) * W * 2);
+  for (size_t i = 0; i < sel.size(); i++) {
+    const uint32_t qs = key_qs(sel[i]);
+    ColStore cs;
+    cs.base = scratch.data();
+    cs.stride = 1;
+    TraceOut out;
+    const uint8_t* pat = queries + (size_t)qs * m;
+    const uint32_t* eq_q = &eq[(size_t)qs * pp.nrows * W];
+    uint32_t* ops = &res->ops[i * res->ops_words];
+    switch (profile) {
+      case kDna:
+        trace_one<kDna>(padded.data(), n, rev[qs] != 0, pat, m, k, eq_q, W, pp.sh0, pp.msk0, key_pos(sel[i]), cs, ops,
+                        res->ops_words, out);
+        break;
+      case kIupac:
+        trace_one<kIupac>(padded.data(), n, rev[qs] != 0, pat, m, k, eq_q, W, pp.sh0, pp.msk0, key_pos(sel[i]), cs,
+                          ops, res->ops_words, out);
+        break;
+      default:
+        trace_one<kAscii>(padded.data(), n, rev[qs] != 0, pat, m, k, eq_q, W, pp.sh0, pp.msk0, key_pos(sel[i]), cs,
+                          ops, res->ops_words, out);
+        break;
+    }
+    GpuMatch gm;
+    gm.text_start = out.text_start;
+    gm.text_end = out.text_end;
+    gm.qs = qs;
+    gm.cost = out.cost;
+    gm.nops = out.nops;
+    gm.failed = out.failed;
+    res->m[i] = gm;
+  }
+  return res;
+}
+
+size_t emu_len(const EmuResult* r) { return r->m.size(); }
+const GpuMatch* emu_matches(const EmuResult* r) { return r->m.data(); }
+const uint32_t* emu_ops(const EmuResult* r) { return r->ops.data(); }
+uint32_t emu_ops_words(const EmuResult* r) { return r->ops_words; }
+uint64_t emu_candidates(const EmuResult* r) { return r->candidates; }
+uint32_t emu_ltot(const EmuResult* r) { return r->g.ltot; }
+uint32_t emu_rows(const EmuResult* r) { return r->g.rows; }
+void emu_free(EmuResult* r) { delete r; }
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+#include "engine.h"
+
+#include <cudaTypedefs.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cub/cub.cuh>
+
+namespace sb {
+
+#define SB_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      char buf__[512];                                                                        \
+      snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+               __FILE__, __LINE__);                                                           \
+      throw CudaError(buf__);                                                                 \
+    }                                                                                         \
+  } while (0)
+
+void DevBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return;
+  release();
+  size_t want = std::max(bytes, (size_t)256);
+  SB_CUDA(cudaMalloc(&p, want));
+  cap = want;
+}
+
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+Engine::Engine(int profile, int device) : profile_(profile), device_(device), variant_(kVariantTma) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw CudaError(std::string("sassy_b200 needs a CUDA device (no CPU fallback exists): ") +
+                    cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) throw CudaError("invalid CUDA device index");
+  SB_CUDA(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  SB_CUDA(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major < 10)
+    throw CudaError(std::string("sassy_b200 is built for sm_100a (B200); found ") + prop.name);
+  sm_count_ = prop.multiProcessorCount;
+  SB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  for (auto& ev : ev_) SB_CUDA(cudaEventCreate(&ev));
+  ProfileParams pp;
+  if (!profile_params(profile_, pp)) throw CudaError("unknown profile");
+  nrows_ = pp.nrows, sh0_ = pp.sh0, msk0_ = pp.msk0;
+  const char* v = getenv("SASSY_B200_VARIANT");
+  if (v && !strcmp(v, "ldg")) variant_ = kVariantLdg;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    encode_tiled_ = fn;
+  if (!encode_tiled_ && variant_ == kVariantTma) throw CudaError("cuTensorMapEncodeTiled not available");
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (DevBuf* b : {&eq_, &patterns_, &revflags_, &keys_, &cost_, &keys2_, &cost2_, &flags_, &sel_, &count_,
+                    &cubtmp_, &scratch_, &ops_, &out_})
+    b->release();
+  if (staged_.d) cudaFree(staged_.d);
+  for (auto& ev : ev_)
+    if (ev) cudaEventDestroy(ev);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+DeviceText* Engine::upload_text(const uint8_t* host, uint64_t n) {
+  SB_CUDA(cudaSetDevice(device_));
+  if (n >= (1ull << kPosBits)) throw CudaError("text longer than 2^40 bytes is not supported");
+  DeviceText* t = new DeviceText;
+  t->n = n;
+  t->alloc = padded_alloc(n);
+  try {
+    SB_CUDA(cudaMalloc((void**)&t->d, t->alloc));
+    if (n) SB_CUDA(cudaMemcpyAsync(t->d, host, n, cudaMemcpyHostToDevice, stream_));
+    SB_CUDA(cudaMemsetAsync(t->d + n, 0, t->alloc - n, stream_));
+    SB_CUDA(cudaStreamSynchronize(stream_));
+  } catch (...) {
+    if (t->d) cudaFree(t->d);
+    delete t;
+    throw;
+  }
+  return t;
+}
+
+DeviceText* Engine::adopt_device_text(const void* dptr, uint64_t n) {
+  SB_CUDA(cudaSetDevice(device_));
+  if (n >= (1ull << kPosBits)) throw CudaError("text longer than 2^40 bytes is not supported");
+  DeviceText* t = new DeviceText;
+  t->n = n;
+  t->alloc = padded_alloc(n);
+  try {
+    SB_CUDA(cudaMalloc((void**)&t->d, t->alloc));
+    if (n) SB_CUDA(cudaMemcpyAsync(t->d, dptr, n, cudaMemcpyDeviceToDevice, stream_));
+    SB_CUDA(cudaMemsetAsync(t->d + n, 0, t->alloc - n, stream_));
+    SB_CUDA(cudaStreamSynchronize(stream_));
+  } catch (...) {
+    if (t->d) cudaFree(t->d);
+    delete t;
+    throw;
+  }
+  return t;
+}
+
+void Engine::free_text(DeviceText* t) {
+  if (!t) return;
+  cudaSetDevice(device_);
+  if (t->d && t->owned) cudaFree(t->d);
+  delete t;
+}
+
+DeviceText* Engine::stage_text(const uint8_t* host, uint64_t n) {
+  SB_CUDA(cudaSetDevice(device_));
+  if (n >= (1ull << kPosBits)) throw CudaError("text longer than 2^40 bytes is not supported");
+  const size_t need = padded_alloc(n);
+  if (need > staged_.alloc) {
+    if (staged_.d) cudaFree(staged_.d);
+    staged_.d = nullptr;
+    staged_.alloc = 0;
+    SB_CUDA(cudaMalloc((void**)&staged_.d, need));
+    staged_.alloc = need;
+  }
+  staged_.n = n;
+  // Copy in slices so that pinned sources stream at full PCIe rate while the
+  // zero padding is written; the scan is queued behind on the same stream.
+  const uint64_t slice = 256ull << 20;
+  for (uint64_t off = 0; off < n; off += slice) {
+    const uint64_t len = std::min(slice, n - off);
+    SB_CUDA(cudaMemcpyAsync(staged_.d + off, host + off, len, cudaMemcpyHostToDevice, stream_));
+  }
+  SB_CUDA(cudaMemsetAsync(staged_.d + n, 0, std::min<size_t>(staged_.alloc - n, 2ull * kMaxRowBytes + 256), stream_));
+  return &staged_;
+}
+
+void Engine::build_tables(const std::vector<Query>& queries, int m, int W) {
+  const size_t nq = queries.size();
+  h_eq_.resize(nq * nrows_ * W);
+  h_pat_.resize(nq * (size_t)m);
+  h_rev_.resize(nq);
+  for (size_t q = 0; q < nq; q++) {
+    memcpy(&h_pat_[q * m], queries[q].bytes, m);
+    h_rev_[q] = queries[q].rev ? 1 : 0;
+    build_eq_table(profile_, queries[q].bytes, m, W, nrows_, &h_eq_[q * nrows_ * W]);
+  }
+  eq_.ensure(h_eq_.size() * sizeof(uint32_t));
+  patterns_.ensure(h_pat_.size());
+  revflags_.ensure(h_rev_.size());
+  SB_CUDA(cudaMemcpyAsync(eq_.p, h_eq_.data(), h_eq_.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+  SB_CUDA(cudaMemcpyAsync(patterns_.p, h_pat_.data(), h_pat_.size(), cudaMemcpyHostToDevice, stream_));
+  SB_CUDA(cudaMemcpyAsync(revflags_.p, h_rev_.data(), h_rev_.size(), cudaMemcpyHostToDevice, stream_));
+}
+
+void Engine::make_tensor_map(CUtensorMap* map, const DeviceText& text, const ScanGeom& g) const {
+  auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(encode_tiled_);
+  const cuuint64_t dims[2] = {g.ltot, std::max<uint32_t>(g.rows, 1)};
+  const cuuint64_t strides[1] = {g.ltot};
+  const cuuint32_t box[2] = {kStageBytes, kScanThreads};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, text.d, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    throw CudaError(buf);
+  }
+}
+
+void Engine::search(const DeviceText& text, const std::vector<Query>& queries, int m, int k, bool all_minima,
+                    bool include_pos0, MatchSet& out) {
+  SB_CUDA(cudaSetDevice(device_));
+  stats_ = SearchStats();
+  out.m.clear();
+  out.ops.clear();
+  const uint32_t nq = (uint32_t)queries.size();
+  if (m <= 0) throw CudaError("empty pattern");
+  const int W = round_words((m + 31) / 32);
+  if (W < 0) throw CudaError("pattern longer than 1024 characters is not supported");
+  if (nq == 0) return;
+  if (nq >= (1u << (64 - kPosBits))) throw CudaError("too many queries in one search");
+  if (k < 0) k = 0;
+  uint32_t nfwd = 0;
+  while (nfwd < nq && !queries[nfwd].rev) nfwd++;
+  for (uint32_t q = nfwd; q < nq; q++)
+    if (!queries[q].rev) throw CudaError("forward queries must precede reversed ones");
+  out.ops_words = (uint32_t)((m + k + 1 + 15) / 16);
+  stats_.words = (uint32_t)W;
+
+  SB_CUDA(cudaEventRecord(ev_[0], stream_));
+  build_tables(queries, m, W);
+
+  const uint64_t n = text.n;
+  const int occ = scan_blocks_per_sm(W, false, variant_, nrows_);
+  stats_.blocks_per_sm = (uint32_t)occ;
+  const ScanGeom g = choose_geom(n, m, k, nq, occ * sm_count_);
+  if ((uint64_t)g.rows * g.ltot > text.alloc) throw CudaError("internal: text padding too small for tiling");
+  stats_.ltot = g.ltot;
+  stats_.rows = g.rows;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof tmap);
+  if (variant_ == kVariantTma && n > 0) make_tensor_map(&tmap, text, g);
+
+  if (cand_cap_ == 0) cand_cap_ = 1ull << 20;
+  count_.ensure(2 * sizeof(unsigned long long));
+  uint64_t ncand = 0;
+  for (int attempt = 0;; attempt++) {
+    keys_.ensure(cand_cap_ * sizeof(uint64_t));
+    cost_.ensure(cand_cap_ * sizeof(uint32_t));
+    // end position 0 (empty text prefix) has cost m: a candidate iff m <= k.
+    // (reference src/search.rs:1320-1322; never reported for an empty text, :1314-1316)
+    std::vector<uint64_t> k0;
+    std::vector<uint32_t> c0;
+    if (include_pos0 && m <= k && n > 0) {
+      for (uint32_t q = 0; q < nq; q++) {
+        k0.push_back(cand_key(q, 0));
+        c0.push_back((uint32_t)m);
+      }
+      SB_CUDA(cudaMemcpyAsync(keys_.p, k0.data(), k0.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream_));
+      SB_CUDA(cudaMemcpyAsync(cost_.p, c0.data(), c0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+    }
+    unsigned long long init = k0.size();
+    SB_CUDA(cudaMemcpyAsync(count_.p, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
+
+    ScanArgs a;
+    memset(&a, 0, sizeof a);
+    a.text = text.d;
+    a.n = n;
+    a.g = g;
+    a.sh0 = sh0_;
+    a.msk0 = msk0_;
+    a.nrows = nrows_;
+    a.rowbytes = (uint32_t)W * 4u;
+    a.m = m;
+    a.k = k;
+    a.cand_keys = keys_.as<uint64_t>();
+    a.cand_cost = cost_.as<uint32_t>();
+    a.cand_count = count_.as<unsigned long long>();
+    a.cand_cap = cand_cap_;
+    SB_CUDA(cudaEventRecord(ev_[1], stream_));
+    if (n > 0) {
+      if (nfwd) {
+        a.reset_idx = 0;
+        a.nq = nfwd;
+        a.qs_base = 0;
+        a.eq = eq_.as<uint32_t>();
+        SB_CUDA(launch_scan(W, false, variant_, &tmap, a, stream_));
+        stats_.scan_launches++;
+      }
+      if (nq > nfwd) {
+        a.reset_idx = n - 1;
+        a.nq = nq - nfwd;
+        a.qs_base = nfwd;
+        a.eq = eq_.as<uint32_t>() + (size_t)nfwd * nrows_ * W;
+        SB_CUDA(launch_scan(W, true, variant_, &tmap, a, stream_));
+        stats_.scan_launches++;
+      }
+    }
+    SB_CUDA(cudaEventRecord(ev_[2], stream_));
+    unsigned long long cnt = 0;
+    SB_CUDA(cudaMemcpyAsync(&cnt, count_.p, sizeof cnt, cudaMemcpyDeviceToHost, stream_));
+    SB_CUDA(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    SB_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2]));
+    stats_.scan_ms += ms;
+    if (cnt <= cand_cap_) {
+      ncand = cnt;
+      break;
+    }
+    if (attempt >= 3) throw CudaError("candidate buffer overflow after retries");
+    cand_cap_ = (size_t)(cnt + cnt / 8 + 1024);  // dense text: re-run with an exact-size buffer
+    stats_.retries++;
+  }
+  stats_.candidates = ncand;
+
+  uint64_t nsel = 0;
+  const uint64_t* sel_keys = nullptr;
+  if (ncand > 0) {
+    keys2_.ensure(ncand * sizeof(uint64_t));
+    cost2_.ensure(ncand * sizeof(uint32_t));
+    int end_bit = kPosBits;
+    while ((1ull << (end_bit - kPosBits)) < nq) end_bit++;
+    size_t tmp_bytes = 0;
+    SB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_.as<uint64_t>(), keys2_.as<uint64_t>(),
+                                            cost_.as<uint32_t>(), cost2_.as<uint32_t>(), ncand, 0, end_bit,
+                                            stream_));
+    cubtmp_.ensure(tmp_bytes);
+    SB_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp_.p, tmp_bytes, keys_.as<uint64_t>(), keys2_.as<uint64_t>(),
+                                            cost_.as<uint32_t>(), cost2_.as<uint32_t>(), ncand, 0, end_bit,
+                                            stream_));
+    if (all_minima) {
+      nsel = ncand;
+      sel_keys = keys2_.as<uint64_t>();
+    } else {
+      flags_.ensure(ncand);
+      sel_.ensure(ncand * sizeof(uint64_t));
+      SB_CUDA(launch_minima(keys2_.as<uint64_t>(), cost2_.as<uint32_t>(), ncand, flags_.as<uint8_t>(), stream_));
+      stats_.aux_launches++;
+      unsigned long long* d_nsel = count_.as<unsigned long long>() + 1;
+      size_t tmp2 = 0;
+      SB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp2, keys2_.as<uint64_t>(), flags_.as<uint8_t>(),
+                                         sel_.as<uint64_t>(), d_nsel, ncand, stream_));
+      cubtmp_.ensure(tmp2);
+      SB_CUDA(cub::DeviceSelect::Flagged(cubtmp_.p, tmp2, keys2_.as<uint64_t>(), flags_.as<uint8_t>(),
+                                         sel_.as<uint64_t>(), d_nsel, ncand, stream_));
+      unsigned long long h = 0;
+      SB_CUDA(cudaMemcpyAsync(&h, d_nsel, sizeof h, cudaMemcpyDeviceToHost, stream_));
+      SB_CUDA(cudaStreamSynchronize(stream_));
+      nsel = h;
+      sel_keys = sel_.as<uint64_t>();
+    }
+  }
+
+  if (nsel > 0) {
+    out_.ensure(nsel * sizeof(GpuMatch));
+    ops_.ensure(nsel * out.ops_words * sizeof(uint32_t));
+    const uint64_t words_per_match = (uint64_t)(m + k + 1) * W * 2;
+    const uint64_t max_scratch_words = (512ull << 20) / 4;  // 512 MiB of scratch per slice
+    uint64_t slice = std::max<uint64_t>(1, max_scratch_words / words_per_match);
+    slice = std::min(slice, nsel);
+    scratch_.ensure(slice * words_per_match * sizeof(uint32_t));
+    TraceArgs t;
+    memset(&t, 0, sizeof t);
+    t.text = text.d;
+    t.n = n;
+    t.profile = profile_;
+    t.patterns = patterns_.as<uint8_t>();
+    t.rev_flags = revflags_.as<uint8_t>();
+    t.eq = eq_.as<uint32_t>();
+    t.nrows = nrows_;
+    t.sh0 = sh0_;
+    t.msk0 = msk0_;
+    t.m = m;
+    t.k = k;
+    t.W = W;
+    t.keys = sel_keys;
+    t.scratch = scratch_.as<uint32_t>();
+    t.ops = ops_.as<uint32_t>();
+    t.ops_words = out.ops_words;
+    t.out = out_.as<GpuMatch>();
+    for (uint64_t first = 0; first < nsel; first += slice) {
+      t.first = first;
+      t.count = std::min(slice, nsel - first);
+      SB_CUDA(launch_trace(t, stream_));
+      stats_.aux_launches++;
+    }
+    out.m.resize(nsel);
+    out.ops.resize(nsel * out.ops_words);
+    SB_CUDA(cudaMemcpyAsync(out.m.data(), out_.p, nsel * sizeof(GpuMatch), cudaMemcpyDeviceToHost, stream_));
+    SB_CUDA(cudaMemcpyAsync(out.ops.data(), ops_.p, out.ops.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            stream_));
+  }
+  SB_CUDA(cudaEventRecord(ev_[3], stream_));
+  SB_CUDA(cudaStreamSynchronize(stream_));
+  float total = 0;
+  SB_CUDA(cudaEventElapsedTime(&total, ev_[0], ev_[3]));
+  stats_.total_ms = total;
+  stats_.matches = nsel;
+}
+
+}  // namespace sb

@@ -1,0 +1,114 @@
+// Host side of the GPU search path: owns the device buffers of one searcher
+// and runs scan -> sort -> local-minima -> traceback on one CUDA stream.
+// Mirrors the role of the reference's `Searcher<P>` internals
+// (src/search.rs:227-256 scratch buffers, :884-937 search_one_strand,
+//  :1372-1517 process_matches); the public surface is in searcher.h / c_api.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace sb {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes);
+  void release();
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// A text resident in HBM, padded with zero bytes so that any row tiling up to
+// kMaxRowBytes can be laid over it (the device analogue of the reference's
+// CachedRev, src/search.rs:144-166: upload once, search many times, both strands).
+struct DeviceText {
+  uint8_t* d = nullptr;
+  uint64_t n = 0;
+  size_t alloc = 0;
+  bool owned = true;
+};
+
+// One searched sequence: the bytes the scan compares against and the direction.
+struct Query {
+  const uint8_t* bytes;  // m bytes
+  bool rev;              // scan the reversed text (v1 reverse-complement strand)
+};
+
+struct SearchStats {
+  float scan_ms = 0;      // scan kernel(s) only (CUDA events on the engine stream)
+  float total_ms = 0;     // scan + sort + minima + traceback + result copies
+  uint32_t scan_launches = 0;
+  uint32_t aux_launches = 0;  // minima + trace launches of ours
+  uint64_t candidates = 0;
+  uint64_t matches = 0;
+  uint32_t ltot = 0, rows = 0, words = 0, blocks_per_sm = 0;
+  uint32_t retries = 0;
+};
+
+struct MatchSet {
+  std::vector<GpuMatch> m;
+  std::vector<uint32_t> ops;  // m.size() * ops_words, 2-bit op codes
+  uint32_t ops_words = 0;
+};
+
+class Engine {
+ public:
+  Engine(int profile, int device);
+  ~Engine();
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+
+  int profile() const { return profile_; }
+  int device() const { return device_; }
+  cudaStream_t stream() const { return stream_; }
+
+  DeviceText* upload_text(const uint8_t* host, uint64_t n);        // host -> HBM (new buffer)
+  DeviceText* adopt_device_text(const void* dptr, uint64_t n);      // device -> padded device copy
+  void free_text(DeviceText* t);
+  // Re-usable staging text for the plain search(pattern, text) ABI.
+  DeviceText* stage_text(const uint8_t* host, uint64_t n);
+
+  // Queries must all have length m; forward queries must precede reversed ones.
+  // include_pos0: also consider end position 0 (cost m) when m <= k (v1 only,
+  // reference src/search.rs:1320-1322).
+  void search(const DeviceText& text, const std::vector<Query>& queries, int m, int k, bool all_minima,
+              bool include_pos0, MatchSet& out);
+
+  const SearchStats& stats() const { return stats_; }
+  void set_variant(int v) { variant_ = v; }
+  int variant() const { return variant_; }
+
+ private:
+  void build_tables(const std::vector<Query>& queries, int m, int W);
+  void make_tensor_map(CUtensorMap* map, const DeviceText& text, const ScanGeom& g) const;
+
+  int profile_;
+  int device_;
+  int variant_;
+  int sm_count_ = 148;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t nrows_, sh0_, msk0_;
+
+  DevBuf eq_, patterns_, revflags_;
+  DevBuf keys_, cost_, keys2_, cost2_, flags_, sel_, count_, cubtmp_;
+  DevBuf scratch_, ops_, out_;
+  uint64_t cand_cap_ = 0;
+  DeviceText staged_;
+  std::vector<uint32_t> h_eq_;
+  std::vector<uint8_t> h_pat_, h_rev_;
+  SearchStats stats_;
+  void* encode_tiled_ = nullptr;
+};
+
+}  // namespace sb

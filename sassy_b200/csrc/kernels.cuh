@@ -1,0 +1,50 @@
+// Launch interface between the host engine (engine.cu) and the CUDA kernels
+// (scan_kernels.cu, post_kernels.cu).  sm_100a only.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "host_logic.h"
+
+namespace sb {
+
+constexpr int kScanStages = 2;     // shared-memory ring depth (128 B per thread per stage)
+
+enum ScanVariant : int { kVariantTma = 0, kVariantLdg = 1 };
+
+
+size_t scan_smem_bytes(int W, int variant, uint32_t nrows);
+// Max resident blocks per SM for the given instantiation (for grid sizing).
+int scan_blocks_per_sm(int W, bool rev, int variant, uint32_t nrows);
+// Launches one scan over `a.nq` queries x ceil(rows / kScanThreads) row tiles.
+cudaError_t launch_scan(int W, bool rev, int variant, const CUtensorMap* tmap, const ScanArgs& a,
+                        cudaStream_t stream);
+
+// flags[i] = 1 iff sorted candidate i is kept by the local-minima rule.
+cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags,
+                          cudaStream_t stream);
+
+struct TraceArgs {
+  const uint8_t* text;
+  uint64_t n;
+  int profile;
+  const uint8_t* patterns;  // [nq_total][m] raw query bytes (already complemented for rc slots)
+  const uint8_t* rev_flags;  // [nq_total] 1 = query scans the reversed text
+  const uint32_t* eq;        // [nq_total][nrows][W]
+  uint32_t nrows;
+  uint32_t sh0, msk0;
+  int32_t m, k;
+  int32_t W;
+  const uint64_t* keys;  // selected candidates (sorted)
+  uint64_t first;        // slice [first, first+count) handled by this launch
+  uint64_t count;
+  uint32_t* scratch;       // count * (m+k+1) * W * 2 words, interleaved by match
+  uint32_t* ops;           // [total][ops_words]
+  uint32_t ops_words;
+  GpuMatch* out;           // [total]
+};
+cudaError_t launch_trace(const TraceArgs& t, cudaStream_t stream);
+
+}  // namespace sb

@@ -1,0 +1,67 @@
+// Kernels that run after the scan on the (small) candidate list:
+//  * minima_kernel : local-minima selection on the sorted candidates
+//  * trace_kernel  : one thread per selected end position -> Match + CIGAR ops
+// Their per-thread logic lives in scan_core.cuh (shared with the host emulator).
+#include "kernels.cuh"
+
+namespace sb {
+namespace {
+
+__global__ void minima_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cost, uint64_t n,
+                              uint8_t* __restrict__ flags) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flags[i] = is_local_minimum(keys, cost, i, n) ? 1 : 0;
+}
+
+template <int P>
+__global__ void trace_kernel(const __grid_constant__ TraceArgs t) {
+  const uint64_t li = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= t.count) return;
+  const uint64_t gi = t.first + li;
+  const uint64_t key = t.keys[gi];
+  const uint32_t qs = key_qs(key);
+  const uint64_t end = key_pos(key);
+  const bool rev = t.rev_flags[qs] != 0;
+  ColStore cs;
+  cs.base = t.scratch + li;
+  cs.stride = t.count;
+  TraceOut out;
+  trace_one<P>(t.text, t.n, rev, t.patterns + (size_t)qs * t.m, t.m, t.k,
+               t.eq + (size_t)qs * t.nrows * t.W, t.W, t.sh0, t.msk0, end, cs,
+               t.ops + gi * t.ops_words, t.ops_words, out);
+  GpuMatch gm;
+  gm.text_start = out.text_start;
+  gm.text_end = out.text_end;
+  gm.qs = qs;
+  gm.cost = out.cost;
+  gm.nops = out.nops;
+  gm.failed = out.failed;
+  t.out[gi] = gm;
+}
+
+}  // namespace
+
+cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags,
+                          cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const unsigned threads = 256;
+  const uint64_t blocks = (n + threads - 1) / threads;
+  minima_kernel<<<(unsigned)blocks, threads, 0, stream>>>(keys, cost, n, flags);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trace(const TraceArgs& t, cudaStream_t stream) {
+  if (t.count == 0) return cudaSuccess;
+  const unsigned threads = 128;
+  const uint64_t blocks = (t.count + threads - 1) / threads;
+  switch (t.profile) {
+    case kDna: trace_kernel<kDna><<<(unsigned)blocks, threads, 0, stream>>>(t); break;
+    case kIupac: trace_kernel<kIupac><<<(unsigned)blocks, threads, 0, stream>>>(t); break;
+    case kAscii: trace_kernel<kAscii><<<(unsigned)blocks, threads, 0, stream>>>(t); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace sb

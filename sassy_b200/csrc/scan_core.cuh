@@ -1,0 +1,451 @@
+// Per-thread logic of the search path, shared by the CUDA kernels and by the
+// host emulator used in the CPU-only tests (tests/test_host_emulation.py).
+//
+// What it computes (reference semantics, restated):
+//   * the bottom row c_i = D[m][i] of the semi-global edit-distance matrix
+//     (top row 0, left column j): reference src/search.rs:1058-1061,1101 and
+//     src/pattern_tiling/search.rs:91-117,148-175;
+//   * every end position with c_i <= k is emitted as a candidate
+//     (reference src/search.rs:1320-1335 "all minima" branch,
+//      src/pattern_tiling/search.rs:389-407).
+// How it computes it is NOT the reference's layout: the bit-vector runs along
+// the pattern in W 32-bit words (Myers'99 / Hyyro'01 recurrences), the pattern
+// sits in the TOP m bits of the 32*W-bit vector and the unused low rows are
+// wildcards with vertical delta 0, so the score delta is always bit 31 of the
+// top word and never needs a per-pattern shift.  The text is cut into rows of
+// `ltot` bytes (one thread per row, cold start + (m+k)-byte warm-up from the
+// neighbouring row), an idea shared with the reference's lane chunking
+// (src/search.rs:1018-1049) but at 10^5-way width.
+#pragma once
+#include <stdint.h>
+
+#include "profile.h"
+
+namespace sb {
+
+// Characters per score check.  The score can change by at most 1 per text
+// character, so if the score after a group of kGroup characters is above
+// k + kGroup - 1 no position inside the group can be <= k.
+constexpr int kGroup = 4;
+// Bytes per thread per pipeline stage (one 128-byte line).
+constexpr int kStageBytes = 128;
+
+// Geometry of one scan: the text is viewed as `rows` rows of `ltot` bytes.
+struct ScanGeom {
+  uint32_t ltot;    // bytes per row, multiple of kStageBytes
+  uint32_t rows;    // ceil(n / ltot)
+  uint32_t nstage;  // ltot / kStageBytes
+  uint32_t nwarm;   // warm-up stages taken from the neighbouring row: ceil((m+k)/kStageBytes)
+};
+
+// Everything that is uniform over one scan launch.
+struct ScanArgs {
+  const uint8_t* text;  // padded device text (used by the non-TMA variant and the emulator)
+  uint64_t n;           // text length in bytes
+  uint64_t reset_idx;   // forward index at which the scan state restarts (0 fwd, n-1 rev)
+  ScanGeom g;
+  uint32_t sh0;   // text byte -> equality row: row = (byte >> sh0) & msk0 (applied to 4 packed bytes)
+  uint32_t msk0;
+  uint32_t nrows;  // equality rows per query (4 Dna, 32 Iupac, 256 Ascii)
+  uint32_t rowbytes;  // W * 4
+  int32_t m;       // pattern length
+  int32_t k;       // threshold
+  uint32_t nq;       // queries in this launch
+  uint32_t qs_base;  // query slot of the first query (strand * n_patterns + pattern)
+  const uint32_t* eq;  // [nq][nrows][W] equality words
+  uint64_t* cand_keys;
+  uint32_t* cand_cost;
+  unsigned long long* cand_count;
+  uint64_t cand_cap;
+};
+
+template <int W>
+struct Lane {
+  uint32_t pv[W];  // vertical +1 deltas of the current column (rows = bits, wildcard rows are 0)
+  uint32_t mv[W];  // vertical -1 deltas
+};
+
+SB_HD int popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+
+template <int W>
+SB_HD void lane_reset(Lane<W>& s, int m) {
+  const int pad = 32 * W - m;  // wildcard rows below the pattern
+#pragma unroll
+  for (int w = 0; w < W; w++) {
+    const int lo = pad - 32 * w;  // first pattern bit inside word w
+    s.pv[w] = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
+    s.mv[w] = 0;
+  }
+}
+
+// D[m][i] of the current column = sum of the vertical deltas (D[0][i] = 0).
+// POPC runs on its own pipe, so checking the score once per kGroup characters
+// costs the saturated ALU pipe one add and one compare.
+template <int W>
+SB_HD int lane_score(const Lane<W>& s) {
+  int v = 0;
+#pragma unroll
+  for (int w = 0; w < W; w++) v += popc32(s.pv[w]) - popc32(s.mv[w]);
+  return v;
+}
+
+// Candidate keys: (query slot << 40) | end position.  Sorting the 64-bit keys
+// orders candidates by query slot, then by end position.
+constexpr int kPosBits = 40;
+SB_HD uint64_t cand_key(uint32_t qs, uint64_t pos) { return ((uint64_t)qs << kPosBits) | pos; }
+SB_HD uint32_t key_qs(uint64_t key) { return (uint32_t)(key >> kPosBits); }
+SB_HD uint64_t key_pos(uint64_t key) { return key & ((1ull << kPosBits) - 1); }
+
+SB_HD void emit_candidate(const ScanArgs& a, uint32_t qs, uint64_t pos, int score) {
+#if defined(__CUDA_ARCH__)
+  const unsigned long long i = atomicAdd(a.cand_count, 1ull);
+#else
+  const unsigned long long i = (*a.cand_count)++;
+#endif
+  if (i < a.cand_cap) {
+    a.cand_keys[i] = cand_key(qs, pos);
+    a.cand_cost[i] = (uint32_t)score;
+  }
+}
+
+// One text character.  eq[w]: bit set where the pattern row matches the
+// character (all ones on the wildcard rows).  Hyyro's formulation of Myers'
+// recurrences with zero horizontal input at row 0 (top row of D is 0).
+// On sm_100a this compiles to 7 LOP3 (ALU pipe) + 3 IMAD (add and the two
+// shifts, FMA pipe) per word.
+template <int W>
+SB_HD void myers_step(Lane<W>& s, const uint32_t* __restrict__ eq) {
+  uint32_t carry = 0, phc = 0, mhc = 0;
+#pragma unroll
+  for (int w = 0; w < W; w++) {
+    const uint32_t pv = s.pv[w], mv = s.mv[w];
+    const uint32_t x = eq[w] | mv;
+    const uint32_t t = x & pv;
+    uint32_t u;
+    if (W == 1) {
+      u = t + pv;
+    } else {
+      const uint64_t sum = (uint64_t)t + pv + carry;
+      u = (uint32_t)sum;
+      carry = (uint32_t)(sum >> 32);
+    }
+    const uint32_t d0 = (u ^ pv) | x;
+    const uint32_t ph = mv | ~(d0 | pv);
+    const uint32_t mh = pv & d0;
+    const uint32_t ph1 = (ph << 1) | phc;
+    const uint32_t mh1 = (mh << 1) | mhc;
+    if (W > 1) {
+      phc = ph >> 31;
+      mhc = mh >> 31;
+    }
+    s.pv[w] = mh1 | ~(d0 | ph1);
+    s.mv[w] = ph1 & d0;
+  }
+}
+
+// A query's equality table [nrows][W].  On the device it lives in shared
+// memory and is addressed by its 32-bit shared-window address.
+struct EqTab {
+  const uint32_t* p;
+  uint32_t saddr;     // device only: shared-window address of p
+  uint32_t rowbytes;  // W * 4, kept in a register so the row offset is an IMAD, not a shift/LEA
+};
+
+// Equality words of the text byte in lane b (0..3) of `pre` (4 packed row
+// indices).  Device: PRMT (ALU pipe) extracts the row, IMAD (FMA pipe) forms
+// the address, LDS fetches; the ALU pipe - the bottleneck of this kernel -
+// spends one instruction per character here.
+template <int W>
+SB_HD void load_eq(uint32_t (&eq)[W], const EqTab& t, uint32_t pre, int b) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t row = __byte_perm(pre, 0u, 0x4440u + (uint32_t)b);
+  uint32_t addr;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(row), "r"(t.rowbytes), "r"(t.saddr));
+  if (W % 4 == 0) {
+#pragma unroll
+    for (int w = 0; w < W; w += 4)
+      asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+          : "=r"(eq[w]), "=r"(eq[w + 1]), "=r"(eq[w + 2]), "=r"(eq[w + 3])
+          : "r"(addr + 4 * w));
+  } else if (W % 2 == 0) {
+#pragma unroll
+    for (int w = 0; w < W; w += 2)
+      asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(eq[w]), "=r"(eq[w + 1]) : "r"(addr + 4 * w));
+  } else {
+#pragma unroll
+    for (int w = 0; w < W; w++) asm("ld.shared.u32 %0, [%1];" : "=r"(eq[w]) : "r"(addr + 4 * w));
+  }
+#else
+  const uint32_t row = (pre >> (8 * b)) & 0xFFu;
+  const uint32_t* p = t.p + row * W;
+  for (int w = 0; w < W; w++) eq[w] = p[w];
+#endif
+}
+
+#if defined(__CUDACC__)
+#define SB_SLOW __host__ __device__ __noinline__
+#else
+#define SB_SLOW
+#endif
+
+// Exact (per character) path: used for the rare groups that may contain a
+// position with score <= k, and for the chunk containing the restart index.
+// Deliberately not inlined and by-value, so that the hot path keeps the lane
+// in registers and stays small in the instruction cache.
+template <int W, bool REV>
+SB_SLOW Lane<W> slow_word(Lane<W> s, uint32_t x, uint64_t base_idx, const ScanArgs& a,
+                          EqTab eqs, uint32_t qs, bool own) {
+  const uint32_t pre = (x >> a.sh0) & a.msk0;
+  for (int bb = 0; bb < 4; bb++) {
+    const int b = REV ? 3 - bb : bb;
+    const uint64_t idx = base_idx + (uint64_t)b;
+    if (idx == a.reset_idx) lane_reset<W>(s, a.m);
+    uint32_t eq[W];
+    load_eq<W>(eq, eqs, pre, b);
+    myers_step<W>(s, eq);
+    const int score = lane_score<W>(s);
+    if (score <= a.k && own && idx < a.n) {
+      const uint64_t pos = REV ? a.n - idx : idx + 1;
+      emit_candidate(a, qs, pos, score);
+    }
+  }
+  return s;
+}
+
+template <int W, bool REV>
+SB_HD void fast_word(Lane<W>& s, uint32_t x, uint64_t base_idx, const ScanArgs& a,
+                     const EqTab& eqs, uint32_t qs, bool own) {
+  const uint32_t pre = (x >> a.sh0) & a.msk0;
+  const Lane<W> saved = s;
+#pragma unroll
+  for (int bb = 0; bb < 4; bb++) {
+    const int b = REV ? 3 - bb : bb;
+    uint32_t eq[W];
+    load_eq<W>(eq, eqs, pre, b);
+    myers_step<W>(s, eq);
+  }
+  // The score moves by at most 1 per character: if it is above k+kGroup-1 now,
+  // no position of the group was <= k.  Otherwise replay the group exactly.
+  if (lane_score<W>(s) <= a.k + (kGroup - 1)) {
+    s = slow_word<W, REV>(saved, x, base_idx, a, eqs, qs, own);
+  }
+}
+
+// 16 text bytes x[0..3] (little endian, x[0] byte 0 = forward index base_idx).
+// EXACT = every word through the per-character path (stage holding the restart index).
+template <int W, bool REV, bool EXACT>
+SB_HD void process16(Lane<W>& s, const uint32_t (&x)[4], uint64_t base_idx, const ScanArgs& a,
+                     const EqTab& eqs, uint32_t qs, bool own) {
+#pragma unroll
+  for (int ww = 0; ww < 4; ww++) {
+    const int w = REV ? 3 - ww : ww;
+    if (EXACT)
+      s = slow_word<W, REV>(s, x[w], base_idx + 4 * w, a, eqs, qs, own);
+    else
+      fast_word<W, REV>(s, x[w], base_idx + 4 * w, a, eqs, qs, own);
+  }
+}
+
+// True when the stage starting at forward index stage_idx holds the restart index.
+SB_HD bool stage_is_special(const ScanArgs& a, uint64_t stage_idx) {
+  return (a.reset_idx - stage_idx) < (uint64_t)kStageBytes;  // unsigned wrap-around intended
+}
+
+// Which 128-byte piece a thread reads in pipeline iteration `it`
+// (it < nwarm: warm-up from the neighbouring row; else own row).
+template <bool REV>
+SB_HD void stage_coord(const ScanGeom& g, uint32_t it, int64_t row, int64_t& r, uint32_t& col, bool& own) {
+  own = it >= g.nwarm;
+  if (!REV) {
+    if (!own) {
+      r = row - 1;
+      col = g.ltot - (g.nwarm - it) * kStageBytes;
+    } else {
+      r = row;
+      col = (it - g.nwarm) * kStageBytes;
+    }
+  } else {
+    if (!own) {
+      r = row + 1;
+      col = (g.nwarm - 1 - it) * kStageBytes;
+    } else {
+      r = row;
+      col = g.ltot - (it - g.nwarm + 1) * kStageBytes;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// Local-minima rule on the sorted candidate list (all positions with cost<=k).
+// A maximal run = same query slot, consecutive positions.  Candidate i is kept
+// iff the next step is up (or the run ends) and the last non-equal step before
+// it inside the run was down (or the run starts).  This is the reference's
+// streaming rule (src/search.rs:1344-1368) restricted to runs, identical to
+// src/pattern_tiling/minima.rs:9-52.
+SB_HD bool is_local_minimum(const uint64_t* keys, const uint32_t* cost, uint64_t i, uint64_t n) {
+  const uint64_t key = keys[i];
+  const uint32_t c = cost[i];
+  if (i + 1 < n && keys[i + 1] == key + 1 && cost[i + 1] <= c) return false;
+  uint64_t j = i;
+  uint64_t kk = key;
+  while (j > 0 && keys[j - 1] == kk - 1) {
+    j--;
+    kk--;
+    if (cost[j] != c) return cost[j] > c;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// Traceback of one match.  Window = the (m+k) text characters before the end
+// position, recomputed with the same recurrences while storing every column's
+// vertical deltas (reference src/search.rs:1477-1478, src/trace.rs:57-104;
+// column lookup as src/pattern_tiling/trace.rs:85-116), then the greedy walk
+// of src/trace.rs:314-388 ('=' > 'X' > 'D' (text only) > 'I' (pattern only)).
+struct TraceOut {
+  uint64_t text_start;  // in scan direction (reversed-text coordinates for REV queries)
+  uint64_t text_end;
+  int32_t cost;
+  uint32_t nops;
+  uint32_t failed;
+};
+
+// Device-side match record (scan-direction coordinates).
+struct GpuMatch {
+  uint64_t text_start;  // scan-direction coordinates
+  uint64_t text_end;
+  uint32_t qs;
+  int32_t cost;
+  uint32_t nops;
+  uint32_t failed;
+};
+
+enum : uint32_t { kOpEq = 0, kOpX = 1, kOpI = 2, kOpD = 3 };
+
+// Column store accessor: word w of column i for this match.
+struct ColStore {
+  uint32_t* base;
+  uint64_t stride;  // distance between consecutive (column, word) slots
+  SB_HD uint32_t& at(uint32_t slot) const { return base[(uint64_t)slot * stride]; }
+};
+
+template <int P>
+SB_HD int col_cost(const ColStore& cs, int W, int pad, int j, uint32_t i) {
+  // D[j][i]: column 0 is j; row 0 is 0; otherwise sum of vertical deltas of rows 1..j.
+  if (j == 0) return 0;
+  if (i == 0) return j;
+  int bits = pad + j;  // rows below `pad` are wildcards with delta 0
+  int v = 0;
+  for (int w = 0; w < W && bits > 0; w++) {
+    const uint32_t msk = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+    const uint32_t pv = cs.at((i * W + w) * 2), mv = cs.at((i * W + w) * 2 + 1);
+#if defined(__CUDA_ARCH__)
+    v += __popc(pv & msk) - __popc(mv & msk);
+#else
+    v += __builtin_popcount(pv & msk) - __builtin_popcount(mv & msk);
+#endif
+    bits -= 32;
+  }
+  return v;
+}
+
+SB_HD uint8_t text_at_dir(const uint8_t* text, uint64_t n, bool rev, uint64_t i) {
+  return rev ? text[n - 1 - i] : text[i];
+}
+
+// `ops` receives 2-bit op codes, 16 per word, in pattern direction.
+// `tmp` (W words * 2) is scratch for the running column.
+template <int P>
+SB_HD void trace_one(const uint8_t* text, uint64_t n, bool rev, const uint8_t* pattern, int m, int k,
+                     const uint32_t* eq /*[rows][W]*/, int W, uint32_t sh0, uint32_t msk0,
+                     uint64_t end, const ColStore& cs, uint32_t* ops, uint32_t ops_words, TraceOut& out) {
+  const int pad = 32 * W - m;
+  const uint64_t fill = (uint64_t)m + (uint64_t)k;
+  const uint64_t off = end > fill ? end - fill : 0;
+  const uint32_t wlen = (uint32_t)(end - off);
+  // column 0 state lives in slots [0, 2W); columns 1..wlen follow.
+  for (int w = 0; w < W; w++) {
+    const int lo = pad - 32 * w;
+    cs.at((0 * W + w) * 2) = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
+    cs.at((0 * W + w) * 2 + 1) = 0;
+  }
+  for (uint32_t i = 1; i <= wlen; i++) {
+    const uint8_t tc = text_at_dir(text, n, rev, off + i - 1);
+    const uint32_t row = ((uint32_t)tc >> sh0) & (msk0 & 0xFFu);
+    const uint32_t* e = eq + row * W;
+    uint32_t carry = 0, phc = 0, mhc = 0;
+    for (int w = 0; w < W; w++) {
+      const uint32_t pv = cs.at(((i - 1) * W + w) * 2), mv = cs.at(((i - 1) * W + w) * 2 + 1);
+      const uint32_t x = e[w] | mv;
+      const uint32_t t = x & pv;
+      const uint64_t sum = (uint64_t)t + pv + carry;
+      const uint32_t u = (uint32_t)sum;
+      carry = (uint32_t)(sum >> 32);
+      const uint32_t d0 = (u ^ pv) | x;
+      const uint32_t ph = mv | ~(d0 | pv);
+      const uint32_t mh = pv & d0;
+      const uint32_t ph1 = (ph << 1) | phc;
+      const uint32_t mh1 = (mh << 1) | mhc;
+      phc = ph >> 31;
+      mhc = mh >> 31;
+      cs.at((i * W + w) * 2) = mh1 | ~(d0 | ph1);
+      cs.at((i * W + w) * 2 + 1) = ph1 & d0;
+    }
+  }
+  for (uint32_t w = 0; w < ops_words; w++) ops[w] = 0;
+  int j = m;
+  uint32_t i = wlen;
+  int g = col_cost<P>(cs, W, pad, j, i);
+  out.cost = g;
+  out.failed = 0;
+  uint32_t nops = 0;
+  const uint32_t max_ops = ops_words * 16;
+  while (j > 0) {
+    uint32_t op;
+    if (i > 0 && col_cost<P>(cs, W, pad, j - 1, i - 1) == g &&
+        trace_match<P>(pattern[j - 1], text_at_dir(text, n, rev, off + i - 1))) {
+      op = kOpEq;
+      j--, i--;
+    } else {
+      g -= 1;
+      if (i > 0 && col_cost<P>(cs, W, pad, j - 1, i - 1) == g) {
+        op = kOpX;
+        j--, i--;
+      } else if (i > 0 && col_cost<P>(cs, W, pad, j, i - 1) == g) {
+        op = kOpD;
+        i--;
+      } else if (col_cost<P>(cs, W, pad, j - 1, i) == g) {
+        op = kOpI;
+        j--;
+      } else {
+        out.failed = 1;  // the reference panics with "Trace failed" (src/trace.rs:367-387)
+        break;
+      }
+    }
+    if (nops < max_ops) ops[nops >> 4] |= op << ((nops & 15) * 2);
+    nops++;
+  }
+  if (nops > max_ops) {
+    out.failed = 1;
+    nops = max_ops;
+  }
+  // reverse into pattern direction (src/trace.rs:393)
+  for (uint32_t a = 0, b = nops; a + 1 < b; a++, b--) {
+    const uint32_t oa = (ops[a >> 4] >> ((a & 15) * 2)) & 3u;
+    const uint32_t ob = (ops[(b - 1) >> 4] >> (((b - 1) & 15) * 2)) & 3u;
+    ops[a >> 4] = (ops[a >> 4] & ~(3u << ((a & 15) * 2))) | (ob << ((a & 15) * 2));
+    ops[(b - 1) >> 4] = (ops[(b - 1) >> 4] & ~(3u << (((b - 1) & 15) * 2))) | (oa << (((b - 1) & 15) * 2));
+  }
+  out.text_start = off + i;
+  out.text_end = end;
+  out.nops = nops;
+}
+
+}  // namespace sb

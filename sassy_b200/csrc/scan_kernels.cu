@@ -1,0 +1,261 @@
+// The scan kernel: one thread per text row, one block per (row tile, query).
+//
+// Data movement (B200): the text is a 2-D tensor [rows][ltot] of bytes in HBM.
+// Each pipeline stage one elected thread issues a single TMA tiled copy
+// (cp.async.bulk.tensor.2d, SASS UTMALDG) of a box [kScanThreads rows][128 B]
+// into shared memory with the 128-byte swizzle, completion signalled on an
+// mbarrier.  Thread t then reads its own 128-byte row with eight conflict-free
+// LDS.128 (chunk c lives at c ^ (t & 7)).  No thread ever issues a global load
+// for text in this variant; the LDG variant (per-thread 16-byte loads, no
+// staging) exists as an A/B baseline and as a safety net.
+//
+// Compute: see scan_core.cuh.  Integer/logic only; no tensor cores.
+#include "kernels.cuh"
+
+namespace sb {
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) __trap();  // a lost TMA must fail loudly, not hang the GPU
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int32_t x, int32_t y,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
+constexpr int kStageBufBytes = kScanThreads * kStageBytes;
+
+template <int W>
+constexpr int min_blocks() {
+  return W <= 2 ? 3 : (W <= 4 ? 2 : 1);
+}
+
+template <int W, bool REV, int VARIANT>
+__global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
+    scan_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kScanStages];
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t q = blockIdx.x % a.nq;  // queries vary fastest: blocks sharing a text tile are co-resident (L2 reuse)
+  const uint32_t tile = blockIdx.x / a.nq;
+  const int64_t row0 = (int64_t)tile * kScanThreads;
+  const int64_t row = row0 + tid;
+  const uint32_t qs = a.qs_base + q;
+
+  // shared memory carve-up: [text ring, 1024-aligned (TMA variant only)] [equality table]
+  uint8_t* ring = smem_raw;
+  uint32_t* eqs;
+  if (VARIANT == kVariantTma) {
+    const uint32_t base = smem_u32(smem_raw);
+    ring = smem_raw + (((base + 1023u) & ~1023u) - base);
+    eqs = reinterpret_cast<uint32_t*>(ring + kScanStages * kStageBufBytes);
+  } else {
+    eqs = reinterpret_cast<uint32_t*>(smem_raw);
+  }
+  {
+    const uint32_t words = a.nrows * W;
+    const uint32_t* src = a.eq + (size_t)q * words;
+    for (uint32_t i = tid; i < words; i += kScanThreads) eqs[i] = src[i];
+  }
+
+  EqTab eqt;
+  eqt.p = eqs;
+  eqt.saddr = smem_u32(eqs);
+  eqt.rowbytes = a.rowbytes;
+
+  const uint32_t total = a.g.nwarm + a.g.nstage;
+
+  auto issue = [&](uint32_t it) {
+    int64_t r;
+    uint32_t col;
+    bool own;
+    stage_coord<REV>(a.g, it, row0, r, col, own);
+    uint64_t* bar = &full_bar[it % kScanStages];
+    mbar_expect_tx(bar, kStageBufBytes);
+    tma_load_2d(ring + (it % kScanStages) * kStageBufBytes, &tmap, (int32_t)col, (int32_t)r, bar);
+  };
+
+  if (VARIANT == kVariantTma) {
+    if (tid == 0) {
+      for (int s = 0; s < kScanStages; s++) mbar_init(&full_bar[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  if (VARIANT == kVariantTma) {
+    if (tid == 0) {
+      for (uint32_t it = 0; it < (uint32_t)kScanStages && it < total; it++) issue(it);
+    }
+  }
+
+  Lane<W> s;
+  lane_reset<W>(s, a.m);
+
+  for (uint32_t it = 0; it < total; ++it) {
+    int64_t r;
+    uint32_t col;
+    bool own;
+    stage_coord<REV>(a.g, it, row, r, col, own);
+    const uint64_t stage_idx = (uint64_t)(r * (int64_t)a.g.ltot + (int64_t)col);
+    const bool special = stage_is_special(a, stage_idx);
+    if (VARIANT == kVariantTma) {
+      const uint32_t st = it % kScanStages;
+      mbar_wait(&full_bar[st], (it / kScanStages) & 1u);
+      const uint8_t* buf = ring + st * kStageBufBytes + tid * kStageBytes;
+      if (!special) {
+#pragma unroll(W <= 2 ? 8 : 1)
+        for (int cc = 0; cc < kStageBytes / 16; cc++) {
+          const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
+          const uint4 v = *reinterpret_cast<const uint4*>(buf + ((c ^ (tid & 7)) << 4));
+          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+          process16<W, REV, false>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+        }
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < kStageBytes / 16; cc++) {
+          const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
+          const uint4 v = *reinterpret_cast<const uint4*>(buf + ((c ^ (tid & 7)) << 4));
+          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+          process16<W, REV, true>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+        }
+      }
+      __syncthreads();  // every thread is done with ring[st]
+      if (tid == 0 && it + kScanStages < total) issue(it + kScanStages);
+    } else {
+      const bool valid = r >= 0 && r < (int64_t)a.g.rows;
+      const uint4* src = reinterpret_cast<const uint4*>(a.text + (valid ? stage_idx : 0));
+      if (!special) {
+#pragma unroll(W <= 2 ? 8 : 1)
+        for (int cc = 0; cc < kStageBytes / 16; cc++) {
+          const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (valid) v = __ldg(src + c);
+          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+          process16<W, REV, false>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+        }
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < kStageBytes / 16; cc++) {
+          const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (valid) v = __ldg(src + c);
+          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+          process16<W, REV, true>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+        }
+      }
+    }
+  }
+}
+
+template <int W, bool REV, int VARIANT>
+cudaError_t launch_one(const CUtensorMap* tmap, const ScanArgs& a, size_t smem, cudaStream_t stream) {
+  auto kern = scan_kernel<W, REV, VARIANT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
+  const uint64_t blocks = tiles * a.nq;
+  if (blocks == 0) return cudaSuccess;
+  if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+  CUtensorMap dummy;
+  if (!tmap) {
+    memset(&dummy, 0, sizeof dummy);
+    tmap = &dummy;
+  }
+  kern<<<(unsigned)blocks, kScanThreads, smem, stream>>>(*tmap, a);
+  return cudaGetLastError();
+}
+
+template <int W, bool REV, int VARIANT>
+int occupancy_one(size_t smem) {
+  auto kern = scan_kernel<W, REV, VARIANT>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kScanThreads, smem) != cudaSuccess) return 1;
+  return nb > 0 ? nb : 1;
+}
+
+}  // namespace
+
+size_t scan_smem_bytes(int W, int variant, uint32_t nrows) {
+  size_t eq = (size_t)nrows * W * sizeof(uint32_t);
+  if (variant == kVariantTma) return 1024 + (size_t)kScanStages * kStageBufBytes + eq;
+  return eq;
+}
+
+#define SB_DISPATCH_W(W_, CALL)            \
+  switch (W_) {                            \
+    case 1: CALL(1); break;                \
+    case 2: CALL(2); break;                \
+    case 3: CALL(3); break;                \
+    case 4: CALL(4); break;                \
+    case 6: CALL(6); break;                \
+    case 8: CALL(8); break;                \
+    case 16: CALL(16); break;              \
+    case 32: CALL(32); break;              \
+    default: break;                        \
+  }
+
+cudaError_t launch_scan(int W, bool rev, int variant, const CUtensorMap* tmap, const ScanArgs& a,
+                        cudaStream_t stream) {
+  const size_t smem = scan_smem_bytes(W, variant, a.nrows);
+  cudaError_t e = cudaErrorInvalidValue;
+#define SB_CALL(WW)                                                                             \
+  if (variant == kVariantTma)                                                                   \
+    e = rev ? launch_one<WW, true, kVariantTma>(tmap, a, smem, stream)                          \
+            : launch_one<WW, false, kVariantTma>(tmap, a, smem, stream);                        \
+  else                                                                                          \
+    e = rev ? launch_one<WW, true, kVariantLdg>(tmap, a, smem, stream)                          \
+            : launch_one<WW, false, kVariantLdg>(tmap, a, smem, stream);
+  SB_DISPATCH_W(W, SB_CALL)
+#undef SB_CALL
+  return e;
+}
+
+int scan_blocks_per_sm(int W, bool rev, int variant, uint32_t nrows) {
+  const size_t smem = scan_smem_bytes(W, variant, nrows);
+  int nb = 1;
+#define SB_CALL(WW)                                                                    \
+  if (variant == kVariantTma)                                                          \
+    nb = rev ? occupancy_one<WW, true, kVariantTma>(smem) : occupancy_one<WW, false, kVariantTma>(smem); \
+  else                                                                                 \
+    nb = rev ? occupancy_one<WW, true, kVariantLdg>(smem) : occupancy_one<WW, false, kVariantLdg>(smem);
+  SB_DISPATCH_W(W, SB_CALL)
+#undef SB_CALL
+  return nb;
+}
+
+}  // namespace sb

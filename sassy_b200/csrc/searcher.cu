@@ -1,0 +1,434 @@
+#include "searcher.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/sassy_gpu.h"
+
+namespace sb {
+
+int parse_alphabet(const std::string& alphabet) {
+  std::string a = alphabet;
+  std::transform(a.begin(), a.end(), a.begin(), [](unsigned char c) { return (char)tolower(c); });
+  if (a == "dna") return kDna;
+  if (a == "iupac") return kIupac;
+  if (a == "ascii") return kAscii;
+  return -1;
+}
+
+std::string Match::cigar() const {
+  std::string out;
+  size_t i = 0;
+  while (i < ops.size()) {
+    size_t j = i;
+    while (j < ops.size() && ops[j] == ops[i]) j++;
+    out += std::to_string(j - i);
+    out += ops[i];
+    i = j;
+  }
+  return out;
+}
+
+Searcher::Searcher(const std::string& alphabet, bool rc, float alpha, int device) : rc_(rc) {
+  profile_ = parse_alphabet(alphabet);
+  if (profile_ < 0) throw std::invalid_argument("Unsupported alphabet: " + alphabet);
+  if (!isnan(alpha))
+    throw std::invalid_argument("overhang (alpha) is outside the GPU search path; pass NAN");
+  engine_.reset(new Engine(profile_, device));
+}
+
+// Reference: Iupac patterns must be valid IUPAC (src/profiles/iupac.rs:19-24 panics);
+// Dna and Ascii accept every byte (src/profiles/dna.rs:19-23, ascii.rs:70-72).
+void Searcher::validate_pattern(const uint8_t* p, size_t m) const {
+  if (profile_ == kIupac && !iupac_valid(p, m)) throw InvalidPattern("Pattern is not valid IUPAC");
+}
+
+static const char kOpChars[4] = {'=', 'X', 'I', 'D'};
+
+static void unpack_ops(const MatchSet& ms, size_t i, std::string& out) {
+  const GpuMatch& g = ms.m[i];
+  const uint32_t* w = &ms.ops[i * ms.ops_words];
+  out.resize(g.nops);
+  for (uint32_t a = 0; a < g.nops; a++) out[a] = kOpChars[(w[a >> 4] >> ((a & 15) * 2)) & 3u];
+}
+
+// v1 strands (reference src/search.rs:787-881): slot 0 = pattern on the text,
+// slot 1 = complement(pattern) on the reversed text; reversed-text coordinates
+// are mapped back (:859-877), the CIGAR is kept as produced (:874-876).
+std::vector<Match> Searcher::convert_v1(const MatchSet& ms, uint64_t n) const {
+  std::vector<Match> out(ms.m.size());
+  for (size_t i = 0; i < ms.m.size(); i++) {
+    const GpuMatch& g = ms.m[i];
+    if (g.failed) throw std::runtime_error("Trace failed (text contains bytes outside the profile's alphabet?)");
+    Match& mm = out[i];
+    mm.pattern_idx = 0;
+    mm.text_idx = 0;
+    mm.cost = g.cost;
+    mm.pattern_start = 0;
+    if (g.qs == 0) {
+      mm.strand = kFwd;
+      mm.text_start = g.text_start;
+      mm.text_end = g.text_end;
+    } else {
+      mm.strand = kRc;
+      mm.text_start = n - g.text_end;
+      mm.text_end = n - g.text_start;
+    }
+    unpack_ops(ms, i, mm.ops);
+  }
+  return out;
+}
+
+std::vector<Match> Searcher::search(const uint8_t* pattern, size_t m, const DeviceText& text, size_t k,
+                                    bool all_minima) {
+  if (m == 0) throw std::invalid_argument("empty pattern");
+  validate_pattern(pattern, m);
+  if (rc_ && profile_ == kAscii)
+    throw std::invalid_argument("reverse complement is not implemented for the Ascii profile");
+  std::vector<uint8_t> comp;
+  std::vector<Query> qs;
+  qs.push_back(Query{pattern, false});
+  if (rc_) {
+    comp.resize(m);
+    for (size_t i = 0; i < m; i++) comp[i] = complement_byte(profile_, pattern[i]);
+    qs.push_back(Query{comp.data(), true});
+  }
+  const int kk = (int)std::min<size_t>(k, 1u << 20);
+  engine_->search(text, qs, (int)m, kk, all_minima, /*include_pos0=*/true, ms_);
+  std::vector<Match> out = convert_v1(ms_, text.n);
+  for (auto& mm : out) mm.pattern_end = m;
+  return out;
+}
+
+std::vector<Match> Searcher::search(const uint8_t* pattern, size_t m, const uint8_t* text, size_t n, size_t k,
+                                    bool all_minima) {
+  if (m == 0) throw std::invalid_argument("empty pattern");
+  validate_pattern(pattern, m);
+  DeviceText* t = engine_->stage_text(text, n);
+  return search(pattern, m, *t, k, all_minima);
+}
+
+// Reference: TQueries::new (src/pattern_tiling/tqueries.rs:53-134): equal
+// lengths, reverse complements appended as queries n..2n when rc (:75-80, it
+// always uses the IUPAC complement table, tqueries.rs:2).
+EncodedPatterns Searcher::encode_patterns(const uint8_t* const* patterns, size_t n_patterns, size_t m) const {
+  if (m == 0) throw std::invalid_argument("empty pattern");
+  if (m > 32 * kMaxWords) throw std::invalid_argument("pattern longer than 1024 characters");
+  EncodedPatterns e;
+  e.n_patterns = n_patterns;
+  e.m = (int)m;
+  e.rc = rc_;
+  e.bytes.resize(e.n_queries() * m);
+  for (size_t q = 0; q < n_patterns; q++) {
+    validate_pattern(patterns[q], m);
+    memcpy(&e.bytes[q * m], patterns[q], m);
+    if (rc_) {
+      uint8_t* dst = &e.bytes[(n_patterns + q) * m];
+      for (size_t i = 0; i < m; i++) dst[i] = complement_byte(kIupac, patterns[q][m - 1 - i]);
+    }
+  }
+  return e;
+}
+
+// Reference: search_with_options -> search_ranges + trace_batch_ranges
+// (src/pattern_tiling/general.rs:369-404, trace.rs:262-452): every query is
+// searched forward; query index >= n_patterns means strand Rc with
+// pattern_idx = idx % n_patterns (trace.rs:444-449); coordinates and CIGAR are
+// in the direction of the searched query.
+std::vector<Match> Searcher::search_encoded(const EncodedPatterns& enc, const DeviceText& text, size_t k,
+                                            bool all_minima) {
+  std::vector<Query> qs(enc.n_queries());
+  for (size_t q = 0; q < qs.size(); q++) qs[q] = Query{&enc.bytes[q * enc.m], false};
+  const int kk = (int)std::min<size_t>(k, 1u << 20);
+  engine_->search(text, qs, enc.m, kk, all_minima, /*include_pos0=*/false, ms_);
+  std::vector<Match> out(ms_.m.size());
+  for (size_t i = 0; i < ms_.m.size(); i++) {
+    const GpuMatch& g = ms_.m[i];
+    if (g.failed) throw std::runtime_error("Trace failed (text contains bytes outside the profile's alphabet?)");
+    Match& mm = out[i];
+    mm.pattern_idx = g.qs % enc.n_patterns;
+    mm.strand = g.qs >= enc.n_patterns ? kRc : kFwd;
+    mm.text_start = g.text_start;
+    mm.text_end = g.text_end;
+    mm.pattern_start = 0;
+    mm.pattern_end = (uint64_t)enc.m;
+    mm.cost = g.cost;
+    unpack_ops(ms_, i, mm.ops);
+  }
+  return out;
+}
+
+std::vector<Match> Searcher::search_encoded(const EncodedPatterns& enc, const uint8_t* text, size_t n, size_t k,
+                                            bool all_minima) {
+  DeviceText* t = engine_->stage_text(text, n);
+  return search_encoded(enc, *t, k, all_minima);
+}
+
+}  // namespace sb
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+
+struct sassy_SearcherType {
+  sb::Searcher s;
+  sassy_SearcherType(const std::string& a, bool rc, float alpha, int dev) : s(a, rc, alpha, dev) {}
+};
+struct sassy_gpu_Text {
+  sb::DeviceText* t;
+};
+struct sassy_gpu_Patterns {
+  sb::EncodedPatterns e;
+};
+struct sassy_gpu_Result {
+  std::vector<sassy_gpu_Match> m;
+  std::string ops;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+[[noreturn]] void die(const char* what) {
+  // The reference panics across extern "C" (src/c.rs:57,68,74,98), which aborts the process.
+  fprintf(stderr, "sassy_b200: %s\n", what);
+  abort();
+}
+
+int default_device() {
+  const char* d = getenv("SASSY_B200_DEVICE");
+  return d ? atoi(d) : 0;
+}
+
+sassy_gpu_Result* to_result(const std::vector<sb::Match>& v) {
+  sassy_gpu_Result* r = new sassy_gpu_Result;
+  r->m.resize(v.size());
+  size_t total = 0;
+  for (auto& x : v) total += x.ops.size();
+  r->ops.reserve(total);
+  for (size_t i = 0; i < v.size(); i++) {
+    sassy_gpu_Match& o = r->m[i];
+    memset(&o, 0, sizeof o);
+    o.pattern_idx = v[i].pattern_idx;
+    o.text_idx = v[i].text_idx;
+    o.text_start = v[i].text_start;
+    o.text_end = v[i].text_end;
+    o.pattern_start = v[i].pattern_start;
+    o.pattern_end = v[i].pattern_end;
+    o.cost = v[i].cost;
+    o.strand = (uint8_t)v[i].strand;
+    o.ops_off = r->ops.size();
+    o.ops_len = (uint32_t)v[i].ops.size();
+    r->ops += v[i].ops;
+  }
+  return r;
+}
+
+template <class F>
+auto guarded(F&& f) -> decltype(f()) {
+  try {
+    g_last_error.clear();
+    return f();
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+  } catch (...) {
+    g_last_error = "unknown error";
+  }
+  return decltype(f())();
+}
+
+}  // namespace
+
+extern "C" {
+
+sassy_SearcherType* sassy_searcher(const char* alphabet, bool rc, float alpha) {
+  if (!alphabet) die("Alphabet pointer must not be null");
+  try {
+    return new sassy_SearcherType(alphabet, rc, alpha, default_device());
+  } catch (const std::exception& e) {
+    die(e.what());
+  }
+}
+
+void sassy_searcher_free(sassy_SearcherType* ptr) {
+  if (!ptr) die("Pointer to SearcherType must not be null");
+  delete ptr;
+}
+
+uintptr_t search(sassy_SearcherType* searcher, const uint8_t* pattern, uintptr_t pattern_len, const uint8_t* text,
+                 uintptr_t text_len, uintptr_t k, sassy_Match** out_matches) {
+  if (!searcher || !pattern || !text || !out_matches) die("Pointers in search() must not be null");
+  std::vector<sb::Match> v;
+  try {
+    v = searcher->s.search(pattern, pattern_len, text, text_len, k, /*all_minima=*/false);
+  } catch (const std::exception& e) {
+    die(e.what());
+  }
+  // len == capacity; non-null even for zero matches (reference src/c.rs:112-117,127).
+  sassy_Match* arr = static_cast<sassy_Match*>(malloc(std::max<size_t>(v.size(), 1) * sizeof(sassy_Match)));
+  if (!arr) die("out of memory");
+  for (size_t i = 0; i < v.size(); i++) {
+    memset(&arr[i], 0, sizeof(sassy_Match));
+    arr[i].text_start = v[i].text_start;
+    arr[i].text_end = v[i].text_end;
+    arr[i].pattern_start = v[i].pattern_start;
+    arr[i].pattern_end = v[i].pattern_end;
+    arr[i].cost = v[i].cost;
+    arr[i].strand = (uint8_t)v[i].strand;
+  }
+  *out_matches = arr;
+  return v.size();
+}
+
+void sassy_matches_free(sassy_Match* ptr, uintptr_t len) {
+  (void)len;
+  if (!ptr) die("Pointer to matches must not be null");
+  free(ptr);
+}
+
+// ---- extensions (include/sassy_gpu.h) --------------------------------------
+
+int sassy_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* sassy_gpu_last_error(void) { return g_last_error.c_str(); }
+
+sassy_SearcherType* sassy_gpu_searcher(const char* alphabet, bool rc, float alpha, int device) {
+  return guarded([&]() -> sassy_SearcherType* {
+    if (!alphabet) throw std::invalid_argument("Alphabet pointer must not be null");
+    return new sassy_SearcherType(alphabet, rc, alpha, device);
+  });
+}
+
+int sassy_gpu_set_variant(sassy_SearcherType* searcher, int variant) {
+  if (!searcher || (variant != sb::kVariantTma && variant != sb::kVariantLdg)) return 1;
+  searcher->s.engine().set_variant(variant);
+  return 0;
+}
+
+int sassy_gpu_stats(const sassy_SearcherType* searcher, sassy_gpu_Stats* out) {
+  if (!searcher || !out) return 1;
+  const sb::SearchStats& st = const_cast<sassy_SearcherType*>(searcher)->s.engine().stats();
+  memset(out, 0, sizeof *out);
+  out->scan_ms = st.scan_ms;
+  out->total_ms = st.total_ms;
+  out->scan_launches = st.scan_launches;
+  out->aux_launches = st.aux_launches;
+  out->candidates = st.candidates;
+  out->matches = st.matches;
+  out->row_bytes = st.ltot;
+  out->rows = st.rows;
+  out->words = st.words;
+  out->blocks_per_sm = st.blocks_per_sm;
+  out->retries = st.retries;
+  return 0;
+}
+
+void* sassy_gpu_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    g_last_error = "cudaHostAlloc failed";
+    return nullptr;
+  }
+  return p;
+}
+
+void sassy_gpu_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+sassy_gpu_Text* sassy_gpu_text_upload(sassy_SearcherType* searcher, const uint8_t* text, size_t text_len) {
+  return guarded([&]() -> sassy_gpu_Text* {
+    if (!searcher || (!text && text_len)) throw std::invalid_argument("null pointer");
+    return new sassy_gpu_Text{searcher->s.engine().upload_text(text, text_len)};
+  });
+}
+
+sassy_gpu_Text* sassy_gpu_text_from_device(sassy_SearcherType* searcher, const void* device_ptr, size_t text_len) {
+  return guarded([&]() -> sassy_gpu_Text* {
+    if (!searcher || (!device_ptr && text_len)) throw std::invalid_argument("null pointer");
+    return new sassy_gpu_Text{searcher->s.engine().adopt_device_text(device_ptr, text_len)};
+  });
+}
+
+size_t sassy_gpu_text_len(const sassy_gpu_Text* text) { return text ? (size_t)text->t->n : 0; }
+
+void sassy_gpu_text_free(sassy_SearcherType* searcher, sassy_gpu_Text* text) {
+  if (!searcher || !text) return;
+  searcher->s.engine().free_text(text->t);
+  delete text;
+}
+
+sassy_gpu_Result* sassy_gpu_search(sassy_SearcherType* searcher, const uint8_t* pattern, size_t pattern_len,
+                                   const uint8_t* text, size_t text_len, size_t k, int all) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !pattern || (!text && text_len)) throw std::invalid_argument("null pointer");
+    return to_result(searcher->s.search(pattern, pattern_len, text, text_len, k, all != 0));
+  });
+}
+
+sassy_gpu_Result* sassy_gpu_search_text(sassy_SearcherType* searcher, const uint8_t* pattern, size_t pattern_len,
+                                        const sassy_gpu_Text* text, size_t k, int all) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !pattern || !text) throw std::invalid_argument("null pointer");
+    return to_result(searcher->s.search(pattern, pattern_len, *text->t, k, all != 0));
+  });
+}
+
+sassy_gpu_Patterns* sassy_gpu_encode_patterns(sassy_SearcherType* searcher, const uint8_t* patterns,
+                                              size_t n_patterns, size_t pattern_len) {
+  return guarded([&]() -> sassy_gpu_Patterns* {
+    if (!searcher || (!patterns && n_patterns)) throw std::invalid_argument("null pointer");
+    std::vector<const uint8_t*> ptrs(n_patterns);
+    for (size_t i = 0; i < n_patterns; i++) ptrs[i] = patterns + i * pattern_len;
+    return new sassy_gpu_Patterns{searcher->s.encode_patterns(ptrs.data(), n_patterns, pattern_len)};
+  });
+}
+
+void sassy_gpu_patterns_free(sassy_gpu_Patterns* patterns) { delete patterns; }
+
+sassy_gpu_Result* sassy_gpu_search_encoded(sassy_SearcherType* searcher, const sassy_gpu_Patterns* patterns,
+                                           const sassy_gpu_Text* text, size_t k, int all) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !patterns || !text) throw std::invalid_argument("null pointer");
+    return to_result(searcher->s.search_encoded(patterns->e, *text->t, k, all != 0));
+  });
+}
+
+sassy_gpu_Result* sassy_gpu_search_encoded_host(sassy_SearcherType* searcher, const sassy_gpu_Patterns* patterns,
+                                                const uint8_t* text, size_t text_len, size_t k, int all) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !patterns || (!text && text_len)) throw std::invalid_argument("null pointer");
+    return to_result(searcher->s.search_encoded(patterns->e, text, text_len, k, all != 0));
+  });
+}
+
+size_t sassy_gpu_result_len(const sassy_gpu_Result* result) { return result ? result->m.size() : 0; }
+const sassy_gpu_Match* sassy_gpu_result_matches(const sassy_gpu_Result* result) {
+  return result ? result->m.data() : nullptr;
+}
+const char* sassy_gpu_result_ops(const sassy_gpu_Result* result) { return result ? result->ops.data() : nullptr; }
+
+size_t sassy_gpu_cigar(const sassy_gpu_Result* result, size_t i, char* buf, size_t cap) {
+  if (!result || i >= result->m.size()) return 0;
+  sb::Match tmp;
+  tmp.ops = result->ops.substr(result->m[i].ops_off, result->m[i].ops_len);
+  const std::string c = tmp.cigar();
+  if (buf && cap) {
+    const size_t nn = std::min(c.size(), cap - 1);
+    memcpy(buf, c.data(), nn);
+    buf[nn] = 0;
+  }
+  return c.size();
+}
+
+void sassy_gpu_result_free(sassy_gpu_Result* result) { delete result; }
+
+}  // extern "C"

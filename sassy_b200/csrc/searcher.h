@@ -1,0 +1,80 @@
+// C++ mirror of the reference's public search surface for this path
+// (reference src/search.rs: Searcher<P> :227-256, new/new_fwd/new_rc :364-371,
+//  search :510, search_all :685, encode_patterns :404, search_encoded_patterns
+//  :415, search_all_encoded_patterns :426; Match :35-62; Strand :116-119).
+// The reference's generic parameter P becomes a runtime profile id; everything
+// below L4 of the reference runs in CUDA (engine.h).
+#pragma once
+#include <stdint.h>
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace sb {
+
+enum Strand : uint8_t { kFwd = 0, kRc = 1 };
+
+struct Match {
+  uint64_t pattern_idx = 0;
+  uint64_t text_idx = 0;
+  uint64_t text_start = 0;
+  uint64_t text_end = 0;
+  uint64_t pattern_start = 0;
+  uint64_t pattern_end = 0;
+  int32_t cost = 0;
+  Strand strand = kFwd;
+  std::string ops;  // one char per op ('=', 'X', 'I', 'D') in pattern direction
+
+  std::string cigar() const;  // run-length "<cnt><op>" (pa_types::Cigar::to_string)
+};
+
+struct InvalidPattern : std::invalid_argument {
+  using std::invalid_argument::invalid_argument;
+};
+
+// Reference: EncodedPatterns (src/pattern_tiling/general.rs:133-150).
+struct EncodedPatterns {
+  size_t n_patterns = 0;  // originals
+  int m = 0;
+  bool rc = false;
+  std::vector<uint8_t> bytes;  // n_queries * m: originals, then reverse complements if rc
+  size_t n_queries() const { return rc ? 2 * n_patterns : n_patterns; }
+};
+
+class Searcher {
+ public:
+  // alphabet: "ascii" | "dna" | "iupac" (case-insensitive), reference src/c.rs:62-67.
+  Searcher(const std::string& alphabet, bool rc, float alpha, int device);
+
+  int profile() const { return profile_; }
+  bool rc() const { return rc_; }
+  Engine& engine() { return *engine_; }
+
+  // Searcher::search / search_all on a host text (copied to HBM for the call).
+  std::vector<Match> search(const uint8_t* pattern, size_t m, const uint8_t* text, size_t n, size_t k,
+                            bool all_minima);
+  // Same on a text already resident in HBM.
+  std::vector<Match> search(const uint8_t* pattern, size_t m, const DeviceText& text, size_t k, bool all_minima);
+
+  EncodedPatterns encode_patterns(const uint8_t* const* patterns, size_t n_patterns, size_t m) const;
+  std::vector<Match> search_encoded(const EncodedPatterns& enc, const DeviceText& text, size_t k, bool all_minima);
+  std::vector<Match> search_encoded(const EncodedPatterns& enc, const uint8_t* text, size_t n, size_t k,
+                                    bool all_minima);
+
+  void validate_pattern(const uint8_t* p, size_t m) const;
+
+ private:
+  std::vector<Match> convert_v1(const MatchSet& ms, uint64_t n) const;
+  int profile_;
+  bool rc_;
+  std::unique_ptr<Engine> engine_;
+  MatchSet ms_;
+};
+
+int parse_alphabet(const std::string& alphabet);  // -1 if unknown
+
+}  // namespace sb

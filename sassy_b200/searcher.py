@@ -1,0 +1,288 @@
+"""Python surface of the GPU search path, mirroring the reference's pyo3 module
+(`sassy.Searcher`, `sassy.Match`; reference src/python.rs:26-220) plus the Rust-only
+encoded-pattern API (src/search.rs:404-433).  All work is done by libsassy_b200.so."""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Iterable, List, Optional, Sequence, Union
+
+from . import _native
+
+
+def _rle(ops: str) -> str:
+    """pa_types::Cigar::to_string: `<cnt><op>` runs, count always printed (src/lib.rs:83,107)."""
+    out = []
+    i = 0
+    n = len(ops)
+    while i < n:
+        j = i
+        while j < n and ops[j] == ops[i]:
+            j += 1
+        out.append(f"{j - i}{ops[i]}")
+        i = j
+    return "".join(out)
+
+
+class Match:
+    """reference src/search.rs:35-62; getters as src/python.rs:155-220."""
+
+    __slots__ = ("pattern_idx", "text_idx", "text_start", "text_end", "pattern_start", "pattern_end",
+                 "cost", "strand", "_ops")
+
+    def __init__(self, pattern_idx, text_idx, text_start, text_end, pattern_start, pattern_end, cost, strand, ops):
+        self.pattern_idx = pattern_idx
+        self.text_idx = text_idx
+        self.text_start = text_start
+        self.text_end = text_end
+        self.pattern_start = pattern_start
+        self.pattern_end = pattern_end
+        self.cost = cost
+        self.strand = strand  # "+" / "-"
+        self._ops = ops
+
+    @property
+    def cigar(self) -> str:
+        return _rle(self._ops)
+
+    def _key(self):
+        return (self.pattern_idx, self.text_idx, self.text_start, self.text_end, self.pattern_start,
+                self.pattern_end, self.cost, self.strand, self._ops)
+
+    def __eq__(self, other):
+        return isinstance(other, Match) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __repr__(self):
+        return (f"<Match pattern_start={self.pattern_start} text_start={self.text_start} "
+                f"pattern_end={self.pattern_end} text_end={self.text_end} cost={self.cost} "
+                f"strand='{self.strand}' cigar='{self.cigar}'>")
+
+
+class DeviceText:
+    """A text resident in HBM (device analogue of the reference's CachedRev, src/search.rs:144-166)."""
+
+    def __init__(self, searcher: "Searcher", handle: int, n: int):
+        self._searcher = searcher
+        self._h = handle
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def free(self):
+        if self._h:
+            _native.load().sassy_gpu_text_free(self._searcher._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._searcher._h:
+                self.free()
+        except Exception:
+            pass
+
+
+class EncodedPatterns:
+    """reference src/pattern_tiling/general.rs:133-150."""
+
+    def __init__(self, handle: int, n_patterns: int, m: int):
+        self._h = handle
+        self.n_patterns = n_patterns
+        self.pattern_len = m
+
+    def __del__(self):
+        try:
+            if self._h:
+                _native.load().sassy_gpu_patterns_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def _as_buffer(b):
+    """Returns (address, length, keepalive) for bytes-like objects and (ptr, len) tuples."""
+    if isinstance(b, tuple):  # (host address, length), e.g. pinned memory from host_alloc()
+        return b[0], b[1], None
+    if isinstance(b, bytes):
+        return ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p).value or 0, len(b), b
+    mv = memoryview(b).cast("B")
+    if mv.readonly:
+        data = bytes(mv)
+        return ctypes.cast(ctypes.c_char_p(data), ctypes.c_void_p).value or 0, len(data), data
+    arr = (ctypes.c_uint8 * len(mv)).from_buffer(mv)
+    return ctypes.addressof(arr), len(mv), (arr, mv)
+
+
+class Searcher:
+    """`Searcher(alphabet, rc=True, alpha=None, max_n_frac=None)` as in src/python.rs:31-65.
+
+    `device` selects the CUDA device (default: env SASSY_B200_DEVICE or 0).  Overhang
+    (`alpha`) and `max_n_frac` filtering are outside the GPU path and raise."""
+
+    def __init__(self, alphabet: str, rc: bool = True, alpha: Optional[float] = None,
+                 max_n_frac: Optional[float] = None, device: Optional[int] = None):
+        import os
+        self._h = None
+        self._lib = _native.load()
+        a = alphabet.lower()
+        if a not in ("ascii", "dna", "iupac"):
+            raise ValueError(f"Unsupported alphabet: {alphabet}")  # src/python.rs:52-57
+        if a == "ascii":
+            rc = False  # src/python.rs:40-42
+        if alpha is not None:
+            raise NotImplementedError("overhang (alpha) is outside the GPU search path")
+        if max_n_frac is not None and max_n_frac < 1.0:
+            raise NotImplementedError("max_n_frac filtering is outside the GPU search path")
+        if device is None:
+            device = int(os.environ.get("SASSY_B200_DEVICE", "0"))
+        self.alphabet = a
+        self.rc = bool(rc)
+        self.device = device
+        h = self._lib.sassy_gpu_searcher(a.encode(), self.rc, math.nan, device)
+        if not h:
+            raise RuntimeError(_native.last_error())
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._lib.sassy_searcher_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------
+    def _collect(self, res) -> List[Match]:
+        if not res:
+            msg = _native.last_error()
+            if "IUPAC" in msg or "pattern" in msg.lower():
+                raise ValueError(msg)
+            raise RuntimeError(msg)
+        lib = self._lib
+        try:
+            n = lib.sassy_gpu_result_len(res)
+            ms = lib.sassy_gpu_result_matches(res)
+            ops_ptr = lib.sassy_gpu_result_ops(res)
+            out = []
+            for i in range(n):
+                m = ms[i]
+                ops = ctypes.string_at(ops_ptr + m.ops_off, m.ops_len).decode() if m.ops_len else ""
+                out.append(Match(m.pattern_idx, m.text_idx, m.text_start, m.text_end, m.pattern_start,
+                                 m.pattern_end, m.cost, "-" if m.strand else "+", ops))
+            return out
+        finally:
+            lib.sassy_gpu_result_free(res)
+
+    def set_variant(self, variant: str):
+        """'tma' (default) or 'ldg' -- scan kernel data path (A/B)."""
+        if self._lib.sassy_gpu_set_variant(self._h, {"tma": 0, "ldg": 1}[variant]) != 0:
+            raise ValueError(variant)
+
+    def stats(self) -> dict:
+        st = _native.GpuStats()
+        self._lib.sassy_gpu_stats(self._h, ctypes.byref(st))
+        return {f: getattr(st, f) for f, _ in st._fields_ if not f.startswith("reserved")}
+
+    def upload_text(self, text) -> DeviceText:
+        addr, n, keep = _as_buffer(text)
+        h = self._lib.sassy_gpu_text_upload(self._h, addr, n)
+        if not h:
+            raise RuntimeError(_native.last_error())
+        return DeviceText(self, h, n)
+
+    def text_from_device(self, device_ptr: int, n: int) -> DeviceText:
+        h = self._lib.sassy_gpu_text_from_device(self._h, device_ptr, n)
+        if not h:
+            raise RuntimeError(_native.last_error())
+        return DeviceText(self, h, n)
+
+    # -- reference API ---------------------------------------------------
+    def _search(self, pattern, text, k: int, all_minima: bool) -> List[Match]:
+        paddr, plen, pkeep = _as_buffer(pattern)
+        if isinstance(text, DeviceText):
+            res = self._lib.sassy_gpu_search_text(self._h, paddr, plen, text._h, k, int(all_minima))
+        else:
+            taddr, tlen, tkeep = _as_buffer(text)
+            res = self._lib.sassy_gpu_search(self._h, paddr, plen, taddr, tlen, k, int(all_minima))
+        return self._collect(res)
+
+    def search(self, pattern, text, k: int) -> List[Match]:
+        """Searcher::search (src/search.rs:510-525; src/python.rs:67-81)."""
+        return self._search(pattern, text, k, False)
+
+    def search_all(self, pattern, text, k: int) -> List[Match]:
+        """Searcher::search_all (src/search.rs:685-700; src/python.rs:139-152)."""
+        return self._search(pattern, text, k, True)
+
+    def search_many(self, patterns: Sequence, texts: Sequence, k: int, threads: int = 1,
+                    mode: str = "single") -> List[Match]:
+        """Searcher::search_many (src/search.rs:531-603): every pattern against every text,
+        pattern_idx/text_idx filled in.  `threads` is accepted for signature compatibility; the
+        GPU processes one (pattern batch, text) at a time."""
+        if mode not in ("single", "batch_patterns", "batch_texts"):
+            raise ValueError("Unsupported search mode. Must be one of 'single', 'batch_patterns', or 'batch_texts'")
+        out: List[Match] = []
+        for ti, text in enumerate(texts):
+            dt = text if isinstance(text, DeviceText) else self.upload_text(text)
+            try:
+                for pi, pattern in enumerate(patterns):
+                    for m in self._search(pattern, dt, k, False):
+                        m.pattern_idx = pi
+                        m.text_idx = ti
+                        out.append(m)
+            finally:
+                if dt is not text:
+                    dt.free()
+        return out
+
+    def encode_patterns(self, patterns: Sequence[bytes]) -> EncodedPatterns:
+        """Searcher::encode_patterns (src/search.rs:404-413): equal-length patterns."""
+        if not patterns:
+            raise ValueError("no patterns")
+        m = len(patterns[0])
+        if any(len(p) != m for p in patterns):
+            raise ValueError("all patterns must have the same length")
+        blob = b"".join(bytes(p) for p in patterns)
+        h = self._lib.sassy_gpu_encode_patterns(self._h, ctypes.cast(ctypes.c_char_p(blob), ctypes.c_void_p),
+                                                len(patterns), m)
+        if not h:
+            raise ValueError(_native.last_error())
+        return EncodedPatterns(h, len(patterns), m)
+
+    def _search_encoded(self, enc: EncodedPatterns, text, k: int, all_minima: bool) -> List[Match]:
+        if isinstance(text, DeviceText):
+            res = self._lib.sassy_gpu_search_encoded(self._h, enc._h, text._h, k, int(all_minima))
+        else:
+            taddr, tlen, tkeep = _as_buffer(text)
+            res = self._lib.sassy_gpu_search_encoded_host(self._h, enc._h, taddr, tlen, k, int(all_minima))
+        return self._collect(res)
+
+    def search_encoded_patterns(self, enc: EncodedPatterns, text, k: int) -> List[Match]:
+        """Searcher::search_encoded_patterns (src/search.rs:415-423)."""
+        return self._search_encoded(enc, text, k, False)
+
+    def search_all_encoded_patterns(self, enc: EncodedPatterns, text, k: int) -> List[Match]:
+        """Searcher::search_all_encoded_patterns (src/search.rs:426-433)."""
+        return self._search_encoded(enc, text, k, True)
+
+
+def host_alloc(nbytes: int) -> int:
+    """Pinned host memory (address) for texts passed as (address, length) tuples."""
+    p = _native.load().sassy_gpu_host_alloc(nbytes)
+    if not p:
+        raise MemoryError(_native.last_error())
+    return p
+
+
+def host_free(addr: int):
+    _native.load().sassy_gpu_host_free(addr)
+
+
+def device_count() -> int:
+    return _native.load().sassy_gpu_device_count()

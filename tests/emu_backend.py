@@ -1,0 +1,115 @@
+"""Test-only backend: drives libsassy_b200_emu.so, the CPU emulation of the per-thread CUDA
+logic (sassy_b200/csrc/emu.cpp), and applies the same strand/coordinate mapping as
+sassy_b200/csrc/searcher.cu.  Lets the CPU-only suite check tiling / warm-up / minima /
+traceback logic against the oracle without a GPU."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence
+
+from oracle import Match, rle, complement, reverse_complement, OracleError
+import oracle as _oracle
+from sassy_b200 import build as _build
+
+PROFILE = {"dna": 0, "iupac": 1, "ascii": 2}
+OPS = "=XID"
+
+
+class _GpuMatch(ctypes.Structure):
+    _fields_ = [
+        ("text_start", ctypes.c_uint64),
+        ("text_end", ctypes.c_uint64),
+        ("qs", ctypes.c_uint32),
+        ("cost", ctypes.c_int32),
+        ("nops", ctypes.c_uint32),
+        ("failed", ctypes.c_uint32),
+    ]
+
+
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        lib = ctypes.CDLL(_build.build_emu())
+        lib.emu_search.restype = ctypes.c_void_p
+        lib.emu_search.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int,
+                                   ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_uint32, ctypes.c_int]
+        lib.emu_len.restype = ctypes.c_size_t
+        lib.emu_len.argtypes = [ctypes.c_void_p]
+        lib.emu_matches.restype = ctypes.POINTER(_GpuMatch)
+        lib.emu_matches.argtypes = [ctypes.c_void_p]
+        lib.emu_ops.restype = ctypes.POINTER(ctypes.c_uint32)
+        lib.emu_ops.argtypes = [ctypes.c_void_p]
+        lib.emu_ops_words.restype = ctypes.c_uint32
+        lib.emu_ops_words.argtypes = [ctypes.c_void_p]
+        lib.emu_candidates.restype = ctypes.c_uint64
+        lib.emu_candidates.argtypes = [ctypes.c_void_p]
+        lib.emu_ltot.restype = ctypes.c_uint32
+        lib.emu_ltot.argtypes = [ctypes.c_void_p]
+        lib.emu_rows.restype = ctypes.c_uint32
+        lib.emu_rows.argtypes = [ctypes.c_void_p]
+        lib.emu_free.argtypes = [ctypes.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+class EmuBackend:
+    def __init__(self, ltot: int = 0, bpw: int = 444):
+        self.ltot = ltot
+        self.bpw = bpw
+        self.last_geom = None
+
+    def _run(self, alphabet, queries: Sequence[bytes], rev: Sequence[int], text: bytes, k: int, all_minima: bool,
+             pos0: bool):
+        lib = _lib()
+        m = len(queries[0])
+        r = lib.emu_search(PROFILE[alphabet.lower()], b"".join(queries), bytes(rev), len(queries), m, text,
+                           len(text), k, int(all_minima), int(pos0), self.ltot, self.bpw)
+        assert r, "emu_search failed"
+        try:
+            n = lib.emu_len(r)
+            ms = lib.emu_matches(r)
+            ops = lib.emu_ops(r)
+            ow = lib.emu_ops_words(r)
+            self.last_geom = (lib.emu_ltot(r), lib.emu_rows(r))
+            out = []
+            for i in range(n):
+                g = ms[i]
+                if g.failed:
+                    raise OracleError("trace failed")
+                s = "".join(OPS[(ops[i * ow + (a >> 4)] >> ((a & 15) * 2)) & 3] for a in range(g.nops))
+                out.append((g.qs, g.text_start, g.text_end, g.cost, s))
+            return out
+        finally:
+            lib.emu_free(r)
+
+    def search(self, alphabet, pattern: bytes, text: bytes, k: int, rc: bool = False, all_minima: bool = False):
+        if alphabet.lower() == "iupac" and not _oracle._lib().oracle_iupac_valid(pattern, len(pattern)):
+            raise OracleError("Pattern is not valid IUPAC")
+        queries = [pattern]
+        rev = [0]
+        if rc:
+            queries.append(complement(alphabet, pattern))
+            rev.append(1)
+        n = len(text)
+        res = []
+        for qs, ts, te, cost, ops in self._run(alphabet, queries, rev, text, k, all_minima, True):
+            if qs == 0:
+                res.append(Match(0, ts, te, 0, len(pattern), cost, "+", rle(ops)))
+            else:
+                res.append(Match(0, n - te, n - ts, 0, len(pattern), cost, "-", rle(ops)))
+        return res
+
+    def search_encoded(self, alphabet, patterns: Sequence[bytes], text: bytes, k: int, rc: bool = False,
+                       all_minima: bool = False):
+        P = len(patterns)
+        queries = list(patterns)
+        if rc:
+            queries += [reverse_complement("iupac", p) for p in patterns]
+        res = []
+        for qs, ts, te, cost, ops in self._run(alphabet, queries, [0] * len(queries), text, k, all_minima, False):
+            res.append(Match(qs % P, ts, te, 0, len(patterns[0]), cost, "-" if qs >= P else "+", rle(ops)))
+        return res

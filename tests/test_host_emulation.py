@@ -1,0 +1,102 @@
+"""CPU-only checks of the logic the CUDA kernels execute (scan_core.cuh / host_logic.h),
+run through the host emulator and compared with the oracle: known-answer vectors, then a
+seeded differential fuzz across row lengths so that matches straddle row boundaries."""
+import random
+
+import pytest
+
+import oracle
+from tests import kat_util
+from tests.emu_backend import EmuBackend
+from tests.test_oracle_props import planted, rand_seq
+
+
+def key(m):
+    return (m.pattern_idx, m.text_start, m.text_end, m.cost, m.strand, m.cigar)
+
+
+@pytest.mark.parametrize("case", kat_util.load_cases(), ids=lambda c: c["source"][:60])
+def test_emu_kat(case):
+    kat_util.check(EmuBackend(), case)
+
+
+@pytest.mark.parametrize("case", kat_util.load_cases(), ids=lambda c: c["source"][:60])
+def test_emu_kat_short_rows(case):
+    kat_util.check(EmuBackend(ltot=128), case)
+
+
+@pytest.mark.parametrize("alphabet", ["dna", "iupac"])
+def test_emu_v1_fuzz(alphabet):
+    rng = random.Random(11)
+    for it in range(150):
+        m = rng.choice([1, 2, 5, 20, 23, 31, 32, 33, 40, 64, 65, 100, 130])
+        n = rng.randrange(0, 1500)
+        k = rng.randrange(0, max(1, m // 3) + 1)
+        p, t = planted(rng, m, max(n, 1), k)
+        t = t[:n]
+        if alphabet == "iupac" and rng.random() < 0.3:
+            t = bytes(c if rng.random() > 0.05 else ord(rng.choice("NRYSWKMBDHV")) for c in t)
+        if rng.random() < 0.15:  # homopolymer plateaus
+            t = b"A" * n
+            p = b"A" * m
+        ltot = rng.choice([0, 128, 256, 384])
+        for allm in (False, True):
+            want = oracle.search(alphabet, p, t, k, rc=True, all_minima=allm)
+            got = EmuBackend(ltot=ltot).search(alphabet, p, t, k, rc=True, all_minima=allm)
+            assert list(map(key, got)) == list(map(key, want)), (alphabet, p, t, k, allm, ltot)
+
+
+def test_emu_v2_fuzz():
+    rng = random.Random(12)
+    for it in range(80):
+        m = rng.choice([3, 8, 16, 23, 32, 33, 64])
+        n = rng.randrange(1, 1200)
+        k = rng.randrange(0, max(1, m // 4) + 1)
+        P = rng.randrange(1, 5)
+        pats = []
+        t = bytearray(rand_seq(rng, n))
+        for _ in range(P):
+            p, tt = planted(rng, m, n, k)
+            pats.append(p)
+            pos = rng.randrange(0, max(1, n - m))
+            t[pos:pos + m] = tt[pos:pos + m]
+        t = bytes(t[:n])
+        ltot = rng.choice([0, 128, 256])
+        for allm in (False, True):
+            want = oracle.search_encoded("iupac", pats, t, k, rc=True, all_minima=allm)
+            got = EmuBackend(ltot=ltot).search_encoded("iupac", pats, t, k, rc=True, all_minima=allm)
+            assert sorted(map(key, got)) == sorted(map(key, want)), (pats, t, k, allm, ltot)
+            assert list(map(key, got)) == list(map(key, want))  # same order: query slot, then end
+
+
+def test_emu_long_pattern_words():
+    # every supported word count, incl. the padded ones (W = 6, 8, 16, 32)
+    rng = random.Random(13)
+    for m in (150, 200, 260, 500, 1000):
+        n = 3000
+        k = 6
+        p, t = planted(rng, m, n, k)
+        want = oracle.search("dna", p, t, k, rc=True)
+        got = EmuBackend(ltot=rng.choice([0, 1152])).search("dna", p, t, k, rc=True)
+        assert list(map(key, got)) == list(map(key, want)), m
+        assert want, m
+
+
+def test_emu_k_ge_m_and_empty():
+    b = EmuBackend()
+    assert b.search("dna", b"ACG", b"", 1) == []
+    for k in (3, 5):
+        want = oracle.search("dna", b"ACG", b"TTACGTT", k, rc=True, all_minima=True)
+        got = b.search("dna", b"ACG", b"TTACGTT", k, rc=True, all_minima=True)
+        assert list(map(key, got)) == list(map(key, want))
+        want = oracle.search("dna", b"ACG", b"TTACGTT", k, rc=True)
+        got = b.search("dna", b"ACG", b"TTACGTT", k, rc=True)
+        assert list(map(key, got)) == list(map(key, want))
+
+
+def test_geometry_covers_text():
+    b = EmuBackend(bpw=444)
+    t = rand_seq(random.Random(5), 100000)
+    b.search("dna", b"ACGTACGTACGTACGTACGT", t, 2)
+    ltot, rows = b.last_geom
+    assert ltot % 128 == 0 and rows * ltot >= len(t) and (rows - 1) * ltot < len(t)
