@@ -18,7 +18,7 @@ from typing import List, Sequence
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-PROFILE = {"dna": 0, "iupac": 1}
+PROFILE = {"dna": 0, "iupac": 1, "ascii": 2}
 
 
 class _OracleMatch(ctypes.Structure):

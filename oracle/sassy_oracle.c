@@ -24,7 +24,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { PROFILE_DNA = 0, PROFILE_IUPAC = 1 };
+enum { PROFILE_DNA = 0, PROFILE_IUPAC = 1, PROFILE_ASCII = 2 };
 enum { MODE_LOCAL_MINIMA = 0, MODE_ALL = 1 };
 
 /* One reported match.  ops_off/ops_len index the op-string buffer (one char
@@ -94,11 +94,13 @@ static void init_tables(void) {
 
 /* Equality used by the *search* DP.
  * Dna: both sides reduced to (c>>1)&3 (src/profiles/dna.rs:19-23,26-45).
+ * Ascii: byte equality (the default case-sensitive Ascii<true>).
  * Iupac: pattern code (validated, <=15) AND low nibble of the text code; text
  *        bytes outside the table act as N (src/profiles/iupac.rs:68-128,
  *        319-330).                                                          */
 static inline int search_eq(int profile, uint8_t p, uint8_t t) {
   if (profile == PROFILE_DNA) return ((p >> 1) & 3) == ((t >> 1) & 3);
+  if (profile == PROFILE_ASCII) return p == t; /* src/profiles/ascii.rs:30-41,76-91 (case-sensitive) */
   return (IUPAC_CODE[p & 31] & (IUPAC_CODE[t & 31] & 0x0F)) != 0;
 }
 
@@ -107,6 +109,7 @@ static inline int search_eq(int profile, uint8_t p, uint8_t t) {
  * Iupac: code(a) & code(b) != 0         src/profiles/iupac.rs:136-138      */
 static inline int trace_eq(int profile, uint8_t p, uint8_t t) {
   if (profile == PROFILE_DNA) return (p | 0x20) == (t | 0x20);
+  if (profile == PROFILE_ASCII) return p == t; /* src/profiles/ascii.rs:44-51 */
   return (IUPAC_CODE[p & 31] & IUPAC_CODE[t & 31]) != 0;
 }
 

@@ -1,0 +1,190 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a B200."""
+import ctypes
+import math
+import random
+
+import pytest
+
+import oracle
+from tests import kat_util
+from tests.test_oracle_props import planted, rand_seq
+
+pytestmark = pytest.mark.gpu
+
+
+def key(m):
+    return (m.pattern_idx, m.text_start, m.text_end, m.cost, m.strand, m.cigar)
+
+
+@pytest.fixture(scope="module", params=["tma", "ldg"])
+def backend(request):
+    from tests.gpu_backend import GpuBackend
+    return GpuBackend(request.param)
+
+
+@pytest.fixture(scope="module")
+def tma():
+    from tests.gpu_backend import GpuBackend
+    return GpuBackend("tma")
+
+
+def test_native_library_is_loaded():
+    """The product path is the CUDA extension; there is nothing to fall back to."""
+    import sassy_b200
+    from sassy_b200 import _native
+    assert sassy_b200.device_count() >= 1
+    with open("/proc/self/maps") as f:
+        assert "libsassy_b200.so" in f.read()
+    assert _native.load().sassy_gpu_searcher is not None
+
+
+@pytest.mark.parametrize("case", kat_util.load_cases(), ids=lambda c: c["source"][:60])
+def test_gpu_kat(backend, case):
+    kat_util.check(backend, case)
+
+
+@pytest.mark.parametrize("alphabet", ["dna", "iupac"])
+def test_gpu_v1_fuzz(backend, alphabet):
+    rng = random.Random(21)
+    for it in range(120):
+        m = rng.choice([1, 2, 5, 20, 23, 31, 32, 33, 40, 64, 65, 100, 130])
+        n = rng.randrange(0, 20000)
+        k = rng.randrange(0, max(1, m // 3) + 1)
+        p, t = planted(rng, m, max(n, 1), k)
+        t = t[:n]
+        if alphabet == "iupac" and rng.random() < 0.3:
+            t = bytes(c if rng.random() > 0.05 else ord(rng.choice("NRYSWKMBDHV")) for c in t)
+        if rng.random() < 0.1:
+            t = b"A" * n
+            p = b"A" * m
+        for allm in (False, True):
+            want = oracle.search(alphabet, p, t, k, rc=True, all_minima=allm)
+            got = backend.search(alphabet, p, t, k, rc=True, all_minima=allm)
+            assert list(map(key, got)) == list(map(key, want)), (alphabet, p, t, k, allm)
+
+
+def test_gpu_v2_fuzz(backend):
+    rng = random.Random(22)
+    for it in range(60):
+        m = rng.choice([3, 8, 16, 23, 32, 33, 64])
+        n = rng.randrange(1, 20000)
+        k = rng.randrange(0, max(1, m // 4) + 1)
+        P = rng.randrange(1, 40)
+        pats = []
+        t = bytearray(rand_seq(rng, n))
+        for _ in range(P):
+            p, tt = planted(rng, m, n, k)
+            pats.append(p)
+            pos = rng.randrange(0, max(1, n - m))
+            t[pos:pos + m] = tt[pos:pos + m]
+        t = bytes(t[:n])
+        for allm in (False, True):
+            want = oracle.search_encoded("iupac", pats, t, k, rc=True, all_minima=allm)
+            got = backend.search_encoded("iupac", pats, t, k, rc=True, all_minima=allm)
+            assert list(map(key, got)) == list(map(key, want)), (pats, t, k, allm)
+
+
+def test_gpu_long_patterns(backend):
+    rng = random.Random(23)
+    for m in (150, 200, 260, 500, 1000):
+        n = 30000
+        k = 6
+        p, t = planted(rng, m, n, k)
+        want = oracle.search("dna", p, t, k, rc=True)
+        got = backend.search("dna", p, t, k, rc=True)
+        assert want and list(map(key, got)) == list(map(key, want)), m
+
+
+def test_gpu_ascii(tma):
+    import sassy_b200
+    s = sassy_b200.Searcher("ascii", rc=False)
+    text = b"the quick brown fox jumps over the lazy dog; the quack brown fax"
+    for k in (0, 2, 4):
+        for allm in (False, True):
+            want = oracle.search("ascii", b"quick brown fox", text, k, rc=False, all_minima=allm)
+            got = tma.search("ascii", b"quick brown fox", text, k, rc=False, all_minima=allm)
+            assert list(map(key, got)) == list(map(key, want))
+    ms = s.search(b"quick brown fox", text, 2)
+    assert [(m.text_start, m.text_end, m.cost, m.cigar) for m in ms] == [(4, 19, 0, "15="), (49, 64, 2, "2=1X10=1X1=")]
+    assert s.search(b"QUICK", text, 0) == []  # case-sensitive (reference Ascii<true>)
+
+
+def test_gpu_multi_megabyte_rows(tma):
+    """configs[0] shape (1 MB, m=20, k=1) and a 64 MB text: candidates at row boundaries."""
+    import sassy_b200
+    rng = random.Random(24)
+    s = sassy_b200.Searcher("dna", rc=True)
+    for n in (1 << 20, 1 << 24):
+        p = rand_seq(rng, 20)
+        table = bytes(b"ACGT"[c & 3] for c in range(256))
+        t = bytearray(rng.randbytes(n).translate(table))
+        # plant exact and 1-edit copies at every multiple of 128 +- a few, covering all row boundaries of any tiling
+        planted_at = []
+        for i in range(200):
+            pos = rng.randrange(0, n - 40)
+            if i % 2 == 0:
+                pos = (pos // 128) * 128 - rng.randrange(0, 24)
+                pos = max(pos, 0)
+            t[pos:pos + 20] = p
+            planted_at.append(pos)
+        t = bytes(t)
+        got = s.search(p, t, 1)
+        ends = {m.text_end for m in got if m.strand == "+" and m.cost == 0}
+        for pos in planted_at:
+            assert pos + 20 in ends, (n, pos)
+        if n == 1 << 20:
+            want = oracle.search("dna", p, t, 1, rc=True)
+            g = [(m.text_start, m.text_end, m.cost, m.strand, m.cigar) for m in got]
+            w = [(m.text_start, m.text_end, m.cost, m.strand, m.cigar) for m in want]
+            assert g == w
+
+
+def test_gpu_candidate_overflow_retry(tma):
+    """Dense candidates (every position matches) overflow the first buffer and trigger a re-scan."""
+    import sassy_b200
+    s = sassy_b200.Searcher("iupac", rc=False)
+    n = 3_000_000
+    t = b"N" * n
+    ms = s.search(b"ACGTACGT", t, 0)  # one plateau -> a single local minimum at the text end
+    assert [(m.text_start, m.text_end, m.cost) for m in ms] == [(n - 8, n, 0)]
+    assert s.stats()["retries"] >= 1 and s.stats()["candidates"] == n - 7
+
+
+def test_c_abi_search_symbol():
+    """The reference's own entry points (include/sassy.h), called as c/example.c does."""
+    from sassy_b200 import _native
+    lib = _native.load()
+    h = lib.sassy_searcher(b"dna", True, math.nan)
+    assert h
+    pattern = b"AAGGGGA"
+    text = b"CCCCCCCCCAAGGGGACCCCCAAGGCGACCCCCCCCC"
+    out = ctypes.POINTER(_native.CMatch)()
+    n = lib.search(h, pattern, len(pattern), text, len(text), 1, ctypes.byref(out))
+    got = [(out[i].text_start, out[i].text_end, out[i].pattern_start, out[i].pattern_end, out[i].cost,
+            out[i].strand) for i in range(n)]
+    want = [(m.text_start, m.text_end, m.pattern_start, m.pattern_end, m.cost, 1 if m.strand == "-" else 0)
+            for m in oracle.search("dna", pattern, text, 1, rc=True)]
+    assert got == want and n >= 2
+    assert ctypes.sizeof(_native.CMatch) == 40
+    lib.sassy_matches_free(out, n)
+    # zero matches: still a non-null pointer (reference src/c.rs:112-127)
+    n = lib.search(h, b"TTTTTTTT", 8, text, len(text), 0, ctypes.byref(out))
+    assert n == 0 and bool(out)
+    lib.sassy_matches_free(out, 0)
+    lib.sassy_searcher_free(h)
+
+
+def test_device_text_reuse(tma):
+    import sassy_b200
+    rng = random.Random(25)
+    s = sassy_b200.Searcher("iupac", rc=True)
+    p, t = planted(rng, 23, 50000, 3)
+    dt = s.upload_text(t)
+    a = s.search(p, dt, 3)
+    b = s.search(p, t, 3)
+    assert a == b and a
+    enc = s.encode_patterns([p, rand_seq(rng, 23)])
+    c = s.search_encoded_patterns(enc, dt, 3)
+    d = s.search_encoded_patterns(enc, t, 3)
+    assert c == d and c
+    dt.free()
