@@ -33,7 +33,7 @@ typedef struct sassy_gpu_Result sassy_gpu_Result;     /* Vec<Match> incl. CIGAR 
 
 /* One match; same fields as the reference's Match (src/search.rs:35-62).
  * The CIGAR ops of match i are the ops_len bytes at sassy_gpu_result_ops() + ops_off,
- * one char per op out of "=XID", in pattern direction. 64 bytes. */
+ * one char per op out of "=XID", in pattern direction. 72 bytes. */
 typedef struct sassy_gpu_Match {
   uint64_t pattern_idx;
   uint64_t text_idx;

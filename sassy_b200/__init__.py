@@ -2,7 +2,7 @@
 
 The compute path is libsassy_b200.so (CUDA, sm_100a); importing this package never
 falls back to a CPU implementation."""
-from .searcher import (DeviceText, EncodedPatterns, Match, Searcher, device_count, host_alloc,
+from .searcher import (DeviceText, EncodedPatterns, Match, MatchList, Searcher, device_count, host_alloc,
                        host_free)
 
-__all__ = ["Searcher", "Match", "DeviceText", "EncodedPatterns", "device_count", "host_alloc", "host_free"]
+__all__ = ["Searcher", "Match", "MatchList", "DeviceText", "EncodedPatterns", "device_count", "host_alloc", "host_free"]

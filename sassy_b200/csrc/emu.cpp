@@ -32,6 +32,7 @@ void scan_rows(const ScanArgs& a, const uint32_t* eq_q, uint32_t qs) {
   for (uint64_t row = 0; row < tiles * kScanThreads; row++) {  // includes the idle threads of the last tile
     Lane<W> s;
     lane_reset<W>(s, a.m);
+    int prev_score = a.m;
     for (uint32_t it = 0; it < total; it++) {
       int64_t r;
       uint32_t col;
@@ -45,9 +46,9 @@ void scan_rows(const ScanArgs& a, const uint32_t* eq_q, uint32_t qs) {
         uint32_t x[4] = {0, 0, 0, 0};
         if (valid) memcpy(x, a.text + stage_idx + 16u * c, 16);
         if (special)
-          process16<W, REV, true>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+          process16<W, REV, true>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
         else
-          process16<W, REV, false>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+          process16<W, REV, false>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
       }
     }
   }
@@ -99,7 +100,7 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
 
   ScanGeom g = choose_geom(n, m, k, nq, bpw > 0 ? bpw : 444);
   if (ltot_override) {
-    g.ltot = std::max<uint32_t>(ltot_override / kStageBytes * kStageBytes, g.nwarm * kStageBytes);
+    g.ltot = std::max<uint32_t>(ltot_override / kStageBytes * kStageBytes, g.nwarm * kStageBytes);  // any multiple of the stage size
     g.rows = (uint32_t)((n + g.ltot - 1) / g.ltot);
     g.nstage = g.ltot / kStageBytes;
   }

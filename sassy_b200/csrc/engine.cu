@@ -165,10 +165,10 @@ void Engine::make_tensor_map(CUtensorMap* map, const DeviceText& text, const Sca
   auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(encode_tiled_);
   const cuuint64_t dims[2] = {g.ltot, std::max<uint32_t>(g.rows, 1)};
   const cuuint64_t strides[1] = {g.ltot};
-  const cuuint32_t box[2] = {kStageBytes, kScanThreads};
+  const cuuint32_t box[2] = {kStageBytes, 32};  // one box per warp per stage
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, text.d, dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[128];

@@ -11,8 +11,9 @@
 
 namespace sb {
 
-constexpr int kScanThreads = 256;  // rows (threads) per block = TMA box height
+constexpr int kScanThreads = 128;  // rows (threads) per block; each warp has its own 32-row TMA box
 constexpr uint32_t kMaxRowBytes = 16384;
+constexpr uint32_t kRowAlign = 128;  // rows start on 128-byte lines
 constexpr int kMaxWords = 32;  // patterns up to 32*32 = 1024 characters
 
 // Supported word counts (kernel template instantiations).
@@ -69,7 +70,7 @@ inline ScanGeom choose_geom(uint64_t n, int m, int k, uint32_t nq, int bpw) {
   ScanGeom g;
   g.nwarm = (uint32_t)((m + k + kStageBytes - 1) / kStageBytes);
   if (g.nwarm == 0) g.nwarm = 1;
-  const uint64_t min_ltot = (uint64_t)g.nwarm * kStageBytes;
+  const uint64_t min_ltot = ((uint64_t)g.nwarm * kStageBytes + kRowAlign - 1) / kRowAlign * kRowAlign;
   const uint64_t per_tile_max = (uint64_t)kScanThreads * kMaxRowBytes;
   uint64_t tiles = std::max<uint64_t>(1, (n + per_tile_max - 1) / per_tile_max);
   const uint64_t fill = ((uint64_t)bpw + nq - 1) / nq;  // tiles needed to give every SM slot a block
@@ -80,7 +81,7 @@ inline ScanGeom choose_geom(uint64_t n, int m, int k, uint32_t nq, int bpw) {
     tiles = (blocks + nq - 1) / nq;
   }
   uint64_t ltot = (n + tiles * kScanThreads - 1) / (tiles * kScanThreads);
-  ltot = (ltot + kStageBytes - 1) / kStageBytes * kStageBytes;
+  ltot = (ltot + kRowAlign - 1) / kRowAlign * kRowAlign;
   ltot = std::max(ltot, min_ltot);
   ltot = std::min<uint64_t>(ltot, std::max<uint64_t>(kMaxRowBytes, min_ltot));
   g.ltot = (uint32_t)ltot;

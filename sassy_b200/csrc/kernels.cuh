@@ -10,7 +10,7 @@
 
 namespace sb {
 
-constexpr int kScanStages = 2;     // shared-memory ring depth (128 B per thread per stage)
+constexpr int kScanStages = 3;  // per-warp shared-memory ring depth (64 B per thread per stage)
 
 enum ScanVariant : int { kVariantTma = 0, kVariantLdg = 1 };
 

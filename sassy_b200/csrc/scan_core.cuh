@@ -27,8 +27,8 @@ namespace sb {
 // character, so if the score after a group of kGroup characters is above
 // k + kGroup - 1 no position inside the group can be <= k.
 constexpr int kGroup = 4;
-// Bytes per thread per pipeline stage (one 128-byte line).
-constexpr int kStageBytes = 128;
+// Bytes per thread per pipeline stage (half a 128-byte line).
+constexpr int kStageBytes = 64;
 
 // Geometry of one scan: the text is viewed as `rows` rows of `ltot` bytes.
 struct ScanGeom {
@@ -218,8 +218,13 @@ SB_SLOW Lane<W> slow_word(Lane<W> s, uint32_t x, uint64_t base_idx, const ScanAr
   return s;
 }
 
+// prev_score = score at the end of the previous group (the thread keeps it in a
+// register).  With s0 the score before a group of G characters and sG after it, a
+// position i in the group can only have score <= k if s0 - i <= k and sG - (G - i) <= k,
+// i.e. only if s0 + sG <= 2k + G.  Otherwise the group is skipped with one add and one
+// compare; else it is replayed exactly.
 template <int W, bool REV>
-SB_HD void fast_word(Lane<W>& s, uint32_t x, uint64_t base_idx, const ScanArgs& a,
+SB_HD void fast_word(Lane<W>& s, int& prev_score, uint32_t x, uint64_t base_idx, const ScanArgs& a,
                      const EqTab& eqs, uint32_t qs, bool own) {
   const uint32_t pre = (x >> a.sh0) & a.msk0;
   const Lane<W> saved = s;
@@ -230,25 +235,27 @@ SB_HD void fast_word(Lane<W>& s, uint32_t x, uint64_t base_idx, const ScanArgs& 
     load_eq<W>(eq, eqs, pre, b);
     myers_step<W>(s, eq);
   }
-  // The score moves by at most 1 per character: if it is above k+kGroup-1 now,
-  // no position of the group was <= k.  Otherwise replay the group exactly.
-  if (lane_score<W>(s) <= a.k + (kGroup - 1)) {
+  const int score = lane_score<W>(s);
+  if (prev_score + score <= 2 * a.k + kGroup) {
     s = slow_word<W, REV>(saved, x, base_idx, a, eqs, qs, own);
   }
+  prev_score = score;
 }
 
 // 16 text bytes x[0..3] (little endian, x[0] byte 0 = forward index base_idx).
 // EXACT = every word through the per-character path (stage holding the restart index).
 template <int W, bool REV, bool EXACT>
-SB_HD void process16(Lane<W>& s, const uint32_t (&x)[4], uint64_t base_idx, const ScanArgs& a,
+SB_HD void process16(Lane<W>& s, int& prev_score, const uint32_t (&x)[4], uint64_t base_idx, const ScanArgs& a,
                      const EqTab& eqs, uint32_t qs, bool own) {
 #pragma unroll
   for (int ww = 0; ww < 4; ww++) {
     const int w = REV ? 3 - ww : ww;
-    if (EXACT)
+    if (EXACT) {
       s = slow_word<W, REV>(s, x[w], base_idx + 4 * w, a, eqs, qs, own);
-    else
-      fast_word<W, REV>(s, x[w], base_idx + 4 * w, a, eqs, qs, own);
+      prev_score = lane_score<W>(s);
+    } else {
+      fast_word<W, REV>(s, prev_score, x[w], base_idx + 4 * w, a, eqs, qs, own);
+    }
   }
 }
 

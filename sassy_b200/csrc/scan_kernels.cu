@@ -1,12 +1,14 @@
 // The scan kernel: one thread per text row, one block per (row tile, query).
 //
 // Data movement (B200): the text is a 2-D tensor [rows][ltot] of bytes in HBM.
-// Each pipeline stage one elected thread issues a single TMA tiled copy
-// (cp.async.bulk.tensor.2d, SASS UTMALDG) of a box [kScanThreads rows][128 B]
-// into shared memory with the 128-byte swizzle, completion signalled on an
-// mbarrier.  Thread t then reads its own 128-byte row with eight conflict-free
-// LDS.128 (chunk c lives at c ^ (t & 7)).  No thread ever issues a global load
-// for text in this variant; the LDG variant (per-thread 16-byte loads, no
+// Every WARP owns a private ring of kScanStages shared-memory buffers and its
+// own mbarriers.  Per pipeline stage lane 0 issues one TMA tiled copy
+// (cp.async.bulk.tensor.2d, SASS UTMALDG) of a box [32 rows][64 B] with the
+// 64-byte swizzle; lane t then reads its own 64-byte row with four
+// conflict-free LDS.128 (16-byte chunk c of row t lives at c ^ ((t >> 1) & 3)).
+// Warps never wait for each other (no __syncthreads in the loop): a warp that
+// takes the rare exact path only delays itself.  No thread issues a global
+// load for text in this variant; the LDG variant (per-thread 16-byte loads, no
 // staging) exists as an A/B baseline and as a safety net.
 //
 // Compute: see scan_core.cuh.  Integer/logic only; no tensor cores.
@@ -55,33 +57,40 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
       : "memory");
 }
 
-constexpr int kStageBufBytes = kScanThreads * kStageBytes;
+constexpr int kWarpsPerBlock = kScanThreads / 32;
+constexpr int kWarpStageBytes = 32 * kStageBytes;                  // one TMA box
+constexpr int kWarpRingBytes = kScanStages * kWarpStageBytes;      // per warp
+constexpr int kRingBytes = kWarpsPerBlock * kWarpRingBytes;        // per block
+constexpr int kChunks = kStageBytes / 16;
 
 template <int W>
 constexpr int min_blocks() {
-  return W <= 2 ? 3 : (W <= 4 ? 2 : 1);
+  // registers: <=64 for 8 blocks of 128 threads (1024 threads/SM)
+  return W <= 2 ? 8 : (W <= 4 ? 6 : (W <= 8 ? 3 : 1));
 }
 
 template <int W, bool REV, int VARIANT>
 __global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
     scan_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[kScanStages];
+  __shared__ uint64_t full_bar[kWarpsPerBlock * kScanStages];
 
   const uint32_t tid = threadIdx.x;
+  const uint32_t warp = tid >> 5, lane = tid & 31;
   const uint32_t q = blockIdx.x % a.nq;  // queries vary fastest: blocks sharing a text tile are co-resident (L2 reuse)
   const uint32_t tile = blockIdx.x / a.nq;
-  const int64_t row0 = (int64_t)tile * kScanThreads;
-  const int64_t row = row0 + tid;
+  const int64_t row0 = (int64_t)tile * kScanThreads + 32 * warp;  // first row of this warp
+  const int64_t row = row0 + lane;
   const uint32_t qs = a.qs_base + q;
 
-  // shared memory carve-up: [text ring, 1024-aligned (TMA variant only)] [equality table]
+  // shared memory carve-up: [text rings, 1024-aligned (TMA variant only)] [equality table]
   uint8_t* ring = smem_raw;
   uint32_t* eqs;
   if (VARIANT == kVariantTma) {
     const uint32_t base = smem_u32(smem_raw);
     ring = smem_raw + (((base + 1023u) & ~1023u) - base);
-    eqs = reinterpret_cast<uint32_t*>(ring + kScanStages * kStageBufBytes);
+    eqs = reinterpret_cast<uint32_t*>(ring + kRingBytes);
+    ring += warp * kWarpRingBytes;
   } else {
     eqs = reinterpret_cast<uint32_t*>(smem_raw);
   }
@@ -90,40 +99,41 @@ __global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
     const uint32_t* src = a.eq + (size_t)q * words;
     for (uint32_t i = tid; i < words; i += kScanThreads) eqs[i] = src[i];
   }
-
   EqTab eqt;
   eqt.p = eqs;
   eqt.saddr = smem_u32(eqs);
   eqt.rowbytes = a.rowbytes;
 
   const uint32_t total = a.g.nwarm + a.g.nstage;
+  uint64_t* wbar = &full_bar[warp * kScanStages];
 
   auto issue = [&](uint32_t it) {
     int64_t r;
     uint32_t col;
     bool own;
     stage_coord<REV>(a.g, it, row0, r, col, own);
-    uint64_t* bar = &full_bar[it % kScanStages];
-    mbar_expect_tx(bar, kStageBufBytes);
-    tma_load_2d(ring + (it % kScanStages) * kStageBufBytes, &tmap, (int32_t)col, (int32_t)r, bar);
+    uint64_t* bar = &wbar[it % kScanStages];
+    mbar_expect_tx(bar, kWarpStageBytes);
+    tma_load_2d(ring + (it % kScanStages) * kWarpStageBytes, &tmap, (int32_t)col, (int32_t)r, bar);
   };
 
   if (VARIANT == kVariantTma) {
-    if (tid == 0) {
-      for (int s = 0; s < kScanStages; s++) mbar_init(&full_bar[s], 1);
+    if (lane == 0) {
+      for (int s = 0; s < kScanStages; s++) mbar_init(&wbar[s], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
   }
-  __syncthreads();
+  __syncthreads();  // equality table + barriers visible; the only block-wide sync
   if (VARIANT == kVariantTma) {
-    if (tid == 0) {
+    if (lane == 0) {
       for (uint32_t it = 0; it < (uint32_t)kScanStages && it < total; it++) issue(it);
     }
   }
 
   Lane<W> s;
   lane_reset<W>(s, a.m);
+  int prev_score = a.m;
 
   for (uint32_t it = 0; it < total; ++it) {
     int64_t r;
@@ -134,47 +144,48 @@ __global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
     const bool special = stage_is_special(a, stage_idx);
     if (VARIANT == kVariantTma) {
       const uint32_t st = it % kScanStages;
-      mbar_wait(&full_bar[st], (it / kScanStages) & 1u);
-      const uint8_t* buf = ring + st * kStageBufBytes + tid * kStageBytes;
+      mbar_wait(&wbar[st], (it / kScanStages) & 1u);
+      const uint8_t* buf = ring + st * kWarpStageBytes + lane * kStageBytes;
+      const uint32_t sw = (lane >> 1) & 3u;  // CU_TENSOR_MAP_SWIZZLE_64B: chunk ^= (row >> 1) & 3
       if (!special) {
-#pragma unroll(W <= 2 ? 8 : 1)
-        for (int cc = 0; cc < kStageBytes / 16; cc++) {
-          const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
-          const uint4 v = *reinterpret_cast<const uint4*>(buf + ((c ^ (tid & 7)) << 4));
+#pragma unroll(W <= 2 ? 2 : 1)
+        for (int cc = 0; cc < kChunks; cc++) {
+          const int c = REV ? (kChunks - 1 - cc) : cc;
+          const uint4 v = *reinterpret_cast<const uint4*>(buf + ((c ^ sw) << 4));
           const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-          process16<W, REV, false>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+          process16<W, REV, false>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
         }
       } else {
 #pragma unroll 1
-        for (int cc = 0; cc < kStageBytes / 16; cc++) {
-          const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
-          const uint4 v = *reinterpret_cast<const uint4*>(buf + ((c ^ (tid & 7)) << 4));
+        for (int cc = 0; cc < kChunks; cc++) {
+          const int c = REV ? (kChunks - 1 - cc) : cc;
+          const uint4 v = *reinterpret_cast<const uint4*>(buf + ((c ^ sw) << 4));
           const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-          process16<W, REV, true>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+          process16<W, REV, true>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
         }
       }
-      __syncthreads();  // every thread is done with ring[st]
-      if (tid == 0 && it + kScanStages < total) issue(it + kScanStages);
+      __syncwarp();  // every lane is done with this warp's ring[st]
+      if (lane == 0 && it + kScanStages < total) issue(it + kScanStages);
     } else {
       const bool valid = r >= 0 && r < (int64_t)a.g.rows;
       const uint4* src = reinterpret_cast<const uint4*>(a.text + (valid ? stage_idx : 0));
       if (!special) {
-#pragma unroll(W <= 2 ? 8 : 1)
-        for (int cc = 0; cc < kStageBytes / 16; cc++) {
-          const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
+#pragma unroll(W <= 2 ? 2 : 1)
+        for (int cc = 0; cc < kChunks; cc++) {
+          const int c = REV ? (kChunks - 1 - cc) : cc;
           uint4 v = make_uint4(0, 0, 0, 0);
           if (valid) v = __ldg(src + c);
           const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-          process16<W, REV, false>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+          process16<W, REV, false>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
         }
       } else {
 #pragma unroll 1
-        for (int cc = 0; cc < kStageBytes / 16; cc++) {
-          const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
+        for (int cc = 0; cc < kChunks; cc++) {
+          const int c = REV ? (kChunks - 1 - cc) : cc;
           uint4 v = make_uint4(0, 0, 0, 0);
           if (valid) v = __ldg(src + c);
           const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-          process16<W, REV, true>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+          process16<W, REV, true>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
         }
       }
     }
@@ -212,7 +223,7 @@ int occupancy_one(size_t smem) {
 
 size_t scan_smem_bytes(int W, int variant, uint32_t nrows) {
   size_t eq = (size_t)nrows * W * sizeof(uint32_t);
-  if (variant == kVariantTma) return 1024 + (size_t)kScanStages * kStageBufBytes + eq;
+  if (variant == kVariantTma) return 1024 + (size_t)kRingBytes + eq;
   return eq;
 }
 

@@ -3,11 +3,19 @@
 encoded-pattern API (src/search.rs:404-433).  All work is done by libsassy_b200.so."""
 from __future__ import annotations
 
+import collections.abc
 import ctypes
 import math
 from typing import Iterable, List, Optional, Sequence, Union
 
+import numpy as np
+
 from . import _native
+
+_REC_DTYPE = np.dtype([("pattern_idx", "<u8"), ("text_idx", "<u8"), ("text_start", "<u8"), ("text_end", "<u8"),
+                       ("pattern_start", "<u8"), ("pattern_end", "<u8"), ("cost", "<i4"), ("strand", "u1"),
+                       ("reserved", "u1", (3,)), ("ops_len", "<u4"), ("reserved2", "<u4"), ("ops_off", "<u8")])
+assert _REC_DTYPE.itemsize == ctypes.sizeof(_native.GpuMatch) == 72
 
 
 def _rle(ops: str) -> str:
@@ -59,6 +67,48 @@ class Match:
         return (f"<Match pattern_start={self.pattern_start} text_start={self.text_start} "
                 f"pattern_end={self.pattern_end} text_end={self.text_end} cost={self.cost} "
                 f"strand='{self.strand}' cigar='{self.cigar}'>")
+
+
+class MatchList(collections.abc.Sequence):
+    """The Vec<Match> of one search: a lazy view over the native result records.
+
+    Behaves like a list of Match (len, indexing, iteration, ==); Match objects are only
+    materialised on access, so result sets with millions of matches cost one memcpy."""
+
+    def __init__(self, recs: "np.ndarray", ops: bytes):
+        self._recs = recs
+        self._ops = ops
+
+    def __len__(self):
+        return len(self._recs)
+
+    def _make(self, r) -> Match:
+        off = int(r["ops_off"])
+        return Match(int(r["pattern_idx"]), int(r["text_idx"]), int(r["text_start"]), int(r["text_end"]),
+                     int(r["pattern_start"]), int(r["pattern_end"]), int(r["cost"]), "-" if r["strand"] else "+",
+                     self._ops[off:off + int(r["ops_len"])].decode())
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._make(r) for r in self._recs[i]]
+        return self._make(self._recs[i])
+
+    def __iter__(self):
+        for r in self._recs:
+            yield self._make(r)
+
+    def __eq__(self, other):
+        if isinstance(other, (list, MatchList)):
+            return len(self) == len(other) and all(a == b for a, b in zip(self, other))
+        return NotImplemented
+
+    def __repr__(self):
+        return f"MatchList({list(self)!r})"
+
+    @property
+    def records(self) -> "np.ndarray":
+        """Structured array with the fields of sassy_gpu_Match (include/sassy_gpu.h)."""
+        return self._recs
 
 
 class DeviceText:
@@ -158,7 +208,7 @@ class Searcher:
             pass
 
     # -- helpers ---------------------------------------------------------
-    def _collect(self, res) -> List[Match]:
+    def _collect(self, res) -> "MatchList":
         if not res:
             msg = _native.last_error()
             if "IUPAC" in msg or "pattern" in msg.lower():
@@ -167,15 +217,14 @@ class Searcher:
         lib = self._lib
         try:
             n = lib.sassy_gpu_result_len(res)
+            if n == 0:
+                return MatchList(np.zeros(0, dtype=_REC_DTYPE), b"")
             ms = lib.sassy_gpu_result_matches(res)
+            recs = np.frombuffer(ctypes.string_at(ms, n * _REC_DTYPE.itemsize), dtype=_REC_DTYPE)
+            last = recs[-1]
             ops_ptr = lib.sassy_gpu_result_ops(res)
-            out = []
-            for i in range(n):
-                m = ms[i]
-                ops = ctypes.string_at(ops_ptr + m.ops_off, m.ops_len).decode() if m.ops_len else ""
-                out.append(Match(m.pattern_idx, m.text_idx, m.text_start, m.text_end, m.pattern_start,
-                                 m.pattern_end, m.cost, "-" if m.strand else "+", ops))
-            return out
+            ops = ctypes.string_at(ops_ptr, int(last["ops_off"]) + int(last["ops_len"])) if ops_ptr else b""
+            return MatchList(recs, ops)
         finally:
             lib.sassy_gpu_result_free(res)
 
