@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--text-bytes", type=int, default=0, help="override the text size (debug)")
+    ap.add_argument("--patterns", type=int, default=0, help="override the number of patterns (debug)")
     ap.add_argument("--variant", default="tma", choices=["tma", "ldg"])
     ap.add_argument("--rc", action="store_true", help="search both strands (default: forward only, as the reference's evals)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -252,6 +253,8 @@ def main():
     profile, n_patterns, m, k, n, desc = WORKLOADS[args.workload]
     if args.text_bytes:
         n = args.text_bytes
+    if args.patterns:
+        n_patterns = args.patterns
     pats = make_patterns(profile, n_patterns, m)
     copies = 64 if n_patterns == 1 else 2
 

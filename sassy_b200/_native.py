@@ -9,7 +9,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsassy_b200.so")
+# SASSY_B200_LIB selects another build of the same library (kernel tuning experiments).
+LIB_PATH = os.environ.get("SASSY_B200_LIB") or os.path.join(HERE, "lib", "libsassy_b200.so")
 
 c_size_t = ctypes.c_size_t
 c_void_p = ctypes.c_void_p

@@ -67,6 +67,17 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines) -> str:
+    """Kernel-tuning experiments: libsassy_b200_<name>.so compiled with extra -D flags
+    (select it at run time with SASSY_B200_LIB=<path>)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, f"libsassy_b200_{name}.so")
+    cmd = [NVCC] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-shared", "-o", out] + \
+        [os.path.join(CSRC, c) for c in CU_SOURCES]
+    subprocess.check_call(cmd)
+    return out
+
+
 def build_emu(force: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     src = os.path.join(CSRC, "emu.cpp")

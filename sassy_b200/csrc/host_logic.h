@@ -11,7 +11,10 @@
 
 namespace sb {
 
-constexpr int kScanThreads = 128;  // rows (threads) per block; each warp has its own 32-row TMA box
+#ifndef SB_THREADS
+#define SB_THREADS 128
+#endif
+constexpr int kScanThreads = SB_THREADS;  // rows (threads) per block; each warp has its own 32-row TMA box
 constexpr uint32_t kMaxRowBytes = 16384;
 constexpr uint32_t kRowAlign = 128;  // rows start on 128-byte lines
 constexpr int kMaxWords = 32;  // patterns up to 32*32 = 1024 characters

@@ -10,7 +10,10 @@
 
 namespace sb {
 
-constexpr int kScanStages = 3;  // per-warp shared-memory ring depth (64 B per thread per stage)
+#ifndef SB_STAGES
+#define SB_STAGES 3
+#endif
+constexpr int kScanStages = SB_STAGES;  // per-warp shared-memory ring depth (64 B per thread per stage)
 
 enum ScanVariant : int { kVariantTma = 0, kVariantLdg = 1 };
 

@@ -26,7 +26,10 @@ namespace sb {
 // Characters per score check.  The score can change by at most 1 per text
 // character, so if the score after a group of kGroup characters is above
 // k + kGroup - 1 no position inside the group can be <= k.
-constexpr int kGroup = 4;
+#ifndef SB_GROUP
+#define SB_GROUP 4
+#endif
+constexpr int kGroup = SB_GROUP;  // 4, 8 or 16 (whole 32-bit text words)
 // Bytes per thread per pipeline stage (half a 128-byte line).
 constexpr int kStageBytes = 64;
 
@@ -222,22 +225,32 @@ SB_SLOW Lane<W> slow_word(Lane<W> s, uint32_t x, uint64_t base_idx, const ScanAr
 // register).  With s0 the score before a group of G characters and sG after it, a
 // position i in the group can only have score <= k if s0 - i <= k and sG - (G - i) <= k,
 // i.e. only if s0 + sG <= 2k + G.  Otherwise the group is skipped with one add and one
-// compare; else it is replayed exactly.
+// compare; else it is replayed exactly.  xs = the kGroup/4 text words of the group in
+// forward order; base_idx = forward index of xs[0] byte 0.
 template <int W, bool REV>
-SB_HD void fast_word(Lane<W>& s, int& prev_score, uint32_t x, uint64_t base_idx, const ScanArgs& a,
-                     const EqTab& eqs, uint32_t qs, bool own) {
-  const uint32_t pre = (x >> a.sh0) & a.msk0;
+SB_HD void fast_group(Lane<W>& s, int& prev_score, const uint32_t* xs, uint64_t base_idx, const ScanArgs& a,
+                      const EqTab& eqs, uint32_t qs, bool own) {
+  constexpr int NW = kGroup / 4;
   const Lane<W> saved = s;
 #pragma unroll
-  for (int bb = 0; bb < 4; bb++) {
-    const int b = REV ? 3 - bb : bb;
-    uint32_t eq[W];
-    load_eq<W>(eq, eqs, pre, b);
-    myers_step<W>(s, eq);
+  for (int ww = 0; ww < NW; ww++) {
+    const int w = REV ? NW - 1 - ww : ww;
+    const uint32_t pre = (xs[w] >> a.sh0) & a.msk0;
+#pragma unroll
+    for (int bb = 0; bb < 4; bb++) {
+      const int b = REV ? 3 - bb : bb;
+      uint32_t eq[W];
+      load_eq<W>(eq, eqs, pre, b);
+      myers_step<W>(s, eq);
+    }
   }
   const int score = lane_score<W>(s);
   if (prev_score + score <= 2 * a.k + kGroup) {
-    s = slow_word<W, REV>(saved, x, base_idx, a, eqs, qs, own);
+    s = saved;
+    for (int ww = 0; ww < NW; ww++) {
+      const int w = REV ? NW - 1 - ww : ww;
+      s = slow_word<W, REV>(s, xs[w], base_idx + 4 * w, a, eqs, qs, own);
+    }
   }
   prev_score = score;
 }
@@ -247,15 +260,20 @@ SB_HD void fast_word(Lane<W>& s, int& prev_score, uint32_t x, uint64_t base_idx,
 template <int W, bool REV, bool EXACT>
 SB_HD void process16(Lane<W>& s, int& prev_score, const uint32_t (&x)[4], uint64_t base_idx, const ScanArgs& a,
                      const EqTab& eqs, uint32_t qs, bool own) {
-#pragma unroll
-  for (int ww = 0; ww < 4; ww++) {
-    const int w = REV ? 3 - ww : ww;
-    if (EXACT) {
+  if (EXACT) {
+    for (int ww = 0; ww < 4; ww++) {
+      const int w = REV ? 3 - ww : ww;
       s = slow_word<W, REV>(s, x[w], base_idx + 4 * w, a, eqs, qs, own);
-      prev_score = lane_score<W>(s);
-    } else {
-      fast_word<W, REV>(s, prev_score, x[w], base_idx + 4 * w, a, eqs, qs, own);
     }
+    prev_score = lane_score<W>(s);
+    return;
+  }
+  constexpr int NW = kGroup / 4;
+  constexpr int NG = 4 / NW;
+#pragma unroll
+  for (int gg = 0; gg < NG; gg++) {
+    const int g = REV ? NG - 1 - gg : gg;
+    fast_group<W, REV>(s, prev_score, &x[g * NW], base_idx + 4 * NW * g, a, eqs, qs, own);
   }
 }
 

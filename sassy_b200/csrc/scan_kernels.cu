@@ -14,6 +14,10 @@
 // Compute: see scan_core.cuh.  Integer/logic only; no tensor cores.
 #include "kernels.cuh"
 
+#ifndef SB_UNROLL
+#define SB_UNROLL 2
+#endif
+
 namespace sb {
 namespace {
 
@@ -62,11 +66,12 @@ constexpr int kWarpStageBytes = 32 * kStageBytes;                  // one TMA bo
 constexpr int kWarpRingBytes = kScanStages * kWarpStageBytes;      // per warp
 constexpr int kRingBytes = kWarpsPerBlock * kWarpRingBytes;        // per block
 constexpr int kChunks = kStageBytes / 16;
+constexpr int kUnroll = SB_UNROLL;  // 16-byte chunks unrolled per loop trip (narrow patterns)
 
 template <int W>
 constexpr int min_blocks() {
-  // registers: <=64 for 8 blocks of 128 threads (1024 threads/SM)
-  return W <= 2 ? 8 : (W <= 4 ? 6 : (W <= 8 ? 3 : 1));
+  // threads per SM: 1024 (<=64 registers) for W <= 2, 768 for W <= 4, 384 for W <= 8
+  return (W <= 2 ? 1024 : (W <= 4 ? 768 : (W <= 8 ? 384 : 128))) / kScanThreads;
 }
 
 template <int W, bool REV, int VARIANT>
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
       const uint8_t* buf = ring + st * kWarpStageBytes + lane * kStageBytes;
       const uint32_t sw = (lane >> 1) & 3u;  // CU_TENSOR_MAP_SWIZZLE_64B: chunk ^= (row >> 1) & 3
       if (!special) {
-#pragma unroll(W <= 2 ? 2 : 1)
+#pragma unroll(W <= 2 ? kUnroll : 1)
         for (int cc = 0; cc < kChunks; cc++) {
           const int c = REV ? (kChunks - 1 - cc) : cc;
           const uint4 v = *reinterpret_cast<const uint4*>(buf + ((c ^ sw) << 4));
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
       const bool valid = r >= 0 && r < (int64_t)a.g.rows;
       const uint4* src = reinterpret_cast<const uint4*>(a.text + (valid ? stage_idx : 0));
       if (!special) {
-#pragma unroll(W <= 2 ? 2 : 1)
+#pragma unroll(W <= 2 ? kUnroll : 1)
         for (int cc = 0; cc < kChunks; cc++) {
           const int c = REV ? (kChunks - 1 - cc) : cc;
           uint4 v = make_uint4(0, 0, 0, 0);

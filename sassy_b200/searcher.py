@@ -78,6 +78,7 @@ class MatchList(collections.abc.Sequence):
     def __init__(self, recs: "np.ndarray", ops: bytes):
         self._recs = recs
         self._ops = ops
+        self._list = None
 
     def __len__(self):
         return len(self._recs)
@@ -88,14 +89,26 @@ class MatchList(collections.abc.Sequence):
                      int(r["pattern_start"]), int(r["pattern_end"]), int(r["cost"]), "-" if r["strand"] else "+",
                      self._ops[off:off + int(r["ops_len"])].decode())
 
+    def _all(self) -> List[Match]:
+        """Materialise every Match once (column-wise, much faster than record by record)."""
+        if self._list is None:
+            r = self._recs
+            ops = self._ops.decode()
+            cols = [r[f].tolist() for f in ("pattern_idx", "text_idx", "text_start", "text_end", "pattern_start",
+                                            "pattern_end", "cost", "strand", "ops_off", "ops_len")]
+            self._list = [Match(pi, ti, ts, te, ps, pe, c, "-" if st else "+", ops[oo:oo + ol])
+                          for pi, ti, ts, te, ps, pe, c, st, oo, ol in zip(*cols)]
+        return self._list
+
     def __getitem__(self, i):
         if isinstance(i, slice):
-            return [self._make(r) for r in self._recs[i]]
+            return self._all()[i]
+        if self._list is not None:
+            return self._list[i]
         return self._make(self._recs[i])
 
     def __iter__(self):
-        for r in self._recs:
-            yield self._make(r)
+        return iter(self._all())
 
     def __eq__(self, other):
         if isinstance(other, (list, MatchList)):
