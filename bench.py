@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--text-bytes", type=int, default=0, help="override the text size (debug)")
     ap.add_argument("--patterns", type=int, default=0, help="override the number of patterns (debug)")
     ap.add_argument("--variant", default="tma", choices=["tma", "ldg"])
+    ap.add_argument("--filter", default="auto", choices=["off", "auto", "force"],
+                    help="exact piece prefilter in front of the scan (result-neutral)")
     ap.add_argument("--rc", action="store_true", help="search both strands (default: forward only, as the reference's evals)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -266,6 +268,7 @@ def main():
 
     s = sassy_b200.Searcher(profile, rc=args.rc, device=local_rank)
     s.set_variant(args.variant)
+    s.set_filter(args.filter)
     dt = s.text_from_device(text_dev.data_ptr(), n)
     enc = s.encode_patterns(pats) if n_patterns > 1 else None
 
@@ -364,12 +367,14 @@ def main():
     achieved = n / (scan_avg_ms * 1e-3) / 1e9  # algorithmic bytes of one scan launch set = the text, read once
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+            args.workload + ("_filter" if st["filter_words"] else "_scan"))
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                "kernel": "scan_kernel", "kernel_ms": scan_avg_ms,
+                "kernel": "filter_kernel" if st["filter_words"] else "scan_kernel", "kernel_ms": scan_avg_ms,
+                "verify_kernel_ms": st["verify_ms"], "prefilter_hits": st["hits"],
                 "kernel_share_of_step": scan_avg_ms / ms_per_step,
                 "algorithmic_bytes_per_launch": n,
                 "lane_steps_per_s": n * len(pats) * (2 if args.rc else 1) / (scan_avg_ms * 1e-3)}
@@ -397,6 +402,8 @@ def main():
                    "rc": bool(args.rc), "mode": "search (local minima) + traceback",
                    "l2": "text (3 GB) is larger than L2 (126 MB); no flush needed", "variant": args.variant,
                    "row_bytes": st["row_bytes"], "rows": st["rows"], "blocks_per_sm": st["blocks_per_sm"],
+                   "prefilter": {"mode": args.filter, "words": st["filter_words"], "piece_len": st["filter_len"],
+                                 "fallback": st["filter_fallback"]},
                    "sharding": "text shards, one per rank; NCCL all-gather of match records per step" if world > 1 else "single GPU"},
         "matches": len(matches), "matches_per_s": len(matches) * args.steps / el,
         "gchar_pattern_per_s": total_bytes * len(pats) * args.steps / el / 1e9,

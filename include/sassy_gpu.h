@@ -62,7 +62,12 @@ typedef struct sassy_gpu_Stats {
   uint32_t words;         /* 32-bit words per pattern bit-vector */
   uint32_t blocks_per_sm;
   uint32_t retries;       /* re-scans after a candidate-buffer overflow */
-  uint32_t reserved;
+  uint32_t filter_words;  /* 32-bit words of the exact piece prefilter automaton; 0 = full scan */
+  float filter_ms;        /* prefilter kernel(s) */
+  float verify_ms;        /* re-scan of the prefilter's hit neighbourhoods */
+  uint64_t hits;          /* text words in which a pattern piece occurs exactly */
+  uint32_t filter_len;    /* piece length */
+  uint32_t filter_fallback; /* 1: prefilter produced too many hits, the full scan was used */
 } sassy_gpu_Stats;
 
 #ifdef __cplusplus
@@ -77,6 +82,9 @@ sassy_SearcherType *sassy_gpu_searcher(const char *alphabet, bool rc, float alph
 
 /* Scan kernel data path: 0 = TMA-staged (default), 1 = per-thread global loads (A/B baseline). */
 int sassy_gpu_set_variant(sassy_SearcherType *searcher, int variant);
+/* Exact piece prefilter (result-neutral, like the reference's suffix prefilter,
+ * src/pattern_tiling/general.rs:294-313): 0 = off, 1 = when profitable (default), 2 = whenever possible. */
+int sassy_gpu_set_filter(sassy_SearcherType *searcher, int mode);
 int sassy_gpu_stats(const sassy_SearcherType *searcher, sassy_gpu_Stats *out);
 
 /* Pinned host memory for texts that are searched through the host-pointer entry points. */

@@ -63,7 +63,12 @@ class GpuStats(ctypes.Structure):
         ("words", ctypes.c_uint32),
         ("blocks_per_sm", ctypes.c_uint32),
         ("retries", ctypes.c_uint32),
-        ("reserved", ctypes.c_uint32),
+        ("filter_words", ctypes.c_uint32),
+        ("filter_ms", ctypes.c_float),
+        ("verify_ms", ctypes.c_float),
+        ("hits", ctypes.c_uint64),
+        ("filter_len", ctypes.c_uint32),
+        ("filter_fallback", ctypes.c_uint32),
     ]
 
 
@@ -80,6 +85,7 @@ SIGNATURES = {
     "sassy_gpu_last_error": (ctypes.c_char_p, []),
     "sassy_gpu_searcher": (c_void_p, [ctypes.c_char_p, ctypes.c_bool, ctypes.c_float, ctypes.c_int]),
     "sassy_gpu_set_variant": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "sassy_gpu_set_filter": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "sassy_gpu_stats": (ctypes.c_int, [c_void_p, ctypes.POINTER(GpuStats)]),
     "sassy_gpu_host_alloc": (c_void_p, [c_size_t]),
     "sassy_gpu_host_free": (None, [c_void_p]),

@@ -54,6 +54,58 @@ void scan_rows(const ScanArgs& a, const uint32_t* eq_q, uint32_t qs) {
   }
 }
 
+template <int WF, bool REV>
+void filter_rows(const ScanArgs& a, const uint32_t* feq_q, uint32_t qs) {
+  EqTab eqt;
+  eqt.p = feq_q;
+  eqt.saddr = 0;
+  eqt.rowbytes = (uint32_t)WF * 4u;
+  const uint32_t total = a.g.nwarm + a.g.nstage;
+  const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
+  for (uint64_t row = 0; row < tiles * kScanThreads; row++) {
+    FLane<WF> s;
+    flane_reset<WF>(s, a);
+    for (uint32_t it = 0; it < total; it++) {
+      int64_t r;
+      uint32_t col;
+      bool own;
+      stage_coord<REV>(a.g, it, (int64_t)row, r, col, own);
+      const uint64_t stage_idx = (uint64_t)(r * (int64_t)a.g.ltot + (int64_t)col);
+      const bool valid = r >= 0 && r < (int64_t)a.g.rows;
+      for (int cc = 0; cc < kStageBytes / 16; cc++) {
+        const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
+        uint32_t x[4] = {0, 0, 0, 0};
+        if (valid) memcpy(x, a.text + stage_idx + 16u * c, 16);
+        filter16<WF, REV>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+      }
+    }
+  }
+}
+
+template <bool REV>
+void filter_dispatch(int WF, const ScanArgs& a, const uint32_t* feq_q, uint32_t qs) {
+  switch (WF) {
+    case 1: filter_rows<1, REV>(a, feq_q, qs); break;
+    case 2: filter_rows<2, REV>(a, feq_q, qs); break;
+    case 4: filter_rows<4, REV>(a, feq_q, qs); break;
+    default: abort();
+  }
+}
+
+void verify_dispatch(int W, const ScanArgs& a, const uint32_t* eq_q, uint32_t qs, bool rev, uint64_t word) {
+  switch (W) {
+    case 1: verify_hit<1>(a, eq_q, qs, rev, word); break;
+    case 2: verify_hit<2>(a, eq_q, qs, rev, word); break;
+    case 3: verify_hit<3>(a, eq_q, qs, rev, word); break;
+    case 4: verify_hit<4>(a, eq_q, qs, rev, word); break;
+    case 6: verify_hit<6>(a, eq_q, qs, rev, word); break;
+    case 8: verify_hit<8>(a, eq_q, qs, rev, word); break;
+    case 16: verify_hit<16>(a, eq_q, qs, rev, word); break;
+    case 32: verify_hit<32>(a, eq_q, qs, rev, word); break;
+    default: abort();
+  }
+}
+
 template <bool REV>
 void scan_dispatch(int W, const ScanArgs& a, const uint32_t* eq_q, uint32_t qs) {
   switch (W) {
@@ -76,6 +128,9 @@ struct EmuResult {
   std::vector<uint32_t> ops;
   uint32_t ops_words;
   uint64_t candidates;
+  uint64_t hits;
+  int filter_words;  // 0 = full scan
+  int filter_len;
   ScanGeom g;
 };
 
@@ -83,10 +138,11 @@ extern "C" {
 
 // queries: nq * m bytes; rev[q] = 1 scans the reversed text.  ltot_override > 0
 // forces the row length (to exercise row boundaries on tiny texts); bpw plays
-// the part of "resident blocks per wave" in the tiling heuristic.
+// the part of "resident blocks per wave" in the tiling heuristic.  use_filter: 0 = full
+// scan, 1 = prefilter + verification whenever a piece layout exists, -1 = the engine's rule.
 EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, uint32_t nq, int m,
                       const uint8_t* text, uint64_t n, int k, int all_minima, int include_pos0,
-                      uint32_t ltot_override, int bpw) {
+                      uint32_t ltot_override, int bpw, int use_filter) {
   ProfileParams pp;
   if (!profile_params(profile, pp) || m <= 0) return nullptr;
   const int W = round_words((m + 31) / 32);
@@ -108,7 +164,8 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   std::vector<uint8_t> padded(std::max<size_t>(padded_alloc(n), (size_t)g.rows * g.ltot + 256), 0);
   if (n) memcpy(padded.data(), text, n);
 
-  const uint64_t cap = (uint64_t)nq * (n + 2) + 16;
+  // with the prefilter every hit word may report up to 4+m+k positions (overlapping windows)
+  const uint64_t cap = (uint64_t)nq * (n / 4 + 2) * (uint64_t)(use_filter ? 5 + m + k : 4) + 64;
   std::vector<uint64_t> keys(cap);
   std::vector<uint32_t> cost(cap);
   unsigned long long count = 0;
@@ -134,7 +191,37 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   a.cand_cost = cost.data();
   a.cand_count = &count;
   a.cand_cap = cap;
-  if (n > 0) {
+  std::vector<const uint8_t*> qptr(nq);
+  for (uint32_t q = 0; q < nq; q++) qptr[q] = queries + (size_t)q * m;
+  FilterPlan fp;
+  if (use_filter != 0) fp = plan_filter(profile, qptr.data(), nq, m, k, use_filter > 0 ? 1e30 : 0.04);
+  res->hits = 0;
+  res->filter_words = fp.enabled ? fp.WF : 0;
+  res->filter_len = fp.enabled ? fp.L : 0;
+  if (n > 0 && fp.enabled) {
+    std::vector<uint32_t> feq((size_t)nq * 256 * fp.WF);
+    for (uint32_t q = 0; q < nq; q++) build_filter_table(profile, fp, qptr[q], &feq[(size_t)q * 256 * fp.WF]);
+    std::vector<uint64_t> hits((size_t)nq * (n / 4 + 2) + 16);
+    unsigned long long nhits = 0;
+    ScanArgs f = a;
+    f.g.nwarm = 1;
+    for (int w = 0; w < kMaxFilterWords; w++) f.finit[w] = fp.finit[w], f.fdelay[w] = fp.fdelay[w];
+    f.hit_keys = hits.data();
+    f.hit_count = &nhits;
+    f.hit_cap = hits.size();
+    for (uint32_t q = 0; q < nq; q++) {
+      const uint32_t* feq_q = &feq[(size_t)q * 256 * fp.WF];
+      if (rev[q])
+        filter_dispatch<true>(fp.WF, f, feq_q, q);
+      else
+        filter_dispatch<false>(fp.WF, f, feq_q, q);
+    }
+    res->hits = nhits;
+    for (unsigned long long h = 0; h < nhits; h++) {
+      const uint32_t qs = key_qs(hits[h]);
+      verify_dispatch(W, a, &eq[(size_t)qs * pp.nrows * W], qs, rev[qs] != 0, key_pos(hits[h]));
+    }
+  } else if (n > 0) {
     for (uint32_t q = 0; q < nq; q++) {
       const uint32_t* eq_q = &eq[(size_t)q * pp.nrows * W];
       if (rev[q]) {
@@ -155,6 +242,14 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   std::vector<uint64_t> skeys(count);
   std::vector<uint32_t> scost(count);
   for (uint64_t i = 0; i < count; i++) skeys[i] = keys[order[i]], scost[i] = cost[order[i]];
+  if (fp.enabled) {  // overlapping verification windows report a position more than once
+    uint64_t o = 0;
+    for (uint64_t i = 0; i < count; i++)
+      if (i == 0 || skeys[i] != skeys[i - 1]) skeys[o] = skeys[i], scost[o] = scost[i], o++;
+    count = o;
+    skeys.resize(count);
+    scost.resize(count);
+  }
 
   std::vector<uint64_t> sel;
   for (uint64_t i = 0; i < count; i++)
@@ -203,6 +298,9 @@ const GpuMatch* emu_matches(const EmuResult* r) { return r->m.data(); }
 const uint32_t* emu_ops(const EmuResult* r) { return r->ops.data(); }
 uint32_t emu_ops_words(const EmuResult* r) { return r->ops_words; }
 uint64_t emu_candidates(const EmuResult* r) { return r->candidates; }
+uint64_t emu_hits(const EmuResult* r) { return r->hits; }
+int emu_filter_words(const EmuResult* r) { return r->filter_words; }
+int emu_filter_len(const EmuResult* r) { return r->filter_len; }
 uint32_t emu_ltot(const EmuResult* r) { return r->g.ltot; }
 uint32_t emu_rows(const EmuResult* r) { return r->g.rows; }
 void emu_free(EmuResult* r) { delete r; }

@@ -55,6 +55,9 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
   nrows_ = pp.nrows, sh0_ = pp.sh0, msk0_ = pp.msk0;
   const char* v = getenv("SASSY_B200_VARIANT");
   if (v && !strcmp(v, "ldg")) variant_ = kVariantLdg;
+  const char* fm = getenv("SASSY_B200_FILTER");
+  if (fm && !strcmp(fm, "off")) filter_mode_ = 0;
+  if (fm && !strcmp(fm, "force")) filter_mode_ = 2;
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
@@ -67,7 +70,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   for (DevBuf* b : {&eq_, &patterns_, &revflags_, &keys_, &cost_, &keys2_, &cost2_, &flags_, &sel_, &count_,
-                    &cubtmp_, &scratch_, &ops_, &out_})
+                    &cubtmp_, &scratch_, &ops_, &out_, &feq_, &hits_})
     b->release();
   if (staged_.d) cudaFree(staged_.d);
   for (auto& ev : ev_)
@@ -212,74 +215,178 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   if (variant_ == kVariantTma && n > 0) make_tensor_map(&tmap, text, g);
 
   if (cand_cap_ == 0) cand_cap_ = 1ull << 20;
-  count_.ensure(2 * sizeof(unsigned long long));
-  uint64_t ncand = 0;
-  for (int attempt = 0;; attempt++) {
+  count_.ensure(4 * sizeof(unsigned long long));
+  unsigned long long* d_cand_count = count_.as<unsigned long long>();
+  unsigned long long* d_hit_count = count_.as<unsigned long long>() + 2;
+
+  ScanArgs a;
+  memset(&a, 0, sizeof a);
+  a.text = text.d;
+  a.n = n;
+  a.g = g;
+  a.sh0 = sh0_;
+  a.msk0 = msk0_;
+  a.nrows = nrows_;
+  a.rowbytes = (uint32_t)W * 4u;
+  a.m = m;
+  a.k = k;
+  a.cand_count = d_cand_count;
+
+  // end position 0 (empty text prefix) has cost m: a candidate iff m <= k.
+  // (reference src/search.rs:1320-1322; never reported for an empty text, :1314-1316)
+  std::vector<uint64_t> k0;
+  std::vector<uint32_t> c0;
+  if (include_pos0 && m <= k && n > 0)
+    for (uint32_t q = 0; q < nq; q++) {
+      k0.push_back(cand_key(q, 0));
+      c0.push_back((uint32_t)m);
+    }
+  auto reset_candidates = [&]() {
     keys_.ensure(cand_cap_ * sizeof(uint64_t));
     cost_.ensure(cand_cap_ * sizeof(uint32_t));
-    // end position 0 (empty text prefix) has cost m: a candidate iff m <= k.
-    // (reference src/search.rs:1320-1322; never reported for an empty text, :1314-1316)
-    std::vector<uint64_t> k0;
-    std::vector<uint32_t> c0;
-    if (include_pos0 && m <= k && n > 0) {
-      for (uint32_t q = 0; q < nq; q++) {
-        k0.push_back(cand_key(q, 0));
-        c0.push_back((uint32_t)m);
-      }
+    if (!k0.empty()) {
       SB_CUDA(cudaMemcpyAsync(keys_.p, k0.data(), k0.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream_));
       SB_CUDA(cudaMemcpyAsync(cost_.p, c0.data(), c0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
     }
-    unsigned long long init = k0.size();
-    SB_CUDA(cudaMemcpyAsync(count_.p, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
-
-    ScanArgs a;
-    memset(&a, 0, sizeof a);
-    a.text = text.d;
-    a.n = n;
-    a.g = g;
-    a.sh0 = sh0_;
-    a.msk0 = msk0_;
-    a.nrows = nrows_;
-    a.rowbytes = (uint32_t)W * 4u;
-    a.m = m;
-    a.k = k;
+    const unsigned long long init = k0.size();
+    SB_CUDA(cudaMemcpyAsync(d_cand_count, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
     a.cand_keys = keys_.as<uint64_t>();
     a.cand_cost = cost_.as<uint32_t>();
-    a.cand_count = count_.as<unsigned long long>();
     a.cand_cap = cand_cap_;
+  };
+  auto read_count = [&](const unsigned long long* d) {
+    unsigned long long v = 0;
+    SB_CUDA(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, stream_));
+    SB_CUDA(cudaStreamSynchronize(stream_));
+    return v;
+  };
+  auto elapsed = [&](cudaEvent_t e0, cudaEvent_t e1) {
+    float ms = 0;
+    SB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    return ms;
+  };
+
+  uint64_t ncand = 0;
+  bool filtered = false;
+
+  // ---- candidates, route 1: exact piece prefilter + re-scan of the hit neighbourhoods -----
+  FilterPlan fp;
+  if (n > 0 && filter_mode_ != 0) {
+    std::vector<const uint8_t*> qptr(nq);
+    for (uint32_t q = 0; q < nq; q++) qptr[q] = queries[q].bytes;
+    fp = plan_filter(profile_, qptr.data(), nq, m, k, filter_mode_ == 2 ? 1e30 : 0.04);
+  }
+  if (fp.enabled) {
+    h_feq_.resize((size_t)nq * 256 * fp.WF);
+    for (uint32_t q = 0; q < nq; q++) build_filter_table(profile_, fp, queries[q].bytes, &h_feq_[(size_t)q * 256 * fp.WF]);
+    feq_.ensure(h_feq_.size() * sizeof(uint32_t));
+    SB_CUDA(cudaMemcpyAsync(feq_.p, h_feq_.data(), h_feq_.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+    if (hit_cap_ == 0) hit_cap_ = 4ull << 20;
+    hits_.ensure(hit_cap_ * sizeof(uint64_t));
+    const unsigned long long zero = 0;
+    SB_CUDA(cudaMemcpyAsync(d_hit_count, &zero, sizeof zero, cudaMemcpyHostToDevice, stream_));
+
+    const int focc = filter_blocks_per_sm(fp.WF, variant_);
+    ScanGeom gf = choose_geom(n, m, k, nq, focc * sm_count_);
+    gf.nwarm = 1;  // a piece plus its delay line is at most 32 characters
+    CUtensorMap ftmap;
+    memset(&ftmap, 0, sizeof ftmap);
+    if (variant_ == kVariantTma) make_tensor_map(&ftmap, text, gf);
+    ScanArgs f = a;
+    f.g = gf;
+    for (int w = 0; w < kMaxFilterWords; w++) f.finit[w] = fp.finit[w], f.fdelay[w] = fp.fdelay[w];
+    f.hit_keys = hits_.as<uint64_t>();
+    f.hit_count = d_hit_count;
+    f.hit_cap = hit_cap_;
     SB_CUDA(cudaEventRecord(ev_[1], stream_));
-    if (n > 0) {
-      if (nfwd) {
-        a.reset_idx = 0;
-        a.nq = nfwd;
-        a.qs_base = 0;
-        a.eq = eq_.as<uint32_t>();
-        SB_CUDA(launch_scan(W, false, variant_, &tmap, a, stream_));
-        stats_.scan_launches++;
-      }
-      if (nq > nfwd) {
-        a.reset_idx = n - 1;
-        a.nq = nq - nfwd;
-        a.qs_base = nfwd;
-        a.eq = eq_.as<uint32_t>() + (size_t)nfwd * nrows_ * W;
-        SB_CUDA(launch_scan(W, true, variant_, &tmap, a, stream_));
-        stats_.scan_launches++;
-      }
+    if (nfwd) {
+      f.nq = nfwd;
+      f.qs_base = 0;
+      f.feq = feq_.as<uint32_t>();
+      SB_CUDA(launch_filter(fp.WF, false, variant_, &ftmap, f, stream_));
+      stats_.scan_launches++;
+    }
+    if (nq > nfwd) {
+      f.nq = nq - nfwd;
+      f.qs_base = nfwd;
+      f.feq = feq_.as<uint32_t>() + (size_t)nfwd * 256 * fp.WF;
+      SB_CUDA(launch_filter(fp.WF, true, variant_, &ftmap, f, stream_));
+      stats_.scan_launches++;
     }
     SB_CUDA(cudaEventRecord(ev_[2], stream_));
-    unsigned long long cnt = 0;
-    SB_CUDA(cudaMemcpyAsync(&cnt, count_.p, sizeof cnt, cudaMemcpyDeviceToHost, stream_));
-    SB_CUDA(cudaStreamSynchronize(stream_));
-    float ms = 0;
-    SB_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2]));
-    stats_.scan_ms += ms;
-    if (cnt <= cand_cap_) {
-      ncand = cnt;
-      break;
+    const unsigned long long nhits = read_count(d_hit_count);
+    stats_.filter_ms = elapsed(ev_[1], ev_[2]);
+    stats_.hits = nhits;
+    stats_.filter_words = (uint32_t)fp.WF;
+    stats_.filter_len = (uint32_t)fp.L;
+    // too many hits (repetitive text, unlucky pieces): the re-scan would cost more than the scan
+    const double rescan = (double)nhits * (2.0 * (m + k) + 4.0);
+    if (nhits > hit_cap_ || rescan > 0.5 * (double)n * nq) {
+      stats_.filter_fallback = 1;
+    } else {
+      stats_.ltot = gf.ltot;
+      stats_.rows = gf.rows;
+      stats_.blocks_per_sm = (uint32_t)focc;
+      for (int attempt = 0;; attempt++) {
+        reset_candidates();
+        ScanArgs v = a;
+        v.nq = nq;
+        v.qs_base = 0;
+        v.eq = eq_.as<uint32_t>();
+        v.hit_keys = hits_.as<uint64_t>();
+        SB_CUDA(cudaEventRecord(ev_[1], stream_));
+        SB_CUDA(launch_verify(W, v, revflags_.as<uint8_t>(), nhits, stream_));
+        if (nhits) stats_.aux_launches++;
+        SB_CUDA(cudaEventRecord(ev_[2], stream_));
+        const unsigned long long cnt = read_count(d_cand_count);
+        stats_.verify_ms += elapsed(ev_[1], ev_[2]);
+        if (cnt <= cand_cap_) {
+          ncand = cnt;
+          break;
+        }
+        if (attempt >= 3) throw CudaError("candidate buffer overflow after retries");
+        cand_cap_ = (size_t)(cnt + cnt / 8 + 1024);
+        stats_.retries++;
+      }
+      filtered = true;
+      stats_.scan_ms = stats_.filter_ms;  // the dominant kernel of this route
     }
-    if (attempt >= 3) throw CudaError("candidate buffer overflow after retries");
-    cand_cap_ = (size_t)(cnt + cnt / 8 + 1024);  // dense text: re-run with an exact-size buffer
-    stats_.retries++;
+  }
+
+  // ---- candidates, route 2: full scan with the bit-parallel recurrences ---------------------
+  if (!filtered) {
+    for (int attempt = 0;; attempt++) {
+      reset_candidates();
+      SB_CUDA(cudaEventRecord(ev_[1], stream_));
+      if (n > 0) {
+        if (nfwd) {
+          a.reset_idx = 0;
+          a.nq = nfwd;
+          a.qs_base = 0;
+          a.eq = eq_.as<uint32_t>();
+          SB_CUDA(launch_scan(W, false, variant_, &tmap, a, stream_));
+          stats_.scan_launches++;
+        }
+        if (nq > nfwd) {
+          a.reset_idx = n - 1;
+          a.nq = nq - nfwd;
+          a.qs_base = nfwd;
+          a.eq = eq_.as<uint32_t>() + (size_t)nfwd * nrows_ * W;
+          SB_CUDA(launch_scan(W, true, variant_, &tmap, a, stream_));
+          stats_.scan_launches++;
+        }
+      }
+      SB_CUDA(cudaEventRecord(ev_[2], stream_));
+      const unsigned long long cnt = read_count(d_cand_count);
+      stats_.scan_ms += elapsed(ev_[1], ev_[2]);
+      if (cnt <= cand_cap_) {
+        ncand = cnt;
+        break;
+      }
+      if (attempt >= 3) throw CudaError("candidate buffer overflow after retries");
+      cand_cap_ = (size_t)(cnt + cnt / 8 + 1024);  // dense text: re-run with an exact-size buffer
+      stats_.retries++;
+    }
   }
   stats_.candidates = ncand;
 
@@ -298,20 +405,35 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     SB_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp_.p, tmp_bytes, keys_.as<uint64_t>(), keys2_.as<uint64_t>(),
                                             cost_.as<uint32_t>(), cost2_.as<uint32_t>(), ncand, 0, end_bit,
                                             stream_));
+    uint64_t* skeys = keys2_.as<uint64_t>();
+    uint32_t* scost = cost2_.as<uint32_t>();
+    if (filtered) {
+      // overlapping re-scan windows report an end position more than once: keep one copy
+      unsigned long long* d_nuniq = count_.as<unsigned long long>() + 1;
+      size_t tmp3 = 0;
+      SB_CUDA(cub::DeviceSelect::UniqueByKey(nullptr, tmp3, keys2_.as<uint64_t>(), cost2_.as<uint32_t>(),
+                                             keys_.as<uint64_t>(), cost_.as<uint32_t>(), d_nuniq, ncand, stream_));
+      cubtmp_.ensure(tmp3);
+      SB_CUDA(cub::DeviceSelect::UniqueByKey(cubtmp_.p, tmp3, keys2_.as<uint64_t>(), cost2_.as<uint32_t>(),
+                                             keys_.as<uint64_t>(), cost_.as<uint32_t>(), d_nuniq, ncand, stream_));
+      ncand = read_count(d_nuniq);
+      skeys = keys_.as<uint64_t>();
+      scost = cost_.as<uint32_t>();
+    }
     if (all_minima) {
       nsel = ncand;
-      sel_keys = keys2_.as<uint64_t>();
+      sel_keys = skeys;
     } else {
       flags_.ensure(ncand);
       sel_.ensure(ncand * sizeof(uint64_t));
-      SB_CUDA(launch_minima(keys2_.as<uint64_t>(), cost2_.as<uint32_t>(), ncand, flags_.as<uint8_t>(), stream_));
+      SB_CUDA(launch_minima(skeys, scost, ncand, flags_.as<uint8_t>(), stream_));
       stats_.aux_launches++;
       unsigned long long* d_nsel = count_.as<unsigned long long>() + 1;
       size_t tmp2 = 0;
-      SB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp2, keys2_.as<uint64_t>(), flags_.as<uint8_t>(),
+      SB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp2, skeys, flags_.as<uint8_t>(),
                                          sel_.as<uint64_t>(), d_nsel, ncand, stream_));
       cubtmp_.ensure(tmp2);
-      SB_CUDA(cub::DeviceSelect::Flagged(cubtmp_.p, tmp2, keys2_.as<uint64_t>(), flags_.as<uint8_t>(),
+      SB_CUDA(cub::DeviceSelect::Flagged(cubtmp_.p, tmp2, skeys, flags_.as<uint8_t>(),
                                          sel_.as<uint64_t>(), d_nsel, ncand, stream_));
       unsigned long long h = 0;
       SB_CUDA(cudaMemcpyAsync(&h, d_nsel, sizeof h, cudaMemcpyDeviceToHost, stream_));

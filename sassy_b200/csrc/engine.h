@@ -53,6 +53,12 @@ struct SearchStats {
   uint64_t matches = 0;
   uint32_t ltot = 0, rows = 0, words = 0, blocks_per_sm = 0;
   uint32_t retries = 0;
+  // exact piece prefilter (0 words = full scan)
+  float filter_ms = 0;   // prefilter kernel(s)
+  float verify_ms = 0;   // re-scan of the hit neighbourhoods
+  uint64_t hits = 0;
+  uint32_t filter_words = 0, filter_len = 0;
+  uint32_t filter_fallback = 0;  // prefilter ran but produced too many hits: full scan used
 };
 
 struct MatchSet {
@@ -87,6 +93,9 @@ class Engine {
   const SearchStats& stats() const { return stats_; }
   void set_variant(int v) { variant_ = v; }
   int variant() const { return variant_; }
+  // 0 = never prefilter, 1 = prefilter when the expected re-scan work is small (default),
+  // 2 = prefilter whenever a piece layout exists (tests)
+  void set_filter_mode(int m) { filter_mode_ = m; }
 
  private:
   void build_tables(const std::vector<Query>& queries, int m, int W);
@@ -95,6 +104,7 @@ class Engine {
   int profile_;
   int device_;
   int variant_;
+  int filter_mode_ = 1;
   int sm_count_ = 148;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -103,6 +113,9 @@ class Engine {
   DevBuf eq_, patterns_, revflags_;
   DevBuf keys_, cost_, keys2_, cost2_, flags_, sel_, count_, cubtmp_;
   DevBuf scratch_, ops_, out_;
+  DevBuf feq_, hits_;
+  uint64_t hit_cap_ = 0;
+  std::vector<uint32_t> h_feq_;
   uint64_t cand_cap_ = 0;
   DeviceText staged_;
   std::vector<uint32_t> h_eq_;

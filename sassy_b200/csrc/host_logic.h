@@ -93,6 +93,106 @@ inline ScanGeom choose_geom(uint64_t n, int m, int k, uint32_t nq, int bpw) {
   return g;
 }
 
+// ---------------------------------------------------------------------------
+// Exact piece prefilter: layout and tables (see scan_core.cuh).
+struct FilterPlan {
+  bool enabled = false;
+  int WF = 0;        // automaton words (1, 2 or 4)
+  int L = 0;         // piece length
+  int npieces = 0;   // k + 1
+  int stride = 0;    // distance between piece starts in the pattern
+  double rate = 0;   // expected piece hits per text position (uniform ACGT text), max over queries
+  uint32_t finit[kMaxFilterWords] = {0, 0, 0, 0};
+  uint32_t fdelay[kMaxFilterWords] = {0, 0, 0, 0};
+};
+
+inline int piece_word(const FilterPlan& f, int p) { return p / ((f.npieces + f.WF - 1) / f.WF); }
+inline int piece_bit(const FilterPlan& f, int p) {
+  return (p % ((f.npieces + f.WF - 1) / f.WF)) * (f.L + kFilterDelay);
+}
+
+// Probability that a uniformly random ACGT character matches pattern byte c.
+inline double match_prob(int profile, uint8_t c) {
+  if (profile == kIupac) {
+    const uint8_t code = iupac_code(c);
+    if (code == 255) return 1.0;
+    int bits = 0;
+    for (int i = 0; i < 4; i++) bits += (code >> i) & 1;
+    return bits / 4.0;
+  }
+  return 0.25;  // Dna classes; Ascii: assumed, the run-time hit counter guards the assumption
+}
+
+// Chooses the smallest automaton for which the expected re-scan work stays small.
+inline FilterPlan plan_filter(int profile, const uint8_t* const* queries, size_t nq, int m, int k,
+                              double max_frac = 0.04) {
+  FilterPlan best;
+  const int np = k + 1;
+  if (k < 0 || np > m || nq == 0) return best;
+  const double window = 2.0 * (m + k) + 4.0;
+  const int wopts[] = {1, 2, 4};
+  for (int WF : wopts) {
+    const int ppw = (np + WF - 1) / WF;  // pieces per word
+    int L = 32 / ppw - kFilterDelay;
+    const int stride = m / np;
+    if (L > stride) L = stride;
+    if (L < 1) continue;
+    FilterPlan f;
+    f.WF = WF, f.L = L, f.npieces = np, f.stride = stride;
+    double worst = 0;
+    for (size_t q = 0; q < nq; q++) {
+      double rate = 0;
+      for (int p = 0; p < np; p++) {
+        double pr = 1;
+        for (int j = 0; j < L; j++) pr *= match_prob(profile, queries[q][p * stride + j]);
+        rate += pr;
+      }
+      if (rate > worst) worst = rate;
+    }
+    f.rate = worst;
+    // re-scan fraction of the text (per query) must stay below 4 %: then the filter pass
+    // (about a quarter of the cost of the full recurrences per character and word) dominates
+    if (worst * window <= max_frac) {
+      for (int p = 0; p < np; p++) {
+        const int w = piece_word(f, p), b = piece_bit(f, p);
+        f.finit[w] |= 1u << b;
+        f.fdelay[w] |= 1u << (b + L - 1);  // the piece's last bit ...
+        for (int d = 0; d < kFilterDelay; d++) f.fdelay[w] |= 1u << (b + L + d);  // ... and its delay line
+      }
+      f.enabled = true;
+      return f;
+    }
+    best = f;  // remember the last candidate for diagnostics
+  }
+  best.enabled = false;
+  return best;
+}
+
+// Filter automaton masks of one query: tab[byte][WF].
+inline void build_filter_table(int profile, const FilterPlan& f, const uint8_t* pat, uint32_t* tab) {
+  ProfileParams pp;
+  profile_params(profile, pp);
+  memset(tab, 0, (size_t)256 * f.WF * sizeof(uint32_t));
+  for (int byte = 0; byte < 256; byte++) {
+    uint32_t* e = tab + (size_t)byte * f.WF;
+    const int row = (int)(((uint32_t)byte >> pp.sh0) & (pp.msk0 & 0xFFu));
+    for (int p = 0; p < f.npieces; p++) {
+      const int w = piece_word(f, p), b = piece_bit(f, p);
+      for (int j = 0; j < f.L; j++) {
+        const uint8_t pc = pat[p * f.stride + j];
+        bool match;
+        switch (profile) {
+          case kDna: match = row_matches<kDna>(pc, row); break;
+          case kIupac: match = row_matches<kIupac>(pc, row); break;
+          default: match = row_matches<kAscii>(pc, row); break;
+        }
+        if (match) e[w] |= 1u << (b + j);
+      }
+      for (int d = 0; d < kFilterDelay; d++) e[w] |= 1u << (b + f.L + d);
+    }
+  }
+}
+
 inline size_t padded_alloc(uint64_t n) {
   // room for one extra row of any tiling plus alignment slack
   return (size_t)((n + 2ull * kMaxRowBytes + 255ull) & ~255ull);

@@ -25,6 +25,15 @@ int scan_blocks_per_sm(int W, bool rev, int variant, uint32_t nrows);
 cudaError_t launch_scan(int W, bool rev, int variant, const CUtensorMap* tmap, const ScanArgs& a,
                         cudaStream_t stream);
 
+// Exact piece prefilter (scan_core.cuh): hits -> a.hit_keys; then one thread per hit re-scans
+// the hit's neighbourhood with the full recurrences -> a.cand_*.
+size_t filter_smem_bytes(int WF, int variant);
+int filter_blocks_per_sm(int WF, int variant);
+cudaError_t launch_filter(int WF, bool rev, int variant, const CUtensorMap* tmap, const ScanArgs& a,
+                          cudaStream_t stream);
+cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, unsigned long long nhits,
+                          cudaStream_t stream);
+
 // flags[i] = 1 iff sorted candidate i is kept by the local-minima rule.
 cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags,
                           cudaStream_t stream);

@@ -33,6 +33,11 @@ constexpr int kGroup = SB_GROUP;  // 4, 8 or 16 (whole 32-bit text words)
 // Bytes per thread per pipeline stage (half a 128-byte line).
 constexpr int kStageBytes = 64;
 
+constexpr int kMaxFilterWords = 4;
+// Delay-line bits behind every piece of the prefilter: together with the piece's last
+// bit they keep an occurrence visible for 4 characters = one text word = one hit test.
+constexpr int kFilterDelay = 3;
+
 // Geometry of one scan: the text is viewed as `rows` rows of `ltot` bytes.
 struct ScanGeom {
   uint32_t ltot;    // bytes per row, multiple of kStageBytes
@@ -60,6 +65,13 @@ struct ScanArgs {
   uint32_t* cand_cost;
   unsigned long long* cand_count;
   uint64_t cand_cap;
+  // exact piece prefilter (filter_kernel / verify_kernel)
+  const uint32_t* feq;      // [nq][256][WF] filter automaton masks, indexed by the raw text byte
+  uint32_t finit[kMaxFilterWords];   // first bit of every piece
+  uint32_t fdelay[kMaxFilterWords];  // delay-line bits behind every piece
+  uint64_t* hit_keys;       // (query slot << 40) | forward index of the hit's text word / 4
+  unsigned long long* hit_count;
+  uint64_t hit_cap;
 };
 
 template <int W>
@@ -274,6 +286,122 @@ SB_HD void process16(Lane<W>& s, int& prev_score, const uint32_t (&x)[4], uint64
   for (int gg = 0; gg < NG; gg++) {
     const int g = REV ? NG - 1 - gg : gg;
     fast_group<W, REV>(s, prev_score, &x[g * NW], base_idx + 4 * NW * g, a, eqs, qs, own);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Exact piece prefilter (pigeonhole).  k+1 pairwise disjoint pieces of the
+// pattern are searched EXACTLY with a Shift-And automaton; an alignment with at
+// most k edits leaves at least one piece intact, so every end position with
+// cost <= k lies within m+k characters behind an exact piece occurrence.  Only
+// those neighbourhoods are then scanned with the Myers recurrences
+// (verify_hit).  The result is identical to the full scan; the reference uses
+// the same idea of an exact prefilter in its v2 engine (suffix prefilter,
+// src/pattern_tiling/general.rs:60-102,294-313), with a different filter.
+//
+// Automaton word layout: pieces are packed from bit 0, each followed by
+// kFilterDelay (3) delay bits whose mask accepts every character.  The hit mask
+// holds every piece's last bit and its delay bits, so an occurrence ending at
+// any of the 4 characters of a text word is visible when the word has been
+// consumed: one test per text word.  Per character: PRMT + LOP3 on the ALU pipe,
+// 2 IMAD on the FMA pipe, 1 LDS.
+template <int WF>
+struct FLane {
+  uint32_t st[WF];
+  uint32_t init[WF];   // copies of ScanArgs::finit / fdelay kept in registers
+  uint32_t delay[WF];
+};
+
+template <int WF>
+SB_HD void flane_reset(FLane<WF>& s, const ScanArgs& a) {
+#pragma unroll
+  for (int w = 0; w < WF; w++) s.st[w] = 0, s.init[w] = a.finit[w], s.delay[w] = a.fdelay[w];
+}
+
+template <int WF>
+SB_HD void load_feq(uint32_t (&eq)[WF], const EqTab& t, uint32_t x, int b) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t row = __byte_perm(x, 0u, 0x4440u + (uint32_t)b);
+  uint32_t addr;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(row), "r"(t.rowbytes), "r"(t.saddr));
+  if (WF == 4) {
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(eq[0]), "=r"(eq[WF > 1 ? 1 : 0]), "=r"(eq[WF > 2 ? 2 : 0]), "=r"(eq[WF > 3 ? 3 : 0]) : "r"(addr));
+  } else if (WF == 2) {
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(eq[0]), "=r"(eq[WF > 1 ? 1 : 0]) : "r"(addr));
+  } else {
+#pragma unroll
+    for (int w = 0; w < WF; w++) asm("ld.shared.u32 %0, [%1];" : "=r"(eq[w]) : "r"(addr + 4 * w));
+  }
+#else
+  const uint32_t row = (x >> (8 * b)) & 0xFFu;
+  const uint32_t* p = t.p + row * WF;
+  for (int w = 0; w < WF; w++) eq[w] = p[w];
+#endif
+}
+
+// Deliberately not inlined: hits are rare, and the ownership / text-end tests must not be
+// hoisted into the per-word fast path.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+static void emit_hit(const ScanArgs& a, uint32_t qs, uint64_t base_idx, bool own) {
+  if (!own || base_idx >= a.n) return;
+#if defined(__CUDA_ARCH__)
+  const unsigned long long i = atomicAdd(a.hit_count, 1ull);
+#else
+  const unsigned long long i = (*a.hit_count)++;
+#endif
+  if (i < a.hit_cap) a.hit_keys[i] = cand_key(qs, base_idx >> 2);
+}
+
+// 16 text bytes through the automaton; a hit is recorded per 4-byte text word.
+template <int WF, bool REV>
+SB_HD void filter16(FLane<WF>& s, const uint32_t (&x)[4], uint64_t base_idx, const ScanArgs& a, const EqTab& feq,
+                    uint32_t qs, bool own) {
+#pragma unroll
+  for (int ww = 0; ww < 4; ww++) {
+    const int w4 = REV ? 3 - ww : ww;
+#pragma unroll
+    for (int bb = 0; bb < 4; bb++) {
+      const int b = REV ? 3 - bb : bb;
+      uint32_t eq[WF];
+      load_feq<WF>(eq, feq, x[w4], b);
+#pragma unroll
+      for (int w = 0; w < WF; w++) s.st[w] = ((s.st[w] << 1) | s.init[w]) & eq[w];
+    }
+    uint32_t hit = 0;
+#pragma unroll
+    for (int w = 0; w < WF; w++) hit |= s.st[w] & s.delay[w];
+    if (hit != 0) emit_hit(a, qs, base_idx + 4u * w4, own);
+  }
+}
+
+// Re-scan of the neighbourhood of one hit with the exact recurrences.  The hit
+// is the text word at forward index 4*word; in scan direction it starts at G0.
+// A piece occurrence ending inside the word implies end positions in
+// (G0, G0 + 4 + m + k]; starting m+k characters before G0 makes them exact.
+template <int W>
+SB_HD void verify_hit(const ScanArgs& a, const uint32_t* eq /*[nrows][W] of this query*/, uint32_t qs, bool rev,
+                      uint64_t word) {
+  const int64_t n = (int64_t)a.n;
+  const int64_t base = (int64_t)(word << 2);
+  const int64_t g0 = rev ? n - 4 - base : base;  // may be negative for the word straddling the text end
+  const int64_t span = (int64_t)a.m + (int64_t)a.k;
+  int64_t w0 = g0 - span;
+  if (w0 < 0) w0 = 0;
+  int64_t end = g0 + 4 + span;
+  if (end > n) end = n;
+  const int64_t emit_from = g0 < 0 ? 0 : g0;
+  Lane<W> s;
+  lane_reset<W>(s, a.m);
+  for (int64_t idx = w0; idx < end; idx++) {
+    const uint8_t c = a.text[rev ? n - 1 - idx : idx];
+    const uint32_t row = ((uint32_t)c >> a.sh0) & (a.msk0 & 0xFFu);
+    myers_step<W>(s, eq + row * W);
+    if (idx >= emit_from) {
+      const int score = lane_score<W>(s);
+      if (score <= a.k) emit_candidate(a, qs, (uint64_t)idx + 1, score);
+    }
   }
 }
 

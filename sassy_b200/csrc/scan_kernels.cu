@@ -74,40 +74,35 @@ constexpr int min_blocks() {
   return (W <= 2 ? 1024 : (W <= 4 ? 768 : (W <= 8 ? 384 : 128))) / kScanThreads;
 }
 
-template <int W, bool REV, int VARIANT>
-__global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
-    scan_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a) {
+// The row pipeline shared by the scan and the prefilter kernels.  Copies the block's
+// query table to shared memory, then feeds every thread its row, 64 bytes per stage:
+//   body(stage_idx, own, chunk) with chunk(c) -> the c-th 16-byte piece of the stage.
+template <bool REV, int VARIANT, class Body>
+__device__ __forceinline__ void row_pipeline(const CUtensorMap& tmap, const ScanArgs& a, const uint32_t* table_src,
+                                             uint32_t table_words, EqTab& tab, Body&& body) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kWarpsPerBlock * kScanStages];
 
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5, lane = tid & 31;
-  const uint32_t q = blockIdx.x % a.nq;  // queries vary fastest: blocks sharing a text tile are co-resident (L2 reuse)
   const uint32_t tile = blockIdx.x / a.nq;
   const int64_t row0 = (int64_t)tile * kScanThreads + 32 * warp;  // first row of this warp
   const int64_t row = row0 + lane;
-  const uint32_t qs = a.qs_base + q;
 
-  // shared memory carve-up: [text rings, 1024-aligned (TMA variant only)] [equality table]
+  // shared memory carve-up: [text rings, 1024-aligned (TMA variant only)] [query table]
   uint8_t* ring = smem_raw;
-  uint32_t* eqs;
+  uint32_t* tbl;
   if (VARIANT == kVariantTma) {
     const uint32_t base = smem_u32(smem_raw);
     ring = smem_raw + (((base + 1023u) & ~1023u) - base);
-    eqs = reinterpret_cast<uint32_t*>(ring + kRingBytes);
+    tbl = reinterpret_cast<uint32_t*>(ring + kRingBytes);
     ring += warp * kWarpRingBytes;
   } else {
-    eqs = reinterpret_cast<uint32_t*>(smem_raw);
+    tbl = reinterpret_cast<uint32_t*>(smem_raw);
   }
-  {
-    const uint32_t words = a.nrows * W;
-    const uint32_t* src = a.eq + (size_t)q * words;
-    for (uint32_t i = tid; i < words; i += kScanThreads) eqs[i] = src[i];
-  }
-  EqTab eqt;
-  eqt.p = eqs;
-  eqt.saddr = smem_u32(eqs);
-  eqt.rowbytes = a.rowbytes;
+  for (uint32_t i = tid; i < table_words; i += kScanThreads) tbl[i] = table_src[i];
+  tab.p = tbl;
+  tab.saddr = smem_u32(tbl);
 
   const uint32_t total = a.g.nwarm + a.g.nstage;
   uint64_t* wbar = &full_bar[warp * kScanStages];
@@ -129,16 +124,12 @@ __global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
   }
-  __syncthreads();  // equality table + barriers visible; the only block-wide sync
+  __syncthreads();  // query table + barriers visible; the only block-wide sync
   if (VARIANT == kVariantTma) {
     if (lane == 0) {
       for (uint32_t it = 0; it < (uint32_t)kScanStages && it < total; it++) issue(it);
     }
   }
-
-  Lane<W> s;
-  lane_reset<W>(s, a.m);
-  int prev_score = a.m;
 
   for (uint32_t it = 0; it < total; ++it) {
     int64_t r;
@@ -146,55 +137,86 @@ __global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
     bool own;
     stage_coord<REV>(a.g, it, row, r, col, own);
     const uint64_t stage_idx = (uint64_t)(r * (int64_t)a.g.ltot + (int64_t)col);
-    const bool special = stage_is_special(a, stage_idx);
     if (VARIANT == kVariantTma) {
       const uint32_t st = it % kScanStages;
       mbar_wait(&wbar[st], (it / kScanStages) & 1u);
       const uint8_t* buf = ring + st * kWarpStageBytes + lane * kStageBytes;
       const uint32_t sw = (lane >> 1) & 3u;  // CU_TENSOR_MAP_SWIZZLE_64B: chunk ^= (row >> 1) & 3
-      if (!special) {
-#pragma unroll(W <= 2 ? kUnroll : 1)
-        for (int cc = 0; cc < kChunks; cc++) {
-          const int c = REV ? (kChunks - 1 - cc) : cc;
-          const uint4 v = *reinterpret_cast<const uint4*>(buf + ((c ^ sw) << 4));
-          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-          process16<W, REV, false>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
-        }
-      } else {
-#pragma unroll 1
-        for (int cc = 0; cc < kChunks; cc++) {
-          const int c = REV ? (kChunks - 1 - cc) : cc;
-          const uint4 v = *reinterpret_cast<const uint4*>(buf + ((c ^ sw) << 4));
-          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-          process16<W, REV, true>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
-        }
-      }
+      body(stage_idx, own, [&](int c) { return *reinterpret_cast<const uint4*>(buf + ((c ^ sw) << 4)); });
       __syncwarp();  // every lane is done with this warp's ring[st]
       if (lane == 0 && it + kScanStages < total) issue(it + kScanStages);
     } else {
       const bool valid = r >= 0 && r < (int64_t)a.g.rows;
       const uint4* src = reinterpret_cast<const uint4*>(a.text + (valid ? stage_idx : 0));
-      if (!special) {
-#pragma unroll(W <= 2 ? kUnroll : 1)
-        for (int cc = 0; cc < kChunks; cc++) {
-          const int c = REV ? (kChunks - 1 - cc) : cc;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (valid) v = __ldg(src + c);
-          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-          process16<W, REV, false>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
-        }
-      } else {
-#pragma unroll 1
-        for (int cc = 0; cc < kChunks; cc++) {
-          const int c = REV ? (kChunks - 1 - cc) : cc;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (valid) v = __ldg(src + c);
-          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-          process16<W, REV, true>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
-        }
-      }
+      body(stage_idx, own, [&](int c) { return valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0); });
     }
   }
+}
+
+template <int W, bool REV, int VARIANT>
+__global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
+    scan_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a) {
+  const uint32_t q = blockIdx.x % a.nq;  // queries vary fastest: blocks sharing a text tile are co-resident (L2 reuse)
+  const uint32_t qs = a.qs_base + q;
+  EqTab eqt;
+  eqt.rowbytes = a.rowbytes;
+  Lane<W> s;
+  lane_reset<W>(s, a.m);
+  int prev_score = a.m;
+  row_pipeline<REV, VARIANT>(
+      tmap, a, a.eq + (size_t)q * a.nrows * W, a.nrows * W, eqt, [&](uint64_t stage_idx, bool own, auto chunk) {
+        if (!stage_is_special(a, stage_idx)) {
+#pragma unroll(W <= 2 ? kUnroll : 1)
+          for (int cc = 0; cc < kChunks; cc++) {
+            const int c = REV ? (kChunks - 1 - cc) : cc;
+            const uint4 v = chunk(c);
+            const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+            process16<W, REV, false>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
+          }
+        } else {
+#pragma unroll 1
+          for (int cc = 0; cc < kChunks; cc++) {
+            const int c = REV ? (kChunks - 1 - cc) : cc;
+            const uint4 v = chunk(c);
+            const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+            process16<W, REV, true>(s, prev_score, x, stage_idx + 16u * c, a, eqt, qs, own);
+          }
+        }
+      });
+}
+
+// Prefilter: Shift-And automaton over k+1 exact pieces (scan_core.cuh); emits the text
+// words in which a piece occurrence ends.
+template <int WF, bool REV, int VARIANT>
+__global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
+    filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a) {
+  const uint32_t q = blockIdx.x % a.nq;
+  const uint32_t qs = a.qs_base + q;
+  EqTab eqt;
+  eqt.rowbytes = (uint32_t)WF * 4u;
+  FLane<WF> s;
+  flane_reset<WF>(s, a);
+  row_pipeline<REV, VARIANT>(tmap, a, a.feq + (size_t)q * 256 * WF, 256 * WF, eqt,
+                             [&](uint64_t stage_idx, bool own, auto chunk) {
+#pragma unroll
+                               for (int cc = 0; cc < kChunks; cc++) {
+                                 const int c = REV ? (kChunks - 1 - cc) : cc;
+                                 const uint4 v = chunk(c);
+                                 const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+                                 filter16<WF, REV>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+                               }
+                             });
+}
+
+// One thread per prefilter hit: exact recurrences over the hit's neighbourhood.
+template <int W>
+__global__ void verify_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags,
+                              unsigned long long nhits) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nhits) return;
+  const uint64_t key = a.hit_keys[i];
+  const uint32_t qs = key_qs(key);
+  verify_hit<W>(a, a.eq + (size_t)qs * a.nrows * W, qs, rev_flags[qs] != 0, key_pos(key));
 }
 
 template <int W, bool REV, int VARIANT>
@@ -224,7 +246,86 @@ int occupancy_one(size_t smem) {
   return nb > 0 ? nb : 1;
 }
 
+template <int WF, bool REV, int VARIANT>
+cudaError_t launch_filter_one(const CUtensorMap* tmap, const ScanArgs& a, size_t smem, cudaStream_t stream) {
+  auto kern = filter_kernel<WF, REV, VARIANT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
+  const uint64_t blocks = tiles * a.nq;
+  if (blocks == 0) return cudaSuccess;
+  if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+  CUtensorMap dummy;
+  if (!tmap) {
+    memset(&dummy, 0, sizeof dummy);
+    tmap = &dummy;
+  }
+  kern<<<(unsigned)blocks, kScanThreads, smem, stream>>>(*tmap, a);
+  return cudaGetLastError();
+}
+
+template <int WF, bool REV, int VARIANT>
+int filter_occupancy_one(size_t smem) {
+  auto kern = filter_kernel<WF, REV, VARIANT>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kScanThreads, smem) != cudaSuccess) return 1;
+  return nb > 0 ? nb : 1;
+}
+
 }  // namespace
+
+size_t filter_smem_bytes(int WF, int variant);
+
+int filter_blocks_per_sm(int WF, int variant) {
+  const size_t smem = filter_smem_bytes(WF, variant);
+  switch (WF) {
+    case 1: return variant == kVariantTma ? filter_occupancy_one<1, false, kVariantTma>(smem) : filter_occupancy_one<1, false, kVariantLdg>(smem);
+    case 2: return variant == kVariantTma ? filter_occupancy_one<2, false, kVariantTma>(smem) : filter_occupancy_one<2, false, kVariantLdg>(smem);
+    case 4: return variant == kVariantTma ? filter_occupancy_one<4, false, kVariantTma>(smem) : filter_occupancy_one<4, false, kVariantLdg>(smem);
+    default: return 1;
+  }
+}
+
+size_t filter_smem_bytes(int WF, int variant) {
+  size_t tab = (size_t)256 * WF * sizeof(uint32_t);
+  if (variant == kVariantTma) return 1024 + (size_t)kRingBytes + tab;
+  return tab;
+}
+
+cudaError_t launch_filter(int WF, bool rev, int variant, const CUtensorMap* tmap, const ScanArgs& a,
+                          cudaStream_t stream) {
+  const size_t smem = filter_smem_bytes(WF, variant);
+#define SB_FCALL(WW)                                                                              \
+  if (variant == kVariantTma)                                                                     \
+    return rev ? launch_filter_one<WW, true, kVariantTma>(tmap, a, smem, stream)                  \
+               : launch_filter_one<WW, false, kVariantTma>(tmap, a, smem, stream);                \
+  else                                                                                            \
+    return rev ? launch_filter_one<WW, true, kVariantLdg>(tmap, a, smem, stream)                  \
+               : launch_filter_one<WW, false, kVariantLdg>(tmap, a, smem, stream);
+  switch (WF) {
+    case 1: SB_FCALL(1)
+    case 2: SB_FCALL(2)
+    case 4: SB_FCALL(4)
+    default: return cudaErrorInvalidValue;
+  }
+#undef SB_FCALL
+}
+
+cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, unsigned long long nhits,
+                          cudaStream_t stream) {
+  if (nhits == 0) return cudaSuccess;
+  const unsigned threads = 128;
+  const unsigned long long blocks = (nhits + threads - 1) / threads;
+  if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+  switch (W) {
+#define SB_VCALL(WW) case WW: verify_kernel<WW><<<(unsigned)blocks, threads, 0, stream>>>(a, rev_flags, nhits); break;
+    SB_VCALL(1) SB_VCALL(2) SB_VCALL(3) SB_VCALL(4) SB_VCALL(6) SB_VCALL(8) SB_VCALL(16) SB_VCALL(32)
+#undef SB_VCALL
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
 
 size_t scan_smem_bytes(int W, int variant, uint32_t nrows) {
   size_t eq = (size_t)nrows * W * sizeof(uint32_t);

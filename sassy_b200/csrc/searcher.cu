@@ -313,6 +313,12 @@ int sassy_gpu_set_variant(sassy_SearcherType* searcher, int variant) {
   return 0;
 }
 
+int sassy_gpu_set_filter(sassy_SearcherType* searcher, int mode) {
+  if (!searcher || mode < 0 || mode > 2) return 1;
+  searcher->s.engine().set_filter_mode(mode);
+  return 0;
+}
+
 int sassy_gpu_stats(const sassy_SearcherType* searcher, sassy_gpu_Stats* out) {
   if (!searcher || !out) return 1;
   const sb::SearchStats& st = const_cast<sassy_SearcherType*>(searcher)->s.engine().stats();
@@ -328,6 +334,12 @@ int sassy_gpu_stats(const sassy_SearcherType* searcher, sassy_gpu_Stats* out) {
   out->words = st.words;
   out->blocks_per_sm = st.blocks_per_sm;
   out->retries = st.retries;
+  out->filter_words = st.filter_words;
+  out->filter_ms = st.filter_ms;
+  out->verify_ms = st.verify_ms;
+  out->hits = st.hits;
+  out->filter_len = st.filter_len;
+  out->filter_fallback = st.filter_fallback;
   return 0;
 }
 

@@ -246,6 +246,11 @@ class Searcher:
         if self._lib.sassy_gpu_set_variant(self._h, {"tma": 0, "ldg": 1}[variant]) != 0:
             raise ValueError(variant)
 
+    def set_filter(self, mode: str):
+        """'off', 'auto' (default) or 'force' -- the exact piece prefilter in front of the scan."""
+        if self._lib.sassy_gpu_set_filter(self._h, {"off": 0, "auto": 1, "force": 2}[mode]) != 0:
+            raise ValueError(mode)
+
     def stats(self) -> dict:
         st = _native.GpuStats()
         self._lib.sassy_gpu_stats(self._h, ctypes.byref(st))

@@ -36,7 +36,7 @@ def _lib():
         lib.emu_search.restype = ctypes.c_void_p
         lib.emu_search.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int,
                                    ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                   ctypes.c_uint32, ctypes.c_int]
+                                   ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
         lib.emu_len.restype = ctypes.c_size_t
         lib.emu_len.argtypes = [ctypes.c_void_p]
         lib.emu_matches.restype = ctypes.POINTER(_GpuMatch)
@@ -51,23 +51,31 @@ def _lib():
         lib.emu_ltot.argtypes = [ctypes.c_void_p]
         lib.emu_rows.restype = ctypes.c_uint32
         lib.emu_rows.argtypes = [ctypes.c_void_p]
+        lib.emu_hits.restype = ctypes.c_uint64
+        lib.emu_hits.argtypes = [ctypes.c_void_p]
+        lib.emu_filter_words.restype = ctypes.c_int
+        lib.emu_filter_words.argtypes = [ctypes.c_void_p]
+        lib.emu_filter_len.restype = ctypes.c_int
+        lib.emu_filter_len.argtypes = [ctypes.c_void_p]
         lib.emu_free.argtypes = [ctypes.c_void_p]
         _LIB = lib
     return _LIB
 
 
 class EmuBackend:
-    def __init__(self, ltot: int = 0, bpw: int = 444):
+    def __init__(self, ltot: int = 0, bpw: int = 444, use_filter: int = 0):
         self.ltot = ltot
         self.bpw = bpw
+        self.use_filter = use_filter  # 0 full scan, 1 prefilter whenever possible, -1 engine's rule
         self.last_geom = None
+        self.last_filter = None
 
     def _run(self, alphabet, queries: Sequence[bytes], rev: Sequence[int], text: bytes, k: int, all_minima: bool,
              pos0: bool):
         lib = _lib()
         m = len(queries[0])
         r = lib.emu_search(PROFILE[alphabet.lower()], b"".join(queries), bytes(rev), len(queries), m, text,
-                           len(text), k, int(all_minima), int(pos0), self.ltot, self.bpw)
+                           len(text), k, int(all_minima), int(pos0), self.ltot, self.bpw, self.use_filter)
         assert r, "emu_search failed"
         try:
             n = lib.emu_len(r)
@@ -75,6 +83,7 @@ class EmuBackend:
             ops = lib.emu_ops(r)
             ow = lib.emu_ops_words(r)
             self.last_geom = (lib.emu_ltot(r), lib.emu_rows(r))
+            self.last_filter = (lib.emu_filter_words(r), lib.emu_filter_len(r), lib.emu_hits(r))
             out = []
             for i in range(n):
                 g = ms[i]

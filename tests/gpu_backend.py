@@ -9,8 +9,9 @@ import sassy_b200
 
 
 class GpuBackend:
-    def __init__(self, variant: str = "tma"):
+    def __init__(self, variant: str = "tma", filter_mode: str = "auto"):
         self.variant = variant
+        self.filter_mode = filter_mode
         self._cache = {}
 
     def _searcher(self, alphabet: str, rc: bool) -> sassy_b200.Searcher:
@@ -18,6 +19,7 @@ class GpuBackend:
         if key not in self._cache:
             s = sassy_b200.Searcher(alphabet, rc=rc)
             s.set_variant(self.variant)
+            s.set_filter(self.filter_mode)
             self._cache[key] = s
         return self._cache[key]
 

@@ -16,10 +16,13 @@ def key(m):
     return (m.pattern_idx, m.text_start, m.text_end, m.cost, m.strand, m.cigar)
 
 
-@pytest.fixture(scope="module", params=["tma", "ldg"])
+# (scan data path, prefilter mode): full scan only, prefilter whenever a piece layout exists,
+# and the production setting (prefilter when profitable) on the LDG data path.
+@pytest.fixture(scope="module", params=[("tma", "off"), ("tma", "force"), ("ldg", "auto"), ("ldg", "force")],
+                ids=lambda p: "-".join(p))
 def backend(request):
     from tests.gpu_backend import GpuBackend
-    return GpuBackend(request.param)
+    return GpuBackend(*request.param)
 
 
 @pytest.fixture(scope="module")
@@ -148,6 +151,40 @@ def test_gpu_candidate_overflow_retry(tma):
     ms = s.search(b"ACGTACGT", t, 0)  # one plateau -> a single local minimum at the text end
     assert [(m.text_start, m.text_end, m.cost) for m in ms] == [(n - 8, n, 0)]
     assert s.stats()["retries"] >= 1 and s.stats()["candidates"] == n - 7
+
+
+def test_prefilter_routes(tma):
+    """The production rule: prefilter for selective pieces, full scan otherwise, fallback on repeats."""
+    import sassy_b200
+    rng = random.Random(26)
+    s = sassy_b200.Searcher("dna", rc=True)
+    n = 1 << 22
+    table = bytes(b"ACGT"[c & 3] for c in range(256))
+    t = bytearray(rng.randbytes(n).translate(table))
+    p = rand_seq(rng, 20)
+    for pos in (0, 5, 1000, n // 2 - 3, n - 20, n - 25):
+        t[pos:pos + 20] = p
+    t = bytes(t)
+    want = oracle.search("dna", p, t, 2, rc=True)
+    got = s.search(p, t, 2)
+    st = s.stats()
+    assert st["filter_words"] == 1 and st["filter_fallback"] == 0 and st["hits"] > 0
+    assert [key(m) for m in got] == [key(m) for m in want] and len(got) >= 6
+    s.set_filter("off")
+    assert [key(m) for m in s.search(p, t, 2)] == [key(m) for m in got]
+    assert s.stats()["filter_words"] == 0
+    s.set_filter("auto")
+    # k too large for selective pieces -> planned off
+    s.search(p, t[:100000], 6)
+    assert s.stats()["filter_words"] == 0
+    # repetitive text: every word is a hit -> fallback to the full scan, same answer
+    rep = (p * (200000 // 20))
+    a = s.search(p, rep, 1)
+    st = s.stats()
+    assert st["filter_fallback"] == 1
+    s.set_filter("off")
+    b = s.search(p, rep, 1)
+    assert [key(m) for m in a] == [key(m) for m in b] and len(a) > 1000
 
 
 def test_c_abi_search_symbol():

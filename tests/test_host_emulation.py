@@ -69,6 +69,49 @@ def test_emu_v2_fuzz():
             assert list(map(key, got)) == list(map(key, want))  # same order: query slot, then end
 
 
+@pytest.mark.parametrize("mode", [1, -1])
+def test_emu_prefilter_fuzz(mode):
+    """Exact piece prefilter + re-scan of the hit neighbourhoods == full scan == oracle."""
+    rng = random.Random(14)
+    used = 0
+    for it in range(150):
+        m = rng.choice([2, 5, 12, 20, 23, 33, 64, 100])
+        n = rng.randrange(0, 1500)
+        k = rng.randrange(0, max(1, m // 4) + 1)
+        p, t = planted(rng, m, max(n, 1), k)
+        t = t[:n]
+        if rng.random() < 0.1:
+            t, p = b"A" * n, b"A" * m
+        alphabet = rng.choice(["dna", "iupac"])
+        for allm in (False, True):
+            want = oracle.search(alphabet, p, t, k, rc=True, all_minima=allm)
+            b = EmuBackend(ltot=rng.choice([0, 64, 128, 192]), use_filter=mode)
+            got = b.search(alphabet, p, t, k, rc=True, all_minima=allm)
+            assert list(map(key, got)) == list(map(key, want)), (alphabet, p, t, k, allm, b.last_filter)
+            used += b.last_filter[0] > 0
+    assert used > 50
+
+
+def test_emu_prefilter_encoded():
+    rng = random.Random(15)
+    for it in range(40):
+        m = rng.choice([16, 23, 32, 40])
+        n = rng.randrange(1, 1200)
+        k = rng.randrange(0, 3)
+        pats = []
+        t = bytearray(rand_seq(rng, n))
+        for _ in range(rng.randrange(1, 4)):
+            p, tt = planted(rng, m, n, k)
+            pats.append(p)
+            pos = rng.randrange(0, max(1, n - m))
+            t[pos:pos + m] = tt[pos:pos + m]
+        t = bytes(t[:n])
+        want = oracle.search_encoded("iupac", pats, t, k, rc=True)
+        b = EmuBackend(use_filter=1)
+        got = b.search_encoded("iupac", pats, t, k, rc=True)
+        assert list(map(key, got)) == list(map(key, want)) and b.last_filter[0] > 0
+
+
 def test_emu_long_pattern_words():
     # every supported word count, incl. the padded ones (W = 6, 8, 16, 32)
     rng = random.Random(13)
