@@ -76,7 +76,7 @@ void filter_rows(const ScanArgs& a, const uint32_t* feq_q, uint32_t qs) {
         const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
         uint32_t x[4] = {0, 0, 0, 0};
         if (valid) memcpy(x, a.text + stage_idx + 16u * c, 16);
-        filter16<WF, REV>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+        filter16<WF, REV>(s, x, stage_idx + 16u * c, a, eqt, HitQueue{nullptr, nullptr}, qs, own);
       }
     }
   }

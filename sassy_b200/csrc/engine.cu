@@ -281,7 +281,11 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     for (uint32_t q = 0; q < nq; q++) build_filter_table(profile_, fp, queries[q].bytes, &h_feq_[(size_t)q * 256 * fp.WF]);
     feq_.ensure(h_feq_.size() * sizeof(uint32_t));
     SB_CUDA(cudaMemcpyAsync(feq_.p, h_feq_.data(), h_feq_.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
-    if (hit_cap_ == 0) hit_cap_ = 4ull << 20;
+    {  // room for 2x the expected number of hits (uniform text), within 8 M .. 128 M entries
+      const double expect = 2.0 * fp.rate * (double)n * nq / 4.0 * 4.0;
+      uint64_t want = (uint64_t)std::min(std::max(expect, 8.0 * 1048576.0), 128.0 * 1048576.0);
+      if (want > hit_cap_) hit_cap_ = want;
+    }
     hits_.ensure(hit_cap_ * sizeof(uint64_t));
     const unsigned long long zero = 0;
     SB_CUDA(cudaMemcpyAsync(d_hit_count, &zero, sizeof zero, cudaMemcpyHostToDevice, stream_));

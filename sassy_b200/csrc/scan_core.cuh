@@ -339,25 +339,43 @@ SB_HD void load_feq(uint32_t (&eq)[WF], const EqTab& t, uint32_t x, int b) {
 #endif
 }
 
+// Per-warp staging queue for hits (shared memory on the device; absent on the host).
+// A single global counter cannot absorb millions of atomics per millisecond, so hits
+// are batched: one global atomic per flush of up to kHitQueueCap hits.
+constexpr uint32_t kHitQueueCap = 128;
+struct HitQueue {
+  uint64_t* q;   // [kHitQueueCap], or nullptr: write straight to the global list
+  uint32_t* n;
+};
+
 // Deliberately not inlined: hits are rare, and the ownership / text-end tests must not be
 // hoisted into the per-word fast path.
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #endif
-static void emit_hit(const ScanArgs& a, uint32_t qs, uint64_t base_idx, bool own) {
+static void emit_hit(const ScanArgs& a, HitQueue hq, uint32_t qs, uint64_t base_idx, bool own) {
   if (!own || base_idx >= a.n) return;
+  const uint64_t key = cand_key(qs, base_idx >> 2);
 #if defined(__CUDA_ARCH__)
+  if (hq.q) {
+    const uint32_t pos = atomicAdd(hq.n, 1u);
+    if (pos < kHitQueueCap) {
+      hq.q[pos] = key;
+      return;
+    }
+  }
   const unsigned long long i = atomicAdd(a.hit_count, 1ull);
 #else
+  (void)hq;
   const unsigned long long i = (*a.hit_count)++;
 #endif
-  if (i < a.hit_cap) a.hit_keys[i] = cand_key(qs, base_idx >> 2);
+  if (i < a.hit_cap) a.hit_keys[i] = key;
 }
 
 // 16 text bytes through the automaton; a hit is recorded per 4-byte text word.
 template <int WF, bool REV>
 SB_HD void filter16(FLane<WF>& s, const uint32_t (&x)[4], uint64_t base_idx, const ScanArgs& a, const EqTab& feq,
-                    uint32_t qs, bool own) {
+                    const HitQueue& hq, uint32_t qs, bool own) {
 #pragma unroll
   for (int ww = 0; ww < 4; ww++) {
     const int w4 = REV ? 3 - ww : ww;
@@ -372,7 +390,7 @@ SB_HD void filter16(FLane<WF>& s, const uint32_t (&x)[4], uint64_t base_idx, con
     uint32_t hit = 0;
 #pragma unroll
     for (int w = 0; w < WF; w++) hit |= s.st[w] & s.delay[w];
-    if (hit != 0) emit_hit(a, qs, base_idx + 4u * w4, own);
+    if (hit != 0) emit_hit(a, hq, qs, base_idx + 4u * w4, own);
   }
 }
 

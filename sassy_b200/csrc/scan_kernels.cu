@@ -185,13 +185,37 @@ __global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
       });
 }
 
+// Moves a warp's staged hits to the global list with one global atomic.
+__device__ __forceinline__ void flush_hits(const ScanArgs& a, const HitQueue& hq, uint32_t lane) {
+  __syncwarp();
+  const uint32_t staged = *hq.n;
+  const uint32_t cnt = staged < kHitQueueCap ? staged : kHitQueueCap;  // the excess went straight to the list
+  if (cnt) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(a.hit_count, (unsigned long long)cnt);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    for (uint32_t i = lane; i < cnt; i += 32)
+      if (base + i < a.hit_cap) a.hit_keys[base + i] = hq.q[i];
+  }
+  __syncwarp();
+  if (lane == 0) *hq.n = 0;
+  __syncwarp();
+}
+
 // Prefilter: Shift-And automaton over k+1 exact pieces (scan_core.cuh); emits the text
 // words in which a piece occurrence ends.
 template <int WF, bool REV, int VARIANT>
 __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
     filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a) {
+  __shared__ uint64_t hit_q[kWarpsPerBlock][kHitQueueCap];
+  __shared__ uint32_t hit_n[kWarpsPerBlock];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t q = blockIdx.x % a.nq;
   const uint32_t qs = a.qs_base + q;
+  HitQueue hq;
+  hq.q = hit_q[warp];
+  hq.n = &hit_n[warp];
+  if (lane == 0) hit_n[warp] = 0;  // ordered before any use by the __syncthreads in row_pipeline
   EqTab eqt;
   eqt.rowbytes = (uint32_t)WF * 4u;
   FLane<WF> s;
@@ -203,9 +227,12 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
                                  const int c = REV ? (kChunks - 1 - cc) : cc;
                                  const uint4 v = chunk(c);
                                  const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-                                 filter16<WF, REV>(s, x, stage_idx + 16u * c, a, eqt, qs, own);
+                                 filter16<WF, REV>(s, x, stage_idx + 16u * c, a, eqt, hq, qs, own);
                                }
+                               __syncwarp();
+                               if (*hq.n >= kHitQueueCap / 2) flush_hits(a, hq, lane);  // warp-uniform
                              });
+  flush_hits(a, hq, lane);
 }
 
 // One thread per prefilter hit: exact recurrences over the hit's neighbourhood.
