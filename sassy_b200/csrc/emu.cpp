@@ -72,12 +72,14 @@ void filter_rows(const ScanArgs& a, const uint32_t* feq_q, uint32_t qs) {
       stage_coord<REV>(a.g, it, (int64_t)row, r, col, own);
       const uint64_t stage_idx = (uint64_t)(r * (int64_t)a.g.ltot + (int64_t)col);
       const bool valid = r >= 0 && r < (int64_t)a.g.rows;
+      uint32_t mask = 0;
       for (int cc = 0; cc < kStageBytes / 16; cc++) {
         const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
         uint32_t x[4] = {0, 0, 0, 0};
         if (valid) memcpy(x, a.text + stage_idx + 16u * c, 16);
-        filter16<WF, REV>(s, x, stage_idx + 16u * c, a, eqt, HitQueue{nullptr, nullptr}, qs, own);
+        if (filter16<WF, REV>(s, x, eqt)) mask |= 1u << c;
       }
+      if (mask) emit_stage_hits(a, HitQueue{nullptr, nullptr}, qs, stage_idx, mask, own);
     }
   }
 }
@@ -165,7 +167,7 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   if (n) memcpy(padded.data(), text, n);
 
   // with the prefilter every hit word may report up to 4+m+k positions (overlapping windows)
-  const uint64_t cap = (uint64_t)nq * (n / 4 + 2) * (uint64_t)(use_filter ? 5 + m + k : 4) + 64;
+  const uint64_t cap = (uint64_t)nq * (n / 4 + 2) * (uint64_t)(use_filter ? 8 + (m + k) / 4 : 4) + 64;
   std::vector<uint64_t> keys(cap);
   std::vector<uint32_t> cost(cap);
   unsigned long long count = 0;
@@ -194,14 +196,14 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   std::vector<const uint8_t*> qptr(nq);
   for (uint32_t q = 0; q < nq; q++) qptr[q] = queries + (size_t)q * m;
   FilterPlan fp;
-  if (use_filter != 0) fp = plan_filter(profile, qptr.data(), nq, m, k, use_filter > 0 ? 1e30 : 0.04);
+  if (use_filter != 0) fp = plan_filter(profile, qptr.data(), nq, m, k, use_filter > 0 ? 1e30 : 0.85);
   res->hits = 0;
   res->filter_words = fp.enabled ? fp.WF : 0;
   res->filter_len = fp.enabled ? fp.L : 0;
   if (n > 0 && fp.enabled) {
     std::vector<uint32_t> feq((size_t)nq * 256 * fp.WF);
     for (uint32_t q = 0; q < nq; q++) build_filter_table(profile, fp, qptr[q], &feq[(size_t)q * 256 * fp.WF]);
-    std::vector<uint64_t> hits((size_t)nq * (n / 4 + 2) + 16);
+    std::vector<uint64_t> hits((size_t)nq * (n / kHitChars + 2) + 16);
     unsigned long long nhits = 0;
     ScanArgs f = a;
     f.g.nwarm = 1;

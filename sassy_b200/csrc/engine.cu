@@ -274,7 +274,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   if (n > 0 && filter_mode_ != 0) {
     std::vector<const uint8_t*> qptr(nq);
     for (uint32_t q = 0; q < nq; q++) qptr[q] = queries[q].bytes;
-    fp = plan_filter(profile_, qptr.data(), nq, m, k, filter_mode_ == 2 ? 1e30 : 0.04);
+    fp = plan_filter(profile_, qptr.data(), nq, m, k, filter_mode_ == 2 ? 1e30 : 0.85);
   }
   if (fp.enabled) {
     h_feq_.resize((size_t)nq * 256 * fp.WF);

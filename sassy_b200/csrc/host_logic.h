@@ -95,21 +95,26 @@ inline ScanGeom choose_geom(uint64_t n, int m, int k, uint32_t nq, int bpw) {
 
 // ---------------------------------------------------------------------------
 // Exact piece prefilter: layout and tables (see scan_core.cuh).
+constexpr int kMaxPieces = 40;  // >= kMaxFilterWords * (32 / (1 + kFilterDelay))
+
+struct FilterPiece {
+  int off;   // first pattern position of the piece
+  int len;   // characters
+  int word;  // automaton word
+  int bit;   // first automaton bit; bits [bit, bit+len) then kFilterDelay delay bits
+};
+
 struct FilterPlan {
   bool enabled = false;
   int WF = 0;        // automaton words (1, 2 or 4)
-  int L = 0;         // piece length
+  int L = 0;         // shortest piece
   int npieces = 0;   // k + 1
-  int stride = 0;    // distance between piece starts in the pattern
-  double rate = 0;   // expected piece hits per text position (uniform ACGT text), max over queries
+  FilterPiece piece[kMaxPieces];
+  double rate = 0;   // expected piece occurrences per text position (uniform ACGT text), max over queries
+  double cost = 0;   // modelled cost relative to the full scan (1.0)
   uint32_t finit[kMaxFilterWords] = {0, 0, 0, 0};
   uint32_t fdelay[kMaxFilterWords] = {0, 0, 0, 0};
 };
-
-inline int piece_word(const FilterPlan& f, int p) { return p / ((f.npieces + f.WF - 1) / f.WF); }
-inline int piece_bit(const FilterPlan& f, int p) {
-  return (p % ((f.npieces + f.WF - 1) / f.WF)) * (f.L + kFilterDelay);
-}
 
 // Probability that a uniformly random ACGT character matches pattern byte c.
 inline double match_prob(int profile, uint8_t c) {
@@ -123,48 +128,72 @@ inline double match_prob(int profile, uint8_t c) {
   return 0.25;  // Dna classes; Ascii: assumed, the run-time hit counter guards the assumption
 }
 
-// Chooses the smallest automaton for which the expected re-scan work stays small.
-inline FilterPlan plan_filter(int profile, const uint8_t* const* queries, size_t nq, int m, int k,
-                              double max_frac = 0.04) {
-  FilterPlan best;
+// Lays k+1 disjoint pieces of the pattern out over WF automaton words: the pattern is cut
+// into k+1 shares (lengths differ by at most 1), the shares are spread evenly over the words,
+// and every piece is the prefix of its share that fits its word (32 / pieces_in_word - 3 bits).
+inline bool layout_pieces(FilterPlan& f, int m, int k, int WF) {
   const int np = k + 1;
-  if (k < 0 || np > m || nq == 0) return best;
+  if (np > m || np > kMaxPieces) return false;
+  f.WF = WF;
+  f.npieces = np;
+  f.L = 1 << 30;
+  for (int w = 0; w < kMaxFilterWords; w++) f.finit[w] = f.fdelay[w] = 0;
+  int p = 0, off = 0;
+  for (int w = 0; w < WF; w++) {
+    const int cnt = np / WF + (w < np % WF ? 1 : 0);  // pieces in this word
+    if (cnt == 0) continue;
+    const int room = 32 / cnt - kFilterDelay;
+    if (room < 1) return false;
+    int bit = 0;
+    for (int c = 0; c < cnt; c++, p++) {
+      const int share = m / np + (p < m % np ? 1 : 0);
+      FilterPiece& pc = f.piece[p];
+      pc.off = off;
+      pc.len = share < room ? share : room;
+      pc.word = w;
+      pc.bit = bit;
+      f.finit[w] |= 1u << bit;
+      f.fdelay[w] |= 1u << (bit + pc.len - 1);  // the piece's last bit ...
+      for (int d = 0; d < kFilterDelay; d++) f.fdelay[w] |= 1u << (bit + pc.len + d);  // ... and its delay line
+      bit += pc.len + kFilterDelay;
+      off += share;
+      if (pc.len < f.L) f.L = pc.len;
+    }
+  }
+  return true;
+}
+
+// Chooses the automaton width with the lowest modelled cost; enabled when that is below
+// `max_cost` times the cost of the full scan.  Model (per text character, in units of one
+// scan word-step): scan = W; prefilter = 0.35 * WF + 0.05 (measured ratio of the two
+// kernels' instruction streams); re-scan = occurrences * window * W * 3 (one thread per hit
+// is about 3x less efficient than the streaming scan).
+inline FilterPlan plan_filter(int profile, const uint8_t* const* queries, size_t nq, int m, int k,
+                              double max_cost = 0.85) {
+  FilterPlan best;
+  if (k < 0 || k + 1 > m || nq == 0) return best;
+  const int W = (m + 31) / 32;
   const double window = 2.0 * (m + k) + 4.0;
   const int wopts[] = {1, 2, 4};
+  bool have = false;
   for (int WF : wopts) {
-    const int ppw = (np + WF - 1) / WF;  // pieces per word
-    int L = 32 / ppw - kFilterDelay;
-    const int stride = m / np;
-    if (L > stride) L = stride;
-    if (L < 1) continue;
     FilterPlan f;
-    f.WF = WF, f.L = L, f.npieces = np, f.stride = stride;
+    if (!layout_pieces(f, m, k, WF)) continue;
     double worst = 0;
     for (size_t q = 0; q < nq; q++) {
       double rate = 0;
-      for (int p = 0; p < np; p++) {
+      for (int p = 0; p < f.npieces; p++) {
         double pr = 1;
-        for (int j = 0; j < L; j++) pr *= match_prob(profile, queries[q][p * stride + j]);
+        for (int j = 0; j < f.piece[p].len; j++) pr *= match_prob(profile, queries[q][f.piece[p].off + j]);
         rate += pr;
       }
       if (rate > worst) worst = rate;
     }
     f.rate = worst;
-    // re-scan fraction of the text (per query) must stay below 4 %: then the filter pass
-    // (about a quarter of the cost of the full recurrences per character and word) dominates
-    if (worst * window <= max_frac) {
-      for (int p = 0; p < np; p++) {
-        const int w = piece_word(f, p), b = piece_bit(f, p);
-        f.finit[w] |= 1u << b;
-        f.fdelay[w] |= 1u << (b + L - 1);  // the piece's last bit ...
-        for (int d = 0; d < kFilterDelay; d++) f.fdelay[w] |= 1u << (b + L + d);  // ... and its delay line
-      }
-      f.enabled = true;
-      return f;
-    }
-    best = f;  // remember the last candidate for diagnostics
+    f.cost = (0.35 * WF + 0.05 + worst * window * W * 3.0) / (double)W;
+    if (!have || f.cost < best.cost) best = f, have = true;
   }
-  best.enabled = false;
+  best.enabled = have && best.cost <= max_cost;
   return best;
 }
 
@@ -177,18 +206,18 @@ inline void build_filter_table(int profile, const FilterPlan& f, const uint8_t* 
     uint32_t* e = tab + (size_t)byte * f.WF;
     const int row = (int)(((uint32_t)byte >> pp.sh0) & (pp.msk0 & 0xFFu));
     for (int p = 0; p < f.npieces; p++) {
-      const int w = piece_word(f, p), b = piece_bit(f, p);
-      for (int j = 0; j < f.L; j++) {
-        const uint8_t pc = pat[p * f.stride + j];
+      const FilterPiece& pc = f.piece[p];
+      for (int j = 0; j < pc.len; j++) {
+        const uint8_t ch = pat[pc.off + j];
         bool match;
         switch (profile) {
-          case kDna: match = row_matches<kDna>(pc, row); break;
-          case kIupac: match = row_matches<kIupac>(pc, row); break;
-          default: match = row_matches<kAscii>(pc, row); break;
+          case kDna: match = row_matches<kDna>(ch, row); break;
+          case kIupac: match = row_matches<kIupac>(ch, row); break;
+          default: match = row_matches<kAscii>(ch, row); break;
         }
-        if (match) e[w] |= 1u << (b + j);
+        if (match) e[pc.word] |= 1u << (pc.bit + j);
       }
-      for (int d = 0; d < kFilterDelay; d++) e[w] |= 1u << (b + f.L + d);
+      for (int d = 0; d < kFilterDelay; d++) e[pc.word] |= 1u << (pc.bit + pc.len + d);
     }
   }
 }

@@ -69,7 +69,7 @@ struct ScanArgs {
   const uint32_t* feq;      // [nq][256][WF] filter automaton masks, indexed by the raw text byte
   uint32_t finit[kMaxFilterWords];   // first bit of every piece
   uint32_t fdelay[kMaxFilterWords];  // delay-line bits behind every piece
-  uint64_t* hit_keys;       // (query slot << 40) | forward index of the hit's text word / 4
+  uint64_t* hit_keys;       // (query slot << 40) | forward index of the hit's 16-byte text chunk / 16
   unsigned long long* hit_count;
   uint64_t hit_cap;
 };
@@ -348,34 +348,45 @@ struct HitQueue {
   uint32_t* n;
 };
 
+// A hit = a 16-byte text chunk in which some piece occurrence ends.
+constexpr int kHitChars = 16;
+
+// Reports the hit chunks of one 64-byte stage (bit c of `mask` = chunk c, forward order).
 // Deliberately not inlined: hits are rare, and the ownership / text-end tests must not be
-// hoisted into the per-word fast path.
+// hoisted into the per-character fast path.
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #endif
-static void emit_hit(const ScanArgs& a, HitQueue hq, uint32_t qs, uint64_t base_idx, bool own) {
-  if (!own || base_idx >= a.n) return;
-  const uint64_t key = cand_key(qs, base_idx >> 2);
+static void emit_stage_hits(const ScanArgs& a, HitQueue hq, uint32_t qs, uint64_t stage_idx, uint32_t mask,
+                            bool own) {
+  if (!own) return;
+  for (int c = 0; c < kStageBytes / kHitChars; c++) {
+    if (!((mask >> c) & 1u)) continue;
+    const uint64_t base_idx = stage_idx + (uint64_t)(kHitChars * c);
+    if (base_idx >= a.n) continue;
+    const uint64_t key = cand_key(qs, base_idx / kHitChars);
 #if defined(__CUDA_ARCH__)
-  if (hq.q) {
-    const uint32_t pos = atomicAdd(hq.n, 1u);
-    if (pos < kHitQueueCap) {
-      hq.q[pos] = key;
-      return;
+    if (hq.q) {
+      const uint32_t pos = atomicAdd(hq.n, 1u);
+      if (pos < kHitQueueCap) {
+        hq.q[pos] = key;
+        continue;
+      }
     }
-  }
-  const unsigned long long i = atomicAdd(a.hit_count, 1ull);
+    const unsigned long long i = atomicAdd(a.hit_count, 1ull);
 #else
-  (void)hq;
-  const unsigned long long i = (*a.hit_count)++;
+    (void)hq;
+    const unsigned long long i = (*a.hit_count)++;
 #endif
-  if (i < a.hit_cap) a.hit_keys[i] = key;
+    if (i < a.hit_cap) a.hit_keys[i] = key;
+  }
 }
 
-// 16 text bytes through the automaton; a hit is recorded per 4-byte text word.
+// 16 text bytes through the automaton.  Returns non-zero iff a piece occurrence ended
+// inside the chunk (the hit mask is sampled after every text word, see above).
 template <int WF, bool REV>
-SB_HD void filter16(FLane<WF>& s, const uint32_t (&x)[4], uint64_t base_idx, const ScanArgs& a, const EqTab& feq,
-                    const HitQueue& hq, uint32_t qs, bool own) {
+SB_HD uint32_t filter16(FLane<WF>& s, const uint32_t (&x)[4], const EqTab& feq) {
+  uint32_t acc = 0;
 #pragma unroll
   for (int ww = 0; ww < 4; ww++) {
     const int w4 = REV ? 3 - ww : ww;
@@ -387,27 +398,26 @@ SB_HD void filter16(FLane<WF>& s, const uint32_t (&x)[4], uint64_t base_idx, con
 #pragma unroll
       for (int w = 0; w < WF; w++) s.st[w] = ((s.st[w] << 1) | s.init[w]) & eq[w];
     }
-    uint32_t hit = 0;
 #pragma unroll
-    for (int w = 0; w < WF; w++) hit |= s.st[w] & s.delay[w];
-    if (hit != 0) emit_hit(a, hq, qs, base_idx + 4u * w4, own);
+    for (int w = 0; w < WF; w++) acc |= s.st[w] & s.delay[w];
   }
+  return acc;
 }
 
 // Re-scan of the neighbourhood of one hit with the exact recurrences.  The hit
-// is the text word at forward index 4*word; in scan direction it starts at G0.
-// A piece occurrence ending inside the word implies end positions in
-// (G0, G0 + 4 + m + k]; starting m+k characters before G0 makes them exact.
+// is the text chunk at forward index 16*unit; in scan direction it starts at G0.
+// A piece occurrence ending inside the chunk implies end positions in
+// (G0, G0 + 16 + m + k]; starting m+k characters before G0 makes them exact.
 template <int W>
 SB_HD void verify_hit(const ScanArgs& a, const uint32_t* eq /*[nrows][W] of this query*/, uint32_t qs, bool rev,
-                      uint64_t word) {
+                      uint64_t unit) {
   const int64_t n = (int64_t)a.n;
-  const int64_t base = (int64_t)(word << 2);
-  const int64_t g0 = rev ? n - 4 - base : base;  // may be negative for the word straddling the text end
+  const int64_t base = (int64_t)(unit * kHitChars);
+  const int64_t g0 = rev ? n - kHitChars - base : base;  // may be negative for the chunk straddling the text end
   const int64_t span = (int64_t)a.m + (int64_t)a.k;
   int64_t w0 = g0 - span;
   if (w0 < 0) w0 = 0;
-  int64_t end = g0 + 4 + span;
+  int64_t end = g0 + kHitChars + span;
   if (end > n) end = n;
   const int64_t emit_from = g0 < 0 ? 0 : g0;
   Lane<W> s;

@@ -222,12 +222,22 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
   flane_reset<WF>(s, a);
   row_pipeline<REV, VARIANT>(tmap, a, a.feq + (size_t)q * 256 * WF, 256 * WF, eqt,
                              [&](uint64_t stage_idx, bool own, auto chunk) {
+                               uint32_t acc[kChunks];
 #pragma unroll
                                for (int cc = 0; cc < kChunks; cc++) {
                                  const int c = REV ? (kChunks - 1 - cc) : cc;
                                  const uint4 v = chunk(c);
                                  const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-                                 filter16<WF, REV>(s, x, stage_idx + 16u * c, a, eqt, hq, qs, own);
+                                 acc[c] = filter16<WF, REV>(s, x, eqt);
+                               }
+                               uint32_t any = 0;
+#pragma unroll
+                               for (int c = 0; c < kChunks; c++) any |= acc[c];
+                               if (any) {  // rare: some piece occurrence ended in this stage
+                                 uint32_t mask = 0;
+#pragma unroll
+                                 for (int c = 0; c < kChunks; c++) mask |= acc[c] ? (1u << c) : 0u;
+                                 emit_stage_hits(a, hq, qs, stage_idx, mask, own);
                                }
                                __syncwarp();
                                if (*hq.n >= kHitQueueCap / 2) flush_hits(a, hq, lane);  // warp-uniform
@@ -235,15 +245,72 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
   flush_hits(a, hq, lane);
 }
 
-// One thread per prefilter hit: exact recurrences over the hit's neighbourhood.
+// One thread per prefilter hit: exact recurrences over the hit's neighbourhood
+// (same window and emission rule as verify_hit in scan_core.cuh, which the host emulator
+// runs).  The window is fetched as aligned 16-byte chunks, one chunk ahead of the
+// computation, after an L2 prefetch of the whole window: thousands of resident threads
+// each touching 2-3 lines would otherwise evict each other's lines from L1 between two
+// consecutive byte loads.
 template <int W>
-__global__ void verify_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags,
-                              unsigned long long nhits) {
+__global__ void __launch_bounds__(128)
+    verify_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags,
+                  unsigned long long nhits) {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nhits) return;
   const uint64_t key = a.hit_keys[i];
   const uint32_t qs = key_qs(key);
-  verify_hit<W>(a, a.eq + (size_t)qs * a.nrows * W, qs, rev_flags[qs] != 0, key_pos(key));
+  const bool rev = rev_flags[qs] != 0;
+  const uint32_t* __restrict__ eq = a.eq + (size_t)qs * a.nrows * W;
+
+  const int64_t n = (int64_t)a.n;
+  const int64_t base = (int64_t)(key_pos(key) * kHitChars);
+  const int64_t g0 = rev ? n - kHitChars - base : base;
+  const int64_t span = (int64_t)a.m + (int64_t)a.k;
+  int64_t w0 = g0 - span;
+  if (w0 < 0) w0 = 0;
+  int64_t end = g0 + kHitChars + span;
+  if (end > n) end = n;
+  const int64_t emit_from = g0 < 0 ? 0 : g0;
+  if (end <= w0) return;
+  // forward byte range [lo, hi) of the window and its aligned 16-byte chunks
+  const int64_t lo = rev ? n - end : w0, hi = rev ? n - w0 : end;
+  const int64_t c_lo = lo >> 4, c_hi = (hi + 15) >> 4;  // chunk indices [c_lo, c_hi)
+  const uint4* __restrict__ chunks = reinterpret_cast<const uint4*>(a.text);
+  for (int64_t c = c_lo; c < c_hi; c += 2)  // one prefetch per 32-byte sector
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(chunks + c));
+
+  Lane<W> s;
+  lane_reset<W>(s, a.m);
+  const int64_t nchunks = c_hi - c_lo;
+  int64_t c = rev ? c_hi - 1 : c_lo;  // chunks in scan order
+  uint4 cur = __ldg(chunks + c);
+  for (int64_t t = 0; t < nchunks; t++) {
+    const int64_t cn = rev ? c - 1 : c + 1;
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (t + 1 < nchunks) nxt = __ldg(chunks + cn);
+    const uint32_t words[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const int j = rev ? 3 - jj : jj;
+      const uint32_t pre = (words[j] >> a.sh0) & a.msk0;
+#pragma unroll
+      for (int bb = 0; bb < 4; bb++) {
+        const int b = rev ? 3 - bb : bb;
+        const int64_t fidx = (c << 4) + 4 * j + b;
+        const int64_t idx = rev ? n - 1 - fidx : fidx;  // scan-direction index
+        if (idx >= w0 && idx < end) {
+          const uint32_t row = (pre >> (8 * b)) & 0xFFu;
+          myers_step<W>(s, eq + row * W);
+          if (idx >= emit_from) {
+            const int score = lane_score<W>(s);
+            if (score <= a.k) emit_candidate(a, qs, (uint64_t)idx + 1, score);
+          }
+        }
+      }
+    }
+    cur = nxt;
+    c = cn;
+  }
 }
 
 template <int W, bool REV, int VARIANT>
