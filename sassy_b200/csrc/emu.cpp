@@ -55,7 +55,7 @@ void scan_rows(const ScanArgs& a, const uint32_t* eq_q, uint32_t qs) {
 }
 
 template <int WF, bool REV>
-void filter_rows(const ScanArgs& a, const uint32_t* feq_q, uint32_t qs) {
+void filter_rows(const ScanArgs& a, const uint32_t* feq_q, uint32_t qs, bool pair) {
   EqTab eqt;
   eqt.p = feq_q;
   eqt.saddr = 0;
@@ -77,7 +77,7 @@ void filter_rows(const ScanArgs& a, const uint32_t* feq_q, uint32_t qs) {
         const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
         uint32_t x[4] = {0, 0, 0, 0};
         if (valid) memcpy(x, a.text + stage_idx + 16u * c, 16);
-        if (filter16<WF, REV>(s, x, eqt)) mask |= 1u << c;
+        if (pair ? filter16_pair<WF, REV>(s, x, eqt) : filter16<WF, REV>(s, x, eqt)) mask |= 1u << c;
       }
       if (mask) emit_stage_hits(a, HitQueue{nullptr, nullptr}, qs, stage_idx, mask, own);
     }
@@ -85,11 +85,11 @@ void filter_rows(const ScanArgs& a, const uint32_t* feq_q, uint32_t qs) {
 }
 
 template <bool REV>
-void filter_dispatch(int WF, const ScanArgs& a, const uint32_t* feq_q, uint32_t qs) {
+void filter_dispatch(int WF, const ScanArgs& a, const uint32_t* feq_q, uint32_t qs, bool pair) {
   switch (WF) {
-    case 1: filter_rows<1, REV>(a, feq_q, qs); break;
-    case 2: filter_rows<2, REV>(a, feq_q, qs); break;
-    case 4: filter_rows<4, REV>(a, feq_q, qs); break;
+    case 1: filter_rows<1, REV>(a, feq_q, qs, pair); break;
+    case 2: filter_rows<2, REV>(a, feq_q, qs, pair); break;
+    case 4: filter_rows<4, REV>(a, feq_q, qs, pair); break;
     default: abort();
   }
 }
@@ -201,8 +201,15 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   res->filter_words = fp.enabled ? fp.WF : 0;
   res->filter_len = fp.enabled ? fp.L : 0;
   if (n > 0 && fp.enabled) {
-    std::vector<uint32_t> feq((size_t)nq * 256 * fp.WF);
-    for (uint32_t q = 0; q < nq; q++) build_filter_table(profile, fp, qptr[q], &feq[(size_t)q * 256 * fp.WF]);
+    const bool pair = profile == kDna;
+    const size_t tab_words = pair ? (size_t)kPairTableWords * fp.WF : (size_t)256 * fp.WF;
+    std::vector<uint32_t> feq((size_t)nq * tab_words + 4);
+    for (uint32_t q = 0; q < nq; q++) {
+      if (pair)
+        build_pair_table(fp, qptr[q], &feq[q * tab_words]);
+      else
+        build_filter_table(profile, fp, qptr[q], &feq[q * tab_words]);
+    }
     std::vector<uint64_t> hits((size_t)nq * (n / kHitChars + 2) + 16);
     unsigned long long nhits = 0;
     ScanArgs f = a;
@@ -212,11 +219,11 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
     f.hit_count = &nhits;
     f.hit_cap = hits.size();
     for (uint32_t q = 0; q < nq; q++) {
-      const uint32_t* feq_q = &feq[(size_t)q * 256 * fp.WF];
+      const uint32_t* feq_q = &feq[q * tab_words];
       if (rev[q])
-        filter_dispatch<true>(fp.WF, f, feq_q, q);
+        filter_dispatch<true>(fp.WF, f, feq_q, q, pair);
       else
-        filter_dispatch<false>(fp.WF, f, feq_q, q);
+        filter_dispatch<false>(fp.WF, f, feq_q, q, pair);
     }
     res->hits = nhits;
     for (unsigned long long h = 0; h < nhits; h++) {

@@ -277,8 +277,16 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     fp = plan_filter(profile_, qptr.data(), nq, m, k, filter_mode_ == 2 ? 1e30 : 0.85);
   }
   if (fp.enabled) {
-    h_feq_.resize((size_t)nq * 256 * fp.WF);
-    for (uint32_t q = 0; q < nq; q++) build_filter_table(profile_, fp, queries[q].bytes, &h_feq_[(size_t)q * 256 * fp.WF]);
+    // Dna: two characters per step through the class-pair table; others: byte-indexed table
+    const bool pair = profile_ == kDna;
+    const size_t tab_words = pair ? (size_t)kPairTableWords * fp.WF : (size_t)256 * fp.WF;
+    h_feq_.resize((size_t)nq * tab_words);
+    for (uint32_t q = 0; q < nq; q++) {
+      if (pair)
+        build_pair_table(fp, queries[q].bytes, &h_feq_[q * tab_words]);
+      else
+        build_filter_table(profile_, fp, queries[q].bytes, &h_feq_[q * tab_words]);
+    }
     feq_.ensure(h_feq_.size() * sizeof(uint32_t));
     SB_CUDA(cudaMemcpyAsync(feq_.p, h_feq_.data(), h_feq_.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
     {  // room for 2x the expected number of hits (uniform text), within 8 M .. 128 M entries
@@ -307,14 +315,14 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       f.nq = nfwd;
       f.qs_base = 0;
       f.feq = feq_.as<uint32_t>();
-      SB_CUDA(launch_filter(fp.WF, false, variant_, &ftmap, f, stream_));
+      SB_CUDA(launch_filter(fp.WF, false, variant_, pair, &ftmap, f, stream_));
       stats_.scan_launches++;
     }
     if (nq > nfwd) {
       f.nq = nq - nfwd;
       f.qs_base = nfwd;
-      f.feq = feq_.as<uint32_t>() + (size_t)nfwd * 256 * fp.WF;
-      SB_CUDA(launch_filter(fp.WF, true, variant_, &ftmap, f, stream_));
+      f.feq = feq_.as<uint32_t>() + (size_t)nfwd * tab_words;
+      SB_CUDA(launch_filter(fp.WF, true, variant_, pair, &ftmap, f, stream_));
       stats_.scan_launches++;
     }
     SB_CUDA(cudaEventRecord(ev_[2], stream_));

@@ -222,6 +222,24 @@ inline void build_filter_table(int profile, const FilterPlan& f, const uint8_t* 
   }
 }
 
+// Pair table of the two-characters-per-step automaton (Dna profile only):
+// tab[first | second << 2] = {A[WF], B[WF]}, see filter16_pair in scan_core.cuh.
+inline void build_pair_table(const FilterPlan& f, const uint8_t* pat, uint32_t* tab) {
+  std::vector<uint32_t> byte_tab((size_t)256 * f.WF);
+  build_filter_table(kDna, f, pat, byte_tab.data());
+  for (int c1 = 0; c1 < 4; c1++)
+    for (int c0 = 0; c0 < 4; c0++) {
+      uint32_t* e = tab + (size_t)(c0 | (c1 << 2)) * 2 * f.WF;
+      const uint32_t* e0 = &byte_tab[(size_t)(c0 << 1) * f.WF];  // any byte of class c0: (byte >> 1) & 3 == c0
+      const uint32_t* e1 = &byte_tab[(size_t)(c1 << 1) * f.WF];
+      for (int w = 0; w < f.WF; w++) {
+        e[w] = (e0[w] << 1) & e1[w];
+        e[f.WF + w] = (((f.finit[w] & e0[w]) << 1) | f.finit[w]) & e1[w];
+      }
+    }
+}
+constexpr int kPairTableWords = 16 * 2;  // per automaton word
+
 inline size_t padded_alloc(uint64_t n) {
   // room for one extra row of any tiling plus alignment slack
   return (size_t)((n + 2ull * kMaxRowBytes + 255ull) & ~255ull);

@@ -29,7 +29,7 @@ cudaError_t launch_scan(int W, bool rev, int variant, const CUtensorMap* tmap, c
 // the hit's neighbourhood with the full recurrences -> a.cand_*.
 size_t filter_smem_bytes(int WF, int variant);
 int filter_blocks_per_sm(int WF, int variant);
-cudaError_t launch_filter(int WF, bool rev, int variant, const CUtensorMap* tmap, const ScanArgs& a,
+cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtensorMap* tmap, const ScanArgs& a,
                           cudaStream_t stream);
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, unsigned long long nhits,
                           cudaStream_t stream);

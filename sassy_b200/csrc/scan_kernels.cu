@@ -77,9 +77,11 @@ constexpr int min_blocks() {
 // The row pipeline shared by the scan and the prefilter kernels.  Copies the block's
 // query table to shared memory, then feeds every thread its row, 64 bytes per stage:
 //   body(stage_idx, own, chunk) with chunk(c) -> the c-th 16-byte piece of the stage.
+// static_tbl: destination of the query table when the kernel keeps it in a static
+// __shared__ array (its address is then an immediate in every LDS), else nullptr.
 template <bool REV, int VARIANT, class Body>
 __device__ __forceinline__ void row_pipeline(const CUtensorMap& tmap, const ScanArgs& a, const uint32_t* table_src,
-                                             uint32_t table_words, EqTab& tab, Body&& body) {
+                                             uint32_t table_words, uint32_t* static_tbl, EqTab& tab, Body&& body) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kWarpsPerBlock * kScanStages];
 
@@ -100,6 +102,7 @@ __device__ __forceinline__ void row_pipeline(const CUtensorMap& tmap, const Scan
   } else {
     tbl = reinterpret_cast<uint32_t*>(smem_raw);
   }
+  if (static_tbl) tbl = static_tbl;
   for (uint32_t i = tid; i < table_words; i += kScanThreads) tbl[i] = table_src[i];
   tab.p = tbl;
   tab.saddr = smem_u32(tbl);
@@ -164,7 +167,8 @@ __global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
   lane_reset<W>(s, a.m);
   int prev_score = a.m;
   row_pipeline<REV, VARIANT>(
-      tmap, a, a.eq + (size_t)q * a.nrows * W, a.nrows * W, eqt, [&](uint64_t stage_idx, bool own, auto chunk) {
+      tmap, a, a.eq + (size_t)q * a.nrows * W, a.nrows * W, nullptr, eqt,
+      [&](uint64_t stage_idx, bool own, auto chunk) {
         if (!stage_is_special(a, stage_idx)) {
 #pragma unroll(W <= 2 ? kUnroll : 1)
           for (int cc = 0; cc < kChunks; cc++) {
@@ -204,7 +208,8 @@ __device__ __forceinline__ void flush_hits(const ScanArgs& a, const HitQueue& hq
 
 // Prefilter: Shift-And automaton over k+1 exact pieces (scan_core.cuh); emits the text
 // words in which a piece occurrence ends.
-template <int WF, bool REV, int VARIANT>
+// PAIR: two characters per automaton step through a class-pair table (Dna profile).
+template <int WF, bool REV, int VARIANT, bool PAIR>
 __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
     filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a) {
   __shared__ uint64_t hit_q[kWarpsPerBlock][kHitQueueCap];
@@ -220,7 +225,9 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
   eqt.rowbytes = (uint32_t)WF * 4u;
   FLane<WF> s;
   flane_reset<WF>(s, a);
-  row_pipeline<REV, VARIANT>(tmap, a, a.feq + (size_t)q * 256 * WF, 256 * WF, eqt,
+  constexpr uint32_t kTabWords = PAIR ? kPairTableWords * WF : 256 * WF;
+  __shared__ __align__(16) uint32_t pair_tab[PAIR ? kPairTableWords * WF : 4];
+  row_pipeline<REV, VARIANT>(tmap, a, a.feq + (size_t)q * kTabWords, kTabWords, PAIR ? pair_tab : nullptr, eqt,
                              [&](uint64_t stage_idx, bool own, auto chunk) {
                                uint32_t acc[kChunks];
 #pragma unroll
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
                                  const int c = REV ? (kChunks - 1 - cc) : cc;
                                  const uint4 v = chunk(c);
                                  const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-                                 acc[c] = filter16<WF, REV>(s, x, eqt);
+                                 acc[c] = PAIR ? filter16_pair<WF, REV>(s, x, eqt) : filter16<WF, REV>(s, x, eqt);
                                }
                                uint32_t any = 0;
 #pragma unroll
@@ -340,9 +347,9 @@ int occupancy_one(size_t smem) {
   return nb > 0 ? nb : 1;
 }
 
-template <int WF, bool REV, int VARIANT>
+template <int WF, bool REV, int VARIANT, bool PAIR>
 cudaError_t launch_filter_one(const CUtensorMap* tmap, const ScanArgs& a, size_t smem, cudaStream_t stream) {
-  auto kern = filter_kernel<WF, REV, VARIANT>;
+  auto kern = filter_kernel<WF, REV, VARIANT, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
@@ -360,7 +367,7 @@ cudaError_t launch_filter_one(const CUtensorMap* tmap, const ScanArgs& a, size_t
 
 template <int WF, bool REV, int VARIANT>
 int filter_occupancy_one(size_t smem) {
-  auto kern = filter_kernel<WF, REV, VARIANT>;
+  auto kern = filter_kernel<WF, REV, VARIANT, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kScanThreads, smem) != cudaSuccess) return 1;
@@ -387,16 +394,22 @@ size_t filter_smem_bytes(int WF, int variant) {
   return tab;
 }
 
-cudaError_t launch_filter(int WF, bool rev, int variant, const CUtensorMap* tmap, const ScanArgs& a,
+cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtensorMap* tmap, const ScanArgs& a,
                           cudaStream_t stream) {
   const size_t smem = filter_smem_bytes(WF, variant);
-#define SB_FCALL(WW)                                                                              \
+#define SB_FCALL2(WW, PP)                                                                         \
   if (variant == kVariantTma)                                                                     \
-    return rev ? launch_filter_one<WW, true, kVariantTma>(tmap, a, smem, stream)                  \
-               : launch_filter_one<WW, false, kVariantTma>(tmap, a, smem, stream);                \
+    return rev ? launch_filter_one<WW, true, kVariantTma, PP>(tmap, a, smem, stream)              \
+               : launch_filter_one<WW, false, kVariantTma, PP>(tmap, a, smem, stream);            \
   else                                                                                            \
-    return rev ? launch_filter_one<WW, true, kVariantLdg>(tmap, a, smem, stream)                  \
-               : launch_filter_one<WW, false, kVariantLdg>(tmap, a, smem, stream);
+    return rev ? launch_filter_one<WW, true, kVariantLdg, PP>(tmap, a, smem, stream)              \
+               : launch_filter_one<WW, false, kVariantLdg, PP>(tmap, a, smem, stream);
+#define SB_FCALL(WW)       \
+  if (pair) {              \
+    SB_FCALL2(WW, true)    \
+  } else {                 \
+    SB_FCALL2(WW, false)   \
+  }
   switch (WF) {
     case 1: SB_FCALL(1)
     case 2: SB_FCALL(2)
@@ -404,6 +417,7 @@ cudaError_t launch_filter(int WF, bool rev, int variant, const CUtensorMap* tmap
     default: return cudaErrorInvalidValue;
   }
 #undef SB_FCALL
+#undef SB_FCALL2
 }
 
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, unsigned long long nhits,
