@@ -201,7 +201,7 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   res->filter_words = fp.enabled ? fp.WF : 0;
   res->filter_len = fp.enabled ? fp.L : 0;
   if (n > 0 && fp.enabled) {
-    const bool pair = profile == kDna;
+    const bool pair = profile == kDna && fp.WF <= 2;
     const size_t tab_words = pair ? (size_t)kPairTableWords * fp.WF : (size_t)256 * fp.WF;
     std::vector<uint32_t> feq((size_t)nq * tab_words + 4);
     for (uint32_t q = 0; q < nq; q++) {

@@ -171,7 +171,8 @@ void Engine::make_tensor_map(CUtensorMap* map, const DeviceText& text, const Sca
   const cuuint32_t box[2] = {kStageBytes, 32};  // one box per warp per stage
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, text.d, dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      kStageBytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[128];
@@ -278,7 +279,9 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   }
   if (fp.enabled) {
     // Dna: two characters per step through the class-pair table; others: byte-indexed table
-    const bool pair = profile_ == kDna;
+    // (the pair table of a 4-word automaton has 512 distinct bytes per warp access: shared-memory
+    //  bandwidth, not instructions, would bound it -- measured 2.4x slower than the byte table)
+    const bool pair = profile_ == kDna && fp.WF <= 2;
     const size_t tab_words = pair ? (size_t)kPairTableWords * fp.WF : (size_t)256 * fp.WF;
     h_feq_.resize((size_t)nq * tab_words);
     for (uint32_t q = 0; q < nq; q++) {

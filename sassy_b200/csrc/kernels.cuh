@@ -11,9 +11,9 @@
 namespace sb {
 
 #ifndef SB_STAGES
-#define SB_STAGES 3
+#define SB_STAGES 2
 #endif
-constexpr int kScanStages = SB_STAGES;  // per-warp shared-memory ring depth (64 B per thread per stage)
+constexpr int kScanStages = SB_STAGES;  // measured: 2 x 64 B beats deeper rings (profiles/r01_pipeline_variants.md)  // per-warp shared-memory ring depth (64 B per thread per stage)
 
 enum ScanVariant : int { kVariantTma = 0, kVariantLdg = 1 };
 

@@ -32,8 +32,11 @@ namespace sb {
 #define SB_GROUP 4
 #endif
 constexpr int kGroup = SB_GROUP;  // 4, 8 or 16 (whole 32-bit text words)
-// Bytes per thread per pipeline stage (half a 128-byte line).
-constexpr int kStageBytes = 64;
+// Bytes per thread per pipeline stage: 64 (half a line, SWIZZLE_64B) or 128 (SWIZZLE_128B).
+#ifndef SB_STAGE_BYTES
+#define SB_STAGE_BYTES 64
+#endif
+constexpr int kStageBytes = SB_STAGE_BYTES;
 
 constexpr int kMaxFilterWords = 4;
 // Delay-line bits behind every piece of the prefilter: together with the piece's last

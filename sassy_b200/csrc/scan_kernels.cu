@@ -144,7 +144,8 @@ __device__ __forceinline__ void row_pipeline(const CUtensorMap& tmap, const Scan
       const uint32_t st = it % kScanStages;
       mbar_wait(&wbar[st], (it / kScanStages) & 1u);
       const uint8_t* buf = ring + st * kWarpStageBytes + lane * kStageBytes;
-      const uint32_t sw = (lane >> 1) & 3u;  // CU_TENSOR_MAP_SWIZZLE_64B: chunk ^= (row >> 1) & 3
+      // CU_TENSOR_MAP_SWIZZLE_64B: chunk ^= (row >> 1) & 3;  SWIZZLE_128B: chunk ^= row & 7
+      const uint32_t sw = kStageBytes == 64 ? ((lane >> 1) & 3u) : (lane & 7u);
       body(stage_idx, own, [&](int c) { return *reinterpret_cast<const uint4*>(buf + ((c ^ sw) << 4)); });
       __syncwarp();  // every lane is done with this warp's ring[st]
       if (lane == 0 && it + kScanStages < total) issue(it + kScanStages);
