@@ -2,7 +2,7 @@
 //
 // This is NOT a CPU fallback and is not part of libsassy_b200.so: it is a test
 // harness (libsassy_b200_emu.so) that executes the very same per-thread code
-// the CUDA kernels run (scan_core.cuh: process16 / is_local_minimum /
+// the CUDA kernels run (scan_core.cuh: process16 / select_candidate /
 // trace_one) and the same host logic (host_logic.h: equality tables, row
 // tiling), one "thread" after the other, so that tiling, warm-up, restart,
 // candidate, minima and traceback logic can be checked against the oracle on
@@ -251,18 +251,9 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   std::vector<uint64_t> skeys(count);
   std::vector<uint32_t> scost(count);
   for (uint64_t i = 0; i < count; i++) skeys[i] = keys[order[i]], scost[i] = cost[order[i]];
-  if (fp.enabled) {  // overlapping verification windows report a position more than once
-    uint64_t o = 0;
-    for (uint64_t i = 0; i < count; i++)
-      if (i == 0 || skeys[i] != skeys[i - 1]) skeys[o] = skeys[i], scost[o] = scost[i], o++;
-    count = o;
-    skeys.resize(count);
-    scost.resize(count);
-  }
-
   std::vector<uint64_t> sel;
   for (uint64_t i = 0; i < count; i++)
-    if (all_minima || is_local_minimum(skeys.data(), scost.data(), i, count)) sel.push_back(skeys[i]);
+    if (select_candidate(skeys.data(), scost.data(), i, count, all_minima != 0)) sel.push_back(skeys[i]);
 
   res->m.resize(sel.size());
   res->ops.assign(sel.size() * res->ops_words, 0);

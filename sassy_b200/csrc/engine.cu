@@ -70,9 +70,10 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   for (DevBuf* b : {&eq_, &patterns_, &revflags_, &keys_, &cost_, &keys2_, &cost2_, &flags_, &sel_, &count_,
-                    &cubtmp_, &scratch_, &ops_, &out_, &feq_, &hits_})
+                    &cubtmp_, &scratch_, &ops_, &out_, &feq_, &hits_, &d_stage_})
     b->release();
   if (staged_.d) cudaFree(staged_.d);
+  if (h_stage_) cudaFreeHost(h_stage_);
   for (auto& ev : ev_)
     if (ev) cudaEventDestroy(ev);
   if (stream_) cudaStreamDestroy(stream_);
@@ -129,6 +130,7 @@ DeviceText* Engine::stage_text(const uint8_t* host, uint64_t n) {
   const size_t need = padded_alloc(n);
   if (need > staged_.alloc) {
     if (staged_.d) cudaFree(staged_.d);
+  if (h_stage_) cudaFreeHost(h_stage_);
     staged_.d = nullptr;
     staged_.alloc = 0;
     SB_CUDA(cudaMalloc((void**)&staged_.d, need));
@@ -146,22 +148,43 @@ DeviceText* Engine::stage_text(const uint8_t* host, uint64_t n) {
   return &staged_;
 }
 
-void Engine::build_tables(const std::vector<Query>& queries, int m, int W) {
+// All small per-search inputs travel in ONE host->device copy from a pinned staging
+// buffer: [4 counters][equality tables][query bytes][direction flags][prefilter tables].
+void Engine::upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair) {
   const size_t nq = queries.size();
-  h_eq_.resize(nq * nrows_ * W);
-  h_pat_.resize(nq * (size_t)m);
-  h_rev_.resize(nq);
-  for (size_t q = 0; q < nq; q++) {
-    memcpy(&h_pat_[q * m], queries[q].bytes, m);
-    h_rev_[q] = queries[q].rev ? 1 : 0;
-    build_eq_table(profile_, queries[q].bytes, m, W, nrows_, &h_eq_[q * nrows_ * W]);
+  const size_t eq_bytes = nq * nrows_ * W * sizeof(uint32_t);
+  const size_t pat_bytes = nq * (size_t)m;
+  const size_t tab_words = !fp.enabled ? 0 : (pair ? (size_t)kPairTableWords * fp.WF : (size_t)256 * fp.WF);
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  off_counts_ = 0;
+  off_eq_ = align(4 * sizeof(unsigned long long));
+  off_pat_ = off_eq_ + align(eq_bytes);
+  off_rev_ = off_pat_ + align(pat_bytes);
+  off_feq_ = off_rev_ + align(nq);
+  const size_t total = off_feq_ + align(nq * tab_words * sizeof(uint32_t));
+  if (total > stage_cap_) {
+    if (h_stage_) cudaFreeHost(h_stage_);
+    h_stage_ = nullptr;
+    stage_cap_ = 0;
+    SB_CUDA(cudaHostAlloc((void**)&h_stage_, total * 2, cudaHostAllocDefault));
+    stage_cap_ = total * 2;
   }
-  eq_.ensure(h_eq_.size() * sizeof(uint32_t));
-  patterns_.ensure(h_pat_.size());
-  revflags_.ensure(h_rev_.size());
-  SB_CUDA(cudaMemcpyAsync(eq_.p, h_eq_.data(), h_eq_.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
-  SB_CUDA(cudaMemcpyAsync(patterns_.p, h_pat_.data(), h_pat_.size(), cudaMemcpyHostToDevice, stream_));
-  SB_CUDA(cudaMemcpyAsync(revflags_.p, h_rev_.data(), h_rev_.size(), cudaMemcpyHostToDevice, stream_));
+  d_stage_.ensure(stage_cap_);
+  memset(h_stage_ + off_counts_, 0, 4 * sizeof(unsigned long long));
+  uint32_t* h_eq = reinterpret_cast<uint32_t*>(h_stage_ + off_eq_);
+  uint32_t* h_feq = reinterpret_cast<uint32_t*>(h_stage_ + off_feq_);
+  for (size_t q = 0; q < nq; q++) {
+    memcpy(h_stage_ + off_pat_ + q * m, queries[q].bytes, m);
+    h_stage_[off_rev_ + q] = queries[q].rev ? 1 : 0;
+    build_eq_table(profile_, queries[q].bytes, m, W, nrows_, h_eq + q * nrows_ * W);
+    if (fp.enabled) {
+      if (pair)
+        build_pair_table(fp, queries[q].bytes, h_feq + q * tab_words);
+      else
+        build_filter_table(profile_, fp, queries[q].bytes, h_feq + q * tab_words);
+    }
+  }
+  SB_CUDA(cudaMemcpyAsync(d_stage_.p, h_stage_, total, cudaMemcpyHostToDevice, stream_));
 }
 
 void Engine::make_tensor_map(CUtensorMap* map, const DeviceText& text, const ScanGeom& g) const {
@@ -201,24 +224,40 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   out.ops_words = (uint32_t)((m + k + 1 + 15) / 16);
   stats_.words = (uint32_t)W;
 
-  SB_CUDA(cudaEventRecord(ev_[0], stream_));
-  build_tables(queries, m, W);
-
   const uint64_t n = text.n;
+  SB_CUDA(cudaEventRecord(ev_[0], stream_));
+
+  // ---- plan: exact piece prefilter or full scan ------------------------------------------------
+  FilterPlan fp;
+  if (n > 0 && filter_mode_ != 0) {
+    std::vector<const uint8_t*> qptr(nq);
+    for (uint32_t q = 0; q < nq; q++) qptr[q] = queries[q].bytes;
+    fp = plan_filter(profile_, qptr.data(), nq, m, k, filter_mode_ == 2 ? 1e30 : 0.85);
+  }
+  // Dna: two characters per step through the class-pair table; others: byte-indexed table
+  // (the pair table of a 4-word automaton has 512 distinct bytes per warp access: shared-memory
+  //  bandwidth, not instructions, would bound it -- measured 2.4x slower than the byte table)
+  const bool pair = profile_ == kDna && fp.WF <= 2;
+  const size_t tab_words = pair ? (size_t)kPairTableWords * fp.WF : (size_t)256 * fp.WF;
+  upload_params(queries, m, W, fp, pair);
+  uint8_t* dst = d_stage_.as<uint8_t>();
+  unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(dst + off_counts_);
+  unsigned long long* d_cand_count = d_counts;      // [0] candidates
+  unsigned long long* d_nsel = d_counts + 1;         // [1] selected candidates
+  unsigned long long* d_hit_count = d_counts + 2;    // [2] prefilter hits
+  const uint32_t* d_eq = reinterpret_cast<const uint32_t*>(dst + off_eq_);
+  const uint8_t* d_pat = dst + off_pat_;
+  const uint8_t* d_rev = dst + off_rev_;
+  const uint32_t* d_feq = reinterpret_cast<const uint32_t*>(dst + off_feq_);
+
   const int occ = scan_blocks_per_sm(W, false, variant_, nrows_);
   stats_.blocks_per_sm = (uint32_t)occ;
   const ScanGeom g = choose_geom(n, m, k, nq, occ * sm_count_);
   if ((uint64_t)g.rows * g.ltot > text.alloc) throw CudaError("internal: text padding too small for tiling");
   stats_.ltot = g.ltot;
   stats_.rows = g.rows;
-  CUtensorMap tmap;
-  memset(&tmap, 0, sizeof tmap);
-  if (variant_ == kVariantTma && n > 0) make_tensor_map(&tmap, text, g);
 
   if (cand_cap_ == 0) cand_cap_ = 1ull << 20;
-  count_.ensure(4 * sizeof(unsigned long long));
-  unsigned long long* d_cand_count = count_.as<unsigned long long>();
-  unsigned long long* d_hit_count = count_.as<unsigned long long>() + 2;
 
   ScanArgs a;
   memset(&a, 0, sizeof a);
@@ -242,6 +281,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       k0.push_back(cand_key(q, 0));
       c0.push_back((uint32_t)m);
     }
+  bool counts_fresh = true;  // the staged upload zeroed the counters
   auto reset_candidates = [&]() {
     keys_.ensure(cand_cap_ * sizeof(uint64_t));
     cost_.ensure(cand_cap_ * sizeof(uint32_t));
@@ -249,17 +289,19 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       SB_CUDA(cudaMemcpyAsync(keys_.p, k0.data(), k0.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream_));
       SB_CUDA(cudaMemcpyAsync(cost_.p, c0.data(), c0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
     }
-    const unsigned long long init = k0.size();
-    SB_CUDA(cudaMemcpyAsync(d_cand_count, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
+    if (!counts_fresh || !k0.empty()) {
+      const unsigned long long init = k0.size();
+      SB_CUDA(cudaMemcpyAsync(d_cand_count, &init, sizeof init, cudaMemcpyHostToDevice, stream_));
+    }
+    counts_fresh = false;
     a.cand_keys = keys_.as<uint64_t>();
     a.cand_cost = cost_.as<uint32_t>();
     a.cand_cap = cand_cap_;
   };
-  auto read_count = [&](const unsigned long long* d) {
-    unsigned long long v = 0;
-    SB_CUDA(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, stream_));
+  unsigned long long h_counts[4] = {0, 0, 0, 0};
+  auto read_counts = [&]() {
+    SB_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, stream_));
     SB_CUDA(cudaStreamSynchronize(stream_));
-    return v;
   };
   auto elapsed = [&](cudaEvent_t e0, cudaEvent_t e1) {
     float ms = 0;
@@ -271,42 +313,20 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   bool filtered = false;
 
   // ---- candidates, route 1: exact piece prefilter + re-scan of the hit neighbourhoods -----
-  FilterPlan fp;
-  if (n > 0 && filter_mode_ != 0) {
-    std::vector<const uint8_t*> qptr(nq);
-    for (uint32_t q = 0; q < nq; q++) qptr[q] = queries[q].bytes;
-    fp = plan_filter(profile_, qptr.data(), nq, m, k, filter_mode_ == 2 ? 1e30 : 0.85);
-  }
   if (fp.enabled) {
-    // Dna: two characters per step through the class-pair table; others: byte-indexed table
-    // (the pair table of a 4-word automaton has 512 distinct bytes per warp access: shared-memory
-    //  bandwidth, not instructions, would bound it -- measured 2.4x slower than the byte table)
-    const bool pair = profile_ == kDna && fp.WF <= 2;
-    const size_t tab_words = pair ? (size_t)kPairTableWords * fp.WF : (size_t)256 * fp.WF;
-    h_feq_.resize((size_t)nq * tab_words);
-    for (uint32_t q = 0; q < nq; q++) {
-      if (pair)
-        build_pair_table(fp, queries[q].bytes, &h_feq_[q * tab_words]);
-      else
-        build_filter_table(profile_, fp, queries[q].bytes, &h_feq_[q * tab_words]);
-    }
-    feq_.ensure(h_feq_.size() * sizeof(uint32_t));
-    SB_CUDA(cudaMemcpyAsync(feq_.p, h_feq_.data(), h_feq_.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
     {  // room for 2x the expected number of hits (uniform text), within 8 M .. 128 M entries
-      const double expect = 2.0 * fp.rate * (double)n * nq / 4.0 * 4.0;
+      const double expect = 2.0 * fp.rate * (double)n * nq;
       uint64_t want = (uint64_t)std::min(std::max(expect, 8.0 * 1048576.0), 128.0 * 1048576.0);
       if (want > hit_cap_) hit_cap_ = want;
     }
     hits_.ensure(hit_cap_ * sizeof(uint64_t));
-    const unsigned long long zero = 0;
-    SB_CUDA(cudaMemcpyAsync(d_hit_count, &zero, sizeof zero, cudaMemcpyHostToDevice, stream_));
-
     const int focc = filter_blocks_per_sm(fp.WF, variant_);
     ScanGeom gf = choose_geom(n, m, k, nq, focc * sm_count_);
     gf.nwarm = 1;  // a piece plus its delay line is at most 32 characters
     CUtensorMap ftmap;
     memset(&ftmap, 0, sizeof ftmap);
     if (variant_ == kVariantTma) make_tensor_map(&ftmap, text, gf);
+    reset_candidates();
     ScanArgs f = a;
     f.g = gf;
     for (int w = 0; w < kMaxFilterWords; w++) f.finit[w] = fp.finit[w], f.fdelay[w] = fp.fdelay[w];
@@ -317,25 +337,38 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     if (nfwd) {
       f.nq = nfwd;
       f.qs_base = 0;
-      f.feq = feq_.as<uint32_t>();
+      f.feq = d_feq;
       SB_CUDA(launch_filter(fp.WF, false, variant_, pair, &ftmap, f, stream_));
       stats_.scan_launches++;
     }
     if (nq > nfwd) {
       f.nq = nq - nfwd;
       f.qs_base = nfwd;
-      f.feq = feq_.as<uint32_t>() + (size_t)nfwd * tab_words;
+      f.feq = d_feq + (size_t)nfwd * tab_words;
       SB_CUDA(launch_filter(fp.WF, true, variant_, pair, &ftmap, f, stream_));
       stats_.scan_launches++;
     }
     SB_CUDA(cudaEventRecord(ev_[2], stream_));
-    const unsigned long long nhits = read_count(d_hit_count);
+    // the re-scan reads the hit count on the device: no host round trip between the two kernels
+    ScanArgs v = a;
+    v.nq = nq;
+    v.qs_base = 0;
+    v.eq = d_eq;
+    v.hit_keys = hits_.as<uint64_t>();
+    v.hit_count = d_hit_count;
+    v.hit_cap = hit_cap_;
+    SB_CUDA(launch_verify(W, v, d_rev, stream_));
+    stats_.aux_launches++;
+    SB_CUDA(cudaEventRecord(ev_[4], stream_));
+    read_counts();
     stats_.filter_ms = elapsed(ev_[1], ev_[2]);
+    stats_.verify_ms = elapsed(ev_[2], ev_[4]);
+    unsigned long long nhits = h_counts[2];
     stats_.hits = nhits;
     stats_.filter_words = (uint32_t)fp.WF;
     stats_.filter_len = (uint32_t)fp.L;
-    // too many hits (repetitive text, unlucky pieces): the re-scan would cost more than the scan
-    const double rescan = (double)nhits * (2.0 * (m + k) + 4.0);
+    // too many hits (repetitive text, unlucky pieces): the re-scan costs more than the scan
+    const double rescan = (double)nhits * (2.0 * (m + k) + kHitChars);
     if (nhits > hit_cap_ || rescan > 0.5 * (double)n * nq) {
       stats_.filter_fallback = 1;
     } else {
@@ -343,18 +376,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       stats_.rows = gf.rows;
       stats_.blocks_per_sm = (uint32_t)focc;
       for (int attempt = 0;; attempt++) {
-        reset_candidates();
-        ScanArgs v = a;
-        v.nq = nq;
-        v.qs_base = 0;
-        v.eq = eq_.as<uint32_t>();
-        v.hit_keys = hits_.as<uint64_t>();
-        SB_CUDA(cudaEventRecord(ev_[1], stream_));
-        SB_CUDA(launch_verify(W, v, revflags_.as<uint8_t>(), nhits, stream_));
-        if (nhits) stats_.aux_launches++;
-        SB_CUDA(cudaEventRecord(ev_[2], stream_));
-        const unsigned long long cnt = read_count(d_cand_count);
-        stats_.verify_ms += elapsed(ev_[1], ev_[2]);
+        const unsigned long long cnt = h_counts[0];
         if (cnt <= cand_cap_) {
           ncand = cnt;
           break;
@@ -362,6 +384,14 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
         if (attempt >= 3) throw CudaError("candidate buffer overflow after retries");
         cand_cap_ = (size_t)(cnt + cnt / 8 + 1024);
         stats_.retries++;
+        reset_candidates();
+        v.cand_keys = a.cand_keys, v.cand_cost = a.cand_cost, v.cand_cap = a.cand_cap;
+        SB_CUDA(cudaEventRecord(ev_[2], stream_));
+        SB_CUDA(launch_verify(W, v, d_rev, stream_));
+        stats_.aux_launches++;
+        SB_CUDA(cudaEventRecord(ev_[4], stream_));
+        read_counts();
+        stats_.verify_ms += elapsed(ev_[2], ev_[4]);
       }
       filtered = true;
       stats_.scan_ms = stats_.filter_ms;  // the dominant kernel of this route
@@ -370,6 +400,9 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
 
   // ---- candidates, route 2: full scan with the bit-parallel recurrences ---------------------
   if (!filtered) {
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (variant_ == kVariantTma && n > 0) make_tensor_map(&tmap, text, g);
     for (int attempt = 0;; attempt++) {
       reset_candidates();
       SB_CUDA(cudaEventRecord(ev_[1], stream_));
@@ -378,7 +411,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
           a.reset_idx = 0;
           a.nq = nfwd;
           a.qs_base = 0;
-          a.eq = eq_.as<uint32_t>();
+          a.eq = d_eq;
           SB_CUDA(launch_scan(W, false, variant_, &tmap, a, stream_));
           stats_.scan_launches++;
         }
@@ -386,14 +419,15 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
           a.reset_idx = n - 1;
           a.nq = nq - nfwd;
           a.qs_base = nfwd;
-          a.eq = eq_.as<uint32_t>() + (size_t)nfwd * nrows_ * W;
+          a.eq = d_eq + (size_t)nfwd * nrows_ * W;
           SB_CUDA(launch_scan(W, true, variant_, &tmap, a, stream_));
           stats_.scan_launches++;
         }
       }
       SB_CUDA(cudaEventRecord(ev_[2], stream_));
-      const unsigned long long cnt = read_count(d_cand_count);
+      read_counts();
       stats_.scan_ms += elapsed(ev_[1], ev_[2]);
+      const unsigned long long cnt = h_counts[0];
       if (cnt <= cand_cap_) {
         ncand = cnt;
         break;
@@ -405,8 +439,8 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   }
   stats_.candidates = ncand;
 
+  // ---- sort, select (de-duplicate + local minima), trace ------------------------------------
   uint64_t nsel = 0;
-  const uint64_t* sel_keys = nullptr;
   if (ncand > 0) {
     keys2_.ensure(ncand * sizeof(uint64_t));
     cost2_.ensure(ncand * sizeof(uint32_t));
@@ -420,82 +454,82 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     SB_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp_.p, tmp_bytes, keys_.as<uint64_t>(), keys2_.as<uint64_t>(),
                                             cost_.as<uint32_t>(), cost2_.as<uint32_t>(), ncand, 0, end_bit,
                                             stream_));
-    uint64_t* skeys = keys2_.as<uint64_t>();
-    uint32_t* scost = cost2_.as<uint32_t>();
-    if (filtered) {
-      // overlapping re-scan windows report an end position more than once: keep one copy
-      unsigned long long* d_nuniq = count_.as<unsigned long long>() + 1;
-      size_t tmp3 = 0;
-      SB_CUDA(cub::DeviceSelect::UniqueByKey(nullptr, tmp3, keys2_.as<uint64_t>(), cost2_.as<uint32_t>(),
-                                             keys_.as<uint64_t>(), cost_.as<uint32_t>(), d_nuniq, ncand, stream_));
-      cubtmp_.ensure(tmp3);
-      SB_CUDA(cub::DeviceSelect::UniqueByKey(cubtmp_.p, tmp3, keys2_.as<uint64_t>(), cost2_.as<uint32_t>(),
-                                             keys_.as<uint64_t>(), cost_.as<uint32_t>(), d_nuniq, ncand, stream_));
-      ncand = read_count(d_nuniq);
-      skeys = keys_.as<uint64_t>();
-      scost = cost_.as<uint32_t>();
-    }
-    if (all_minima) {
-      nsel = ncand;
-      sel_keys = skeys;
-    } else {
+    const uint64_t* skeys = keys2_.as<uint64_t>();
+    const uint32_t* scost = cost2_.as<uint32_t>();
+    const uint64_t* sel_keys = skeys;
+    // overlapping re-scan windows of the prefilter report an end position more than once; the
+    // selection kernel keeps the first copy only
+    const bool need_select = !all_minima || filtered;
+    if (need_select) {
       flags_.ensure(ncand);
       sel_.ensure(ncand * sizeof(uint64_t));
-      SB_CUDA(launch_minima(skeys, scost, ncand, flags_.as<uint8_t>(), stream_));
+      SB_CUDA(launch_minima(skeys, scost, ncand, flags_.as<uint8_t>(), all_minima, stream_));
       stats_.aux_launches++;
-      unsigned long long* d_nsel = count_.as<unsigned long long>() + 1;
       size_t tmp2 = 0;
-      SB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp2, skeys, flags_.as<uint8_t>(),
-                                         sel_.as<uint64_t>(), d_nsel, ncand, stream_));
+      SB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp2, skeys, flags_.as<uint8_t>(), sel_.as<uint64_t>(), d_nsel,
+                                         ncand, stream_));
       cubtmp_.ensure(tmp2);
-      SB_CUDA(cub::DeviceSelect::Flagged(cubtmp_.p, tmp2, skeys, flags_.as<uint8_t>(),
-                                         sel_.as<uint64_t>(), d_nsel, ncand, stream_));
-      unsigned long long h = 0;
-      SB_CUDA(cudaMemcpyAsync(&h, d_nsel, sizeof h, cudaMemcpyDeviceToHost, stream_));
-      SB_CUDA(cudaStreamSynchronize(stream_));
-      nsel = h;
+      SB_CUDA(cub::DeviceSelect::Flagged(cubtmp_.p, tmp2, skeys, flags_.as<uint8_t>(), sel_.as<uint64_t>(), d_nsel,
+                                         ncand, stream_));
       sel_keys = sel_.as<uint64_t>();
     }
-  }
-
-  if (nsel > 0) {
-    out_.ensure(nsel * sizeof(GpuMatch));
-    ops_.ensure(nsel * out.ops_words * sizeof(uint32_t));
-    const uint64_t words_per_match = (uint64_t)(m + k + 1) * W * 2;
-    const uint64_t max_scratch_words = (512ull << 20) / 4;  // 512 MiB of scratch per slice
-    uint64_t slice = std::max<uint64_t>(1, max_scratch_words / words_per_match);
-    slice = std::min(slice, nsel);
-    scratch_.ensure(slice * words_per_match * sizeof(uint32_t));
-    TraceArgs t;
-    memset(&t, 0, sizeof t);
-    t.text = text.d;
-    t.n = n;
-    t.profile = profile_;
-    t.patterns = patterns_.as<uint8_t>();
-    t.rev_flags = revflags_.as<uint8_t>();
-    t.eq = eq_.as<uint32_t>();
-    t.nrows = nrows_;
-    t.sh0 = sh0_;
-    t.msk0 = msk0_;
-    t.m = m;
-    t.k = k;
-    t.W = W;
-    t.keys = sel_keys;
-    t.scratch = scratch_.as<uint32_t>();
-    t.ops = ops_.as<uint32_t>();
-    t.ops_words = out.ops_words;
-    t.out = out_.as<GpuMatch>();
-    for (uint64_t first = 0; first < nsel; first += slice) {
-      t.first = first;
-      t.count = std::min(slice, nsel - first);
-      SB_CUDA(launch_trace(t, stream_));
-      stats_.aux_launches++;
+    // Small candidate lists (the normal case): trace every possible selection slot bounded by the
+    // device-side count and fetch results + count with one synchronisation.  Large lists: read
+    // the count first so that buffers and copies have the exact size.
+    const bool fast = ncand <= 65536;
+    uint64_t bound = ncand;
+    if (need_select && !fast) {
+      read_counts();
+      bound = h_counts[1];
     }
-    out.m.resize(nsel);
-    out.ops.resize(nsel * out.ops_words);
-    SB_CUDA(cudaMemcpyAsync(out.m.data(), out_.p, nsel * sizeof(GpuMatch), cudaMemcpyDeviceToHost, stream_));
-    SB_CUDA(cudaMemcpyAsync(out.ops.data(), ops_.p, out.ops.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                            stream_));
+    if (bound > 0) {
+      const uint64_t words_per_match = (uint64_t)(m + k + 1) * W * 2;
+      const uint64_t max_scratch_words = (512ull << 20) / 4;  // 512 MiB of scratch per slice
+      uint64_t slice = bound;
+      while (slice > 1 && trace_threads(slice) * words_per_match > max_scratch_words) slice = (slice + 1) / 2;
+      scratch_.ensure(trace_threads(slice) * words_per_match * sizeof(uint32_t));
+      out_.ensure(bound * sizeof(GpuMatch));
+      ops_.ensure(bound * out.ops_words * sizeof(uint32_t));
+      TraceArgs t;
+      memset(&t, 0, sizeof t);
+      t.text = text.d;
+      t.n = n;
+      t.profile = profile_;
+      t.patterns = d_pat;
+      t.rev_flags = d_rev;
+      t.eq = d_eq;
+      t.nrows = nrows_;
+      t.sh0 = sh0_;
+      t.msk0 = msk0_;
+      t.m = m;
+      t.k = k;
+      t.W = W;
+      t.keys = sel_keys;
+      t.count_dev = (need_select && fast) ? d_nsel : nullptr;
+      t.scratch = scratch_.as<uint32_t>();
+      t.ops = ops_.as<uint32_t>();
+      t.ops_words = out.ops_words;
+      t.out = out_.as<GpuMatch>();
+      for (uint64_t first = 0; first < bound; first += slice) {
+        t.first = first;
+        t.count = std::min(slice, bound - first);
+        SB_CUDA(launch_trace(t, stream_));
+        stats_.aux_launches++;
+      }
+      out.m.resize(bound);
+      out.ops.resize(bound * out.ops_words);
+      SB_CUDA(cudaMemcpyAsync(out.m.data(), out_.p, bound * sizeof(GpuMatch), cudaMemcpyDeviceToHost, stream_));
+      SB_CUDA(cudaMemcpyAsync(out.ops.data(), ops_.p, out.ops.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                              stream_));
+    }
+    if (need_select && fast) {
+      read_counts();
+      nsel = h_counts[1];
+      out.m.resize(nsel);
+      out.ops.resize(nsel * out.ops_words);
+    } else {
+      nsel = bound;
+    }
   }
   SB_CUDA(cudaEventRecord(ev_[3], stream_));
   SB_CUDA(cudaStreamSynchronize(stream_));

@@ -98,7 +98,7 @@ class Engine {
   void set_filter_mode(int m) { filter_mode_ = m; }
 
  private:
-  void build_tables(const std::vector<Query>& queries, int m, int W);
+  void upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair);
   void make_tensor_map(CUtensorMap* map, const DeviceText& text, const ScanGeom& g) const;
 
   int profile_;
@@ -107,13 +107,16 @@ class Engine {
   int filter_mode_ = 1;
   int sm_count_ = 148;
   cudaStream_t stream_ = nullptr;
-  cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   uint32_t nrows_, sh0_, msk0_;
 
   DevBuf eq_, patterns_, revflags_;
   DevBuf keys_, cost_, keys2_, cost2_, flags_, sel_, count_, cubtmp_;
   DevBuf scratch_, ops_, out_;
-  DevBuf feq_, hits_;
+  DevBuf feq_, hits_, d_stage_;
+  uint8_t* h_stage_ = nullptr;  // pinned staging for the per-search parameter block
+  size_t stage_cap_ = 0;
+  size_t off_counts_ = 0, off_eq_ = 0, off_pat_ = 0, off_rev_ = 0, off_feq_ = 0;
   uint64_t hit_cap_ = 0;
   std::vector<uint32_t> h_feq_;
   uint64_t cand_cap_ = 0;

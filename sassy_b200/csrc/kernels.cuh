@@ -31,11 +31,11 @@ size_t filter_smem_bytes(int WF, int variant);
 int filter_blocks_per_sm(int WF, int variant);
 cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtensorMap* tmap, const ScanArgs& a,
                           cudaStream_t stream);
-cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, unsigned long long nhits,
-                          cudaStream_t stream);
+// nhits is read from a.hit_count on the device (clipped to a.hit_cap): no host round trip.
+cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream);
 
 // flags[i] = 1 iff sorted candidate i is kept by the local-minima rule.
-cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags,
+cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags, bool all_minima,
                           cudaStream_t stream);
 
 struct TraceArgs {
@@ -52,11 +52,13 @@ struct TraceArgs {
   const uint64_t* keys;  // selected candidates (sorted)
   uint64_t first;        // slice [first, first+count) handled by this launch
   uint64_t count;
-  uint32_t* scratch;       // count * (m+k+1) * W * 2 words, interleaved by match
+  const unsigned long long* count_dev;  // optional device-side total that clips the slice
+  uint32_t* scratch;       // trace_threads(count) * (m+k+1) * W * 2 words, interleaved by thread
   uint32_t* ops;           // [total][ops_words]
   uint32_t ops_words;
   GpuMatch* out;           // [total]
 };
 cudaError_t launch_trace(const TraceArgs& t, cudaStream_t stream);
+uint64_t trace_threads(uint64_t count);  // threads launch_trace uses for a slice of `count` matches
 
 }  // namespace sb

@@ -533,22 +533,29 @@ SB_HD void stage_coord(const ScanGeom& g, uint32_t it, int64_t row, int64_t& r, 
 
 // ---------------------------------------------------------------------------
 // ---------------------------------------------------------------------------
-// Local-minima rule on the sorted candidate list (all positions with cost<=k).
-// A maximal run = same query slot, consecutive positions.  Candidate i is kept
-// iff the next step is up (or the run ends) and the last non-equal step before
-// it inside the run was down (or the run starts).  This is the reference's
-// streaming rule (src/search.rs:1344-1368) restricted to runs, identical to
+// Selection on the sorted candidate list (all positions with cost<=k; a position may be
+// listed several times when re-scan windows of the prefilter overlap -- copies carry the
+// same cost and only the first copy can be selected).
+// Local-minima rule: a maximal run = same query slot, consecutive positions.  A candidate
+// is kept iff the next step is up (or the run ends) and the last non-equal step before it
+// inside the run was down (or the run starts).  This is the reference's streaming rule
+// (src/search.rs:1344-1368) restricted to runs, identical to
 // src/pattern_tiling/minima.rs:9-52.
-SB_HD bool is_local_minimum(const uint64_t* keys, const uint32_t* cost, uint64_t i, uint64_t n) {
+SB_HD bool select_candidate(const uint64_t* keys, const uint32_t* cost, uint64_t i, uint64_t n, bool all_minima) {
   const uint64_t key = keys[i];
+  if (i > 0 && keys[i - 1] == key) return false;  // a later copy
+  if (all_minima) return true;
   const uint32_t c = cost[i];
-  if (i + 1 < n && keys[i + 1] == key + 1 && cost[i + 1] <= c) return false;
-  uint64_t j = i;
+  uint64_t j = i + 1;
+  while (j < n && keys[j] == key) j++;  // next distinct candidate
+  if (j < n && keys[j] == key + 1 && cost[j] <= c) return false;
+  uint64_t p = i;  // first copy of the position we stand on
   uint64_t kk = key;
-  while (j > 0 && keys[j - 1] == kk - 1) {
-    j--;
+  while (p > 0 && keys[p - 1] == kk - 1) {
+    p--;
     kk--;
-    if (cost[j] != c) return cost[j] > c;
+    if (cost[p] != c) return cost[p] > c;
+    while (p > 0 && keys[p - 1] == kk) p--;  // move to the first copy
   }
   return true;
 }

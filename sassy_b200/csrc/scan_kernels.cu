@@ -253,6 +253,10 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
   flush_hits(a, hq, lane);
 }
 
+template <int W>
+__device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __restrict__ rev_flags,
+                                           unsigned long long i);
+
 // One thread per prefilter hit: exact recurrences over the hit's neighbourhood
 // (same window and emission rule as verify_hit in scan_core.cuh, which the host emulator
 // runs).  The window is fetched as aligned 16-byte chunks, one chunk ahead of the
@@ -261,10 +265,17 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
 // consecutive byte loads.
 template <int W>
 __global__ void __launch_bounds__(128)
-    verify_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags,
-                  unsigned long long nhits) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nhits) return;
+    verify_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags) {
+  unsigned long long nhits = *a.hit_count;
+  if (nhits > a.hit_cap) nhits = a.hit_cap;
+  const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nhits; i += nthreads)
+    verify_one<W>(a, rev_flags, i);
+}
+
+template <int W>
+__device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __restrict__ rev_flags,
+                                           unsigned long long i) {
   const uint64_t key = a.hit_keys[i];
   const uint32_t qs = key_qs(key);
   const bool rev = rev_flags[qs] != 0;
@@ -421,14 +432,11 @@ cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtens
 #undef SB_FCALL2
 }
 
-cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, unsigned long long nhits,
-                          cudaStream_t stream) {
-  if (nhits == 0) return cudaSuccess;
+cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream) {
   const unsigned threads = 128;
-  const unsigned long long blocks = (nhits + threads - 1) / threads;
-  if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+  const unsigned blocks = 148 * 12;  // grid-stride over the device-side hit count
   switch (W) {
-#define SB_VCALL(WW) case WW: verify_kernel<WW><<<(unsigned)blocks, threads, 0, stream>>>(a, rev_flags, nhits); break;
+#define SB_VCALL(WW) case WW: verify_kernel<WW><<<blocks, threads, 0, stream>>>(a, rev_flags); break;
     SB_VCALL(1) SB_VCALL(2) SB_VCALL(3) SB_VCALL(4) SB_VCALL(6) SB_VCALL(8) SB_VCALL(16) SB_VCALL(32)
 #undef SB_VCALL
     default: return cudaErrorInvalidValue;
