@@ -335,8 +335,15 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
 template <int W, bool REV, int VARIANT>
 cudaError_t launch_one(const CUtensorMap* tmap, const ScanArgs& a, size_t smem, cudaStream_t stream) {
   auto kern = scan_kernel<W, REV, VARIANT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static size_t smem_set_dev[64] = {};  // per device: the attribute lives in the device's context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& smem_set = smem_set_dev[dev & 63];
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
   const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
   const uint64_t blocks = tiles * a.nq;
   if (blocks == 0) return cudaSuccess;
@@ -362,8 +369,15 @@ int occupancy_one(size_t smem) {
 template <int WF, bool REV, int VARIANT, bool PAIR>
 cudaError_t launch_filter_one(const CUtensorMap* tmap, const ScanArgs& a, size_t smem, cudaStream_t stream) {
   auto kern = filter_kernel<WF, REV, VARIANT, PAIR>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static size_t smem_set_dev[64] = {};  // per device: the attribute lives in the device's context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& smem_set = smem_set_dev[dev & 63];
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
   const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
   const uint64_t blocks = tiles * a.nq;
   if (blocks == 0) return cudaSuccess;
@@ -389,8 +403,18 @@ int filter_occupancy_one(size_t smem) {
 }  // namespace
 
 size_t filter_smem_bytes(int WF, int variant);
+int filter_blocks_per_sm_uncached(int WF, int variant);
 
 int filter_blocks_per_sm(int WF, int variant) {
+  static int cache[8][2] = {};  // occupancy queries cost tens of microseconds: ask once per shape
+  // (all devices of a box are the same part, so one answer serves every device)
+  if (WF >= 1 && WF < 8 && cache[WF][variant & 1]) return cache[WF][variant & 1];
+  const int nb = filter_blocks_per_sm_uncached(WF, variant);
+  if (WF >= 1 && WF < 8) cache[WF][variant & 1] = nb;
+  return nb;
+}
+
+int filter_blocks_per_sm_uncached(int WF, int variant) {
   const size_t smem = filter_smem_bytes(WF, variant);
   switch (WF) {
     case 1: return variant == kVariantTma ? filter_occupancy_one<1, false, kVariantTma>(smem) : filter_occupancy_one<1, false, kVariantLdg>(smem);
@@ -480,6 +504,10 @@ cudaError_t launch_scan(int W, bool rev, int variant, const CUtensorMap* tmap, c
 }
 
 int scan_blocks_per_sm(int W, bool rev, int variant, uint32_t nrows) {
+  static int cache[33][2][2][3] = {};  // occupancy queries cost tens of microseconds: ask once per shape
+  const int rb = nrows <= 4 ? 0 : (nrows <= 32 ? 1 : 2);
+  int* slot = (W >= 1 && W <= 32) ? &cache[W][rev ? 1 : 0][variant & 1][rb] : nullptr;
+  if (slot && *slot) return *slot;
   const size_t smem = scan_smem_bytes(W, variant, nrows);
   int nb = 1;
 #define SB_CALL(WW)                                                                    \
@@ -489,6 +517,7 @@ int scan_blocks_per_sm(int W, bool rev, int variant, uint32_t nrows) {
     nb = rev ? occupancy_one<WW, true, kVariantLdg>(smem) : occupancy_one<WW, false, kVariantLdg>(smem);
   SB_DISPATCH_W(W, SB_CALL)
 #undef SB_CALL
+  if (slot) *slot = nb;
   return nb;
 }
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 from typing import List, Sequence
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -51,32 +52,84 @@ def unpack_matches(t: torch.Tensor) -> List[Match]:
     return out
 
 
-def gather_matches(matches: Sequence[Match], max_ops: int, device=None, group=None) -> List[Match]:
-    """All ranks receive the concatenation (rank order) of every rank's matches.
+def _local_block(matches, max_ops: int):
+    """(records uint8 [n, 72], ops uint8 [n, max_ops]) of a MatchList or a list of Match."""
+    from .searcher import MatchList, _REC_DTYPE
+    n = len(matches)
+    if isinstance(matches, MatchList):
+        recs = matches.records
+        raw = np.frombuffer(matches._ops, dtype=np.uint8)
+    else:
+        recs = np.zeros(n, dtype=_REC_DTYPE)
+        chunks = []
+        off = 0
+        for i, m in enumerate(matches):
+            recs[i] = (m.pattern_idx, m.text_idx, m.text_start, m.text_end, m.pattern_start, m.pattern_end, m.cost,
+                       1 if m.strand == "-" else 0, (0, 0, 0), len(m._ops), 0, off)
+            chunks.append(m._ops.encode())
+            off += len(m._ops)
+        raw = np.frombuffer(b"".join(chunks), dtype=np.uint8)
+    ops = np.zeros((n, max_ops), dtype=np.uint8)
+    if n:
+        lens = recs["ops_len"].astype(np.int64)
+        if lens.max(initial=0) > max_ops:
+            raise ValueError("max_ops too small for CIGAR")
+        offs = recs["ops_off"].astype(np.int64)
+        idx = offs[:, None] + np.arange(max_ops)[None, :]
+        mask = np.arange(max_ops)[None, :] < lens[:, None]
+        ops[mask] = raw[np.minimum(idx, max(len(raw) - 1, 0))][mask]
+    return np.ascontiguousarray(recs).view(np.uint8).reshape(n, _REC_DTYPE.itemsize), ops
 
-    Two collectives of which only the second carries data: an all-gather of the counts
-    (8 bytes per rank) and one all-gather of the records padded to the largest count
-    (NCCL has no gatherv)."""
+
+_GATHER_CAP = {}
+
+
+def gather_matches(matches, max_ops: int, device=None, group=None):
+    """All ranks receive the concatenation (rank order) of every rank's matches (a MatchList).
+
+    ONE collective in the common case: every rank contributes a fixed-capacity block
+    [count | records | ops]; only if some rank holds more matches than the capacity is the
+    exchange repeated with a larger block (NCCL has no gatherv)."""
+    from .searcher import MatchList, _REC_DTYPE
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return list(matches)
+        return matches
     world = dist.get_world_size(group)
-    ops_words = (max_ops + 31) // 32
-    local = pack_matches(matches, ops_words)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
-    cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=device)
-    counts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(counts, cnt, group=group)
-    counts = [int(c.item()) for c in counts]
-    mx = max(counts)
-    if mx == 0:
-        return []
-    buf = torch.zeros((mx, local.shape[1]), dtype=torch.int64, device=device)
-    buf[: local.shape[0]] = local.to(device)
-    allbuf = torch.empty((world * mx, local.shape[1]), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(allbuf, buf, group=group)
-    allbuf = allbuf.cpu().view(world, mx, local.shape[1])
-    out: List[Match] = []
+    recs, ops = _local_block(matches, max_ops)
+    n = recs.shape[0]
+    width = _REC_DTYPE.itemsize + max_ops
+    key = (id(group), max_ops)
+    cap = max(_GATHER_CAP.get(key, 256), 1)
+    while True:
+        block = np.zeros(8 + cap * width, dtype=np.uint8)
+        block[:8] = np.frombuffer(np.int64(n).tobytes(), dtype=np.uint8)
+        take = min(n, cap)
+        body = block[8:].reshape(cap, width)
+        body[:take, :_REC_DTYPE.itemsize] = recs[:take]
+        body[:take, _REC_DTYPE.itemsize:] = ops[:take]
+        send = torch.from_numpy(block).to(device, non_blocking=False)
+        recv = torch.empty(world * block.size, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        allb = recv.cpu().numpy().reshape(world, block.size)
+        counts = [int(np.frombuffer(allb[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(world)]
+        if max(counts) <= cap:
+            break
+        cap = 2 * max(counts)
+    _GATHER_CAP[key] = max(cap, 2 * max(counts))
+    out_recs = []
+    out_ops = []
+    off = 0
     for r in range(world):
-        out.extend(unpack_matches(allbuf[r, : counts[r]]))
-    return out
+        body = allb[r, 8:].reshape(cap, width)[:counts[r]]
+        rr = np.ascontiguousarray(body[:, :_REC_DTYPE.itemsize]).view(_REC_DTYPE).reshape(-1).copy()
+        lens = rr["ops_len"].astype(np.int64)
+        o = body[:, _REC_DTYPE.itemsize:]
+        mask = np.arange(max_ops)[None, :] < lens[:, None]
+        flat = o[mask]
+        starts = off + np.concatenate(([0], np.cumsum(lens)[:-1])) if len(lens) else np.zeros(0, dtype=np.int64)
+        rr["ops_off"] = starts
+        off += int(lens.sum())
+        out_recs.append(rr)
+        out_ops.append(flat.tobytes())
+    return MatchList(np.concatenate(out_recs) if out_recs else np.zeros(0, dtype=_REC_DTYPE), b"".join(out_ops))
