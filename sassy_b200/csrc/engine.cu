@@ -130,7 +130,6 @@ DeviceText* Engine::stage_text(const uint8_t* host, uint64_t n) {
   const size_t need = padded_alloc(n);
   if (need > staged_.alloc) {
     if (staged_.d) cudaFree(staged_.d);
-  if (h_stage_) cudaFreeHost(h_stage_);
     staged_.d = nullptr;
     staged_.alloc = 0;
     SB_CUDA(cudaMalloc((void**)&staged_.d, need));

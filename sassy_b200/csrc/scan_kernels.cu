@@ -332,17 +332,39 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
   }
 }
 
+// Raises (never lowers) a kernel's dynamic shared-memory limit; one tracker per kernel
+// instantiation and device, because the attribute lives in the device's context and
+// cudaFuncSetAttribute *sets* the limit rather than maximising it.
+template <class Kern>
+cudaError_t ensure_smem(Kern kern, size_t smem, size_t (&set_dev)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& cur = set_dev[dev & 63];
+  if (smem > cur) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cur = smem;
+  }
+  return cudaSuccess;
+}
+
+template <int W, bool REV, int VARIANT>
+size_t (&scan_smem_tracker())[64] {
+  static size_t t[64] = {};
+  return t;
+}
+template <int WF, bool REV, int VARIANT, bool PAIR>
+size_t (&filter_smem_tracker())[64] {
+  static size_t t[64] = {};
+  return t;
+}
+
 template <int W, bool REV, int VARIANT>
 cudaError_t launch_one(const CUtensorMap* tmap, const ScanArgs& a, size_t smem, cudaStream_t stream) {
   auto kern = scan_kernel<W, REV, VARIANT>;
-  static size_t smem_set_dev[64] = {};  // per device: the attribute lives in the device's context
-  int dev = 0;
-  cudaGetDevice(&dev);
-  size_t& smem_set = smem_set_dev[dev & 63];
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_smem(kern, smem, scan_smem_tracker<W, REV, VARIANT>());
     if (e != cudaSuccess) return e;
-    smem_set = smem;
   }
   const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
   const uint64_t blocks = tiles * a.nq;
@@ -360,7 +382,7 @@ cudaError_t launch_one(const CUtensorMap* tmap, const ScanArgs& a, size_t smem, 
 template <int W, bool REV, int VARIANT>
 int occupancy_one(size_t smem) {
   auto kern = scan_kernel<W, REV, VARIANT>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+  if (ensure_smem(kern, smem, scan_smem_tracker<W, REV, VARIANT>()) != cudaSuccess) return 1;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kScanThreads, smem) != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;
@@ -369,14 +391,9 @@ int occupancy_one(size_t smem) {
 template <int WF, bool REV, int VARIANT, bool PAIR>
 cudaError_t launch_filter_one(const CUtensorMap* tmap, const ScanArgs& a, size_t smem, cudaStream_t stream) {
   auto kern = filter_kernel<WF, REV, VARIANT, PAIR>;
-  static size_t smem_set_dev[64] = {};  // per device: the attribute lives in the device's context
-  int dev = 0;
-  cudaGetDevice(&dev);
-  size_t& smem_set = smem_set_dev[dev & 63];
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_smem(kern, smem, filter_smem_tracker<WF, REV, VARIANT, PAIR>());
     if (e != cudaSuccess) return e;
-    smem_set = smem;
   }
   const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
   const uint64_t blocks = tiles * a.nq;
@@ -394,7 +411,7 @@ cudaError_t launch_filter_one(const CUtensorMap* tmap, const ScanArgs& a, size_t
 template <int WF, bool REV, int VARIANT>
 int filter_occupancy_one(size_t smem) {
   auto kern = filter_kernel<WF, REV, VARIANT, false>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+  if (ensure_smem(kern, smem, filter_smem_tracker<WF, REV, VARIANT, false>()) != cudaSuccess) return 1;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kScanThreads, smem) != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;
