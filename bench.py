@@ -24,7 +24,6 @@ import random
 import statistics
 import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -44,8 +43,8 @@ METRIC = "GB/s text scanned"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--text-bytes", type=int, default=0, help="override the text size (debug)")
@@ -126,52 +125,67 @@ def synth_text_device(torch, n, seed, device):
     return out
 
 
-def sample_clocks_start(uuid):
-    f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-    try:
-        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                              "-i", uuid], stdout=f, stderr=subprocess.DEVNULL)
-    except Exception:
-        return None, f.name
-    return p, f.name
+class ClockSampler:
+    """SM clock / throttle-reason samples taken DURING the timed region through NVML
+    (nvidia-ml-py), every `every` steps from inside the step loop; falls back to one
+    `nvidia-smi` query if NVML is unavailable."""
 
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-def sample_clocks_stop(p, path):
-    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-    if p is not None:
-        p.terminate()
+    def __init__(self, uuid: str, every: int = 8):
+        self.every = every
+        self.sm = []
+        self.power = []
+        self.reasons = set()
+        self.sm_max = None
+        self.h = None
+        self.uuid = uuid
         try:
-            p.wait(timeout=5)
-        except Exception:
-            p.kill()
-    try:
-        rows = [l.strip().split(", ") for l in open(path) if l.strip()]
-        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = float(rows[0][1])
-            out["samples"] = len(sm)
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            reasons = set()
-            for r in rows:
-                for nm, v in zip(names, r[4:8]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(nm)
-            out["reasons"] = sorted(reasons)
-            pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
-            if pw:
-                out["power_w_max"] = max(pw)
-    except Exception as e:  # clocks are evidence, not a reason to lose the measurement
-        out["error"] = str(e)
-    finally:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:
+            self.h = None
+            self.err = str(e)
+
+    def sample(self, step: int = 0):
+        if self.h is None or step % self.every:
+            return
+        nv = self.nv
         try:
-            os.unlink(path)
-        except OSError:
-            pass
-    return out
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception as e:
+            self.err = str(e)
+
+    def result(self):
+        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "source": "nvml"}
+        if self.sm:
+            out["sm_mhz"] = statistics.median(self.sm)
+            out["samples"] = len(self.sm)
+            out["power_w_max"] = max(self.power) if self.power else None
+            return out
+        try:  # fallback: one nvidia-smi query (not under load)
+            q = "clocks.sm,clocks.max.sm,power.draw"
+            txt = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", self.uuid],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().split(", ")
+            out.update({"sm_mhz": float(txt[0]), "sm_max_mhz": float(txt[1]), "power_w_max": float(txt[2]),
+                        "samples": 1, "source": "nvidia-smi after the timed region (NVML unavailable: %s)" % getattr(self, "err", "?")})
+        except Exception as e:
+            out["error"] = str(e)
+        return out
 
 
 # ----------------------------------------------------------------------------------------
@@ -199,7 +213,8 @@ def run_reference(args):
     from oracle import cpu_port
     rate = cpu_port.calibrate(profile, pats[:min(len(pats), 32)], k, args.rc)  # bytes*patterns/s/thread
     sample_pats = pats[:min(len(pats), 64)]
-    budget = args.cpu_seconds
+    # each step is a bounded sample; the whole --steps/--warmup run stays within a few minutes
+    budget = min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup))
     sample_n = int(min(n, max(1 << 24, rate * cores * budget / max(1, len(sample_pats)))))
     rng = np.random.default_rng(42)
     text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=sample_n, dtype=np.uint8)]
@@ -304,14 +319,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             ms = fn()
         barrier()
         scan_ms, total_ms, launches = [], [], 0
         t0 = time.perf_counter()
-        for _ in range(steps):
+        for it in range(steps):
             ms = fn()
+            if sampler is not None:
+                sampler.sample(it)
             st = s.stats()
             scan_ms.append(st["scan_ms"])
             total_ms.append(st["total_ms"])
@@ -327,9 +344,9 @@ def main():
     uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
     if not uuid.startswith("GPU-"):
         uuid = "GPU-" + uuid
-    clk_p, clk_path = sample_clocks_start(uuid) if rank == 0 else (None, None)
-    el, matches, scan_ms, total_ms, launches, st = timed(step_resident, args.steps, args.warmup)
-    clocks = sample_clocks_stop(clk_p, clk_path) if rank == 0 else None
+    sampler = ClockSampler(uuid) if rank == 0 else None
+    el, matches, scan_ms, total_ms, launches, st = timed(step_resident, args.steps, args.warmup, sampler)
+    clocks = sampler.result() if rank == 0 else None
 
     total_bytes = n * world
     value = total_bytes * args.steps / el / 1e9

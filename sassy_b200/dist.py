@@ -81,7 +81,24 @@ def _local_block(matches, max_ops: int):
     return np.ascontiguousarray(recs).view(np.uint8).reshape(n, _REC_DTYPE.itemsize), ops
 
 
-_GATHER_CAP = {}
+class _GatherBuffers:
+    """Re-used staging for gather_matches: pinned host blocks and device blocks of one capacity."""
+
+    def __init__(self, world: int, cap: int, width: int, device):
+        self.cap = cap
+        self.block = 8 + cap * width
+        cuda = torch.device(device).type == "cuda"
+        self.send_host = torch.zeros(self.block, dtype=torch.uint8, pin_memory=cuda)
+        self.recv_host = torch.zeros(world * self.block, dtype=torch.uint8, pin_memory=cuda)
+        if cuda:
+            self.send_dev = torch.zeros(self.block, dtype=torch.uint8, device=device)
+            self.recv_dev = torch.zeros(world * self.block, dtype=torch.uint8, device=device)
+        else:
+            self.send_dev, self.recv_dev = self.send_host, self.recv_host
+        self.cuda = cuda
+
+
+_GATHER = {}
 
 
 def gather_matches(matches, max_ops: int, device=None, group=None):
@@ -98,37 +115,44 @@ def gather_matches(matches, max_ops: int, device=None, group=None):
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
     recs, ops = _local_block(matches, max_ops)
     n = recs.shape[0]
-    width = _REC_DTYPE.itemsize + max_ops
-    key = (id(group), max_ops)
-    cap = max(_GATHER_CAP.get(key, 256), 1)
+    rsz = _REC_DTYPE.itemsize
+    width = rsz + max_ops
+    key = (id(group), max_ops, str(device))
     while True:
-        block = np.zeros(8 + cap * width, dtype=np.uint8)
+        gb = _GATHER.get(key)
+        if gb is None:
+            gb = _GATHER[key] = _GatherBuffers(world, 256, width, device)
+        cap = gb.cap
+        block = gb.send_host.numpy()
         block[:8] = np.frombuffer(np.int64(n).tobytes(), dtype=np.uint8)
         take = min(n, cap)
         body = block[8:].reshape(cap, width)
-        body[:take, :_REC_DTYPE.itemsize] = recs[:take]
-        body[:take, _REC_DTYPE.itemsize:] = ops[:take]
-        send = torch.from_numpy(block).to(device, non_blocking=False)
-        recv = torch.empty(world * block.size, dtype=torch.uint8, device=device)
-        dist.all_gather_into_tensor(recv, send, group=group)
-        allb = recv.cpu().numpy().reshape(world, block.size)
-        counts = [int(np.frombuffer(allb[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(world)]
+        body[:take, :rsz] = recs[:take]
+        body[:take, rsz:] = ops[:take]
+        if gb.cuda:
+            gb.send_dev.copy_(gb.send_host, non_blocking=True)
+            dist.all_gather_into_tensor(gb.recv_dev, gb.send_dev, group=group)
+            gb.recv_host.copy_(gb.recv_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            dist.all_gather_into_tensor(gb.recv_host, gb.send_host, group=group)
+        allb = gb.recv_host.numpy().reshape(world, gb.block)
+        counts = allb[:, :8].copy().view(np.int64).reshape(world).tolist()
         if max(counts) <= cap:
             break
-        cap = 2 * max(counts)
-    _GATHER_CAP[key] = max(cap, 2 * max(counts))
+        _GATHER[key] = _GatherBuffers(world, 2 * max(counts), width, device)  # same decision on every rank
     out_recs = []
     out_ops = []
     off = 0
     for r in range(world):
+        if counts[r] == 0:
+            continue
         body = allb[r, 8:].reshape(cap, width)[:counts[r]]
-        rr = np.ascontiguousarray(body[:, :_REC_DTYPE.itemsize]).view(_REC_DTYPE).reshape(-1).copy()
+        rr = np.ascontiguousarray(body[:, :rsz]).view(_REC_DTYPE).reshape(-1).copy()
         lens = rr["ops_len"].astype(np.int64)
-        o = body[:, _REC_DTYPE.itemsize:]
         mask = np.arange(max_ops)[None, :] < lens[:, None]
-        flat = o[mask]
-        starts = off + np.concatenate(([0], np.cumsum(lens)[:-1])) if len(lens) else np.zeros(0, dtype=np.int64)
-        rr["ops_off"] = starts
+        flat = body[:, rsz:][mask]
+        rr["ops_off"] = off + np.concatenate(([0], np.cumsum(lens)[:-1]))
         off += int(lens.sum())
         out_recs.append(rr)
         out_ops.append(flat.tobytes())
