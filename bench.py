@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--filter", default="auto", choices=["off", "auto", "force"],
                     help="exact piece prefilter in front of the scan (result-neutral)")
     ap.add_argument("--rc", action="store_true", help="search both strands (default: forward only, as the reference's evals)")
+    ap.add_argument("--transport", default="packed", choices=["packed", "bytes"],
+                    help="host->device transport of Dna texts in the e2e leg (2 bits per character, or bytes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
@@ -284,6 +286,7 @@ def main():
     s = sassy_b200.Searcher(profile, rc=args.rc, device=local_rank)
     s.set_variant(args.variant)
     s.set_filter(args.filter)
+    s.set_transport(args.transport)
     dt = s.text_from_device(text_dev.data_ptr(), n)
     enc = s.encode_patterns(pats) if n_patterns > 1 else None
 
@@ -363,8 +366,12 @@ def main():
             same = sorted(x._key() for x in e_matches) == sorted(x._key() for x in matches)
         assert same, "host-pointer path and resident path disagree"
         tables = s.stats()["words"] * 4 * {"dna": 4, "iupac": 32, "ascii": 256}[profile] * len(pats) * (2 if args.rc else 1)
+        est = s.stats()
+        packed = bool(est["transfer_packed"])
         e2e = {"value": total_bytes * e_steps / e_el / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": n + tables + len(pats) * m,
+               "h2d_bytes_per_step": ((n + 63) // 64 * 16 if packed else n) + tables + len(pats) * m,
+               "transport": "2 bits per character, packed by host threads inside the timed region" if packed else "bytes",
+               "transfer_ms": est["transfer_ms"],
                "d2h_bytes_per_step": len(e_matches) // max(1, world) * (24 + 4 * ((m + k + 1 + 15) // 16)) + 16,
                "ms_per_step": e_el / e_steps * 1e3, "steps": e_steps}
 

@@ -68,6 +68,8 @@ typedef struct sassy_gpu_Stats {
   uint64_t hits;          /* text words in which a pattern piece occurs exactly */
   uint32_t filter_len;    /* piece length */
   uint32_t filter_fallback; /* 1: prefilter produced too many hits, the full scan was used */
+  float transfer_ms;        /* host->device transfer of the text (host-text entry points) */
+  uint32_t transfer_packed; /* 1: the text crossed PCIe at 2 bits per character (Dna) */
 } sassy_gpu_Stats;
 
 #ifdef __cplusplus
@@ -85,6 +87,9 @@ int sassy_gpu_set_variant(sassy_SearcherType *searcher, int variant);
 /* Exact piece prefilter (result-neutral, like the reference's suffix prefilter,
  * src/pattern_tiling/general.rs:294-313): 0 = off, 1 = when profitable (default), 2 = whenever possible. */
 int sassy_gpu_set_filter(sassy_SearcherType *searcher, int mode);
+/* Host->device transport of large Dna texts: 1 = packed to 2 bits per character by host threads
+ * (default; result-neutral, texts with bytes outside ACGTacgt are sent as bytes), 0 = bytes. */
+int sassy_gpu_set_transport(sassy_SearcherType *searcher, int mode);
 int sassy_gpu_stats(const sassy_SearcherType *searcher, sassy_gpu_Stats *out);
 
 /* Pinned host memory for texts that are searched through the host-pointer entry points. */

@@ -69,6 +69,8 @@ class GpuStats(ctypes.Structure):
         ("hits", ctypes.c_uint64),
         ("filter_len", ctypes.c_uint32),
         ("filter_fallback", ctypes.c_uint32),
+        ("transfer_ms", ctypes.c_float),
+        ("transfer_packed", ctypes.c_uint32),
     ]
 
 
@@ -86,6 +88,7 @@ SIGNATURES = {
     "sassy_gpu_searcher": (c_void_p, [ctypes.c_char_p, ctypes.c_bool, ctypes.c_float, ctypes.c_int]),
     "sassy_gpu_set_variant": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "sassy_gpu_set_filter": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "sassy_gpu_set_transport": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "sassy_gpu_stats": (ctypes.c_int, [c_void_p, ctypes.POINTER(GpuStats)]),
     "sassy_gpu_host_alloc": (c_void_p, [c_size_t]),
     "sassy_gpu_host_free": (None, [c_void_p]),

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cub/cub.cuh>
+#include <thread>
 
 namespace sb {
 
@@ -55,6 +56,8 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
   nrows_ = pp.nrows, sh0_ = pp.sh0, msk0_ = pp.msk0;
   const char* v = getenv("SASSY_B200_VARIANT");
   if (v && !strcmp(v, "ldg")) variant_ = kVariantLdg;
+  const char* tm = getenv("SASSY_B200_TRANSPORT");
+  if (tm && !strcmp(tm, "bytes")) transport_mode_ = 0;
   const char* fm = getenv("SASSY_B200_FILTER");
   if (fm && !strcmp(fm, "off")) filter_mode_ = 0;
   if (fm && !strcmp(fm, "force")) filter_mode_ = 2;
@@ -74,6 +77,9 @@ Engine::~Engine() {
     b->release();
   if (staged_.d) cudaFree(staged_.d);
   if (h_stage_) cudaFreeHost(h_stage_);
+  if (h_pack_) cudaFreeHost(h_pack_);
+  d_pack_.release();
+  delete pool_;
   for (auto& ev : ev_)
     if (ev) cudaEventDestroy(ev);
   if (stream_) cudaStreamDestroy(stream_);
@@ -87,9 +93,10 @@ DeviceText* Engine::upload_text(const uint8_t* host, uint64_t n) {
   t->alloc = padded_alloc(n);
   try {
     SB_CUDA(cudaMalloc((void**)&t->d, t->alloc));
-    if (n) SB_CUDA(cudaMemcpyAsync(t->d, host, n, cudaMemcpyHostToDevice, stream_));
-    SB_CUDA(cudaMemsetAsync(t->d + n, 0, t->alloc - n, stream_));
+    send_text(t->d, t->alloc, host, n);
     SB_CUDA(cudaStreamSynchronize(stream_));
+    SB_CUDA(cudaEventElapsedTime(&transfer_ms_, ev_[5], ev_[6]));
+    transfer_pending_ = false;
   } catch (...) {
     if (t->d) cudaFree(t->d);
     delete t;
@@ -136,15 +143,68 @@ DeviceText* Engine::stage_text(const uint8_t* host, uint64_t n) {
     staged_.alloc = need;
   }
   staged_.n = n;
-  // Copy in slices so that pinned sources stream at full PCIe rate while the
-  // zero padding is written; the scan is queued behind on the same stream.
-  const uint64_t slice = 256ull << 20;
-  for (uint64_t off = 0; off < n; off += slice) {
-    const uint64_t len = std::min(slice, n - off);
-    SB_CUDA(cudaMemcpyAsync(staged_.d + off, host + off, len, cudaMemcpyHostToDevice, stream_));
-  }
-  SB_CUDA(cudaMemsetAsync(staged_.d + n, 0, std::min<size_t>(staged_.alloc - n, 2ull * kMaxRowBytes + 256), stream_));
+  send_text(staged_.d, staged_.alloc, host, n);
   return &staged_;
+}
+
+// Text transfer.  Large Dna texts go over PCIe at 2 bits per character (transport.cu): the
+// pool packs chunk by chunk into pinned memory, every finished chunk is handed to the copy
+// engine at once, and a streaming kernel expands the text in HBM.  Everything else, and any
+// text holding a byte outside ACGTacgt, is copied as bytes.  The tail padding is zeroed.
+void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint64_t n) {
+  SB_CUDA(cudaEventRecord(ev_[5], stream_));
+  transfer_pending_ = true;
+  transfer_packed_ = false;
+  const size_t pad = std::min<size_t>(dst_alloc - n, 2ull * kMaxRowBytes + 256);
+  bool sent = false;
+  if (transport_mode_ == 1 && profile_ == kDna && n >= (8ull << 20)) {
+    const size_t packed_bytes = (size_t)((n + 63) / 64 * 16);
+    if (packed_bytes > h_pack_cap_) {
+      if (h_pack_) cudaFreeHost(h_pack_);
+      h_pack_ = nullptr;
+      h_pack_cap_ = 0;
+      SB_CUDA(cudaHostAlloc((void**)&h_pack_, packed_bytes, cudaHostAllocDefault));
+      h_pack_cap_ = packed_bytes;
+    }
+    d_pack_.ensure(packed_bytes);
+    if (!pool_) {
+      int nt = (int)std::thread::hardware_concurrency();
+      const char* e = getenv("SASSY_B200_PACK_THREADS");
+      if (e) nt = atoi(e);
+      nt = std::max(1, std::min(nt, 64));
+      pool_ = new PackPool(nt);
+    }
+    const size_t chunk = 32ull << 20;  // characters per chunk (8 MiB packed)
+    // the last group of 64 characters is zero-padded in the staging buffer
+    if (n % 64) memset(h_pack_ + (n / 64) * 16, 0, 16);
+    pool_->start(host, h_pack_, n, chunk);
+    bool clean = true;
+    for (size_t c = 0; c < pool_->chunks(); c++) {
+      clean &= pool_->wait_chunk(c);
+      if (!clean) break;
+      const size_t off = c * (chunk / 4);
+      const size_t len = std::min(chunk / 4, packed_bytes - off);
+      SB_CUDA(cudaMemcpyAsync(d_pack_.as<uint8_t>() + off, h_pack_ + off, len, cudaMemcpyHostToDevice, stream_));
+    }
+    pool_->finish();
+    if (clean) {
+      SB_CUDA(launch_unpack_dna(d_pack_.as<uint8_t>(), dst, n, stream_));
+      // the expansion wrote whole groups of 64: clear what lies beyond the text
+      SB_CUDA(cudaMemsetAsync(dst + n, 0, pad, stream_));
+      transfer_packed_ = true;
+      sent = true;
+    }
+  }
+  if (!sent) {
+    // Copy in slices so that pinned sources stream at full PCIe rate.
+    const uint64_t slice = 256ull << 20;
+    for (uint64_t off = 0; off < n; off += slice) {
+      const uint64_t len = std::min(slice, n - off);
+      SB_CUDA(cudaMemcpyAsync(dst + off, host + off, len, cudaMemcpyHostToDevice, stream_));
+    }
+    SB_CUDA(cudaMemsetAsync(dst + n, 0, pad, stream_));
+  }
+  SB_CUDA(cudaEventRecord(ev_[6], stream_));
 }
 
 // All small per-search inputs travel in ONE host->device copy from a pinned staging
@@ -536,6 +596,12 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   SB_CUDA(cudaEventElapsedTime(&total, ev_[0], ev_[3]));
   stats_.total_ms = total;
   stats_.matches = nsel;
+  if (transfer_pending_) {  // the text of this search came from the host just before it
+    SB_CUDA(cudaEventElapsedTime(&transfer_ms_, ev_[5], ev_[6]));
+    transfer_pending_ = false;
+    stats_.transfer_ms = transfer_ms_;
+    stats_.transfer_packed = transfer_packed_ ? 1 : 0;
+  }
 }
 
 }  // namespace sb

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "transport.h"
 
 namespace sb {
 
@@ -59,6 +60,8 @@ struct SearchStats {
   uint64_t hits = 0;
   uint32_t filter_words = 0, filter_len = 0;
   uint32_t filter_fallback = 0;  // prefilter ran but produced too many hits: full scan used
+  float transfer_ms = 0;         // host->device transfer of the text, when the search got a host text
+  uint32_t transfer_packed = 0;  // 1: sent at 2 bits per character (Dna transport encoding)
 };
 
 struct MatchSet {
@@ -83,6 +86,10 @@ class Engine {
   void free_text(DeviceText* t);
   // Re-usable staging text for the plain search(pattern, text) ABI.
   DeviceText* stage_text(const uint8_t* host, uint64_t n);
+  // 0 = always send bytes; 1 = send large Dna texts at 2 bits per character (default)
+  void set_transport(int mode) { transport_mode_ = mode; }
+  float last_transfer_ms() const { return transfer_ms_; }
+  bool last_transfer_packed() const { return transfer_packed_; }
 
   // Queries must all have length m; forward queries must precede reversed ones.
   // include_pos0: also consider end position 0 (cost m) when m <= k (v1 only,
@@ -100,14 +107,24 @@ class Engine {
  private:
   void upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair);
   void make_tensor_map(CUtensorMap* map, const DeviceText& text, const ScanGeom& g) const;
+  // host -> dst (device, padded): packed transport for large Dna texts, else plain copies
+  void send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint64_t n);
 
   int profile_;
   int device_;
   int variant_;
   int filter_mode_ = 1;
+  int transport_mode_ = 1;
+  float transfer_ms_ = 0;
+  bool transfer_pending_ = false;
+  bool transfer_packed_ = false;
+  PackPool* pool_ = nullptr;
+  uint8_t* h_pack_ = nullptr;  // pinned staging of the packed text
+  size_t h_pack_cap_ = 0;
+  DevBuf d_pack_;
   int sm_count_ = 148;
   cudaStream_t stream_ = nullptr;
-  cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint32_t nrows_, sh0_, msk0_;
 
   DevBuf eq_, patterns_, revflags_;

@@ -319,6 +319,12 @@ int sassy_gpu_set_filter(sassy_SearcherType* searcher, int mode) {
   return 0;
 }
 
+int sassy_gpu_set_transport(sassy_SearcherType* searcher, int mode) {
+  if (!searcher || mode < 0 || mode > 1) return 1;
+  searcher->s.engine().set_transport(mode);
+  return 0;
+}
+
 int sassy_gpu_stats(const sassy_SearcherType* searcher, sassy_gpu_Stats* out) {
   if (!searcher || !out) return 1;
   const sb::SearchStats& st = const_cast<sassy_SearcherType*>(searcher)->s.engine().stats();
@@ -340,6 +346,8 @@ int sassy_gpu_stats(const sassy_SearcherType* searcher, sassy_gpu_Stats* out) {
   out->hits = st.hits;
   out->filter_len = st.filter_len;
   out->filter_fallback = st.filter_fallback;
+  out->transfer_ms = st.transfer_ms;
+  out->transfer_packed = st.transfer_packed;
   return 0;
 }
 

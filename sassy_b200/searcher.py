@@ -251,6 +251,11 @@ class Searcher:
         if self._lib.sassy_gpu_set_filter(self._h, {"off": 0, "auto": 1, "force": 2}[mode]) != 0:
             raise ValueError(mode)
 
+    def set_transport(self, mode: str):
+        """'packed' (default: large Dna host texts cross PCIe at 2 bits per character) or 'bytes'."""
+        if self._lib.sassy_gpu_set_transport(self._h, {"bytes": 0, "packed": 1}[mode]) != 0:
+            raise ValueError(mode)
+
     def stats(self) -> dict:
         st = _native.GpuStats()
         self._lib.sassy_gpu_stats(self._h, ctypes.byref(st))

@@ -187,6 +187,41 @@ def test_prefilter_routes(tma):
     assert [key(m) for m in a] == [key(m) for m in b] and len(a) > 1000
 
 
+def test_dna_packed_transport(tma):
+    """Large Dna host texts cross PCIe at 2 bits per character; results equal the byte transport,
+    mixed case included; a text with a byte outside ACGTacgt is sent as bytes."""
+    import sassy_b200
+    rng = random.Random(27)
+    n = (9 << 20) + 37  # not a multiple of 64
+    table = bytes(b"ACGTacgt"[c & 7] for c in range(256))
+    t = bytearray(rng.randbytes(n).translate(table))
+    p = rand_seq(rng, 24)
+    for pos in (0, 3, 777, n // 2, n - 24, n - 61):
+        t[pos:pos + 24] = p if pos % 2 else p.lower()
+    t = bytes(t)
+    s = sassy_b200.Searcher("dna", rc=True)
+    s.set_transport("bytes")
+    a = s.search(p, t, 2)
+    assert s.stats()["transfer_packed"] == 0
+    s.set_transport("packed")
+    b = s.search(p, t, 2)
+    assert s.stats()["transfer_packed"] == 1
+    assert a == b and len(a) >= 5
+    dt = s.upload_text(t)
+    assert s.search(p, dt, 2) == a
+    dt.free()
+    want = oracle.search("dna", p, t[:200000], 2, rc=True)
+    assert [key(m) for m in s.search(p, t[:200000], 2)] == [key(m) for m in want]  # small text: byte path
+    t2 = bytearray(t)
+    t2[n // 3] = ord("N")
+    s.search(p, bytes(t2), 2)
+    assert s.stats()["transfer_packed"] == 0
+    # the Iupac profile never packs
+    s2 = sassy_b200.Searcher("iupac", rc=False)
+    s2.search(p, t, 1)
+    assert s2.stats()["transfer_packed"] == 0
+
+
 def test_c_abi_search_symbol():
     """The reference's own entry points (include/sassy.h), called as c/example.c does."""
     from sassy_b200 import _native
