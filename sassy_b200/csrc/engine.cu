@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cub/cub.cuh>
+#include <chrono>
 #include <thread>
 
 namespace sb {
@@ -158,26 +159,45 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
   const size_t pad = std::min<size_t>(dst_alloc - n, 2ull * kMaxRowBytes + 256);
   bool sent = false;
   if (transport_mode_ == 1 && profile_ == kDna && n >= (8ull << 20)) {
-    const size_t packed_bytes = (size_t)((n + 63) / 64 * 16);
-    if (packed_bytes > h_pack_cap_) {
-      if (h_pack_) cudaFreeHost(h_pack_);
-      h_pack_ = nullptr;
-      h_pack_cap_ = 0;
-      SB_CUDA(cudaHostAlloc((void**)&h_pack_, packed_bytes, cudaHostAllocDefault));
-      h_pack_cap_ = packed_bytes;
-    }
-    d_pack_.ensure(packed_bytes);
     if (!pool_) {
       int nt = (int)std::thread::hardware_concurrency();
       const char* e = getenv("SASSY_B200_PACK_THREADS");
       if (e) nt = atoi(e);
       nt = std::max(1, std::min(nt, 64));
       pool_ = new PackPool(nt);
+      pack_gbps_ = 5.0 * nt;  // first guess; refined from every transfer
     }
-    const size_t chunk = 32ull << 20;  // characters per chunk (8 MiB packed)
+    const size_t chunk = 8ull << 20;  // characters per chunk (2 MiB packed): the first copy starts early
+    // Packing (host cores) and PCIe run concurrently; when the source is pinned the tail of the
+    // text is sent as plain bytes so that both finish together:
+    //   f * n / Rp = (f * n / 4 + (1 - f) * n) / Rc   =>   f = Rp / (Rc + 0.75 Rp)
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // unregistered memory is not an error here
+    double f = 1.0;
+    if (pinned) f = std::min(1.0, pack_gbps_ / (pcie_gbps_ + 0.75 * pack_gbps_));
+    uint64_t n_packed = (uint64_t)(f * (double)n) / chunk * chunk;
+    if (n_packed + chunk > n) n_packed = n;  // no tiny raw tail
+    const size_t packed_bytes = (size_t)((n_packed + 63) / 64 * 16);
+    if (packed_bytes > h_pack_cap_) {
+      if (h_pack_) cudaFreeHost(h_pack_);
+      h_pack_ = nullptr;
+      h_pack_cap_ = 0;
+      const size_t want = (size_t)((n + 63) / 64 * 16);
+      SB_CUDA(cudaHostAlloc((void**)&h_pack_, want, cudaHostAllocDefault));
+      h_pack_cap_ = want;
+    }
+    d_pack_.ensure(h_pack_cap_);
     // the last group of 64 characters is zero-padded in the staging buffer
-    if (n % 64) memset(h_pack_ + (n / 64) * 16, 0, 16);
-    pool_->start(host, h_pack_, n, chunk);
+    if (n_packed % 64) memset(h_pack_ + (n_packed / 64) * 16, 0, 16);
+    const auto t0 = std::chrono::steady_clock::now();
+    pool_->start(host, h_pack_, n_packed, chunk);
+    // plain-byte tail first: it keeps the copy engine busy while the first chunks are packed
+    const uint64_t slice = 64ull << 20;
+    for (uint64_t off = n_packed; off < n; off += slice) {
+      const uint64_t len = std::min(slice, n - off);
+      SB_CUDA(cudaMemcpyAsync(dst + off, host + off, len, cudaMemcpyHostToDevice, stream_));
+    }
     bool clean = true;
     for (size_t c = 0; c < pool_->chunks(); c++) {
       clean &= pool_->wait_chunk(c);
@@ -186,9 +206,11 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
       const size_t len = std::min(chunk / 4, packed_bytes - off);
       SB_CUDA(cudaMemcpyAsync(d_pack_.as<uint8_t>() + off, h_pack_ + off, len, cudaMemcpyHostToDevice, stream_));
     }
+    const double pack_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     pool_->finish();
     if (clean) {
-      SB_CUDA(launch_unpack_dna(d_pack_.as<uint8_t>(), dst, n, stream_));
+      if (pack_s > 1e-4) pack_gbps_ = 0.5 * pack_gbps_ + 0.5 * ((double)n_packed / pack_s / 1e9);
+      SB_CUDA(launch_unpack_dna(d_pack_.as<uint8_t>(), dst, n_packed, stream_));
       // the expansion wrote whole groups of 64: clear what lies beyond the text
       SB_CUDA(cudaMemsetAsync(dst + n, 0, pad, stream_));
       transfer_packed_ = true;

@@ -119,6 +119,8 @@ class Engine {
   bool transfer_pending_ = false;
   bool transfer_packed_ = false;
   PackPool* pool_ = nullptr;
+  double pack_gbps_ = 40.0;  // measured host packing rate (characters/s), refined per transfer
+  double pcie_gbps_ = 52.0;  // pinned host->device copy rate assumed for the split
   uint8_t* h_pack_ = nullptr;  // pinned staging of the packed text
   size_t h_pack_cap_ = 0;
   DevBuf d_pack_;

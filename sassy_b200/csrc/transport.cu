@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -105,6 +106,7 @@ __attribute__((target("avx512f,avx512bw"))) bool pack_avx512(const uint8_t* src,
   __mmask64 all_ok = ~(__mmask64)0;
   size_t i = 0;
   for (; i + 64 <= n; i += 64) {
+    _mm_prefetch(reinterpret_cast<const char*>(src + i + 1024), _MM_HINT_NTA);
     const __m512i v = _mm512_loadu_si512(src + i);
     const __m512i u = _mm512_and_si512(v, up);
     all_ok &= _mm512_cmpeq_epi8_mask(u, cA) | _mm512_cmpeq_epi8_mask(u, cC) | _mm512_cmpeq_epi8_mask(u, cG) |
@@ -112,8 +114,10 @@ __attribute__((target("avx512f,avx512bw"))) bool pack_avx512(const uint8_t* src,
     const __m512i codes = _mm512_and_si512(_mm512_srli_epi16(v, 1), three);
     const __m512i pairs = _mm512_maddubs_epi16(codes, m1);
     const __m512i quads = _mm512_madd_epi16(pairs, m2);
-    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + (i >> 2)), _mm512_cvtepi32_epi8(quads));
+    // dst chunks start on 16-byte boundaries: streaming store, no read-for-ownership
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + (i >> 2)), _mm512_cvtepi32_epi8(quads));
   }
+  _mm_sfence();
   bool ok = all_ok == ~(__mmask64)0;
   if (i < n) ok &= pack_scalar(src + i, dst + (i >> 2), n - i);
   return ok;
@@ -228,7 +232,9 @@ size_t PackPool::chunks() const { return impl_->nchunks; }
 
 bool PackPool::wait_chunk(size_t c) {
   uint8_t v;
-  while ((v = impl_->done[c].load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+  // sleep rather than spin: the workers own every core
+  while ((v = impl_->done[c].load(std::memory_order_acquire)) == 0)
+    std::this_thread::sleep_for(std::chrono::microseconds(30));
   return v == 1;
 }
 
