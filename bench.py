@@ -156,8 +156,11 @@ class ClockSampler:
             self.err = str(e)
 
     def sample(self, step: int = 0):
-        if self.h is None or step % self.every:
+        # NVML queries cost up to a millisecond: at most one sample per 50 ms of wall time
+        now = time.perf_counter()
+        if self.h is None or now - getattr(self, "_last", 0.0) < 0.05:
             return
+        self._last = now
         nv = self.nv
         try:
             self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
@@ -369,8 +372,9 @@ def main():
         est = s.stats()
         packed = bool(est["transfer_packed"])
         e2e = {"value": total_bytes * e_steps / e_el / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": ((n + 63) // 64 * 16 if packed else n) + tables + len(pats) * m,
-               "transport": "2 bits per character, packed by host threads inside the timed region" if packed else "bytes",
+               "h2d_bytes_per_step": est["transfer_bytes"] + tables + len(pats) * m,
+               "transport": ("head of the text at 2 bits per character (packed by host threads inside the timed "
+                             "region), tail as bytes, split so that packing and PCIe finish together") if packed else "bytes",
                "transfer_ms": est["transfer_ms"],
                "d2h_bytes_per_step": len(e_matches) // max(1, world) * (24 + 4 * ((m + k + 1 + 15) // 16)) + 16,
                "ms_per_step": e_el / e_steps * 1e3, "steps": e_steps}

@@ -69,7 +69,8 @@ typedef struct sassy_gpu_Stats {
   uint32_t filter_len;    /* piece length */
   uint32_t filter_fallback; /* 1: prefilter produced too many hits, the full scan was used */
   float transfer_ms;        /* host->device transfer of the text (host-text entry points) */
-  uint32_t transfer_packed; /* 1: the text crossed PCIe at 2 bits per character (Dna) */
+  uint32_t transfer_packed; /* 1: (part of) the text crossed PCIe at 2 bits per character (Dna) */
+  uint64_t transfer_bytes;  /* bytes that crossed PCIe for the text */
 } sassy_gpu_Stats;
 
 #ifdef __cplusplus

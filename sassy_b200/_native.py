@@ -71,6 +71,7 @@ class GpuStats(ctypes.Structure):
         ("filter_fallback", ctypes.c_uint32),
         ("transfer_ms", ctypes.c_float),
         ("transfer_packed", ctypes.c_uint32),
+        ("transfer_bytes", ctypes.c_uint64),
     ]
 
 

@@ -214,10 +214,12 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
       // the expansion wrote whole groups of 64: clear what lies beyond the text
       SB_CUDA(cudaMemsetAsync(dst + n, 0, pad, stream_));
       transfer_packed_ = true;
+      transfer_bytes_ = packed_bytes + (n - n_packed);
       sent = true;
     }
   }
   if (!sent) {
+    transfer_bytes_ = n;
     // Copy in slices so that pinned sources stream at full PCIe rate.
     const uint64_t slice = 256ull << 20;
     for (uint64_t off = 0; off < n; off += slice) {
@@ -623,6 +625,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     transfer_pending_ = false;
     stats_.transfer_ms = transfer_ms_;
     stats_.transfer_packed = transfer_packed_ ? 1 : 0;
+    stats_.transfer_bytes = transfer_bytes_;
   }
 }
 

@@ -62,6 +62,7 @@ struct SearchStats {
   uint32_t filter_fallback = 0;  // prefilter ran but produced too many hits: full scan used
   float transfer_ms = 0;         // host->device transfer of the text, when the search got a host text
   uint32_t transfer_packed = 0;  // 1: sent at 2 bits per character (Dna transport encoding)
+  uint64_t transfer_bytes = 0;   // bytes that crossed PCIe for the text
 };
 
 struct MatchSet {
@@ -117,6 +118,7 @@ class Engine {
   int transport_mode_ = 1;
   float transfer_ms_ = 0;
   bool transfer_pending_ = false;
+  uint64_t transfer_bytes_ = 0;
   bool transfer_packed_ = false;
   PackPool* pool_ = nullptr;
   double pack_gbps_ = 40.0;  // measured host packing rate (characters/s), refined per transfer

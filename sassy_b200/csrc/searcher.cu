@@ -348,6 +348,7 @@ int sassy_gpu_stats(const sassy_SearcherType* searcher, sassy_gpu_Stats* out) {
   out->filter_fallback = st.filter_fallback;
   out->transfer_ms = st.transfer_ms;
   out->transfer_packed = st.transfer_packed;
+  out->transfer_bytes = st.transfer_bytes;
   return 0;
 }
 
