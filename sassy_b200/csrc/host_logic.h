@@ -225,16 +225,21 @@ inline void build_filter_table(int profile, const FilterPlan& f, const uint8_t* 
 // Pair table of the two-characters-per-step automaton (Dna profile only):
 // tab[first | second << 2] = {A[WF], B[WF]}, see filter16_pair in scan_core.cuh.
 inline void build_pair_table(const FilterPlan& f, const uint8_t* pat, uint32_t* tab) {
-  std::vector<uint32_t> byte_tab((size_t)256 * f.WF);
-  build_filter_table(kDna, f, pat, byte_tab.data());
+  // masks of the four character classes (instead of all 256 bytes of the byte-indexed table)
+  uint32_t cls[4][kMaxFilterWords] = {};
+  for (int c = 0; c < 4; c++)
+    for (int p = 0; p < f.npieces; p++) {
+      const FilterPiece& pc = f.piece[p];
+      for (int j = 0; j < pc.len; j++)
+        if (row_matches<kDna>(pat[pc.off + j], c)) cls[c][pc.word] |= 1u << (pc.bit + j);
+      for (int d = 0; d < kFilterDelay; d++) cls[c][pc.word] |= 1u << (pc.bit + pc.len + d);
+    }
   for (int c1 = 0; c1 < 4; c1++)
     for (int c0 = 0; c0 < 4; c0++) {
       uint32_t* e = tab + (size_t)(c0 | (c1 << 2)) * 2 * f.WF;
-      const uint32_t* e0 = &byte_tab[(size_t)(c0 << 1) * f.WF];  // any byte of class c0: (byte >> 1) & 3 == c0
-      const uint32_t* e1 = &byte_tab[(size_t)(c1 << 1) * f.WF];
       for (int w = 0; w < f.WF; w++) {
-        e[w] = (e0[w] << 1) & e1[w];
-        e[f.WF + w] = (((f.finit[w] & e0[w]) << 1) | f.finit[w]) & e1[w];
+        e[w] = (cls[c0][w] << 1) & cls[c1][w];
+        e[f.WF + w] = (((f.finit[w] & cls[c0][w]) << 1) | f.finit[w]) & cls[c1][w];
       }
     }
 }

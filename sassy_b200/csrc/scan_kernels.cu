@@ -301,28 +301,34 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
   Lane<W> s;
   lane_reset<W>(s, a.m);
   const int64_t nchunks = c_hi - c_lo;
+  // 32-bit scan-direction offsets relative to w0 keep the per-character bookkeeping to one
+  // add and one unsigned compare; words and bytes of a chunk are put into scan order once
+  // per chunk (SEL / PRMT) so that the unrolled loops index registers statically.
+  const uint32_t wlen = (uint32_t)(end - w0);
+  const int32_t emit_rel = (int32_t)(emit_from - w0);
+  const uint32_t byte_order = rev ? 0x0123u : 0x3210u;
   int64_t c = rev ? c_hi - 1 : c_lo;  // chunks in scan order
   uint4 cur = __ldg(chunks + c);
   for (int64_t t = 0; t < nchunks; t++) {
     const int64_t cn = rev ? c - 1 : c + 1;
     uint4 nxt = make_uint4(0, 0, 0, 0);
     if (t + 1 < nchunks) nxt = __ldg(chunks + cn);
-    const uint32_t words[4] = {cur.x, cur.y, cur.z, cur.w};
+    // scan-direction offset of the chunk's first character in scan order
+    const int32_t rel0 = rev ? (int32_t)((n - 1 - ((c << 4) + 15)) - w0) : (int32_t)((c << 4) - w0);
+    const uint32_t words[4] = {rev ? cur.w : cur.x, rev ? cur.z : cur.y, rev ? cur.y : cur.z, rev ? cur.x : cur.w};
 #pragma unroll
-    for (int jj = 0; jj < 4; jj++) {
-      const int j = rev ? 3 - jj : jj;
-      const uint32_t pre = (words[j] >> a.sh0) & a.msk0;
+    for (int j = 0; j < 4; j++) {
+      const uint32_t wv = __byte_perm(words[j], 0u, byte_order);
+      const uint32_t pre = (wv >> a.sh0) & a.msk0;
 #pragma unroll
-      for (int bb = 0; bb < 4; bb++) {
-        const int b = rev ? 3 - bb : bb;
-        const int64_t fidx = (c << 4) + 4 * j + b;
-        const int64_t idx = rev ? n - 1 - fidx : fidx;  // scan-direction index
-        if (idx >= w0 && idx < end) {
+      for (int b = 0; b < 4; b++) {
+        const int32_t srel = rel0 + 4 * j + b;
+        if ((uint32_t)srel < wlen) {
           const uint32_t row = (pre >> (8 * b)) & 0xFFu;
           myers_step<W>(s, eq + row * W);
-          if (idx >= emit_from) {
+          if (srel >= emit_rel) {
             const int score = lane_score<W>(s);
-            if (score <= a.k) emit_candidate(a, qs, (uint64_t)idx + 1, score);
+            if (score <= a.k) emit_candidate(a, qs, (uint64_t)(w0 + srel) + 1, score);
           }
         }
       }
