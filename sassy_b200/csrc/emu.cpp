@@ -72,14 +72,25 @@ void filter_rows(const ScanArgs& a, const uint32_t* feq_q, uint32_t qs, bool pai
       stage_coord<REV>(a.g, it, (int64_t)row, r, col, own);
       const uint64_t stage_idx = (uint64_t)(r * (int64_t)a.g.ltot + (int64_t)col);
       const bool valid = r >= 0 && r < (int64_t)a.g.rows;
-      uint32_t mask = 0;
+      uint32_t mask = 0, mask1 = 0;
       for (int cc = 0; cc < kStageBytes / 16; cc++) {
         const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
         uint32_t x[4] = {0, 0, 0, 0};
         if (valid) memcpy(x, a.text + stage_idx + 16u * c, 16);
-        if (pair ? filter16_pair<WF, REV>(s, x, eqt) : filter16<WF, REV>(s, x, eqt)) mask |= 1u << c;
+        uint32_t acc[2];
+        if (pair)
+          filter16_pair<WF, REV>(s, x, eqt, acc);
+        else
+          filter16<WF, REV>(s, x, eqt, acc);
+        if (acc[0]) mask |= 1u << c;
+        if (acc[1]) mask1 |= 1u << c;
       }
-      if (mask) emit_stage_hits(a, HitQueue{nullptr, nullptr}, qs, stage_idx, mask, own);
+      if (a.fused) {
+        if (mask) emit_stage_hits(a, HitQueue{nullptr, nullptr}, qs, stage_idx, mask, own);
+        if (mask1) emit_stage_hits(a, HitQueue{nullptr, nullptr}, qs + a.nq, stage_idx, mask1, own);
+      } else if (mask | mask1) {
+        emit_stage_hits(a, HitQueue{nullptr, nullptr}, qs, stage_idx, mask | mask1, own);
+      }
     }
   }
 }
@@ -198,33 +209,45 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   FilterPlan fp;
   if (use_filter != 0) fp = plan_filter(profile, qptr.data(), nq, m, k, use_filter > 0 ? 1e30 : 0.85);
   res->hits = 0;
-  res->filter_words = fp.enabled ? fp.WF : 0;
+  res->filter_words = fp.enabled ? fp.WF : 0;  // per strand
   res->filter_len = fp.enabled ? fp.L : 0;
   if (n > 0 && fp.enabled) {
-    const bool pair = profile == kDna && fp.WF <= 2;
-    const size_t tab_words = pair ? (size_t)kPairTableWords * fp.WF : (size_t)256 * fp.WF;
-    std::vector<uint32_t> feq((size_t)nq * tab_words + 4);
-    for (uint32_t q = 0; q < nq; q++) {
+    uint32_t nfwd = 0;
+    while (nfwd < nq && !rev[nfwd]) nfwd++;
+    const bool fused = nfwd > 0 && nq == 2 * nfwd && fp.WF <= 2;  // as Engine::search
+    const int WT = fused ? 2 * fp.WF : fp.WF;
+    const size_t ntab = fused ? nfwd : nq;
+    const bool pair = profile == kDna && WT <= 2;
+    const size_t tab_words = pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT;
+    std::vector<uint32_t> feq(ntab * tab_words + 4);
+    for (uint32_t q = 0; q < ntab; q++) {
+      const uint8_t* partner = fused ? qptr[q + nfwd] : nullptr;
       if (pair)
-        build_pair_table(fp, qptr[q], &feq[q * tab_words]);
+        build_pair_table(fp, qptr[q], &feq[q * tab_words], partner);
       else
-        build_filter_table(profile, fp, qptr[q], &feq[q * tab_words]);
+        build_filter_table(profile, fp, qptr[q], &feq[q * tab_words], partner);
     }
     std::vector<uint64_t> hits((size_t)nq * (n / kHitChars + 2) + 16);
     unsigned long long nhits = 0;
     ScanArgs f = a;
     f.g.nwarm = 1;
     for (int w = 0; w < kMaxFilterWords; w++) f.finit[w] = fp.finit[w], f.fdelay[w] = fp.fdelay[w];
+    if (fused)
+      for (int w = 0; w < fp.WF; w++) f.finit[fp.WF + w] = fp.finit[w], f.fdelay[fp.WF + w] = fp.fdelay[w];
+    f.fused = fused ? 1 : 0;
+    f.nq = fused ? nfwd : nq;
     f.hit_keys = hits.data();
     f.hit_count = &nhits;
     f.hit_cap = hits.size();
-    for (uint32_t q = 0; q < nq; q++) {
+    for (uint32_t q = 0; q < ntab; q++) {
       const uint32_t* feq_q = &feq[q * tab_words];
       if (rev[q])
-        filter_dispatch<true>(fp.WF, f, feq_q, q, pair);
+        filter_dispatch<true>(WT, f, feq_q, q, pair);
       else
-        filter_dispatch<false>(fp.WF, f, feq_q, q, pair);
+        filter_dispatch<false>(WT, f, feq_q, q, pair);
     }
+    if (fused)
+      for (int p = 0; p < fp.npieces; p++) a.rev_lead = std::max<uint32_t>(a.rev_lead, (uint32_t)fp.piece[p].len);
     res->hits = nhits;
     for (unsigned long long h = 0; h < nhits; h++) {
       const uint32_t qs = key_qs(hits[h]);

@@ -62,6 +62,8 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
   const char* fm = getenv("SASSY_B200_FILTER");
   if (fm && !strcmp(fm, "off")) filter_mode_ = 0;
   if (fm && !strcmp(fm, "force")) filter_mode_ = 2;
+  const char* fs = getenv("SASSY_B200_FUSE_STRANDS");
+  if (fs && !strcmp(fs, "0")) fuse_strands_ = false;
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
@@ -233,18 +235,21 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
 
 // All small per-search inputs travel in ONE host->device copy from a pinned staging
 // buffer: [4 counters][equality tables][query bytes][direction flags][prefilter tables].
-void Engine::upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair) {
+void Engine::upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair,
+                           bool fused) {
   const size_t nq = queries.size();
   const size_t eq_bytes = nq * nrows_ * W * sizeof(uint32_t);
   const size_t pat_bytes = nq * (size_t)m;
-  const size_t tab_words = !fp.enabled ? 0 : (pair ? (size_t)kPairTableWords * fp.WF : (size_t)256 * fp.WF);
+  const int WT = fused ? 2 * fp.WF : fp.WF;  // automaton words per filter table
+  const size_t ntab = fused ? nq / 2 : nq;
+  const size_t tab_words = !fp.enabled ? 0 : (pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT);
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   off_counts_ = 0;
   off_eq_ = align(4 * sizeof(unsigned long long));
   off_pat_ = off_eq_ + align(eq_bytes);
   off_rev_ = off_pat_ + align(pat_bytes);
   off_feq_ = off_rev_ + align(nq);
-  const size_t total = off_feq_ + align(nq * tab_words * sizeof(uint32_t));
+  const size_t total = off_feq_ + align(ntab * tab_words * sizeof(uint32_t));
   if (total > stage_cap_) {
     if (h_stage_) cudaFreeHost(h_stage_);
     h_stage_ = nullptr;
@@ -260,11 +265,12 @@ void Engine::upload_params(const std::vector<Query>& queries, int m, int W, cons
     memcpy(h_stage_ + off_pat_ + q * m, queries[q].bytes, m);
     h_stage_[off_rev_ + q] = queries[q].rev ? 1 : 0;
     build_eq_table(profile_, queries[q].bytes, m, W, nrows_, h_eq + q * nrows_ * W);
-    if (fp.enabled) {
+    if (fp.enabled && q < ntab) {
+      const uint8_t* partner = fused ? queries[q + ntab].bytes : nullptr;  // the reversed partner query
       if (pair)
-        build_pair_table(fp, queries[q].bytes, h_feq + q * tab_words);
+        build_pair_table(fp, queries[q].bytes, h_feq + q * tab_words, partner);
       else
-        build_filter_table(profile_, fp, queries[q].bytes, h_feq + q * tab_words);
+        build_filter_table(profile_, fp, queries[q].bytes, h_feq + q * tab_words, partner);
     }
   }
   SB_CUDA(cudaMemcpyAsync(d_stage_.p, h_stage_, total, cudaMemcpyHostToDevice, stream_));
@@ -320,9 +326,13 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   // Dna: two characters per step through the class-pair table; others: byte-indexed table
   // (the pair table of a 4-word automaton has 512 distinct bytes per warp access: shared-memory
   //  bandwidth, not instructions, would bound it -- measured 2.4x slower than the byte table)
-  const bool pair = profile_ == kDna && fp.WF <= 2;
-  const size_t tab_words = pair ? (size_t)kPairTableWords * fp.WF : (size_t)256 * fp.WF;
-  upload_params(queries, m, W, fp, pair);
+  // Both strands of a v1 search (forward queries followed by their reversed partners) share ONE
+  // forward pass: the partner's pieces, matched back to front, occupy a second set of words.
+  const bool fused = fp.enabled && fuse_strands_ && nfwd > 0 && nq == 2 * nfwd && fp.WF <= 2;
+  const int WT = fused ? 2 * fp.WF : fp.WF;
+  const bool pair = profile_ == kDna && WT <= 2;
+  const size_t tab_words = pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT;
+  upload_params(queries, m, W, fp, pair, fused);
   uint8_t* dst = d_stage_.as<uint8_t>();
   unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(dst + off_counts_);
   unsigned long long* d_cand_count = d_counts;      // [0] candidates
@@ -403,7 +413,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       if (want > hit_cap_) hit_cap_ = want;
     }
     hits_.ensure(hit_cap_ * sizeof(uint64_t));
-    const int focc = filter_blocks_per_sm(fp.WF, variant_);
+    const int focc = filter_blocks_per_sm(WT, variant_);
     ScanGeom gf = choose_geom(n, m, k, nq, focc * sm_count_);
     gf.nwarm = 1;  // a piece plus its delay line is at most 32 characters
     CUtensorMap ftmap;
@@ -413,6 +423,9 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     ScanArgs f = a;
     f.g = gf;
     for (int w = 0; w < kMaxFilterWords; w++) f.finit[w] = fp.finit[w], f.fdelay[w] = fp.fdelay[w];
+    if (fused)
+      for (int w = 0; w < fp.WF; w++) f.finit[fp.WF + w] = fp.finit[w], f.fdelay[fp.WF + w] = fp.fdelay[w];
+    f.fused = fused ? 1 : 0;
     f.hit_keys = hits_.as<uint64_t>();
     f.hit_count = d_hit_count;
     f.hit_cap = hit_cap_;
@@ -421,10 +434,10 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       f.nq = nfwd;
       f.qs_base = 0;
       f.feq = d_feq;
-      SB_CUDA(launch_filter(fp.WF, false, variant_, pair, &ftmap, f, stream_));
+      SB_CUDA(launch_filter(WT, false, variant_, pair, &ftmap, f, stream_));
       stats_.scan_launches++;
     }
-    if (nq > nfwd) {
+    if (nq > nfwd && !fused) {
       f.nq = nq - nfwd;
       f.qs_base = nfwd;
       f.feq = d_feq + (size_t)nfwd * tab_words;
@@ -440,6 +453,8 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     v.hit_keys = hits_.as<uint64_t>();
     v.hit_count = d_hit_count;
     v.hit_cap = hit_cap_;
+    if (fused)  // a reversed query's hit marks the START of its piece in scan direction
+      for (int p = 0; p < fp.npieces; p++) v.rev_lead = std::max<uint32_t>(v.rev_lead, (uint32_t)fp.piece[p].len);
     SB_CUDA(launch_verify(W, v, d_rev, stream_));
     stats_.aux_launches++;
     SB_CUDA(cudaEventRecord(ev_[4], stream_));
@@ -448,7 +463,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     stats_.verify_ms = elapsed(ev_[2], ev_[4]);
     unsigned long long nhits = h_counts[2];
     stats_.hits = nhits;
-    stats_.filter_words = (uint32_t)fp.WF;
+    stats_.filter_words = (uint32_t)WT;
     stats_.filter_len = (uint32_t)fp.L;
     // too many hits (repetitive text, unlucky pieces): the re-scan costs more than the scan
     const double rescan = (double)nhits * (2.0 * (m + k) + kHitChars);

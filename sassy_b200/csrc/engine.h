@@ -106,7 +106,7 @@ class Engine {
   void set_filter_mode(int m) { filter_mode_ = m; }
 
  private:
-  void upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair);
+  void upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair, bool fused);
   void make_tensor_map(CUtensorMap* map, const DeviceText& text, const ScanGeom& g) const;
   // host -> dst (device, padded): packed transport for large Dna texts, else plain copies
   void send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint64_t n);
@@ -115,6 +115,7 @@ class Engine {
   int device_;
   int variant_;
   int filter_mode_ = 1;
+  bool fuse_strands_ = true;
   int transport_mode_ = 1;
   float transfer_ms_ = 0;
   bool transfer_pending_ = false;

@@ -197,49 +197,61 @@ inline FilterPlan plan_filter(int profile, const uint8_t* const* queries, size_t
   return best;
 }
 
-// Filter automaton masks of one query: tab[byte][WF].
-inline void build_filter_table(int profile, const FilterPlan& f, const uint8_t* pat, uint32_t* tab) {
+// Automaton masks of the text class `row` for one query.  reversed = the query is the
+// reversed partner (scanned over the reversed text by the reference) but the automaton
+// scans the text FORWARD (strand-fused prefilter): every piece is matched back to front.
+inline void class_masks(int profile, const FilterPlan& f, const uint8_t* pat, bool reversed, int row,
+                        uint32_t* out /*[f.WF]*/) {
+  for (int w = 0; w < f.WF; w++) out[w] = 0;
+  for (int p = 0; p < f.npieces; p++) {
+    const FilterPiece& pc = f.piece[p];
+    for (int j = 0; j < pc.len; j++) {
+      const uint8_t ch = pat[pc.off + (reversed ? pc.len - 1 - j : j)];
+      bool match;
+      switch (profile) {
+        case kDna: match = row_matches<kDna>(ch, row); break;
+        case kIupac: match = row_matches<kIupac>(ch, row); break;
+        default: match = row_matches<kAscii>(ch, row); break;
+      }
+      if (match) out[pc.word] |= 1u << (pc.bit + j);
+    }
+    for (int d = 0; d < kFilterDelay; d++) out[pc.word] |= 1u << (pc.bit + pc.len + d);
+  }
+}
+
+// Filter automaton masks: tab[byte][WF_total].  pat_rev != nullptr builds the strand-fused
+// automaton: words [0, f.WF) for `pat`, words [f.WF, 2 f.WF) for the reversed partner.
+inline void build_filter_table(int profile, const FilterPlan& f, const uint8_t* pat, uint32_t* tab,
+                               const uint8_t* pat_rev = nullptr) {
   ProfileParams pp;
   profile_params(profile, pp);
-  memset(tab, 0, (size_t)256 * f.WF * sizeof(uint32_t));
+  const int WT = pat_rev ? 2 * f.WF : f.WF;
   for (int byte = 0; byte < 256; byte++) {
-    uint32_t* e = tab + (size_t)byte * f.WF;
+    uint32_t* e = tab + (size_t)byte * WT;
     const int row = (int)(((uint32_t)byte >> pp.sh0) & (pp.msk0 & 0xFFu));
-    for (int p = 0; p < f.npieces; p++) {
-      const FilterPiece& pc = f.piece[p];
-      for (int j = 0; j < pc.len; j++) {
-        const uint8_t ch = pat[pc.off + j];
-        bool match;
-        switch (profile) {
-          case kDna: match = row_matches<kDna>(ch, row); break;
-          case kIupac: match = row_matches<kIupac>(ch, row); break;
-          default: match = row_matches<kAscii>(ch, row); break;
-        }
-        if (match) e[pc.word] |= 1u << (pc.bit + j);
-      }
-      for (int d = 0; d < kFilterDelay; d++) e[pc.word] |= 1u << (pc.bit + pc.len + d);
-    }
+    class_masks(profile, f, pat, false, row, e);
+    if (pat_rev) class_masks(profile, f, pat_rev, true, row, e + f.WF);
   }
 }
 
 // Pair table of the two-characters-per-step automaton (Dna profile only):
-// tab[first | second << 2] = {A[WF], B[WF]}, see filter16_pair in scan_core.cuh.
-inline void build_pair_table(const FilterPlan& f, const uint8_t* pat, uint32_t* tab) {
-  // masks of the four character classes (instead of all 256 bytes of the byte-indexed table)
-  uint32_t cls[4][kMaxFilterWords] = {};
-  for (int c = 0; c < 4; c++)
-    for (int p = 0; p < f.npieces; p++) {
-      const FilterPiece& pc = f.piece[p];
-      for (int j = 0; j < pc.len; j++)
-        if (row_matches<kDna>(pat[pc.off + j], c)) cls[c][pc.word] |= 1u << (pc.bit + j);
-      for (int d = 0; d < kFilterDelay; d++) cls[c][pc.word] |= 1u << (pc.bit + pc.len + d);
-    }
+// tab[first | second << 2] = {A[WT], B[WT]}, see filter16_pair in scan_core.cuh.
+inline void build_pair_table(const FilterPlan& f, const uint8_t* pat, uint32_t* tab,
+                             const uint8_t* pat_rev = nullptr) {
+  const int WT = pat_rev ? 2 * f.WF : f.WF;
+  uint32_t cls[4][2 * kMaxFilterWords] = {};
+  uint32_t init[2 * kMaxFilterWords] = {};
+  for (int w = 0; w < f.WF; w++) init[w] = f.finit[w], init[f.WF + w] = f.finit[w];
+  for (int c = 0; c < 4; c++) {
+    class_masks(kDna, f, pat, false, c, cls[c]);
+    if (pat_rev) class_masks(kDna, f, pat_rev, true, c, cls[c] + f.WF);
+  }
   for (int c1 = 0; c1 < 4; c1++)
     for (int c0 = 0; c0 < 4; c0++) {
-      uint32_t* e = tab + (size_t)(c0 | (c1 << 2)) * 2 * f.WF;
-      for (int w = 0; w < f.WF; w++) {
+      uint32_t* e = tab + (size_t)(c0 | (c1 << 2)) * 2 * WT;
+      for (int w = 0; w < WT; w++) {
         e[w] = (cls[c0][w] << 1) & cls[c1][w];
-        e[f.WF + w] = (((f.finit[w] & cls[c0][w]) << 1) | f.finit[w]) & cls[c1][w];
+        e[WT + w] = (((init[w] & cls[c0][w]) << 1) | init[w]) & cls[c1][w];
       }
     }
 }

@@ -74,6 +74,8 @@ struct ScanArgs {
   const uint32_t* feq;      // [nq][256][WF] filter automaton masks, indexed by the raw text byte
   uint32_t finit[kMaxFilterWords];   // first bit of every piece
   uint32_t fdelay[kMaxFilterWords];  // delay-line bits behind every piece
+  uint32_t rev_lead;        // strand-fused prefilter: extra window length for hits of reversed queries
+  uint32_t fused;           // 1: automaton words [WF/2, WF) belong to the reversed partner query (slot + nq)
   uint64_t* hit_keys;       // (query slot << 40) | forward index of the hit's 16-byte text chunk / 16
   unsigned long long* hit_count;
   uint64_t hit_cap;
@@ -389,9 +391,12 @@ static void emit_stage_hits(const ScanArgs& a, HitQueue hq, uint32_t qs, uint64_
 
 // 16 text bytes through the automaton.  Returns non-zero iff a piece occurrence ended
 // inside the chunk (the hit mask is sampled after every text word, see above).
+// acc[0] collects the hit bits of automaton words [0, max(1, WF/2)), acc[1] those of the rest
+// (the reversed partner query when the two strands share one pass).
 template <int WF, bool REV>
-SB_HD uint32_t filter16(FLane<WF>& s, const uint32_t (&x)[4], const EqTab& feq) {
-  uint32_t acc = 0;
+SB_HD void filter16(FLane<WF>& s, const uint32_t (&x)[4], const EqTab& feq, uint32_t (&acc)[2]) {
+  constexpr int kHalf = WF > 1 ? WF / 2 : 1;
+  acc[0] = acc[1] = 0;
 #pragma unroll
   for (int ww = 0; ww < 4; ww++) {
     const int w4 = REV ? 3 - ww : ww;
@@ -404,9 +409,8 @@ SB_HD uint32_t filter16(FLane<WF>& s, const uint32_t (&x)[4], const EqTab& feq) 
       for (int w = 0; w < WF; w++) s.st[w] = ((s.st[w] << 1) | s.init[w]) & eq[w];
     }
 #pragma unroll
-    for (int w = 0; w < WF; w++) acc |= s.st[w] & s.delay[w];
+    for (int w = 0; w < WF; w++) acc[w < kHalf ? 0 : 1] |= s.st[w] & s.delay[w];
   }
-  return acc;
 }
 
 // Two-characters-per-step form of the same automaton for the Dna profile (4 character
@@ -443,10 +447,11 @@ SB_HD void load_pair(uint32_t (&ab)[2 * WF], const EqTab& t, uint32_t off) {
 // byte of the result IS the table offset of a pair (8 bytes per entry for WF = 1, 16 for
 // WF = 2; WF = 4 doubles the 16-byte offsets).
 template <int WF, bool REV>
-SB_HD uint32_t filter16_pair(FLane<WF>& s, const uint32_t (&x)[4], const EqTab& ftab) {
+SB_HD void filter16_pair(FLane<WF>& s, const uint32_t (&x)[4], const EqTab& ftab, uint32_t (&acc)[2]) {
   constexpr int kSh = WF == 1 ? 2 : 3;
   constexpr uint32_t kMask = WF == 1 ? 0x18181818u : 0x30303030u;
-  uint32_t acc = 0;
+  constexpr int kHalf = WF > 1 ? WF / 2 : 1;
+  acc[0] = acc[1] = 0;
 #pragma unroll
   for (int ww = 0; ww < 4; ww++) {
     const int w4 = REV ? 3 - ww : ww;
@@ -468,9 +473,8 @@ SB_HD uint32_t filter16_pair(FLane<WF>& s, const uint32_t (&x)[4], const EqTab& 
       for (int w = 0; w < WF; w++) s.st[w] = ((s.st[w] << 2) & ab[w]) | ab[WF + w];
     }
 #pragma unroll
-    for (int w = 0; w < WF; w++) acc |= s.st[w] & s.delay[w];
+    for (int w = 0; w < WF; w++) acc[w < kHalf ? 0 : 1] |= s.st[w] & s.delay[w];
   }
-  return acc;
 }
 
 // Re-scan of the neighbourhood of one hit with the exact recurrences.  The hit
@@ -486,7 +490,8 @@ SB_HD void verify_hit(const ScanArgs& a, const uint32_t* eq /*[nrows][W] of this
   const int64_t span = (int64_t)a.m + (int64_t)a.k;
   int64_t w0 = g0 - span;
   if (w0 < 0) w0 = 0;
-  int64_t end = g0 + kHitChars + span;
+  // strand-fused prefilter: a reversed query's hit marks where its piece STARTS in scan direction
+  int64_t end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
   if (end > n) end = n;
   const int64_t emit_from = g0 < 0 ? 0 : g0;
   Lane<W> s;

@@ -230,22 +230,33 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
   __shared__ __align__(16) uint32_t pair_tab[PAIR ? kPairTableWords * WF : 4];
   row_pipeline<REV, VARIANT>(tmap, a, a.feq + (size_t)q * kTabWords, kTabWords, PAIR ? pair_tab : nullptr, eqt,
                              [&](uint64_t stage_idx, bool own, auto chunk) {
-                               uint32_t acc[kChunks];
+                               uint32_t acc[kChunks][2];
 #pragma unroll
                                for (int cc = 0; cc < kChunks; cc++) {
                                  const int c = REV ? (kChunks - 1 - cc) : cc;
                                  const uint4 v = chunk(c);
                                  const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-                                 acc[c] = PAIR ? filter16_pair<WF, REV>(s, x, eqt) : filter16<WF, REV>(s, x, eqt);
+                                 if (PAIR)
+                                   filter16_pair<WF, REV>(s, x, eqt, acc[c]);
+                                 else
+                                   filter16<WF, REV>(s, x, eqt, acc[c]);
                                }
                                uint32_t any = 0;
 #pragma unroll
-                               for (int c = 0; c < kChunks; c++) any |= acc[c];
+                               for (int c = 0; c < kChunks; c++) any |= acc[c][0] | acc[c][1];
                                if (any) {  // rare: some piece occurrence ended in this stage
-                                 uint32_t mask = 0;
+                                 uint32_t mask0 = 0, mask1 = 0;
 #pragma unroll
-                                 for (int c = 0; c < kChunks; c++) mask |= acc[c] ? (1u << c) : 0u;
-                                 emit_stage_hits(a, hq, qs, stage_idx, mask, own);
+                                 for (int c = 0; c < kChunks; c++) {
+                                   mask0 |= acc[c][0] ? (1u << c) : 0u;
+                                   mask1 |= acc[c][1] ? (1u << c) : 0u;
+                                 }
+                                 if (a.fused) {  // second half of the automaton = the reversed partner query
+                                   if (mask0) emit_stage_hits(a, hq, qs, stage_idx, mask0, own);
+                                   if (mask1) emit_stage_hits(a, hq, qs + a.nq, stage_idx, mask1, own);
+                                 } else {
+                                   emit_stage_hits(a, hq, qs, stage_idx, mask0 | mask1, own);
+                                 }
                                }
                                __syncwarp();
                                if (*hq.n >= kHitQueueCap / 2) flush_hits(a, hq, lane);  // warp-uniform
@@ -287,7 +298,7 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
   const int64_t span = (int64_t)a.m + (int64_t)a.k;
   int64_t w0 = g0 - span;
   if (w0 < 0) w0 = 0;
-  int64_t end = g0 + kHitChars + span;
+  int64_t end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
   if (end > n) end = n;
   const int64_t emit_from = g0 < 0 ? 0 : g0;
   if (end <= w0) return;
