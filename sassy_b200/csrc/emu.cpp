@@ -217,7 +217,7 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
     const bool fused = nfwd > 0 && nq == 2 * nfwd && fp.WF <= 2;  // as Engine::search
     const int WT = fused ? 2 * fp.WF : fp.WF;
     const size_t ntab = fused ? nfwd : nq;
-    const bool pair = profile == kDna && WT <= 2;
+    const bool pair = profile == kDna && WT <= 4;
     const size_t tab_words = pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT;
     std::vector<uint32_t> feq(ntab * tab_words + 4);
     for (uint32_t q = 0; q < ntab; q++) {

@@ -62,6 +62,8 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
   const char* fm = getenv("SASSY_B200_FILTER");
   if (fm && !strcmp(fm, "off")) filter_mode_ = 0;
   if (fm && !strcmp(fm, "force")) filter_mode_ = 2;
+  const char* pm = getenv("SASSY_B200_PAIR_MAX_WORDS");
+  if (pm) pair_max_words_ = atoi(pm);
   const char* fs = getenv("SASSY_B200_FUSE_STRANDS");
   if (fs && !strcmp(fs, "0")) fuse_strands_ = false;
   cudaDriverEntryPointQueryResult qres;
@@ -330,7 +332,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   // forward pass: the partner's pieces, matched back to front, occupy a second set of words.
   const bool fused = fp.enabled && fuse_strands_ && nfwd > 0 && nq == 2 * nfwd && fp.WF <= 2;
   const int WT = fused ? 2 * fp.WF : fp.WF;
-  const bool pair = profile_ == kDna && WT <= 2;
+  const bool pair = profile_ == kDna && WT <= pair_max_words_;
   const size_t tab_words = pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT;
   upload_params(queries, m, W, fp, pair, fused);
   uint8_t* dst = d_stage_.as<uint8_t>();

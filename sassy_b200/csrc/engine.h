@@ -116,6 +116,7 @@ class Engine {
   int variant_;
   int filter_mode_ = 1;
   bool fuse_strands_ = true;
+  int pair_max_words_ = 4;  // Dna: two characters per automaton step up to this many words
   int transport_mode_ = 1;
   float transfer_ms_ = 0;
   bool transfer_pending_ = false;

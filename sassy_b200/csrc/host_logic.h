@@ -235,7 +235,8 @@ inline void build_filter_table(int profile, const FilterPlan& f, const uint8_t* 
 }
 
 // Pair table of the two-characters-per-step automaton (Dna profile only):
-// tab[first | second << 2] = {A[WT], B[WT]}, see filter16_pair in scan_core.cuh.
+// tab[word][first | second << 2] = {A, B} (one 128-byte sub-table per automaton word), see
+// filter16_pair / load_pair in scan_core.cuh.
 inline void build_pair_table(const FilterPlan& f, const uint8_t* pat, uint32_t* tab,
                              const uint8_t* pat_rev = nullptr) {
   const int WT = pat_rev ? 2 * f.WF : f.WF;
@@ -248,10 +249,10 @@ inline void build_pair_table(const FilterPlan& f, const uint8_t* pat, uint32_t* 
   }
   for (int c1 = 0; c1 < 4; c1++)
     for (int c0 = 0; c0 < 4; c0++) {
-      uint32_t* e = tab + (size_t)(c0 | (c1 << 2)) * 2 * WT;
       for (int w = 0; w < WT; w++) {
-        e[w] = (cls[c0][w] << 1) & cls[c1][w];
-        e[WT + w] = (((init[w] & cls[c0][w]) << 1) | init[w]) & cls[c1][w];
+        uint32_t* e = tab + (size_t)w * 32 + (size_t)(c0 | (c1 << 2)) * 2;
+        e[0] = (cls[c0][w] << 1) & cls[c1][w];
+        e[1] = (((init[w] & cls[c0][w]) << 1) | init[w]) & cls[c1][w];
       }
     }
 }

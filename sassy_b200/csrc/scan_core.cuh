@@ -421,56 +421,53 @@ SB_HD void filter16(FLane<WF>& s, const uint32_t (&x)[4], const EqTab& feq, uint
 // so a pair costs PRMT + LDS (A and B of the pair) + IMAD.SHL + LOP3.  The pair table
 // [16][2*WF] is indexed by first | second << 2 in scan order; the pair offsets of a text
 // word come from two shift/mask operations on the whole word.
+// Pair table layout: tab[word][pair] = {A, B}: one 128-byte sub-table per automaton word, so
+// that a warp access touches at most 16 distinct 8-byte entries in 16 distinct bank pairs (no
+// bank conflicts, one shared-memory wavefront per half warp).  Interleaving the words of an
+// entry (16- or 32-byte entries) was measured 2.5x slower: conflicts + bytes per access.
 template <int WF>
-SB_HD void load_pair(uint32_t (&ab)[2 * WF], const EqTab& t, uint32_t off) {
+SB_HD void load_pair(uint32_t (&a)[WF], uint32_t (&b)[WF], const EqTab& t, uint32_t off) {
   // plain indexing: on the device t.p points into shared memory and the compiler folds the
   // table base into the LDS address (register + uniform register + immediate), no add
   const uint8_t* base = reinterpret_cast<const uint8_t*>(t.p) + off;
-#if defined(__CUDA_ARCH__)
-  if (WF == 1) {
-    const uint2 v = *reinterpret_cast<const uint2*>(base);
-    ab[0] = v.x, ab[2 * WF - 1] = v.y;
-  } else {
 #pragma unroll
-    for (int w = 0; w < 2 * WF; w += 4) {
-      const uint4 v = *reinterpret_cast<const uint4*>(base + 4 * w);
-      ab[w] = v.x, ab[(w + 1) % (2 * WF)] = v.y, ab[(w + 2) % (2 * WF)] = v.z, ab[(w + 3) % (2 * WF)] = v.w;
-    }
-  }
+  for (int w = 0; w < WF; w++) {
+#if defined(__CUDA_ARCH__)
+    const uint2 v = *reinterpret_cast<const uint2*>(base + 128 * w);
+    a[w] = v.x, b[w] = v.y;
 #else
-  memcpy(ab, base, sizeof(uint32_t) * 2 * WF);
+    uint32_t v[2];
+    memcpy(v, base + 128 * w, 8);
+    a[w] = v[0], b[w] = v[1];
 #endif
+  }
 }
 
-// Bits of the pair offset: class c = (byte >> 1) & 3 is moved to the entry-stride bit
-// position of its byte, then first | second << 2 is assembled by one more shift, so that a
-// byte of the result IS the table offset of a pair (8 bytes per entry for WF = 1, 16 for
-// WF = 2; WF = 4 doubles the 16-byte offsets).
+// Bits of the pair offset: class c = (byte >> 1) & 3 is moved to bits 3-4 of its byte
+// ((x << 2) & 0x18), then first | second << 2 is assembled by one more shift, so that a byte
+// of the result IS the offset pair * 8 inside a word's sub-table.
 template <int WF, bool REV>
 SB_HD void filter16_pair(FLane<WF>& s, const uint32_t (&x)[4], const EqTab& ftab, uint32_t (&acc)[2]) {
-  constexpr int kSh = WF == 1 ? 2 : 3;
-  constexpr uint32_t kMask = WF == 1 ? 0x18181818u : 0x30303030u;
   constexpr int kHalf = WF > 1 ? WF / 2 : 1;
   acc[0] = acc[1] = 0;
 #pragma unroll
   for (int ww = 0; ww < 4; ww++) {
     const int w4 = REV ? 3 - ww : ww;
-    const uint32_t pre = (x[w4] << kSh) & kMask;
+    const uint32_t pre = (x[w4] << 2) & 0x18181818u;
     const uint32_t t = REV ? (pre | (pre << 10)) : (pre | (pre >> 6));
 #pragma unroll
     for (int pp = 0; pp < 2; pp++) {
       // forward: pairs live in bytes 0 and 2; reverse: bytes 3 and 1
       const int byte = REV ? 3 - 2 * pp : 2 * pp;
 #if defined(__CUDA_ARCH__)
-      uint32_t off = __byte_perm(t, 0u, 0x4440u + (uint32_t)byte);
+      const uint32_t off = __byte_perm(t, 0u, 0x4440u + (uint32_t)byte);
 #else
-      uint32_t off = (t >> (8 * byte)) & 0xFFu;
+      const uint32_t off = (t >> (8 * byte)) & 0xFFu;
 #endif
-      if (WF == 4) off *= 2;
-      uint32_t ab[2 * WF];
-      load_pair<WF>(ab, ftab, off);
+      uint32_t a[WF], b[WF];
+      load_pair<WF>(a, b, ftab, off);
 #pragma unroll
-      for (int w = 0; w < WF; w++) s.st[w] = ((s.st[w] << 2) & ab[w]) | ab[WF + w];
+      for (int w = 0; w < WF; w++) s.st[w] = ((s.st[w] << 2) & a[w]) | b[w];
     }
 #pragma unroll
     for (int w = 0; w < WF; w++) acc[w < kHalf ? 0 : 1] |= s.st[w] & s.delay[w];
