@@ -168,7 +168,8 @@ def test_prefilter_routes(tma):
     want = oracle.search("dna", p, t, 2, rc=True)
     got = s.search(p, t, 2)
     st = s.stats()
-    assert st["filter_words"] == 1 and st["filter_fallback"] == 0 and st["hits"] > 0
+    # rc=True: both strands share one pass, one automaton word each
+    assert st["filter_words"] == 2 and st["filter_fallback"] == 0 and st["hits"] > 0
     assert [key(m) for m in got] == [key(m) for m in want] and len(got) >= 4
     s.set_filter("off")
     assert [key(m) for m in s.search(p, t, 2)] == [key(m) for m in got]
