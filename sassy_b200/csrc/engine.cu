@@ -83,6 +83,8 @@ Engine::~Engine() {
   if (staged_.d) cudaFree(staged_.d);
   if (h_stage_) cudaFreeHost(h_stage_);
   if (h_pack_) cudaFreeHost(h_pack_);
+  if (h_small_) cudaFreeHost(h_small_);
+  sel_small_.release();
   d_pack_.release();
   delete pool_;
   for (auto& ev : ev_)
@@ -185,6 +187,8 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
     const size_t packed_bytes = (size_t)((n_packed + 63) / 64 * 16);
     if (packed_bytes > h_pack_cap_) {
       if (h_pack_) cudaFreeHost(h_pack_);
+  if (h_small_) cudaFreeHost(h_small_);
+  sel_small_.release();
       h_pack_ = nullptr;
       h_pack_cap_ = 0;
       const size_t want = (size_t)((n + 63) / 64 * 16);
@@ -404,6 +408,61 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     return ms;
   };
 
+  // Fast tail for small candidate lists (the normal case): one block sorts + selects, the
+  // traceback runs on the device-side selection count and writes straight into pinned host
+  // memory.  Queued right behind the candidate producers, so a search needs ONE host
+  // synchronisation; longer lists set the `big` flag and take the general path below.
+  int end_bit = kPosBits;
+  while ((1ull << (end_bit - kPosBits)) < nq) end_bit++;
+  const uint64_t words_per_match = (uint64_t)(m + k + 1) * W * 2;
+  const bool small_path = words_per_match <= 4096;
+  unsigned long long* d_big = d_counts + 3;
+  if (small_path) {
+    const size_t need_out = (size_t)kSmallCandidates * sizeof(GpuMatch);
+    const size_t need_ops = (size_t)kSmallCandidates * out.ops_words * sizeof(uint32_t);
+    if (need_out + need_ops > h_small_cap_) {
+      if (h_small_) cudaFreeHost(h_small_);
+      h_small_ = nullptr;
+      h_small_cap_ = 0;
+      SB_CUDA(cudaHostAlloc((void**)&h_small_, 2 * (need_out + need_ops), cudaHostAllocDefault));
+      h_small_cap_ = 2 * (need_out + need_ops);
+    }
+    sel_small_.ensure((size_t)kSmallCandidates * sizeof(uint64_t));
+    scratch_.ensure(trace_threads(kSmallCandidates) * words_per_match * sizeof(uint32_t));
+  }
+  GpuMatch* h_small_out = reinterpret_cast<GpuMatch*>(h_small_);
+  uint32_t* h_small_ops = reinterpret_cast<uint32_t*>(h_small_ + (size_t)kSmallCandidates * sizeof(GpuMatch));
+  auto queue_small_tail = [&]() {
+    if (!small_path) return;
+    SB_CUDA(launch_post_small(a.cand_keys, a.cand_cost, d_cand_count, a.cand_cap, sel_small_.as<uint64_t>(), d_nsel,
+                              d_big, all_minima, end_bit, stream_));
+    TraceArgs t;
+    memset(&t, 0, sizeof t);
+    t.text = text.d;
+    t.n = n;
+    t.profile = profile_;
+    t.patterns = d_pat;
+    t.rev_flags = d_rev;
+    t.eq = d_eq;
+    t.nrows = nrows_;
+    t.sh0 = sh0_;
+    t.msk0 = msk0_;
+    t.m = m;
+    t.k = k;
+    t.W = W;
+    t.keys = sel_small_.as<uint64_t>();
+    t.first = 0;
+    t.count = kSmallCandidates;
+    t.count_dev = d_nsel;
+    t.scratch = scratch_.as<uint32_t>();
+    t.ops = h_small_ops;   // pinned host memory, written by the kernel over PCIe
+    t.ops_words = out.ops_words;
+    t.out = h_small_out;
+    SB_CUDA(launch_trace(t, stream_));
+    stats_.aux_launches += 2;
+  };
+  bool small_done = false;
+
   uint64_t ncand = 0;
   bool filtered = false;
 
@@ -460,6 +519,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     SB_CUDA(launch_verify(W, v, d_rev, stream_));
     stats_.aux_launches++;
     SB_CUDA(cudaEventRecord(ev_[4], stream_));
+    queue_small_tail();
     read_counts();
     stats_.filter_ms = elapsed(ev_[1], ev_[2]);
     stats_.verify_ms = elapsed(ev_[2], ev_[4]);
@@ -490,10 +550,12 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
         SB_CUDA(launch_verify(W, v, d_rev, stream_));
         stats_.aux_launches++;
         SB_CUDA(cudaEventRecord(ev_[4], stream_));
+        queue_small_tail();
         read_counts();
         stats_.verify_ms += elapsed(ev_[2], ev_[4]);
       }
       filtered = true;
+      small_done = small_path && h_counts[3] == 0;
       stats_.scan_ms = stats_.filter_ms;  // the dominant kernel of this route
     }
   }
@@ -525,11 +587,13 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
         }
       }
       SB_CUDA(cudaEventRecord(ev_[2], stream_));
+      queue_small_tail();
       read_counts();
       stats_.scan_ms += elapsed(ev_[1], ev_[2]);
       const unsigned long long cnt = h_counts[0];
       if (cnt <= cand_cap_) {
         ncand = cnt;
+        small_done = small_path && h_counts[3] == 0;
         break;
       }
       if (attempt >= 3) throw CudaError("candidate buffer overflow after retries");
@@ -541,11 +605,13 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
 
   // ---- sort, select (de-duplicate + local minima), trace ------------------------------------
   uint64_t nsel = 0;
-  if (ncand > 0) {
+  if (small_done) {
+    nsel = h_counts[1];
+    out.m.assign(h_small_out, h_small_out + nsel);
+    out.ops.assign(h_small_ops, h_small_ops + nsel * out.ops_words);
+  } else if (ncand > 0) {
     keys2_.ensure(ncand * sizeof(uint64_t));
     cost2_.ensure(ncand * sizeof(uint32_t));
-    int end_bit = kPosBits;
-    while ((1ull << (end_bit - kPosBits)) < nq) end_bit++;
     size_t tmp_bytes = 0;
     SB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_.as<uint64_t>(), keys2_.as<uint64_t>(),
                                             cost_.as<uint32_t>(), cost2_.as<uint32_t>(), ncand, 0, end_bit,

@@ -136,7 +136,9 @@ class Engine {
   DevBuf eq_, patterns_, revflags_;
   DevBuf keys_, cost_, keys2_, cost2_, flags_, sel_, count_, cubtmp_;
   DevBuf scratch_, ops_, out_;
-  DevBuf feq_, hits_, d_stage_;
+  DevBuf feq_, hits_, d_stage_, sel_small_;
+  uint8_t* h_small_ = nullptr;  // pinned: results of the small-list fast path, written by the GPU
+  size_t h_small_cap_ = 0;
   uint8_t* h_stage_ = nullptr;  // pinned staging for the per-search parameter block
   size_t stage_cap_ = 0;
   size_t off_counts_ = 0, off_eq_ = 0, off_pat_ = 0, off_rev_ = 0, off_feq_ = 0;

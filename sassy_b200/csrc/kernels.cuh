@@ -38,6 +38,13 @@ cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cu
 cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags, bool all_minima,
                           cudaStream_t stream);
 
+// One-block sort + selection for candidate lists of at most kSmallCandidates entries, driven by
+// the device-side candidate count (*big = 1 and *nsel = 0 if the list is longer).
+constexpr int kSmallCandidates = 2048;
+cudaError_t launch_post_small(const uint64_t* keys, const uint32_t* cost, const unsigned long long* cand_count,
+                              uint64_t cand_cap, uint64_t* sel_keys, unsigned long long* nsel,
+                              unsigned long long* big, bool all_minima, int end_bit, cudaStream_t stream);
+
 struct TraceArgs {
   const uint8_t* text;
   uint64_t n;

@@ -4,6 +4,9 @@
 // Their per-thread logic lives in scan_core.cuh (shared with the host emulator).
 #include "kernels.cuh"
 
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
+
 namespace sb {
 namespace {
 
@@ -12,6 +15,72 @@ __global__ void minima_kernel(const uint64_t* __restrict__ keys, const uint32_t*
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   flags[i] = select_candidate(keys, cost, i, n, all_minima) ? 1 : 0;
+}
+
+// Whole post-processing of a SMALL candidate list in one block: sort by key, keep the first
+// copy of every position, apply the local-minima rule, compact.  Reads the candidate count
+// on the device, so the host can queue it (and the traceback) right behind the scan without
+// a round trip; lists above kSmallCandidates raise `big` and are handled by the general path
+// (device radix sort + selection kernel + stream compaction).
+constexpr int kSmallThreads = 256;
+constexpr int kSmallItems = kSmallCandidates / kSmallThreads;
+
+__global__ void __launch_bounds__(kSmallThreads)
+    post_small_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cost,
+                      const unsigned long long* __restrict__ cand_count, uint64_t cand_cap,
+                      uint64_t* __restrict__ sel_keys, unsigned long long* __restrict__ nsel,
+                      unsigned long long* __restrict__ big, bool all_minima, int end_bit) {
+  using Sort = cub::BlockRadixSort<uint64_t, kSmallThreads, kSmallItems, uint32_t>;
+  using Scan = cub::BlockScan<uint32_t, kSmallThreads>;
+  __shared__ union {
+    typename Sort::TempStorage sort;
+    struct {
+      uint64_t keys[kSmallCandidates];
+      uint32_t cost[kSmallCandidates];
+    } sorted;
+  } sm;
+  __shared__ typename Scan::TempStorage scan_tmp;
+  const unsigned long long n = *cand_count;
+  if (n > (unsigned long long)kSmallCandidates || n > cand_cap) {
+    if (threadIdx.x == 0) {
+      *big = 1;
+      *nsel = 0;
+    }
+    return;
+  }
+  uint64_t k[kSmallItems];
+  uint32_t v[kSmallItems];
+#pragma unroll
+  for (int i = 0; i < kSmallItems; i++) {
+    const uint32_t idx = threadIdx.x * kSmallItems + i;
+    k[i] = idx < n ? keys[idx] : ~0ull;  // padding sorts to the end
+    v[i] = idx < n ? cost[idx] : 0u;
+  }
+  Sort(sm.sort).Sort(k, v, 0, 64);
+  (void)end_bit;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSmallItems; i++) {
+    const uint32_t idx = threadIdx.x * kSmallItems + i;
+    sm.sorted.keys[idx] = k[i];
+    sm.sorted.cost[idx] = v[i];
+  }
+  __syncthreads();
+  uint32_t flag[kSmallItems], pos[kSmallItems];
+#pragma unroll
+  for (int i = 0; i < kSmallItems; i++) {
+    const uint32_t idx = threadIdx.x * kSmallItems + i;
+    flag[i] = idx < n && select_candidate(sm.sorted.keys, sm.sorted.cost, idx, n, all_minima) ? 1u : 0u;
+  }
+  uint32_t total;
+  Scan(scan_tmp).ExclusiveSum(flag, pos, total);
+#pragma unroll
+  for (int i = 0; i < kSmallItems; i++)
+    if (flag[i]) sel_keys[pos[i]] = k[i];
+  if (threadIdx.x == 0) {
+    *nsel = total;
+    *big = 0;
+  }
 }
 
 // Grid-stride over the slice [first, first + count) of the selected candidates; when
@@ -58,6 +127,14 @@ cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n
   const unsigned threads = 256;
   const uint64_t blocks = (n + threads - 1) / threads;
   minima_kernel<<<(unsigned)blocks, threads, 0, stream>>>(keys, cost, n, flags, all_minima);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_post_small(const uint64_t* keys, const uint32_t* cost, const unsigned long long* cand_count,
+                              uint64_t cand_cap, uint64_t* sel_keys, unsigned long long* nsel,
+                              unsigned long long* big, bool all_minima, int end_bit, cudaStream_t stream) {
+  post_small_kernel<<<1, kSmallThreads, 0, stream>>>(keys, cost, cand_count, cand_cap, sel_keys, nsel, big,
+                                                     all_minima, end_bit);
   return cudaGetLastError();
 }
 

@@ -52,14 +52,15 @@ def unpack_matches(t: torch.Tensor) -> List[Match]:
     return out
 
 
-def _local_block(matches, max_ops: int):
-    """(records uint8 [n, 72], ops uint8 [n, max_ops]) of a MatchList or a list of Match."""
+def _local_block(matches):
+    """(records as uint8 [n*72], raw CIGAR op bytes as uint8) of a MatchList or a list of Match;
+    ops_off of the records is relative to the returned op bytes."""
     from .searcher import MatchList, _REC_DTYPE
-    n = len(matches)
     if isinstance(matches, MatchList):
         recs = matches.records
         raw = np.frombuffer(matches._ops, dtype=np.uint8)
     else:
+        n = len(matches)
         recs = np.zeros(n, dtype=_REC_DTYPE)
         chunks = []
         off = 0
@@ -69,24 +70,18 @@ def _local_block(matches, max_ops: int):
             chunks.append(m._ops.encode())
             off += len(m._ops)
         raw = np.frombuffer(b"".join(chunks), dtype=np.uint8)
-    ops = np.zeros((n, max_ops), dtype=np.uint8)
-    if n:
-        lens = recs["ops_len"].astype(np.int64)
-        if lens.max(initial=0) > max_ops:
-            raise ValueError("max_ops too small for CIGAR")
-        offs = recs["ops_off"].astype(np.int64)
-        idx = offs[:, None] + np.arange(max_ops)[None, :]
-        mask = np.arange(max_ops)[None, :] < lens[:, None]
-        ops[mask] = raw[np.minimum(idx, max(len(raw) - 1, 0))][mask]
-    return np.ascontiguousarray(recs).view(np.uint8).reshape(n, _REC_DTYPE.itemsize), ops
+    return np.ascontiguousarray(recs).view(np.uint8).reshape(-1), raw
 
 
 class _GatherBuffers:
-    """Re-used staging for gather_matches: pinned host blocks and device blocks of one capacity."""
+    """Re-used staging for gather_matches: pinned host blocks and device blocks of one capacity.
+    Block layout: [n_records:int64][n_op_bytes:int64][records: cap*72][op bytes: cap*max_ops]."""
 
-    def __init__(self, world: int, cap: int, width: int, device):
+    def __init__(self, world: int, cap: int, max_ops: int, rsz: int, device):
         self.cap = cap
-        self.block = 8 + cap * width
+        self.rec_bytes = cap * rsz
+        self.ops_bytes = cap * max_ops
+        self.block = 16 + self.rec_bytes + self.ops_bytes
         cuda = torch.device(device).type == "cuda"
         self.send_host = torch.zeros(self.block, dtype=torch.uint8, pin_memory=cuda)
         self.recv_host = torch.zeros(world * self.block, dtype=torch.uint8, pin_memory=cuda)
@@ -96,6 +91,9 @@ class _GatherBuffers:
         else:
             self.send_dev, self.recv_dev = self.send_host, self.recv_host
         self.cuda = cuda
+        self.send_np = self.send_host.numpy()
+        self.recv_np = self.recv_host.numpy().reshape(world, self.block)
+        self.head = self.send_np[:16].view(np.int64)
 
 
 _GATHER = {}
@@ -105,30 +103,28 @@ def gather_matches(matches, max_ops: int, device=None, group=None):
     """All ranks receive the concatenation (rank order) of every rank's matches (a MatchList).
 
     ONE collective in the common case: every rank contributes a fixed-capacity block
-    [count | records | ops]; only if some rank holds more matches than the capacity is the
-    exchange repeated with a larger block (NCCL has no gatherv)."""
+    [counts | records | CIGAR op bytes]; only if some rank holds more than the capacity is
+    the exchange repeated with a larger block (NCCL has no gatherv)."""
     from .searcher import MatchList, _REC_DTYPE
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return matches
     world = dist.get_world_size(group)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
-    recs, ops = _local_block(matches, max_ops)
-    n = recs.shape[0]
     rsz = _REC_DTYPE.itemsize
-    width = rsz + max_ops
+    recs, raw = _local_block(matches)
+    n = recs.size // rsz
     key = (id(group), max_ops, str(device))
     while True:
         gb = _GATHER.get(key)
         if gb is None:
-            gb = _GATHER[key] = _GatherBuffers(world, 256, width, device)
-        cap = gb.cap
-        block = gb.send_host.numpy()
-        block[:8] = np.frombuffer(np.int64(n).tobytes(), dtype=np.uint8)
-        take = min(n, cap)
-        body = block[8:].reshape(cap, width)
-        body[:take, :rsz] = recs[:take]
-        body[:take, rsz:] = ops[:take]
+            gb = _GATHER[key] = _GatherBuffers(world, 256, max_ops, rsz, device)
+        fits = n <= gb.cap and raw.size <= gb.ops_bytes
+        gb.head[0] = n
+        gb.head[1] = raw.size
+        if fits:
+            gb.send_np[16:16 + recs.size] = recs
+            gb.send_np[16 + gb.rec_bytes:16 + gb.rec_bytes + raw.size] = raw
         if gb.cuda:
             gb.send_dev.copy_(gb.send_host, non_blocking=True)
             dist.all_gather_into_tensor(gb.recv_dev, gb.send_dev, group=group)
@@ -136,24 +132,21 @@ def gather_matches(matches, max_ops: int, device=None, group=None):
             torch.cuda.current_stream().synchronize()
         else:
             dist.all_gather_into_tensor(gb.recv_host, gb.send_host, group=group)
-        allb = gb.recv_host.numpy().reshape(world, gb.block)
-        counts = allb[:, :8].copy().view(np.int64).reshape(world).tolist()
-        if max(counts) <= cap:
+        heads = gb.recv_np[:, :16].copy().view(np.int64).reshape(world, 2)
+        need = int(max(heads[:, 0].max(), -(-int(heads[:, 1].max()) // max(max_ops, 1))))
+        if need <= gb.cap:
             break
-        _GATHER[key] = _GatherBuffers(world, 2 * max(counts), width, device)  # same decision on every rank
+        _GATHER[key] = _GatherBuffers(world, 2 * need, max_ops, rsz, device)  # same decision on every rank
     out_recs = []
     out_ops = []
     off = 0
     for r in range(world):
-        if counts[r] == 0:
+        cnt, nops = int(heads[r, 0]), int(heads[r, 1])
+        if cnt == 0:
             continue
-        body = allb[r, 8:].reshape(cap, width)[:counts[r]]
-        rr = np.ascontiguousarray(body[:, :rsz]).view(_REC_DTYPE).reshape(-1).copy()
-        lens = rr["ops_len"].astype(np.int64)
-        mask = np.arange(max_ops)[None, :] < lens[:, None]
-        flat = body[:, rsz:][mask]
-        rr["ops_off"] = off + np.concatenate(([0], np.cumsum(lens)[:-1]))
-        off += int(lens.sum())
+        rr = gb.recv_np[r, 16:16 + cnt * rsz].copy().view(_REC_DTYPE)
+        rr["ops_off"] += off
+        off += nops
         out_recs.append(rr)
-        out_ops.append(flat.tobytes())
+        out_ops.append(gb.recv_np[r, 16 + gb.rec_bytes:16 + gb.rec_bytes + nops].tobytes())
     return MatchList(np.concatenate(out_recs) if out_recs else np.zeros(0, dtype=_REC_DTYPE), b"".join(out_ops))
