@@ -187,8 +187,6 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
     const size_t packed_bytes = (size_t)((n_packed + 63) / 64 * 16);
     if (packed_bytes > h_pack_cap_) {
       if (h_pack_) cudaFreeHost(h_pack_);
-  if (h_small_) cudaFreeHost(h_small_);
-  sel_small_.release();
       h_pack_ = nullptr;
       h_pack_cap_ = 0;
       const size_t want = (size_t)((n + 63) / 64 * 16);
@@ -302,6 +300,7 @@ void Engine::make_tensor_map(CUtensorMap* map, const DeviceText& text, const Sca
 void Engine::search(const DeviceText& text, const std::vector<Query>& queries, int m, int k, bool all_minima,
                     bool include_pos0, MatchSet& out) {
   SB_CUDA(cudaSetDevice(device_));
+  cudaGetLastError();  // a stale error left by another library in this thread is not ours to report
   stats_ = SearchStats();
   out.m.clear();
   out.ops.clear();
