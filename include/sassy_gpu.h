@@ -14,6 +14,14 @@
  *   search_all_encoded_patterns src/search.rs:426        sassy_gpu_search_encoded(all=1)
  *   Match{.., cigar}            src/search.rs:35-62      sassy_gpu_Match + sassy_gpu_result_ops
  *   Cigar::to_string (pa-types) src/lib.rs:83,107        sassy_gpu_cigar
+ *   with_trace / without_trace  src/search.rs:446-449    sassy_gpu_set_trace
+ *   only_best_match             src/search.rs:441-444    sassy_gpu_set_only_best_match
+ *   set_max_n_frac              src/search.rs:452-458    sassy_gpu_set_max_n_frac
+ *   search_with_fn + PAM filter src/search.rs:767-784,   sassy_gpu_search_pam(_text)
+ *                               bin/crispr.rs:198-221
+ *   search_patterns             src/search.rs:648-683    sassy_gpu_search_patterns
+ *   search_texts                src/search.rs:615-640    sassy_gpu_search_texts
+ *   search_many                 src/search.rs:531-603    sassy_gpu_search_many
  *
  * Error handling: functions returning a pointer return NULL on error and
  * functions returning int return non-zero; sassy_gpu_last_error() then holds a
@@ -107,6 +115,43 @@ sassy_gpu_Result *sassy_gpu_search(sassy_SearcherType *searcher, const uint8_t *
                                    const uint8_t *text, size_t text_len, size_t k, int all);
 sassy_gpu_Result *sassy_gpu_search_text(sassy_SearcherType *searcher, const uint8_t *pattern, size_t pattern_len,
                                         const sassy_gpu_Text *text, size_t k, int all);
+
+/* Searcher options; they apply to every later search of this searcher like the reference's
+ * builder methods.  trace = 0: matches carry the end position and the cost only
+ * (text_start = pattern_start = UINT64_MAX; on the reverse strand text_end = UINT64_MAX and
+ * text_start holds the known coordinate, src/search.rs:866-872), no CIGAR.
+ * max_n_frac = 1.0 disables the N filter (src/search.rs:452-458). */
+int sassy_gpu_set_trace(sassy_SearcherType *searcher, int trace);
+int sassy_gpu_set_only_best_match(sassy_SearcherType *searcher, int on);
+int sassy_gpu_set_max_n_frac(sassy_SearcherType *searcher, float max_n_frac);
+
+/* search_with_fn with the end filter of the reference's CRISPR mode: an end position is kept
+ * only if the pam_len (<= 16) text characters before it match `pam` exactly under the
+ * profile's is_match (on the reverse strand: the complemented PAM on the reversed text,
+ * bin/crispr.rs:198-205).  all = 1 reports every passing end position (crispr.rs:218). */
+sassy_gpu_Result *sassy_gpu_search_pam(sassy_SearcherType *searcher, const uint8_t *pattern, size_t pattern_len,
+                                       const uint8_t *text, size_t text_len, size_t k, int all,
+                                       const uint8_t *pam, size_t pam_len);
+sassy_gpu_Result *sassy_gpu_search_pam_text(sassy_SearcherType *searcher, const uint8_t *pattern,
+                                            size_t pattern_len, const sassy_gpu_Text *text, size_t k, int all,
+                                            const uint8_t *pam, size_t pam_len);
+
+/* Searcher::search_patterns: n_patterns patterns of equal length against one text; v1 semantics
+ * per pattern, sassy_gpu_Match::pattern_idx set. */
+sassy_gpu_Result *sassy_gpu_search_patterns(sassy_SearcherType *searcher, const uint8_t *const *patterns,
+                                            size_t n_patterns, size_t pattern_len, const uint8_t *text,
+                                            size_t text_len, size_t k);
+/* Searcher::search_texts: one pattern against n_texts texts (sassy_gpu_Match::text_idx set);
+ * short texts are searched by one kernel launch, one thread per (text, strand). */
+sassy_gpu_Result *sassy_gpu_search_texts(sassy_SearcherType *searcher, const uint8_t *pattern, size_t pattern_len,
+                                         const uint8_t *const *texts, const size_t *text_lens, size_t n_texts,
+                                         size_t k);
+/* Searcher::search_many: every pattern against every text; result ordered like the reference's
+ * SearchMode::Single (pattern-major, then text, forward before reverse-complement matches). */
+sassy_gpu_Result *sassy_gpu_search_many(sassy_SearcherType *searcher, const uint8_t *const *patterns,
+                                        const size_t *pattern_lens, size_t n_patterns,
+                                        const uint8_t *const *texts, const size_t *text_lens, size_t n_texts,
+                                        size_t k);
 
 /* Searcher::encode_patterns: n_patterns patterns of equal length pattern_len, back to back. */
 sassy_gpu_Patterns *sassy_gpu_encode_patterns(sassy_SearcherType *searcher, const uint8_t *patterns,

@@ -32,6 +32,7 @@ class _OracleMatch(ctypes.Structure):
         ("strand", ctypes.c_uint32),
         ("ops_len", ctypes.c_uint32),
         ("ops_off", ctypes.c_uint64),
+        ("text_idx", ctypes.c_uint64),
     ]
 
 
@@ -47,6 +48,10 @@ class Match:
     cost: int
     strand: str  # "+" / "-" as in src/python.rs:201-206
     cigar: str
+    text_idx: int = 0
+
+
+USIZE_MAX = 2**64 - 1  # what the reference stores in the untraced fields (src/search.rs:1466-1469)
 
 
 def build(force: bool = False) -> str:
@@ -82,6 +87,23 @@ def _lib():
             ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
         ]
         lib.oracle_search_encoded.restype = ctypes.c_int
+        lib.oracle_search_opts.argtypes = [
+            ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+            ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+            ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p,
+        ]
+        lib.oracle_search_opts.restype = ctypes.c_int
+        lib.oracle_search_many.argtypes = [
+            ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_void_p,
+            ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+            ctypes.c_void_p,
+        ]
+        lib.oracle_search_many.restype = ctypes.c_int
+        lib.oracle_search_encoded_nfrac.argtypes = [
+            ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p,
+            ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
+        ]
+        lib.oracle_search_encoded_nfrac.restype = ctypes.c_int
         lib.oracle_bottom_row.argtypes = [
             ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
             ctypes.c_int, ctypes.c_void_p,
@@ -121,11 +143,12 @@ def _collect(lib, out) -> List[Match]:
                 pattern_idx=m.pattern_idx,
                 text_start=m.text_start,
                 text_end=m.text_end,
-                pattern_start=m.pattern_start,
+                pattern_start=USIZE_MAX if m.pattern_start == 0xFFFFFFFF else m.pattern_start,
                 pattern_end=m.pattern_end,
                 cost=m.cost,
                 strand="-" if m.strand else "+",
                 cigar=rle(ops),
+                text_idx=m.text_idx,
             )
         )
     return res
@@ -136,13 +159,40 @@ class OracleError(RuntimeError):
 
 
 def search(alphabet: str, pattern: bytes, text: bytes, k: int, rc: bool = False,
-           all_minima: bool = False) -> List[Match]:
-    """Searcher::<P>::new(rc, None).search / search_all."""
+           all_minima: bool = False, without_trace: bool = False, only_best: bool = False,
+           max_n_frac: float | None = None, pam: bytes | None = None) -> List[Match]:
+    """Searcher::<P>::new(rc, None).search / search_all, optionally under the Searcher options
+    (without_trace, only_best_match, max_n_frac) and with the CRISPR end filter of
+    search_with_fn (``pam``: the characters before the end position must match it)."""
     lib = _lib()
     out = lib.oracle_out_new()
     try:
-        r = lib.oracle_search(PROFILE[alphabet.lower()], pattern, len(pattern), text, len(text),
-                              k, int(rc), int(all_minima), out)
+        nf = -1.0 if max_n_frac is None or max_n_frac == 1.0 else float(max_n_frac)
+        r = lib.oracle_search_opts(PROFILE[alphabet.lower()], pattern, len(pattern), text, len(text),
+                                   k, int(rc), int(all_minima), int(without_trace), int(only_best), nf,
+                                   pam, len(pam) if pam else 0, out)
+        if r == -2:
+            raise OracleError("Pattern is not valid IUPAC")
+        if r != 0:
+            raise OracleError(f"trace failed ({r})")
+        return _collect(lib, out)
+    finally:
+        lib.oracle_out_free(out)
+
+
+def search_many(alphabet: str, patterns: Sequence[bytes], texts: Sequence[bytes], k: int, rc: bool = False,
+                without_trace: bool = False, only_best: bool = False,
+                max_n_frac: float | None = None) -> List[Match]:
+    """Searcher::search_many (SearchMode::Single order: pattern-major, then text)."""
+    lib = _lib()
+    out = lib.oracle_out_new()
+    try:
+        plens = (ctypes.c_uint64 * max(1, len(patterns)))(*[len(p) for p in patterns])
+        tlens = (ctypes.c_uint64 * max(1, len(texts)))(*[len(t) for t in texts])
+        nf = -1.0 if max_n_frac is None or max_n_frac == 1.0 else float(max_n_frac)
+        r = lib.oracle_search_many(PROFILE[alphabet.lower()], b"".join(patterns), plens, len(patterns),
+                                   b"".join(texts), tlens, len(texts), k, int(rc), int(without_trace),
+                                   int(only_best), nf, out)
         if r == -2:
             raise OracleError("Pattern is not valid IUPAC")
         if r != 0:
@@ -153,15 +203,16 @@ def search(alphabet: str, pattern: bytes, text: bytes, k: int, rc: bool = False,
 
 
 def search_encoded(alphabet: str, patterns: Sequence[bytes], text: bytes, k: int, rc: bool = False,
-                   all_minima: bool = False) -> List[Match]:
+                   all_minima: bool = False, max_n_frac: float | None = None) -> List[Match]:
     """encode_patterns + search_encoded_patterns / search_all_encoded_patterns."""
     lib = _lib()
     m = len(patterns[0])
     assert all(len(p) == m for p in patterns)
     out = lib.oracle_out_new()
     try:
-        r = lib.oracle_search_encoded(PROFILE[alphabet.lower()], b"".join(patterns), len(patterns),
-                                      m, text, len(text), k, int(rc), int(all_minima), out)
+        nf = -1.0 if max_n_frac is None or max_n_frac == 1.0 else float(max_n_frac)
+        r = lib.oracle_search_encoded_nfrac(PROFILE[alphabet.lower()], b"".join(patterns), len(patterns),
+                                            m, text, len(text), k, int(rc), int(all_minima), nf, out)
         if r == -2:
             raise OracleError("Pattern is not valid IUPAC")
         if r != 0:

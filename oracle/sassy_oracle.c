@@ -39,7 +39,17 @@ typedef struct {
   uint32_t strand; /* 0 = Fwd, 1 = Rc */
   uint32_t ops_len;
   uint64_t ops_off;
+  uint64_t text_idx;
 } OracleMatch;
+
+/* Searcher options and the end filter (reference src/search.rs:227-256,441-483,767-784). */
+typedef struct {
+  int without_trace;   /* src/search.rs:446-449 */
+  int only_best;       /* src/search.rs:441-444 */
+  float max_n_frac;    /* < 0: off (src/search.rs:452-458) */
+  const uint8_t *pam;  /* end filter of bin/crispr.rs:198-205; NULL: none */
+  size_t pam_len;
+} OracleOpts;
 
 typedef struct {
   OracleMatch *m;
@@ -350,30 +360,100 @@ static size_t select_v2(const int32_t *c, size_t n, int32_t k, int all, uint64_t
 /* ------------------------------------------------------------------------ */
 /* One strand of v1: src/search.rs:884-937 + process_matches :1372-1517.     */
 
+/* check_n_fraction: src/n_filter.rs:8-34 (f32 arithmetic as there). */
+static int n_fraction_ok(const uint8_t *t, size_t n, int rev, size_t start, size_t end,
+                         float max_n_frac, size_t denom) {
+  if (start >= n) return 1;
+  if (end <= start) return 1;
+  size_t cnt = 0;
+  for (size_t i = start; i < end; i++) {
+    uint8_t c = text_at(t, n, rev, i);
+    cnt += (c == 'N' || c == 'n');
+  }
+  float frac = (float)cnt / (float)(denom ? denom : end - start);
+  return frac <= max_n_frac;
+}
+
 static int v1_one_strand(int profile, const uint8_t *p, size_t m, const uint8_t *t, size_t n,
-                         int32_t k, int all, int rev, uint32_t pattern_idx, OracleOut *out) {
+                         int32_t k, int all, int rev, uint32_t pattern_idx, uint64_t text_idx,
+                         const OracleOpts *o, OracleOut *out) {
   int32_t *c = bottom_row(profile, p, m, t, n, rev);
   uint64_t *sel = (uint64_t *)malloc((n + 2) * sizeof(uint64_t));
   size_t ns = select_v1(c, n, k, all, sel);
   int rc = 0;
+  /* end filter (search_with_fn, src/search.rs:895-905) with the closure of bin/crispr.rs:
+   * the pam_len characters before the end match the PAM (complemented on the rc strand).
+   * An end position shorter than the PAM panics in the reference; it is rejected here. */
+  if (o && o->pam && o->pam_len) {
+    uint8_t pamc[64];
+    const uint8_t *pam = o->pam;
+    if (rev) {
+      oracle_complement(profile, o->pam, o->pam_len, pamc);
+      pam = pamc;
+    }
+    size_t w = 0;
+    for (size_t a = 0; a < ns; a++) {
+      size_t end = sel[a];
+      int ok = end >= o->pam_len;
+      for (size_t i = 0; ok && i < o->pam_len; i++)
+        ok = trace_eq(profile, text_at(t, n, rev, end - o->pam_len + i), pam[i]);
+      if (ok) sel[w++] = end;
+    }
+    ns = w;
+  }
+  /* N end-point filter: src/search.rs:907-919, src/n_filter.rs:41-53 */
+  if (o && o->max_n_frac >= 0.f) {
+    size_t w = 0;
+    for (size_t a = 0; a < ns; a++) {
+      size_t end = sel[a] < n ? sel[a] : n;
+      size_t mand = m > (size_t)k ? m - (size_t)k : 0;
+      size_t start = end > mand ? end - mand : 0;
+      if (n_fraction_ok(t, n, rev, start, end, o->max_n_frac, m + (size_t)k)) sel[w++] = sel[a];
+    }
+    ns = w;
+  }
+  /* only_best_match: rightmost end with minimal cost, src/search.rs:1392-1413 */
+  if (o && o->only_best && ns > 0) {
+    size_t best = 0;
+    for (size_t a = 1; a < ns; a++)
+      if (c[sel[a]] < c[sel[best]] || (c[sel[a]] == c[sel[best]] && sel[a] > sel[best])) best = a;
+    sel[0] = sel[best];
+    ns = 1;
+  }
   for (size_t a = 0; a < ns; a++) {
     size_t end = sel[a];
     size_t fill = m + (size_t)k;
     size_t off = end > fill ? end - fill : 0; /* saturating_sub: :1477 */
     OracleMatch mm;
     memset(&mm, 0, sizeof mm);
-    char *ops;
-    size_t nops;
-    if (trace_window(profile, p, m, t, n, rev, off, end, &mm, &ops, &nops) != 0) rc = -1;
+    char *ops = NULL;
+    size_t nops = 0;
+    if (o && o->without_trace) {
+      /* src/search.rs:1464-1475 and the rc mapping :859-872 */
+      mm.text_start = UINT64_MAX;
+      mm.text_end = end < n ? end : n;
+      mm.pattern_start = UINT32_MAX;
+      mm.pattern_end = (uint32_t)m;
+      mm.cost = c[end];
+    } else {
+      if (trace_window(profile, p, m, t, n, rev, off, end, &mm, &ops, &nops) != 0) rc = -1;
+      /* traced N filter: src/search.rs:924-934, src/n_filter.rs:59-61 */
+      if (o && o->max_n_frac >= 0.f &&
+          !n_fraction_ok(t, n, rev, mm.text_start, mm.text_end, o->max_n_frac, 0)) {
+        free(ops);
+        continue;
+      }
+    }
     mm.pattern_idx = pattern_idx;
+    mm.text_idx = text_idx;
     mm.strand = rev ? 1 : 0;
     if (rev) {
       /* map to forward coordinates: src/search.rs:859-877 */
       uint64_t rs = mm.text_start, re = mm.text_end;
       mm.text_start = n - re;
-      mm.text_end = n - rs;
+      mm.text_end = (o && o->without_trace) ? UINT64_MAX : n - rs;
     }
-    out_push(out, mm, ops, nops);
+    out_push(out, mm, ops ? ops : "", nops);
     free(ops);
   }
   free(sel);
@@ -399,16 +479,58 @@ const char *oracle_out_ops(const OracleOut *o) { return o->ops; }
  * Output order: forward matches by ascending end, then rc matches by
  * ascending end in the reversed text.  Returns 0, or -1 when a traceback
  * failed (the reference would panic), -2 on an invalid IUPAC pattern.       */
+static int search_pair(int profile, const uint8_t *pattern, size_t m, const uint8_t *text, size_t n,
+                       uint32_t k, int rc_strand, int all, uint32_t pattern_idx, uint64_t text_idx,
+                       const OracleOpts *o, OracleOut *out) {
+  int rc = v1_one_strand(profile, pattern, m, text, n, (int32_t)k, all, 0, pattern_idx, text_idx, o, out);
+  if (rc_strand) {
+    uint8_t *cp = (uint8_t *)malloc(m + 1);
+    oracle_complement(profile, pattern, m, cp);
+    if (v1_one_strand(profile, cp, m, text, n, (int32_t)k, all, 1, pattern_idx, text_idx, o, out) != 0) rc = -1;
+    free(cp);
+  }
+  return rc;
+}
+
 int oracle_search(int profile, const uint8_t *pattern, size_t m, const uint8_t *text, size_t n,
                   uint32_t k, int rc_strand, int all, OracleOut *out) {
   init_tables();
   if (profile == PROFILE_IUPAC && !oracle_iupac_valid(pattern, m)) return -2;
-  int rc = v1_one_strand(profile, pattern, m, text, n, (int32_t)k, all, 0, 0, out);
-  if (rc_strand) {
-    uint8_t *cp = (uint8_t *)malloc(m + 1);
-    oracle_complement(profile, pattern, m, cp);
-    if (v1_one_strand(profile, cp, m, text, n, (int32_t)k, all, 1, 0, out) != 0) rc = -1;
-    free(cp);
+  return search_pair(profile, pattern, m, text, n, k, rc_strand, all, 0, 0, NULL, out);
+}
+
+/* search / search_all / search_with_fn(PAM) under the Searcher options. */
+int oracle_search_opts(int profile, const uint8_t *pattern, size_t m, const uint8_t *text, size_t n,
+                       uint32_t k, int rc_strand, int all, int without_trace, int only_best,
+                       float max_n_frac, const uint8_t *pam, size_t pam_len, OracleOut *out) {
+  init_tables();
+  if (profile == PROFILE_IUPAC && !oracle_iupac_valid(pattern, m)) return -2;
+  if (pam_len > 64) return -3;
+  OracleOpts o = {without_trace, only_best, max_n_frac, pam, pam_len};
+  return search_pair(profile, pattern, m, text, n, k, rc_strand, all, 0, 0, &o, out);
+}
+
+/* Searcher::search_many in SearchMode::Single (src/search.rs:531-553,1519-1549): every pattern
+ * against every text with `search`, pattern-major; the other modes must return the same set
+ * (src/search.rs:3624-3730).  Patterns / texts are concatenated; *_lens give the lengths.   */
+int oracle_search_many(int profile, const uint8_t *patterns, const uint64_t *pattern_lens,
+                       size_t n_patterns, const uint8_t *texts, const uint64_t *text_lens,
+                       size_t n_texts, uint32_t k, int rc_strand, int without_trace, int only_best,
+                       float max_n_frac, OracleOut *out) {
+  init_tables();
+  OracleOpts o = {without_trace, only_best, max_n_frac, NULL, 0};
+  int rc = 0;
+  const uint8_t *p = patterns;
+  for (size_t pi = 0; pi < n_patterns; pi++) {
+    if (profile == PROFILE_IUPAC && !oracle_iupac_valid(p, pattern_lens[pi])) return -2;
+    const uint8_t *t = texts;
+    for (size_t ti = 0; ti < n_texts; ti++) {
+      if (search_pair(profile, p, pattern_lens[pi], t, text_lens[ti], k, rc_strand, 0, (uint32_t)pi, ti,
+                      &o, out) != 0)
+        rc = -1;
+      t += text_lens[ti];
+    }
+    p += pattern_lens[pi];
   }
   return rc;
 }
@@ -425,9 +547,20 @@ int oracle_search(int profile, const uint8_t *pattern, size_t m, const uint8_t *
  * own fuzz test sorts before comparing, src/pattern_tiling/search.rs:748-796).
  * The traceback window starts at max(0, range.start - (m+k)) like the
  * reference (src/pattern_tiling/trace.rs:65-82), not at end-(m+k).           */
+int oracle_search_encoded_nfrac(int profile, const uint8_t *patterns, size_t n_patterns, size_t m,
+                                const uint8_t *text, size_t n, uint32_t k, int rc_strand, int all,
+                                float max_n_frac, OracleOut *out);
+
 int oracle_search_encoded(int profile, const uint8_t *patterns, size_t n_patterns, size_t m,
                           const uint8_t *text, size_t n, uint32_t k, int rc_strand, int all,
                           OracleOut *out) {
+  return oracle_search_encoded_nfrac(profile, patterns, n_patterns, m, text, n, k, rc_strand, all, -1.f, out);
+}
+
+/* max_n_frac >= 0: traced N filter of the v2 engine (src/pattern_tiling/general.rs:399-402). */
+int oracle_search_encoded_nfrac(int profile, const uint8_t *patterns, size_t n_patterns, size_t m,
+                                const uint8_t *text, size_t n, uint32_t k, int rc_strand, int all,
+                                float max_n_frac, OracleOut *out) {
   init_tables();
   if (m == 0 || m > 64) return -3; /* general.rs:285-291, tqueries.rs:60-66 */
   for (size_t q = 0; q < n_patterns; q++)
@@ -459,7 +592,8 @@ int oracle_search_encoded(int profile, const uint8_t *patterns, size_t n_pattern
       if (trace_window(profile, p, m, text, n, 0, off, end, &mm, &ops, &nops) != 0) rc = -1;
       mm.pattern_idx = (uint32_t)(q % n_patterns);
       mm.strand = q >= n_patterns ? 1 : 0;
-      out_push(out, mm, ops, nops);
+      if (max_n_frac < 0.f || n_fraction_ok(text, n, 0, mm.text_start, mm.text_end, max_n_frac, 0))
+        out_push(out, mm, ops, nops);
       free(ops);
     }
     free(c);

@@ -99,6 +99,17 @@ SIGNATURES = {
     "sassy_gpu_text_free": (None, [c_void_p, c_void_p]),
     "sassy_gpu_search": (c_void_p, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, ctypes.c_int]),
     "sassy_gpu_search_text": (c_void_p, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, ctypes.c_int]),
+    "sassy_gpu_set_trace": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "sassy_gpu_set_only_best_match": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "sassy_gpu_set_max_n_frac": (ctypes.c_int, [c_void_p, ctypes.c_float]),
+    "sassy_gpu_search_pam": (c_void_p, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, ctypes.c_int,
+                                        c_void_p, c_size_t]),
+    "sassy_gpu_search_pam_text": (c_void_p, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, ctypes.c_int,
+                                             c_void_p, c_size_t]),
+    "sassy_gpu_search_patterns": (c_void_p, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_size_t]),
+    "sassy_gpu_search_texts": (c_void_p, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_size_t]),
+    "sassy_gpu_search_many": (c_void_p, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t,
+                                         c_size_t]),
     "sassy_gpu_encode_patterns": (c_void_p, [c_void_p, c_void_p, c_size_t, c_size_t]),
     "sassy_gpu_patterns_free": (None, [c_void_p]),
     "sassy_gpu_search_encoded": (c_void_p, [c_void_p, c_void_p, c_void_p, c_size_t, ctypes.c_int]),

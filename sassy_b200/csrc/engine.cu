@@ -78,7 +78,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   for (DevBuf* b : {&eq_, &patterns_, &revflags_, &keys_, &cost_, &keys2_, &cost2_, &flags_, &sel_, &count_,
-                    &cubtmp_, &scratch_, &ops_, &out_, &feq_, &hits_, &d_stage_})
+                    &cubtmp_, &scratch_, &ops_, &out_, &feq_, &hits_, &d_stage_, &best_, &sel_cost_, &d_texts_})
     b->release();
   if (staged_.d) cudaFree(staged_.d);
   if (h_stage_) cudaFreeHost(h_stage_);
@@ -297,8 +297,165 @@ void Engine::make_tensor_map(CUtensorMap* map, const DeviceText& text, const Sca
   }
 }
 
-void Engine::search(const DeviceText& text, const std::vector<Query>& queries, int m, int k, bool all_minima,
-                    bool include_pos0, MatchSet& out) {
+// Candidates (unsorted, in keys_/cost_) -> device radix sort -> selection (first copy of a
+// position, local-minima rule, end filters, only_best_match) -> stream compaction -> traceback
+// (or end position + cost only) -> host.  Returns the number of records written to `out`.
+uint64_t Engine::post_process(const PostCtx& c, const SearchOpts& opts, uint64_t ncand, MatchSet& out) {
+  const int m = c.m, k = c.k, W = c.W;
+  unsigned long long* d_nsel = c.d_counts + 1;
+  unsigned long long h_counts[4] = {0, 0, 0, 0};
+  auto read_counts = [&]() {
+    SB_CUDA(cudaMemcpyAsync(h_counts, c.d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, stream_));
+    SB_CUDA(cudaStreamSynchronize(stream_));
+  };
+  keys2_.ensure(ncand * sizeof(uint64_t));
+  cost2_.ensure(ncand * sizeof(uint32_t));
+  size_t tmp_bytes = 0;
+  SB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_.as<uint64_t>(), keys2_.as<uint64_t>(),
+                                          cost_.as<uint32_t>(), cost2_.as<uint32_t>(), ncand, 0, c.end_bit,
+                                          stream_));
+  cubtmp_.ensure(tmp_bytes);
+  SB_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp_.p, tmp_bytes, keys_.as<uint64_t>(), keys2_.as<uint64_t>(),
+                                          cost_.as<uint32_t>(), cost2_.as<uint32_t>(), ncand, 0, c.end_bit,
+                                          stream_));
+  const uint64_t* skeys = keys2_.as<uint64_t>();
+  const uint32_t* scost = cost2_.as<uint32_t>();
+  const uint64_t* sel_keys = skeys;
+  const uint32_t* sel_cost = scost;
+  // overlapping re-scan windows of the prefilter report an end position more than once; the
+  // selection kernel keeps the first copy only
+  const bool end_filter = opts.pam_len > 0 || (opts.n_endpoint && opts.max_n_frac >= 0.f);
+  const bool need_select = !opts.all_minima || c.dedup || end_filter || opts.only_best;
+  if (need_select) {
+    flags_.ensure(ncand);
+    sel_.ensure(ncand * sizeof(uint64_t));
+    EndFilter ef;
+    memset(&ef, 0, sizeof ef);
+    if (end_filter) {
+      if (opts.pam_len > kMaxPam) throw CudaError("PAM longer than 16 characters is not supported");
+      ef.text = c.text;
+      ef.rev_flags = c.d_rev;
+      ef.profile = profile_;
+      ef.m = m, ef.k = k;
+      ef.pam_len = opts.pam_len;
+      for (int i = 0; i < opts.pam_len; i++) {
+        ef.pam[0][i] = opts.pam[i];
+        ef.pam[1][i] = complement_byte(profile_, opts.pam[i]);
+      }
+      ef.n_endpoint = (opts.n_endpoint && opts.max_n_frac >= 0.f) ? 1 : 0;
+      ef.max_n_frac = opts.max_n_frac;
+    }
+    SB_CUDA(launch_minima(skeys, scost, ncand, flags_.as<uint8_t>(), opts.all_minima, end_filter ? &ef : nullptr,
+                          stream_));
+    stats_.aux_launches++;
+    if (opts.only_best) {
+      best_.ensure((size_t)c.nslots * sizeof(unsigned long long));
+      SB_CUDA(launch_best(skeys, scost, ncand, flags_.as<uint8_t>(), best_.as<unsigned long long>(), c.nslots,
+                          stream_));
+      stats_.aux_launches += 2;
+    }
+    size_t tmp2 = 0;
+    SB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp2, skeys, flags_.as<uint8_t>(), sel_.as<uint64_t>(), d_nsel,
+                                       ncand, stream_));
+    cubtmp_.ensure(tmp2);
+    SB_CUDA(cub::DeviceSelect::Flagged(cubtmp_.p, tmp2, skeys, flags_.as<uint8_t>(), sel_.as<uint64_t>(), d_nsel,
+                                       ncand, stream_));
+    sel_keys = sel_.as<uint64_t>();
+    if (opts.without_trace) {
+      sel_cost_.ensure(ncand * sizeof(uint32_t));
+      SB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp2, scost, flags_.as<uint8_t>(), sel_cost_.as<uint32_t>(),
+                                         d_nsel, ncand, stream_));
+      cubtmp_.ensure(tmp2);
+      SB_CUDA(cub::DeviceSelect::Flagged(cubtmp_.p, tmp2, scost, flags_.as<uint8_t>(), sel_cost_.as<uint32_t>(),
+                                         d_nsel, ncand, stream_));
+      sel_cost = sel_cost_.as<uint32_t>();
+    }
+  }
+  // Small candidate lists (the normal case): trace every possible selection slot bounded by the
+  // device-side count and fetch results + count with one synchronisation.  Large lists: read
+  // the count first so that buffers and copies have the exact size.
+  const bool fast = ncand <= 65536;
+  uint64_t bound = ncand;
+  if (need_select && !fast) {
+    read_counts();
+    bound = h_counts[1];
+  }
+  uint64_t nsel = 0;
+  if (bound > 0) {
+    const uint64_t words_per_match = opts.without_trace ? 0 : (uint64_t)(m + k + 1) * W * 2;
+    const uint64_t max_scratch_words = (512ull << 20) / 4;  // 512 MiB of scratch per slice
+    uint64_t slice = bound;
+    while (slice > 1 && trace_threads(slice) * words_per_match > max_scratch_words) slice = (slice + 1) / 2;
+    scratch_.ensure(trace_threads(slice) * words_per_match * sizeof(uint32_t));
+    out_.ensure(bound * sizeof(GpuMatch));
+    const uint32_t ops_words = opts.without_trace ? 0 : out.ops_words;
+    ops_.ensure(bound * ops_words * sizeof(uint32_t));
+    TraceArgs t;
+    memset(&t, 0, sizeof t);
+    t.text = c.text;
+    t.profile = profile_;
+    t.patterns = c.d_pat;
+    t.rev_flags = c.d_rev;
+    t.eq = c.d_eq;
+    t.nrows = nrows_;
+    t.sh0 = sh0_;
+    t.msk0 = msk0_;
+    t.m = m;
+    t.k = k;
+    t.W = W;
+    t.keys = sel_keys;
+    t.costs = opts.without_trace ? sel_cost : nullptr;
+    t.max_n_frac = opts.without_trace ? -1.f : opts.max_n_frac;
+    t.count_dev = (need_select && fast) ? d_nsel : nullptr;
+    t.scratch = scratch_.as<uint32_t>();
+    t.ops = ops_.as<uint32_t>();
+    t.ops_words = ops_words;
+    t.out = out_.as<GpuMatch>();
+    for (uint64_t first = 0; first < bound; first += slice) {
+      t.first = first;
+      t.count = std::min(slice, bound - first);
+      SB_CUDA(launch_trace(t, stream_));
+      stats_.aux_launches++;
+    }
+    out.m.resize(bound);
+    out.ops.resize(bound * out.ops_words);
+    SB_CUDA(cudaMemcpyAsync(out.m.data(), out_.p, bound * sizeof(GpuMatch), cudaMemcpyDeviceToHost, stream_));
+    if (ops_words)
+      SB_CUDA(cudaMemcpyAsync(out.ops.data(), ops_.p, out.ops.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                              stream_));
+  }
+  if (need_select && fast) {
+    read_counts();
+    nsel = h_counts[1];
+    out.m.resize(nsel);
+    out.ops.resize(nsel * out.ops_words);
+  } else {
+    SB_CUDA(cudaStreamSynchronize(stream_));
+    nsel = bound;
+  }
+  // traced N-fraction filter (src/search.rs:924-934, general.rs:399-402): the kernel flagged
+  // the records, drop them here (keeps order)
+  if (!opts.without_trace && opts.max_n_frac >= 0.f) {
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < nsel; i++) {
+      if (out.m[i].failed & 2u) continue;
+      if (w != i) {
+        out.m[w] = out.m[i];
+        std::copy(out.ops.begin() + i * out.ops_words, out.ops.begin() + (i + 1) * out.ops_words,
+                  out.ops.begin() + w * out.ops_words);
+      }
+      w++;
+    }
+    nsel = w;
+    out.m.resize(nsel);
+    out.ops.resize(nsel * out.ops_words);
+  }
+  return nsel;
+}
+
+void Engine::search(const DeviceText& text, const std::vector<Query>& queries, int m, int k, const SearchOpts& opts,
+                    MatchSet& out) {
+  const bool all_minima = opts.all_minima, include_pos0 = opts.include_pos0;
   SB_CUDA(cudaSetDevice(device_));
   cudaGetLastError();  // a stale error left by another library in this thread is not ours to report
   stats_ = SearchStats();
@@ -414,7 +571,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   int end_bit = kPosBits;
   while ((1ull << (end_bit - kPosBits)) < nq) end_bit++;
   const uint64_t words_per_match = (uint64_t)(m + k + 1) * W * 2;
-  const bool small_path = words_per_match <= 4096;
+  const bool small_path = words_per_match <= 4096 && !opts.special();
   unsigned long long* d_big = d_counts + 3;
   if (small_path) {
     const size_t need_out = (size_t)kSmallCandidates * sizeof(GpuMatch);
@@ -437,8 +594,8 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
                               d_big, all_minima, end_bit, stream_));
     TraceArgs t;
     memset(&t, 0, sizeof t);
-    t.text = text.d;
-    t.n = n;
+    t.text = TextRef{text.d, n, nullptr, nullptr, nq};
+    t.max_n_frac = -1.f;
     t.profile = profile_;
     t.patterns = d_pat;
     t.rev_flags = d_rev;
@@ -602,99 +759,22 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   }
   stats_.candidates = ncand;
 
-  // ---- sort, select (de-duplicate + local minima), trace ------------------------------------
+  // ---- sort, select (de-duplicate + local minima + end filters), trace ------------------------
   uint64_t nsel = 0;
   if (small_done) {
     nsel = h_counts[1];
     out.m.assign(h_small_out, h_small_out + nsel);
     out.ops.assign(h_small_ops, h_small_ops + nsel * out.ops_words);
   } else if (ncand > 0) {
-    keys2_.ensure(ncand * sizeof(uint64_t));
-    cost2_.ensure(ncand * sizeof(uint32_t));
-    size_t tmp_bytes = 0;
-    SB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_.as<uint64_t>(), keys2_.as<uint64_t>(),
-                                            cost_.as<uint32_t>(), cost2_.as<uint32_t>(), ncand, 0, end_bit,
-                                            stream_));
-    cubtmp_.ensure(tmp_bytes);
-    SB_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp_.p, tmp_bytes, keys_.as<uint64_t>(), keys2_.as<uint64_t>(),
-                                            cost_.as<uint32_t>(), cost2_.as<uint32_t>(), ncand, 0, end_bit,
-                                            stream_));
-    const uint64_t* skeys = keys2_.as<uint64_t>();
-    const uint32_t* scost = cost2_.as<uint32_t>();
-    const uint64_t* sel_keys = skeys;
-    // overlapping re-scan windows of the prefilter report an end position more than once; the
-    // selection kernel keeps the first copy only
-    const bool need_select = !all_minima || filtered;
-    if (need_select) {
-      flags_.ensure(ncand);
-      sel_.ensure(ncand * sizeof(uint64_t));
-      SB_CUDA(launch_minima(skeys, scost, ncand, flags_.as<uint8_t>(), all_minima, stream_));
-      stats_.aux_launches++;
-      size_t tmp2 = 0;
-      SB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp2, skeys, flags_.as<uint8_t>(), sel_.as<uint64_t>(), d_nsel,
-                                         ncand, stream_));
-      cubtmp_.ensure(tmp2);
-      SB_CUDA(cub::DeviceSelect::Flagged(cubtmp_.p, tmp2, skeys, flags_.as<uint8_t>(), sel_.as<uint64_t>(), d_nsel,
-                                         ncand, stream_));
-      sel_keys = sel_.as<uint64_t>();
-    }
-    // Small candidate lists (the normal case): trace every possible selection slot bounded by the
-    // device-side count and fetch results + count with one synchronisation.  Large lists: read
-    // the count first so that buffers and copies have the exact size.
-    const bool fast = ncand <= 65536;
-    uint64_t bound = ncand;
-    if (need_select && !fast) {
-      read_counts();
-      bound = h_counts[1];
-    }
-    if (bound > 0) {
-      const uint64_t words_per_match = (uint64_t)(m + k + 1) * W * 2;
-      const uint64_t max_scratch_words = (512ull << 20) / 4;  // 512 MiB of scratch per slice
-      uint64_t slice = bound;
-      while (slice > 1 && trace_threads(slice) * words_per_match > max_scratch_words) slice = (slice + 1) / 2;
-      scratch_.ensure(trace_threads(slice) * words_per_match * sizeof(uint32_t));
-      out_.ensure(bound * sizeof(GpuMatch));
-      ops_.ensure(bound * out.ops_words * sizeof(uint32_t));
-      TraceArgs t;
-      memset(&t, 0, sizeof t);
-      t.text = text.d;
-      t.n = n;
-      t.profile = profile_;
-      t.patterns = d_pat;
-      t.rev_flags = d_rev;
-      t.eq = d_eq;
-      t.nrows = nrows_;
-      t.sh0 = sh0_;
-      t.msk0 = msk0_;
-      t.m = m;
-      t.k = k;
-      t.W = W;
-      t.keys = sel_keys;
-      t.count_dev = (need_select && fast) ? d_nsel : nullptr;
-      t.scratch = scratch_.as<uint32_t>();
-      t.ops = ops_.as<uint32_t>();
-      t.ops_words = out.ops_words;
-      t.out = out_.as<GpuMatch>();
-      for (uint64_t first = 0; first < bound; first += slice) {
-        t.first = first;
-        t.count = std::min(slice, bound - first);
-        SB_CUDA(launch_trace(t, stream_));
-        stats_.aux_launches++;
-      }
-      out.m.resize(bound);
-      out.ops.resize(bound * out.ops_words);
-      SB_CUDA(cudaMemcpyAsync(out.m.data(), out_.p, bound * sizeof(GpuMatch), cudaMemcpyDeviceToHost, stream_));
-      SB_CUDA(cudaMemcpyAsync(out.ops.data(), ops_.p, out.ops.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                              stream_));
-    }
-    if (need_select && fast) {
-      read_counts();
-      nsel = h_counts[1];
-      out.m.resize(nsel);
-      out.ops.resize(nsel * out.ops_words);
-    } else {
-      nsel = bound;
-    }
+    PostCtx c;
+    c.text = TextRef{text.d, n, nullptr, nullptr, nq};
+    c.nslots = nq;
+    c.m = m, c.k = k, c.W = W;
+    c.d_pat = d_pat, c.d_rev = d_rev, c.d_eq = d_eq;
+    c.d_counts = d_counts;
+    c.dedup = filtered;
+    c.end_bit = end_bit;
+    nsel = post_process(c, opts, ncand, out);
   }
   SB_CUDA(cudaEventRecord(ev_[3], stream_));
   SB_CUDA(cudaStreamSynchronize(stream_));
@@ -709,6 +789,127 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     stats_.transfer_packed = transfer_packed_ ? 1 : 0;
     stats_.transfer_bytes = transfer_bytes_;
   }
+}
+
+// Every query against every text.  The texts are packed back to back (16-byte aligned starts)
+// into one device buffer per call; candidates carry slot = text * nq + query, and the shared
+// post-processing resolves a slot back to its text through TextRef.
+void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, size_t ntexts,
+                          const std::vector<Query>& queries, int m, int k, const SearchOpts& opts, MatchSet& out) {
+  SB_CUDA(cudaSetDevice(device_));
+  cudaGetLastError();
+  stats_ = SearchStats();
+  out.m.clear();
+  out.ops.clear();
+  const uint32_t nq = (uint32_t)queries.size();
+  if (m <= 0) throw CudaError("empty pattern");
+  const int W = round_words((m + 31) / 32);
+  if (W < 0) throw CudaError("pattern longer than 1024 characters is not supported");
+  if (k < 0) k = 0;
+  out.ops_words = (uint32_t)((m + k + 1 + 15) / 16);
+  stats_.words = (uint32_t)W;
+  if (nq == 0 || ntexts == 0) return;
+  const uint64_t nslots = (uint64_t)ntexts * nq;
+  if (nslots >= (1ull << (64 - kPosBits))) throw CudaError("too many (text, query) pairs in one search");
+
+  // ---- pack and upload the texts -------------------------------------------------------------
+  std::vector<uint64_t> meta(2 * ntexts);
+  uint64_t total = 0;
+  for (size_t i = 0; i < ntexts; i++) {
+    if (lens[i] >= (1ull << kPosBits)) throw CudaError("text longer than 2^40 bytes is not supported");
+    meta[i] = total;
+    meta[ntexts + i] = lens[i];
+    total += (lens[i] + 15) & ~15ull;
+  }
+  const size_t text_bytes = (size_t)total + 64;
+  const size_t meta_off = (text_bytes + 255) & ~(size_t)255;
+  std::vector<uint8_t> packed(meta_off + meta.size() * sizeof(uint64_t), 0);
+  for (size_t i = 0; i < ntexts; i++)
+    if (lens[i]) memcpy(&packed[meta[i]], texts[i], lens[i]);
+  memcpy(&packed[meta_off], meta.data(), meta.size() * sizeof(uint64_t));
+  d_texts_.ensure(packed.size());
+  SB_CUDA(cudaEventRecord(ev_[0], stream_));
+  SB_CUDA(cudaMemcpyAsync(d_texts_.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, stream_));
+  const uint8_t* d_base = d_texts_.as<uint8_t>();
+  const uint64_t* d_offs = reinterpret_cast<const uint64_t*>(d_base + meta_off);
+  const uint64_t* d_lens = d_offs + ntexts;
+
+  upload_params(queries, m, W, FilterPlan(), false, false);
+  uint8_t* dst = d_stage_.as<uint8_t>();
+  unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(dst + off_counts_);
+  const uint32_t* d_eq = reinterpret_cast<const uint32_t*>(dst + off_eq_);
+  const uint8_t* d_pat = dst + off_pat_;
+  const uint8_t* d_rev = dst + off_rev_;
+
+  if (cand_cap_ == 0) cand_cap_ = 1ull << 20;
+  ScanArgs a;
+  memset(&a, 0, sizeof a);
+  a.sh0 = sh0_;
+  a.msk0 = msk0_;
+  a.nrows = nrows_;
+  a.rowbytes = (uint32_t)W * 4u;
+  a.m = m;
+  a.k = k;
+  a.nq = nq;
+  a.eq = d_eq;
+  a.cand_count = d_counts;
+  TextsArgs t;
+  memset(&t, 0, sizeof t);
+  t.base = d_base;
+  t.offs = d_offs;
+  t.lens = d_lens;
+  t.rev_flags = d_rev;
+  t.ntexts = (uint32_t)ntexts;
+  t.nq = nq;
+  t.include_pos0 = opts.include_pos0 ? 1 : 0;
+
+  unsigned long long h_counts[4] = {0, 0, 0, 0};
+  uint64_t ncand = 0;
+  for (int attempt = 0;; attempt++) {
+    keys_.ensure(cand_cap_ * sizeof(uint64_t));
+    cost_.ensure(cand_cap_ * sizeof(uint32_t));
+    a.cand_keys = keys_.as<uint64_t>();
+    a.cand_cost = cost_.as<uint32_t>();
+    a.cand_cap = cand_cap_;
+    if (attempt > 0) SB_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long), stream_));
+    SB_CUDA(cudaEventRecord(ev_[1], stream_));
+    SB_CUDA(launch_texts(W, a, t, stream_));
+    stats_.scan_launches++;
+    SB_CUDA(cudaEventRecord(ev_[2], stream_));
+    SB_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, stream_));
+    SB_CUDA(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    SB_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2]));
+    stats_.scan_ms += ms;
+    if (h_counts[0] <= cand_cap_) {
+      ncand = h_counts[0];
+      break;
+    }
+    if (attempt >= 3) throw CudaError("candidate buffer overflow after retries");
+    cand_cap_ = (size_t)(h_counts[0] + h_counts[0] / 8 + 1024);
+    stats_.retries++;
+  }
+  stats_.candidates = ncand;
+  uint64_t nsel = 0;
+  if (ncand > 0) {
+    PostCtx c;
+    c.text = TextRef{d_base, 0, d_offs, d_lens, nq};
+    c.nslots = (uint32_t)nslots;
+    c.m = m, c.k = k, c.W = W;
+    c.d_pat = d_pat, c.d_rev = d_rev, c.d_eq = d_eq;
+    c.d_counts = d_counts;
+    c.dedup = false;
+    c.end_bit = kPosBits;
+    while ((1ull << (c.end_bit - kPosBits)) < nslots) c.end_bit++;
+    nsel = post_process(c, opts, ncand, out);
+  }
+  SB_CUDA(cudaEventRecord(ev_[3], stream_));
+  SB_CUDA(cudaStreamSynchronize(stream_));
+  float total_ms = 0;
+  SB_CUDA(cudaEventElapsedTime(&total_ms, ev_[0], ev_[3]));
+  stats_.total_ms = total_ms;
+  stats_.matches = nsel;
+  stats_.rows = (uint32_t)ntexts;
 }
 
 }  // namespace sb

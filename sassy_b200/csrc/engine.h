@@ -71,6 +71,30 @@ struct MatchSet {
   uint32_t ops_words = 0;
 };
 
+// Per-search options (reference Searcher fields src/search.rs:227-256 and the arguments of
+// search / search_all / search_with_fn).
+struct SearchOpts {
+  bool all_minima = false;     // search_all: every end position with cost <= k
+  bool include_pos0 = false;   // v1: end position 0 is a candidate when m <= k (src/search.rs:1320-1322)
+  bool without_trace = false;  // Searcher::without_trace (src/search.rs:446-449)
+  bool only_best = false;      // Searcher::only_best_match (src/search.rs:441-444)
+  float max_n_frac = -1.f;     // Searcher::set_max_n_frac (src/search.rs:452-458); < 0 = off
+  bool n_endpoint = false;     // also apply the pre-trace N end-point filter (v1, src/search.rs:907-919)
+  const uint8_t* pam = nullptr;  // end filter of search_with_fn as used by bin/crispr.rs:198-205
+  int pam_len = 0;
+  bool special() const { return without_trace || only_best || max_n_frac >= 0.f || pam_len > 0; }
+};
+
+// Many texts resident in HBM (search_texts / search_many): the texts back to back, every
+// start aligned to 16 bytes, followed by zero padding.
+struct DeviceTexts {
+  uint8_t* d = nullptr;
+  uint64_t* d_offs = nullptr;  // [count] start of text i in d
+  uint64_t* d_lens = nullptr;  // [count]
+  std::vector<uint64_t> lens;
+  uint64_t total = 0;
+};
+
 class Engine {
  public:
   Engine(int profile, int device);
@@ -95,8 +119,13 @@ class Engine {
   // Queries must all have length m; forward queries must precede reversed ones.
   // include_pos0: also consider end position 0 (cost m) when m <= k (v1 only,
   // reference src/search.rs:1320-1322).
-  void search(const DeviceText& text, const std::vector<Query>& queries, int m, int k, bool all_minima,
-              bool include_pos0, MatchSet& out);
+  void search(const DeviceText& text, const std::vector<Query>& queries, int m, int k, const SearchOpts& opts,
+              MatchSet& out);
+  // Every query against every text: one thread per (text, query) pair; GpuMatch::qs =
+  // text index * queries.size() + query index.  For many short texts (reference
+  // Searcher::search_texts / search_many, src/search.rs:531-640).
+  void search_texts(const uint8_t* const* texts, const uint64_t* lens, size_t ntexts,
+                    const std::vector<Query>& queries, int m, int k, const SearchOpts& opts, MatchSet& out);
 
   const SearchStats& stats() const { return stats_; }
   void set_variant(int v) { variant_ = v; }
@@ -106,6 +135,18 @@ class Engine {
   void set_filter_mode(int m) { filter_mode_ = m; }
 
  private:
+  struct PostCtx {
+    TextRef text;
+    uint32_t nslots = 0;  // query slots (queries, or texts x queries)
+    int m = 0, k = 0, W = 0;
+    const uint8_t* d_pat = nullptr;
+    const uint8_t* d_rev = nullptr;
+    const uint32_t* d_eq = nullptr;
+    unsigned long long* d_counts = nullptr;
+    bool dedup = false;   // candidate list may hold a position more than once
+    int end_bit = 64;
+  };
+  uint64_t post_process(const PostCtx& c, const SearchOpts& opts, uint64_t ncand, MatchSet& out);
   void upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair, bool fused);
   void make_tensor_map(CUtensorMap* map, const DeviceText& text, const ScanGeom& g) const;
   // host -> dst (device, padded): packed transport for large Dna texts, else plain copies
@@ -136,7 +177,7 @@ class Engine {
   DevBuf eq_, patterns_, revflags_;
   DevBuf keys_, cost_, keys2_, cost2_, flags_, sel_, count_, cubtmp_;
   DevBuf scratch_, ops_, out_;
-  DevBuf feq_, hits_, d_stage_, sel_small_;
+  DevBuf feq_, hits_, d_stage_, sel_small_, best_, sel_cost_, d_texts_;
   uint8_t* h_small_ = nullptr;  // pinned: results of the small-list fast path, written by the GPU
   size_t h_small_cap_ = 0;
   uint8_t* h_stage_ = nullptr;  // pinned staging for the per-search parameter block

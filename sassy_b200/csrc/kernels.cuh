@@ -34,9 +34,25 @@ cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtens
 // nhits is read from a.hit_count on the device (clipped to a.hit_cap): no host round trip.
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream);
 
-// flags[i] = 1 iff sorted candidate i is kept by the local-minima rule.
+// Many texts, one thread per (text, query) pair (search_texts / search_many).
+struct TextsArgs {
+  const uint8_t* base;       // texts back to back, every start 16-byte aligned, zero padded
+  const uint64_t* offs;      // [ntexts]
+  const uint64_t* lens;      // [ntexts]
+  const uint8_t* rev_flags;  // [nq]
+  uint32_t ntexts, nq;
+  uint32_t include_pos0;
+};
+cudaError_t launch_texts(int W, const ScanArgs& a, const TextsArgs& t, cudaStream_t stream);
+
+// flags[i] = 1 iff sorted candidate i is kept by the local-minima rule and, when `filter` is
+// given, by the end-position predicates (end_filter_pass, scan_core.cuh).
 cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags, bool all_minima,
-                          cudaStream_t stream);
+                          const EndFilter* filter, cudaStream_t stream);
+// only_best_match (reference src/search.rs:1392-1413): among the flagged candidates of every
+// query slot keep the one with minimal cost, rightmost on ties.  best[nslots] is scratch.
+cudaError_t launch_best(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags,
+                        unsigned long long* best, uint32_t nslots, cudaStream_t stream);
 
 // One-block sort + selection for candidate lists of at most kSmallCandidates entries, driven by
 // the device-side candidate count (*big = 1 and *nsel = 0 if the list is longer).
@@ -46,8 +62,7 @@ cudaError_t launch_post_small(const uint64_t* keys, const uint32_t* cost, const 
                               unsigned long long* big, bool all_minima, int end_bit, cudaStream_t stream);
 
 struct TraceArgs {
-  const uint8_t* text;
-  uint64_t n;
+  TextRef text;
   int profile;
   const uint8_t* patterns;  // [nq_total][m] raw query bytes (already complemented for rc slots)
   const uint8_t* rev_flags;  // [nq_total] 1 = query scans the reversed text
@@ -57,6 +72,8 @@ struct TraceArgs {
   int32_t m, k;
   int32_t W;
   const uint64_t* keys;  // selected candidates (sorted)
+  const uint32_t* costs; // without_trace: cost of every selected candidate (no traceback is run)
+  float max_n_frac;      // >= 0: flag traced matches whose text slice holds too many N (src/n_filter.rs:59-61)
   uint64_t first;        // slice [first, first+count) handled by this launch
   uint64_t count;
   const unsigned long long* count_dev;  // optional device-side total that clips the slice

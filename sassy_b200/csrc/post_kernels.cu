@@ -10,11 +10,33 @@
 namespace sb {
 namespace {
 
+template <bool FILTER>
 __global__ void minima_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cost, uint64_t n,
-                              uint8_t* __restrict__ flags, bool all_minima) {
+                              uint8_t* __restrict__ flags, bool all_minima, const __grid_constant__ EndFilter f) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  flags[i] = select_candidate(keys, cost, i, n, all_minima) ? 1 : 0;
+  bool keep = select_candidate(keys, cost, i, n, all_minima);
+  if (FILTER) keep = keep && end_filter_pass(f, keys[i]);
+  flags[i] = keep ? 1 : 0;
+}
+
+// (cost, rightmost end) packed so that the minimum is the best match of a slot
+__device__ __forceinline__ unsigned long long best_pack(uint64_t key, uint32_t cost) {
+  return ((unsigned long long)cost << kPosBits) | (((1ull << kPosBits) - 1) - key_pos(key));
+}
+
+__global__ void best_reduce_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cost, uint64_t n,
+                                   const uint8_t* __restrict__ flags, unsigned long long* __restrict__ best) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flags[i]) return;
+  atomicMin(&best[key_qs(keys[i])], best_pack(keys[i], cost[i]));
+}
+
+__global__ void best_flag_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cost, uint64_t n,
+                                 uint8_t* __restrict__ flags, const unsigned long long* __restrict__ best) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flags[i]) return;
+  if (best[key_qs(keys[i])] != best_pack(keys[i], cost[i])) flags[i] = 0;
 }
 
 // Whole post-processing of a SMALL candidate list in one block: sort by key, keep the first
@@ -100,21 +122,35 @@ __global__ void trace_kernel(const __grid_constant__ TraceArgs t) {
   const uint64_t key = t.keys[gi];
   const uint32_t qs = key_qs(key);
   const uint64_t end = key_pos(key);
-  const bool rev = t.rev_flags[qs] != 0;
-  ColStore cs;
-  cs.base = t.scratch + (li % nthreads);
-  cs.stride = nthreads;
-  TraceOut out;
-  trace_one<P>(t.text, t.n, rev, t.patterns + (size_t)qs * t.m, t.m, t.k,
-               t.eq + (size_t)qs * t.nrows * t.W, t.W, t.sh0, t.msk0, end, cs,
-               t.ops + gi * t.ops_words, t.ops_words, out);
+  const uint8_t* text;
+  uint64_t n;
+  uint32_t q;
+  text_of_slot(t.text, qs, text, n, q);
+  const bool rev = t.rev_flags[q] != 0;
   GpuMatch gm;
-  gm.text_start = out.text_start;
-  gm.text_end = out.text_end;
   gm.qs = qs;
-  gm.cost = out.cost;
-  gm.nops = out.nops;
-  gm.failed = out.failed;
+  if (t.costs) {  // without_trace: end position and cost only (reference src/search.rs:1464-1475)
+    gm.text_start = ~0ull;
+    gm.text_end = end < n ? end : n;
+    gm.cost = (int32_t)t.costs[gi];
+    gm.nops = 0;
+    gm.failed = 0;
+  } else {
+    ColStore cs;
+    cs.base = t.scratch + (li % nthreads);
+    cs.stride = nthreads;
+    TraceOut out;
+    trace_one<P>(text, n, rev, t.patterns + (size_t)q * t.m, t.m, t.k, t.eq + (size_t)q * t.nrows * t.W, t.W,
+                 t.sh0, t.msk0, end, cs, t.ops + gi * t.ops_words, t.ops_words, out);
+    gm.text_start = out.text_start;
+    gm.text_end = out.text_end;
+    gm.cost = out.cost;
+    gm.nops = out.nops;
+    gm.failed = out.failed;
+    if (t.max_n_frac >= 0.f &&
+        !n_fraction_ok(text, n, rev, out.text_start, out.text_end < n ? out.text_end : n, t.max_n_frac, 0))
+      gm.failed |= 2u;
+  }
   t.out[gi] = gm;
   }
 }
@@ -122,11 +158,29 @@ __global__ void trace_kernel(const __grid_constant__ TraceArgs t) {
 }  // namespace
 
 cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags, bool all_minima,
-                          cudaStream_t stream) {
+                          const EndFilter* filter, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   const unsigned threads = 256;
   const uint64_t blocks = (n + threads - 1) / threads;
-  minima_kernel<<<(unsigned)blocks, threads, 0, stream>>>(keys, cost, n, flags, all_minima);
+  if (filter) {
+    minima_kernel<true><<<(unsigned)blocks, threads, 0, stream>>>(keys, cost, n, flags, all_minima, *filter);
+  } else {
+    EndFilter none;
+    memset(&none, 0, sizeof none);
+    minima_kernel<false><<<(unsigned)blocks, threads, 0, stream>>>(keys, cost, n, flags, all_minima, none);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_best(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags,
+                        unsigned long long* best, uint32_t nslots, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(best, 0xFF, (size_t)nslots * sizeof(unsigned long long), stream);
+  if (e != cudaSuccess) return e;
+  const unsigned threads = 256;
+  const uint64_t blocks = (n + threads - 1) / threads;
+  best_reduce_kernel<<<(unsigned)blocks, threads, 0, stream>>>(keys, cost, n, flags, best);
+  best_flag_kernel<<<(unsigned)blocks, threads, 0, stream>>>(keys, cost, n, flags, best);
   return cudaGetLastError();
 }
 

@@ -563,6 +563,96 @@ SB_HD bool select_candidate(const uint64_t* keys, const uint32_t* cost, uint64_t
 }
 
 // ---------------------------------------------------------------------------
+// End-position predicates evaluated together with the selection, in the reference's order
+// (src/search.rs:895-919): the caller's end filter, then the N end-point filter.  The
+// reference takes an arbitrary closure (search_with_fn, :767-784); a device kernel cannot,
+// so the one closure the reference itself ships is built in: "the last pam_len characters
+// before the end position match the PAM exactly" (bin/crispr.rs:136-143,198-205), with the
+// profile's is_match and, for reversed queries, the complemented PAM on the reversed text.
+// Several texts (search_texts / search_many): query slot = text index * nq_per_text + query.
+struct TextRef {
+  const uint8_t* base;      // one text, or the concatenation of all texts
+  uint64_t n;               // length of the single text
+  const uint64_t* offs;     // nullptr for a single text, else start of every text in `base`
+  const uint64_t* lens;
+  uint32_t nq_per_text;
+};
+
+SB_HD void text_of_slot(const TextRef& t, uint32_t qs, const uint8_t*& text, uint64_t& n, uint32_t& q) {
+  if (t.offs) {
+    const uint32_t ti = qs / t.nq_per_text;
+    q = qs - ti * t.nq_per_text;
+    text = t.base + t.offs[ti];
+    n = t.lens[ti];
+  } else {
+    q = qs;
+    text = t.base;
+    n = t.n;
+  }
+}
+
+constexpr int kMaxPam = 16;
+struct EndFilter {
+  TextRef text;
+  const uint8_t* rev_flags;  // per query (not per slot)
+  int32_t profile;
+  int32_t m, k;
+  int32_t pam_len;           // 0: no end filter
+  uint8_t pam[2][kMaxPam];   // [0] forward queries, [1] reversed queries (complemented, not reversed)
+  int32_t n_endpoint;        // 1: N end-point filter (v1 only, src/n_filter.rs:41-53)
+  float max_n_frac;
+};
+
+SB_HD bool profile_is_match(int profile, uint8_t a, uint8_t b) {
+  switch (profile) {
+    case kDna: return trace_match<kDna>(a, b);
+    case kIupac: return trace_match<kIupac>(a, b);
+    default: return trace_match<kAscii>(a, b);
+  }
+}
+
+// count(N or n in td[start, end)) / denom <= max_n_frac, in f32 like src/n_filter.rs:8-34.
+SB_HD bool n_fraction_ok(const uint8_t* text, uint64_t n, bool rev, uint64_t start, uint64_t end, float max_n_frac,
+                         uint64_t denom /*0 = slice length*/) {
+  if (start >= n) return true;
+  if (end <= start) return true;
+  uint64_t cnt = 0;
+  for (uint64_t i = start; i < end; i++) {
+    const uint8_t c = rev ? text[n - 1 - i] : text[i];
+    cnt += (c | 0x20) == 'n';
+  }
+  const float frac = (float)cnt / (float)(denom ? denom : end - start);
+  return frac <= max_n_frac;
+}
+
+SB_HD bool end_filter_pass(const EndFilter& f, uint64_t key) {
+  const uint8_t* text;
+  uint64_t n;
+  uint32_t q;
+  text_of_slot(f.text, key_qs(key), text, n, q);
+  const bool rev = f.rev_flags[q] != 0;
+  const uint64_t end = key_pos(key);
+  if (f.pam_len > 0) {
+    // the reference's closure indexes text[len - pam_len..] and panics when the prefix is
+    // shorter than the PAM; such an end position cannot hold the PAM: rejected
+    if (end < (uint64_t)f.pam_len) return false;
+    const uint8_t* pam = f.pam[rev ? 1 : 0];
+    for (int i = 0; i < f.pam_len; i++) {
+      const uint64_t idx = end - (uint64_t)f.pam_len + (uint64_t)i;
+      const uint8_t c = rev ? text[n - 1 - idx] : text[idx];
+      if (!profile_is_match(f.profile, c, pam[i])) return false;
+    }
+  }
+  if (f.n_endpoint) {
+    const uint64_t e = end < n ? end : n;
+    const uint64_t mand = f.m > f.k ? (uint64_t)(f.m - f.k) : 0;
+    const uint64_t s = e > mand ? e - mand : 0;
+    if (!n_fraction_ok(text, n, rev, s, e, f.max_n_frac, (uint64_t)(f.m + f.k))) return false;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------
 // Traceback of one match.  Window = the (m+k) text characters before the end
 // position, recomputed with the same recurrences while storing every column's
 // vertical deltas (reference src/search.rs:1477-1478, src/trace.rs:57-104;
@@ -583,7 +673,7 @@ struct GpuMatch {
   uint32_t qs;
   int32_t cost;
   uint32_t nops;
-  uint32_t failed;
+  uint32_t failed;  // bit 0: traceback failed; bit 1: dropped by the traced N-fraction filter
 };
 
 enum : uint32_t { kOpEq = 0, kOpX = 1, kOpI = 2, kOpD = 3 };

@@ -284,29 +284,19 @@ __global__ void __launch_bounds__(128)
     verify_one<W>(a, rev_flags, i);
 }
 
+// Exact recurrences over scan-direction positions [w0, end) of one text, emitting every end
+// position > emit_from with score <= k under query slot `qs`.  `text` must be 16-byte aligned
+// and padded to a multiple of 16 bytes.
 template <int W>
-__device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __restrict__ rev_flags,
-                                           unsigned long long i) {
-  const uint64_t key = a.hit_keys[i];
-  const uint32_t qs = key_qs(key);
-  const bool rev = rev_flags[qs] != 0;
-  const uint32_t* __restrict__ eq = a.eq + (size_t)qs * a.nrows * W;
-
-  const int64_t n = (int64_t)a.n;
-  const int64_t base = (int64_t)(key_pos(key) * kHitChars);
-  const int64_t g0 = rev ? n - kHitChars - base : base;
-  const int64_t span = (int64_t)a.m + (int64_t)a.k;
-  int64_t w0 = g0 - span;
-  if (w0 < 0) w0 = 0;
-  int64_t end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
-  if (end > n) end = n;
-  const int64_t emit_from = g0 < 0 ? 0 : g0;
+__device__ __forceinline__ void scan_window(const ScanArgs& a, const uint32_t* __restrict__ eq, uint32_t qs, bool rev,
+                                            const uint8_t* __restrict__ text, int64_t n, int64_t w0, int64_t end,
+                                            int64_t emit_from) {
   if (end <= w0) return;
   // forward byte range [lo, hi) of the window and its aligned 16-byte chunks
   const int64_t lo = rev ? n - end : w0, hi = rev ? n - w0 : end;
   const int64_t c_lo = lo >> 4, c_hi = (hi + 15) >> 4;  // chunk indices [c_lo, c_hi)
-  const uint4* __restrict__ chunks = reinterpret_cast<const uint4*>(a.text);
-  for (int64_t c = c_lo; c < c_hi; c += 2)  // one prefetch per 32-byte sector
+  const uint4* __restrict__ chunks = reinterpret_cast<const uint4*>(text);
+  for (int64_t c = c_lo; c < c_hi && c < c_lo + 16; c += 2)  // one prefetch per 32-byte sector
     asm volatile("prefetch.global.L2 [%0];" ::"l"(chunks + c));
 
   Lane<W> s;
@@ -346,6 +336,46 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
     }
     cur = nxt;
     c = cn;
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __restrict__ rev_flags,
+                                           unsigned long long i) {
+  const uint64_t key = a.hit_keys[i];
+  const uint32_t qs = key_qs(key);
+  const bool rev = rev_flags[qs] != 0;
+  const uint32_t* __restrict__ eq = a.eq + (size_t)qs * a.nrows * W;
+
+  const int64_t n = (int64_t)a.n;
+  const int64_t base = (int64_t)(key_pos(key) * kHitChars);
+  const int64_t g0 = rev ? n - kHitChars - base : base;
+  const int64_t span = (int64_t)a.m + (int64_t)a.k;
+  int64_t w0 = g0 - span;
+  if (w0 < 0) w0 = 0;
+  int64_t end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
+  if (end > n) end = n;
+  const int64_t emit_from = g0 < 0 ? 0 : g0;
+  scan_window<W>(a, eq, qs, rev, a.text, n, w0, end, emit_from);
+}
+
+// search_texts / search_many: many short texts, one thread per (text, query) pair runs the
+// exact recurrences over its whole text (the v1 boundary conditions hold per text: fresh state
+// at the text start).  Slot = text index * nq + query index.
+template <int W>
+__global__ void __launch_bounds__(128)
+    texts_kernel(const __grid_constant__ ScanArgs a, const __grid_constant__ TextsArgs t) {
+  const unsigned long long total = (unsigned long long)t.ntexts * t.nq;
+  const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long slot = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; slot < total;
+       slot += nthreads) {
+    const uint32_t ti = (uint32_t)(slot / t.nq);
+    const uint32_t q = (uint32_t)(slot - (unsigned long long)ti * t.nq);
+    const int64_t n = (int64_t)t.lens[ti];
+    if (n == 0) continue;
+    if (t.include_pos0 && a.m <= a.k) emit_candidate(a, (uint32_t)slot, 0, a.m);
+    scan_window<W>(a, a.eq + (size_t)q * a.nrows * W, (uint32_t)slot, t.rev_flags[q] != 0, t.base + t.offs[ti], n, 0,
+                   n, 0);
   }
 }
 
@@ -497,6 +527,20 @@ cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cu
 #define SB_VCALL(WW) case WW: verify_kernel<WW><<<blocks, threads, 0, stream>>>(a, rev_flags); break;
     SB_VCALL(1) SB_VCALL(2) SB_VCALL(3) SB_VCALL(4) SB_VCALL(6) SB_VCALL(8) SB_VCALL(16) SB_VCALL(32)
 #undef SB_VCALL
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_texts(int W, const ScanArgs& a, const TextsArgs& t, cudaStream_t stream) {
+  const unsigned long long total = (unsigned long long)t.ntexts * t.nq;
+  if (total == 0) return cudaSuccess;
+  const unsigned threads = 128;
+  const unsigned blocks = (unsigned)std::min<unsigned long long>((total + threads - 1) / threads, 148ull * 16);
+  switch (W) {
+#define SB_TCALL(WW) case WW: texts_kernel<WW><<<blocks, threads, 0, stream>>>(a, t); break;
+    SB_TCALL(1) SB_TCALL(2) SB_TCALL(3) SB_TCALL(4) SB_TCALL(6) SB_TCALL(8) SB_TCALL(16) SB_TCALL(32)
+#undef SB_TCALL
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

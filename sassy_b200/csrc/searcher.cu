@@ -56,39 +56,64 @@ static void unpack_ops(const MatchSet& ms, size_t i, std::string& out) {
   for (uint32_t a = 0; a < g.nops; a++) out[a] = kOpChars[(w[a >> 4] >> ((a & 15) * 2)) & 3u];
 }
 
-// v1 strands (reference src/search.rs:787-881): slot 0 = pattern on the text,
-// slot 1 = complement(pattern) on the reversed text; reversed-text coordinates
-// are mapped back (:859-877), the CIGAR is kept as produced (:874-876).
-std::vector<Match> Searcher::convert_v1(const MatchSet& ms, uint64_t n) const {
+SearchOpts Searcher::v1_opts(bool all_minima) const {
+  SearchOpts o;
+  o.all_minima = all_minima;
+  o.include_pos0 = true;
+  o.without_trace = without_trace_;
+  o.only_best = only_best_;
+  o.max_n_frac = max_n_frac_;
+  o.n_endpoint = true;  // v1 filters end points before the traceback as well (src/search.rs:907-919)
+  return o;
+}
+
+// v1 strands (reference src/search.rs:787-881): queries [0, n_pat) = the patterns on the text,
+// queries [n_pat, 2 n_pat) = complement(pattern) on the reversed text; reversed-text
+// coordinates are mapped back (:859-877), the CIGAR is kept as produced (:874-876).  Without
+// trace only the end position is known (:1464-1475): text_start / pattern_start are
+// usize::MAX, and for the reverse strand the known end becomes text_start (:866-872).
+// Slot = text index * n_queries + query.
+template <class LenFn>
+std::vector<Match> Searcher::convert_v1(const MatchSet& ms, size_t n_pat, size_t m, LenFn text_len) const {
+  const size_t nq = rc_ ? 2 * n_pat : n_pat;
   std::vector<Match> out(ms.m.size());
   for (size_t i = 0; i < ms.m.size(); i++) {
     const GpuMatch& g = ms.m[i];
-    if (g.failed) throw std::runtime_error("Trace failed (text contains bytes outside the profile's alphabet?)");
+    if (g.failed & 1u) throw std::runtime_error("Trace failed (text contains bytes outside the profile's alphabet?)");
     Match& mm = out[i];
-    mm.pattern_idx = 0;
-    mm.text_idx = 0;
+    const size_t ti = g.qs / nq, q = g.qs % nq;
+    const uint64_t n = text_len(ti);
+    mm.pattern_idx = q % n_pat;
+    mm.text_idx = ti;
     mm.cost = g.cost;
-    mm.pattern_start = 0;
-    if (g.qs == 0) {
+    mm.pattern_start = without_trace_ ? ~0ull : 0;
+    mm.pattern_end = m;
+    if (q < n_pat) {
       mm.strand = kFwd;
       mm.text_start = g.text_start;
       mm.text_end = g.text_end;
     } else {
       mm.strand = kRc;
       mm.text_start = n - g.text_end;
-      mm.text_end = n - g.text_start;
+      mm.text_end = without_trace_ ? ~0ull : n - g.text_start;
     }
-    unpack_ops(ms, i, mm.ops);
+    if (!without_trace_) unpack_ops(ms, i, mm.ops);
   }
   return out;
 }
 
 std::vector<Match> Searcher::search(const uint8_t* pattern, size_t m, const DeviceText& text, size_t k,
                                     bool all_minima) {
+  return search_with_pam(pattern, m, text, k, all_minima, nullptr, 0);
+}
+
+std::vector<Match> Searcher::search_with_pam(const uint8_t* pattern, size_t m, const DeviceText& text, size_t k,
+                                             bool all_minima, const uint8_t* pam, size_t pam_len) {
   if (m == 0) throw std::invalid_argument("empty pattern");
   validate_pattern(pattern, m);
   if (rc_ && profile_ == kAscii)
     throw std::invalid_argument("reverse complement is not implemented for the Ascii profile");
+  if (pam_len > (size_t)kMaxPam) throw std::invalid_argument("PAM longer than 16 characters");
   std::vector<uint8_t> comp;
   std::vector<Query> qs;
   qs.push_back(Query{pattern, false});
@@ -98,18 +123,126 @@ std::vector<Match> Searcher::search(const uint8_t* pattern, size_t m, const Devi
     qs.push_back(Query{comp.data(), true});
   }
   const int kk = (int)std::min<size_t>(k, 1u << 20);
-  engine_->search(text, qs, (int)m, kk, all_minima, /*include_pos0=*/true, ms_);
-  std::vector<Match> out = convert_v1(ms_, text.n);
-  for (auto& mm : out) mm.pattern_end = m;
-  return out;
+  SearchOpts o = v1_opts(all_minima);
+  o.pam = pam;
+  o.pam_len = (int)pam_len;
+  engine_->search(text, qs, (int)m, kk, o, ms_);
+  const uint64_t n = text.n;
+  return convert_v1(ms_, 1, m, [n](size_t) { return n; });
 }
 
 std::vector<Match> Searcher::search(const uint8_t* pattern, size_t m, const uint8_t* text, size_t n, size_t k,
                                     bool all_minima) {
+  return search_with_pam(pattern, m, text, n, k, all_minima, nullptr, 0);
+}
+
+std::vector<Match> Searcher::search_with_pam(const uint8_t* pattern, size_t m, const uint8_t* text, size_t n,
+                                             size_t k, bool all_minima, const uint8_t* pam, size_t pam_len) {
   if (m == 0) throw std::invalid_argument("empty pattern");
   validate_pattern(pattern, m);
   DeviceText* t = engine_->stage_text(text, n);
-  return search(pattern, m, *t, k, all_minima);
+  return search_with_pam(pattern, m, *t, k, all_minima, pam, pam_len);
+}
+
+// Equal-length patterns x texts with v1 semantics per (pattern, text) pair.  Short texts go
+// through the one-thread-per-pair kernel in a single launch; a long text is staged and
+// scanned by the row-tiled kernels with all patterns as queries.
+std::vector<Match> Searcher::search_group(const uint8_t* const* patterns, size_t n_pat, size_t m,
+                                          const uint8_t* const* texts, const uint64_t* text_lens, size_t n_texts,
+                                          size_t k) {
+  if (m == 0) throw std::invalid_argument("empty pattern");
+  if (rc_ && profile_ == kAscii)
+    throw std::invalid_argument("reverse complement is not implemented for the Ascii profile");
+  std::vector<uint8_t> comp(rc_ ? n_pat * m : 0);
+  std::vector<Query> qs;
+  for (size_t p = 0; p < n_pat; p++) {
+    validate_pattern(patterns[p], m);
+    qs.push_back(Query{patterns[p], false});
+  }
+  if (rc_)
+    for (size_t p = 0; p < n_pat; p++) {
+      for (size_t i = 0; i < m; i++) comp[p * m + i] = complement_byte(profile_, patterns[p][i]);
+      qs.push_back(Query{&comp[p * m], true});
+    }
+  const int kk = (int)std::min<size_t>(k, 1u << 20);
+  const SearchOpts o = v1_opts(false);
+  std::vector<Match> out;
+  constexpr uint64_t kShortText = 1ull << 17;  // longer texts are worth a row-tiled scan of their own
+  std::vector<const uint8_t*> sp;
+  std::vector<uint64_t> sl;
+  std::vector<size_t> sidx;
+  for (size_t t = 0; t < n_texts; t++) {
+    if (text_lens[t] <= kShortText) {
+      sp.push_back(texts[t]), sl.push_back(text_lens[t]), sidx.push_back(t);
+      continue;
+    }
+    DeviceText* dt = engine_->stage_text(texts[t], text_lens[t]);
+    engine_->search(*dt, qs, (int)m, kk, o, ms_);
+    const uint64_t n = text_lens[t];
+    std::vector<Match> part = convert_v1(ms_, n_pat, m, [n](size_t) { return n; });
+    for (auto& mm : part) mm.text_idx = t;
+    out.insert(out.end(), std::make_move_iterator(part.begin()), std::make_move_iterator(part.end()));
+  }
+  // pairs per launch are bounded by the 24-bit slot field of the candidate keys
+  const size_t max_texts = std::max<size_t>(1, ((1u << 23) - 1) / qs.size());
+  for (size_t first = 0; first < sp.size(); first += max_texts) {
+    const size_t cnt = std::min(max_texts, sp.size() - first);
+    engine_->search_texts(sp.data() + first, sl.data() + first, cnt, qs, (int)m, kk, o, ms_);
+    std::vector<Match> part = convert_v1(ms_, n_pat, m, [&](size_t ti) { return sl[first + ti]; });
+    for (auto& mm : part) mm.text_idx = sidx[first + mm.text_idx];
+    out.insert(out.end(), std::make_move_iterator(part.begin()), std::make_move_iterator(part.end()));
+  }
+  return out;
+}
+
+static void sort_single_mode(std::vector<Match>& v) {
+  // SearchMode::Single order (src/search.rs:541-553,1519-1549): pattern-major, then text, forward
+  // matches before reverse-complement ones; positions keep their scan order (stable)
+  std::stable_sort(v.begin(), v.end(), [](const Match& a, const Match& b) {
+    if (a.pattern_idx != b.pattern_idx) return a.pattern_idx < b.pattern_idx;
+    if (a.text_idx != b.text_idx) return a.text_idx < b.text_idx;
+    return a.strand < b.strand;
+  });
+}
+
+std::vector<Match> Searcher::search_patterns(const uint8_t* const* patterns, size_t n_patterns, size_t m,
+                                             const uint8_t* text, size_t n, size_t k) {
+  if (n_patterns == 0) return {};
+  const uint64_t len = n;
+  std::vector<Match> out = search_group(patterns, n_patterns, m, &text, &len, 1, k);
+  sort_single_mode(out);
+  return out;
+}
+
+std::vector<Match> Searcher::search_texts(const uint8_t* pattern, size_t m, const uint8_t* const* texts,
+                                          const uint64_t* text_lens, size_t n_texts, size_t k) {
+  if (n_texts == 0) return {};
+  std::vector<Match> out = search_group(&pattern, 1, m, texts, text_lens, n_texts, k);
+  sort_single_mode(out);
+  return out;
+}
+
+std::vector<Match> Searcher::search_many(const uint8_t* const* patterns, const uint64_t* pattern_lens,
+                                         size_t n_patterns, const uint8_t* const* texts, const uint64_t* text_lens,
+                                         size_t n_texts, size_t k) {
+  std::vector<Match> out;
+  if (n_patterns == 0 || n_texts == 0) return out;
+  // group the patterns by length: one launch set per group
+  std::vector<size_t> order(n_patterns);
+  for (size_t i = 0; i < n_patterns; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pattern_lens[a] < pattern_lens[b]; });
+  for (size_t g0 = 0; g0 < n_patterns;) {
+    size_t g1 = g0;
+    while (g1 < n_patterns && pattern_lens[order[g1]] == pattern_lens[order[g0]]) g1++;
+    std::vector<const uint8_t*> grp;
+    for (size_t i = g0; i < g1; i++) grp.push_back(patterns[order[i]]);
+    std::vector<Match> part = search_group(grp.data(), grp.size(), pattern_lens[order[g0]], texts, text_lens, n_texts, k);
+    for (auto& mm : part) mm.pattern_idx = order[g0 + mm.pattern_idx];
+    out.insert(out.end(), std::make_move_iterator(part.begin()), std::make_move_iterator(part.end()));
+    g0 = g1;
+  }
+  sort_single_mode(out);
+  return out;
 }
 
 // Reference: TQueries::new (src/pattern_tiling/tqueries.rs:53-134): equal
@@ -144,11 +277,16 @@ std::vector<Match> Searcher::search_encoded(const EncodedPatterns& enc, const De
   std::vector<Query> qs(enc.n_queries());
   for (size_t q = 0; q < qs.size(); q++) qs[q] = Query{&enc.bytes[q * enc.m], false};
   const int kk = (int)std::min<size_t>(k, 1u << 20);
-  engine_->search(text, qs, enc.m, kk, all_minima, /*include_pos0=*/false, ms_);
+  // the v2 engine knows all_minima and max_n_frac only (traced filter, general.rs:399-402);
+  // without_trace / only_best_match do not reach it (src/search.rs:415-433)
+  SearchOpts o;
+  o.all_minima = all_minima;
+  o.max_n_frac = max_n_frac_;
+  engine_->search(text, qs, enc.m, kk, o, ms_);
   std::vector<Match> out(ms_.m.size());
   for (size_t i = 0; i < ms_.m.size(); i++) {
     const GpuMatch& g = ms_.m[i];
-    if (g.failed) throw std::runtime_error("Trace failed (text contains bytes outside the profile's alphabet?)");
+    if (g.failed & 1u) throw std::runtime_error("Trace failed (text contains bytes outside the profile's alphabet?)");
     Match& mm = out[i];
     mm.pattern_idx = g.qs % enc.n_patterns;
     mm.strand = g.qs >= enc.n_patterns ? kRc : kFwd;
@@ -400,6 +538,72 @@ sassy_gpu_Result* sassy_gpu_search_text(sassy_SearcherType* searcher, const uint
   return guarded([&]() -> sassy_gpu_Result* {
     if (!searcher || !pattern || !text) throw std::invalid_argument("null pointer");
     return to_result(searcher->s.search(pattern, pattern_len, *text->t, k, all != 0));
+  });
+}
+
+int sassy_gpu_set_trace(sassy_SearcherType* searcher, int trace) {
+  if (!searcher) return 1;
+  searcher->s.set_trace(trace != 0);
+  return 0;
+}
+
+int sassy_gpu_set_only_best_match(sassy_SearcherType* searcher, int on) {
+  if (!searcher) return 1;
+  searcher->s.set_only_best_match(on != 0);
+  return 0;
+}
+
+int sassy_gpu_set_max_n_frac(sassy_SearcherType* searcher, float max_n_frac) {
+  if (!searcher || !(max_n_frac >= 0.f)) return 1;
+  searcher->s.set_max_n_frac(max_n_frac);
+  return 0;
+}
+
+sassy_gpu_Result* sassy_gpu_search_pam(sassy_SearcherType* searcher, const uint8_t* pattern, size_t pattern_len,
+                                       const uint8_t* text, size_t text_len, size_t k, int all, const uint8_t* pam,
+                                       size_t pam_len) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !pattern || (!text && text_len) || (!pam && pam_len)) throw std::invalid_argument("null pointer");
+    return to_result(searcher->s.search_with_pam(pattern, pattern_len, text, text_len, k, all != 0, pam, pam_len));
+  });
+}
+
+sassy_gpu_Result* sassy_gpu_search_pam_text(sassy_SearcherType* searcher, const uint8_t* pattern, size_t pattern_len,
+                                            const sassy_gpu_Text* text, size_t k, int all, const uint8_t* pam,
+                                            size_t pam_len) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !pattern || !text || (!pam && pam_len)) throw std::invalid_argument("null pointer");
+    return to_result(searcher->s.search_with_pam(pattern, pattern_len, *text->t, k, all != 0, pam, pam_len));
+  });
+}
+
+sassy_gpu_Result* sassy_gpu_search_patterns(sassy_SearcherType* searcher, const uint8_t* const* patterns,
+                                            size_t n_patterns, size_t pattern_len, const uint8_t* text,
+                                            size_t text_len, size_t k) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || (!patterns && n_patterns) || (!text && text_len)) throw std::invalid_argument("null pointer");
+    return to_result(searcher->s.search_patterns(patterns, n_patterns, pattern_len, text, text_len, k));
+  });
+}
+
+sassy_gpu_Result* sassy_gpu_search_texts(sassy_SearcherType* searcher, const uint8_t* pattern, size_t pattern_len,
+                                         const uint8_t* const* texts, const size_t* text_lens, size_t n_texts,
+                                         size_t k) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !pattern || ((!texts || !text_lens) && n_texts)) throw std::invalid_argument("null pointer");
+    return to_result(searcher->s.search_texts(pattern, pattern_len, texts,
+                                              reinterpret_cast<const uint64_t*>(text_lens), n_texts, k));
+  });
+}
+
+sassy_gpu_Result* sassy_gpu_search_many(sassy_SearcherType* searcher, const uint8_t* const* patterns,
+                                        const size_t* pattern_lens, size_t n_patterns, const uint8_t* const* texts,
+                                        const size_t* text_lens, size_t n_texts, size_t k) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || ((!patterns || !pattern_lens) && n_patterns) || ((!texts || !text_lens) && n_texts))
+      throw std::invalid_argument("null pointer");
+    return to_result(searcher->s.search_many(patterns, reinterpret_cast<const uint64_t*>(pattern_lens), n_patterns,
+                                             texts, reinterpret_cast<const uint64_t*>(text_lens), n_texts, k));
   });
 }
 

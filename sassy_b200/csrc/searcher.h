@@ -65,12 +65,47 @@ class Searcher {
   std::vector<Match> search_encoded(const EncodedPatterns& enc, const uint8_t* text, size_t n, size_t k,
                                     bool all_minima);
 
+  // ---- Searcher options (reference src/search.rs:441-483) ------------------------------------
+  void set_trace(bool trace) { without_trace_ = !trace; }          // with_trace / without_trace / set_trace
+  void set_only_best_match(bool on) { only_best_ = on; }          // only_best_match
+  void set_max_n_frac(float f) { max_n_frac_ = (f == 1.0f) ? -1.f : f; }  // set_max_n_frac; 1.0 disables
+  bool without_trace() const { return without_trace_; }
+
+  // search_with_fn (src/search.rs:767-784) with the end filter the reference ships
+  // (bin/crispr.rs:198-205): keep an end position only if the pam_len text characters before
+  // it match `pam` exactly (profile is_match; complemented PAM on the reverse strand).
+  std::vector<Match> search_with_pam(const uint8_t* pattern, size_t m, const DeviceText& text, size_t k,
+                                     bool all_minima, const uint8_t* pam, size_t pam_len);
+  std::vector<Match> search_with_pam(const uint8_t* pattern, size_t m, const uint8_t* text, size_t n, size_t k,
+                                     bool all_minima, const uint8_t* pam, size_t pam_len);
+
+  // search_patterns (src/search.rs:648-683): equal-length patterns against one text (v1
+  // semantics per pattern, pattern_idx set).
+  std::vector<Match> search_patterns(const uint8_t* const* patterns, size_t n_patterns, size_t m,
+                                     const uint8_t* text, size_t n, size_t k);
+  // search_texts (src/search.rs:615-640): one pattern against many texts (text_idx set).
+  std::vector<Match> search_texts(const uint8_t* pattern, size_t m, const uint8_t* const* texts,
+                                  const uint64_t* text_lens, size_t n_texts, size_t k);
+  // search_many (src/search.rs:531-603): every pattern against every text; the three modes of
+  // the reference return the same set, ordered here like SearchMode::Single (pattern-major).
+  std::vector<Match> search_many(const uint8_t* const* patterns, const uint64_t* pattern_lens, size_t n_patterns,
+                                 const uint8_t* const* texts, const uint64_t* text_lens, size_t n_texts, size_t k);
+
   void validate_pattern(const uint8_t* p, size_t m) const;
 
  private:
-  std::vector<Match> convert_v1(const MatchSet& ms, uint64_t n) const;
+  SearchOpts v1_opts(bool all_minima) const;
+  // Converts slot-indexed device records of a v1 search over `n_pat` patterns (queries =
+  // patterns, then their complements when rc) to Matches; text_len(text_idx) gives the text length.
+  template <class LenFn>
+  std::vector<Match> convert_v1(const MatchSet& ms, size_t n_pat, size_t m, LenFn text_len) const;
+  std::vector<Match> search_group(const uint8_t* const* patterns, size_t n_pat, size_t m,
+                                  const uint8_t* const* texts, const uint64_t* text_lens, size_t n_texts, size_t k);
   int profile_;
   bool rc_;
+  bool without_trace_ = false;
+  bool only_best_ = false;
+  float max_n_frac_ = -1.f;
   std::unique_ptr<Engine> engine_;
   MatchSet ms_;
 };

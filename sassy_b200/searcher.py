@@ -183,7 +183,7 @@ class Searcher:
     """`Searcher(alphabet, rc=True, alpha=None, max_n_frac=None)` as in src/python.rs:31-65.
 
     `device` selects the CUDA device (default: env SASSY_B200_DEVICE or 0).  Overhang
-    (`alpha`) and `max_n_frac` filtering are outside the GPU path and raise."""
+    (`alpha`) is outside the GPU path and raises."""
 
     def __init__(self, alphabet: str, rc: bool = True, alpha: Optional[float] = None,
                  max_n_frac: Optional[float] = None, device: Optional[int] = None):
@@ -197,8 +197,6 @@ class Searcher:
             rc = False  # src/python.rs:40-42
         if alpha is not None:
             raise NotImplementedError("overhang (alpha) is outside the GPU search path")
-        if max_n_frac is not None and max_n_frac < 1.0:
-            raise NotImplementedError("max_n_frac filtering is outside the GPU search path")
         if device is None:
             device = int(os.environ.get("SASSY_B200_DEVICE", "0"))
         self.alphabet = a
@@ -208,6 +206,39 @@ class Searcher:
         if not h:
             raise RuntimeError(_native.last_error())
         self._h = h
+        if max_n_frac is not None:
+            self.set_max_n_frac(max_n_frac)
+
+    # -- Searcher options (reference src/search.rs:441-483) ----------------
+    def set_max_n_frac(self, max_n_frac: float):
+        """Searcher::set_max_n_frac: drop matches whose text holds more than this fraction of N
+        (1.0 disables the filter)."""
+        if self._lib.sassy_gpu_set_max_n_frac(self._h, float(max_n_frac)) != 0:
+            raise ValueError(max_n_frac)
+        return self
+
+    def with_max_n_frac(self, max_n_frac: float):
+        return self.set_max_n_frac(max_n_frac)
+
+    def without_max_n_frac(self):
+        return self.set_max_n_frac(1.0)
+
+    def set_trace(self, trace: bool):
+        """Searcher::set_trace / with_trace / without_trace: without trace a match carries the end
+        position and cost only (the unknown fields hold USIZE_MAX, like the reference)."""
+        self._lib.sassy_gpu_set_trace(self._h, int(bool(trace)))
+        return self
+
+    def without_trace(self):
+        return self.set_trace(False)
+
+    def with_trace(self):
+        return self.set_trace(True)
+
+    def only_best_match(self, on: bool = True):
+        """Searcher::only_best_match: the rightmost match of minimal cost per (pattern, text, strand)."""
+        self._lib.sassy_gpu_set_only_best_match(self._h, int(bool(on)))
+        return self
 
     def close(self):
         if self._h:
@@ -292,26 +323,56 @@ class Searcher:
         """Searcher::search_all (src/search.rs:685-700; src/python.rs:139-152)."""
         return self._search(pattern, text, k, True)
 
-    def search_many(self, patterns: Sequence, texts: Sequence, k: int, threads: int = 1,
+    def search_with_pam(self, pattern, text, k: int, pam, all_minima: bool = True) -> List[Match]:
+        """Searcher::search_with_fn (src/search.rs:767-784) with the end filter of the reference's
+        CRISPR mode (bin/crispr.rs:198-221): an end position is kept only if the len(pam) text
+        characters before it match `pam` exactly (complemented PAM on the reverse strand)."""
+        paddr, plen, pkeep = _as_buffer(pattern)
+        maddr, mlen, mkeep = _as_buffer(pam)
+        if isinstance(text, DeviceText):
+            res = self._lib.sassy_gpu_search_pam_text(self._h, paddr, plen, text._h, k, int(all_minima), maddr, mlen)
+        else:
+            taddr, tlen, tkeep = _as_buffer(text)
+            res = self._lib.sassy_gpu_search_pam(self._h, paddr, plen, taddr, tlen, k, int(all_minima), maddr, mlen)
+        return self._collect(res)
+
+    @staticmethod
+    def _ptr_array(items):
+        """(void* array, size_t array, keepalives) for a sequence of bytes-like objects."""
+        bufs = [_as_buffer(x) for x in items]
+        ptrs = (ctypes.c_void_p * max(1, len(bufs)))(*[b[0] for b in bufs])
+        lens = (ctypes.c_size_t * max(1, len(bufs)))(*[b[1] for b in bufs])
+        return ptrs, lens, bufs
+
+    def search_patterns(self, patterns: Sequence, text, k: int) -> List[Match]:
+        """Searcher::search_patterns (src/search.rs:648-683): equal-length patterns, one text."""
+        if not patterns:
+            return MatchList(np.zeros(0, dtype=_REC_DTYPE), b"")
+        m = len(patterns[0])
+        if any(len(p) != m for p in patterns):
+            raise ValueError("All patterns passed to search_patterns must have the same length")
+        ptrs, lens, keep = self._ptr_array(patterns)
+        taddr, tlen, tkeep = _as_buffer(text)
+        return self._collect(self._lib.sassy_gpu_search_patterns(self._h, ptrs, len(patterns), m, taddr, tlen, k))
+
+    def search_texts(self, pattern, texts: Sequence, k: int) -> List[Match]:
+        """Searcher::search_texts (src/search.rs:615-640): one pattern, many (short) texts."""
+        paddr, plen, pkeep = _as_buffer(pattern)
+        ptrs, lens, keep = self._ptr_array(texts)
+        return self._collect(self._lib.sassy_gpu_search_texts(self._h, paddr, plen, ptrs, lens, len(texts), k))
+
+    def search_many(self, patterns: Sequence, texts: Sequence, k: int, threads: int = 0,
                     mode: str = "single") -> List[Match]:
-        """Searcher::search_many (src/search.rs:531-603): every pattern against every text,
-        pattern_idx/text_idx filled in.  `threads` is accepted for signature compatibility; the
-        GPU processes one (pattern batch, text) at a time."""
+        """Searcher::search_many (src/search.rs:531-603; src/python.rs:83-116): every pattern
+        against every text, pattern_idx / text_idx filled in.  The reference's three modes return
+        the same set of matches; here short texts are searched by one kernel launch per pattern
+        length (one thread per (text, pattern, strand)) and long texts by the row-tiled scan.
+        `threads` is accepted for signature compatibility."""
         if mode not in ("single", "batch_patterns", "batch_texts"):
             raise ValueError("Unsupported search mode. Must be one of 'single', 'batch_patterns', or 'batch_texts'")
-        out: List[Match] = []
-        for ti, text in enumerate(texts):
-            dt = text if isinstance(text, DeviceText) else self.upload_text(text)
-            try:
-                for pi, pattern in enumerate(patterns):
-                    for m in self._search(pattern, dt, k, False):
-                        m.pattern_idx = pi
-                        m.text_idx = ti
-                        out.append(m)
-            finally:
-                if dt is not text:
-                    dt.free()
-        return out
+        pp, pl, pk = self._ptr_array(patterns)
+        tp, tl, tk = self._ptr_array(texts)
+        return self._collect(self._lib.sassy_gpu_search_many(self._h, pp, pl, len(patterns), tp, tl, len(texts), k))
 
     def encode_patterns(self, patterns: Sequence[bytes]) -> EncodedPatterns:
         """Searcher::encode_patterns (src/search.rs:404-413): equal-length patterns."""

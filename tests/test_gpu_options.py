@@ -1,0 +1,175 @@
+"""CUDA path under the Searcher options and the multi-text / multi-pattern entry points,
+against the oracle.  Needs a B200."""
+import random
+
+import pytest
+
+import oracle
+from tests.test_oracle_props import planted, rand_seq
+
+pytestmark = pytest.mark.gpu
+
+
+def key(m):
+    return (m.pattern_idx, m.text_idx, m.text_start, m.text_end, m.pattern_start, m.pattern_end, m.cost, m.strand,
+            m.cigar)
+
+
+def mk(alphabet, rc, filt="auto", **opts):
+    import sassy_b200
+    s = sassy_b200.Searcher(alphabet, rc=rc, max_n_frac=opts.get("max_n_frac"))
+    s.set_filter(filt)
+    if opts.get("without_trace"):
+        s.without_trace()
+    if opts.get("only_best"):
+        s.only_best_match()
+    return s
+
+
+def noisy(rng, t, alphabet):
+    """Sprinkle N runs (and IUPAC codes) into a text."""
+    t = bytearray(t)
+    for _ in range(rng.randrange(0, 4)):
+        if len(t) < 2:
+            break
+        a = rng.randrange(len(t))
+        for i in range(a, min(len(t), a + rng.randrange(1, 30))):
+            t[i] = ord("N")
+    return bytes(t)
+
+
+def test_reference_kats_for_options():
+    s = mk("iupac", False, max_n_frac=0.5)
+    p = b"ACGTACGTACGT"
+    t = b"NNNNNNNNNNNNNAAAAAAAAAAAAAAAAAANNNNNNNGTACGT"
+    assert [m.text_end for m in s.search_all(p, t, 1)] == [44]            # src/n_filter.rs:84-106
+    s.without_max_n_frac()
+    assert [m.text_end for m in s.search_all(p, t, 1)] == [11, 12, 13, 14, 43, 44]
+    d = mk("dna", True)
+    p = b"ATCGATCA"
+    t = bytearray(b"G" * 100)
+    t[10:10] = p
+    t[50:50] = oracle.reverse_complement("dna", p)
+    ms = d.search_with_pam(p, bytes(t), 0, p, all_minima=False)             # src/search.rs:2583-2607
+    assert [(m.text_start, m.strand) for m in ms] == [(10, "+"), (50, "-")]
+
+
+@pytest.mark.parametrize("filt", ["off", "force"])
+@pytest.mark.parametrize("alphabet", ["dna", "iupac"])
+def test_gpu_options_fuzz(alphabet, filt):
+    rng = random.Random(31)
+    searchers = {}
+    for it in range(150):
+        m = rng.choice([4, 8, 20, 23, 33, 70])
+        n = rng.randrange(0, 6000)
+        k = rng.randrange(0, max(1, m // 4) + 1)
+        p, t = planted(rng, m, max(n, 1), k)
+        t = t[:n]
+        if alphabet == "iupac":
+            t = noisy(rng, t, alphabet)
+        opts = dict(without_trace=rng.random() < 0.3, only_best=rng.random() < 0.3,
+                    max_n_frac=rng.choice([None, None, 0.0, 0.1, 0.5]) if alphabet == "iupac" else None)
+        pam = p[-3:] if rng.random() < 0.4 else None
+        allm = rng.random() < 0.5
+        okey = (opts["without_trace"], opts["only_best"], opts["max_n_frac"])
+        if okey not in searchers:
+            searchers[okey] = mk(alphabet, True, filt, **opts)
+        s = searchers[okey]
+        want = oracle.search(alphabet, p, t, k, rc=True, all_minima=allm, pam=pam, **opts)
+        if pam is not None:
+            got = s.search_with_pam(p, t, k, pam, all_minima=allm)
+        else:
+            got = s.search_all(p, t, k) if allm else s.search(p, t, k)
+        assert list(map(key, got)) == list(map(key, want)), (alphabet, p, t, k, allm, opts, pam)
+
+
+def test_gpu_encoded_max_n_frac():
+    rng = random.Random(32)
+    s = mk("iupac", True, max_n_frac=0.2)
+    for it in range(30):
+        m = rng.choice([8, 23, 32])
+        n = rng.randrange(1, 5000)
+        k = rng.randrange(0, m // 4 + 1)
+        pats = []
+        t = bytearray(rand_seq(rng, n))
+        for _ in range(rng.randrange(1, 12)):
+            p, tt = planted(rng, m, n, k)
+            pats.append(p)
+            a = rng.randrange(0, max(1, n - m))
+            t[a:a + m] = p[:max(0, min(m, n - a))]
+        t = noisy(rng, bytes(t[:n]), "iupac")
+        enc = s.encode_patterns(pats)
+        for allm in (False, True):
+            want = oracle.search_encoded("iupac", pats, t, k, rc=True, all_minima=allm, max_n_frac=0.2)
+            got = s.search_all_encoded_patterns(enc, t, k) if allm else s.search_encoded_patterns(enc, t, k)
+            kk = lambda x: (x.pattern_idx, x.text_start, x.text_end, x.cost, x.strand, x.cigar)
+            assert sorted(map(kk, got)) == sorted(map(kk, want))
+
+
+@pytest.mark.parametrize("alphabet", ["dna", "iupac"])
+def test_gpu_search_many_fuzz(alphabet):
+    """Mirrors the reference's search_many_fuzz (src/search.rs:3624-3730): random pattern and
+    text sets, all three modes, against pattern-by-text single searches (the oracle)."""
+    rng = random.Random(33)
+    s = mk(alphabet, True)
+    fwd = mk(alphabet, False)
+    for it in range(40):
+        np_, nt = rng.randrange(1, 30), rng.randrange(1, 40)
+        m = rng.randrange(1, 100)
+        pats = [rand_seq(rng, m) for _ in range(np_)]
+        texts = [rand_seq(rng, rng.randrange(2, 1000)) for _ in range(nt)]
+        for i in range(0, nt, 3):  # make sure there is something to find
+            p = pats[rng.randrange(np_)]
+            a = rng.randrange(0, max(1, len(texts[i])))
+            texts[i] = (texts[i][:a] + p + texts[i][a:])[:1000]
+        if it % 7 == 0:
+            texts.append(b"")
+        k = rng.randrange(0, m * 4 // 10 + 1)
+        rc = rng.random() < 0.5
+        srch = s if rc else fwd
+        want = oracle.search_many(alphabet, pats, texts, k, rc=rc)
+        for mode in ("single", "batch_patterns", "batch_texts"):
+            got = srch.search_many(pats, texts, k, 0, mode)
+            assert list(map(key, got)) == list(map(key, want)), (it, mode, m, k, rc)
+
+
+def test_gpu_search_many_mixed_lengths_and_long_text():
+    rng = random.Random(34)
+    s = mk("dna", True)
+    pats = [rand_seq(rng, m) for m in (12, 30, 12, 20, 30)]
+    long_text = bytearray(rand_seq(rng, 400_000))
+    for i, p in enumerate(pats):
+        long_text[50_000 * (i + 1):50_000 * (i + 1) + len(p)] = p
+    texts = [rand_seq(rng, 300), bytes(long_text), pats[1] + rand_seq(rng, 50) + pats[3]]
+    want = oracle.search_many("dna", pats, texts, 2, rc=True)
+    got = s.search_many(pats, texts, 2)
+    assert list(map(key, got)) == list(map(key, want))
+    assert len(got) >= 7
+
+
+def test_gpu_search_texts_and_patterns():
+    rng = random.Random(35)
+    s = mk("dna", True)
+    for opts in ({}, {"only_best": True}, {"without_trace": True}):
+        so = mk("dna", True, **opts)
+        p = rand_seq(rng, 24)
+        texts = []
+        for i in range(200):
+            t = bytearray(rand_seq(rng, rng.randrange(0, 400)))
+            if i % 2 and len(t) > 30:
+                a = rng.randrange(0, len(t) - 24)
+                q = bytearray(p)
+                q[rng.randrange(24)] = ord("A")
+                t[a:a + 24] = q
+            texts.append(bytes(t))
+        want = oracle.search_many("dna", [p], texts, 3, rc=True, **opts)
+        got = so.search_texts(p, texts, 3)
+        assert list(map(key, got)) == list(map(key, want)), opts
+        assert len(got) >= 50
+        pats = [rand_seq(rng, 16) for _ in range(37)]
+        t = bytearray(rand_seq(rng, 30_000))
+        for i, q in enumerate(pats):
+            t[700 * i + 5:700 * i + 21] = q
+        want = oracle.search_many("dna", pats, [bytes(t)], 2, rc=True, **opts)
+        got = so.search_patterns(pats, bytes(t), 2)
+        assert list(map(key, got)) == list(map(key, want)), opts
