@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--rc", action="store_true", help="search both strands (default: forward only, as the reference's evals)")
     ap.add_argument("--transport", default="packed", choices=["packed", "bytes"],
                     help="host->device transport of Dna texts in the e2e leg (2 bits per character, or bytes)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: fused peer-memory exchange of the match records (default) or NCCL all-gather")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
@@ -301,13 +303,20 @@ def main():
     del text_dev
     torch.cuda.empty_cache()
 
+    # N > 1: the match records of all ranks reach every rank through the fused peer-memory
+    # exchange behind the traceback (csrc/peer_gather.cu); --gather nccl uses the host-staged
+    # NCCL all-gather instead (A/B)
+    pg = sdist.PeerGather(s, max_ops=m + k + 1) if (world > 1 and args.gather == "peer") else None
+
     def step_resident():
+        if pg is not None:
+            return pg.search_encoded(enc, dt, k) if enc is not None else pg.search(pats[0], dt, k)
         if enc is not None:
             ms = s.search_encoded_patterns(enc, dt, k)
         else:
             ms = s.search(pats[0], dt, k)
         if world > 1:
-            ms = sdist.gather_matches(ms, max_ops=m + k + 1, device=dev)
+            ms = sdist.gather_matches(sdist.tag_rank(ms, rank), max_ops=m + k + 1, device=dev)
         return ms
 
     def step_e2e():
@@ -317,7 +326,7 @@ def main():
         else:
             ms = s.search(pats[0], buf, k)
         if world > 1:
-            ms = sdist.gather_matches(ms, max_ops=m + k + 1, device=dev)
+            ms = sdist.gather_matches(sdist.tag_rank(ms, rank), max_ops=m + k + 1, device=dev)
         return ms
 
     def barrier():
@@ -432,7 +441,9 @@ def main():
                    "row_bytes": st["row_bytes"], "rows": st["rows"], "blocks_per_sm": st["blocks_per_sm"],
                    "prefilter": {"mode": args.filter, "words": st["filter_words"], "piece_len": st["filter_len"],
                                  "fallback": st["filter_fallback"]},
-                   "sharding": "text shards, one per rank; NCCL all-gather of match records per step" if world > 1 else "single GPU"},
+                   "sharding": ("text shards, one per rank; match records of all ranks exchanged per step by "
+                                + ("peer-memory stores over NVLink fused behind the traceback (%d NCCL fall-backs)" % pg.fallbacks
+                                   if pg is not None else "a host-staged NCCL all-gather")) if world > 1 else "single GPU"},
         "matches": len(matches), "matches_per_s": len(matches) * args.steps / el,
         "gchar_pattern_per_s": total_bytes * len(pats) * args.steps / el / 1e9,
         "device_ms_per_step": sum(total_ms) / len(total_ms),

@@ -38,6 +38,7 @@
 typedef struct sassy_gpu_Text sassy_gpu_Text;         /* a text resident in HBM */
 typedef struct sassy_gpu_Patterns sassy_gpu_Patterns; /* EncodedPatterns */
 typedef struct sassy_gpu_Result sassy_gpu_Result;     /* Vec<Match> incl. CIGAR ops */
+typedef struct sassy_gpu_Gather sassy_gpu_Gather;     /* multi-GPU match gather over peer memory */
 
 /* One match; same fields as the reference's Match (src/search.rs:35-62).
  * The CIGAR ops of match i are the ops_len bytes at sassy_gpu_result_ops() + ops_off,
@@ -162,6 +163,31 @@ sassy_gpu_Result *sassy_gpu_search_encoded(sassy_SearcherType *searcher, const s
                                            const sassy_gpu_Text *text, size_t k, int all);
 sassy_gpu_Result *sassy_gpu_search_encoded_host(sassy_SearcherType *searcher, const sassy_gpu_Patterns *patterns,
                                                 const uint8_t *text, size_t text_len, size_t k, int all);
+
+/* ---- multi-GPU (one process per GPU of one box) -------------------------------------------
+ * The reference fans (pattern, text) tasks out over threads and concatenates the match lists
+ * (src/search.rs:531-603,1519-1549).  Here every rank searches its shard and the records of all
+ * ranks reach every rank through ONE fused exchange: the traceback leaves the records in the
+ * rank's slot of a receive buffer, a kernel stores them into the same slot of every peer's
+ * buffer over NVLink (CUDA IPC mapped peer memory) and releases a step flag, a second kernel
+ * acquires all flags and moves the records to pinned host memory.  No collective library call.
+ *   1. sassy_gpu_gather_create on every rank (cap_records per rank and search, max_ops = m + k + 1
+ *      of the longest search), 2. exchange the 64-byte handles (any transport), 3. connect,
+ *   4. sassy_gpu_search_*_gathered in lock step on all ranks.
+ * *complete = 1: the result holds the matches of all ranks in rank order with text_idx = source
+ * rank.  *complete = 0: some rank's result did not fit the exchange; the result holds this rank's
+ * matches only and the caller gathers them itself (sassy_b200/dist.py uses an NCCL all-gather). */
+sassy_gpu_Gather *sassy_gpu_gather_create(sassy_SearcherType *searcher, int world, int rank, size_t cap_records,
+                                          size_t max_ops);
+int sassy_gpu_gather_handle(sassy_gpu_Gather *gather, uint8_t *out64);
+int sassy_gpu_gather_connect(sassy_gpu_Gather *gather, const uint8_t *handles /* world x 64 bytes */);
+void sassy_gpu_gather_free(sassy_gpu_Gather *gather);
+sassy_gpu_Result *sassy_gpu_search_text_gathered(sassy_SearcherType *searcher, sassy_gpu_Gather *gather,
+                                                 const uint8_t *pattern, size_t pattern_len,
+                                                 const sassy_gpu_Text *text, size_t k, int all, int *complete);
+sassy_gpu_Result *sassy_gpu_search_encoded_gathered(sassy_SearcherType *searcher, sassy_gpu_Gather *gather,
+                                                    const sassy_gpu_Patterns *patterns, const sassy_gpu_Text *text,
+                                                    size_t k, int all, int *complete);
 
 size_t sassy_gpu_result_len(const sassy_gpu_Result *result);
 const sassy_gpu_Match *sassy_gpu_result_matches(const sassy_gpu_Result *result);

@@ -114,6 +114,14 @@ SIGNATURES = {
     "sassy_gpu_patterns_free": (None, [c_void_p]),
     "sassy_gpu_search_encoded": (c_void_p, [c_void_p, c_void_p, c_void_p, c_size_t, ctypes.c_int]),
     "sassy_gpu_search_encoded_host": (c_void_p, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, ctypes.c_int]),
+    "sassy_gpu_gather_create": (c_void_p, [c_void_p, ctypes.c_int, ctypes.c_int, c_size_t, c_size_t]),
+    "sassy_gpu_gather_handle": (ctypes.c_int, [c_void_p, c_void_p]),
+    "sassy_gpu_gather_connect": (ctypes.c_int, [c_void_p, c_void_p]),
+    "sassy_gpu_gather_free": (None, [c_void_p]),
+    "sassy_gpu_search_text_gathered": (c_void_p, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
+                                                  ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "sassy_gpu_search_encoded_gathered": (c_void_p, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, ctypes.c_int,
+                                                     ctypes.POINTER(ctypes.c_int)]),
     "sassy_gpu_result_len": (c_size_t, [c_void_p]),
     "sassy_gpu_result_matches": (ctypes.POINTER(GpuMatch), [c_void_p]),
     "sassy_gpu_result_ops": (c_void_p, [c_void_p]),

@@ -465,7 +465,10 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   if (m <= 0) throw CudaError("empty pattern");
   const int W = round_words((m + 31) / 32);
   if (W < 0) throw CudaError("pattern longer than 1024 characters is not supported");
-  if (nq == 0) return;
+  if (nq == 0) {
+    if (pg_) throw CudaError("a gathered search needs at least one query on every rank");
+    return;
+  }
   if (nq >= (1u << (64 - kPosBits))) throw CudaError("too many queries in one search");
   if (k < 0) k = 0;
   uint32_t nfwd = 0;
@@ -588,8 +591,27 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   }
   GpuMatch* h_small_out = reinterpret_cast<GpuMatch*>(h_small_);
   uint32_t* h_small_ops = reinterpret_cast<uint32_t*>(h_small_ + (size_t)kSmallCandidates * sizeof(GpuMatch));
+  // Multi-GPU gather over peer memory (peer_gather.cu): the traceback leaves the records in this
+  // rank's slot of the receive buffer, push + collect follow in the same stream.  Exactly one
+  // exchange per search keeps the ranks in lock step; a search whose result is not complete in
+  // the slot (long candidate list, overflow, re-scan) marks its slot `overflow` and every rank
+  // falls back to the caller's collective.
+  PeerGather* pg = pg_;
+  gather_ok_ = false;
+  const bool pg_slot = pg && small_path && out.ops_words <= pg->max_ops_words() && pg->cap() >= (size_t)kSmallCandidates;
+  bool pg_pushed = false, small_in_slot = false;
+  auto pg_exchange = [&](bool force_overflow) {
+    if (!pg || pg_pushed) return;
+    pg_pushed = true;
+    SB_CUDA(pg->exchange(d_counts, a.cand_cap, fp.enabled ? hit_cap_ : ~0ull, out.ops_words, force_overflow, n,
+                         pg_user_, stream_));
+    stats_.aux_launches += 2;
+  };
   auto queue_small_tail = [&]() {
-    if (!small_path) return;
+    if (!small_path) {
+      pg_exchange(true);
+      return;
+    }
     SB_CUDA(launch_post_small(a.cand_keys, a.cand_cost, d_cand_count, a.cand_cap, sel_small_.as<uint64_t>(), d_nsel,
                               d_big, all_minima, end_bit, stream_));
     TraceArgs t;
@@ -611,11 +633,27 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     t.count = kSmallCandidates;
     t.count_dev = d_nsel;
     t.scratch = scratch_.as<uint32_t>();
-    t.ops = h_small_ops;   // pinned host memory, written by the kernel over PCIe
     t.ops_words = out.ops_words;
-    t.out = h_small_out;
+    small_in_slot = pg_slot && !pg_pushed;
+    if (small_in_slot) {
+      size_t ops_off = 0;
+      uint8_t* rec = pg->local_records(&ops_off);  // device memory: this rank's slot
+      t.out = reinterpret_cast<GpuMatch*>(rec);
+      t.ops = reinterpret_cast<uint32_t*>(rec + ops_off);
+    } else {
+      t.ops = h_small_ops;   // pinned host memory, written by the kernel over PCIe
+      t.out = h_small_out;
+    }
     SB_CUDA(launch_trace(t, stream_));
     stats_.aux_launches += 2;
+    pg_exchange(!small_in_slot);
+  };
+  // after the synchronisation that follows a tail: did every rank deliver a complete result?
+  auto pg_check = [&]() {
+    if (!pg || !pg_pushed || gather_ok_) return gather_ok_;
+    if (pg->timed_out()) throw CudaError("peer gather timed out: a rank did not reach this search");
+    gather_ok_ = pg->ok();
+    return gather_ok_;
   };
   bool small_done = false;
 
@@ -685,7 +723,15 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     stats_.filter_len = (uint32_t)fp.L;
     // too many hits (repetitive text, unlucky pieces): the re-scan costs more than the scan
     const double rescan = (double)nhits * (2.0 * (m + k) + kHitChars);
-    if (nhits > hit_cap_ || rescan > 0.5 * (double)n * nq) {
+    if (pg_check()) {  // every rank's result is complete and already gathered
+      stats_.ltot = gf.ltot;
+      stats_.rows = gf.rows;
+      stats_.blocks_per_sm = (uint32_t)focc;
+      ncand = h_counts[0];
+      filtered = true;
+      small_done = true;
+      stats_.scan_ms = stats_.filter_ms;
+    } else if (nhits > hit_cap_ || rescan > 0.5 * (double)n * nq) {
       stats_.filter_fallback = 1;
     } else {
       stats_.ltot = gf.ltot;
@@ -747,6 +793,11 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       read_counts();
       stats_.scan_ms += elapsed(ev_[1], ev_[2]);
       const unsigned long long cnt = h_counts[0];
+      if (pg_check()) {
+        ncand = cnt;
+        small_done = true;
+        break;
+      }
       if (cnt <= cand_cap_) {
         ncand = cnt;
         small_done = small_path && h_counts[3] == 0;
@@ -763,8 +814,15 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   uint64_t nsel = 0;
   if (small_done) {
     nsel = h_counts[1];
-    out.m.assign(h_small_out, h_small_out + nsel);
-    out.ops.assign(h_small_ops, h_small_ops + nsel * out.ops_words);
+    const GpuMatch* src_m = h_small_out;
+    const uint32_t* src_ops = h_small_ops;
+    if (small_in_slot) {  // the collect kernel mirrored this rank's slot into pinned host memory
+      const PeerGather::Slot sl = pg->slot(pg->rank());
+      src_m = sl.records;
+      src_ops = sl.ops;
+    }
+    out.m.assign(src_m, src_m + nsel);
+    out.ops.assign(src_ops, src_ops + nsel * out.ops_words);
   } else if (ncand > 0) {
     PostCtx c;
     c.text = TextRef{text.d, n, nullptr, nullptr, nq};

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "peer_gather.h"
 #include "transport.h"
 
 namespace sb {
@@ -127,6 +128,13 @@ class Engine {
   void search_texts(const uint8_t* const* texts, const uint64_t* lens, size_t ntexts,
                     const std::vector<Query>& queries, int m, int k, const SearchOpts& opts, MatchSet& out);
 
+  // Multi-GPU: while a PeerGather is attached every search() ends with one exchange of the
+  // match records over peer memory (all ranks must search in lock step).  gather_ok() tells
+  // whether the last search left every rank's complete result in pg->slot(r); if not, `out`
+  // holds the local result and the caller falls back to its own collective.
+  void set_gather(PeerGather* pg, uint64_t user) { pg_ = pg, pg_user_ = user; }
+  bool gather_ok() const { return gather_ok_; }
+
   const SearchStats& stats() const { return stats_; }
   void set_variant(int v) { variant_ = v; }
   int variant() const { return variant_; }
@@ -155,6 +163,9 @@ class Engine {
   int profile_;
   int device_;
   int variant_;
+  PeerGather* pg_ = nullptr;  // not owned
+  uint64_t pg_user_ = 0;
+  bool gather_ok_ = false;
   int filter_mode_ = 1;
   bool fuse_strands_ = true;
   int pair_max_words_ = 4;  // Dna: two characters per automaton step up to this many words

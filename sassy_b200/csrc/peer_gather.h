@@ -1,0 +1,61 @@
+// Multi-GPU gather of match records over peer memory (see peer_gather.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "scan_core.cuh"
+
+namespace sb {
+
+constexpr int kMaxPeers = 16;
+
+class PeerGather {
+ public:
+  // cap = records per rank and step that fit a slot; max_ops_words = 32-bit words of packed
+  // CIGAR ops per record ((m + k + 1 + 15) / 16 of the longest pattern searched).
+  PeerGather(int device, int world, int rank, size_t cap, size_t max_ops_words);
+  ~PeerGather();
+  PeerGather(const PeerGather&) = delete;
+  PeerGather& operator=(const PeerGather&) = delete;
+
+  int world() const { return world_; }
+  int rank() const { return rank_; }
+  size_t cap() const { return cap_; }
+  size_t max_ops_words() const { return max_ops_words_; }
+
+  void export_handle(uint8_t out[64]) const;  // CUDA IPC handle of this rank's receive buffer
+  void connect(const uint8_t* handles);       // world x 64 bytes, in rank order
+
+  // Device pointer where the traceback of the NEXT exchange has to leave this rank's records
+  // (GpuMatch[cap]); the packed ops follow at *ops_offset bytes, `ops_words` words per record.
+  uint8_t* local_records(size_t* ops_offset);
+  // Queues push + collect on `stream`.  d_counts = the engine's device counters
+  // ([0] candidates, [1] selected, [2] prefilter hits, [3] list too long for the fast tail);
+  // the push marks the slot `overflow` when the records in the slot are not this step's
+  // complete result.  After the stream is synchronised ok() / slot() describe the step.
+  cudaError_t exchange(const unsigned long long* d_counts, unsigned long long cand_cap, unsigned long long hit_cap,
+                       uint32_t ops_words, bool force_overflow, unsigned long long text_n, unsigned long long user,
+                       cudaStream_t stream);
+  bool ok() const;         // every rank delivered a complete result for the last step
+  bool timed_out() const;  // some rank did not arrive within the time-out
+  struct Slot {
+    unsigned long long count, text_n, user;
+    uint32_t ops_words;
+    const GpuMatch* records;
+    const uint32_t* ops;
+  };
+  Slot slot(int r) const;  // host view of rank r's records of the last step
+
+ private:
+  int device_, world_, rank_;
+  size_t cap_, max_ops_words_;
+  size_t slot_bytes_ = 0, flags_off_ = 0, bytes_ = 0;
+  uint8_t* local_ = nullptr;
+  uint8_t* host_ = nullptr;
+  uint8_t* peer_[kMaxPeers];
+  bool connected_ = false;
+  unsigned long long step_ = 0;
+};
+
+}  // namespace sb

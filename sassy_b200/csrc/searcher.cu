@@ -283,19 +283,79 @@ std::vector<Match> Searcher::search_encoded(const EncodedPatterns& enc, const De
   o.all_minima = all_minima;
   o.max_n_frac = max_n_frac_;
   engine_->search(text, qs, enc.m, kk, o, ms_);
-  std::vector<Match> out(ms_.m.size());
-  for (size_t i = 0; i < ms_.m.size(); i++) {
-    const GpuMatch& g = ms_.m[i];
+  return convert_v2(ms_, enc.n_patterns, enc.m);
+}
+
+std::vector<Match> Searcher::convert_v2(const MatchSet& ms, size_t n_patterns, int m) const {
+  std::vector<Match> out(ms.m.size());
+  for (size_t i = 0; i < ms.m.size(); i++) {
+    const GpuMatch& g = ms.m[i];
     if (g.failed & 1u) throw std::runtime_error("Trace failed (text contains bytes outside the profile's alphabet?)");
     Match& mm = out[i];
-    mm.pattern_idx = g.qs % enc.n_patterns;
-    mm.strand = g.qs >= enc.n_patterns ? kRc : kFwd;
+    mm.pattern_idx = g.qs % n_patterns;
+    mm.strand = g.qs >= n_patterns ? kRc : kFwd;
     mm.text_start = g.text_start;
     mm.text_end = g.text_end;
     mm.pattern_start = 0;
-    mm.pattern_end = (uint64_t)enc.m;
+    mm.pattern_end = (uint64_t)m;
     mm.cost = g.cost;
-    unpack_ops(ms_, i, mm.ops);
+    unpack_ops(ms, i, mm.ops);
+  }
+  return out;
+}
+
+// Copies rank r's records of the last exchange into a MatchSet.
+static MatchSet slot_set(const PeerGather& pg, int r) {
+  const PeerGather::Slot sl = pg.slot(r);
+  MatchSet ms;
+  ms.ops_words = sl.ops_words;
+  ms.m.assign(sl.records, sl.records + sl.count);
+  ms.ops.assign(sl.ops, sl.ops + sl.count * sl.ops_words);
+  return ms;
+}
+
+std::vector<Match> Searcher::search_gathered(PeerGather& pg, const uint8_t* pattern, size_t m,
+                                             const DeviceText& text, size_t k, bool all_minima, bool* complete) {
+  engine_->set_gather(&pg, 1);
+  std::vector<Match> local;
+  try {
+    local = search_with_pam(pattern, m, text, k, all_minima, nullptr, 0);
+  } catch (...) {
+    engine_->set_gather(nullptr, 0);
+    throw;
+  }
+  engine_->set_gather(nullptr, 0);
+  *complete = engine_->gather_ok();
+  if (!*complete) return local;
+  std::vector<Match> out;
+  for (int r = 0; r < pg.world(); r++) {
+    const uint64_t n = pg.slot(r).text_n;
+    std::vector<Match> part = convert_v1(slot_set(pg, r), 1, m, [n](size_t) { return n; });
+    for (auto& mm : part) mm.text_idx = (uint64_t)r;
+    out.insert(out.end(), std::make_move_iterator(part.begin()), std::make_move_iterator(part.end()));
+  }
+  return out;
+}
+
+std::vector<Match> Searcher::search_encoded_gathered(PeerGather& pg, const EncodedPatterns& enc,
+                                                     const DeviceText& text, size_t k, bool all_minima,
+                                                     bool* complete) {
+  engine_->set_gather(&pg, enc.n_patterns);
+  std::vector<Match> local;
+  try {
+    local = search_encoded(enc, text, k, all_minima);
+  } catch (...) {
+    engine_->set_gather(nullptr, 0);
+    throw;
+  }
+  engine_->set_gather(nullptr, 0);
+  *complete = engine_->gather_ok();
+  if (!*complete) return local;
+  std::vector<Match> out;
+  for (int r = 0; r < pg.world(); r++) {
+    std::vector<Match> part = convert_v2(slot_set(pg, r), (size_t)pg.slot(r).user, enc.m);
+    for (auto& mm : part) mm.text_idx = (uint64_t)r;
+    out.insert(out.end(), std::make_move_iterator(part.begin()), std::make_move_iterator(part.end()));
   }
   return out;
 }
@@ -325,6 +385,10 @@ struct sassy_gpu_Patterns {
 struct sassy_gpu_Result {
   std::vector<sassy_gpu_Match> m;
   std::string ops;
+};
+struct sassy_gpu_Gather {
+  sb::PeerGather g;
+  sassy_gpu_Gather(int dev, int world, int rank, size_t cap, size_t ops_words) : g(dev, world, rank, cap, ops_words) {}
 };
 
 namespace {
@@ -632,6 +696,57 @@ sassy_gpu_Result* sassy_gpu_search_encoded_host(sassy_SearcherType* searcher, co
   return guarded([&]() -> sassy_gpu_Result* {
     if (!searcher || !patterns || (!text && text_len)) throw std::invalid_argument("null pointer");
     return to_result(searcher->s.search_encoded(patterns->e, text, text_len, k, all != 0));
+  });
+}
+
+sassy_gpu_Gather* sassy_gpu_gather_create(sassy_SearcherType* searcher, int world, int rank, size_t cap_records,
+                                          size_t max_ops) {
+  return guarded([&]() -> sassy_gpu_Gather* {
+    if (!searcher) throw std::invalid_argument("null pointer");
+    if (cap_records < (size_t)sb::kSmallCandidates) cap_records = sb::kSmallCandidates;
+    return new sassy_gpu_Gather(searcher->s.engine().device(), world, rank, cap_records, (max_ops + 15) / 16);
+  });
+}
+
+int sassy_gpu_gather_handle(sassy_gpu_Gather* gather, uint8_t* out64) {
+  return guarded([&]() -> int {
+           if (!gather || !out64) throw std::invalid_argument("null pointer");
+           gather->g.export_handle(out64);
+           return 1;
+         }) == 1 ? 0 : 1;
+}
+
+int sassy_gpu_gather_connect(sassy_gpu_Gather* gather, const uint8_t* handles) {
+  return guarded([&]() -> int {
+           if (!gather || !handles) throw std::invalid_argument("null pointer");
+           gather->g.connect(handles);
+           return 1;
+         }) == 1 ? 0 : 1;
+}
+
+void sassy_gpu_gather_free(sassy_gpu_Gather* gather) { delete gather; }
+
+sassy_gpu_Result* sassy_gpu_search_text_gathered(sassy_SearcherType* searcher, sassy_gpu_Gather* gather,
+                                                 const uint8_t* pattern, size_t pattern_len,
+                                                 const sassy_gpu_Text* text, size_t k, int all, int* complete) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !gather || !pattern || !text || !complete) throw std::invalid_argument("null pointer");
+    bool ok = false;
+    auto v = searcher->s.search_gathered(gather->g, pattern, pattern_len, *text->t, k, all != 0, &ok);
+    *complete = ok ? 1 : 0;
+    return to_result(v);
+  });
+}
+
+sassy_gpu_Result* sassy_gpu_search_encoded_gathered(sassy_SearcherType* searcher, sassy_gpu_Gather* gather,
+                                                    const sassy_gpu_Patterns* patterns, const sassy_gpu_Text* text,
+                                                    size_t k, int all, int* complete) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !gather || !patterns || !text || !complete) throw std::invalid_argument("null pointer");
+    bool ok = false;
+    auto v = searcher->s.search_encoded_gathered(gather->g, patterns->e, *text->t, k, all != 0, &ok);
+    *complete = ok ? 1 : 0;
+    return to_result(v);
   });
 }
 

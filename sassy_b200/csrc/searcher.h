@@ -91,9 +91,21 @@ class Searcher {
   std::vector<Match> search_many(const uint8_t* const* patterns, const uint64_t* pattern_lens, size_t n_patterns,
                                  const uint8_t* const* texts, const uint64_t* text_lens, size_t n_texts, size_t k);
 
+  // ---- multi-GPU: search + gather of all ranks' matches over peer memory --------------------
+  // Every rank of `pg` must make the same sequence of gathered calls.  *complete = true: the
+  // returned matches are those of ALL ranks in rank order, text_idx = source rank (pattern_idx
+  // local to the source rank's pattern set).  *complete = false (some rank's result did not fit
+  // the fused exchange): only this rank's matches are returned and the caller runs its own
+  // collective (sassy_b200/dist.py: NCCL all-gather).
+  std::vector<Match> search_gathered(PeerGather& pg, const uint8_t* pattern, size_t m, const DeviceText& text,
+                                     size_t k, bool all_minima, bool* complete);
+  std::vector<Match> search_encoded_gathered(PeerGather& pg, const EncodedPatterns& enc, const DeviceText& text,
+                                             size_t k, bool all_minima, bool* complete);
+
   void validate_pattern(const uint8_t* p, size_t m) const;
 
  private:
+  std::vector<Match> convert_v2(const MatchSet& ms, size_t n_patterns, int m) const;
   SearchOpts v1_opts(bool all_minima) const;
   // Converts slot-indexed device records of a v1 search over `n_pat` patterns (queries =
   // patterns, then their complements when rc) to Matches; text_len(text_idx) gives the text length.

@@ -99,6 +99,14 @@ class _GatherBuffers:
 _GATHER = {}
 
 
+def tag_rank(matches, rank: int):
+    """Copy of a MatchList with text_idx = rank (what the fused PeerGather reports as source)."""
+    from .searcher import MatchList
+    recs = matches.records.copy()
+    recs["text_idx"] = rank
+    return MatchList(recs, matches._ops)
+
+
 def gather_matches(matches, max_ops: int, device=None, group=None):
     """All ranks receive the concatenation (rank order) of every rank's matches (a MatchList).
 
@@ -150,3 +158,83 @@ def gather_matches(matches, max_ops: int, device=None, group=None):
         out_recs.append(rr)
         out_ops.append(gb.recv_np[r, 16 + gb.rec_bytes:16 + gb.rec_bytes + nops].tobytes())
     return MatchList(np.concatenate(out_recs) if out_recs else np.zeros(0, dtype=_REC_DTYPE), b"".join(out_ops))
+
+
+class PeerGather:
+    """Search + gather of every rank's matches through ONE fused exchange over peer memory
+    (csrc/peer_gather.cu): the traceback kernel leaves the records in this rank's slot of a
+    receive buffer, a kernel stores them into every peer's buffer over NVLink and releases a
+    step flag, a second kernel acquires all flags and moves the records to pinned host memory.
+    torch.distributed is used once, to exchange the 64-byte CUDA IPC handles, and for the
+    fall-back all-gather when some rank's result does not fit the exchange.
+
+    All ranks must call search()/search_encoded() in lock step.  Results: all ranks' matches in
+    rank order, text_idx = source rank, pattern_idx local to the source rank's pattern set."""
+
+    def __init__(self, searcher, max_ops: int, cap: int = 2048, group=None):
+        import ctypes
+        from . import _native
+        self._lib = _native.load()
+        self._searcher = searcher
+        self._group = group
+        self.max_ops = max_ops
+        if dist.is_initialized():
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        else:
+            self.world, self.rank = 1, 0
+        self.fallbacks = 0
+        self._h = self._lib.sassy_gpu_gather_create(searcher._h, self.world, self.rank, cap, max_ops)
+        if not self._h:
+            raise RuntimeError(_native.last_error())
+        if self.world > 1:
+            buf = (ctypes.c_uint8 * 64)()
+            if self._lib.sassy_gpu_gather_handle(self._h, buf) != 0:
+                raise RuntimeError(_native.last_error())
+            dev = torch.device("cuda", searcher.device) if dist.get_backend(group) == "nccl" else "cpu"
+            mine = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+            allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            blob = bytes(allh.cpu().numpy().tobytes())
+            if self._lib.sassy_gpu_gather_connect(self._h, blob) != 0:
+                raise RuntimeError(_native.last_error())
+            dist.barrier(group=group)
+
+    def close(self):
+        if self._h:
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self._group)  # no peer may still be writing into our buffer
+            self._lib.sassy_gpu_gather_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.sassy_gpu_gather_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _finish(self, res, complete: int):
+        from .searcher import MatchList
+        ms = self._searcher._collect(res)
+        if complete or self.world == 1:
+            return ms
+        # some rank's result did not fit the fused exchange: plain all-gather of the local lists
+        self.fallbacks += 1
+        return gather_matches(tag_rank(ms, self.rank), self.max_ops, group=self._group)
+
+    def search(self, pattern: bytes, text, k: int, all_minima: bool = False):
+        import ctypes
+        from .searcher import _as_buffer
+        paddr, plen, keep = _as_buffer(pattern)
+        ok = ctypes.c_int(0)
+        res = self._lib.sassy_gpu_search_text_gathered(self._searcher._h, self._h, paddr, plen, text._h, k,
+                                                       int(all_minima), ctypes.byref(ok))
+        return self._finish(res, ok.value)
+
+    def search_encoded(self, enc, text, k: int, all_minima: bool = False):
+        import ctypes
+        ok = ctypes.c_int(0)
+        res = self._lib.sassy_gpu_search_encoded_gathered(self._searcher._h, self._h, enc._h, text._h, k,
+                                                          int(all_minima), ctypes.byref(ok))
+        return self._finish(res, ok.value)
