@@ -1,21 +1,15 @@
-import sys, ctypes, faulthandler
-faulthandler.enable()
-import sassy_b200
-n = int(sys.argv[1])
-use_torch = len(sys.argv) > 2 and sys.argv[2] == "torch"
-s = sassy_b200.Searcher("dna", rc=False)
-if use_torch:
-    import torch
-    host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-    host.fill_(65)
-    addr = host.data_ptr()
-else:
-    addr = sassy_b200.host_alloc(n)
-    ctypes.memset(addr, 65, n)
-print("alloc ok", hex(addr), flush=True)
-dt = s.upload_text((addr, n))
-print("upload ok", flush=True)
-print(len(s.search(b"ACGTACGTACGTACGTACGT", dt, 2)), s.stats(), flush=True)
-print(len(s.search(b"ACGTACGTACGTACGTACGT", (addr, n), 2)), s.stats(), flush=True)
-print(len(s.search(b"ACGTACGTACGTACGTACGT", (addr, n), 2)), flush=True)
-print("done", flush=True)
+"""Scratch: A/B of library variants (SASSY_B200_LIB) on the C2 bench; prints kernel times."""
+import json, os, subprocess, sys
+variants = sys.argv[1].split(",")
+extra = sys.argv[2:] 
+for v in variants:
+    env = dict(os.environ)
+    if v != "default":
+        env["SASSY_B200_LIB"] = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sassy_b200", "lib", f"libsassy_b200_{v}.so")
+    out = subprocess.run([sys.executable, "bench.py", "--no-cpu", "--no-e2e", "--steps", "60"] + extra, env=env, capture_output=True, text=True)
+    try:
+        j = json.loads(out.stdout.strip().splitlines()[-1])
+        r = j["roofline"]
+        print(v, extra, "ms/step %.4f" % j["ms_per_step"], "kernel_ms %.4f" % r["kernel_ms"], "verify %.4f" % r["verify_kernel_ms"], "frac %.3f" % r["frac"], "bps", j["config"]["blocks_per_sm"], "rows", j["config"]["rows"], flush=True)
+    except Exception as e:
+        print(v, "FAILED", out.stderr[-500:], flush=True)

@@ -668,7 +668,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       if (want > hit_cap_) hit_cap_ = want;
     }
     hits_.ensure(hit_cap_ * sizeof(uint64_t));
-    const int focc = filter_blocks_per_sm(WT, variant_);
+    const int focc = filter_blocks_per_sm(WT, variant_, pair);
     ScanGeom gf = choose_geom(n, m, k, nq, focc * sm_count_);
     gf.nwarm = 1;  // a piece plus its delay line is at most 32 characters
     CUtensorMap ftmap;

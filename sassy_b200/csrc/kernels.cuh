@@ -27,8 +27,7 @@ cudaError_t launch_scan(int W, bool rev, int variant, const CUtensorMap* tmap, c
 
 // Exact piece prefilter (scan_core.cuh): hits -> a.hit_keys; then one thread per hit re-scans
 // the hit's neighbourhood with the full recurrences -> a.cand_*.
-size_t filter_smem_bytes(int WF, int variant);
-int filter_blocks_per_sm(int WF, int variant);
+int filter_blocks_per_sm(int WF, int variant, bool pair);
 cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtensorMap* tmap, const ScanArgs& a,
                           cudaStream_t stream);
 // nhits is read from a.hit_count on the device (clipped to a.hit_cap): no host round trip.
@@ -77,6 +76,7 @@ struct TraceArgs {
   uint64_t first;        // slice [first, first+count) handled by this launch
   uint64_t count;
   const unsigned long long* count_dev;  // optional device-side total that clips the slice
+  uint32_t smem_cols;      // set by launch_trace: the column store fits the block's shared memory
   uint32_t* scratch;       // trace_threads(count) * (m+k+1) * W * 2 words, interleaved by thread
   uint32_t* ops;           // [total][ops_words]
   uint32_t ops_words;

@@ -47,20 +47,61 @@ __global__ void best_flag_kernel(const uint64_t* __restrict__ keys, const uint32
 constexpr int kSmallThreads = 256;
 constexpr int kSmallItems = kSmallCandidates / kSmallThreads;
 
+// ITEMS keys per thread: the list is sorted with ITEMS = 1 when it has at most kSmallThreads
+// entries (the usual case: a handful of planted or chance matches) and with kSmallItems else.
+template <int ITEMS>
+__device__ __forceinline__ void post_small_body(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cost,
+                                                unsigned long long n, uint64_t* __restrict__ sel_keys,
+                                                unsigned long long* __restrict__ nsel, bool all_minima, int end_bit,
+                                                uint64_t* s_keys, uint32_t* s_cost, void* sort_tmp, void* scan_tmp) {
+  using Sort = cub::BlockRadixSort<uint64_t, kSmallThreads, ITEMS, uint32_t>;
+  using Scan = cub::BlockScan<uint32_t, kSmallThreads>;
+  const uint64_t pad_key = 1ull << end_bit;  // above every real key: padding sorts to the end
+  uint64_t k[ITEMS];
+  uint32_t v[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    const uint32_t idx = threadIdx.x * ITEMS + i;
+    k[i] = idx < n ? keys[idx] : pad_key;
+    v[i] = idx < n ? cost[idx] : 0u;
+  }
+  Sort(*reinterpret_cast<typename Sort::TempStorage*>(sort_tmp)).Sort(k, v, 0, end_bit + 1);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    const uint32_t idx = threadIdx.x * ITEMS + i;
+    s_keys[idx] = k[i];
+    s_cost[idx] = v[i];
+  }
+  __syncthreads();
+  uint32_t flag[ITEMS], pos[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    const uint32_t idx = threadIdx.x * ITEMS + i;
+    flag[i] = idx < n && select_candidate(s_keys, s_cost, idx, n, all_minima) ? 1u : 0u;
+  }
+  uint32_t total;
+  Scan(*reinterpret_cast<typename Scan::TempStorage*>(scan_tmp)).ExclusiveSum(flag, pos, total);
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    if (flag[i]) sel_keys[pos[i]] = k[i];
+  if (threadIdx.x == 0) *nsel = total;
+}
+
 __global__ void __launch_bounds__(kSmallThreads)
     post_small_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cost,
                       const unsigned long long* __restrict__ cand_count, uint64_t cand_cap,
                       uint64_t* __restrict__ sel_keys, unsigned long long* __restrict__ nsel,
                       unsigned long long* __restrict__ big, bool all_minima, int end_bit) {
-  using Sort = cub::BlockRadixSort<uint64_t, kSmallThreads, kSmallItems, uint32_t>;
+  using SortBig = cub::BlockRadixSort<uint64_t, kSmallThreads, kSmallItems, uint32_t>;
+  using SortOne = cub::BlockRadixSort<uint64_t, kSmallThreads, 1, uint32_t>;
   using Scan = cub::BlockScan<uint32_t, kSmallThreads>;
   __shared__ union {
-    typename Sort::TempStorage sort;
-    struct {
-      uint64_t keys[kSmallCandidates];
-      uint32_t cost[kSmallCandidates];
-    } sorted;
-  } sm;
+    typename SortBig::TempStorage sort_big;
+    typename SortOne::TempStorage sort_one;
+  } sort_tmp;
+  __shared__ uint64_t s_keys[kSmallCandidates];
+  __shared__ uint32_t s_cost[kSmallCandidates];
   __shared__ typename Scan::TempStorage scan_tmp;
   const unsigned long long n = *cand_count;
   if (n > (unsigned long long)kSmallCandidates || n > cand_cap) {
@@ -70,39 +111,12 @@ __global__ void __launch_bounds__(kSmallThreads)
     }
     return;
   }
-  uint64_t k[kSmallItems];
-  uint32_t v[kSmallItems];
-#pragma unroll
-  for (int i = 0; i < kSmallItems; i++) {
-    const uint32_t idx = threadIdx.x * kSmallItems + i;
-    k[i] = idx < n ? keys[idx] : ~0ull;  // padding sorts to the end
-    v[i] = idx < n ? cost[idx] : 0u;
-  }
-  Sort(sm.sort).Sort(k, v, 0, 64);
-  (void)end_bit;
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < kSmallItems; i++) {
-    const uint32_t idx = threadIdx.x * kSmallItems + i;
-    sm.sorted.keys[idx] = k[i];
-    sm.sorted.cost[idx] = v[i];
-  }
-  __syncthreads();
-  uint32_t flag[kSmallItems], pos[kSmallItems];
-#pragma unroll
-  for (int i = 0; i < kSmallItems; i++) {
-    const uint32_t idx = threadIdx.x * kSmallItems + i;
-    flag[i] = idx < n && select_candidate(sm.sorted.keys, sm.sorted.cost, idx, n, all_minima) ? 1u : 0u;
-  }
-  uint32_t total;
-  Scan(scan_tmp).ExclusiveSum(flag, pos, total);
-#pragma unroll
-  for (int i = 0; i < kSmallItems; i++)
-    if (flag[i]) sel_keys[pos[i]] = k[i];
-  if (threadIdx.x == 0) {
-    *nsel = total;
-    *big = 0;
-  }
+  if (threadIdx.x == 0) *big = 0;
+  if (n <= (unsigned long long)kSmallThreads)
+    post_small_body<1>(keys, cost, n, sel_keys, nsel, all_minima, end_bit, s_keys, s_cost, &sort_tmp, &scan_tmp);
+  else
+    post_small_body<kSmallItems>(keys, cost, n, sel_keys, nsel, all_minima, end_bit, s_keys, s_cost, &sort_tmp,
+                                 &scan_tmp);
 }
 
 // Grid-stride over the slice [first, first + count) of the selected candidates; when
@@ -111,6 +125,7 @@ __global__ void __launch_bounds__(kSmallThreads)
 // not read it back before the launch.
 template <int P>
 __global__ void trace_kernel(const __grid_constant__ TraceArgs t) {
+  extern __shared__ uint32_t trace_smem[];  // column store of the block when t.smem_cols is set
   uint64_t count = t.count;
   if (t.count_dev) {
     const unsigned long long total = *t.count_dev;
@@ -137,8 +152,13 @@ __global__ void trace_kernel(const __grid_constant__ TraceArgs t) {
     gm.failed = 0;
   } else {
     ColStore cs;
-    cs.base = t.scratch + (li % nthreads);
-    cs.stride = nthreads;
+    if (t.smem_cols) {
+      cs.base = trace_smem + threadIdx.x;
+      cs.stride = blockDim.x;
+    } else {
+      cs.base = t.scratch + (li % nthreads);
+      cs.stride = nthreads;
+    }
     TraceOut out;
     trace_one<P>(text, n, rev, t.patterns + (size_t)q * t.m, t.m, t.k, t.eq + (size_t)q * t.nrows * t.W, t.W,
                  t.sh0, t.msk0, end, cs, t.ops + gi * t.ops_words, t.ops_words, out);
@@ -200,14 +220,20 @@ uint64_t trace_threads(uint64_t count) {
   return blocks * threads;
 }
 
-cudaError_t launch_trace(const TraceArgs& t, cudaStream_t stream) {
-  if (t.count == 0) return cudaSuccess;
+cudaError_t launch_trace(const TraceArgs& t0, cudaStream_t stream) {
+  if (t0.count == 0) return cudaSuccess;
+  TraceArgs t = t0;
   const unsigned threads = 128;
   const uint64_t blocks = trace_threads(t.count) / threads;
+  // the per-match column store ((m+k+1) columns x W words x 2) lives in shared memory when a
+  // block's share fits the default 48 KB: every column is read back by the greedy walk
+  const size_t smem = t.costs ? 0 : (size_t)(t.m + t.k + 1) * t.W * 2 * sizeof(uint32_t) * threads;
+  t.smem_cols = (smem > 0 && smem <= 48 * 1024) ? 1 : 0;
+  const size_t dyn = t.smem_cols ? smem : 0;
   switch (t.profile) {
-    case kDna: trace_kernel<kDna><<<(unsigned)blocks, threads, 0, stream>>>(t); break;
-    case kIupac: trace_kernel<kIupac><<<(unsigned)blocks, threads, 0, stream>>>(t); break;
-    case kAscii: trace_kernel<kAscii><<<(unsigned)blocks, threads, 0, stream>>>(t); break;
+    case kDna: trace_kernel<kDna><<<(unsigned)blocks, threads, dyn, stream>>>(t); break;
+    case kIupac: trace_kernel<kIupac><<<(unsigned)blocks, threads, dyn, stream>>>(t); break;
+    case kAscii: trace_kernel<kAscii><<<(unsigned)blocks, threads, dyn, stream>>>(t); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

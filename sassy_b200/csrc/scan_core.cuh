@@ -725,12 +725,43 @@ SB_HD void trace_one(const uint8_t* text, uint64_t n, bool rev, const uint8_t* p
     cs.at((0 * W + w) * 2) = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
     cs.at((0 * W + w) * 2 + 1) = 0;
   }
+  // previous column: in registers for W <= 4 (the store is then write-only in this loop)
+  constexpr int kRegW = 4;
+  uint32_t ppv[kRegW], pmv[kRegW];
+  for (int w = 0; w < kRegW; w++) {
+    const int lo = pad - 32 * w;
+    ppv[w] = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
+    pmv[w] = 0;
+  }
+  const bool in_regs = W <= kRegW;
   for (uint32_t i = 1; i <= wlen; i++) {
     const uint8_t tc = text_at_dir(text, n, rev, off + i - 1);
     const uint32_t row = ((uint32_t)tc >> sh0) & (msk0 & 0xFFu);
     const uint32_t* e = eq + row * W;
     uint32_t carry = 0, phc = 0, mhc = 0;
-    for (int w = 0; w < W; w++) {
+#pragma unroll
+    for (int w = 0; w < kRegW; w++) {
+      if (w >= W) break;
+      const uint32_t pv = in_regs ? ppv[w] : cs.at(((i - 1) * W + w) * 2);
+      const uint32_t mv = in_regs ? pmv[w] : cs.at(((i - 1) * W + w) * 2 + 1);
+      const uint32_t x = e[w] | mv;
+      const uint32_t t = x & pv;
+      const uint64_t sum = (uint64_t)t + pv + carry;
+      const uint32_t u = (uint32_t)sum;
+      carry = (uint32_t)(sum >> 32);
+      const uint32_t d0 = (u ^ pv) | x;
+      const uint32_t ph = mv | ~(d0 | pv);
+      const uint32_t mh = pv & d0;
+      const uint32_t ph1 = (ph << 1) | phc;
+      const uint32_t mh1 = (mh << 1) | mhc;
+      phc = ph >> 31;
+      mhc = mh >> 31;
+      ppv[w] = mh1 | ~(d0 | ph1);
+      pmv[w] = ph1 & d0;
+      cs.at((i * W + w) * 2) = ppv[w];
+      cs.at((i * W + w) * 2 + 1) = pmv[w];
+    }
+    for (int w = kRegW; w < W; w++) {
       const uint32_t pv = cs.at(((i - 1) * W + w) * 2), mv = cs.at(((i - 1) * W + w) * 2 + 1);
       const uint32_t x = e[w] | mv;
       const uint32_t t = x & pv;

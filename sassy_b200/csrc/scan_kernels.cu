@@ -14,6 +14,8 @@
 // Compute: see scan_core.cuh.  Integer/logic only; no tensor cores.
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 #ifndef SB_UNROLL
 #define SB_UNROLL 2
 #endif
@@ -34,21 +36,33 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                : "memory");
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok;
+}
+
+// Out of line: the stage was not there at the first look.
+__device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
   uint32_t spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) break;
+  while (!mbar_try_wait(addr, parity))
     if (++spins > (1u << 22)) __trap();  // a lost TMA must fail loudly, not hang the GPU
-  }
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+#ifdef SB_WAIT_INLINE
+  uint32_t spins = 0;
+  while (!mbar_try_wait(addr, parity))
+    if (++spins > (1u << 22)) __trap();
+#else
+  if (!mbar_try_wait(addr, parity)) mbar_wait_slow(addr, parity);
+#endif
 }
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int32_t x, int32_t y,
@@ -109,15 +123,28 @@ __device__ __forceinline__ void row_pipeline(const CUtensorMap& tmap, const Scan
 
   const uint32_t total = a.g.nwarm + a.g.nstage;
   uint64_t* wbar = &full_bar[warp * kScanStages];
+  const uint32_t wbar_addr = smem_u32(wbar);
+  const uint32_t ring_addr = smem_u32(ring);
 
-  auto issue = [&](uint32_t it) {
-    int64_t r;
-    uint32_t col;
-    bool own;
-    stage_coord<REV>(a.g, it, row0, r, col, own);
-    uint64_t* bar = &wbar[it % kScanStages];
+  // Stage `it` of a row: the nwarm warm-up stages are the END (forward scan) or the START
+  // (reverse scan) of the neighbouring row, so in memory the stages of one thread are
+  // contiguous: forward index of stage it = start + it * step (see stage_coord).  TMA wants
+  // 2-D coordinates: x = (it - nwarm) * 64 is the column inside the own row, a negative x
+  // lies in the previous row (forward) / the mirrored column beyond the row lies in the next.
+  auto issue = [&](uint32_t it) {  // lane 0 only
+    const int32_t x = ((int32_t)it - (int32_t)a.g.nwarm) * kStageBytes;
+    int32_t col, r = (int32_t)row0;
+    if (!REV) {
+      col = x;
+      if (x < 0) col += (int32_t)a.g.ltot, r -= 1;
+    } else {
+      col = (int32_t)a.g.ltot - kStageBytes - x;
+      if (x < 0) col -= (int32_t)a.g.ltot, r += 1;
+    }
+    const uint32_t slot = it % kScanStages;
+    uint64_t* bar = &wbar[slot];
     mbar_expect_tx(bar, kWarpStageBytes);
-    tma_load_2d(ring + (it % kScanStages) * kWarpStageBytes, &tmap, (int32_t)col, (int32_t)r, bar);
+    tma_load_2d(ring + slot * kWarpStageBytes, &tmap, col, r, bar);
   };
 
   if (VARIANT == kVariantTma) {
@@ -134,23 +161,38 @@ __device__ __forceinline__ void row_pipeline(const CUtensorMap& tmap, const Scan
     }
   }
 
-  for (uint32_t it = 0; it < total; ++it) {
-    int64_t r;
-    uint32_t col;
-    bool own;
-    stage_coord<REV>(a.g, it, row, r, col, own);
-    const uint64_t stage_idx = (uint64_t)(r * (int64_t)a.g.ltot + (int64_t)col);
+  // forward index of this thread's stage 0 and the step between stages
+  const int64_t warm_bytes = (int64_t)a.g.nwarm * kStageBytes;
+  int64_t sidx = REV ? (row + 1) * (int64_t)a.g.ltot + warm_bytes - kStageBytes : row * (int64_t)a.g.ltot - warm_bytes;
+  constexpr int64_t kStep = REV ? -(int64_t)kStageBytes : (int64_t)kStageBytes;
+  // CU_TENSOR_MAP_SWIZZLE_64B: chunk ^= (row >> 1) & 3;  SWIZZLE_128B: chunk ^= row & 7
+  const uint32_t sw = kStageBytes == 64 ? ((lane >> 1) & 3u) : (lane & 7u);
+  const uint32_t lane_buf = ring_addr + lane * kStageBytes;
+
+  for (uint32_t it = 0; it < total; ++it, sidx += kStep) {
+    const bool own = it >= a.g.nwarm;
+    const uint64_t stage_idx = (uint64_t)sidx;
     if (VARIANT == kVariantTma) {
       const uint32_t st = it % kScanStages;
-      mbar_wait(&wbar[st], (it / kScanStages) & 1u);
-      const uint8_t* buf = ring + st * kWarpStageBytes + lane * kStageBytes;
-      // CU_TENSOR_MAP_SWIZZLE_64B: chunk ^= (row >> 1) & 3;  SWIZZLE_128B: chunk ^= row & 7
-      const uint32_t sw = kStageBytes == 64 ? ((lane >> 1) & 3u) : (lane & 7u);
-      body(stage_idx, own, [&](int c) { return *reinterpret_cast<const uint4*>(buf + ((c ^ sw) << 4)); });
+      mbar_wait(wbar_addr + st * 8u, (it / kScanStages) & 1u);
+      const uint32_t buf = lane_buf + st * kWarpStageBytes;
+#ifdef SB_LDS_C
+      const uint8_t* bufp = ring + st * kWarpStageBytes + lane * kStageBytes;
+      body(stage_idx, own, [&](int c) { return *reinterpret_cast<const uint4*>(bufp + ((c ^ sw) << 4)); });
+#else
+      body(stage_idx, own, [&](int c) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(buf + (((uint32_t)c ^ sw) << 4)));
+        return v;
+      });
+#endif
       __syncwarp();  // every lane is done with this warp's ring[st]
       if (lane == 0 && it + kScanStages < total) issue(it + kScanStages);
     } else {
-      const bool valid = r >= 0 && r < (int64_t)a.g.rows;
+      // rows outside the text: (r < 0 || r >= rows) <=> the stage lies outside [0, rows * ltot)
+      const bool valid = sidx >= 0 && sidx < (int64_t)a.g.rows * (int64_t)a.g.ltot;
       const uint4* src = reinterpret_cast<const uint4*>(a.text + (valid ? stage_idx : 0));
       body(stage_idx, own, [&](int c) { return valid ? __ldg(src + c) : make_uint4(0, 0, 0, 0); });
     }
@@ -207,6 +249,19 @@ __device__ __forceinline__ void flush_hits(const ScanArgs& a, const HitQueue& hq
   __syncwarp();
 }
 
+// Stages one hit (16-byte text chunk at forward index base_idx) in the warp's queue; a full
+// queue sends it straight to the global list.
+__device__ __forceinline__ void push_hit(const ScanArgs& a, const HitQueue& hq, uint32_t qs, uint64_t base_idx) {
+  const uint64_t key = cand_key(qs, base_idx / kHitChars);
+  const uint32_t pos = atomicAdd(hq.n, 1u);
+  if (pos < kHitQueueCap) {
+    hq.q[pos] = key;
+  } else {
+    const unsigned long long i = atomicAdd(a.hit_count, 1ull);
+    if (i < a.hit_cap) a.hit_keys[i] = key;
+  }
+}
+
 // Prefilter: Shift-And automaton over k+1 exact pieces (scan_core.cuh); emits the text
 // words in which a piece occurrence ends.
 // PAIR: two characters per automaton step through a class-pair table (Dna profile).
@@ -244,22 +299,38 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
                                uint32_t any = 0;
 #pragma unroll
                                for (int c = 0; c < kChunks; c++) any |= acc[c][0] | acc[c][1];
-                               if (any) {  // rare: some piece occurrence ended in this stage
-                                 uint32_t mask0 = 0, mask1 = 0;
+                               // One vote per stage; everything below runs only in warps that saw a
+                               // piece occurrence in this stage (hits are staged per warp, see HitQueue).
+                               if (__any_sync(0xFFFFFFFFu, any != 0)) {
+#ifdef SB_HITS_CALL
+                                 if (any) {
+                                   uint32_t mask0 = 0, mask1 = 0;
 #pragma unroll
-                                 for (int c = 0; c < kChunks; c++) {
-                                   mask0 |= acc[c][0] ? (1u << c) : 0u;
-                                   mask1 |= acc[c][1] ? (1u << c) : 0u;
+                                   for (int c = 0; c < kChunks; c++) {
+                                     mask0 |= acc[c][0] ? (1u << c) : 0u;
+                                     mask1 |= acc[c][1] ? (1u << c) : 0u;
+                                   }
+                                   if (a.fused) {
+                                     if (mask0) emit_stage_hits(a, hq, qs, stage_idx, mask0, own);
+                                     if (mask1) emit_stage_hits(a, hq, qs + a.nq, stage_idx, mask1, own);
+                                   } else {
+                                     emit_stage_hits(a, hq, qs, stage_idx, mask0 | mask1, own);
+                                   }
                                  }
-                                 if (a.fused) {  // second half of the automaton = the reversed partner query
-                                   if (mask0) emit_stage_hits(a, hq, qs, stage_idx, mask0, own);
-                                   if (mask1) emit_stage_hits(a, hq, qs + a.nq, stage_idx, mask1, own);
-                                 } else {
-                                   emit_stage_hits(a, hq, qs, stage_idx, mask0 | mask1, own);
+#else
+                                 if (any && own) {
+#pragma unroll
+                                   for (int c = 0; c < kChunks; c++) {
+                                     const uint64_t base_idx = stage_idx + (uint64_t)(kHitChars * c);
+                                     if (base_idx >= a.n) continue;
+                                     if (acc[c][0] | (a.fused ? 0u : acc[c][1])) push_hit(a, hq, qs, base_idx);
+                                     if (a.fused && acc[c][1]) push_hit(a, hq, qs + a.nq, base_idx);
+                                   }
                                  }
+#endif
+                                 __syncwarp();
+                                 if (*hq.n >= kHitQueueCap / 2) flush_hits(a, hq, lane);  // warp-uniform
                                }
-                               __syncwarp();
-                               if (*hq.n >= kHitQueueCap / 2) flush_hits(a, hq, lane);  // warp-uniform
                              });
   flush_hits(a, hq, lane);
 }
@@ -455,10 +526,10 @@ cudaError_t launch_filter_one(const CUtensorMap* tmap, const ScanArgs& a, size_t
   return cudaGetLastError();
 }
 
-template <int WF, bool REV, int VARIANT>
+template <int WF, bool REV, int VARIANT, bool PAIR>
 int filter_occupancy_one(size_t smem) {
-  auto kern = filter_kernel<WF, REV, VARIANT, false>;
-  if (ensure_smem(kern, smem, filter_smem_tracker<WF, REV, VARIANT, false>()) != cudaSuccess) return 1;
+  auto kern = filter_kernel<WF, REV, VARIANT, PAIR>;
+  if (ensure_smem(kern, smem, filter_smem_tracker<WF, REV, VARIANT, PAIR>()) != cudaSuccess) return 1;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kScanThreads, smem) != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;
@@ -466,37 +537,70 @@ int filter_occupancy_one(size_t smem) {
 
 }  // namespace
 
-size_t filter_smem_bytes(int WF, int variant);
-int filter_blocks_per_sm_uncached(int WF, int variant);
+namespace {
 
-int filter_blocks_per_sm(int WF, int variant) {
-  static int cache[8][2] = {};  // occupancy queries cost tens of microseconds: ask once per shape
-  // (all devices of a box are the same part, so one answer serves every device)
-  if (WF >= 1 && WF < 8 && cache[WF][variant & 1]) return cache[WF][variant & 1];
-  const int nb = filter_blocks_per_sm_uncached(WF, variant);
-  if (WF >= 1 && WF < 8) cache[WF][variant & 1] = nb;
-  return nb;
-}
-
-int filter_blocks_per_sm_uncached(int WF, int variant) {
-  const size_t smem = filter_smem_bytes(WF, variant);
+int filter_occupancy(int WF, int variant, bool pair, size_t smem) {
+#define SB_OCC(WW)                                                                                              \
+  if (pair)                                                                                                     \
+    return variant == kVariantTma ? filter_occupancy_one<WW, false, kVariantTma, true>(smem)                    \
+                                  : filter_occupancy_one<WW, false, kVariantLdg, true>(smem);                   \
+  return variant == kVariantTma ? filter_occupancy_one<WW, false, kVariantTma, false>(smem)                     \
+                                : filter_occupancy_one<WW, false, kVariantLdg, false>(smem);
   switch (WF) {
-    case 1: return variant == kVariantTma ? filter_occupancy_one<1, false, kVariantTma>(smem) : filter_occupancy_one<1, false, kVariantLdg>(smem);
-    case 2: return variant == kVariantTma ? filter_occupancy_one<2, false, kVariantTma>(smem) : filter_occupancy_one<2, false, kVariantLdg>(smem);
-    case 4: return variant == kVariantTma ? filter_occupancy_one<4, false, kVariantTma>(smem) : filter_occupancy_one<4, false, kVariantLdg>(smem);
+    case 1: SB_OCC(1)
+    case 2: SB_OCC(2)
+    case 4: SB_OCC(4)
     default: return 1;
   }
+#undef SB_OCC
 }
 
-size_t filter_smem_bytes(int WF, int variant) {
-  size_t tab = (size_t)256 * WF * sizeof(uint32_t);
-  if (variant == kVariantTma) return 1024 + (size_t)kRingBytes + tab;
-  return tab;
+// Resident prefilter blocks per SM.  Measured on B200 (profiles/r01b_filter_residency.md): the
+// TMA-fed kernel loses a third of its throughput when a 9th block (36 warps, 72 stages in
+// flight) becomes resident, and the one-word pair automaton is fastest with 6.
+int filter_target_bps(int WF, bool pair) {
+  static const int env = [] {
+    const char* e = getenv("SASSY_B200_FILTER_BPS");
+    const int x = e ? atoi(e) : 0;
+    return x >= 1 && x <= 16 ? x : 0;
+  }();
+  if (env) return env;
+  return (WF == 1 && pair) ? 6 : 8;
 }
+
+struct FilterConfig {
+  size_t smem = 0;  // dynamic shared memory per block, padded until at most the target is resident
+  int bps = 0;
+};
+
+const FilterConfig& filter_config(int WF, int variant, bool pair) {
+  static FilterConfig cache[8][2][2];  // (all devices of a box are the same part)
+  static FilterConfig none;
+  if (WF < 1 || WF >= 8) return none;
+  FilterConfig& c = cache[WF][variant & 1][pair ? 1 : 0];
+  if (c.bps) return c;
+  size_t smem = (size_t)256 * WF * sizeof(uint32_t);
+  if (variant == kVariantTma) smem += 1024 + (size_t)kRingBytes;
+  int occ = filter_occupancy(WF, variant, pair, smem);
+  if (variant == kVariantTma) {
+    const int target = filter_target_bps(WF, pair);
+    while (occ > target && smem + 1024 <= 200 * 1024) {
+      smem += 1024;
+      occ = filter_occupancy(WF, variant, pair, smem);
+    }
+  }
+  c.smem = smem;
+  c.bps = occ;
+  return c;
+}
+
+}  // namespace
+
+int filter_blocks_per_sm(int WF, int variant, bool pair) { return filter_config(WF, variant, pair).bps; }
 
 cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtensorMap* tmap, const ScanArgs& a,
                           cudaStream_t stream) {
-  const size_t smem = filter_smem_bytes(WF, variant);
+  const size_t smem = filter_config(WF, variant, pair).smem;
 #define SB_FCALL2(WW, PP)                                                                         \
   if (variant == kVariantTma)                                                                     \
     return rev ? launch_filter_one<WW, true, kVariantTma, PP>(tmap, a, smem, stream)              \
