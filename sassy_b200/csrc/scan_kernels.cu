@@ -56,13 +56,7 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-#ifdef SB_WAIT_INLINE
-  uint32_t spins = 0;
-  while (!mbar_try_wait(addr, parity))
-    if (++spins > (1u << 22)) __trap();
-#else
   if (!mbar_try_wait(addr, parity)) mbar_wait_slow(addr, parity);
-#endif
 }
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int32_t x, int32_t y,
@@ -176,10 +170,6 @@ __device__ __forceinline__ void row_pipeline(const CUtensorMap& tmap, const Scan
       const uint32_t st = it % kScanStages;
       mbar_wait(wbar_addr + st * 8u, (it / kScanStages) & 1u);
       const uint32_t buf = lane_buf + st * kWarpStageBytes;
-#ifdef SB_LDS_C
-      const uint8_t* bufp = ring + st * kWarpStageBytes + lane * kStageBytes;
-      body(stage_idx, own, [&](int c) { return *reinterpret_cast<const uint4*>(bufp + ((c ^ sw) << 4)); });
-#else
       body(stage_idx, own, [&](int c) {
         uint4 v;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -187,7 +177,6 @@ __device__ __forceinline__ void row_pipeline(const CUtensorMap& tmap, const Scan
                      : "r"(buf + (((uint32_t)c ^ sw) << 4)));
         return v;
       });
-#endif
       __syncwarp();  // every lane is done with this warp's ring[st]
       if (lane == 0 && it + kScanStages < total) issue(it + kScanStages);
     } else {
@@ -302,22 +291,6 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
                                // One vote per stage; everything below runs only in warps that saw a
                                // piece occurrence in this stage (hits are staged per warp, see HitQueue).
                                if (__any_sync(0xFFFFFFFFu, any != 0)) {
-#ifdef SB_HITS_CALL
-                                 if (any) {
-                                   uint32_t mask0 = 0, mask1 = 0;
-#pragma unroll
-                                   for (int c = 0; c < kChunks; c++) {
-                                     mask0 |= acc[c][0] ? (1u << c) : 0u;
-                                     mask1 |= acc[c][1] ? (1u << c) : 0u;
-                                   }
-                                   if (a.fused) {
-                                     if (mask0) emit_stage_hits(a, hq, qs, stage_idx, mask0, own);
-                                     if (mask1) emit_stage_hits(a, hq, qs + a.nq, stage_idx, mask1, own);
-                                   } else {
-                                     emit_stage_hits(a, hq, qs, stage_idx, mask0 | mask1, own);
-                                   }
-                                 }
-#else
                                  if (any && own) {
 #pragma unroll
                                    for (int c = 0; c < kChunks; c++) {
@@ -327,7 +300,6 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
                                      if (a.fused && acc[c][1]) push_hit(a, hq, qs + a.nq, base_idx);
                                    }
                                  }
-#endif
                                  __syncwarp();
                                  if (*hq.n >= kHitQueueCap / 2) flush_hits(a, hq, lane);  // warp-uniform
                                }

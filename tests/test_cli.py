@@ -72,7 +72,7 @@ def _expected_tsv(pats, recs, k, alphabet, rc, sam, max_n_frac):
     return "".join(lines)
 
 
-def make_inputs(tmp_path, rng, n_rec=12, n_pat=5, m=16):
+def make_inputs(tmp_path, rng, n_rec=12, n_pat=5, m=16, n_prob=0.3, tag=""):
     pats = [(f"p{i}", rand_seq(rng, m)) for i in range(n_pat)]
     recs = []
     for i in range(n_rec):
@@ -81,13 +81,13 @@ def make_inputs(tmp_path, rng, n_rec=12, n_pat=5, m=16):
             pid, p = pats[rng.randrange(n_pat)]
             q = bytearray(p if rng.random() < 0.5 else oracle.reverse_complement("dna", p))
             if rng.random() < 0.5:
-                q[rng.randrange(m)] = ord("N") if rng.random() < 0.3 else ord("A")
+                q[rng.randrange(m)] = ord("N") if rng.random() < n_prob else ord("A")
             a = rng.randrange(0, len(t) - m)
             t[a:a + m] = q
         recs.append((f"rec{i} len={len(t)}", bytes(t)))
-    fa = tmp_path / "texts.fa"
+    fa = tmp_path / f"texts{tag}.fa"
     fa.write_text("".join(f">{rid}\n{seq.decode()}\n" for rid, seq in recs))
-    pf = tmp_path / "pats.fa"
+    pf = tmp_path / f"pats{tag}.fa"
     pf.write_text("".join(f">{pid}\n{p.decode()}\n" for pid, p in pats))
     return pats, recs, str(fa), str(pf)
 
@@ -95,10 +95,13 @@ def make_inputs(tmp_path, rng, n_rec=12, n_pat=5, m=16):
 def test_search_tsv_matches_reference_loop(tmp_path):
     rng = random.Random(51)
     pats, recs, fa, pf = make_inputs(tmp_path, rng)
+    # Dna texts must stay inside ACGT (an N ends in the reference's "Trace failed" panic)
+    dpats, drecs, dfa, dpf = make_inputs(tmp_path, rng, n_prob=0.0, tag="_dna")
     for sam in (False, True):
-        for alphabet, nfrac in (("iupac", 0.2), ("dna", None)):
-            argv = ["search", "-f", pf, "-k", "2", "-a", alphabet, fa] + (["--sam"] if sam else [])
-            assert run(argv) == _expected_tsv(pats, recs, 2, alphabet, True, sam, nfrac)
+        argv = ["search", "-f", pf, "-k", "2", "-a", "iupac", fa] + (["--sam"] if sam else [])
+        assert run(argv) == _expected_tsv(pats, recs, 2, "iupac", True, sam, 0.2)
+        argv = ["search", "-f", dpf, "-k", "2", "-a", "dna", dfa] + (["--sam"] if sam else [])
+        assert run(argv) == _expected_tsv(dpats, drecs, 2, "dna", True, sam, None)
     # single inline pattern, forward only, tiny pattern batches give the same lines per record
     argv = ["search", "-p", pats[0][1].decode(), "-k", "1", "--no-rc", fa]
     assert run(argv) == _expected_tsv([("pattern", pats[0][1])], recs, 1, "iupac", False, False, 0.2)

@@ -17,8 +17,9 @@ def gpu_make(alphabet, rc, max_n_frac):
 def test_cli_search_filter_on_gpu(tmp_path):
     rng = random.Random(61)
     pats, recs, fa, pf = make_inputs(tmp_path, rng, n_rec=40, n_pat=7)
+    dpats, drecs, dfa, dpf = make_inputs(tmp_path, rng, n_rec=40, n_pat=7, n_prob=0.0, tag="_dna")
     for argv in (["search", "-f", pf, "-k", "2", fa],
-                 ["search", "-f", pf, "-k", "2", "-a", "dna", "--sam", fa],
+                 ["search", "-f", dpf, "-k", "2", "-a", "dna", "--sam", dfa],
                  ["search", "-f", pf, "-k", "1", "--no-rc", "--pattern-batch-size", "3", fa],
                  ["filter", "-f", pf, "-k", "1", "-v", fa],
                  ["search", "-p", pats[2][1].decode(), "-k", "3", "--max-n-frac", "0.0", fa]):
