@@ -306,7 +306,9 @@ def main():
     # N > 1: the match records of all ranks reach every rank through the fused peer-memory
     # exchange behind the traceback (csrc/peer_gather.cu); --gather nccl uses the host-staged
     # NCCL all-gather instead (A/B)
-    pg = sdist.PeerGather(s, max_ops=m + k + 1) if (world > 1 and args.gather == "peer") else None
+    pg = None
+    if world > 1 and args.gather == "peer":
+        pg = sdist.PeerGather.create_or_none(s, max_ops=m + k + 1, device=dev)
 
     def step_resident():
         if pg is not None:

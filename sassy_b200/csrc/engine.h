@@ -86,16 +86,6 @@ struct SearchOpts {
   bool special() const { return without_trace || only_best || max_n_frac >= 0.f || pam_len > 0; }
 };
 
-// Many texts resident in HBM (search_texts / search_many): the texts back to back, every
-// start aligned to 16 bytes, followed by zero padding.
-struct DeviceTexts {
-  uint8_t* d = nullptr;
-  uint64_t* d_offs = nullptr;  // [count] start of text i in d
-  uint64_t* d_lens = nullptr;  // [count]
-  std::vector<uint64_t> lens;
-  uint64_t total = 0;
-};
-
 class Engine {
  public:
   Engine(int profile, int device);

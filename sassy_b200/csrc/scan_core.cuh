@@ -29,7 +29,7 @@ namespace sb {
 // character, so if the score after a group of kGroup characters is above
 // k + kGroup - 1 no position inside the group can be <= k.
 #ifndef SB_GROUP
-#define SB_GROUP 4
+#define SB_GROUP 8
 #endif
 constexpr int kGroup = SB_GROUP;  // 4, 8 or 16 (whole 32-bit text words)
 // Bytes per thread per pipeline stage: 64 (half a line, SWIZZLE_64B) or 128 (SWIZZLE_128B).

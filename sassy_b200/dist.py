@@ -183,21 +183,50 @@ class PeerGather:
         else:
             self.world, self.rank = 1, 0
         self.fallbacks = 0
+        self._h = None
+        # Set-up is collective: no rank raises between two collectives, the outcome is agreed on
+        # by an all-reduce (which doubles as the barrier before the first exchange).
+        err = None
+        buf = (ctypes.c_uint8 * 64)()
         self._h = self._lib.sassy_gpu_gather_create(searcher._h, self.world, self.rank, cap, max_ops)
         if not self._h:
-            raise RuntimeError(_native.last_error())
+            err = _native.last_error()
+        elif self.world > 1 and self._lib.sassy_gpu_gather_handle(self._h, buf) != 0:
+            err = _native.last_error()
         if self.world > 1:
-            buf = (ctypes.c_uint8 * 64)()
-            if self._lib.sassy_gpu_gather_handle(self._h, buf) != 0:
-                raise RuntimeError(_native.last_error())
             dev = torch.device("cuda", searcher.device) if dist.get_backend(group) == "nccl" else "cpu"
             mine = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
             allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(allh, mine, group=group)
-            blob = bytes(allh.cpu().numpy().tobytes())
-            if self._lib.sassy_gpu_gather_connect(self._h, blob) != 0:
-                raise RuntimeError(_native.last_error())
-            dist.barrier(group=group)
+            if err is None:
+                blob = bytes(allh.cpu().numpy().tobytes())
+                if self._lib.sassy_gpu_gather_connect(self._h, blob) != 0:
+                    err = _native.last_error()
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0 and err is None:
+                err = "peer memory could not be mapped on another rank"
+        if err is not None:
+            self._free_local()
+            raise RuntimeError(err)
+
+    @classmethod
+    def create_or_none(cls, searcher, max_ops: int, device=None, group=None):
+        """Collective constructor: every rank gets a PeerGather, or -- if peer memory cannot be
+        mapped on some rank (no P2P path between two GPUs) -- every rank gets None and the caller
+        uses gather_matches (NCCL) instead."""
+        try:
+            return cls(searcher, max_ops, group=group)  # raises on every rank or on none
+        except RuntimeError as e:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+            import sys
+            print(f"[sassy_b200] peer-memory gather unavailable (rank {rank}): {e}", file=sys.stderr, flush=True)
+            return None
+
+    def _free_local(self):
+        if self._h:
+            self._lib.sassy_gpu_gather_free(self._h)
+            self._h = None
 
     def close(self):
         if self._h:
