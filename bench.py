@@ -259,6 +259,12 @@ def main():
         run_reference(args)
         return
 
+    # the contract is ONE JSON line on stdout: libraries that write there (NCCL prints its version
+    # banner at communicator creation) go to stderr while the benchmark runs
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import sassy_b200
@@ -451,7 +457,8 @@ def main():
         "device_ms_per_step": sum(total_ms) / len(total_ms),
         "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

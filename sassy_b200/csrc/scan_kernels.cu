@@ -353,28 +353,55 @@ __device__ __forceinline__ void scan_window(const ScanArgs& a, const uint32_t* _
   const uint32_t byte_order = rev ? 0x0123u : 0x3210u;
   int64_t c = rev ? c_hi - 1 : c_lo;  // chunks in scan order
   uint4 cur = __ldg(chunks + c);
+  int prev = -1;  // score before the current text word once the emit zone has been entered
   for (int64_t t = 0; t < nchunks; t++) {
     const int64_t cn = rev ? c - 1 : c + 1;
     uint4 nxt = make_uint4(0, 0, 0, 0);
     if (t + 1 < nchunks) nxt = __ldg(chunks + cn);
     // scan-direction offset of the chunk's first character in scan order
-    const int32_t rel0 = rev ? (int32_t)((n - 1 - ((c << 4) + 15)) - w0) : (int32_t)((c << 4) - w0);
-    const uint32_t words[4] = {rev ? cur.w : cur.x, rev ? cur.z : cur.y, rev ? cur.y : cur.z, rev ? cur.x : cur.w};
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint32_t wv = __byte_perm(words[j], 0u, byte_order);
+    int32_t srel0 = rev ? (int32_t)((n - 1 - ((c << 4) + 15)) - w0) : (int32_t)((c << 4) - w0);
+    uint32_t q0 = rev ? cur.w : cur.x, q1 = rev ? cur.z : cur.y, q2 = rev ? cur.y : cur.z, q3 = rev ? cur.x : cur.w;
+#pragma unroll 1
+    for (int j = 0; j < 4; j++, srel0 += 4) {
+      const uint32_t wv = __byte_perm(q0, 0u, byte_order);  // the word's characters in scan order
+      q0 = q1, q1 = q2, q2 = q3;
       const uint32_t pre = (wv >> a.sh0) & a.msk0;
+      // all four characters inside the window?  (one unsigned compare: srel0 in [0, wlen - 4])
+      const bool inside = wlen >= 4u && (uint32_t)srel0 <= wlen - 4u;
+      if (inside && srel0 + 4 <= emit_rel) {  // warm-up: no position of this word can be reported
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
-        const int32_t srel = rel0 + 4 * j + b;
-        if ((uint32_t)srel < wlen) {
-          const uint32_t row = (pre >> (8 * b)) & 0xFFu;
-          myers_step<W>(s, eq + row * W);
-          if (srel >= emit_rel) {
-            const int score = lane_score<W>(s);
-            if (score <= a.k) emit_candidate(a, qs, (uint64_t)(w0 + srel) + 1, score);
+        for (int b = 0; b < 4; b++) myers_step<W>(s, eq + ((pre >> (8 * b)) & 0xFFu) * W);
+      } else if (inside && srel0 >= emit_rel) {
+        // emit zone: the score moves by at most 1 per character, so a position of this word can
+        // only be <= k if score_before + score_after <= 2k + 4 (as fast_group in scan_core.cuh)
+        if (prev < 0) prev = lane_score<W>(s);
+        const Lane<W> saved = s;
+#pragma unroll
+        for (int b = 0; b < 4; b++) myers_step<W>(s, eq + ((pre >> (8 * b)) & 0xFFu) * W);
+        const int score = lane_score<W>(s);
+        if (prev + score <= 2 * a.k + 4) {
+          s = saved;
+#pragma unroll 1
+          for (int b = 0; b < 4; b++) {
+            myers_step<W>(s, eq + ((pre >> (8 * b)) & 0xFFu) * W);
+            const int sc = lane_score<W>(s);
+            if (sc <= a.k) emit_candidate(a, qs, (uint64_t)(w0 + srel0 + b) + 1, sc);
           }
         }
+        prev = score;
+      } else {  // a word straddling the window or the start of the emit zone: character by character
+#pragma unroll 1
+        for (int b = 0; b < 4; b++) {
+          const int32_t srel = srel0 + b;
+          if ((uint32_t)srel < wlen) {
+            myers_step<W>(s, eq + ((pre >> (8 * b)) & 0xFFu) * W);
+            if (srel >= emit_rel) {
+              const int sc = lane_score<W>(s);
+              if (sc <= a.k) emit_candidate(a, qs, (uint64_t)(w0 + srel) + 1, sc);
+            }
+          }
+        }
+        prev = -1;
       }
     }
     cur = nxt;
