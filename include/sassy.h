@@ -9,8 +9,8 @@
  *   - sassy_searcher: alphabet is "ascii" | "dna" | "iupac", case-insensitive
  *     (c.rs:62-67); alpha = NAN disables overhang (c.rs:60).  The reference
  *     panics (process abort across extern "C") on a null pointer or unknown
- *     alphabet; so does this library.  Overhang (alpha != NAN) is outside the
- *     GPU path and aborts with a message.
+ *     alphabet; so does this library, and likewise on overhang with a profile
+ *     other than iupac or alpha outside [0, 1] (src/search.rs:373-383).
  *   - search: == Searcher::<P>::search, i.e. local-minima mode with traceback
  *     (c.rs:88-122).  The returned array is owned by the caller and must be
  *     released with sassy_matches_free(ptr, len) with the same len; for zero

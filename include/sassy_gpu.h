@@ -17,6 +17,8 @@
  *   with_trace / without_trace  src/search.rs:446-449    sassy_gpu_set_trace
  *   only_best_match             src/search.rs:441-444    sassy_gpu_set_only_best_match
  *   set_max_n_frac              src/search.rs:452-458    sassy_gpu_set_max_n_frac
+ *   new_*_with_overhang(alpha)  src/search.rs:385-402    alpha of sassy_searcher / sassy_gpu_searcher
+ *   with_max_overhang           src/search.rs:436-439    sassy_gpu_set_max_overhang
  *   search_with_fn + PAM filter src/search.rs:767-784,   sassy_gpu_search_pam(_text)
  *                               bin/crispr.rs:198-221
  *   search_patterns             src/search.rs:648-683    sassy_gpu_search_patterns
@@ -125,6 +127,11 @@ sassy_gpu_Result *sassy_gpu_search_text(sassy_SearcherType *searcher, const uint
 int sassy_gpu_set_trace(sassy_SearcherType *searcher, int trace);
 int sassy_gpu_set_only_best_match(sassy_SearcherType *searcher, int on);
 int sassy_gpu_set_max_n_frac(sassy_SearcherType *searcher, float max_n_frac);
+/* Searcher::with_max_overhang (src/search.rs:436-439); < 0 = unlimited.  Overhang itself is the
+ * `alpha` of the constructor (Iupac only, 0 <= alpha <= 1, src/search.rs:373-400): pattern
+ * characters hanging over a text end cost alpha each; matches then report pattern_start /
+ * pattern_end inside the pattern.  Not available for encoded patterns or with a PAM filter. */
+int sassy_gpu_set_max_overhang(sassy_SearcherType *searcher, int max_overhang);
 
 /* search_with_fn with the end filter of the reference's CRISPR mode: an end position is kept
  * only if the pam_len (<= 16) text characters before it match `pam` exactly under the

@@ -90,13 +90,13 @@ def _lib():
         lib.oracle_search_opts.argtypes = [
             ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
             ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
-            ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p,
+            ctypes.c_char_p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int64, ctypes.c_void_p,
         ]
         lib.oracle_search_opts.restype = ctypes.c_int
         lib.oracle_search_many.argtypes = [
             ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_void_p,
             ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
-            ctypes.c_void_p,
+            ctypes.c_float, ctypes.c_int64, ctypes.c_void_p,
         ]
         lib.oracle_search_many.restype = ctypes.c_int
         lib.oracle_search_encoded_nfrac.argtypes = [
@@ -160,7 +160,8 @@ class OracleError(RuntimeError):
 
 def search(alphabet: str, pattern: bytes, text: bytes, k: int, rc: bool = False,
            all_minima: bool = False, without_trace: bool = False, only_best: bool = False,
-           max_n_frac: float | None = None, pam: bytes | None = None) -> List[Match]:
+           max_n_frac: float | None = None, pam: bytes | None = None, alpha: float | None = None,
+           max_overhang: int | None = None) -> List[Match]:
     """Searcher::<P>::new(rc, None).search / search_all, optionally under the Searcher options
     (without_trace, only_best_match, max_n_frac) and with the CRISPR end filter of
     search_with_fn (``pam``: the characters before the end position must match it)."""
@@ -170,7 +171,10 @@ def search(alphabet: str, pattern: bytes, text: bytes, k: int, rc: bool = False,
         nf = -1.0 if max_n_frac is None or max_n_frac == 1.0 else float(max_n_frac)
         r = lib.oracle_search_opts(PROFILE[alphabet.lower()], pattern, len(pattern), text, len(text),
                                    k, int(rc), int(all_minima), int(without_trace), int(only_best), nf,
-                                   pam, len(pam) if pam else 0, out)
+                                   pam, len(pam) if pam else 0, -1.0 if alpha is None else float(alpha),
+                                   -1 if max_overhang is None else int(max_overhang), out)
+        if r == -4:
+            raise OracleError("Overhang is not supported for this profile")
         if r == -2:
             raise OracleError("Pattern is not valid IUPAC")
         if r != 0:
@@ -182,7 +186,8 @@ def search(alphabet: str, pattern: bytes, text: bytes, k: int, rc: bool = False,
 
 def search_many(alphabet: str, patterns: Sequence[bytes], texts: Sequence[bytes], k: int, rc: bool = False,
                 without_trace: bool = False, only_best: bool = False,
-                max_n_frac: float | None = None) -> List[Match]:
+                max_n_frac: float | None = None, alpha: float | None = None,
+                max_overhang: int | None = None) -> List[Match]:
     """Searcher::search_many (SearchMode::Single order: pattern-major, then text)."""
     lib = _lib()
     out = lib.oracle_out_new()
@@ -192,7 +197,8 @@ def search_many(alphabet: str, patterns: Sequence[bytes], texts: Sequence[bytes]
         nf = -1.0 if max_n_frac is None or max_n_frac == 1.0 else float(max_n_frac)
         r = lib.oracle_search_many(PROFILE[alphabet.lower()], b"".join(patterns), plens, len(patterns),
                                    b"".join(texts), tlens, len(texts), k, int(rc), int(without_trace),
-                                   int(only_best), nf, out)
+                                   int(only_best), nf, -1.0 if alpha is None else float(alpha),
+                                   -1 if max_overhang is None else int(max_overhang), out)
         if r == -2:
             raise OracleError("Pattern is not valid IUPAC")
         if r != 0:

@@ -20,6 +20,7 @@
  * (boundary conditions: reference src/search.rs:1058-1061 (hp=1,hm=0 => left
  *  column +1 per row) and src/search.rs:1101 (vp=vm=0 => top row 0)).
  */
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -49,6 +50,8 @@ typedef struct {
   float max_n_frac;    /* < 0: off (src/search.rs:452-458) */
   const uint8_t *pam;  /* end filter of bin/crispr.rs:198-205; NULL: none */
   size_t pam_len;
+  float alpha;          /* overhang cost per pattern character, src/search.rs:231-233; < 0: off */
+  int64_t max_overhang; /* src/search.rs:238-239; < 0: unlimited */
 } OracleOpts;
 
 typedef struct {
@@ -173,29 +176,61 @@ static inline uint8_t text_at(const uint8_t *t, size_t n, int rev, size_t i) {
   return rev ? t[n - 1 - i] : t[i];
 }
 
-static int32_t *bottom_row(int profile, const uint8_t *p, size_t m, const uint8_t *t, size_t n,
-                           int rev) {
-  int32_t *c = (int32_t *)malloc((n + 1) * sizeof(int32_t));
+/* Overhang (reference src/search.rs:347-356,1274-1282,1693-1710; src/trace.rs:36-53):
+ * with alpha set, pattern characters hanging over either end of the text cost alpha each
+ * instead of 1: the left column of D is floor(j * alpha) (up to max_overhang rows, then +1 per
+ * row), the text is followed by `steps` wildcard characters and an end position o characters
+ * beyond the text costs floor(alpha * o) on top of the DP value.  All in f32 like the reference. */
+static int32_t left_cost(size_t j, float alpha, int64_t mo) {
+  if (alpha < 0.f) return (int32_t)j;
+  size_t jm = (mo >= 0 && (size_t)mo < j) ? (size_t)mo : j;
+  return (int32_t)floorf((float)jm * alpha) + (int32_t)(j - jm);
+}
+
+static size_t overhang_steps(size_t m, size_t k, float alpha, int64_t mo) {
+  if (alpha < 0.f) return 0;
+  float r = ceilf(((float)k + alpha) / alpha); /* Rust `as usize`: NaN -> 0, +inf saturates */
+  size_t s = isnan(r) ? 0 : (r >= 1e18f ? SIZE_MAX : (size_t)r);
+  if (m < s) s = m;
+  if (mo >= 0 && (size_t)mo < s) s = (size_t)mo;
+  return s;
+}
+
+static int32_t overshoot_cost(float alpha, size_t o) {
+  return (alpha < 0.f || o == 0) ? 0 : (int32_t)floorf(alpha * (float)o);
+}
+
+/* c_i for i in [0, n + steps]; beyond the text every character matches (the reference pads
+ * with 'N', src/search.rs:203) and the overshoot cost is added (src/search.rs:1274-1282). */
+static int32_t *bottom_row_ov(int profile, const uint8_t *p, size_t m, const uint8_t *t, size_t n,
+                              int rev, float alpha, int64_t mo, size_t steps) {
+  int32_t *c = (int32_t *)malloc((n + steps + 1) * sizeof(int32_t));
   int32_t *col = (int32_t *)malloc((m + 1) * sizeof(int32_t));
-  for (size_t j = 0; j <= m; j++) col[j] = (int32_t)j;
-  c[0] = (int32_t)m;
-  for (size_t i = 1; i <= n; i++) {
-    uint8_t tc = text_at(t, n, rev, i - 1);
+  for (size_t j = 0; j <= m; j++) col[j] = left_cost(j, alpha, mo);
+  c[0] = col[m];
+  for (size_t i = 1; i <= n + steps; i++) {
+    int wild = i > n;
+    uint8_t tc = wild ? 0 : text_at(t, n, rev, i - 1);
     int32_t diag = col[0]; /* D[j-1][i-1] */
     col[0] = 0;
     for (size_t j = 1; j <= m; j++) {
       int32_t up = col[j - 1];  /* D[j-1][i]   */
       int32_t left = col[j];    /* D[j][i-1]   */
-      int32_t v = diag + (search_eq(profile, p[j - 1], tc) ? 0 : 1);
+      int32_t v = diag + ((wild || search_eq(profile, p[j - 1], tc)) ? 0 : 1);
       if (left + 1 < v) v = left + 1;
       if (up + 1 < v) v = up + 1;
       diag = left;
       col[j] = v;
     }
-    c[i] = col[m];
+    c[i] = col[m] + overshoot_cost(alpha, wild ? i - n : 0);
   }
   free(col);
   return c;
+}
+
+static int32_t *bottom_row(int profile, const uint8_t *p, size_t m, const uint8_t *t, size_t n,
+                           int rev) {
+  return bottom_row_ov(profile, p, m, t, n, rev, -1.f, -1, 0);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -206,18 +241,26 @@ static int32_t *bottom_row(int profile, const uint8_t *p, size_t m, const uint8_
 /* Returns 0 on success, -1 if the greedy walk finds no ancestor (the        */
 /* reference panics with "Trace failed").                                    */
 
-static int trace_window(int profile, const uint8_t *p, size_t m, const uint8_t *t, size_t n,
-                        int rev, size_t off, size_t end, OracleMatch *mm, char **ops_out,
-                        size_t *nops_out) {
+/* With alpha >= 0 (src/trace.rs:57-104,273-406): the matrix has `cols` = m + k columns, the
+ * left column is the overhang cost, columns beyond the text slice are wildcards; an end position
+ * beyond the slice first steps diagonally back into the text (right overshoot, pattern_end
+ * shrinks), reaching column 0 with j rows left is a left overshoot (pattern_start = j).       */
+static int trace_window_ov(int profile, const uint8_t *p, size_t m, const uint8_t *t, size_t n,
+                           int rev, size_t off, size_t end, float alpha, int64_t mo, size_t cols,
+                           OracleMatch *mm, char **ops_out, size_t *nops_out) {
+  size_t slice = (end < n ? end : n) - off; /* t[off .. min(end, n)) */
   size_t w = end - off;
-  size_t stride = w + 1;
+  if (alpha < 0.f) cols = w;
+  if (cols < w) cols = w;
+  size_t stride = cols + 1;
   int32_t *D = (int32_t *)malloc((m + 1) * stride * sizeof(int32_t));
-  for (size_t i = 0; i <= w; i++) D[i] = 0;
+  for (size_t i = 0; i <= cols; i++) D[i] = 0;
   for (size_t j = 1; j <= m; j++) {
-    D[j * stride] = (int32_t)j;
-    for (size_t i = 1; i <= w; i++) {
-      uint8_t tc = text_at(t, n, rev, off + i - 1);
-      int32_t v = D[(j - 1) * stride + i - 1] + (search_eq(profile, p[j - 1], tc) ? 0 : 1);
+    D[j * stride] = left_cost(j, alpha, mo);
+    for (size_t i = 1; i <= cols; i++) {
+      int wild = i > slice;
+      uint8_t tc = wild ? 0 : text_at(t, n, rev, off + i - 1);
+      int32_t v = D[(j - 1) * stride + i - 1] + ((wild || search_eq(profile, p[j - 1], tc)) ? 0 : 1);
       int32_t l = D[j * stride + i - 1] + 1;
       int32_t u = D[(j - 1) * stride + i] + 1;
       if (l < v) v = l;
@@ -225,13 +268,26 @@ static int trace_window(int profile, const uint8_t *p, size_t m, const uint8_t *
       D[j * stride + i] = v;
     }
   }
-  char *ops = (char *)malloc(m + w + 1);
+  char *ops = (char *)malloc(m + cols + 1);
   size_t nops = 0;
   size_t j = m, i = w;
   int32_t g = D[j * stride + i];
   int32_t total = g;
+  size_t pattern_start = 0, pattern_end = m;
   int rc = 0;
+  if (i > slice) { /* src/trace.rs:298-309 */
+    size_t o = i - slice;
+    pattern_end -= o;
+    total += overshoot_cost(alpha, o);
+    i -= o;
+    j -= o;
+  }
   while (j > 0) {
+    if (i == 0 && alpha >= 0.f) { /* src/trace.rs:320-334 */
+      pattern_start = j;
+      g -= left_cost(j, alpha, mo);
+      break;
+    }
     if (i > 0 && D[(j - 1) * stride + i - 1] == g &&
         trace_eq(profile, p[j - 1], text_at(t, n, rev, off + i - 1))) {
       ops[nops++] = '=';
@@ -257,6 +313,7 @@ static int trace_window(int profile, const uint8_t *p, size_t m, const uint8_t *
     rc = -1;
     break;
   }
+  if (alpha >= 0.f && rc == 0 && g != 0) rc = -1; /* assert_eq!(g, 0), src/trace.rs:390 */
   /* cigar.reverse(): src/trace.rs:393 */
   for (size_t a = 0, b = nops; a + 1 < b; a++, b--) {
     char tmp = ops[a];
@@ -265,13 +322,19 @@ static int trace_window(int profile, const uint8_t *p, size_t m, const uint8_t *
   }
   mm->cost = total;
   mm->text_start = off + i;
-  mm->text_end = end;
-  mm->pattern_start = 0;
-  mm->pattern_end = (uint32_t)m;
+  mm->text_end = off + slice;
+  mm->pattern_start = (uint32_t)pattern_start;
+  mm->pattern_end = (uint32_t)pattern_end;
   *ops_out = ops;
   *nops_out = nops;
   free(D);
   return rc;
+}
+
+static int trace_window(int profile, const uint8_t *p, size_t m, const uint8_t *t, size_t n,
+                        int rev, size_t off, size_t end, OracleMatch *mm, char **ops_out,
+                        size_t *nops_out) {
+  return trace_window_ov(profile, p, m, t, n, rev, off, end, -1.f, -1, 0, mm, ops_out, nops_out);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -377,9 +440,12 @@ static int n_fraction_ok(const uint8_t *t, size_t n, int rev, size_t start, size
 static int v1_one_strand(int profile, const uint8_t *p, size_t m, const uint8_t *t, size_t n,
                          int32_t k, int all, int rev, uint32_t pattern_idx, uint64_t text_idx,
                          const OracleOpts *o, OracleOut *out) {
-  int32_t *c = bottom_row(profile, p, m, t, n, rev);
-  uint64_t *sel = (uint64_t *)malloc((n + 2) * sizeof(uint64_t));
-  size_t ns = select_v1(c, n, k, all, sel);
+  const float alpha = o ? o->alpha : -1.f;
+  const int64_t mo = o ? o->max_overhang : -1;
+  const size_t steps = overhang_steps(m, (size_t)k, alpha, mo);
+  int32_t *c = bottom_row_ov(profile, p, m, t, n, rev, alpha, mo, steps);
+  uint64_t *sel = (uint64_t *)malloc((n + steps + 2) * sizeof(uint64_t));
+  size_t ns = select_v1(c, n + steps, k, all, sel); /* max_pos = n + steps, src/search.rs:1298-1308 */
   int rc = 0;
   /* end filter (search_with_fn, src/search.rs:895-905) with the closure of bin/crispr.rs:
    * the pam_len characters before the end match the PAM (complemented on the rc strand).
@@ -433,10 +499,10 @@ static int v1_one_strand(int profile, const uint8_t *p, size_t m, const uint8_t 
       mm.text_start = UINT64_MAX;
       mm.text_end = end < n ? end : n;
       mm.pattern_start = UINT32_MAX;
-      mm.pattern_end = (uint32_t)m;
+      mm.pattern_end = (uint32_t)(m - (end > n ? end - n : 0)); /* src/search.rs:1470 */
       mm.cost = c[end];
     } else {
-      if (trace_window(profile, p, m, t, n, rev, off, end, &mm, &ops, &nops) != 0) rc = -1;
+      if (trace_window_ov(profile, p, m, t, n, rev, off, end, alpha, mo, fill, &mm, &ops, &nops) != 0) rc = -1;
       /* traced N filter: src/search.rs:924-934, src/n_filter.rs:59-61 */
       if (o && o->max_n_frac >= 0.f &&
           !n_fraction_ok(t, n, rev, mm.text_start, mm.text_end, o->max_n_frac, 0)) {
@@ -502,11 +568,14 @@ int oracle_search(int profile, const uint8_t *pattern, size_t m, const uint8_t *
 /* search / search_all / search_with_fn(PAM) under the Searcher options. */
 int oracle_search_opts(int profile, const uint8_t *pattern, size_t m, const uint8_t *text, size_t n,
                        uint32_t k, int rc_strand, int all, int without_trace, int only_best,
-                       float max_n_frac, const uint8_t *pam, size_t pam_len, OracleOut *out) {
+                       float max_n_frac, const uint8_t *pam, size_t pam_len, float alpha,
+                       int64_t max_overhang, OracleOut *out) {
   init_tables();
   if (profile == PROFILE_IUPAC && !oracle_iupac_valid(pattern, m)) return -2;
   if (pam_len > 64) return -3;
-  OracleOpts o = {without_trace, only_best, max_n_frac, pam, pam_len};
+  OracleOpts o = {without_trace, only_best, max_n_frac, pam, pam_len, alpha, max_overhang};
+  if (alpha >= 0.f && profile != PROFILE_IUPAC) return -4; /* src/search.rs:373-383 */
+  if (alpha >= 0.f && pam_len) return -5; /* the PAM closure would index beyond the text */
   return search_pair(profile, pattern, m, text, n, k, rc_strand, all, 0, 0, &o, out);
 }
 
@@ -516,9 +585,10 @@ int oracle_search_opts(int profile, const uint8_t *pattern, size_t m, const uint
 int oracle_search_many(int profile, const uint8_t *patterns, const uint64_t *pattern_lens,
                        size_t n_patterns, const uint8_t *texts, const uint64_t *text_lens,
                        size_t n_texts, uint32_t k, int rc_strand, int without_trace, int only_best,
-                       float max_n_frac, OracleOut *out) {
+                       float max_n_frac, float alpha, int64_t max_overhang, OracleOut *out) {
   init_tables();
-  OracleOpts o = {without_trace, only_best, max_n_frac, NULL, 0};
+  OracleOpts o = {without_trace, only_best, max_n_frac, NULL, 0, alpha, max_overhang};
+  if (alpha >= 0.f && profile != PROFILE_IUPAC) return -4;
   int rc = 0;
   const uint8_t *p = patterns;
   for (size_t pi = 0; pi < n_patterns; pi++) {

@@ -102,6 +102,7 @@ SIGNATURES = {
     "sassy_gpu_set_trace": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "sassy_gpu_set_only_best_match": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "sassy_gpu_set_max_n_frac": (ctypes.c_int, [c_void_p, ctypes.c_float]),
+    "sassy_gpu_set_max_overhang": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "sassy_gpu_search_pam": (c_void_p, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, ctypes.c_int,
                                         c_void_p, c_size_t]),
     "sassy_gpu_search_pam_text": (c_void_p, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, ctypes.c_int,

@@ -137,9 +137,9 @@ def write_record(rec: Record, out) -> None:
         out.write(f">{rec.id}\n{rec.seq.decode('utf-8', 'replace')}\n")
 
 
-def _default_searcher(alphabet: str, rc: bool, max_n_frac: Optional[float]):
+def _default_searcher(alphabet: str, rc: bool, max_n_frac: Optional[float], alpha: Optional[float] = None):
     import sassy_b200
-    return sassy_b200.Searcher(alphabet, rc=rc, max_n_frac=max_n_frac)
+    return sassy_b200.Searcher(alphabet, rc=rc, alpha=alpha, max_n_frac=max_n_frac)
 
 
 def run_search(args, match_out=None, filter_out=None, make_searcher: Callable = _default_searcher) -> List[int]:
@@ -149,10 +149,11 @@ def run_search(args, match_out=None, filter_out=None, make_searcher: Callable = 
         raise SystemExit("No pattern sequences found")
     k = args.k
     rc = not args.no_rc
-    if args.overhang is not None:
-        raise SystemExit("--overhang is outside the GPU search path")
+    if args.overhang is not None and args.v2:
+        raise SystemExit("--overhang with --v2 is outside the GPU search path")
     # only the Iupac searcher gets the N filter (bin/grep.rs:489-497)
-    searcher = make_searcher(args.alphabet, rc, args.max_n_frac if args.alphabet == "iupac" else None)
+    searcher = make_searcher(args.alphabet, rc, args.max_n_frac if args.alphabet == "iupac" else None,
+                             **({"alpha": args.overhang} if args.overhang is not None else {}))
     hist = [0] * (k + 1)
     if match_out is not None:
         match_out.write(TSV_HEADER)

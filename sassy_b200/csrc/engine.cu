@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cub/cub.cuh>
 #include <chrono>
 #include <thread>
@@ -297,6 +298,25 @@ void Engine::make_tensor_map(CUtensorMap* map, const DeviceText& text, const Sca
   }
 }
 
+void Engine::overhang_args(const SearchOpts& opts, int m, int k, int W, OverhangArgs& o) const {
+  memset(&o, 0, sizeof o);
+  const int pad = 32 * W - m;
+  for (int j = 0; j < m; j++)
+    if (overhang_left_cost(j + 1, opts.alpha, opts.max_overhang) - overhang_left_cost(j, opts.alpha, opts.max_overhang)) {
+      const int b = pad + j;
+      o.init_pv[b >> 5] |= 1u << (b & 31);
+    }
+  o.left_total = overhang_left_cost(m, opts.alpha, opts.max_overhang);
+  // get_overhang_steps (src/search.rs:347-356): min(m, ceil((k + alpha) / alpha), max_overhang);
+  // Rust's `as usize` turns NaN (k = 0, alpha = 0) into 0 and saturates +inf
+  const float r = ceilf(((float)k + opts.alpha) / opts.alpha);
+  uint64_t steps = std::isnan(r) ? 0 : (r >= 1e18f ? ~0ull : (uint64_t)r);
+  steps = std::min<uint64_t>(steps, (uint64_t)m);
+  if (opts.max_overhang >= 0) steps = std::min<uint64_t>(steps, (uint64_t)opts.max_overhang);
+  o.steps = (uint32_t)steps;
+  o.alpha = opts.alpha;
+}
+
 // Candidates (unsorted, in keys_/cost_) -> device radix sort -> selection (first copy of a
 // position, local-minima rule, end filters, only_best_match) -> stream compaction -> traceback
 // (or end position + cost only) -> host.  Returns the number of records written to `out`.
@@ -406,6 +426,8 @@ uint64_t Engine::post_process(const PostCtx& c, const SearchOpts& opts, uint64_t
     t.keys = sel_keys;
     t.costs = opts.without_trace ? sel_cost : nullptr;
     t.max_n_frac = opts.without_trace ? -1.f : opts.max_n_frac;
+    t.alpha = opts.alpha;
+    t.max_overhang = opts.max_overhang;
     t.count_dev = (need_select && fast) ? d_nsel : nullptr;
     t.scratch = scratch_.as<uint32_t>();
     t.ops = ops_.as<uint32_t>();
@@ -482,8 +504,12 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   SB_CUDA(cudaEventRecord(ev_[0], stream_));
 
   // ---- plan: exact piece prefilter or full scan ------------------------------------------------
+  // Overhang: the pigeonhole argument of the prefilter does not hold for alignments that hang
+  // over a text end, so the full scan runs; the edge kernel owns the end positions it changes.
+  const bool ov = opts.alpha >= 0.f;
+  if (ov && opts.pam_len > 0) throw CudaError("an end filter cannot be combined with overhang");
   FilterPlan fp;
-  if (n > 0 && filter_mode_ != 0) {
+  if (n > 0 && filter_mode_ != 0 && !ov) {
     std::vector<const uint8_t*> qptr(nq);
     for (uint32_t q = 0; q < nq; q++) qptr[q] = queries[q].bytes;
     fp = plan_filter(profile_, qptr.data(), nq, m, k, filter_mode_ == 2 ? 1e30 : 0.85);
@@ -529,12 +555,20 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   a.m = m;
   a.k = k;
   a.cand_count = d_cand_count;
+  OverhangArgs oa;
+  if (ov) {
+    a.emit_min = std::min<uint64_t>(n, (uint64_t)m + (uint64_t)k);
+    overhang_args(opts, m, k, W, oa);
+    oa.text = TextRef{text.d, n, nullptr, nullptr, nq};
+    oa.rev_flags = d_rev;
+    oa.nslots = nq;
+  }
 
   // end position 0 (empty text prefix) has cost m: a candidate iff m <= k.
   // (reference src/search.rs:1320-1322; never reported for an empty text, :1314-1316)
   std::vector<uint64_t> k0;
   std::vector<uint32_t> c0;
-  if (include_pos0 && m <= k && n > 0)
+  if (include_pos0 && m <= k && n > 0 && !ov)
     for (uint32_t q = 0; q < nq; q++) {
       k0.push_back(cand_key(q, 0));
       c0.push_back((uint32_t)m);
@@ -618,6 +652,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     memset(&t, 0, sizeof t);
     t.text = TextRef{text.d, n, nullptr, nullptr, nq};
     t.max_n_frac = -1.f;
+    t.alpha = -1.f;
     t.profile = profile_;
     t.patterns = d_pat;
     t.rev_flags = d_rev;
@@ -788,6 +823,13 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
           stats_.scan_launches++;
         }
       }
+      if (ov) {
+        a.nq = nq;
+        a.qs_base = 0;
+        a.eq = d_eq;
+        SB_CUDA(launch_overhang_edges(W, a, oa, stream_));
+        stats_.aux_launches++;
+      }
       SB_CUDA(cudaEventRecord(ev_[2], stream_));
       queue_small_tail();
       read_counts();
@@ -920,6 +962,16 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
   t.ntexts = (uint32_t)ntexts;
   t.nq = nq;
   t.include_pos0 = opts.include_pos0 ? 1 : 0;
+  const bool ov = opts.alpha >= 0.f;
+  if (ov && opts.pam_len > 0) throw CudaError("an end filter cannot be combined with overhang");
+  t.overhang = ov ? 1 : 0;
+  OverhangArgs oa;
+  if (ov) {
+    overhang_args(opts, m, k, W, oa);
+    oa.text = TextRef{d_base, 0, d_offs, d_lens, nq};
+    oa.rev_flags = d_rev;
+    oa.nslots = (uint32_t)nslots;
+  }
 
   unsigned long long h_counts[4] = {0, 0, 0, 0};
   uint64_t ncand = 0;
@@ -933,6 +985,10 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
     SB_CUDA(cudaEventRecord(ev_[1], stream_));
     SB_CUDA(launch_texts(W, a, t, stream_));
     stats_.scan_launches++;
+    if (ov) {
+      SB_CUDA(launch_overhang_edges(W, a, oa, stream_));
+      stats_.aux_launches++;
+    }
     SB_CUDA(cudaEventRecord(ev_[2], stream_));
     SB_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, stream_));
     SB_CUDA(cudaStreamSynchronize(stream_));

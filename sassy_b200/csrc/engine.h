@@ -83,7 +83,11 @@ struct SearchOpts {
   bool n_endpoint = false;     // also apply the pre-trace N end-point filter (v1, src/search.rs:907-919)
   const uint8_t* pam = nullptr;  // end filter of search_with_fn as used by bin/crispr.rs:198-205
   int pam_len = 0;
-  bool special() const { return without_trace || only_best || max_n_frac >= 0.f || pam_len > 0; }
+  float alpha = -1.f;          // overhang cost per pattern character (src/search.rs:231-233); < 0 = off
+  int max_overhang = -1;       // Searcher::with_max_overhang (src/search.rs:436-439); < 0 = unlimited
+  bool special() const {
+    return without_trace || only_best || max_n_frac >= 0.f || pam_len > 0 || alpha >= 0.f;
+  }
 };
 
 class Engine {
@@ -145,6 +149,8 @@ class Engine {
     int end_bit = 64;
   };
   uint64_t post_process(const PostCtx& c, const SearchOpts& opts, uint64_t ncand, MatchSet& out);
+  // Overhang: fills the arguments of the edge kernel (left-column deltas, wildcard steps).
+  void overhang_args(const SearchOpts& opts, int m, int k, int W, OverhangArgs& o) const;
   void upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair, bool fused);
   void make_tensor_map(CUtensorMap* map, const DeviceText& text, const ScanGeom& g) const;
   // host -> dst (device, padded): packed transport for large Dna texts, else plain copies

@@ -41,8 +41,24 @@ struct TextsArgs {
   const uint8_t* rev_flags;  // [nq]
   uint32_t ntexts, nq;
   uint32_t include_pos0;
+  uint32_t overhang;  // 1: positions <= min(n, m+k) of every text are left to the edge kernel
 };
 cudaError_t launch_texts(int W, const ScanArgs& a, const TextsArgs& t, cudaStream_t stream);
+
+// Overhang: the end positions that the overhang changes -- 0..min(n, m+k) (cheap left column)
+// and n+1..n+steps (wildcard columns beyond the text, + floor(alpha * overshoot)) -- are
+// computed per (slot, edge) by one thread each with the exact recurrences; the scan kernels
+// leave positions <= ScanArgs::emit_min to it.
+struct OverhangArgs {
+  TextRef text;
+  const uint8_t* rev_flags;  // [nq]
+  uint32_t nslots;
+  uint32_t init_pv[kMaxWords];  // vertical deltas of the left column L(j)
+  int32_t left_total;           // L(m): cost of end position 0
+  uint32_t steps;               // wildcard columns beyond the text
+  float alpha;
+};
+cudaError_t launch_overhang_edges(int W, const ScanArgs& a, const OverhangArgs& o, cudaStream_t stream);
 
 // flags[i] = 1 iff sorted candidate i is kept by the local-minima rule and, when `filter` is
 // given, by the end-position predicates (end_filter_pass, scan_core.cuh).
@@ -73,6 +89,8 @@ struct TraceArgs {
   const uint64_t* keys;  // selected candidates (sorted)
   const uint32_t* costs; // without_trace: cost of every selected candidate (no traceback is run)
   float max_n_frac;      // >= 0: flag traced matches whose text slice holds too many N (src/n_filter.rs:59-61)
+  float alpha;           // >= 0: overhang traceback (trace_one_ov)
+  int32_t max_overhang;  // < 0: unlimited
   uint64_t first;        // slice [first, first+count) handled by this launch
   uint64_t count;
   const unsigned long long* count_dev;  // optional device-side total that clips the slice

@@ -149,7 +149,7 @@ __global__ void trace_kernel(const __grid_constant__ TraceArgs t) {
     gm.text_end = end < n ? end : n;
     gm.cost = (int32_t)t.costs[gi];
     gm.nops = 0;
-    gm.failed = 0;
+    gm.failed = pack_overhang(0, end > n ? (uint32_t)(end - n) : 0u);  // pattern_end = m - overshoot
   } else {
     ColStore cs;
     if (t.smem_cols) {
@@ -160,8 +160,12 @@ __global__ void trace_kernel(const __grid_constant__ TraceArgs t) {
       cs.stride = nthreads;
     }
     TraceOut out;
-    trace_one<P>(text, n, rev, t.patterns + (size_t)q * t.m, t.m, t.k, t.eq + (size_t)q * t.nrows * t.W, t.W,
-                 t.sh0, t.msk0, end, cs, t.ops + gi * t.ops_words, t.ops_words, out);
+    if (t.alpha >= 0.f)
+      trace_one_ov<P>(text, n, rev, t.patterns + (size_t)q * t.m, t.m, t.k, t.eq + (size_t)q * t.nrows * t.W, t.W,
+                      t.sh0, t.msk0, end, t.alpha, t.max_overhang, cs, t.ops + gi * t.ops_words, t.ops_words, out);
+    else
+      trace_one<P>(text, n, rev, t.patterns + (size_t)q * t.m, t.m, t.k, t.eq + (size_t)q * t.nrows * t.W, t.W,
+                   t.sh0, t.msk0, end, cs, t.ops + gi * t.ops_words, t.ops_words, out);
     gm.text_start = out.text_start;
     gm.text_end = out.text_end;
     gm.cost = out.cost;

@@ -21,6 +21,7 @@
 
 #include "profile.h"
 
+#include <math.h>
 #include <string.h>
 
 namespace sb {
@@ -79,6 +80,7 @@ struct ScanArgs {
   uint64_t* hit_keys;       // (query slot << 40) | forward index of the hit's 16-byte text chunk / 16
   unsigned long long* hit_count;
   uint64_t hit_cap;
+  uint64_t emit_min;        // overhang: end positions <= emit_min come from the edge kernel instead
 };
 
 template <int W>
@@ -234,7 +236,7 @@ SB_SLOW Lane<W> slow_word(Lane<W> s, uint32_t x, uint64_t base_idx, const ScanAr
     const int score = lane_score<W>(s);
     if (score <= a.k && own && idx < a.n) {
       const uint64_t pos = REV ? a.n - idx : idx + 1;
-      emit_candidate(a, qs, pos, score);
+      if (pos > a.emit_min) emit_candidate(a, qs, pos, score);
     }
   }
   return s;
@@ -826,6 +828,142 @@ SB_HD void trace_one(const uint8_t* text, uint64_t n, bool rev, const uint8_t* p
   out.text_start = off + i;
   out.text_end = end;
   out.nops = nops;
+}
+
+// ---------------------------------------------------------------------------
+// Overhang (reference src/search.rs:347-356,1274-1282,1693-1710; src/trace.rs:36-53,298-334):
+// pattern characters hanging over either end of the text cost alpha each.  The left column of D
+// is L(j) = floor(min(j, mo) * alpha) + (j - min(j, mo)), the text is followed by `steps`
+// wildcard characters, and an end position o characters beyond the text costs floor(alpha * o)
+// on top of the DP value.  f32 arithmetic as in the reference.
+SB_HD int overhang_left_cost(int j, float alpha, int mo) {
+  const int jm = (mo >= 0 && mo < j) ? mo : j;
+  return (int)floorf((float)jm * alpha) + (j - jm);
+}
+SB_HD int overhang_overshoot_cost(float alpha, uint32_t o) { return o == 0 ? 0 : (int)floorf(alpha * (float)o); }
+
+// Record flags (GpuMatch::failed / TraceOut::failed): bit 0 traceback failed, bit 1 dropped by the
+// traced N filter, bits 8-19 pattern_start (left overhang), bits 20-31 right overshoot
+// (pattern_end = m - overshoot).
+SB_HD uint32_t pack_overhang(uint32_t pattern_start, uint32_t overshoot) {
+  return (pattern_start << 8) | (overshoot << 20);
+}
+
+// trace_one with overhang: the window has m + k columns whatever the end position, the left
+// column is L(j), columns beyond the text are wildcards (src/trace.rs:57-104); an end beyond the
+// text first steps diagonally back into it, reaching column 0 with j rows left is a left overhang.
+template <int P>
+SB_HD void trace_one_ov(const uint8_t* text, uint64_t n, bool rev, const uint8_t* pattern, int m, int k,
+                        const uint32_t* eq /*[rows][W]*/, int W, uint32_t sh0, uint32_t msk0, uint64_t end,
+                        float alpha, int mo, const ColStore& cs, uint32_t* ops, uint32_t ops_words, TraceOut& out) {
+  const int pad = 32 * W - m;
+  const uint64_t fill = (uint64_t)m + (uint64_t)k;
+  const uint64_t off = end > fill ? end - fill : 0;
+  const uint32_t slice = (uint32_t)((end < n ? end : n) - off);
+  const uint32_t wlen = (uint32_t)(end - off);
+  const uint32_t cols = (uint32_t)fill > wlen ? (uint32_t)fill : wlen;
+  // column 0: vertical deltas of L(j)
+  for (int w = 0; w < W; w++) cs.at((0 * W + w) * 2) = 0, cs.at((0 * W + w) * 2 + 1) = 0;
+  for (int j = 0; j < m; j++)
+    if (overhang_left_cost(j + 1, alpha, mo) - overhang_left_cost(j, alpha, mo)) {
+      const int b = pad + j;
+      cs.at((0 * W + (b >> 5)) * 2) |= 1u << (b & 31);
+    }
+  for (uint32_t i = 1; i <= cols; i++) {
+    const bool wild = i > slice;
+    const uint8_t tc = wild ? 0 : text_at_dir(text, n, rev, off + i - 1);
+    const uint32_t row = ((uint32_t)tc >> sh0) & (msk0 & 0xFFu);
+    const uint32_t* e = eq + row * W;
+    uint32_t carry = 0, phc = 0, mhc = 0;
+    for (int w = 0; w < W; w++) {
+      const uint32_t pv = cs.at(((i - 1) * W + w) * 2), mv = cs.at(((i - 1) * W + w) * 2 + 1);
+      const uint32_t x = (wild ? 0xFFFFFFFFu : e[w]) | mv;
+      const uint32_t t = x & pv;
+      const uint64_t sum = (uint64_t)t + pv + carry;
+      const uint32_t u = (uint32_t)sum;
+      carry = (uint32_t)(sum >> 32);
+      const uint32_t d0 = (u ^ pv) | x;
+      const uint32_t ph = mv | ~(d0 | pv);
+      const uint32_t mh = pv & d0;
+      const uint32_t ph1 = (ph << 1) | phc;
+      const uint32_t mh1 = (mh << 1) | mhc;
+      phc = ph >> 31;
+      mhc = mh >> 31;
+      cs.at((i * W + w) * 2) = mh1 | ~(d0 | ph1);
+      cs.at((i * W + w) * 2 + 1) = ph1 & d0;
+    }
+  }
+  // D[j][i]: row 0 is 0; otherwise the sum of the column's vertical deltas of rows 1..j
+  auto cost = [&](int j, uint32_t i) -> int {
+    if (j == 0) return 0;
+    int bits = pad + j, v = 0;
+    for (int w = 0; w < W && bits > 0; w++) {
+      const uint32_t msk = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+      v += popc32(cs.at((i * W + w) * 2) & msk) - popc32(cs.at((i * W + w) * 2 + 1) & msk);
+      bits -= 32;
+    }
+    return v;
+  };
+  for (uint32_t w = 0; w < ops_words; w++) ops[w] = 0;
+  int j = m;
+  uint32_t i = wlen;
+  int g = cost(j, i);
+  int total = g;
+  uint32_t pattern_start = 0, overshoot = 0;
+  out.failed = 0;
+  if (i > slice) {  // src/trace.rs:298-309
+    overshoot = i - slice;
+    total += overhang_overshoot_cost(alpha, overshoot);
+    i -= overshoot;
+    j -= (int)overshoot;
+  }
+  uint32_t nops = 0;
+  const uint32_t max_ops = ops_words * 16;
+  while (j > 0) {
+    if (i == 0) {  // src/trace.rs:320-334
+      pattern_start = (uint32_t)j;
+      g -= overhang_left_cost(j, alpha, mo);
+      break;
+    }
+    uint32_t op;
+    if (cost(j - 1, i - 1) == g && trace_match<P>(pattern[j - 1], text_at_dir(text, n, rev, off + i - 1))) {
+      op = kOpEq;
+      j--, i--;
+    } else {
+      g -= 1;
+      if (cost(j - 1, i - 1) == g) {
+        op = kOpX;
+        j--, i--;
+      } else if (cost(j, i - 1) == g) {
+        op = kOpD;
+        i--;
+      } else if (cost(j - 1, i) == g) {
+        op = kOpI;
+        j--;
+      } else {
+        out.failed = 1;
+        break;
+      }
+    }
+    if (nops < max_ops) ops[nops >> 4] |= op << ((nops & 15) * 2);
+    nops++;
+  }
+  if (!out.failed && g != 0) out.failed = 1;  // assert_eq!(g, 0), src/trace.rs:390
+  if (nops > max_ops) {
+    out.failed = 1;
+    nops = max_ops;
+  }
+  for (uint32_t a = 0, b = nops; a + 1 < b; a++, b--) {
+    const uint32_t oa = (ops[a >> 4] >> ((a & 15) * 2)) & 3u;
+    const uint32_t ob = (ops[(b - 1) >> 4] >> (((b - 1) & 15) * 2)) & 3u;
+    ops[a >> 4] = (ops[a >> 4] & ~(3u << ((a & 15) * 2))) | (ob << ((a & 15) * 2));
+    ops[(b - 1) >> 4] = (ops[(b - 1) >> 4] & ~(3u << (((b - 1) & 15) * 2))) | (oa << (((b - 1) & 15) * 2));
+  }
+  out.cost = total;
+  out.text_start = off + i;
+  out.text_end = off + slice;
+  out.nops = nops;
+  out.failed |= pack_overhang(pattern_start, overshoot);
 }
 
 }  // namespace sb

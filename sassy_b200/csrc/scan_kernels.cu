@@ -443,6 +443,13 @@ __global__ void __launch_bounds__(128)
     const uint32_t q = (uint32_t)(slot - (unsigned long long)ti * t.nq);
     const int64_t n = (int64_t)t.lens[ti];
     if (n == 0) continue;
+    const int64_t span = (int64_t)a.m + (int64_t)a.k;
+    if (t.overhang) {  // the first m+k end positions (and those beyond the text) come from the edge kernel
+      if (n > span)
+        scan_window<W>(a, a.eq + (size_t)q * a.nrows * W, (uint32_t)slot, t.rev_flags[q] != 0, t.base + t.offs[ti],
+                       n, 0, n, span);
+      continue;
+    }
     if (t.include_pos0 && a.m <= a.k) emit_candidate(a, (uint32_t)slot, 0, a.m);
     scan_window<W>(a, a.eq + (size_t)q * a.nrows * W, (uint32_t)slot, t.rev_flags[q] != 0, t.base + t.offs[ti], n, 0,
                    n, 0);
@@ -630,6 +637,78 @@ cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cu
 #define SB_VCALL(WW) case WW: verify_kernel<WW><<<blocks, threads, 0, stream>>>(a, rev_flags); break;
     SB_VCALL(1) SB_VCALL(2) SB_VCALL(3) SB_VCALL(4) SB_VCALL(6) SB_VCALL(8) SB_VCALL(16) SB_VCALL(32)
 #undef SB_VCALL
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+namespace {
+
+template <int W>
+__global__ void __launch_bounds__(128)
+    overhang_edges_kernel(const __grid_constant__ ScanArgs a, const __grid_constant__ OverhangArgs o) {
+  const unsigned long long total = 2ull * o.nslots;
+  const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += nthreads) {
+    const uint32_t slot = (uint32_t)(id >> 1);
+    const bool right = (id & 1) != 0;
+    const uint8_t* text;
+    uint64_t n;
+    uint32_t q;
+    text_of_slot(o.text, slot, text, n, q);
+    if (n + o.steps == 0) continue;  // max_pos == 0: nothing is reported (src/search.rs:1314-1316)
+    const bool rev = o.rev_flags[q] != 0;
+    const uint32_t* __restrict__ eq = a.eq + (size_t)q * a.nrows * W;
+    const uint64_t span = (uint64_t)a.m + (uint64_t)a.k;
+    Lane<W> init;
+#pragma unroll
+    for (int w = 0; w < W; w++) init.pv[w] = o.init_pv[w], init.mv[w] = 0;
+    uint32_t wild[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) wild[w] = 0xFFFFFFFFu;
+    if (!right) {
+      // end positions 0 .. min(n, m+k) from the overhang left column
+      if (o.left_total <= a.k) emit_candidate(a, slot, 0, o.left_total);
+      Lane<W> s = init;
+      const uint64_t lim = n < span ? n : span;
+      for (uint64_t i = 0; i < lim; i++) {
+        const uint8_t c = text_at_dir(text, n, rev, i);
+        myers_step<W>(s, eq + (((uint32_t)c >> a.sh0) & (a.msk0 & 0xFFu)) * W);
+        const int sc = lane_score<W>(s);
+        if (sc <= a.k) emit_candidate(a, slot, i + 1, sc);
+      }
+    } else if (o.steps > 0) {
+      // end positions n+1 .. n+steps: wildcard columns, + floor(alpha * overshoot)
+      const uint64_t w0 = n > span ? n - span : 0;
+      Lane<W> s;
+      if (w0 == 0)
+        s = init;
+      else
+        lane_reset<W>(s, a.m);
+      for (uint64_t i = w0; i < n; i++) {
+        const uint8_t c = text_at_dir(text, n, rev, i);
+        myers_step<W>(s, eq + (((uint32_t)c >> a.sh0) & (a.msk0 & 0xFFu)) * W);
+      }
+      for (uint32_t ov = 1; ov <= o.steps; ov++) {
+        myers_step<W>(s, wild);
+        const int sc = lane_score<W>(s) + overhang_overshoot_cost(o.alpha, ov);
+        if (sc <= a.k) emit_candidate(a, slot, n + ov, sc);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_overhang_edges(int W, const ScanArgs& a, const OverhangArgs& o, cudaStream_t stream) {
+  const unsigned long long total = 2ull * o.nslots;
+  if (total == 0) return cudaSuccess;
+  const unsigned threads = 128;
+  const unsigned blocks = (unsigned)std::min<unsigned long long>((total + threads - 1) / threads, 148ull * 16);
+  switch (W) {
+#define SB_OCALL(WW) case WW: overhang_edges_kernel<WW><<<blocks, threads, 0, stream>>>(a, o); break;
+    SB_OCALL(1) SB_OCALL(2) SB_OCALL(3) SB_OCALL(4) SB_OCALL(6) SB_OCALL(8) SB_OCALL(16) SB_OCALL(32)
+#undef SB_OCALL
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

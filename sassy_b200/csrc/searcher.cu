@@ -36,8 +36,12 @@ std::string Match::cigar() const {
 Searcher::Searcher(const std::string& alphabet, bool rc, float alpha, int device) : rc_(rc) {
   profile_ = parse_alphabet(alphabet);
   if (profile_ < 0) throw std::invalid_argument("Unsupported alphabet: " + alphabet);
-  if (!isnan(alpha))
-    throw std::invalid_argument("overhang (alpha) is outside the GPU search path; pass NAN");
+  if (!isnan(alpha)) {
+    // reference Searcher::_overhang_check (src/search.rs:373-383)
+    if (profile_ != kIupac) throw std::invalid_argument("Overhang is not supported for this profile (use iupac)");
+    if (!(alpha >= 0.f && alpha <= 1.f)) throw std::invalid_argument("Alpha must be in range 0.0 <= alpha <= 1.0");
+    alpha_ = alpha;
+  }
   engine_.reset(new Engine(profile_, device));
 }
 
@@ -64,6 +68,8 @@ SearchOpts Searcher::v1_opts(bool all_minima) const {
   o.only_best = only_best_;
   o.max_n_frac = max_n_frac_;
   o.n_endpoint = true;  // v1 filters end points before the traceback as well (src/search.rs:907-919)
+  o.alpha = alpha_;
+  o.max_overhang = max_overhang_;
   return o;
 }
 
@@ -86,8 +92,9 @@ std::vector<Match> Searcher::convert_v1(const MatchSet& ms, size_t n_pat, size_t
     mm.pattern_idx = q % n_pat;
     mm.text_idx = ti;
     mm.cost = g.cost;
-    mm.pattern_start = without_trace_ ? ~0ull : 0;
-    mm.pattern_end = m;
+    // overhang: rows of the pattern hanging over the text ends (scan_core.cuh pack_overhang)
+    mm.pattern_start = without_trace_ ? ~0ull : (uint64_t)((g.failed >> 8) & 0xFFFu);
+    mm.pattern_end = m - (uint64_t)(g.failed >> 20);
     if (q < n_pat) {
       mm.strand = kFwd;
       mm.text_start = g.text_start;
@@ -277,6 +284,7 @@ std::vector<Match> Searcher::search_encoded(const EncodedPatterns& enc, const De
   std::vector<Query> qs(enc.n_queries());
   for (size_t q = 0; q < qs.size(); q++) qs[q] = Query{&enc.bytes[q * enc.m], false};
   const int kk = (int)std::min<size_t>(k, 1u << 20);
+  if (alpha_ >= 0.f) throw std::invalid_argument("overhang with encoded patterns is outside the GPU search path");
   // the v2 engine knows all_minima and max_n_frac only (traced filter, general.rs:399-402);
   // without_trace / only_best_match do not reach it (src/search.rs:415-433)
   SearchOpts o;
@@ -614,6 +622,12 @@ int sassy_gpu_set_trace(sassy_SearcherType* searcher, int trace) {
 int sassy_gpu_set_only_best_match(sassy_SearcherType* searcher, int on) {
   if (!searcher) return 1;
   searcher->s.set_only_best_match(on != 0);
+  return 0;
+}
+
+int sassy_gpu_set_max_overhang(sassy_SearcherType* searcher, int max_overhang) {
+  if (!searcher) return 1;
+  searcher->s.set_max_overhang(max_overhang);
   return 0;
 }
 

@@ -69,6 +69,7 @@ class Searcher {
   void set_trace(bool trace) { without_trace_ = !trace; }          // with_trace / without_trace / set_trace
   void set_only_best_match(bool on) { only_best_ = on; }          // only_best_match
   void set_max_n_frac(float f) { max_n_frac_ = (f == 1.0f) ? -1.f : f; }  // set_max_n_frac; 1.0 disables
+  void set_max_overhang(int max_overhang) { max_overhang_ = max_overhang < 0 ? -1 : max_overhang; }  // with_max_overhang
   bool without_trace() const { return without_trace_; }
 
   // search_with_fn (src/search.rs:767-784) with the end filter the reference ships
@@ -118,6 +119,8 @@ class Searcher {
   bool without_trace_ = false;
   bool only_best_ = false;
   float max_n_frac_ = -1.f;
+  float alpha_ = -1.f;      // overhang cost (Iupac only), < 0 = off
+  int max_overhang_ = -1;
   std::unique_ptr<Engine> engine_;
   MatchSet ms_;
 };

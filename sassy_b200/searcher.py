@@ -182,8 +182,8 @@ def _as_buffer(b):
 class Searcher:
     """`Searcher(alphabet, rc=True, alpha=None, max_n_frac=None)` as in src/python.rs:31-65.
 
-    `device` selects the CUDA device (default: env SASSY_B200_DEVICE or 0).  Overhang
-    (`alpha`) is outside the GPU path and raises."""
+    `device` selects the CUDA device (default: env SASSY_B200_DEVICE or 0).  `alpha` enables
+    overhang (iupac only): pattern characters hanging over a text end cost alpha each."""
 
     def __init__(self, alphabet: str, rc: bool = True, alpha: Optional[float] = None,
                  max_n_frac: Optional[float] = None, device: Optional[int] = None):
@@ -195,14 +195,16 @@ class Searcher:
             raise ValueError(f"Unsupported alphabet: {alphabet}")  # src/python.rs:52-57
         if a == "ascii":
             rc = False  # src/python.rs:40-42
-        if alpha is not None:
-            raise NotImplementedError("overhang (alpha) is outside the GPU search path")
+        if alpha is not None and a != "iupac":
+            raise ValueError("Overhang is only supported for the iupac alphabet")  # src/search.rs:373-379
+        if alpha is not None and not (0.0 <= alpha <= 1.0):
+            raise ValueError("Alpha must be in range 0.0 <= alpha <= 1.0")
         if device is None:
             device = int(os.environ.get("SASSY_B200_DEVICE", "0"))
         self.alphabet = a
         self.rc = bool(rc)
         self.device = device
-        h = self._lib.sassy_gpu_searcher(a.encode(), self.rc, math.nan, device)
+        h = self._lib.sassy_gpu_searcher(a.encode(), self.rc, math.nan if alpha is None else float(alpha), device)
         if not h:
             raise RuntimeError(_native.last_error())
         self._h = h
@@ -222,6 +224,11 @@ class Searcher:
 
     def without_max_n_frac(self):
         return self.set_max_n_frac(1.0)
+
+    def with_max_overhang(self, max_overhang: Optional[int]):
+        """Searcher::with_max_overhang (src/search.rs:436-439)."""
+        self._lib.sassy_gpu_set_max_overhang(self._h, -1 if max_overhang is None else int(max_overhang))
+        return self
 
     def set_trace(self, trace: bool):
         """Searcher::set_trace / with_trace / without_trace: without trace a match carries the end

@@ -17,21 +17,21 @@ def _conv(ms):
 
 
 class OracleSearcher:
-    def __init__(self, alphabet, rc=True, max_n_frac=None):
-        self.alphabet, self.rc, self.max_n_frac = alphabet, rc, max_n_frac
+    def __init__(self, alphabet, rc=True, max_n_frac=None, alpha=None):
+        self.alphabet, self.rc, self.max_n_frac, self.alpha = alphabet, rc, max_n_frac, alpha
 
     def search(self, p, t, k):
-        return _conv(oracle.search(self.alphabet, p, t, k, rc=self.rc, max_n_frac=self.max_n_frac))
+        return _conv(oracle.search(self.alphabet, p, t, k, rc=self.rc, max_n_frac=self.max_n_frac, alpha=self.alpha))
 
     def search_all(self, p, t, k):
-        return _conv(oracle.search(self.alphabet, p, t, k, rc=self.rc, all_minima=True, max_n_frac=self.max_n_frac))
+        return _conv(oracle.search(self.alphabet, p, t, k, rc=self.rc, all_minima=True, max_n_frac=self.max_n_frac, alpha=self.alpha))
 
     def search_with_pam(self, p, t, k, pam, all_minima=True):
         return _conv(oracle.search(self.alphabet, p, t, k, rc=self.rc, all_minima=all_minima, pam=pam,
                                    max_n_frac=self.max_n_frac))
 
     def search_many(self, pats, texts, k, threads=0, mode="single"):
-        return _conv(oracle.search_many(self.alphabet, pats, texts, k, rc=self.rc, max_n_frac=self.max_n_frac))
+        return _conv(oracle.search_many(self.alphabet, pats, texts, k, rc=self.rc, max_n_frac=self.max_n_frac, alpha=self.alpha))
 
     def encode_patterns(self, pats):
         return list(pats)
@@ -40,5 +40,5 @@ class OracleSearcher:
         return _conv(oracle.search_encoded(self.alphabet, enc, t, k, rc=self.rc, max_n_frac=self.max_n_frac))
 
 
-def make(alphabet, rc, max_n_frac):
-    return OracleSearcher(alphabet, rc, max_n_frac)
+def make(alphabet, rc, max_n_frac, alpha=None):
+    return OracleSearcher(alphabet, rc, max_n_frac, alpha)

@@ -173,3 +173,76 @@ def test_gpu_search_texts_and_patterns():
         want = oracle.search_many("dna", pats, [bytes(t)], 2, rc=True, **opts)
         got = so.search_patterns(pats, bytes(t), 2)
         assert list(map(key, got)) == list(map(key, want)), opts
+
+
+def okey(m):
+    return (m.pattern_idx, m.text_idx, m.text_start, m.text_end, m.pattern_start, m.pattern_end, m.cost, m.strand,
+            m.cigar)
+
+
+def test_gpu_overhang_reference_kats():
+    import sassy_b200
+    s = sassy_b200.Searcher("iupac", rc=False, alpha=0.5)
+    ms = s.search(b"GGGGAAAA", b"TTTTTTTTTTTTTTTTGGGG", 4)                      # src/search.rs:2430-2456
+    assert len(ms) == 2 and any(m.text_end == 20 and m.pattern_end == 3 and m.cost == 2 for m in ms)
+    m = s.search(b"ATCGATCG", b"ATCGGGGGGGGGG", 2)[0]                             # :2929-2942
+    assert (m.pattern_start, m.pattern_end, m.text_start, m.text_end, m.cost, m.cigar) == (4, 8, 0, 4, 2, "4=")
+    m = s.search(b"ATCGATCG", b"GGGGGGGATCG", 2)[0]                               # :2944-2958
+    assert (m.pattern_start, m.pattern_end, m.text_start, m.text_end, m.cost, m.cigar) == (0, 4, 7, 11, 2, "4=")
+    s.set_max_n_frac(0.0)
+    assert len(s.search_all(b"AAAA", b"GGGGGG", 2)) == 4                          # src/n_filter.rs:66-82
+    with pytest.raises(ValueError):
+        sassy_b200.Searcher("dna", alpha=0.5)                                     # src/search.rs:2344-2348
+
+
+def test_gpu_overhang_fuzz():
+    import sassy_b200
+    rng = random.Random(36)
+    cache = {}
+    for it in range(200):
+        m = rng.choice([3, 8, 20, 33, 70])
+        n = rng.choice([0, 1, 2, 5, 17, 40, 200, 3000, 70_000]) if it % 3 else rng.randrange(0, 400)
+        k = rng.randrange(0, max(1, m // 3) + 1)
+        p, t = planted(rng, m, max(n, 1), k)
+        t = t[:n]
+        # pattern prefixes / suffixes at the text ends: the overhang cases
+        if n >= 4 and rng.random() < 0.7:
+            cut = rng.randrange(1, min(m, n))
+            t = (p[cut:] + t[len(p) - cut:])[:n] if rng.random() < 0.5 else (t[:n - cut] + p[:cut])[:n]
+        alpha = rng.choice([0.0, 0.3, 0.5, 1.0])
+        mo = rng.choice([None, None, 0, 2, 5])
+        opts = dict(without_trace=rng.random() < 0.25, only_best=rng.random() < 0.25,
+                    max_n_frac=rng.choice([None, None, 0.2]))
+        rc = rng.random() < 0.7
+        ck = (alpha, rc, opts["without_trace"], opts["only_best"], opts["max_n_frac"])
+        if ck not in cache:
+            s = sassy_b200.Searcher("iupac", rc=rc, alpha=alpha, max_n_frac=opts["max_n_frac"])
+            if opts["without_trace"]:
+                s.without_trace()
+            if opts["only_best"]:
+                s.only_best_match()
+            cache[ck] = s
+        s = cache[ck].with_max_overhang(mo)
+        for allm in (False, True):
+            want = oracle.search("iupac", p, t, k, rc=rc, all_minima=allm, alpha=alpha, max_overhang=mo, **opts)
+            got = s.search_all(p, t, k) if allm else s.search(p, t, k)
+            assert list(map(okey, got)) == list(map(okey, want)), (p, t, k, alpha, mo, rc, allm, opts)
+
+
+def test_gpu_overhang_search_many():
+    import sassy_b200
+    rng = random.Random(37)
+    s = sassy_b200.Searcher("iupac", rc=True, alpha=0.5)
+    for it in range(15):
+        m = rng.randrange(4, 40)
+        pats = [rand_seq(rng, m) for _ in range(rng.randrange(1, 8))]
+        texts = []
+        for _ in range(rng.randrange(1, 30)):
+            t = rand_seq(rng, rng.randrange(0, 300))
+            p = pats[rng.randrange(len(pats))]
+            cut = rng.randrange(1, m)
+            texts.append((p[cut:] + t) if rng.random() < 0.5 else (t + p[:cut]))
+        k = rng.randrange(0, m // 3 + 1)
+        want = oracle.search_many("iupac", pats, texts, k, rc=True, alpha=0.5)
+        got = s.search_many(pats, texts, k)
+        assert list(map(okey, got)) == list(map(okey, want)), (it, m, k)

@@ -89,3 +89,58 @@ def test_search_many_equals_single_searches():
                 for x in oracle.search("dna", p, t, k, rc=True):
                     want.append((pi, ti, x.text_start, x.text_end, x.cost, x.strand, x.cigar))
         assert [(x.pattern_idx, x.text_idx, x.text_start, x.text_end, x.cost, x.strand, x.cigar) for x in got] == want
+
+
+# ---- overhang (alpha): known answers of the reference's own tests ------------------------------
+
+def _ends(ms):
+    """(end position incl. overshoot, cost) of untraced matches: end = text_end + (m - pattern_end)."""
+    return [(m.text_end, m.pattern_end, m.cost) for m in ms]
+
+
+def test_overhang_reference_kats():
+    S = lambda p, t, k, **kw: oracle.search("iupac", p, t, k, alpha=0.5, **kw)
+    # src/search.rs:2372-2398 overshoot_simple_prefix: end position 3 with cost <= 2
+    assert (3, 8, 2) in _ends(S(b"AAAAGGGG", b"GGGGTTTTTTTTTTTTTTTT", 2, all_minima=True, without_trace=True))
+    # :2400-2428 overshoot_simple_suffix: end position 24 = text end 20 + 4 pattern characters beyond it
+    assert (20, 4, 2) in _ends(S(b"GGGGAAAA", b"TTTTTTTTTTTTTTTTGGGG", 2, all_minima=True, without_trace=True))
+    # :2430-2456 overshoot_simple_suffix_local_minima
+    ms = S(b"GGGGAAAA", b"TTTTTTTTTTTTTTTTGGGG", 4)
+    assert len(ms) == 2 and any(m.text_end == 20 and m.pattern_end == 3 and m.cost == 2 for m in ms)
+    # :2458-2490 overshoot_test_prefix_and_suffix: ends 3 and 13, cost 2 each
+    e = _ends(S(b"AAAAGGGG", b"GGGGGAAAAA", 2, all_minima=True, without_trace=True))
+    assert (3, 8, 2) in e and (10, 5, 2) in e
+    # :2929-2942 test_pattern_trace_path_with_overhang_prefix: path (4,0) (5,1) (6,2) (7,3)
+    m = S(b"ATCGATCG", b"ATCGGGGGGGGGG", 2)[0]
+    assert (m.pattern_start, m.pattern_end, m.text_start, m.text_end, m.cost, m.cigar) == (4, 8, 0, 4, 2, "4=")
+    # :2944-2958 ..._suffix: path (0,7) (1,8) (2,9) (3,10)
+    m = S(b"ATCGATCG", b"GGGGGGGATCG", 2)[0]
+    assert (m.pattern_start, m.pattern_end, m.text_start, m.text_end, m.cost, m.cigar) == (0, 4, 7, 11, 2, "4=")
+    # :3022-3058 test_case4: a match ending at 1 with cost 1, in both modes
+    assert any(m.text_end == 1 and m.cost == 1 for m in S(b"ATC", b"CGGGGGG", 3))
+    assert any(m.text_end == 1 and m.cost == 1 for m in S(b"ATC", b"CGGGGGG", 3, all_minima=True))
+    # src/n_filter.rs:66-82 n_filter_full_overhang_match: the overhang's wildcards do not count as N
+    assert len(S(b"AAAA", b"GGGGGG", 2, all_minima=True, max_n_frac=0.0)) == 4
+    # src/search.rs:2344-2348: Dna has no overhang
+    try:
+        oracle.search("dna", b"ACGT", b"ACGT", 1, alpha=0.5)
+    except oracle.OracleError:
+        pass
+    else:
+        raise AssertionError("overhang must be rejected for dna")
+
+
+def test_overhang_is_plain_search_away_from_the_ends():
+    """Matches whose alignment stays m+k characters away from both text ends do not change."""
+    rng = random.Random(9)
+    for _ in range(60):
+        m = rng.randrange(6, 30)
+        k = rng.randrange(0, m // 3 + 1)
+        n = rng.randrange(4 * m, 600)
+        p, t = planted(rng, m, n, k)
+        t = t[:n]
+        a = oracle.search("iupac", p, t, k, rc=True, all_minima=True)
+        b = oracle.search("iupac", p, t, k, rc=True, all_minima=True, alpha=rng.choice([0.0, 0.5, 1.0]))
+        inner = lambda ms: [x for x in ms if x.text_start > m + k and x.text_end < n - (m + k) and x.pattern_start == 0
+                            and x.pattern_end == m]
+        assert inner(a) == inner(b)
