@@ -159,3 +159,12 @@ def test_crispr_reference_counts(tmp_path):
     thr = 3.0 / 17.0
     assert _crispr_counts(tmp_path, max_n_frac=thr + 0.01)["n_frac"] == 1
     assert _crispr_counts(tmp_path, max_n_frac=thr - 0.01)["n_frac"] == 0
+
+
+def test_overhang_flag(tmp_path):
+    """--overhang (bin/grep.rs:76-78) reaches the searcher: a pattern hanging over the end of a read."""
+    fa = tmp_path / "reads.fa"
+    fa.write_text(">r1\nGGGGGGGATCG\n>r2\nATCGGGGGGGGGG\n")
+    out = run(["search", "-p", "ATCGATCG", "-k", "2", "--no-rc", "--overhang", "0.5", str(fa)])
+    assert out == (cli.TSV_HEADER + "pattern\tr1\t2\t+\t7\t11\tATCG\t4=\n" + "pattern\tr2\t2\t+\t0\t4\tATCG\t4=\n")
+    assert run(["search", "-p", "ATCGATCG", "-k", "2", "--no-rc", str(fa)]) == cli.TSV_HEADER

@@ -9,9 +9,9 @@ from tests.test_cli import _crispr_counts, make_inputs, run
 pytestmark = pytest.mark.gpu
 
 
-def gpu_make(alphabet, rc, max_n_frac):
+def gpu_make(alphabet, rc, max_n_frac, alpha=None):
     import sassy_b200
-    return sassy_b200.Searcher(alphabet, rc=rc, max_n_frac=max_n_frac)
+    return sassy_b200.Searcher(alphabet, rc=rc, alpha=alpha, max_n_frac=max_n_frac)
 
 
 def test_cli_search_filter_on_gpu(tmp_path):
@@ -22,6 +22,7 @@ def test_cli_search_filter_on_gpu(tmp_path):
                  ["search", "-f", dpf, "-k", "2", "-a", "dna", "--sam", dfa],
                  ["search", "-f", pf, "-k", "1", "--no-rc", "--pattern-batch-size", "3", fa],
                  ["filter", "-f", pf, "-k", "1", "-v", fa],
+                 ["search", "-f", pf, "-k", "3", "--overhang", "0.5", fa],
                  ["search", "-p", pats[2][1].decode(), "-k", "3", "--max-n-frac", "0.0", fa]):
         assert run(argv, gpu_make) == run(argv, cli_backend.make), argv
     a = run(["search", "-f", pf, "-k", "2", "--v2", fa], gpu_make)

@@ -246,3 +246,23 @@ def test_gpu_overhang_search_many():
         want = oracle.search_many("iupac", pats, texts, k, rc=True, alpha=0.5)
         got = s.search_many(pats, texts, k)
         assert list(map(okey, got)) == list(map(okey, want)), (it, m, k)
+
+
+def test_reference_c_abi_with_alpha():
+    """The reference's own four symbols (c/sassy.h:38-63) with overhang: sassy_searcher(alphabet, rc,
+    alpha) + search, records with pattern_start / pattern_end inside the pattern."""
+    import ctypes
+    from sassy_b200 import _native
+    lib = _native.load()
+    h = lib.sassy_searcher(b"iupac", False, 0.5)
+    assert h
+    out = ctypes.POINTER(_native.CMatch)()
+    p, t = b"ATCGATCG", b"ATCGGGGGGGGGG"
+    n = lib.search(h, p, len(p), t, len(t), 2, ctypes.byref(out))
+    want = oracle.search("iupac", p, t, 2, alpha=0.5)
+    got = [(out[i].text_start, out[i].text_end, out[i].pattern_start, out[i].pattern_end, out[i].cost, out[i].strand)
+           for i in range(n)]
+    assert got == [(w.text_start, w.text_end, w.pattern_start, w.pattern_end, w.cost, 0) for w in want]
+    assert got[0] == (0, 4, 4, 8, 2, 0)  # src/search.rs:2929-2942
+    lib.sassy_matches_free(out, n)
+    lib.sassy_searcher_free(h)
