@@ -342,16 +342,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_wall = []  # host wall time of every timed step (diagnostics: p50 / max next to the mean)
+
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             ms = fn()
         barrier()
         scan_ms, total_ms, launches = [], [], 0
+        step_wall.clear()
         t0 = time.perf_counter()
+        tp = t0
         for it in range(steps):
             ms = fn()
             if sampler is not None:
                 sampler.sample(it)
+            tn = time.perf_counter()
+            step_wall.append((tn - tp) * 1e3)
+            tp = tn
             st = s.stats()
             scan_ms.append(st["scan_ms"])
             total_ms.append(st["total_ms"])
@@ -368,8 +375,15 @@ def main():
     if not uuid.startswith("GPU-"):
         uuid = "GPU-" + uuid
     sampler = ClockSampler(uuid) if rank == 0 else None
+    if sampler is not None:  # the first NVML queries of a process can take long: not inside the timed region
+        sampler.sample(0)
+        sampler.sm.clear(), sampler.power.clear(), sampler.reasons.clear()
+        sampler._last = 0.0
     el, matches, scan_ms, total_ms, launches, st = timed(step_resident, args.steps, args.warmup, sampler)
     clocks = sampler.result() if rank == 0 else None
+    wall_sorted = sorted(step_wall)
+    step_stats = {"p50": wall_sorted[len(wall_sorted) // 2], "max": wall_sorted[-1],
+                  "p90": wall_sorted[int(len(wall_sorted) * 0.9)]} if wall_sorted else None
 
     total_bytes = n * world
     value = total_bytes * args.steps / el / 1e9
@@ -378,7 +392,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         e_steps = max(2, min(args.steps, 5))
-        e_el, e_matches, _, _, _, _ = timed(step_e2e, e_steps, 1)
+        e_el, e_matches, _, _, _, _ = timed(step_e2e, e_steps, 2)  # 2 warm-ups: buffers, pool and the pack-rate estimate settle
         if hasattr(e_matches, "records") and hasattr(matches, "records"):
             import numpy as np
             same = np.array_equal(e_matches.records, matches.records) and e_matches._ops == matches._ops
@@ -454,7 +468,7 @@ def main():
                                    if pg is not None else "a host-staged NCCL all-gather")) if world > 1 else "single GPU"},
         "matches": len(matches), "matches_per_s": len(matches) * args.steps / el,
         "gchar_pattern_per_s": total_bytes * len(pats) * args.steps / el / 1e9,
-        "device_ms_per_step": sum(total_ms) / len(total_ms),
+        "device_ms_per_step": sum(total_ms) / len(total_ms), "step_wall_ms": step_stats,
         "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
     }
     sys.stdout.flush()
