@@ -36,7 +36,11 @@ WORKLOADS = {
     "c2": ("dna", 1, 20, 2, 3_000_000_000, "Dna, 1 pattern len=20, k=2, 3 GB synthetic ACGT (BASELINE configs[1])"),
     "c3": ("iupac", 1024, 23, 4, 3_000_000_000, "Iupac, 1024 encoded patterns len=23 (20nt+NGG), k=4, 3 GB (BASELINE configs[2])"),
     "c4": ("dna", 1, 100, 8, 3_000_000_000, "Dna, 1 pattern len=100, k=8, 3 GB synthetic ACGT (BASELINE configs[3])"),
+    # pattern shards: every rank holds the whole text and searches patterns rank, rank + N, ...;
+    # 100 000 x 3 GB is 3e14 character-pattern steps (minutes per step): use --patterns to bound a run
+    "c5": ("iupac", 100_000, 23, 3, 3_000_000_000, "Iupac, 100k encoded patterns len=23 (20nt+NGG), k=3, 3 GB, patterns sharded over the GPUs (BASELINE configs[4])"),
 }
+PATTERN_SHARDED = {"c5"}
 METRIC = "GB/s text scanned"
 
 
@@ -285,12 +289,17 @@ def main():
         n = args.text_bytes
     if args.patterns:
         n_patterns = args.patterns
-    pats = make_patterns(profile, n_patterns, m)
+    all_pats = make_patterns(profile, n_patterns, m)
     copies = 64 if n_patterns == 1 else 2
+    pshard = args.workload in PATTERN_SHARDED
+    # pattern-sharded workloads: the same text on every rank, this rank's share of the patterns
+    pats = [all_pats[i] for i in sdist.shard_indices(len(all_pats), rank, world)] if pshard else all_pats
+    if not pats:
+        raise SystemExit("fewer patterns than ranks")
 
-    # ---- inputs: text shard of this rank, generated in HBM --------------------------------
-    text_dev = synth_text_device(torch, n, 42 + rank, dev)
-    for pos, q in plant_list(pats, n, k, copies, seed=44 + rank):
+    # ---- inputs: text (shard) of this rank, generated in HBM ------------------------------
+    text_dev = synth_text_device(torch, n, 42 + (0 if pshard else rank), dev)
+    for pos, q in plant_list(all_pats[:4096], n, k, copies, seed=44 + (0 if pshard else rank)):
         text_dev[pos:pos + len(q)] = torch.tensor(list(q), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
@@ -385,7 +394,10 @@ def main():
     step_stats = {"p50": wall_sorted[len(wall_sorted) // 2], "max": wall_sorted[-1],
                   "p90": wall_sorted[int(len(wall_sorted) * 0.9)]} if wall_sorted else None
 
-    total_bytes = n * world
+    # text shards: N x n bytes scanned per step (weak scaling); pattern shards: the job is
+    # "all patterns over the n-byte text", the same total work for every N (strong scaling)
+    total_bytes = n if pshard else n * world
+    total_patterns = len(all_pats)
     value = total_bytes * args.steps / el / 1e9
     ms_per_step = el / args.steps * 1e3
 
@@ -443,11 +455,11 @@ def main():
         try:
             from oracle import cpu_port
             cores = os.cpu_count() or 1
-            sample_pats = pats[:min(len(pats), 64)]
+            sample_pats = all_pats[:min(len(all_pats), 64)]
             rate = cpu_port.calibrate(profile, sample_pats[:32], k, args.rc)
             sample_n = int(min(n, max(1 << 24, rate * cores * args.cpu_seconds / len(sample_pats))))
             sec, nm, kind = cpu_port.search_timed(profile, sample_pats, k, args.rc, host.data_ptr(), sample_n, cores)
-            cpu = {"value": sample_n / sec / 1e9 * len(sample_pats) / len(pats), "unit": "GB/s", "cores": cores,
+            cpu = {"value": sample_n / sec / 1e9 * len(sample_pats) / total_patterns, "unit": "GB/s", "cores": cores,
                    "kind": "port", "sample": f"first {sample_n} text bytes x {len(sample_pats)} patterns, {sec:.2f} s ({kind})",
                    "matches_in_sample": nm}
         except Exception as e:
@@ -455,19 +467,22 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if pshard else "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": desc, "text_bytes_per_gpu": n, "patterns": len(pats), "pattern_len": m, "k": k,
+        "config": {"workload": desc, "text_bytes_per_gpu": n, "patterns": total_patterns,
+                   "patterns_per_gpu": len(pats), "pattern_len": m, "k": k,
                    "rc": bool(args.rc), "mode": "search (local minima) + traceback",
                    "l2": "text (3 GB) is larger than L2 (126 MB); no flush needed", "variant": args.variant,
                    "row_bytes": st["row_bytes"], "rows": st["rows"], "blocks_per_sm": st["blocks_per_sm"],
                    "prefilter": {"mode": args.filter, "words": st["filter_words"], "piece_len": st["filter_len"],
                                  "fallback": st["filter_fallback"]},
-                   "sharding": ("text shards, one per rank; match records of all ranks exchanged per step by "
+                   "sharding": (("pattern shards (round-robin), text replicated; " if pshard else "text shards, one per rank; ")
+                                + "match records of all ranks exchanged per step by "
                                 + ("peer-memory stores over NVLink fused behind the traceback (%d NCCL fall-backs)" % pg.fallbacks
                                    if pg is not None else "a host-staged NCCL all-gather")) if world > 1 else "single GPU"},
         "matches": len(matches), "matches_per_s": len(matches) * args.steps / el,
-        "gchar_pattern_per_s": total_bytes * len(pats) * args.steps / el / 1e9,
+        "gchar_pattern_per_s": (n * total_patterns if pshard else total_bytes * len(pats)) * args.steps / el / 1e9,
         "device_ms_per_step": sum(total_ms) / len(total_ms), "step_wall_ms": step_stats,
         "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
     }

@@ -280,7 +280,7 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
 
   res->m.resize(sel.size());
   res->ops.assign(sel.size() * res->ops_words, 0);
-  std::vector<uint32_t> scratch((size_t)(m + k + 1) * W * 2);
+  std::vector<uint32_t> scratch((size_t)trace_words_per_match(m, k, W));
   for (size_t i = 0; i < sel.size(); i++) {
     const uint32_t qs = key_qs(sel[i]);
     ColStore cs;

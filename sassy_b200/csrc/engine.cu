@@ -402,7 +402,7 @@ uint64_t Engine::post_process(const PostCtx& c, const SearchOpts& opts, uint64_t
   }
   uint64_t nsel = 0;
   if (bound > 0) {
-    const uint64_t words_per_match = opts.without_trace ? 0 : (uint64_t)(m + k + 1) * W * 2;
+    const uint64_t words_per_match = opts.without_trace ? 0 : trace_words_per_match(m, k, W);
     const uint64_t max_scratch_words = (512ull << 20) / 4;  // 512 MiB of scratch per slice
     uint64_t slice = bound;
     while (slice > 1 && trace_threads(slice) * words_per_match > max_scratch_words) slice = (slice + 1) / 2;
@@ -607,7 +607,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   // synchronisation; longer lists set the `big` flag and take the general path below.
   int end_bit = kPosBits;
   while ((1ull << (end_bit - kPosBits)) < nq) end_bit++;
-  const uint64_t words_per_match = (uint64_t)(m + k + 1) * W * 2;
+  const uint64_t words_per_match = trace_words_per_match(m, k, W);
   const bool small_path = words_per_match <= 4096 && !opts.special();
   unsigned long long* d_big = d_counts + 3;
   if (small_path) {

@@ -231,7 +231,7 @@ cudaError_t launch_trace(const TraceArgs& t0, cudaStream_t stream) {
   const uint64_t blocks = trace_threads(t.count) / threads;
   // the per-match column store ((m+k+1) columns x W words x 2) lives in shared memory when a
   // block's share fits the default 48 KB: every column is read back by the greedy walk
-  const size_t smem = t.costs ? 0 : (size_t)(t.m + t.k + 1) * t.W * 2 * sizeof(uint32_t) * threads;
+  const size_t smem = t.costs ? 0 : (size_t)trace_words_per_match(t.m, t.k, t.W) * sizeof(uint32_t) * threads;
   t.smem_cols = (smem > 0 && smem <= 48 * 1024) ? 1 : 0;
   const size_t dyn = t.smem_cols ? smem : 0;
   switch (t.profile) {

@@ -687,55 +687,47 @@ struct ColStore {
   SB_HD uint32_t& at(uint32_t slot) const { return base[(uint64_t)slot * stride]; }
 };
 
-template <int P>
-SB_HD int col_cost(const ColStore& cs, int W, int pad, int j, uint32_t i) {
-  // D[j][i]: column 0 is j; row 0 is 0; otherwise sum of vertical deltas of rows 1..j.
-  if (j == 0) return 0;
-  if (i == 0) return j;
-  int bits = pad + j;  // rows below `pad` are wildcards with delta 0
-  int v = 0;
-  for (int w = 0; w < W && bits > 0; w++) {
-    const uint32_t msk = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
-    const uint32_t pv = cs.at((i * W + w) * 2), mv = cs.at((i * W + w) * 2 + 1);
-#if defined(__CUDA_ARCH__)
-    v += __popc(pv & msk) - __popc(mv & msk);
-#else
-    v += __builtin_popcount(pv & msk) - __builtin_popcount(mv & msk);
-#endif
-    bits -= 32;
-  }
-  return v;
-}
-
 SB_HD uint8_t text_at_dir(const uint8_t* text, uint64_t n, bool rev, uint64_t i) {
   return rev ? text[n - 1 - i] : text[i];
 }
 
+// Column store of the traceback: per column i (0..m+k) and word w the vertical deltas (pv, mv);
+// for patterns of more than 4 words also the horizontal deltas (ph, mh) of the step that produced
+// the column, so that the greedy walk looks its three neighbours up with single-bit reads instead
+// of prefix popcounts over up to 32 words (a 1000-character pattern walks 1000 steps).
+SB_HD int trace_fields(int W) { return W > 4 ? 4 : 2; }
+SB_HD uint64_t trace_words_per_match(int m, int k, int W) {
+  return (uint64_t)(m + k + 1) * (uint64_t)W * (uint64_t)trace_fields(W);
+}
+
+// +1 / -1 / 0 from a (plus, minus) pair of delta words at bit b
+SB_HD int delta_at(uint32_t p, uint32_t mn, int bit) { return (int)((p >> bit) & 1u) - (int)((mn >> bit) & 1u); }
+
 // `ops` receives 2-bit op codes, 16 per word, in pattern direction.
-// `tmp` (W words * 2) is scratch for the running column.
 template <int P>
 SB_HD void trace_one(const uint8_t* text, uint64_t n, bool rev, const uint8_t* pattern, int m, int k,
                      const uint32_t* eq /*[rows][W]*/, int W, uint32_t sh0, uint32_t msk0,
                      uint64_t end, const ColStore& cs, uint32_t* ops, uint32_t ops_words, TraceOut& out) {
   const int pad = 32 * W - m;
+  const int F = trace_fields(W);
+  const bool wide = F == 4;
   const uint64_t fill = (uint64_t)m + (uint64_t)k;
   const uint64_t off = end > fill ? end - fill : 0;
   const uint32_t wlen = (uint32_t)(end - off);
-  // column 0 state lives in slots [0, 2W); columns 1..wlen follow.
+  // previous column: registers for the first 4 words, a local array beyond
+  constexpr int kRegW = 4, kMaxW = 32;
+  uint32_t ppv[kRegW], pmv[kRegW];
+  uint32_t lpv[kMaxW - kRegW], lmv[kMaxW - kRegW];
   for (int w = 0; w < W; w++) {
     const int lo = pad - 32 * w;
-    cs.at((0 * W + w) * 2) = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
-    cs.at((0 * W + w) * 2 + 1) = 0;
+    const uint32_t v0 = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
+    if (w < kRegW)
+      ppv[w] = v0, pmv[w] = 0;
+    else
+      lpv[w - kRegW] = v0, lmv[w - kRegW] = 0;
+    cs.at((0 * W + w) * F) = v0;  // column 0: D[j][0] = j
+    cs.at((0 * W + w) * F + 1) = 0;
   }
-  // previous column: in registers for W <= 4 (the store is then write-only in this loop)
-  constexpr int kRegW = 4;
-  uint32_t ppv[kRegW], pmv[kRegW];
-  for (int w = 0; w < kRegW; w++) {
-    const int lo = pad - 32 * w;
-    ppv[w] = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
-    pmv[w] = 0;
-  }
-  const bool in_regs = W <= kRegW;
   for (uint32_t i = 1; i <= wlen; i++) {
     const uint8_t tc = text_at_dir(text, n, rev, off + i - 1);
     const uint32_t row = ((uint32_t)tc >> sh0) & (msk0 & 0xFFu);
@@ -744,8 +736,7 @@ SB_HD void trace_one(const uint8_t* text, uint64_t n, bool rev, const uint8_t* p
 #pragma unroll
     for (int w = 0; w < kRegW; w++) {
       if (w >= W) break;
-      const uint32_t pv = in_regs ? ppv[w] : cs.at(((i - 1) * W + w) * 2);
-      const uint32_t mv = in_regs ? pmv[w] : cs.at(((i - 1) * W + w) * 2 + 1);
+      const uint32_t pv = ppv[w], mv = pmv[w];
       const uint32_t x = e[w] | mv;
       const uint32_t t = x & pv;
       const uint64_t sum = (uint64_t)t + pv + carry;
@@ -760,11 +751,12 @@ SB_HD void trace_one(const uint8_t* text, uint64_t n, bool rev, const uint8_t* p
       mhc = mh >> 31;
       ppv[w] = mh1 | ~(d0 | ph1);
       pmv[w] = ph1 & d0;
-      cs.at((i * W + w) * 2) = ppv[w];
-      cs.at((i * W + w) * 2 + 1) = pmv[w];
+      cs.at((i * W + w) * F) = ppv[w];
+      cs.at((i * W + w) * F + 1) = pmv[w];
+      if (wide) cs.at((i * W + w) * F + 2) = ph, cs.at((i * W + w) * F + 3) = mh;
     }
     for (int w = kRegW; w < W; w++) {
-      const uint32_t pv = cs.at(((i - 1) * W + w) * 2), mv = cs.at(((i - 1) * W + w) * 2 + 1);
+      const uint32_t pv = lpv[w - kRegW], mv = lmv[w - kRegW];
       const uint32_t x = e[w] | mv;
       const uint32_t t = x & pv;
       const uint64_t sum = (uint64_t)t + pv + carry;
@@ -777,33 +769,74 @@ SB_HD void trace_one(const uint8_t* text, uint64_t n, bool rev, const uint8_t* p
       const uint32_t mh1 = (mh << 1) | mhc;
       phc = ph >> 31;
       mhc = mh >> 31;
-      cs.at((i * W + w) * 2) = mh1 | ~(d0 | ph1);
-      cs.at((i * W + w) * 2 + 1) = ph1 & d0;
+      const uint32_t npv = mh1 | ~(d0 | ph1), nmv = ph1 & d0;
+      lpv[w - kRegW] = npv, lmv[w - kRegW] = nmv;
+      cs.at((i * W + w) * F) = npv;
+      cs.at((i * W + w) * F + 1) = nmv;
+      cs.at((i * W + w) * F + 2) = ph;  // W > 4: always the wide layout
+      cs.at((i * W + w) * F + 3) = mh;
     }
   }
   for (uint32_t w = 0; w < ops_words; w++) ops[w] = 0;
+  // D[j][i] for the narrow layout: column 0 is j, row 0 is 0, else the sum of the vertical deltas
+  auto cost = [&](int j, uint32_t i) -> int {
+    if (j == 0) return 0;
+    if (i == 0) return j;
+    int bits = pad + j, v = 0;
+    for (int w = 0; w < W && bits > 0; w++) {
+      const uint32_t msk = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+      v += popc32(cs.at((i * W + w) * F) & msk) - popc32(cs.at((i * W + w) * F + 1) & msk);
+      bits -= 32;
+    }
+    return v;
+  };
+  // neighbours of (j, i) with value g (wide layout): single-bit reads
+  //   left  D[j][i-1]   = g - h(j, i)
+  //   up    D[j-1][i]   = g - v(j, i)
+  //   diag  D[j-1][i-1] = left - v(j, i-1)
+  auto vdelta = [&](int j, uint32_t i) -> int {  // D[j][i] - D[j-1][i]
+    const int b = pad + j - 1;
+    return delta_at(cs.at((i * W + (b >> 5)) * F), cs.at((i * W + (b >> 5)) * F + 1), b & 31);
+  };
+  auto hdelta = [&](int j, uint32_t i) -> int {  // D[j][i] - D[j][i-1], i >= 1
+    const int b = pad + j - 1;
+    return delta_at(cs.at((i * W + (b >> 5)) * F + 2), cs.at((i * W + (b >> 5)) * F + 3), b & 31);
+  };
   int j = m;
   uint32_t i = wlen;
-  int g = col_cost<P>(cs, W, pad, j, i);
+  int g = cost(j, i);
   out.cost = g;
   out.failed = 0;
   uint32_t nops = 0;
   const uint32_t max_ops = ops_words * 16;
   while (j > 0) {
+    int diag, left, up;
+    if (wide) {
+      up = g - vdelta(j, i);
+      if (i > 0) {
+        left = g - hdelta(j, i);
+        diag = left - vdelta(j, i - 1);
+      } else {
+        left = diag = 0;
+      }
+    } else {
+      up = cost(j - 1, i);
+      left = i > 0 ? cost(j, i - 1) : 0;
+      diag = i > 0 ? cost(j - 1, i - 1) : 0;
+    }
     uint32_t op;
-    if (i > 0 && col_cost<P>(cs, W, pad, j - 1, i - 1) == g &&
-        trace_match<P>(pattern[j - 1], text_at_dir(text, n, rev, off + i - 1))) {
+    if (i > 0 && diag == g && trace_match<P>(pattern[j - 1], text_at_dir(text, n, rev, off + i - 1))) {
       op = kOpEq;
       j--, i--;
     } else {
       g -= 1;
-      if (i > 0 && col_cost<P>(cs, W, pad, j - 1, i - 1) == g) {
+      if (i > 0 && diag == g) {
         op = kOpX;
         j--, i--;
-      } else if (i > 0 && col_cost<P>(cs, W, pad, j, i - 1) == g) {
+      } else if (i > 0 && left == g) {
         op = kOpD;
         i--;
-      } else if (col_cost<P>(cs, W, pad, j - 1, i) == g) {
+      } else if (up == g) {
         op = kOpI;
         j--;
       } else {

@@ -271,10 +271,13 @@ class Searcher:
             if n == 0:
                 return MatchList(np.zeros(0, dtype=_REC_DTYPE), b"")
             ms = lib.sassy_gpu_result_matches(res)
-            recs = np.frombuffer(ctypes.string_at(ms, n * _REC_DTYPE.itemsize), dtype=_REC_DTYPE)
+            # (c_char * size).from_address: sizes beyond 2 GiB are fine (ctypes.string_at takes a C int)
+            addr = ctypes.cast(ms, ctypes.c_void_p).value
+            recs = np.frombuffer(bytes((ctypes.c_char * (n * _REC_DTYPE.itemsize)).from_address(addr)), dtype=_REC_DTYPE)
             last = recs[-1]
             ops_ptr = lib.sassy_gpu_result_ops(res)
-            ops = ctypes.string_at(ops_ptr, int(last["ops_off"]) + int(last["ops_len"])) if ops_ptr else b""
+            total = int(last["ops_off"]) + int(last["ops_len"])
+            ops = bytes((ctypes.c_char * total).from_address(ops_ptr)) if ops_ptr and total else b""
             return MatchList(recs, ops)
         finally:
             lib.sassy_gpu_result_free(res)
