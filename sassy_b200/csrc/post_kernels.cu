@@ -179,7 +179,119 @@ __global__ void trace_kernel(const __grid_constant__ TraceArgs t) {
   }
 }
 
+// One word of the recurrences with explicit carries (as myers_word in scan_kernels.cu).
+__device__ __forceinline__ void trace_word(uint32_t& pv, uint32_t& mv, uint32_t eq, uint32_t cin, uint32_t& cout,
+                                           uint32_t& ph_out, uint32_t& mh_out) {
+  const uint32_t x = eq | mv;
+  const uint32_t t = x & pv;
+  const uint64_t sum = (uint64_t)t + pv + (cin & 1u);
+  const uint32_t u = (uint32_t)sum;
+  const uint32_t d0 = (u ^ pv) | x;
+  const uint32_t ph = mv | ~(d0 | pv);
+  const uint32_t mh = pv & d0;
+  const uint32_t ph1 = (ph << 1) | ((cin >> 1) & 1u);
+  const uint32_t mh1 = (mh << 1) | ((cin >> 2) & 1u);
+  cout = (uint32_t)(sum >> 32) | ((ph >> 31) << 1) | ((mh >> 31) << 2);
+  pv = mh1 | ~(d0 | ph1);
+  mv = ph1 & d0;
+  ph_out = ph;
+  mh_out = mh;
+}
+
+constexpr int kTraceWideWarps = 4;
+constexpr int kTraceWideWindow = 1280;  // characters of a traceback window staged in shared memory
+
+// Traceback for patterns of many words (W >= 8): ONE WARP per match.  The column store is filled
+// systolically -- word w in lane w, lane w one column behind lane w-1, carries by shuffle -- in
+// m + k + W steps instead of (m + k) x W word-steps of one thread; lane 0 then walks the path
+// (single-bit look-ups in the wide layout).
+template <int P>
+__global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const __grid_constant__ TraceArgs t) {
+  __shared__ uint8_t win[kTraceWideWarps][kTraceWideWindow];
+  uint64_t count = t.count;
+  if (t.count_dev) {
+    const unsigned long long total = *t.count_dev;
+    count = total > t.first ? (total - t.first < count ? total - t.first : count) : 0;
+  }
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t nwarps = (uint64_t)gridDim.x * kTraceWideWarps;
+  const int W = t.W, m = t.m, k = t.k;
+  const int pad = 32 * W - m;
+  constexpr int F = 4;
+  for (uint64_t li = (uint64_t)blockIdx.x * kTraceWideWarps + (threadIdx.x >> 5); li < count; li += nwarps) {
+    const uint64_t gi = t.first + li;
+    const uint64_t key = t.keys[gi];
+    const uint32_t qs = key_qs(key);
+    const uint64_t end = key_pos(key);
+    const uint8_t* text;
+    uint64_t n;
+    uint32_t q;
+    text_of_slot(t.text, qs, text, n, q);
+    const bool rev = t.rev_flags[q] != 0;
+    const uint32_t* __restrict__ eq = t.eq + (size_t)q * t.nrows * W;
+    // contiguous column store per match: the 4 fields of a word are 16 adjacent bytes, the words of a
+    // column adjacent lines, so the walk touches one new 128-byte line per step
+    ColStore cs;
+    cs.base = t.scratch + (li % nwarps) * trace_words_per_match(m, k, W);
+    cs.stride = 1;
+    const uint64_t fill = (uint64_t)m + (uint64_t)k;
+    const uint64_t off = end > fill ? end - fill : 0;
+    const uint32_t wlen = (uint32_t)(end - off);
+    // stage the window's characters (scan order): the fill reads one per lane and step
+    const bool staged = wlen <= (uint32_t)kTraceWideWindow;
+    uint8_t* wbuf = win[threadIdx.x >> 5];
+    __syncwarp();
+    if (staged)
+      for (uint32_t i = lane; i < wlen; i += 32) wbuf[i] = text_at_dir(text, n, rev, off + i);
+    __syncwarp();
+    uint32_t pv = 0, mv = 0;
+    if (lane < (uint32_t)W) {
+      const int lo = pad - 32 * (int)lane;
+      pv = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
+      cs.at((0 * W + lane) * F) = pv;  // column 0: D[j][0] = j
+      cs.at((0 * W + lane) * F + 1) = 0;
+    }
+    uint32_t carry = 0;
+    for (uint32_t step = 0; step < wlen + (uint32_t)W - 1; step++) {
+      const int32_t c = (int32_t)step - (int32_t)lane;  // this lane's column is c + 1
+      uint32_t cout = 0;
+      if (lane < (uint32_t)W && c >= 0 && c < (int32_t)wlen) {
+        const uint8_t tc = staged ? wbuf[c] : text_at_dir(text, n, rev, off + (uint64_t)c);
+        const uint32_t row = ((uint32_t)tc >> t.sh0) & (t.msk0 & 0xFFu);
+        uint32_t ph, mh;
+        trace_word(pv, mv, __ldg(eq + row * W + lane), carry, cout, ph, mh);
+        const uint32_t slot = (((uint32_t)c + 1) * W + lane) * F;
+        *reinterpret_cast<uint4*>(&cs.at(slot)) = make_uint4(pv, mv, ph, mh);  // 16-byte aligned: slot % 4 == 0
+      }
+      carry = __shfl_up_sync(0xFFFFFFFFu, cout, 1);
+      if (lane == 0) carry = 0;
+    }
+    __threadfence_block();
+    __syncwarp();  // the column store written by all lanes is read by lane 0
+    if (lane == 0) {
+      TraceOut out;
+      trace_walk<P>(text, n, rev, t.patterns + (size_t)q * m, m, W, off, wlen, end, cs, t.ops + gi * t.ops_words,
+                    t.ops_words, out);
+      GpuMatch gm;
+      gm.qs = qs;
+      gm.text_start = out.text_start;
+      gm.text_end = out.text_end;
+      gm.cost = out.cost;
+      gm.nops = out.nops;
+      gm.failed = out.failed;
+      if (t.max_n_frac >= 0.f &&
+          !n_fraction_ok(text, n, rev, out.text_start, out.text_end < n ? out.text_end : n, t.max_n_frac, 0))
+        gm.failed |= 2u;
+      t.out[gi] = gm;
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
+
+// Wide path: patterns of >= 8 words, traced (not cost-only), no overhang.
+static bool trace_is_wide(const TraceArgs& t) { return t.W >= 8 && !t.costs && !(t.alpha >= 0.f); }
 
 cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags, bool all_minima,
                           const EndFilter* filter, cudaStream_t stream) {
@@ -224,9 +336,28 @@ uint64_t trace_threads(uint64_t count) {
   return blocks * threads;
 }
 
+// matches in flight of the one-warp-per-match kernel (each needs a column store)
+static uint64_t trace_wide_warps(uint64_t count) {
+  uint64_t blocks = (count + kTraceWideWarps - 1) / kTraceWideWarps;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks == 0) blocks = 1;
+  return blocks * kTraceWideWarps;
+}
+
 cudaError_t launch_trace(const TraceArgs& t0, cudaStream_t stream) {
   if (t0.count == 0) return cudaSuccess;
   TraceArgs t = t0;
+  if (trace_is_wide(t)) {
+    // the scratch holds trace_threads(count) column stores, the warps in flight need fewer
+    const unsigned blocks = (unsigned)(trace_wide_warps(t.count) / kTraceWideWarps);
+    switch (t.profile) {
+      case kDna: trace_wide_kernel<kDna><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t); break;
+      case kIupac: trace_wide_kernel<kIupac><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t); break;
+      case kAscii: trace_wide_kernel<kAscii><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t); break;
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
   const unsigned threads = 128;
   const uint64_t blocks = trace_threads(t.count) / threads;
   // the per-match column store ((m+k+1) columns x W words x 2) lives in shared memory when a

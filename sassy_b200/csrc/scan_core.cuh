@@ -685,6 +685,14 @@ struct ColStore {
   uint32_t* base;
   uint64_t stride;  // distance between consecutive (column, word) slots
   SB_HD uint32_t& at(uint32_t slot) const { return base[(uint64_t)slot * stride]; }
+  // hint: the line holding `slot` will be read a few steps from now (device only)
+  SB_HD void prefetch(uint32_t slot) const {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (uint64_t)slot * stride));
+#else
+    (void)slot;
+#endif
+  }
 };
 
 SB_HD uint8_t text_at_dir(const uint8_t* text, uint64_t n, bool rev, uint64_t i) {
@@ -702,6 +710,103 @@ SB_HD uint64_t trace_words_per_match(int m, int k, int W) {
 
 // +1 / -1 / 0 from a (plus, minus) pair of delta words at bit b
 SB_HD int delta_at(uint32_t p, uint32_t mn, int bit) { return (int)((p >> bit) & 1u) - (int)((mn >> bit) & 1u); }
+
+// The greedy walk of src/trace.rs:314-388 over a filled column store (columns 0..wlen of the
+// window starting at `off`): '=' > 'X' > 'D' (text only) > 'I' (pattern only).
+template <int P>
+SB_HD void trace_walk(const uint8_t* text, uint64_t n, bool rev, const uint8_t* pattern, int m, int W, uint64_t off,
+                      uint32_t wlen, uint64_t end, const ColStore& cs, uint32_t* ops, uint32_t ops_words,
+                      TraceOut& out) {
+  const int pad = 32 * W - m;
+  const int F = trace_fields(W);
+  const bool wide = F == 4;
+  for (uint32_t w = 0; w < ops_words; w++) ops[w] = 0;
+  // D[j][i] for the narrow layout: column 0 is j, row 0 is 0, else the sum of the vertical deltas
+  auto cost = [&](int j, uint32_t i) -> int {
+    if (j == 0) return 0;
+    if (i == 0) return j;
+    int bits = pad + j, v = 0;
+    for (int w = 0; w < W && bits > 0; w++) {
+      const uint32_t msk = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+      v += popc32(cs.at((i * W + w) * F) & msk) - popc32(cs.at((i * W + w) * F + 1) & msk);
+      bits -= 32;
+    }
+    return v;
+  };
+  // neighbours of (j, i) with value g (wide layout): single-bit reads
+  //   left  D[j][i-1]   = g - h(j, i)
+  //   up    D[j-1][i]   = g - v(j, i)
+  //   diag  D[j-1][i-1] = left - v(j, i-1)
+  auto vdelta = [&](int j, uint32_t i) -> int {  // D[j][i] - D[j-1][i]
+    const int b = pad + j - 1;
+    return delta_at(cs.at((i * W + (b >> 5)) * F), cs.at((i * W + (b >> 5)) * F + 1), b & 31);
+  };
+  auto hdelta = [&](int j, uint32_t i) -> int {  // D[j][i] - D[j][i-1], i >= 1
+    const int b = pad + j - 1;
+    return delta_at(cs.at((i * W + (b >> 5)) * F + 2), cs.at((i * W + (b >> 5)) * F + 3), b & 31);
+  };
+  int j = m;
+  uint32_t i = wlen;
+  int g = cost(j, i);
+  out.cost = g;
+  out.failed = 0;
+  uint32_t nops = 0;
+  const uint32_t max_ops = ops_words * 16;
+  while (j > 0) {
+    int diag, left, up;
+    if (wide) {
+      // the walk moves one column per step at most: fetch the words around the path 6 columns ahead
+      if (i >= 6) cs.prefetch(((i - 6) * W + ((pad + j - 1) >> 5)) * F);
+      up = g - vdelta(j, i);
+      if (i > 0) {
+        left = g - hdelta(j, i);
+        diag = left - vdelta(j, i - 1);
+      } else {
+        left = diag = 0;
+      }
+    } else {
+      up = cost(j - 1, i);
+      left = i > 0 ? cost(j, i - 1) : 0;
+      diag = i > 0 ? cost(j - 1, i - 1) : 0;
+    }
+    uint32_t op;
+    if (i > 0 && diag == g && trace_match<P>(pattern[j - 1], text_at_dir(text, n, rev, off + i - 1))) {
+      op = kOpEq;
+      j--, i--;
+    } else {
+      g -= 1;
+      if (i > 0 && diag == g) {
+        op = kOpX;
+        j--, i--;
+      } else if (i > 0 && left == g) {
+        op = kOpD;
+        i--;
+      } else if (up == g) {
+        op = kOpI;
+        j--;
+      } else {
+        out.failed = 1;  // the reference panics with "Trace failed" (src/trace.rs:367-387)
+        break;
+      }
+    }
+    if (nops < max_ops) ops[nops >> 4] |= op << ((nops & 15) * 2);
+    nops++;
+  }
+  if (nops > max_ops) {
+    out.failed = 1;
+    nops = max_ops;
+  }
+  // reverse into pattern direction (src/trace.rs:393)
+  for (uint32_t a = 0, b = nops; a + 1 < b; a++, b--) {
+    const uint32_t oa = (ops[a >> 4] >> ((a & 15) * 2)) & 3u;
+    const uint32_t ob = (ops[(b - 1) >> 4] >> (((b - 1) & 15) * 2)) & 3u;
+    ops[a >> 4] = (ops[a >> 4] & ~(3u << ((a & 15) * 2))) | (ob << ((a & 15) * 2));
+    ops[(b - 1) >> 4] = (ops[(b - 1) >> 4] & ~(3u << (((b - 1) & 15) * 2))) | (oa << (((b - 1) & 15) * 2));
+  }
+  out.text_start = off + i;
+  out.text_end = end;
+  out.nops = nops;
+}
 
 // `ops` receives 2-bit op codes, 16 per word, in pattern direction.
 template <int P>
@@ -777,90 +882,7 @@ SB_HD void trace_one(const uint8_t* text, uint64_t n, bool rev, const uint8_t* p
       cs.at((i * W + w) * F + 3) = mh;
     }
   }
-  for (uint32_t w = 0; w < ops_words; w++) ops[w] = 0;
-  // D[j][i] for the narrow layout: column 0 is j, row 0 is 0, else the sum of the vertical deltas
-  auto cost = [&](int j, uint32_t i) -> int {
-    if (j == 0) return 0;
-    if (i == 0) return j;
-    int bits = pad + j, v = 0;
-    for (int w = 0; w < W && bits > 0; w++) {
-      const uint32_t msk = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
-      v += popc32(cs.at((i * W + w) * F) & msk) - popc32(cs.at((i * W + w) * F + 1) & msk);
-      bits -= 32;
-    }
-    return v;
-  };
-  // neighbours of (j, i) with value g (wide layout): single-bit reads
-  //   left  D[j][i-1]   = g - h(j, i)
-  //   up    D[j-1][i]   = g - v(j, i)
-  //   diag  D[j-1][i-1] = left - v(j, i-1)
-  auto vdelta = [&](int j, uint32_t i) -> int {  // D[j][i] - D[j-1][i]
-    const int b = pad + j - 1;
-    return delta_at(cs.at((i * W + (b >> 5)) * F), cs.at((i * W + (b >> 5)) * F + 1), b & 31);
-  };
-  auto hdelta = [&](int j, uint32_t i) -> int {  // D[j][i] - D[j][i-1], i >= 1
-    const int b = pad + j - 1;
-    return delta_at(cs.at((i * W + (b >> 5)) * F + 2), cs.at((i * W + (b >> 5)) * F + 3), b & 31);
-  };
-  int j = m;
-  uint32_t i = wlen;
-  int g = cost(j, i);
-  out.cost = g;
-  out.failed = 0;
-  uint32_t nops = 0;
-  const uint32_t max_ops = ops_words * 16;
-  while (j > 0) {
-    int diag, left, up;
-    if (wide) {
-      up = g - vdelta(j, i);
-      if (i > 0) {
-        left = g - hdelta(j, i);
-        diag = left - vdelta(j, i - 1);
-      } else {
-        left = diag = 0;
-      }
-    } else {
-      up = cost(j - 1, i);
-      left = i > 0 ? cost(j, i - 1) : 0;
-      diag = i > 0 ? cost(j - 1, i - 1) : 0;
-    }
-    uint32_t op;
-    if (i > 0 && diag == g && trace_match<P>(pattern[j - 1], text_at_dir(text, n, rev, off + i - 1))) {
-      op = kOpEq;
-      j--, i--;
-    } else {
-      g -= 1;
-      if (i > 0 && diag == g) {
-        op = kOpX;
-        j--, i--;
-      } else if (i > 0 && left == g) {
-        op = kOpD;
-        i--;
-      } else if (up == g) {
-        op = kOpI;
-        j--;
-      } else {
-        out.failed = 1;  // the reference panics with "Trace failed" (src/trace.rs:367-387)
-        break;
-      }
-    }
-    if (nops < max_ops) ops[nops >> 4] |= op << ((nops & 15) * 2);
-    nops++;
-  }
-  if (nops > max_ops) {
-    out.failed = 1;
-    nops = max_ops;
-  }
-  // reverse into pattern direction (src/trace.rs:393)
-  for (uint32_t a = 0, b = nops; a + 1 < b; a++, b--) {
-    const uint32_t oa = (ops[a >> 4] >> ((a & 15) * 2)) & 3u;
-    const uint32_t ob = (ops[(b - 1) >> 4] >> (((b - 1) & 15) * 2)) & 3u;
-    ops[a >> 4] = (ops[a >> 4] & ~(3u << ((a & 15) * 2))) | (ob << ((a & 15) * 2));
-    ops[(b - 1) >> 4] = (ops[(b - 1) >> 4] & ~(3u << (((b - 1) & 15) * 2))) | (oa << (((b - 1) & 15) * 2));
-  }
-  out.text_start = off + i;
-  out.text_end = end;
-  out.nops = nops;
+  trace_walk<P>(text, n, rev, pattern, m, W, off, wlen, end, cs, ops, ops_words, out);
 }
 
 // ---------------------------------------------------------------------------

@@ -630,9 +630,112 @@ cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtens
 #undef SB_FCALL2
 }
 
+namespace {
+
+// One word of the recurrences with explicit carries (the multi-word form of myers_step): used by
+// the warp-systolic kernels, where word w of a pattern lives in lane w.
+//   cin / cout: bit 0 = carry of the addition, bit 1 = Ph carry, bit 2 = Mh carry
+__device__ __forceinline__ void myers_word(uint32_t& pv, uint32_t& mv, uint32_t eq, uint32_t cin, uint32_t& cout,
+                                           uint32_t& ph_out, uint32_t& mh_out) {
+  const uint32_t x = eq | mv;
+  const uint32_t t = x & pv;
+  const uint64_t sum = (uint64_t)t + pv + (cin & 1u);
+  const uint32_t u = (uint32_t)sum;
+  const uint32_t d0 = (u ^ pv) | x;
+  const uint32_t ph = mv | ~(d0 | pv);
+  const uint32_t mh = pv & d0;
+  const uint32_t ph1 = (ph << 1) | ((cin >> 1) & 1u);
+  const uint32_t mh1 = (mh << 1) | ((cin >> 2) & 1u);
+  cout = (uint32_t)(sum >> 32) | ((ph >> 31) << 1) | ((mh >> 31) << 2);
+  pv = mh1 | ~(d0 | ph1);
+  mv = ph1 & d0;
+  ph_out = ph;
+  mh_out = mh;
+}
+
+constexpr int kWideWarps = 4;        // warps per block of the systolic kernels
+constexpr int kWideWindow = 2304;    // >= 2 (m + k) + 16 + piece length for m + k <= 1100
+
+// Re-scan of the prefilter's hits for patterns of many words: ONE WARP per hit, word w of the
+// pattern in lane w, the lanes skewed by one character (lane w works on character t - w at step
+// t), so that the carries of the addition and of the two shifts travel to the next lane with one
+// shuffle per step and all lanes are busy: a window of L characters takes L + W steps instead of
+// L x W word-steps of a single thread.  Lane W-1 follows the score through the horizontal delta of
+// the pattern's last row and emits the candidates.
+template <int W>
+__global__ void __launch_bounds__(32 * kWideWarps)
+    verify_wide_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags) {
+  __shared__ uint8_t win[kWideWarps][kWideWindow];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long nhits = *a.hit_count;
+  if (nhits > a.hit_cap) nhits = a.hit_cap;
+  const unsigned long long nwarps = (unsigned long long)gridDim.x * kWideWarps;
+  const int pad = 32 * W - a.m;
+  for (unsigned long long h = (unsigned long long)blockIdx.x * kWideWarps + warp; h < nhits; h += nwarps) {
+    const uint64_t key = a.hit_keys[h];
+    const uint32_t qs = key_qs(key);
+    const bool rev = rev_flags[qs] != 0;
+    const uint32_t* __restrict__ eq = a.eq + (size_t)qs * a.nrows * W;
+    const int64_t n = (int64_t)a.n;
+    const int64_t base = (int64_t)(key_pos(key) * kHitChars);
+    const int64_t g0 = rev ? n - kHitChars - base : base;
+    const int64_t span = (int64_t)a.m + (int64_t)a.k;
+    int64_t w0 = g0 - span;
+    if (w0 < 0) w0 = 0;
+    int64_t end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
+    if (end > n) end = n;
+    const int64_t emit_from = g0 < 0 ? 0 : g0;
+    if (end <= w0) continue;
+    const int32_t L = (int32_t)(end - w0);
+    // stage the window in scan order; a window beyond the buffer is processed in pieces below
+    __syncwarp();
+    for (int32_t i = (int32_t)lane; i < L && i < kWideWindow; i += 32)
+      win[warp][i] = text_at_dir(a.text, (uint64_t)n, rev, (uint64_t)(w0 + i));
+    __syncwarp();
+    const int32_t Lc = L < kWideWindow ? L : kWideWindow;  // (engine guarantees L <= kWideWindow for W <= 32)
+    uint32_t pv = 0, mv = 0;
+    if (lane < (uint32_t)W) {
+      const int lo = pad - 32 * (int)lane;
+      pv = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
+    }
+    uint32_t carry = 0;  // carries handed over by the previous lane for the character of this step
+    int score = a.m;
+    const int32_t emit_rel = (int32_t)(emit_from - w0);
+    for (int32_t t = 0; t < Lc + W - 1; t++) {
+      const int32_t idx = t - (int32_t)lane;
+      uint32_t cout = 0;
+      if (lane < (uint32_t)W && idx >= 0 && idx < Lc) {
+        const uint32_t row = ((uint32_t)win[warp][idx] >> a.sh0) & (a.msk0 & 0xFFu);
+        uint32_t ph, mh;
+        myers_word(pv, mv, __ldg(eq + row * W + lane), carry, cout, ph, mh);
+        if (lane == (uint32_t)(W - 1)) {
+          score += (int)(ph >> 31) - (int)(mh >> 31);
+          if (idx >= emit_rel && score <= a.k) emit_candidate(a, qs, (uint64_t)(w0 + idx) + 1, score);
+        }
+      }
+      carry = __shfl_up_sync(0xFFFFFFFFu, cout, 1);
+      if (lane == 0) carry = 0;
+    }
+  }
+}
+
+}  // namespace
+
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream) {
   const unsigned threads = 128;
   const unsigned blocks = 148 * 12;  // grid-stride over the device-side hit count
+  // many words: one warp per hit (systolic), when the window fits the staging buffer
+  const int64_t window = 2 * ((int64_t)a.m + a.k) + kHitChars + (int64_t)a.rev_lead;
+  if (W >= 8 && window <= kWideWindow) {
+    const unsigned wblocks = 148 * 8;
+    switch (W) {
+      case 8: verify_wide_kernel<8><<<wblocks, 32 * kWideWarps, 0, stream>>>(a, rev_flags); break;
+      case 16: verify_wide_kernel<16><<<wblocks, 32 * kWideWarps, 0, stream>>>(a, rev_flags); break;
+      case 32: verify_wide_kernel<32><<<wblocks, 32 * kWideWarps, 0, stream>>>(a, rev_flags); break;
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
   switch (W) {
 #define SB_VCALL(WW) case WW: verify_kernel<WW><<<blocks, threads, 0, stream>>>(a, rev_flags); break;
     SB_VCALL(1) SB_VCALL(2) SB_VCALL(3) SB_VCALL(4) SB_VCALL(6) SB_VCALL(8) SB_VCALL(16) SB_VCALL(32)
