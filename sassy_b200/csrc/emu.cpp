@@ -101,6 +101,7 @@ void filter_dispatch(int WF, const ScanArgs& a, const uint32_t* feq_q, uint32_t 
     case 1: filter_rows<1, REV>(a, feq_q, qs, pair); break;
     case 2: filter_rows<2, REV>(a, feq_q, qs, pair); break;
     case 4: filter_rows<4, REV>(a, feq_q, qs, pair); break;
+    case 8: filter_rows<8, REV>(a, feq_q, qs, pair); break;
     default: abort();
   }
 }

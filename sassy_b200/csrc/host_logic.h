@@ -95,7 +95,7 @@ inline ScanGeom choose_geom(uint64_t n, int m, int k, uint32_t nq, int bpw) {
 
 // ---------------------------------------------------------------------------
 // Exact piece prefilter: layout and tables (see scan_core.cuh).
-constexpr int kMaxPieces = 40;  // >= kMaxFilterWords * (32 / (1 + kFilterDelay))
+constexpr int kMaxPieces = 64;  // >= kMaxFilterWords * (32 / (1 + kFilterDelay))
 
 struct FilterPiece {
   int off;   // first pattern position of the piece
@@ -106,14 +106,14 @@ struct FilterPiece {
 
 struct FilterPlan {
   bool enabled = false;
-  int WF = 0;        // automaton words (1, 2 or 4)
+  int WF = 0;        // automaton words (1, 2, 4 or 8)
   int L = 0;         // shortest piece
   int npieces = 0;   // k + 1
   FilterPiece piece[kMaxPieces];
   double rate = 0;   // expected piece occurrences per text position (uniform ACGT text), max over queries
   double cost = 0;   // modelled cost relative to the full scan (1.0)
-  uint32_t finit[kMaxFilterWords] = {0, 0, 0, 0};
-  uint32_t fdelay[kMaxFilterWords] = {0, 0, 0, 0};
+  uint32_t finit[kMaxFilterWords] = {};
+  uint32_t fdelay[kMaxFilterWords] = {};
 };
 
 // Probability that a uniformly random ACGT character matches pattern byte c.
@@ -174,7 +174,7 @@ inline FilterPlan plan_filter(int profile, const uint8_t* const* queries, size_t
   if (k < 0 || k + 1 > m || nq == 0) return best;
   const int W = (m + 31) / 32;
   const double window = 2.0 * (m + k) + 4.0;
-  const int wopts[] = {1, 2, 4};
+  const int wopts[] = {1, 2, 4, 8};
   bool have = false;
   for (int WF : wopts) {
     FilterPlan f;

@@ -39,7 +39,7 @@ constexpr int kGroup = SB_GROUP;  // 4, 8 or 16 (whole 32-bit text words)
 #endif
 constexpr int kStageBytes = SB_STAGE_BYTES;
 
-constexpr int kMaxFilterWords = 4;
+constexpr int kMaxFilterWords = 8;
 // Delay-line bits behind every piece of the prefilter: together with the piece's last
 // bit they keep an occurrence visible for 4 characters = one text word = one hit test.
 constexpr int kFilterDelay = 3;
@@ -333,8 +333,12 @@ SB_HD void load_feq(uint32_t (&eq)[WF], const EqTab& t, uint32_t x, int b) {
   const uint32_t row = __byte_perm(x, 0u, 0x4440u + (uint32_t)b);
   uint32_t addr;
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(row), "r"(t.rowbytes), "r"(t.saddr));
-  if (WF == 4) {
-    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(eq[0]), "=r"(eq[WF > 1 ? 1 : 0]), "=r"(eq[WF > 2 ? 2 : 0]), "=r"(eq[WF > 3 ? 3 : 0]) : "r"(addr));
+  if (WF % 4 == 0) {
+#pragma unroll
+    for (int w = 0; w + 3 < WF; w += 4)
+      asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+          : "=r"(eq[w]), "=r"(eq[w + 1 < WF ? w + 1 : 0]), "=r"(eq[w + 2 < WF ? w + 2 : 0]), "=r"(eq[w + 3 < WF ? w + 3 : 0])
+          : "r"(addr + 4 * w));
   } else if (WF == 2) {
     asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(eq[0]), "=r"(eq[WF > 1 ? 1 : 0]) : "r"(addr));
   } else {

@@ -255,7 +255,7 @@ __device__ __forceinline__ void push_hit(const ScanArgs& a, const HitQueue& hq, 
 // words in which a piece occurrence ends.
 // PAIR: two characters per automaton step through a class-pair table (Dna profile).
 template <int WF, bool REV, int VARIANT, bool PAIR>
-__global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, (WF <= 4 ? 1024 : 512) / kScanThreads)
     filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a) {
   __shared__ uint64_t hit_q[kWarpsPerBlock][kHitQueueCap];
   __shared__ uint32_t hit_n[kWarpsPerBlock];
@@ -552,13 +552,19 @@ int filter_occupancy(int WF, int variant, bool pair, size_t smem) {
                                   : filter_occupancy_one<WW, false, kVariantLdg, true>(smem);                   \
   return variant == kVariantTma ? filter_occupancy_one<WW, false, kVariantTma, false>(smem)                     \
                                 : filter_occupancy_one<WW, false, kVariantLdg, false>(smem);
+  // 8 words: byte-indexed table only (the pair table is used up to 4 words)
+#define SB_OCC8                                                                                                 \
+  return variant == kVariantTma ? filter_occupancy_one<8, false, kVariantTma, false>(smem)                      \
+                                : filter_occupancy_one<8, false, kVariantLdg, false>(smem);
   switch (WF) {
     case 1: SB_OCC(1)
     case 2: SB_OCC(2)
     case 4: SB_OCC(4)
+    case 8: SB_OCC8
     default: return 1;
   }
 #undef SB_OCC
+#undef SB_OCC8
 }
 
 // Resident prefilter blocks per SM.  Measured on B200 (profiles/r01b_filter_residency.md): the
@@ -580,9 +586,9 @@ struct FilterConfig {
 };
 
 const FilterConfig& filter_config(int WF, int variant, bool pair) {
-  static FilterConfig cache[8][2][2];  // (all devices of a box are the same part)
+  static FilterConfig cache[9][2][2];  // (all devices of a box are the same part)
   static FilterConfig none;
-  if (WF < 1 || WF >= 8) return none;
+  if (WF < 1 || WF > 8) return none;
   FilterConfig& c = cache[WF][variant & 1][pair ? 1 : 0];
   if (c.bps) return c;
   size_t smem = (size_t)256 * WF * sizeof(uint32_t);
@@ -624,6 +630,9 @@ cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtens
     case 1: SB_FCALL(1)
     case 2: SB_FCALL(2)
     case 4: SB_FCALL(4)
+    case 8:
+      if (pair) return cudaErrorInvalidValue;
+      SB_FCALL2(8, false)
     default: return cudaErrorInvalidValue;
   }
 #undef SB_FCALL

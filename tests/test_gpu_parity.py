@@ -261,3 +261,27 @@ def test_device_text_reuse(tma):
     d = s.search_encoded_patterns(enc, t, 3)
     assert c == d and c
     dt.free()
+
+
+def test_gpu_long_patterns_many_pieces(tma):
+    """m up to 1000 with k >= 8: the 8-word prefilter automaton, the warp-systolic re-scan and the
+    warp-systolic traceback (patterns of >= 8 words)."""
+    import sassy_b200
+    rng = random.Random(29)
+    s = sassy_b200.Searcher("dna", rc=True)
+    for m, k, n in ((300, 8, 200_000), (1000, 8, 300_000), (1000, 3, 300_000), (520, 12, 100_000), (260, 9, 50_000)):
+        p, t = planted(rng, m, n, k)
+        t = bytearray(t)
+        for j in range(5):  # a few more copies with edits
+            a = rng.randrange(0, n - m - 20)
+            q = bytearray(p)
+            for _ in range(rng.randrange(0, k + 1)):
+                q[rng.randrange(len(q))] = rng.choice(b"ACGT")
+            t[a:a + len(q)] = q
+        t = bytes(t[:n])
+        for allm in (False, True):
+            want = oracle.search("dna", p, t, k, rc=True, all_minima=allm)
+            got = s.search_all(p, t, k) if allm else s.search(p, t, k)
+            assert list(map(key, got)) == list(map(key, want)), (m, k, allm)
+        assert len(want) >= 1
+    assert s.stats()["filter_words"] in (1, 2, 4, 8)

@@ -143,3 +143,21 @@ def test_geometry_covers_text():
     b.search("dna", b"ACGTACGTACGTACGTACGT", t, 2)
     ltot, rows = b.last_geom
     assert ltot % 128 == 0 and rows * ltot >= len(t) and (rows - 1) * ltot < len(t)
+
+
+def test_emu_prefilter_eight_words():
+    """k + 1 >= 9 pieces of a long pattern need the 8-word automaton."""
+    rng = random.Random(17)
+    b = EmuBackend()
+    b.use_filter = 1
+    used = set()
+    for it in range(6):
+        m = rng.choice([200, 300, 500])
+        k = rng.choice([8, 9, 12])
+        p, t = planted(rng, m, 5000, k)
+        got = b.search("dna", p, t, k, rc=True)
+        want = oracle.search("dna", p, t, k, rc=True)
+        assert [(x.text_start, x.text_end, x.cost, x.strand, x.cigar) for x in got] == \
+               [(x.text_start, x.text_end, x.cost, x.strand, x.cigar) for x in want]
+        used.add(b.last_filter[0])
+    assert 8 in used
