@@ -78,8 +78,8 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
 Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
-  for (DevBuf* b : {&eq_, &patterns_, &revflags_, &keys_, &cost_, &keys2_, &cost2_, &flags_, &sel_, &count_,
-                    &cubtmp_, &scratch_, &ops_, &out_, &feq_, &hits_, &d_stage_, &best_, &sel_cost_, &d_texts_})
+  for (DevBuf* b : {&keys_, &cost_, &keys2_, &cost2_, &flags_, &sel_, &cubtmp_, &scratch_, &ops_, &out_, &hits_,
+                    &d_stage_, &best_, &sel_cost_, &d_texts_})
     b->release();
   if (staged_.d) cudaFree(staged_.d);
   if (h_stage_) cudaFreeHost(h_stage_);

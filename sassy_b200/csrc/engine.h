@@ -181,21 +181,17 @@ class Engine {
   cudaEvent_t ev_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint32_t nrows_, sh0_, msk0_;
 
-  DevBuf eq_, patterns_, revflags_;
-  DevBuf keys_, cost_, keys2_, cost2_, flags_, sel_, count_, cubtmp_;
+  DevBuf keys_, cost_, keys2_, cost2_, flags_, sel_, cubtmp_;
   DevBuf scratch_, ops_, out_;
-  DevBuf feq_, hits_, d_stage_, sel_small_, best_, sel_cost_, d_texts_;
+  DevBuf hits_, d_stage_, sel_small_, best_, sel_cost_, d_texts_;
   uint8_t* h_small_ = nullptr;  // pinned: results of the small-list fast path, written by the GPU
   size_t h_small_cap_ = 0;
   uint8_t* h_stage_ = nullptr;  // pinned staging for the per-search parameter block
   size_t stage_cap_ = 0;
   size_t off_counts_ = 0, off_eq_ = 0, off_pat_ = 0, off_rev_ = 0, off_feq_ = 0;
   uint64_t hit_cap_ = 0;
-  std::vector<uint32_t> h_feq_;
   uint64_t cand_cap_ = 0;
   DeviceText staged_;
-  std::vector<uint32_t> h_eq_;
-  std::vector<uint8_t> h_pat_, h_rev_;
   SearchStats stats_;
   void* encode_tiled_ = nullptr;
 };

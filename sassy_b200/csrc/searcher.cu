@@ -281,6 +281,17 @@ EncodedPatterns Searcher::encode_patterns(const uint8_t* const* patterns, size_t
 // in the direction of the searched query.
 std::vector<Match> Searcher::search_encoded(const EncodedPatterns& enc, const DeviceText& text, size_t k,
                                             bool all_minima) {
+  search_encoded_raw(enc, text, k, all_minima);
+  return convert_v2(ms_, enc.n_patterns, enc.m);
+}
+
+void Searcher::search_encoded_raw(const EncodedPatterns& enc, const uint8_t* text, size_t n, size_t k,
+                                  bool all_minima) {
+  DeviceText* t = engine_->stage_text(text, n);
+  search_encoded_raw(enc, *t, k, all_minima);
+}
+
+void Searcher::search_encoded_raw(const EncodedPatterns& enc, const DeviceText& text, size_t k, bool all_minima) {
   std::vector<Query> qs(enc.n_queries());
   for (size_t q = 0; q < qs.size(); q++) qs[q] = Query{&enc.bytes[q * enc.m], false};
   const int kk = (int)std::min<size_t>(k, 1u << 20);
@@ -291,7 +302,6 @@ std::vector<Match> Searcher::search_encoded(const EncodedPatterns& enc, const De
   o.all_minima = all_minima;
   o.max_n_frac = max_n_frac_;
   engine_->search(text, qs, enc.m, kk, o, ms_);
-  return convert_v2(ms_, enc.n_patterns, enc.m);
 }
 
 std::vector<Match> Searcher::convert_v2(const MatchSet& ms, size_t n_patterns, int m) const {
@@ -434,6 +444,42 @@ sassy_gpu_Result* to_result(const std::vector<sb::Match>& v) {
     o.ops_off = r->ops.size();
     o.ops_len = (uint32_t)v[i].ops.size();
     r->ops += v[i].ops;
+  }
+  return r;
+}
+
+// v2 records -> flat C result in one pass (no per-match heap allocation): same mapping as
+// Searcher::convert_v2.
+sassy_gpu_Result* to_result_v2(const sb::MatchSet& ms, size_t n_patterns, int m) {
+  sassy_gpu_Result* r = new sassy_gpu_Result;
+  const size_t n = ms.m.size();
+  r->m.resize(n);
+  size_t total = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (ms.m[i].failed & 1u) {
+      delete r;
+      throw std::runtime_error("Trace failed (text contains bytes outside the profile's alphabet?)");
+    }
+    total += ms.m[i].nops;
+  }
+  r->ops.resize(total);
+  char* ops = total ? &r->ops[0] : nullptr;
+  size_t off = 0;
+  for (size_t i = 0; i < n; i++) {
+    const sb::GpuMatch& g = ms.m[i];
+    sassy_gpu_Match& o = r->m[i];
+    memset(&o, 0, sizeof o);
+    o.pattern_idx = g.qs % n_patterns;
+    o.strand = g.qs >= n_patterns ? 1 : 0;
+    o.text_start = g.text_start;
+    o.text_end = g.text_end;
+    o.pattern_end = (uint64_t)m;
+    o.cost = g.cost;
+    o.ops_off = off;
+    o.ops_len = g.nops;
+    const uint32_t* w = &ms.ops[i * ms.ops_words];
+    for (uint32_t a = 0; a < g.nops; a++) ops[off + a] = "=XID"[(w[a >> 4] >> ((a & 15) * 2)) & 3u];
+    off += g.nops;
   }
   return r;
 }
@@ -701,7 +747,8 @@ sassy_gpu_Result* sassy_gpu_search_encoded(sassy_SearcherType* searcher, const s
                                            const sassy_gpu_Text* text, size_t k, int all) {
   return guarded([&]() -> sassy_gpu_Result* {
     if (!searcher || !patterns || !text) throw std::invalid_argument("null pointer");
-    return to_result(searcher->s.search_encoded(patterns->e, *text->t, k, all != 0));
+    searcher->s.search_encoded_raw(patterns->e, *text->t, k, all != 0);
+    return to_result_v2(searcher->s.last_set(), patterns->e.n_patterns, patterns->e.m);
   });
 }
 
@@ -709,7 +756,8 @@ sassy_gpu_Result* sassy_gpu_search_encoded_host(sassy_SearcherType* searcher, co
                                                 const uint8_t* text, size_t text_len, size_t k, int all) {
   return guarded([&]() -> sassy_gpu_Result* {
     if (!searcher || !patterns || (!text && text_len)) throw std::invalid_argument("null pointer");
-    return to_result(searcher->s.search_encoded(patterns->e, text, text_len, k, all != 0));
+    searcher->s.search_encoded_raw(patterns->e, text, text_len, k, all != 0);
+    return to_result_v2(searcher->s.last_set(), patterns->e.n_patterns, patterns->e.m);
   });
 }
 

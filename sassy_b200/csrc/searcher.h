@@ -64,6 +64,11 @@ class Searcher {
   std::vector<Match> search_encoded(const EncodedPatterns& enc, const DeviceText& text, size_t k, bool all_minima);
   std::vector<Match> search_encoded(const EncodedPatterns& enc, const uint8_t* text, size_t n, size_t k,
                                     bool all_minima);
+  // Same search, result left in device-record form (last_set()): batch searches return matches by
+  // the million, and the C ABI turns the records into its flat result without a Match per record.
+  void search_encoded_raw(const EncodedPatterns& enc, const DeviceText& text, size_t k, bool all_minima);
+  void search_encoded_raw(const EncodedPatterns& enc, const uint8_t* text, size_t n, size_t k, bool all_minima);
+  const MatchSet& last_set() const { return ms_; }
 
   // ---- Searcher options (reference src/search.rs:441-483) ------------------------------------
   void set_trace(bool trace) { without_trace_ = !trace; }          // with_trace / without_trace / set_trace
