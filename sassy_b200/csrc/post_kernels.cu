@@ -252,14 +252,21 @@ __global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const 
       cs.at((0 * W + lane) * F + 1) = 0;
     }
     uint32_t carry = 0;
+    // equality word of the next step fetched one step ahead (it does not depend on the carries)
+    auto fetch = [&](int32_t c) -> uint32_t {
+      if (lane >= (uint32_t)W || c < 0 || c >= (int32_t)wlen) return 0u;
+      const uint8_t tc = staged ? wbuf[c] : text_at_dir(text, n, rev, off + (uint64_t)c);
+      return __ldg(eq + (((uint32_t)tc >> t.sh0) & (t.msk0 & 0xFFu)) * W + lane);
+    };
+    uint32_t eq_next = fetch(-(int32_t)lane);
     for (uint32_t step = 0; step < wlen + (uint32_t)W - 1; step++) {
       const int32_t c = (int32_t)step - (int32_t)lane;  // this lane's column is c + 1
+      const uint32_t eq_cur = eq_next;
+      eq_next = fetch(c + 1);
       uint32_t cout = 0;
       if (lane < (uint32_t)W && c >= 0 && c < (int32_t)wlen) {
-        const uint8_t tc = staged ? wbuf[c] : text_at_dir(text, n, rev, off + (uint64_t)c);
-        const uint32_t row = ((uint32_t)tc >> t.sh0) & (t.msk0 & 0xFFu);
         uint32_t ph, mh;
-        trace_word(pv, mv, __ldg(eq + row * W + lane), carry, cout, ph, mh);
+        trace_word(pv, mv, eq_cur, carry, cout, ph, mh);
         const uint32_t slot = (((uint32_t)c + 1) * W + lane) * F;
         *reinterpret_cast<uint4*>(&cs.at(slot)) = make_uint4(pv, mv, ph, mh);  // 16-byte aligned: slot % 4 == 0
       }

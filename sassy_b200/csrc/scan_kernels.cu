@@ -710,13 +710,22 @@ __global__ void __launch_bounds__(32 * kWideWarps)
     uint32_t carry = 0;  // carries handed over by the previous lane for the character of this step
     int score = a.m;
     const int32_t emit_rel = (int32_t)(emit_from - w0);
+    // the equality word of a step does not depend on the carries: it is fetched one step ahead, so
+    // the chain between two steps is the word step and the shuffle only
+    auto fetch = [&](int32_t idx) -> uint32_t {
+      if (lane >= (uint32_t)W || idx < 0 || idx >= Lc) return 0u;
+      const uint32_t row = ((uint32_t)win[warp][idx] >> a.sh0) & (a.msk0 & 0xFFu);
+      return __ldg(eq + row * W + lane);
+    };
+    uint32_t eq_next = fetch(-(int32_t)lane);
     for (int32_t t = 0; t < Lc + W - 1; t++) {
       const int32_t idx = t - (int32_t)lane;
+      const uint32_t eq_cur = eq_next;
+      eq_next = fetch(idx + 1);
       uint32_t cout = 0;
       if (lane < (uint32_t)W && idx >= 0 && idx < Lc) {
-        const uint32_t row = ((uint32_t)win[warp][idx] >> a.sh0) & (a.msk0 & 0xFFu);
         uint32_t ph, mh;
-        myers_word(pv, mv, __ldg(eq + row * W + lane), carry, cout, ph, mh);
+        myers_word(pv, mv, eq_cur, carry, cout, ph, mh);
         if (lane == (uint32_t)(W - 1)) {
           score += (int)(ph >> 31) - (int)(mh >> 31);
           if (idx >= emit_rel && score <= a.k) emit_candidate(a, qs, (uint64_t)(w0 + idx) + 1, score);
