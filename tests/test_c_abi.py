@@ -74,3 +74,19 @@ def test_no_cpu_fallback_without_a_device():
         pass
     else:
         raise AssertionError("Searcher must not construct without a GPU")
+
+
+def build_c_caller(tmp_path):
+    exe = tmp_path / "abi_caller"
+    libdir = os.path.join(ROOT, "sassy_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", INC, os.path.join(ROOT, "tests", "c", "abi_caller.c"),
+                           "-L", libdir, "-lsassy_b200", "-Wl,-rpath," + libdir, "-lm", "-o", str(exe)])
+    return str(exe)
+
+
+def test_c_caller_compiles_and_links(tmp_path):
+    """A C program written against include/*.h links against libsassy_b200.so (like the reference's
+    c/example.c against libsassy)."""
+    from sassy_b200 import _native
+    _native.load()  # the library is built
+    assert os.path.exists(build_c_caller(tmp_path))

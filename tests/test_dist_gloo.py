@@ -73,3 +73,52 @@ def test_pack_roundtrip():
           Match(0, 0, 2**35, 2**35 + 70, 0, 64, 0, "+", "=" * 64 + "DDDDDD")]
     t = sd.pack_matches(ms, 3)
     assert sd.unpack_matches(t) == ms
+
+
+def _worker_ml(rank, world, port, q):
+    """gather_matches on MatchList inputs (the form the GPU path returns) incl. a growing block."""
+    import numpy as np
+    import torch.distributed as dist
+    from sassy_b200 import dist as sd
+    from sassy_b200.searcher import MatchList, _REC_DTYPE
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = []
+    for n in (3, 0 if rank == 0 else 700, 5):  # 700 > the initial capacity of 256: the block grows
+        recs = np.zeros(n, dtype=_REC_DTYPE)
+        ops = []
+        off = 0
+        for i in range(n):
+            o = "=" * (10 + (i + rank) % 7) + "X"
+            recs[i] = (i, 0, 100 * i + rank, 100 * i + rank + len(o), 0, len(o), 1, rank, (0, 0, 0), len(o), 0, off)
+            ops.append(o)
+            off += len(o)
+        ml = sd.tag_rank(MatchList(recs, "".join(ops).encode()), rank)
+        g = sd.gather_matches(ml, max_ops=24)
+        out.append(sorted((m.pattern_idx, m.text_idx, m.text_start, m.text_end, m.cost, m.strand, m.cigar) for m in g))
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_matchlists_and_rank_tags():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ml, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for got, sizes in zip(out, ((3, 3), (0, 700), (5, 5))):
+        assert len(got) == sum(sizes)
+        for rank, n in enumerate(sizes):
+            mine = [g for g in got if g[1] == rank]  # text_idx = source rank
+            assert len(mine) == n
+            for i, g in enumerate(sorted(mine)):
+                o = 10 + (i + rank) % 7
+                assert g == (i, rank, 100 * i + rank, 100 * i + rank + o + 1, 1, "-" if rank else "+", f"{o}=1X")

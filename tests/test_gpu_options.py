@@ -266,3 +266,11 @@ def test_reference_c_abi_with_alpha():
     assert got[0] == (0, 4, 4, 8, 2, 0)  # src/search.rs:2929-2942
     lib.sassy_matches_free(out, n)
     lib.sassy_searcher_free(h)
+
+
+def test_c_program_against_the_library(tmp_path):
+    """The doctest of the reference (src/lib.rs:62-107: ATCG in CCCATCACCC, k = 1) from a plain C program."""
+    import subprocess
+    from tests.test_c_abi import build_c_caller
+    out = subprocess.check_output([build_c_caller(tmp_path), "dna", "ATCG", "CCCATCACCC", "1"]).decode().splitlines()
+    assert out == ["3 7 0 4 1 0", "1 5 0 4 1 1", "cigar 3=1X", "cigar 2=1X1="]
