@@ -317,6 +317,22 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   return res;
 }
 
+// The prefilter plan for inspection in tests: out = {enabled, WF, npieces, L, then (off, len, word, bit) per piece};
+// returns the number of ints written (<= cap).
+int emu_plan_filter(int profile, const uint8_t* queries, uint32_t nq, int m, int k, double max_cost, int* out, int cap) {
+  std::vector<const uint8_t*> qptr(nq);
+  for (uint32_t q = 0; q < nq; q++) qptr[q] = queries + (size_t)q * m;
+  const FilterPlan fp = plan_filter(profile, qptr.data(), nq, m, k, max_cost);
+  int n = 0;
+  auto put = [&](int v) {
+    if (n < cap) out[n] = v;
+    n++;
+  };
+  put(fp.enabled ? 1 : 0), put(fp.WF), put(fp.npieces), put(fp.L);
+  for (int p = 0; p < fp.npieces; p++) put(fp.piece[p].off), put(fp.piece[p].len), put(fp.piece[p].word), put(fp.piece[p].bit);
+  return n;
+}
+
 size_t emu_len(const EmuResult* r) { return r->m.size(); }
 const GpuMatch* emu_matches(const EmuResult* r) { return r->m.data(); }
 const uint32_t* emu_ops(const EmuResult* r) { return r->ops.data(); }

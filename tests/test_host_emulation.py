@@ -1,6 +1,7 @@
 """CPU-only checks of the logic the CUDA kernels execute (scan_core.cuh / host_logic.h),
 run through the host emulator and compared with the oracle: known-answer vectors, then a
 seeded differential fuzz across row lengths so that matches straddle row boundaries."""
+import os
 import random
 
 import pytest
@@ -161,3 +162,41 @@ def test_emu_prefilter_eight_words():
                [(x.text_start, x.text_end, x.cost, x.strand, x.cigar) for x in want]
         used.add(b.last_filter[0])
     assert 8 in used
+
+
+def test_filter_plan_invariants():
+    """plan_filter (csrc/host_logic.h): k + 1 pairwise disjoint pieces inside the pattern, every piece
+    with its 3 delay bits inside one 32-bit automaton word, no two pieces sharing a bit."""
+    import ctypes
+    from tests import emu_backend
+    lib = emu_backend._lib() if hasattr(emu_backend, "_lib") else ctypes.CDLL(
+        os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sassy_b200", "lib", "libsassy_b200_emu.so"))
+    lib.emu_plan_filter.restype = ctypes.c_int
+    lib.emu_plan_filter.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_double, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    rng = random.Random(19)
+    seen_words = set()
+    for it in range(400):
+        m = rng.choice([4, 8, 20, 23, 50, 100, 300, 1000])
+        k = rng.randrange(0, min(m - 1, 20) + 1)
+        q = rand_seq(rng, m)
+        buf = (ctypes.c_int * 512)()
+        n = lib.emu_plan_filter(0, q, 1, m, k, 1e30, buf, 512)
+        enabled, WF, npieces, L = buf[0], buf[1], buf[2], buf[3]
+        if not enabled:
+            continue
+        assert n == 4 + 4 * npieces and npieces == k + 1 and WF in (1, 2, 4, 8)
+        seen_words.add(WF)
+        pieces = [tuple(buf[4 + 4 * i:8 + 4 * i]) for i in range(npieces)]
+        covered = set()
+        bits = {}
+        for off, ln, word, bit in pieces:
+            assert ln >= L >= 1 and 0 <= off and off + ln <= m and 0 <= word < WF
+            span = set(range(off, off + ln))
+            assert not (span & covered)
+            covered |= span
+            used = set(range(bit, bit + ln + 3))  # the piece and its delay line
+            assert max(used) < 32
+            assert not (used & bits.setdefault(word, set()))
+            bits[word] |= used
+    assert seen_words == {1, 2, 4, 8}
