@@ -90,6 +90,9 @@ extern "C" {
 
 int sassy_gpu_device_count(void);
 const char *sassy_gpu_last_error(void);
+/* Device facts for the self-check (the reference's `sassy test` prints CPU features, src/lib.rs:187-281). */
+int sassy_gpu_device_info(int device, char *name, size_t name_cap, int *sm_count, int *sm_clock_mhz,
+                          size_t *total_mem, int *cc_major, int *cc_minor);
 
 /* Like sassy_searcher (src/c.rs:51-70) with an explicit CUDA device; NULL on error. */
 sassy_SearcherType *sassy_gpu_searcher(const char *alphabet, bool rc, float alpha, int device);

@@ -86,6 +86,9 @@ SIGNATURES = {
     # include/sassy_gpu.h
     "sassy_gpu_device_count": (ctypes.c_int, []),
     "sassy_gpu_last_error": (ctypes.c_char_p, []),
+    "sassy_gpu_device_info": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, c_size_t, ctypes.POINTER(ctypes.c_int),
+                                             ctypes.POINTER(ctypes.c_int), ctypes.POINTER(c_size_t),
+                                             ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "sassy_gpu_searcher": (c_void_p, [ctypes.c_char_p, ctypes.c_bool, ctypes.c_float, ctypes.c_int]),
     "sassy_gpu_set_variant": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "sassy_gpu_set_filter": (ctypes.c_int, [c_void_p, ctypes.c_int]),

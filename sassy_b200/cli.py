@@ -228,6 +228,53 @@ def run_crispr(args, out, make_searcher: Callable = _default_searcher, log=sys.s
     return total
 
 
+def run_selfcheck(out=sys.stderr) -> int:
+    """`sassy test` (src/lib.rs:187-281 prints CPU features and a throughput figure): the device the
+    library would use, the reference's doctest as a known answer, and search throughput."""
+    import ctypes
+    import random
+    import time
+    from . import _native, Searcher
+    lib = _native.load()
+    n_dev = lib.sassy_gpu_device_count()
+    print(f"libsassy_b200: {_native.LIB_PATH}", file=out)
+    print(f"CUDA devices: {n_dev}", file=out)
+    if n_dev == 0:
+        print("no CUDA device: this library has no CPU fallback", file=out)
+        return 1
+    for d in range(n_dev):
+        name = ctypes.create_string_buffer(128)
+        sms, mhz, cmaj, cmin = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        mem = ctypes.c_size_t()
+        lib.sassy_gpu_device_info(d, name, 128, ctypes.byref(sms), ctypes.byref(mhz), ctypes.byref(mem),
+                                  ctypes.byref(cmaj), ctypes.byref(cmin))
+        ok = "+" if cmaj.value >= 10 else "- (needs sm_100a)"
+        print(f"  [{d}] {name.value.decode()}  sm_{cmaj.value}{cmin.value} {ok}  {sms.value} SMs  {mhz.value} MHz  "
+              f"{mem.value / 2**30:.0f} GiB", file=out)
+    s = Searcher("dna", rc=True)
+    got = [(m.text_start, m.text_end, m.cost, m.strand, m.cigar) for m in s.search(b"ATCG", b"CCCATCACCC", 1)]
+    want = [(3, 7, 1, "+", "3=1X"), (1, 5, 1, "-", "2=1X1=")]  # src/lib.rs:72-107
+    print(f"known answer (src/lib.rs doctest): {'ok' if got == want else 'MISMATCH ' + repr(got)}", file=out)
+    rng = random.Random(1)
+    n = 1 << 28
+    block = bytes(rng.choice(b"ACGT") for _ in range(1 << 16))
+    text = block * (n // len(block))
+    pattern = bytes(rng.choice(b"ACGT") for _ in range(23))
+    si = Searcher("iupac", rc=False)
+    dt = si.upload_text(text)
+    si.search(pattern, dt, 1)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        si.search(pattern, dt, 1)
+    el = (time.perf_counter() - t0) / 10
+    print(f"23 bp pattern, k = 1, {n >> 20} MiB text resident in HBM: {n / el / 1e9:.0f} GB/s", file=out)
+    t0 = time.perf_counter()
+    si.search(pattern, text, 1)
+    el = time.perf_counter() - t0
+    print(f"same search from a host buffer (copy included): {n / el / 1e9:.1f} GB/s", file=out)
+    return 0 if got == want else 1
+
+
 def _base_args(p: argparse.ArgumentParser) -> None:
     p.add_argument("-p", "--pattern")
     p.add_argument("-l", "--pattern-file")
@@ -254,6 +301,7 @@ def build_parser() -> argparse.ArgumentParser:
     f = sub.add_parser("filter", help="matching (or with -v non-matching) records on stdout")
     _base_args(f)
     f.add_argument("--search", nargs="?", const="-", help="also write the TSV of all matches here")
+    sub.add_parser("test", help="self-check: device, known answer, throughput")
     c = sub.add_parser("crispr", help="CRISPR off-target search")
     c.add_argument("-g", "--guide", required=True)
     c.add_argument("-k", "--k", type=int, required=True)
@@ -277,6 +325,8 @@ def _writer(path: Optional[str]):
 
 def main(argv: Optional[Sequence[str]] = None, make_searcher: Callable = _default_searcher) -> int:
     args = build_parser().parse_args(argv)
+    if args.cmd == "test":
+        return run_selfcheck()
     if args.cmd == "crispr":
         out, close = _writer(args.output or "-")
         try:

@@ -556,6 +556,28 @@ int sassy_gpu_device_count(void) {
 
 const char* sassy_gpu_last_error(void) { return g_last_error.c_str(); }
 
+int sassy_gpu_device_info(int device, char* name, size_t name_cap, int* sm_count, int* sm_clock_mhz,
+                          size_t* total_mem, int* cc_major, int* cc_minor) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    cudaGetLastError();
+    g_last_error = "no such CUDA device";
+    return 1;
+  }
+  if (name && name_cap) {
+    strncpy(name, prop.name, name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (sm_clock_mhz) *sm_clock_mhz = khz / 1000;
+  if (total_mem) *total_mem = prop.totalGlobalMem;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
 sassy_SearcherType* sassy_gpu_searcher(const char* alphabet, bool rc, float alpha, int device) {
   return guarded([&]() -> sassy_SearcherType* {
     if (!alphabet) throw std::invalid_argument("Alphabet pointer must not be null");
