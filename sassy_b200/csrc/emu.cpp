@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <numeric>
 #include <vector>
 
@@ -148,15 +149,96 @@ struct EmuResult {
   ScanGeom g;
 };
 
+// The two end zones the overhang changes, per query: the body of overhang_edges_kernel
+// (scan_kernels.cu) on the host.
+template <int W>
+void edges_rows(const ScanArgs& a, const uint32_t* eq, uint32_t slot, bool rev, const uint8_t* text, uint64_t n,
+                const uint32_t* init_pv, int left_total, uint32_t steps, float alpha) {
+  if (n + steps == 0) return;
+  const uint64_t span = (uint64_t)a.m + (uint64_t)a.k;
+  Lane<W> init;
+  for (int w = 0; w < W; w++) init.pv[w] = init_pv[w], init.mv[w] = 0;
+  uint32_t wild[W];
+  for (int w = 0; w < W; w++) wild[w] = 0xFFFFFFFFu;
+  {  // left: end positions 0 .. min(n, m+k)
+    if (left_total <= a.k) emit_candidate(a, slot, 0, left_total);
+    Lane<W> s = init;
+    const uint64_t lim = n < span ? n : span;
+    for (uint64_t i = 0; i < lim; i++) {
+      const uint8_t c = text_at_dir(text, n, rev, i);
+      myers_step<W>(s, eq + (((uint32_t)c >> a.sh0) & (a.msk0 & 0xFFu)) * W);
+      const int sc = lane_score<W>(s);
+      if (sc <= a.k) emit_candidate(a, slot, i + 1, sc);
+    }
+  }
+  if (steps > 0) {  // right: end positions n+1 .. n+steps
+    const uint64_t w0 = n > span ? n - span : 0;
+    Lane<W> s;
+    if (w0 == 0)
+      s = init;
+    else
+      lane_reset<W>(s, a.m);
+    for (uint64_t i = w0; i < n; i++) {
+      const uint8_t c = text_at_dir(text, n, rev, i);
+      myers_step<W>(s, eq + (((uint32_t)c >> a.sh0) & (a.msk0 & 0xFFu)) * W);
+    }
+    for (uint32_t o = 1; o <= steps; o++) {
+      myers_step<W>(s, wild);
+      const int sc = lane_score<W>(s) + overhang_overshoot_cost(alpha, o);
+      if (sc <= a.k) emit_candidate(a, slot, n + o, sc);
+    }
+  }
+}
+
+void edges_dispatch(int W, const ScanArgs& a, const uint32_t* eq, uint32_t slot, bool rev, const uint8_t* text,
+                    uint64_t n, const uint32_t* init_pv, int left_total, uint32_t steps, float alpha) {
+  switch (W) {
+    case 1: edges_rows<1>(a, eq, slot, rev, text, n, init_pv, left_total, steps, alpha); break;
+    case 2: edges_rows<2>(a, eq, slot, rev, text, n, init_pv, left_total, steps, alpha); break;
+    case 3: edges_rows<3>(a, eq, slot, rev, text, n, init_pv, left_total, steps, alpha); break;
+    case 4: edges_rows<4>(a, eq, slot, rev, text, n, init_pv, left_total, steps, alpha); break;
+    case 6: edges_rows<6>(a, eq, slot, rev, text, n, init_pv, left_total, steps, alpha); break;
+    case 8: edges_rows<8>(a, eq, slot, rev, text, n, init_pv, left_total, steps, alpha); break;
+    case 16: edges_rows<16>(a, eq, slot, rev, text, n, init_pv, left_total, steps, alpha); break;
+    case 32: edges_rows<32>(a, eq, slot, rev, text, n, init_pv, left_total, steps, alpha); break;
+    default: abort();
+  }
+}
+
 extern "C" {
 
 // queries: nq * m bytes; rev[q] = 1 scans the reversed text.  ltot_override > 0
 // forces the row length (to exercise row boundaries on tiny texts); bpw plays
 // the part of "resident blocks per wave" in the tiling heuristic.  use_filter: 0 = full
 // scan, 1 = prefilter + verification whenever a piece layout exists, -1 = the engine's rule.
+// Options of the post-processing (SearchOpts in engine.h); the same per-thread functions as the
+// kernels run here on the host: end_filter_pass, n_fraction_ok, trace_one_ov, and the edge
+// computation of overhang_edges_kernel (scan_kernels.cu) restated below.
+struct EmuOpts {
+  int without_trace, only_best, n_endpoint;
+  float max_n_frac;      // < 0: off
+  const uint8_t* pam;
+  int pam_len;
+  float alpha;           // < 0: off
+  int max_overhang;      // < 0: unlimited
+};
+
+EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* rev, uint32_t nq, int m,
+                           const uint8_t* text, uint64_t n, int k, int all_minima, int include_pos0,
+                           uint32_t ltot_override, int bpw, int use_filter, const EmuOpts* eo);
+
 EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, uint32_t nq, int m,
                       const uint8_t* text, uint64_t n, int k, int all_minima, int include_pos0,
                       uint32_t ltot_override, int bpw, int use_filter) {
+  return emu_search_opts(profile, queries, rev, nq, m, text, n, k, all_minima, include_pos0, ltot_override, bpw,
+                         use_filter, nullptr);
+}
+
+EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* rev, uint32_t nq, int m,
+                           const uint8_t* text, uint64_t n, int k, int all_minima, int include_pos0,
+                           uint32_t ltot_override, int bpw, int use_filter, const EmuOpts* eo) {
+  const bool ov = eo && eo->alpha >= 0.f;
+  if (ov) use_filter = 0;  // as Engine::search: no prefilter with overhang
   ProfileParams pp;
   if (!profile_params(profile, pp) || m <= 0) return nullptr;
   const int W = round_words((m + 31) / 32);
@@ -179,11 +261,13 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   if (n) memcpy(padded.data(), text, n);
 
   // with the prefilter every hit word may report up to 4+m+k positions (overlapping windows)
-  const uint64_t cap = (uint64_t)nq * (n / 4 + 2) * (uint64_t)(use_filter ? 8 + (m + k) / 4 : 4) + 64;
+  // (with overhang: up to m more end positions beyond the text per query)
+  const uint64_t cap = (uint64_t)nq * (n / 4 + 2) * (uint64_t)(use_filter ? 8 + (m + k) / 4 : 4) + 64 +
+                       (ov ? (uint64_t)nq * (uint64_t)(m + k + 8) : 0);
   std::vector<uint64_t> keys(cap);
   std::vector<uint32_t> cost(cap);
   unsigned long long count = 0;
-  if (include_pos0 && m <= k && n > 0)
+  if (include_pos0 && m <= k && n > 0 && !ov)
     for (uint32_t q = 0; q < nq; q++) {
       keys[count] = cand_key(q, 0);
       cost[count] = (uint32_t)m;
@@ -205,6 +289,7 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   a.cand_cost = cost.data();
   a.cand_count = &count;
   a.cand_cap = cap;
+  if (ov) a.emit_min = std::min<uint64_t>(n, (uint64_t)m + (uint64_t)k);
   std::vector<const uint8_t*> qptr(nq);
   for (uint32_t q = 0; q < nq; q++) qptr[q] = queries + (size_t)q * m;
   FilterPlan fp;
@@ -266,7 +351,26 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
       }
     }
   }
+  if (ov) {  // the two edges per query (overhang_edges_kernel)
+    std::vector<uint32_t> init_pv(W, 0);
+    const int pad = 32 * W - m;
+    for (int j = 0; j < m; j++)
+      if (overhang_left_cost(j + 1, eo->alpha, eo->max_overhang) - overhang_left_cost(j, eo->alpha, eo->max_overhang))
+        init_pv[(pad + j) >> 5] |= 1u << ((pad + j) & 31);
+    const int left_total = overhang_left_cost(m, eo->alpha, eo->max_overhang);
+    const float r = ceilf(((float)k + eo->alpha) / eo->alpha);
+    uint64_t steps = std::isnan(r) ? 0 : (r >= 1e18f ? ~0ull : (uint64_t)r);
+    steps = std::min<uint64_t>(steps, (uint64_t)m);
+    if (eo->max_overhang >= 0) steps = std::min<uint64_t>(steps, (uint64_t)eo->max_overhang);
+    for (uint32_t q = 0; q < nq; q++)
+      edges_dispatch(W, a, &eq[(size_t)q * pp.nrows * W], q, rev[q] != 0, padded.data(), n, init_pv.data(),
+                     left_total, (uint32_t)steps, eo->alpha);
+  }
   res->candidates = count;
+  if (count > cap) {  // the emulator's buffer is sized for the worst case; never read beyond it
+    delete res;
+    return nullptr;
+  }
 
   // sort by key (the GPU path uses a device radix sort)
   std::vector<uint64_t> order(count);
@@ -275,44 +379,83 @@ EmuResult* emu_search(int profile, const uint8_t* queries, const uint8_t* rev, u
   std::vector<uint64_t> skeys(count);
   std::vector<uint32_t> scost(count);
   for (uint64_t i = 0; i < count; i++) skeys[i] = keys[order[i]], scost[i] = cost[order[i]];
+  EndFilter ef;
+  memset(&ef, 0, sizeof ef);
+  const bool end_filter = eo && (eo->pam_len > 0 || (eo->n_endpoint && eo->max_n_frac >= 0.f));
+  if (end_filter) {
+    ef.text = TextRef{padded.data(), n, nullptr, nullptr, nq};
+    ef.rev_flags = rev;
+    ef.profile = profile;
+    ef.m = m, ef.k = k;
+    ef.pam_len = eo->pam_len;
+    for (int i = 0; i < eo->pam_len; i++) ef.pam[0][i] = eo->pam[i], ef.pam[1][i] = complement_byte(profile, eo->pam[i]);
+    ef.n_endpoint = (eo->n_endpoint && eo->max_n_frac >= 0.f) ? 1 : 0;
+    ef.max_n_frac = eo->max_n_frac;
+  }
   std::vector<uint64_t> sel;
+  std::vector<uint32_t> sel_cost;
   for (uint64_t i = 0; i < count; i++)
-    if (select_candidate(skeys.data(), scost.data(), i, count, all_minima != 0)) sel.push_back(skeys[i]);
+    if (select_candidate(skeys.data(), scost.data(), i, count, all_minima != 0) &&
+        (!end_filter || end_filter_pass(ef, skeys[i])))
+      sel.push_back(skeys[i]), sel_cost.push_back(scost[i]);
+  if (eo && eo->only_best) {  // launch_best: minimal cost, rightmost end, per query slot
+    std::vector<uint64_t> bk;
+    std::vector<uint32_t> bc;
+    for (uint32_t q = 0; q < nq; q++) {
+      int best = -1;
+      for (size_t i = 0; i < sel.size(); i++)
+        if (key_qs(sel[i]) == q && (best < 0 || sel_cost[i] < sel_cost[best] ||
+                                    (sel_cost[i] == sel_cost[best] && key_pos(sel[i]) > key_pos(sel[best]))))
+          best = (int)i;
+      if (best >= 0) bk.push_back(sel[best]), bc.push_back(sel_cost[best]);
+    }
+    sel = bk, sel_cost = bc;
+  }
 
-  res->m.resize(sel.size());
-  res->ops.assign(sel.size() * res->ops_words, 0);
   std::vector<uint32_t> scratch((size_t)trace_words_per_match(m, k, W));
   for (size_t i = 0; i < sel.size(); i++) {
     const uint32_t qs = key_qs(sel[i]);
+    const uint64_t end = key_pos(sel[i]);
     ColStore cs;
     cs.base = scratch.data();
     cs.stride = 1;
     TraceOut out;
     const uint8_t* pat = queries + (size_t)qs * m;
     const uint32_t* eq_q = &eq[(size_t)qs * pp.nrows * W];
-    uint32_t* ops = &res->ops[i * res->ops_words];
-    switch (profile) {
-      case kDna:
-        trace_one<kDna>(padded.data(), n, rev[qs] != 0, pat, m, k, eq_q, W, pp.sh0, pp.msk0, key_pos(sel[i]), cs, ops,
-                        res->ops_words, out);
-        break;
-      case kIupac:
-        trace_one<kIupac>(padded.data(), n, rev[qs] != 0, pat, m, k, eq_q, W, pp.sh0, pp.msk0, key_pos(sel[i]), cs,
-                          ops, res->ops_words, out);
-        break;
-      default:
-        trace_one<kAscii>(padded.data(), n, rev[qs] != 0, pat, m, k, eq_q, W, pp.sh0, pp.msk0, key_pos(sel[i]), cs,
-                          ops, res->ops_words, out);
-        break;
-    }
+    std::vector<uint32_t> ops(res->ops_words, 0);
+    const bool rv = rev[qs] != 0;
     GpuMatch gm;
-    gm.text_start = out.text_start;
-    gm.text_end = out.text_end;
     gm.qs = qs;
-    gm.cost = out.cost;
-    gm.nops = out.nops;
-    gm.failed = out.failed;
-    res->m[i] = gm;
+    if (eo && eo->without_trace) {  // trace_kernel, costs branch
+      gm.text_start = ~0ull;
+      gm.text_end = end < n ? end : n;
+      gm.cost = (int32_t)sel_cost[i];
+      gm.nops = 0;
+      gm.failed = pack_overhang(0, end > n ? (uint32_t)(end - n) : 0u);
+    } else {
+#define EMU_TRACE(P)                                                                                              \
+  if (ov)                                                                                                         \
+    trace_one_ov<P>(padded.data(), n, rv, pat, m, k, eq_q, W, pp.sh0, pp.msk0, end, eo->alpha, eo->max_overhang,  \
+                    cs, ops.data(), res->ops_words, out);                                                        \
+  else                                                                                                            \
+    trace_one<P>(padded.data(), n, rv, pat, m, k, eq_q, W, pp.sh0, pp.msk0, end, cs, ops.data(), res->ops_words, out);
+      switch (profile) {
+        case kDna: EMU_TRACE(kDna) break;
+        case kIupac: EMU_TRACE(kIupac) break;
+        default: EMU_TRACE(kAscii) break;
+      }
+#undef EMU_TRACE
+      gm.text_start = out.text_start;
+      gm.text_end = out.text_end;
+      gm.cost = out.cost;
+      gm.nops = out.nops;
+      gm.failed = out.failed;
+      if (eo && eo->max_n_frac >= 0.f &&
+          !n_fraction_ok(padded.data(), n, rv, out.text_start, out.text_end < n ? out.text_end : n, eo->max_n_frac, 0))
+        continue;  // traced N filter: dropped
+    }
+    res->m.push_back(gm);
+    res->ops.insert(res->ops.end(), ops.begin(), ops.end());
   }
   return res;
 }

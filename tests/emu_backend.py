@@ -26,6 +26,13 @@ class _GpuMatch(ctypes.Structure):
     ]
 
 
+class _EmuOpts(ctypes.Structure):
+    _fields_ = [("without_trace", ctypes.c_int), ("only_best", ctypes.c_int), ("n_endpoint", ctypes.c_int),
+                ("max_n_frac", ctypes.c_float), ("pam", ctypes.c_char_p), ("pam_len", ctypes.c_int),
+                ("alpha", ctypes.c_float), ("max_overhang", ctypes.c_int)]
+
+
+USIZE_MAX = 2**64 - 1
 _LIB = None
 
 
@@ -37,6 +44,8 @@ def _lib():
         lib.emu_search.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int,
                                    ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
+        lib.emu_search_opts.restype = ctypes.c_void_p
+        lib.emu_search_opts.argtypes = lib.emu_search.argtypes + [ctypes.POINTER(_EmuOpts)]
         lib.emu_len.restype = ctypes.c_size_t
         lib.emu_len.argtypes = [ctypes.c_void_p]
         lib.emu_matches.restype = ctypes.POINTER(_GpuMatch)
@@ -71,11 +80,16 @@ class EmuBackend:
         self.last_filter = None
 
     def _run(self, alphabet, queries: Sequence[bytes], rev: Sequence[int], text: bytes, k: int, all_minima: bool,
-             pos0: bool):
+             pos0: bool, opts=None, raw=False):
         lib = _lib()
         m = len(queries[0])
-        r = lib.emu_search(PROFILE[alphabet.lower()], b"".join(queries), bytes(rev), len(queries), m, text,
-                           len(text), k, int(all_minima), int(pos0), self.ltot, self.bpw, self.use_filter)
+        if opts is None:
+            r = lib.emu_search(PROFILE[alphabet.lower()], b"".join(queries), bytes(rev), len(queries), m, text,
+                               len(text), k, int(all_minima), int(pos0), self.ltot, self.bpw, self.use_filter)
+        else:
+            r = lib.emu_search_opts(PROFILE[alphabet.lower()], b"".join(queries), bytes(rev), len(queries), m, text,
+                                    len(text), k, int(all_minima), int(pos0), self.ltot, self.bpw, self.use_filter,
+                                    ctypes.byref(opts))
         assert r, "emu_search failed"
         try:
             n = lib.emu_len(r)
@@ -87,10 +101,13 @@ class EmuBackend:
             out = []
             for i in range(n):
                 g = ms[i]
-                if g.failed:
+                if g.failed & 1:
                     raise OracleError("trace failed")
                 s = "".join(OPS[(ops[i * ow + (a >> 4)] >> ((a & 15) * 2)) & 3] for a in range(g.nops))
-                out.append((g.qs, g.text_start, g.text_end, g.cost, s))
+                if raw:
+                    out.append((g.qs, g.text_start, g.text_end, g.cost, s, (g.failed >> 8) & 0xFFF, g.failed >> 20))
+                else:
+                    out.append((g.qs, g.text_start, g.text_end, g.cost, s))
             return out
         finally:
             lib.emu_free(r)
@@ -110,6 +127,27 @@ class EmuBackend:
                 res.append(Match(0, ts, te, 0, len(pattern), cost, "+", rle(ops)))
             else:
                 res.append(Match(0, n - te, n - ts, 0, len(pattern), cost, "-", rle(ops)))
+        return res
+
+    def search_opts(self, alphabet, pattern: bytes, text: bytes, k: int, rc: bool = False, all_minima: bool = False,
+                    without_trace: bool = False, only_best: bool = False, max_n_frac=None, pam=None, alpha=None,
+                    max_overhang=None):
+        """v1 search under the Searcher options, with the mapping of Searcher::convert_v1 (searcher.cu)."""
+        queries, rev = [pattern], [0]
+        if rc:
+            queries.append(complement(alphabet, pattern))
+            rev.append(1)
+        o = _EmuOpts(int(without_trace), int(only_best), 1, -1.0 if max_n_frac is None else float(max_n_frac),
+                     pam, len(pam) if pam else 0, -1.0 if alpha is None else float(alpha),
+                     -1 if max_overhang is None else int(max_overhang))
+        n, m = len(text), len(pattern)
+        res = []
+        for qs, ts, te, cost, ops, ps, over in self._run(alphabet, queries, rev, text, k, all_minima, True, o, raw=True):
+            pstart = USIZE_MAX if without_trace else ps
+            if qs == 0:
+                res.append(Match(0, ts, te, pstart, m - over, cost, "+", rle(ops)))
+            else:
+                res.append(Match(0, n - te, USIZE_MAX if without_trace else n - ts, pstart, m - over, cost, "-", rle(ops)))
         return res
 
     def search_encoded(self, alphabet, patterns: Sequence[bytes], text: bytes, k: int, rc: bool = False,

@@ -200,3 +200,56 @@ def test_filter_plan_invariants():
             assert not (used & bits.setdefault(word, set()))
             bits[word] |= used
     assert seen_words == {1, 2, 4, 8}
+
+
+def okey(m):
+    return (m.text_start, m.text_end, m.pattern_start, m.pattern_end, m.cost, m.strand, m.cigar)
+
+
+@pytest.mark.parametrize("alphabet", ["dna", "iupac"])
+def test_emu_options_fuzz(alphabet):
+    """The post-processing functions the kernels share with the host (end_filter_pass, n_fraction_ok,
+    the only_best rule, the untraced record) against the oracle, without a GPU."""
+    rng = random.Random(41)
+    b = EmuBackend(ltot=256)
+    for it in range(150):
+        m = rng.choice([4, 8, 20, 33])
+        n = rng.randrange(0, 2500)
+        k = rng.randrange(0, max(1, m // 4) + 1)
+        p, t = planted(rng, m, max(n, 1), k)
+        t = bytearray(t[:n])
+        if alphabet == "iupac":
+            for _ in range(rng.randrange(0, 3)):
+                if len(t) > 2:
+                    a = rng.randrange(len(t))
+                    t[a:a + rng.randrange(1, 25)] = b"N" * min(rng.randrange(1, 25), len(t) - a)
+        t = bytes(t[:n])
+        opts = dict(without_trace=rng.random() < 0.3, only_best=rng.random() < 0.3,
+                    max_n_frac=rng.choice([None, 0.0, 0.2]) if alphabet == "iupac" else None)
+        pam = p[-3:] if rng.random() < 0.4 else None
+        allm = rng.random() < 0.5
+        want = oracle.search(alphabet, p, t, k, rc=True, all_minima=allm, pam=pam, **opts)
+        got = b.search_opts(alphabet, p, t, k, rc=True, all_minima=allm, pam=pam, **opts)
+        assert list(map(okey, got)) == list(map(okey, want)), (p, t, k, allm, opts, pam)
+
+
+def test_emu_overhang_fuzz():
+    """trace_one_ov, the overhang start state and the edge computation against the oracle."""
+    rng = random.Random(42)
+    b = EmuBackend(ltot=128)
+    for it in range(200):
+        m = rng.choice([3, 8, 20, 33, 70])
+        n = rng.choice([0, 1, 2, 5, 17, 40, 200, 1500]) if it % 3 else rng.randrange(0, 300)
+        k = rng.randrange(0, max(1, m // 3) + 1)
+        p, t = planted(rng, m, max(n, 1), k)
+        t = t[:n]
+        if n >= 4 and rng.random() < 0.7:
+            cut = rng.randrange(1, min(m, n))
+            t = (p[cut:] + t[len(p) - cut:])[:n] if rng.random() < 0.5 else (t[:n - cut] + p[:cut])[:n]
+        alpha = rng.choice([0.0, 0.3, 0.5, 1.0])
+        mo = rng.choice([None, None, 0, 2, 5])
+        opts = dict(without_trace=rng.random() < 0.2, only_best=rng.random() < 0.2)
+        for allm in (False, True):
+            want = oracle.search("iupac", p, t, k, rc=True, all_minima=allm, alpha=alpha, max_overhang=mo, **opts)
+            got = b.search_opts("iupac", p, t, k, rc=True, all_minima=allm, alpha=alpha, max_overhang=mo, **opts)
+            assert list(map(okey, got)) == list(map(okey, want)), (p, t, k, alpha, mo, allm, opts)
