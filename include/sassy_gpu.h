@@ -133,7 +133,7 @@ int sassy_gpu_set_max_n_frac(sassy_SearcherType *searcher, float max_n_frac);
 /* Searcher::with_max_overhang (src/search.rs:436-439); < 0 = unlimited.  Overhang itself is the
  * `alpha` of the constructor (Iupac only, 0 <= alpha <= 1, src/search.rs:373-400): pattern
  * characters hanging over a text end cost alpha each; matches then report pattern_start /
- * pattern_end inside the pattern.  Not available for encoded patterns or with a PAM filter. */
+ * pattern_end inside the pattern.  Cannot be combined with a PAM filter. */
 int sassy_gpu_set_max_overhang(sassy_SearcherType *searcher, int max_overhang);
 
 /* search_with_fn with the end filter of the reference's CRISPR mode: an end position is kept

@@ -104,6 +104,12 @@ def _lib():
             ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
         ]
         lib.oracle_search_encoded_nfrac.restype = ctypes.c_int
+        lib.oracle_search_encoded_opts.argtypes = [
+            ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p,
+            ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+            ctypes.c_int64, ctypes.c_void_p,
+        ]
+        lib.oracle_search_encoded_opts.restype = ctypes.c_int
         lib.oracle_bottom_row.argtypes = [
             ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
             ctypes.c_int, ctypes.c_void_p,
@@ -209,7 +215,8 @@ def search_many(alphabet: str, patterns: Sequence[bytes], texts: Sequence[bytes]
 
 
 def search_encoded(alphabet: str, patterns: Sequence[bytes], text: bytes, k: int, rc: bool = False,
-                   all_minima: bool = False, max_n_frac: float | None = None) -> List[Match]:
+                   all_minima: bool = False, max_n_frac: float | None = None, alpha: float | None = None,
+                   max_overhang: int | None = None) -> List[Match]:
     """encode_patterns + search_encoded_patterns / search_all_encoded_patterns."""
     lib = _lib()
     m = len(patterns[0])
@@ -217,8 +224,12 @@ def search_encoded(alphabet: str, patterns: Sequence[bytes], text: bytes, k: int
     out = lib.oracle_out_new()
     try:
         nf = -1.0 if max_n_frac is None or max_n_frac == 1.0 else float(max_n_frac)
-        r = lib.oracle_search_encoded_nfrac(PROFILE[alphabet.lower()], b"".join(patterns), len(patterns),
-                                            m, text, len(text), k, int(rc), int(all_minima), nf, out)
+        r = lib.oracle_search_encoded_opts(PROFILE[alphabet.lower()], b"".join(patterns), len(patterns),
+                                           m, text, len(text), k, int(rc), int(all_minima), nf,
+                                           -1.0 if alpha is None else float(alpha),
+                                           -1 if max_overhang is None else int(max_overhang), out)
+        if r == -4:
+            raise OracleError("Overhang is not supported for this profile")
         if r == -2:
             raise OracleError("Pattern is not valid IUPAC")
         if r != 0:

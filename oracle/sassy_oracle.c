@@ -620,6 +620,9 @@ int oracle_search_many(int profile, const uint8_t *patterns, const uint64_t *pat
 int oracle_search_encoded_nfrac(int profile, const uint8_t *patterns, size_t n_patterns, size_t m,
                                 const uint8_t *text, size_t n, uint32_t k, int rc_strand, int all,
                                 float max_n_frac, OracleOut *out);
+int oracle_search_encoded_opts(int profile, const uint8_t *patterns, size_t n_patterns, size_t m,
+                               const uint8_t *text, size_t n, uint32_t k, int rc_strand, int all,
+                               float max_n_frac, float alpha, int64_t max_overhang, OracleOut *out);
 
 int oracle_search_encoded(int profile, const uint8_t *patterns, size_t n_patterns, size_t m,
                           const uint8_t *text, size_t n, uint32_t k, int rc_strand, int all,
@@ -669,6 +672,41 @@ int oracle_search_encoded_nfrac(int profile, const uint8_t *patterns, size_t n_p
     free(c);
   }
   free(sel);
+  free(buf);
+  return rc;
+}
+
+/* Encoded patterns with overhang (PatterntilingSearcher::new(alpha), src/pattern_tiling/search.rs:
+ * 91-117,223-323).  The reference pins this engine to the v1 one: its fuzz_against_sassy_batch
+ * (src/pattern_tiling/search.rs:690-848, run with alpha = 0.5 at :886-896) requires the v2 matches
+ * to EQUAL -- all Match fields incl. pattern_start / pattern_end / CIGAR -- the forward v1 overhang
+ * search of every pattern and, for the rc strand, of its reverse complement with the strand
+ * relabelled.  That definition is restated here.                                                */
+int oracle_search_encoded_opts(int profile, const uint8_t *patterns, size_t n_patterns, size_t m,
+                               const uint8_t *text, size_t n, uint32_t k, int rc_strand, int all,
+                               float max_n_frac, float alpha, int64_t max_overhang, OracleOut *out) {
+  if (alpha < 0.f)
+    return oracle_search_encoded_nfrac(profile, patterns, n_patterns, m, text, n, k, rc_strand, all, max_n_frac, out);
+  init_tables();
+  if (profile != PROFILE_IUPAC) return -4;
+  if (m == 0 || m > 64) return -3;
+  for (size_t q = 0; q < n_patterns; q++)
+    if (!oracle_iupac_valid(patterns + q * m, m)) return -2;
+  OracleOpts o = {0, 0, max_n_frac, NULL, 0, alpha, max_overhang};
+  int rc = 0;
+  size_t nq = n_patterns * (rc_strand ? 2 : 1);
+  uint8_t *buf = (uint8_t *)malloc(m + 1);
+  for (size_t q = 0; q < nq; q++) {
+    const uint8_t *p = patterns + (q % n_patterns) * m;
+    if (q >= n_patterns) {
+      oracle_reverse_complement(PROFILE_IUPAC, p, m, buf);
+      p = buf;
+    }
+    size_t first = out->n;
+    if (v1_one_strand(profile, p, m, text, n, (int32_t)k, all, 0, (uint32_t)(q % n_patterns), 0, &o, out) != 0) rc = -1;
+    if (q >= n_patterns)
+      for (size_t i = first; i < out->n; i++) out->m[i].strand = 1;
+  }
   free(buf);
   return rc;
 }

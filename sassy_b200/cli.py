@@ -149,8 +149,6 @@ def run_search(args, match_out=None, filter_out=None, make_searcher: Callable = 
         raise SystemExit("No pattern sequences found")
     k = args.k
     rc = not args.no_rc
-    if args.overhang is not None and args.v2:
-        raise SystemExit("--overhang with --v2 is outside the GPU search path")
     # only the Iupac searcher gets the N filter (bin/grep.rs:489-497)
     searcher = make_searcher(args.alphabet, rc, args.max_n_frac if args.alphabet == "iupac" else None,
                              **({"alpha": args.overhang} if args.overhang is not None else {}))

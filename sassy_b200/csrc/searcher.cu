@@ -295,12 +295,16 @@ void Searcher::search_encoded_raw(const EncodedPatterns& enc, const DeviceText& 
   std::vector<Query> qs(enc.n_queries());
   for (size_t q = 0; q < qs.size(); q++) qs[q] = Query{&enc.bytes[q * enc.m], false};
   const int kk = (int)std::min<size_t>(k, 1u << 20);
-  if (alpha_ >= 0.f) throw std::invalid_argument("overhang with encoded patterns is outside the GPU search path");
-  // the v2 engine knows all_minima and max_n_frac only (traced filter, general.rs:399-402);
-  // without_trace / only_best_match do not reach it (src/search.rs:415-433)
+  // the v2 engine knows all_minima, max_n_frac (traced filter, general.rs:399-402) and the overhang
+  // (PatterntilingSearcher::new(alpha)); without_trace / only_best_match do not reach it
+  // (src/search.rs:415-433).  With overhang the reference pins v2 to the forward v1 search of every
+  // query (fuzz_against_sassy_batch, src/pattern_tiling/search.rs:690-848,886-896): same options.
   SearchOpts o;
   o.all_minima = all_minima;
   o.max_n_frac = max_n_frac_;
+  o.alpha = alpha_;
+  o.max_overhang = max_overhang_;
+  o.n_endpoint = alpha_ >= 0.f;
   engine_->search(text, qs, enc.m, kk, o, ms_);
 }
 
@@ -314,8 +318,8 @@ std::vector<Match> Searcher::convert_v2(const MatchSet& ms, size_t n_patterns, i
     mm.strand = g.qs >= n_patterns ? kRc : kFwd;
     mm.text_start = g.text_start;
     mm.text_end = g.text_end;
-    mm.pattern_start = 0;
-    mm.pattern_end = (uint64_t)m;
+    mm.pattern_start = (uint64_t)((g.failed >> 8) & 0xFFFu);  // overhang (scan_core.cuh pack_overhang), else 0
+    mm.pattern_end = (uint64_t)m - (uint64_t)(g.failed >> 20);
     mm.cost = g.cost;
     unpack_ops(ms, i, mm.ops);
   }
@@ -473,7 +477,8 @@ sassy_gpu_Result* to_result_v2(const sb::MatchSet& ms, size_t n_patterns, int m)
     o.strand = g.qs >= n_patterns ? 1 : 0;
     o.text_start = g.text_start;
     o.text_end = g.text_end;
-    o.pattern_end = (uint64_t)m;
+    o.pattern_start = (uint64_t)((g.failed >> 8) & 0xFFFu);
+    o.pattern_end = (uint64_t)m - (uint64_t)(g.failed >> 20);
     o.cost = g.cost;
     o.ops_off = off;
     o.ops_len = g.nops;

@@ -151,12 +151,20 @@ class EmuBackend:
         return res
 
     def search_encoded(self, alphabet, patterns: Sequence[bytes], text: bytes, k: int, rc: bool = False,
-                       all_minima: bool = False):
+                       all_minima: bool = False, alpha=None, max_overhang=None, max_n_frac=None):
         P = len(patterns)
         queries = list(patterns)
         if rc:
             queries += [reverse_complement("iupac", p) for p in patterns]
         res = []
+        if alpha is not None or max_n_frac is not None:  # Searcher::search_encoded_raw + convert_v2
+            o = _EmuOpts(0, 0, 1 if alpha is not None else 0, -1.0 if max_n_frac is None else float(max_n_frac), None, 0,
+                         -1.0 if alpha is None else float(alpha), -1 if max_overhang is None else int(max_overhang))
+            m = len(patterns[0])
+            for qs, ts, te, cost, ops, ps, over in self._run(alphabet, queries, [0] * len(queries), text, k,
+                                                             all_minima, False, o, raw=True):
+                res.append(Match(qs % P, ts, te, ps, m - over, cost, "-" if qs >= P else "+", rle(ops)))
+            return res
         for qs, ts, te, cost, ops in self._run(alphabet, queries, [0] * len(queries), text, k, all_minima, False):
             res.append(Match(qs % P, ts, te, 0, len(patterns[0]), cost, "-" if qs >= P else "+", rle(ops)))
         return res

@@ -274,3 +274,29 @@ def test_c_program_against_the_library(tmp_path):
     from tests.test_c_abi import build_c_caller
     out = subprocess.check_output([build_c_caller(tmp_path), "dna", "ATCG", "CCCATCACCC", "1"]).decode().splitlines()
     assert out == ["3 7 0 4 1 0", "1 5 0 4 1 1", "cigar 3=1X", "cigar 2=1X1="]
+
+
+def test_gpu_encoded_overhang():
+    """Encoded patterns with overhang: equal to the forward v1 overhang search of every query, as the
+    reference's fuzz_against_sassy_batch requires (src/pattern_tiling/search.rs:690-848,886-896)."""
+    import sassy_b200
+    rng = random.Random(38)
+    s = sassy_b200.Searcher("iupac", rc=True, alpha=0.5)
+    kk = lambda x: (x.pattern_idx, x.text_start, x.text_end, x.pattern_start, x.pattern_end, x.cost, x.strand, x.cigar)
+    for it in range(40):
+        m = rng.choice([5, 12, 23, 40, 59])
+        n = rng.choice([10, 30, 59, 300, 5000])
+        k = rng.randrange(0, 4)
+        pats = [rand_seq(rng, m) for _ in range(rng.randrange(1, 26))]
+        t = bytearray(rand_seq(rng, n))
+        cut = rng.randrange(1, min(m, n))
+        if rng.random() < 0.5:
+            t[:m - cut] = pats[0][cut:][:n]
+        else:
+            t[n - cut:] = pats[0][:cut]
+        t = bytes(t[:n])
+        enc = s.encode_patterns(pats)
+        for allm in (False, True):
+            want = oracle.search_encoded("iupac", pats, t, k, rc=True, all_minima=allm, alpha=0.5)
+            got = s.search_all_encoded_patterns(enc, t, k) if allm else s.search_encoded_patterns(enc, t, k)
+            assert sorted(map(kk, got)) == sorted(map(kk, want)), (it, m, n, k, allm)

@@ -253,3 +253,27 @@ def test_emu_overhang_fuzz():
             want = oracle.search("iupac", p, t, k, rc=True, all_minima=allm, alpha=alpha, max_overhang=mo, **opts)
             got = b.search_opts("iupac", p, t, k, rc=True, all_minima=allm, alpha=alpha, max_overhang=mo, **opts)
             assert list(map(okey, got)) == list(map(okey, want)), (p, t, k, alpha, mo, allm, opts)
+
+
+def test_emu_encoded_overhang_fuzz():
+    """Encoded patterns with overhang (defined by the reference's v2 == v1 fuzz, see oracle)."""
+    rng = random.Random(43)
+    b = EmuBackend(ltot=128)
+    for it in range(60):
+        m = rng.choice([5, 12, 23, 40])
+        n = rng.randrange(10, 200)
+        k = rng.randrange(0, 4)
+        pats = [rand_seq(rng, m) for _ in range(rng.randrange(1, 8))]
+        t = bytearray(rand_seq(rng, n))
+        p = pats[0]
+        cut = rng.randrange(1, min(m, n))
+        if rng.random() < 0.5:
+            t[:m - cut] = p[cut:][:n]
+        else:
+            t[n - cut:] = p[:cut]
+        t = bytes(t[:n])
+        for allm in (False, True):
+            want = oracle.search_encoded("iupac", pats, t, k, rc=True, all_minima=allm, alpha=0.5)
+            got = b.search_encoded("iupac", pats, t, k, rc=True, all_minima=allm, alpha=0.5)
+            kk = lambda x: (x.pattern_idx, x.text_start, x.text_end, x.pattern_start, x.pattern_end, x.cost, x.strand, x.cigar)
+            assert sorted(map(kk, got)) == sorted(map(kk, want)), (pats, t, k, allm)
