@@ -11,7 +11,10 @@
  * Parity pinning: the reference is Rust and cannot be compiled in this image
  * (no cargo/rustc), so this restatement is pinned against the known-answer
  * vectors held by the reference's own tests/docs (tests/golden/kat.json, each
- * entry cites its source file:line).
+ * entry cites its source file:line), and for the Searcher options, the PAM end
+ * filter, search_many and overhang against the reference's tests of those
+ * (tests/test_oracle_options.py, tests/test_cli.py: src/n_filter.rs:66-106,
+ * src/search.rs:2372-2607,2929-3058, bin/crispr.rs:264-362, bin/grep.rs:795-813).
  *
  * The DP is the plain O(m*n) column recurrence (no bit tricks), so that it is
  * independent of both the reference's and the CUDA path's bit-parallel code:
