@@ -1,23 +1,33 @@
 #!/usr/bin/env python
 """Benchmark of the Searcher::search hot path on B200 (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4|c5]
 
-One "step" = one search of the pattern (batch) over the rank's whole text.  Default
-workload = BASELINE.json configs[1]: Dna profile, one pattern of length 20, k=2, 3 GB of
-synthetic ACGT per GPU (weak scaling: every rank scans its own 3 GB shard; the match
-records are all-gathered over NCCL at the end of every step).
+One "step" = one search of the pattern (batch) over the text.  The top-level record is
+BASELINE.json configs[1] (c2): Dna profile, one pattern of length 20, k=2, 3 GB of synthetic
+ACGT per GPU.  At N > 1 the N x 3 GB form ONE text cut into N slabs with (m+k) halos; every rank
+searches its slab, the records are exchanged by the fused peer-memory gather and the local-minima
+rule runs on the merged list (sassy_b200.dist.search_text_sharded): weak scaling.
 
-Prints ONE JSON line (rank 0).  `value` = text bytes scanned per second with the text
-resident in HBM; `e2e` = the same search through the host-pointer C-ABI entry point
-(host->device copy of the text and device->host copy of the matches inside the timed
-region).  `--impl reference` times the CPU restatement of the reference's algorithm
-(oracle/, the reference itself is Rust and cannot be built here) on the host cores.
+The same JSON line carries the other BASELINE configs as sub-records under "configs":
+c3 and c4 (N = 1) and c5 (every N: patterns sharded round-robin, text replicated, match records
+gathered; a bounded pattern count, see --c5-patterns), each with ms_per_step, value,
+gchar_pattern_per_s, roofline, cpu_baseline and matches.
+
+Parity is asserted inside the run (a mismatch exits non-zero): GPU end positions and costs ==
+the CPU port's on the same text (whole text for c2/c4, a pattern sub-sample for c3/c5), the
+host-pointer path == the resident path, and at N > 1 the gathered result == the single-GPU
+search of the same job on rank 0.
+
+`value` = text bytes scanned per second with the text resident in HBM; `e2e` = the same search
+through the host-pointer C-ABI entry point (host->device copy of the text and device->host copy
+of the matches inside the timed region).  `--impl reference` times the CPU restatement of the
+reference's algorithm (oracle/; the reference itself is Rust and cannot be built here) on the
+host cores, on the same text (one generator for both arms).
 """
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import os
 import random
@@ -37,11 +47,13 @@ WORKLOADS = {
     "c3": ("iupac", 1024, 23, 4, 3_000_000_000, "Iupac, 1024 encoded patterns len=23 (20nt+NGG), k=4, 3 GB (BASELINE configs[2])"),
     "c4": ("dna", 1, 100, 8, 3_000_000_000, "Dna, 1 pattern len=100, k=8, 3 GB synthetic ACGT (BASELINE configs[3])"),
     # pattern shards: every rank holds the whole text and searches patterns rank, rank + N, ...;
-    # 100 000 x 3 GB is 3e14 character-pattern steps (minutes per step): use --patterns to bound a run
+    # 100 000 x 3 GB is 3e14 character-pattern steps (minutes per step): --c5-patterns bounds a run
     "c5": ("iupac", 100_000, 23, 3, 3_000_000_000, "Iupac, 100k encoded patterns len=23 (20nt+NGG), k=3, 3 GB, patterns sharded over the GPUs (BASELINE configs[4])"),
 }
 PATTERN_SHARDED = {"c5"}
 METRIC = "GB/s text scanned"
+SM_COUNT = 148
+PATTERN_SEED = {"dna": 43, "iupac": 45}
 
 
 def parse_args():
@@ -52,7 +64,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--text-bytes", type=int, default=0, help="override the text size (debug)")
-    ap.add_argument("--patterns", type=int, default=0, help="override the number of patterns (debug)")
+    ap.add_argument("--patterns", type=int, default=0, help="override the number of patterns of the top-level workload")
+    ap.add_argument("--c5-patterns", type=int, default=2048,
+                    help="patterns of the c5 sub-record (the first P of the 100 000; bounds the run time)")
+    ap.add_argument("--sub", default="auto", help="sub-records: auto (c3,c4,c5 at N=1; c5 at N>1), none, or a list like c3,c5")
+    ap.add_argument("--sub-steps", type=int, default=3)
     ap.add_argument("--variant", default="tma", choices=["tma", "ldg"])
     ap.add_argument("--filter", default="auto", choices=["off", "auto", "force"],
                     help="exact piece prefilter in front of the scan (result-neutral)")
@@ -63,16 +79,49 @@ def parse_args():
                     help="N > 1: fused peer-memory exchange of the match records (default) or NCCL all-gather")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-check", action="store_true", help="skip the in-bench parity assertions")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of a cpu_baseline sample")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------
-# synthetic workload (same on every leg): uniform ACGT text, uniform ACGT patterns, planted
-# copies with 0..k edits (seeded), cf. BASELINE.md section 2.
+# Synthetic workload, identical in both arms and on every rank: the character at absolute text
+# position p is a pure function of (seed, p) (splitmix64 of p // 32, two bits per character), so
+# any window of the global text can be generated anywhere, on the CPU or on the GPU, with the
+# same bytes.  Patterns: uniform ACGT (c3/c5: 20 nt + NGG).  Planted copies with 0..k edits.
 
-def make_patterns(profile, n_patterns, m, seed=43):
-    rng = random.Random(seed)
+_LUT = {}
+
+
+def synth_text(torch, n, offset, seed, device, chunk=1 << 27):
+    dev = torch.device(device)
+    if dev not in _LUT:
+        acgt = [65, 67, 71, 84]
+        vals = [sum(acgt[(b >> (2 * j)) & 3] << (8 * j) for j in range(4)) for b in range(256)]
+        vals = [v - (1 << 32) if v >= (1 << 31) else v for v in vals]
+        _LUT[dev] = torch.tensor(vals, dtype=torch.int32, device=dev)
+    lut = _LUT[dev]
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    first_blk, last_blk = offset // 32, (offset + n + 31) // 32
+    cb = chunk // 32
+    for b0 in range(first_blk, last_blk, cb):
+        b1 = min(last_blk, b0 + cb)
+        x = torch.arange(b0, b1, dtype=torch.int64, device=dev)
+        x = (x + seed * 0x1000003) * -7046029254386353131  # 0x9E3779B97F4A7C15
+        x = x ^ ((x >> 30) & ((1 << 34) - 1))
+        x = x * -4658895280553007687  # 0xBF58476D1CE4E5B9
+        x = x ^ ((x >> 27) & ((1 << 37) - 1))
+        x = x * -7723592293110705685  # 0x94D049BB133111EB
+        x = x ^ ((x >> 31) & ((1 << 33) - 1))
+        ch = lut[x.view(torch.uint8).to(torch.int32)].view(torch.uint8).reshape(-1)
+        lo, hi = max(offset, b0 * 32), min(offset + n, b1 * 32)
+        out[lo - offset:hi - offset] = ch[lo - b0 * 32:hi - b0 * 32]
+        del x, ch
+    return out
+
+
+def make_patterns(profile, n_patterns, m, seed=None):
+    rng = random.Random(PATTERN_SEED[profile] if seed is None else seed)
     pats = []
     for _ in range(n_patterns):
         if profile == "iupac":
@@ -96,52 +145,91 @@ def mutate(rng, p, edits):
     return bytes(p)
 
 
-def plant_list(pats, n, k, copies, seed=44):
-    """[(pos, bytes)] non-overlapping planted copies (concrete ACGT, N -> A)."""
-    rng = random.Random(seed)
-    out = []
-    m = len(pats[0])
-    slots = max(1, n // (4 * (m + k + 1)))
+PLANT_SLOT = 512  # bytes per planting slot (> 2 x the longest planted copy)
+
+
+def slab_plants(slab, n, planted):
+    """[(global position, bytes)] of the copies planted into slab `slab` of n bytes: for every
+    (pattern, k, copies) of `planted`, `copies` mutated copies (0..k edits) at seeded,
+    non-overlapping slots that keep 4 KB clear of the slab's ends."""
+    rng = random.Random(1000 + slab)
+    slots = max(1, (n - 8192) // PLANT_SLOT)
     used = set()
-    for p in pats:
+    out = []
+    for p, k, copies in planted:
         for _ in range(copies):
             s = rng.randrange(slots)
             while s in used:
                 s = rng.randrange(slots)
             used.add(s)
             q = mutate(rng, p.replace(b"N", b"A"), rng.randrange(0, k + 1))
-            pos = s * 4 * (m + k + 1)
-            if pos + len(q) <= n:
-                out.append((pos, q))
+            pos = 4096 + s * PLANT_SLOT
+            if pos + len(q) + 4096 <= n:
+                out.append((slab * n + pos, q))
     return out
 
 
-def synth_text_device(torch, n, seed, device):
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    out = torch.empty(n, dtype=torch.uint8, device=device)
-    ch = 1 << 28
-    for off in range(0, n, ch):
-        mlen = min(ch, n - off)
-        r = torch.randint(0, 4, (mlen,), dtype=torch.uint8, device=device, generator=g)
-        # 0,1,2,3 -> 'A','C','G','T' (65,67,71,84)
-        o = r * 2 + 65
-        o += (r == 2).to(torch.uint8) * 2
-        o += (r == 3).to(torch.uint8) * 13
-        out[off:off + mlen] = o
-        del r, o
+def border_plants(slab, n, pattern):
+    """Copies of the single pattern ACROSS the border between slab `slab` and the next one: an exact
+    copy whose end positions <= k straddle the border, and a homopolymer-extended copy whose
+    plateau of equal costs crosses it (the local-minima rule must see the merged run)."""
+    b = (slab + 1) * n
+    m = len(pattern)
+    return [(b - m + 1, pattern), (b + 300 - m // 2, pattern[:m // 2] + pattern[m // 2:m // 2 + 1] * 3 + pattern[m // 2 + 1:])]
+
+
+def apply_plants(torch, text, window_lo, plants):
+    n = text.numel()
+    for pos, q in plants:
+        lo, hi = max(pos, window_lo), min(pos + len(q), window_lo + n)
+        if lo < hi:
+            text[lo - window_lo:hi - window_lo] = torch.tensor(list(q[lo - pos:hi - pos]), dtype=torch.uint8,
+                                                              device=text.device)
+
+
+def planted_set(args):
+    """What is planted into every slab (both arms, every rank): the c2 and c4 patterns 64 times,
+    the first c5-patterns (at least 1024: the c3 set; the two sets share their patterns) twice."""
+    out = []
+    for name in ("c2", "c4"):
+        profile, _, m, k, _, _ = WORKLOADS[name]
+        out.append((make_patterns(profile, 1, m, seed=PATTERN_SEED[profile] + m)[0], k, 64))
+    for p in make_patterns("iupac", max(1024, min(args.c5_patterns, 4096)), 23):
+        out.append((p, 3, 2))
     return out
+
+
+def workload_patterns(name, n_patterns):
+    profile, _, m, _, _, _ = WORKLOADS[name]
+    if profile == "dna":
+        return make_patterns(profile, n_patterns, m, seed=PATTERN_SEED[profile] + m)
+    return make_patterns(profile, n_patterns, m)
+
+
+def build_window(torch, args, n, world, lo, hi, device):
+    """Bytes [lo, hi) of the global text (world slabs of n bytes) with every plant that touches it."""
+    text = synth_text(torch, hi - lo, lo, 42, device)
+    planted = planted_set(args)
+    c2pat = planted[0][0]
+    first, last = max(0, lo // n - 1), min(world - 1, (hi - 1) // n + 1)
+    plants = []
+    for s in range(first, last + 1):
+        if s * n < hi and (s + 1) * n > lo:
+            plants += slab_plants(s, n, planted)
+        if s + 1 < world:
+            plants += border_plants(s, n, c2pat)
+    apply_plants(torch, text, lo, plants)
+    return text
 
 
 class ClockSampler:
-    """SM clock / throttle-reason samples taken DURING the timed region through NVML
-    (nvidia-ml-py), every `every` steps from inside the step loop; falls back to one
-    `nvidia-smi` query if NVML is unavailable."""
+    """SM clock / throttle-reason samples taken DURING the timed regions through NVML
+    (nvidia-ml-py) from inside the step loops; falls back to one `nvidia-smi` query if NVML is
+    unavailable."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, uuid: str, every: int = 8):
-        self.every = every
+    def __init__(self, uuid: str):
         self.sm = []
         self.power = []
         self.reasons = set()
@@ -161,10 +249,10 @@ class ClockSampler:
             self.h = None
             self.err = str(e)
 
-    def sample(self, step: int = 0):
-        # NVML queries cost up to a millisecond: at most one sample per 50 ms of wall time
+    def sample(self, min_gap=0.01):
+        # NVML queries cost up to a millisecond: at most one sample per 10 ms of wall time
         now = time.perf_counter()
-        if self.h is None or now - getattr(self, "_last", 0.0) < 0.05:
+        if self.h is None or now - getattr(self, "_last", 0.0) < min_gap:
             return
         self._last = now
         nv = self.nv
@@ -180,6 +268,10 @@ class ClockSampler:
                     self.reasons.add(name)
         except Exception as e:
             self.err = str(e)
+
+    def reset(self):
+        self.sm.clear(), self.power.clear(), self.reasons.clear()
+        self._last = 0.0
 
     def result(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "source": "nvml"}
@@ -202,57 +294,135 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------
 # CPU leg (oracle/ is test + baseline infrastructure; never on the product path)
 
-def cpu_port_run(profile, pats, k, rc, text_addr, nbytes, threads):
-    """Runs the CPU restatement of the reference's search over text[0:nbytes].
-    Returns (seconds, matches, kind_description)."""
+def cpu_sample(profile, pats, k, rc, text_addr, n, cores, seconds, runs=3):
+    """Times the CPU port on a bounded sample of the workload: all of the text, as many of the
+    patterns as fit the time budget (at least 1); one warm-up run, then the median of `runs`.
+    Returns (dict for cpu_baseline, sample patterns, {(pattern index, end, cost)})."""
     from oracle import cpu_port
-    return cpu_port.search_timed(profile, pats, k, rc, text_addr, nbytes, threads)
+    rate = cpu_port.calibrate(profile, pats[:1], k, rc)  # text bytes x patterns / s / thread
+    per_pattern = n / max(rate * cores * 0.6, 1.0)  # seconds per pattern over the whole text
+    np_sample = int(max(1, min(len(pats), 64, seconds / (runs + 1) / max(per_pattern, 1e-3))))
+    sample = pats[:np_sample]
+    ends = set()
+    times = []
+    kind = ""
+    for it in range(runs + 1):
+        t0 = time.perf_counter()
+        got = []
+        for pi, p in enumerate(sample):
+            e, _ = cpu_port.search_ends(profile, p, text_addr, n, k, rc, False, cores)
+            got += [(pi, pos, cost, strand) for pos, cost, strand in e]
+        sec = time.perf_counter() - t0
+        if it > 0:
+            times.append(sec)
+        ends = set(got)
+    kind = cpu_port.kind(cores)
+    sec = statistics.median(times)
+    return {"seconds": sec, "patterns": np_sample, "kind": kind, "runs": runs, "times": times}, sample, ends
+
+
+def check_against_cpu(name, matches, ends, n_sample_patterns, n_text, rc):
+    """GPU end positions and costs == the CPU port's, for the sampled patterns (both arms searched
+    the same bytes).  v1 semantics: a reverse-complement match ends at n - text_start."""
+    got = set()
+    for r in matches.records if hasattr(matches, "records") else []:
+        pi = int(r["pattern_idx"])
+        if pi >= n_sample_patterns:
+            continue
+        if r["strand"]:
+            got.add((pi, n_text - int(r["text_start"]), int(r["cost"]), 1))
+        else:
+            got.add((pi, int(r["text_end"]), int(r["cost"]), 0))
+    if got != ends:
+        only_g = sorted(got - ends)[:5]
+        only_c = sorted(ends - got)[:5]
+        raise SystemExit(f"PARITY FAILURE [{name}]: GPU and CPU port disagree on the same text: "
+                         f"{len(got)} vs {len(ends)} end positions; only GPU {only_g}; only CPU {only_c}")
+    return len(got)
+
+
+def match_keys(ms):
+    r = ms.records
+    ops = ms._ops
+    return sorted((int(a["pattern_idx"]), int(a["text_start"]), int(a["text_end"]), int(a["cost"]), int(a["strand"]),
+                   ops[int(a["ops_off"]):int(a["ops_off"]) + int(a["ops_len"])]) for a in r)
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (restated, oracle/) on all host cores."""
+    """--impl reference: the reference's CPU algorithm (restated, oracle/) on all host cores, on the
+    same text as the GPU arm (a prefix of it when the whole text does not fit the time budget)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    profile, n_patterns, m, k, n, desc = WORKLOADS[args.workload]
+    import torch
+    from oracle import cpu_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+
+    def one(name, steps, warmup, seconds, n_patterns=0):
+        profile, np_full, m, k, n, desc = WORKLOADS[name]
+        if args.text_bytes:
+            n = args.text_bytes
+        if n_patterns:
+            np_full = n_patterns
+        pats = workload_patterns(name, min(np_full, 4096))
+        rate = cpu_port.calibrate(profile, pats[:1], k, args.rc)
+        budget = min(seconds, 150.0 / max(1, steps + warmup))
+        per_pattern = n / max(rate * cores * 0.6, 1.0)
+        sample_pats = pats[:int(max(1, min(len(pats), 64, budget / max(per_pattern, 1e-3))))]
+        sample_n = n if per_pattern <= budget else int(max(1 << 24, n * budget / per_pattern))
+        if n not in texts:
+            texts[n] = build_window(torch, args, n, 1, 0, n, "cpu")
+        addr = texts[n].data_ptr()  # the sample is a prefix of the same text
+        times = []
+        nm = 0
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            nm = 0
+            for p in sample_pats:
+                e, _ = cpu_port.search_ends(profile, p, addr, sample_n, k, args.rc, False, cores)
+                nm += len(e)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        sec = sum(times) / len(times)
+        value = sample_n / sec / 1e9 * len(sample_pats) / np_full  # text GB/s for the whole pattern set
+        return {"workload": desc, "value": value, "unit": "GB/s", "ms_per_step": sec * 1e3,
+                "gchar_pattern_per_s": sample_n * len(sample_pats) / sec / 1e9, "matches_in_sample": nm,
+                "sample": f"first {sample_n} text bytes x {len(sample_pats)} of {np_full} patterns per step",
+                "sample_bytes": sample_n, "sample_patterns": len(sample_pats), "patterns": np_full,
+                "pattern_len": m, "k": k}
+
+    texts = {}
+    profile, np_full, m, k, n, desc = WORKLOADS[args.workload]
     if args.text_bytes:
         n = args.text_bytes
-    pats = make_patterns(profile, n_patterns, m)
-    cores = os.cpu_count() or 1
-    # bounded sample of the same workload: a prefix of the text (and of the pattern set)
-    from oracle import cpu_port
-    rate = cpu_port.calibrate(profile, pats[:min(len(pats), 32)], k, args.rc)  # bytes*patterns/s/thread
-    sample_pats = pats[:min(len(pats), 64)]
-    # each step is a bounded sample; the whole --steps/--warmup run stays within a few minutes
-    budget = min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup))
-    sample_n = int(min(n, max(1 << 24, rate * cores * budget / max(1, len(sample_pats)))))
-    rng = np.random.default_rng(42)
-    text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=sample_n, dtype=np.uint8)]
-    for pos, q in plant_list(pats, sample_n, k, 64 if n_patterns == 1 else 2):
-        text[pos:pos + len(q)] = np.frombuffer(q, dtype=np.uint8)
-    text = np.ascontiguousarray(text)
-    times = []
-    nm = 0
-    for it in range(args.warmup + args.steps):
-        sec, nm, kind = cpu_port.search_timed(profile, sample_pats, k, args.rc, text.ctypes.data, sample_n, cores)
-        if it >= args.warmup:
-            times.append(sec)
-    sec = sum(times) / len(times)
-    # throughput of the FULL workload's metric: text bytes/s for the whole pattern set
-    scale = len(sample_pats) / n_patterns
-    value = sample_n / sec / 1e9 * scale
+    texts[n] = build_window(torch, args, n, 1, 0, n, "cpu")
+    top = one(args.workload, args.steps, args.warmup, args.cpu_seconds, args.patterns)
+    subs = {}
+    for name in sub_list(args, 1):
+        subs[name] = one(name, 2, 1, 4.0, args.c5_patterns if name == "c5" else 0)
+    kind = cpu_port.kind(cores)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": desc, "rc": bool(args.rc), "sample_bytes": sample_n, "sample_patterns": len(sample_pats)},
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_n} text bytes x {len(sample_pats)} patterns per step ({kind})"},
-        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "matches": nm,
+        "impl": "reference", "metric": METRIC, "value": top["value"], "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": top["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": desc, "rc": bool(args.rc), "sample_bytes": top["sample_bytes"],
+                   "sample_patterns": top["sample_patterns"],
+                   "text": "same generator and plants as the GPU arm (bench.py synth_text, seed 42)"},
+        "cpu_baseline": {"value": top["value"], "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": top["sample"] + f" ({kind})"},
+        "e2e": {"value": top["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "matches": top["matches_in_sample"], "configs": subs,
     }
     print(json.dumps(line), flush=True)
+
+
+def sub_list(args, world):
+    if args.sub == "none" or args.workload != "c2":
+        return []
+    if args.sub == "auto":
+        return ["c3", "c4", "c5"] if world == 1 else ["c5"]
+    return [x for x in args.sub.split(",") if x in WORKLOADS]
 
 
 # ----------------------------------------------------------------------------------------
@@ -269,6 +439,7 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     import sassy_b200
@@ -283,144 +454,342 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    cores = os.cpu_count() or 1
 
-    profile, n_patterns, m, k, n, desc = WORKLOADS[args.workload]
-    if args.text_bytes:
-        n = args.text_bytes
-    if args.patterns:
-        n_patterns = args.patterns
-    all_pats = make_patterns(profile, n_patterns, m)
-    copies = 64 if n_patterns == 1 else 2
-    pshard = args.workload in PATTERN_SHARDED
-    # pattern-sharded workloads: the same text on every rank, this rank's share of the patterns
-    pats = [all_pats[i] for i in sdist.shard_indices(len(all_pats), rank, world)] if pshard else all_pats
-    if not pats:
-        raise SystemExit("fewer patterns than ranks")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    try:
+        instr_tab = json.load(open(os.path.join(ROOT, "profiles", "instr_per_step.json")))
+    except Exception:
+        instr_tab = {}
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        traffic_tab = {}
 
-    # ---- inputs: text (shard) of this rank, generated in HBM ------------------------------
-    text_dev = synth_text_device(torch, n, 42 + (0 if pshard else rank), dev)
-    for pos, q in plant_list(all_pats[:4096], n, k, copies, seed=44 + (0 if pshard else rank)):
-        text_dev[pos:pos + len(q)] = torch.tensor(list(q), dtype=torch.uint8, device=dev)
-    torch.cuda.synchronize()
-
-    s = sassy_b200.Searcher(profile, rc=args.rc, device=local_rank)
-    s.set_variant(args.variant)
-    s.set_filter(args.filter)
-    s.set_transport(args.transport)
-    dt = s.text_from_device(text_dev.data_ptr(), n)
-    enc = s.encode_patterns(pats) if n_patterns > 1 else None
-
-    host = None
-    if not args.no_e2e or not args.no_cpu:
-        host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        host.copy_(text_dev)
-        torch.cuda.synchronize()
-    del text_dev
-    torch.cuda.empty_cache()
-
-    # N > 1: the match records of all ranks reach every rank through the fused peer-memory
-    # exchange behind the traceback (csrc/peer_gather.cu); --gather nccl uses the host-staged
-    # NCCL all-gather instead (A/B)
-    pg = None
-    if world > 1 and args.gather == "peer":
-        pg = sdist.PeerGather.create_or_none(s, max_ops=m + k + 1, device=dev)
-
-    def step_resident():
-        if pg is not None:
-            return pg.search_encoded(enc, dt, k) if enc is not None else pg.search(pats[0], dt, k)
-        if enc is not None:
-            ms = s.search_encoded_patterns(enc, dt, k)
-        else:
-            ms = s.search(pats[0], dt, k)
-        if world > 1:
-            ms = sdist.gather_matches(sdist.tag_rank(ms, rank), max_ops=m + k + 1, device=dev)
-        return ms
-
-    def step_e2e():
-        buf = (host.data_ptr(), n)
-        if enc is not None:
-            ms = s.search_encoded_patterns(enc, buf, k)
-        else:
-            ms = s.search(pats[0], buf, k)
-        if world > 1:
-            ms = sdist.gather_matches(sdist.tag_rank(ms, rank), max_ops=m + k + 1, device=dev)
-        return ms
+    uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    if not uuid.startswith("GPU-"):
+        uuid = "GPU-" + uuid
+    sampler = ClockSampler(uuid) if rank == 0 else None
+    if sampler is not None:  # the first NVML queries of a process can take long: not inside a timed region
+        sampler.sample()
+        sampler.reset()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    step_wall = []  # host wall time of every timed step (diagnostics: p50 / max next to the mean)
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
 
-    def timed(fn, steps, warmup, sampler=None):
+    top_profile, top_np, top_m, top_k, n, top_desc = WORKLOADS[args.workload]
+    if args.text_bytes:
+        n = args.text_bytes
+    subs = sub_list(args, world)
+
+    # ---- texts -----------------------------------------------------------------------------
+    # text0: slab 0 of the global text = THE text of every single-GPU config and of the
+    # pattern-sharded c5 (replicated on every rank).  Text-sharded top level at N > 1: this rank's
+    # window (slab + halos) of the N x n-byte global text.
+    text_sharded = world > 1 and args.workload not in PATTERN_SHARDED
+    n_global = n * world if text_sharded else n
+    searchers = {}
+
+    def searcher(profile):
+        if profile not in searchers:
+            s = sassy_b200.Searcher(profile, rc=args.rc, device=local_rank)
+            s.set_variant(args.variant)
+            s.set_filter(args.filter)
+            s.set_transport(args.transport)
+            searchers[profile] = s
+        return searchers[profile]
+
+    s_top = searcher(top_profile)
+    need_text0 = (not text_sharded) or bool(subs)
+    host0 = None
+    dt0 = {}
+    if need_text0:
+        t0_dev = build_window(torch, args, n, world if text_sharded else 1, 0, n, dev)
+        torch.cuda.synchronize()
+        if not (args.no_e2e and args.no_cpu and args.no_check):
+            host0 = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            host0.copy_(t0_dev)
+            torch.cuda.synchronize()
+
+    def text0_for(profile):  # a DeviceText belongs to its searcher's engine
+        if profile not in dt0:
+            dt0[profile] = searcher(profile).text_from_device(t0_dev.data_ptr(), n)
+        return dt0[profile]
+
+    layout = sdist.slab_layout(n_global, world, top_m, top_k) if text_sharded else None
+    if text_sharded:
+        wlo, whi, _, _ = layout[rank]
+        w_dev = build_window(torch, args, n, world, wlo, whi, dev)
+        dt_window = s_top.text_from_device(w_dev.data_ptr(), whi - wlo)
+        del w_dev
+    torch.cuda.empty_cache()
+
+    pgs = {}
+
+    def peer_gather(s, max_ops):
+        key = (id(s), max_ops)
+        if key not in pgs:
+            pgs[key] = sdist.PeerGather.create_or_none(s, max_ops=max_ops, device=dev) \
+                if (world > 1 and args.gather == "peer") else None
+        return pgs[key]
+
+    launches_total = [0]
+
+    def timed(fn, s, steps, warmup):
         for _ in range(warmup):
             ms = fn()
         barrier()
-        scan_ms, total_ms, launches = [], [], 0
-        step_wall.clear()
+        scan_ms, total_ms, walls, launches = [], [], [], 0
         t0 = time.perf_counter()
         tp = t0
         for it in range(steps):
             ms = fn()
             if sampler is not None:
-                sampler.sample(it)
+                sampler.sample()
             tn = time.perf_counter()
-            step_wall.append((tn - tp) * 1e3)
+            walls.append((tn - tp) * 1e3)
             tp = tn
             st = s.stats()
             scan_ms.append(st["scan_ms"])
             total_ms.append(st["total_ms"])
             launches += st["scan_launches"] + st["aux_launches"]
         barrier()
-        el = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([el], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            el = float(t.item())
-        return el, ms, scan_ms, total_ms, launches, s.stats()
+        el = max_over_ranks(time.perf_counter() - t0)
+        launches_total[0] += launches
+        return {"el": el, "matches": ms, "scan_ms": scan_ms, "total_ms": total_ms, "walls": sorted(walls),
+                "launches": launches, "stats": s.stats()}
 
-    uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
-    if not uuid.startswith("GPU-"):
-        uuid = "GPU-" + uuid
-    sampler = ClockSampler(uuid) if rank == 0 else None
-    if sampler is not None:  # the first NVML queries of a process can take long: not inside the timed region
-        sampler.sample(0)
-        sampler.sm.clear(), sampler.power.clear(), sampler.reasons.clear()
-        sampler._last = 0.0
-    el, matches, scan_ms, total_ms, launches, st = timed(step_resident, args.steps, args.warmup, sampler)
-    clocks = sampler.result() if rank == 0 else None
-    wall_sorted = sorted(step_wall)
-    step_stats = {"p50": wall_sorted[len(wall_sorted) // 2], "max": wall_sorted[-1],
-                  "p90": wall_sorted[int(len(wall_sorted) * 0.9)]} if wall_sorted else None
-
-    # text shards: N x n bytes scanned per step (weak scaling); pattern shards: the job is
-    # "all patterns over the n-byte text", the same total work for every N (strong scaling)
-    total_bytes = n if pshard else n * world
-    total_patterns = len(all_pats)
-    value = total_bytes * args.steps / el / 1e9
-    ms_per_step = el / args.steps * 1e3
-
-    e2e = None
-    if not args.no_e2e:
-        e_steps = max(2, min(args.steps, 5))
-        e_el, e_matches, _, _, _, _ = timed(step_e2e, e_steps, 2)  # 2 warm-ups: buffers, pool and the pack-rate estimate settle
-        if hasattr(e_matches, "records") and hasattr(matches, "records"):
-            import numpy as np
-            same = np.array_equal(e_matches.records, matches.records) and e_matches._ops == matches._ops
+    def roofline_of(name, st, n_text, n_queries, scan_avg_ms, ms_per_step):
+        """hbm: algorithmic bytes (the text, read once) / time of the dominant kernel vs the measured
+        copy bandwidth.  Routes whose dominant kernel is the bit-parallel scan are bound by the
+        instruction issue rate, not by HBM: for them the roofline is warp instructions issued per
+        second vs SMs x 4 schedulers x SM clock, with the instructions per (character x pattern x
+        32-bit word) measured by ncu (profiles/instr_per_step.json)."""
+        filt = bool(st["filter_words"]) and not st["filter_fallback"]
+        kernel = ("qgram_kernel" if st.get("filter_kind", 0) == 2 else "filter_kernel") if filt else "scan_kernel"
+        achieved = n_text / (scan_avg_ms * 1e-3) / 1e9
+        hbm = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+               "traffic": traffic_tab.get(name + ("_filter" if filt else "_scan")),
+               "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "kernel": kernel,
+               "kernel_ms": scan_avg_ms, "verify_kernel_ms": st["verify_ms"], "prefilter_hits": st["hits"],
+               "kernel_share_of_step": scan_avg_ms / ms_per_step, "algorithmic_bytes_per_launch": n_text,
+               "lane_steps_per_s": n_text * n_queries / (scan_avg_ms * 1e-3)}
+        if filt:
+            return hbm
+        lanes = st.get("swar_lanes", 1) or 1
+        key = f"scan_w{st['words']}" + (f"_swar{lanes}" if lanes > 1 else "")
+        ips = instr_tab.get(key, {}).get("instr_per_char_word")
+        word_steps = n_text * n_queries * st["words"] / (scan_avg_ms * 1e-3)
+        peak = SM_COUNT * 4 * sm_max_mhz * 1e6 / 1e9  # G warp-instructions / s
+        out = dict(hbm)
+        out.update({"bound": "int_issue", "unit": "Gwarp-inst/s", "peak": peak, "hbm_frac": hbm["frac"],
+                    "hbm_achieved_gbs": achieved, "word_steps_per_s": word_steps,
+                    "instr_per_char_word": ips, "instr_source": instr_tab.get(key, {}).get("source")})
+        if ips:
+            out["achieved"] = word_steps * ips / 32 / 1e9
+            out["frac"] = out["achieved"] / peak
         else:
-            same = sorted(x._key() for x in e_matches) == sorted(x._key() for x in matches)
-        assert same, "host-pointer path and resident path disagree"
-        tables = s.stats()["words"] * 4 * {"dna": 4, "iupac": 32, "ascii": 256}[profile] * len(pats) * (2 if args.rc else 1)
-        est = s.stats()
-        packed = bool(est["transfer_packed"])
-        e2e = {"value": total_bytes * e_steps / e_el / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": est["transfer_bytes"] + tables + len(pats) * m,
-               "transport": ("head of the text at 2 bits per character (packed by host threads inside the timed "
-                             "region), tail as bytes, split so that packing and PCIe finish together") if packed else "bytes",
-               "transfer_ms": est["transfer_ms"],
-               "d2h_bytes_per_step": len(e_matches) // max(1, world) * (24 + 4 * ((m + k + 1 + 15) // 16)) + 16,
-               "ms_per_step": e_el / e_steps * 1e3, "steps": e_steps}
+            out["achieved"] = None
+            out["frac"] = None
+        return out
+
+    def run_config(name, steps, warmup, n_patterns=0, top=False):
+        """One workload record.  Pattern-sharded at N > 1 for c5 (and any batch workload run as the
+        top level); text-sharded for single-pattern top-level workloads at N > 1."""
+        profile, np_full, m, k, _, desc = WORKLOADS[name]
+        if n_patterns:
+            np_full = n_patterns
+        s = searcher(profile)
+        all_pats = workload_patterns(name, np_full)
+        batch = np_full > 1
+        pshard = batch and world > 1
+        tshard = top and text_sharded
+        pats = [all_pats[i] for i in sdist.shard_indices(len(all_pats), rank, world)] if pshard else all_pats
+        if not pats:
+            raise SystemExit("fewer patterns than ranks")
+        enc = s.encode_patterns(pats) if batch else None
+        dt = dt_window if tshard else text0_for(profile)
+        n_text = n_global if tshard else n
+        pg = peer_gather(s, m + k + 1) if (pshard or tshard) else None
+
+        def step_resident():
+            if tshard:
+                return sdist.search_text_sharded(s, pats[0], dt, k, n_global, peer_gather=pg)
+            if pg is not None:
+                return pg.search_encoded(enc, dt, k)
+            ms = s.search_encoded_patterns(enc, dt, k) if batch else s.search(pats[0], dt, k)
+            if pshard:
+                ms = sdist.gather_matches(sdist.tag_rank(ms, rank), max_ops=m + k + 1, device=dev)
+            return ms
+
+        r = timed(step_resident, s, steps, warmup)
+        st = r["stats"]
+        matches = r["matches"]
+        ms_per_step = r["el"] / steps * 1e3
+        value = n_text / (ms_per_step * 1e-3) / 1e9  # whole job: all patterns over the (global) text
+        scan_avg_ms = sum(r["scan_ms"]) / len(r["scan_ms"])
+        nq_local = len(pats) * (2 if args.rc else 1)
+        rec = {"workload": desc, "value": value, "unit": "GB/s", "ms_per_step": ms_per_step, "steps": steps,
+               "warmup": warmup, "patterns": np_full, "patterns_per_gpu": len(pats), "pattern_len": m, "k": k,
+               "text_bytes": n_text, "rc": bool(args.rc),
+               "scaling": "strong" if pshard else "weak",
+               "gchar_pattern_per_s": n_text * np_full / (ms_per_step * 1e-3) / 1e9,
+               "matches": len(matches), "matches_per_s": len(matches) / (ms_per_step * 1e-3),
+               "device_ms_per_step": sum(r["total_ms"]) / len(r["total_ms"]),
+               "step_wall_ms": {"p50": r["walls"][len(r["walls"]) // 2], "p90": r["walls"][int(len(r["walls"]) * 0.9)],
+                                "max": r["walls"][-1]},
+               "gpu_launches": r["launches"],
+               "prefilter": {"mode": args.filter, "words": st["filter_words"], "piece_len": st["filter_len"],
+                             "kind": {0: "none", 1: "shift-and pieces", 2: "q-gram bitmap", 3: "swar suffix"}.get(
+                                 st.get("filter_kind", 1 if st["filter_words"] else 0), "?"),
+                             "fallback": st["filter_fallback"], "hits": st["hits"]},
+               "row_bytes": st["row_bytes"], "rows": st["rows"], "blocks_per_sm": st["blocks_per_sm"],
+               "roofline": roofline_of(name, st, n if not tshard else (layout[rank][1] - layout[rank][0]), nq_local,
+                                       scan_avg_ms, ms_per_step),
+               "sharding": "single GPU"}
+        if pshard:
+            rec["sharding"] = ("pattern shards (round-robin), text replicated; match records of all ranks gathered per "
+                               "step by " + ("the fused peer-memory exchange, NCCL all-gather when a rank's records do "
+                                             "not fit its slot (%d of the steps)" % pg.fallbacks if pg is not None
+                                             else "a host-staged NCCL all-gather"))
+        if tshard:
+            rec["sharding"] = ("ONE text of %d bytes cut into %d slabs with (m+k) halos; per-slab search_all, records "
+                               "exchanged by %s, local-minima rule on the merged list" %
+                               (n_global, world, ("peer-memory stores over NVLink fused behind the traceback (%d NCCL "
+                                                  "fall-backs)" % pg.fallbacks) if pg is not None else "an NCCL all-gather"))
+
+        # ---- parity inside the run -------------------------------------------------------------
+        checks = {}
+        if not args.no_check:
+            if world > 1:  # gathered result == the single-GPU search of the same job on rank 0
+                ok = 1
+                if rank == 0:
+                    if tshard:
+                        g_dev = build_window(torch, args, n, world, 0, n_global, dev)
+                        dtg = s.text_from_device(g_dev.data_ptr(), n_global)
+                        del g_dev
+                        single = s.search(pats[0], dtg, k)
+                        dtg.free()
+                        got, want = match_keys(matches), match_keys(single)
+                    else:
+                        enc_all = s.encode_patterns(all_pats)
+                        single = s.search_encoded_patterns(enc_all, dt, k)
+                        # gathered records carry the pattern index local to the source rank
+                        rr = matches.records
+                        gl = rr["pattern_idx"] * world + rr["text_idx"]
+                        mm = sassy_b200.searcher.MatchList(rr.copy(), matches._ops)
+                        mm.records["pattern_idx"] = gl
+                        mm.records["text_idx"] = 0
+                        got, want = match_keys(mm), match_keys(single)
+                        got = sorted((a[0], a[1], a[2], a[3], a[4], a[5]) for a in got)
+                    if got != want:
+                        ok = 0
+                        print(f"PARITY FAILURE [{name}]: {world}-rank gathered result != 1-rank result "
+                              f"({len(got)} vs {len(want)} matches)", file=sys.stderr, flush=True)
+                    checks["n_rank_equals_1_rank"] = {"matches": len(want), "ok": bool(ok)}
+                    torch.cuda.empty_cache()
+                t = torch.tensor([ok], dtype=torch.int32, device=dev)
+                dist.broadcast(t, 0)
+                if int(t.item()) == 0:
+                    raise SystemExit(3)
+        cpu = None
+        if rank == 0 and world == 1 and host0 is not None and not args.no_cpu:
+            # CPU port on the same bytes (text0): timing for cpu_baseline + the parity check
+            try:
+                info, sample, ends = cpu_sample(profile, all_pats, k, args.rc, host0.data_ptr(), n, cores,
+                                                args.cpu_seconds if top else min(args.cpu_seconds, 8.0))
+                cpu = {"value": n / info["seconds"] / 1e9 * info["patterns"] / np_full, "unit": "GB/s", "cores": cores,
+                       "kind": "port", "gchar_pattern_per_s": n * info["patterns"] / info["seconds"] / 1e9,
+                       "sample": f"whole {n}-byte text x first {info['patterns']} of {np_full} patterns, median of "
+                                 f"{info['runs']} runs after a warm-up run: {info['seconds']:.3f} s ({info['kind']})"}
+                if not args.no_check:
+                    # the GPU side of the comparison: the sampled patterns over text0, single GPU
+                    if batch:
+                        enc_s = s.encode_patterns(sample)
+                        gm = s.search_encoded_patterns(enc_s, text0_for(profile), k)
+                    else:
+                        gm = s.search(sample[0], text0_for(profile), k)
+                    checks["gpu_equals_cpu_port"] = {
+                        "end_positions": check_against_cpu(name, gm, ends, len(sample), n, args.rc),
+                        "patterns": len(sample), "text_bytes": n, "ok": True}
+            except SystemExit:
+                raise
+            except Exception as e:
+                cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        rec["cpu_baseline"] = cpu
+
+        # ---- e2e: the same search through the host-pointer entry point ---------------------------
+        if not args.no_e2e and host0 is not None and not tshard and not pshard:
+            buf = (host0.data_ptr(), n)
+
+            def step_e2e():
+                return s.search_encoded_patterns(enc, buf, k) if batch else s.search(pats[0], buf, k)
+
+            e_steps = max(2, min(steps, 5)) if ms_per_step < 200 else 1
+            e = timed(step_e2e, s, e_steps, 2 if ms_per_step < 200 else 1)
+            if not args.no_check:
+                same = np.array_equal(e["matches"].records, matches.records) and e["matches"]._ops == matches._ops
+                if not same:
+                    raise SystemExit(f"PARITY FAILURE [{name}]: host-pointer path and resident path disagree")
+                checks["host_pointer_equals_resident"] = True
+            est = e["stats"]
+            tables = est["words"] * 4 * {"dna": 4, "iupac": 32, "ascii": 256}[profile] * nq_local
+            rec["e2e"] = {"value": n * e_steps / e["el"] / 1e9, "unit": "GB/s",
+                          "h2d_bytes_per_step": est["transfer_bytes"] + tables + len(pats) * m,
+                          "transport": ("head of the text at 2 bits per character (packed by host threads inside the "
+                                        "timed region), tail as bytes, split so that packing and PCIe finish together")
+                          if est["transfer_packed"] else "bytes",
+                          "transfer_ms": est["transfer_ms"],
+                          "d2h_bytes_per_step": len(matches) * (24 + 4 * ((m + k + 1 + 15) // 16)) + 16,
+                          "ms_per_step": e["el"] / e_steps * 1e3, "steps": e_steps}
+        elif not args.no_e2e and top and tshard:
+            # N > 1: every rank sends its own window from pinned host memory, then the sharded search
+            hw = torch.empty(layout[rank][1] - layout[rank][0], dtype=torch.uint8, pin_memory=True)
+            wtmp = build_window(torch, args, n, world, layout[rank][0], layout[rank][1], dev)
+            hw.copy_(wtmp)
+            del wtmp
+            torch.cuda.synchronize()
+            buf = (hw.data_ptr(), hw.numel())
+
+            def step_e2e():
+                ms = s.search_all(pats[0], buf, k)
+                ms = sdist.gather_matches(sdist.tag_rank(ms, rank), max_ops=m + k + 1, device=dev)
+                return sdist.merge_slabs(ms, layout, n_global)
+
+            e_steps = max(2, min(steps, 5))
+            e = timed(step_e2e, s, e_steps, 2)
+            if not args.no_check and match_keys(e["matches"]) != match_keys(matches):
+                raise SystemExit(f"PARITY FAILURE [{name}]: host-pointer path and resident path disagree")
+            est = e["stats"]
+            rec["e2e"] = {"value": n_global * e_steps / e["el"] / 1e9, "unit": "GB/s",
+                          "per_gpu": n_global * e_steps / e["el"] / 1e9 / world,
+                          "h2d_bytes_per_step": est["transfer_bytes"] * world, "transfer_ms": est["transfer_ms"],
+                          "d2h_bytes_per_step": len(matches) * (24 + 4 * ((m + k + 1 + 15) // 16)) + 16,
+                          "ms_per_step": e["el"] / e_steps * 1e3, "steps": e_steps,
+                          "transport": "packed" if est["transfer_packed"] else "bytes"}
+        rec["checks"] = checks
+        return rec
+
+    top = run_config(args.workload, args.steps, args.warmup, args.patterns, top=True)
+    sub_recs = {}
+    for name in subs:
+        sub_recs[name] = run_config(name, args.sub_steps, 3, args.c5_patterns if name == "c5" else 0)
+    clocks = sampler.result() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -428,63 +797,22 @@ def main():
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    scan_avg_ms = sum(scan_ms) / len(scan_ms)
-    achieved = n / (scan_avg_ms * 1e-3) / 1e9  # algorithmic bytes of one scan launch set = the text, read once
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-            args.workload + ("_filter" if st["filter_words"] else "_scan"))
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                "kernel": "filter_kernel" if st["filter_words"] else "scan_kernel", "kernel_ms": scan_avg_ms,
-                "verify_kernel_ms": st["verify_ms"], "prefilter_hits": st["hits"],
-                "kernel_share_of_step": scan_avg_ms / ms_per_step,
-                "algorithmic_bytes_per_launch": n,
-                "lane_steps_per_s": n * len(pats) * (2 if args.rc else 1) / (scan_avg_ms * 1e-3)}
-
-    cpu = None
-    if not args.no_cpu:
-        try:
-            from oracle import cpu_port
-            cores = os.cpu_count() or 1
-            sample_pats = all_pats[:min(len(all_pats), 64)]
-            rate = cpu_port.calibrate(profile, sample_pats[:32], k, args.rc)
-            sample_n = int(min(n, max(1 << 24, rate * cores * args.cpu_seconds / len(sample_pats))))
-            sec, nm, kind = cpu_port.search_timed(profile, sample_pats, k, args.rc, host.data_ptr(), sample_n, cores)
-            cpu = {"value": sample_n / sec / 1e9 * len(sample_pats) / total_patterns, "unit": "GB/s", "cores": cores,
-                   "kind": "port", "sample": f"first {sample_n} text bytes x {len(sample_pats)} patterns, {sec:.2f} s ({kind})",
-                   "matches_in_sample": nm}
-        except Exception as e:
-            cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-
     line = {
-        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if pshard else "weak",
-        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": desc, "text_bytes_per_gpu": n, "patterns": total_patterns,
-                   "patterns_per_gpu": len(pats), "pattern_len": m, "k": k,
-                   "rc": bool(args.rc), "mode": "search (local minima) + traceback",
+        "metric": METRIC, "value": top["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": top["ms_per_step"], "higher_is_better": True,
+        "scaling": top["scaling"], "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": top_desc, "text_bytes_per_gpu": n, "text_bytes": top["text_bytes"],
+                   "patterns": top["patterns"], "patterns_per_gpu": top["patterns_per_gpu"], "pattern_len": top_m,
+                   "k": top_k, "rc": bool(args.rc), "mode": "search (local minima) + traceback",
                    "l2": "text (3 GB) is larger than L2 (126 MB); no flush needed", "variant": args.variant,
-                   "row_bytes": st["row_bytes"], "rows": st["rows"], "blocks_per_sm": st["blocks_per_sm"],
-                   "prefilter": {"mode": args.filter, "words": st["filter_words"], "piece_len": st["filter_len"],
-                                 "fallback": st["filter_fallback"]},
-                   "sharding": (("pattern shards (round-robin), text replicated; " if pshard else "text shards, one per rank; ")
-                                + "match records of all ranks exchanged per step by "
-                                + ("peer-memory stores over NVLink fused behind the traceback (%d NCCL fall-backs)" % pg.fallbacks
-                                   if pg is not None else "a host-staged NCCL all-gather")) if world > 1 else "single GPU"},
-        "matches": len(matches), "matches_per_s": len(matches) * args.steps / el,
-        "gchar_pattern_per_s": (n * total_patterns if pshard else total_bytes * len(pats)) * args.steps / el / 1e9,
-        "device_ms_per_step": sum(total_ms) / len(total_ms), "step_wall_ms": step_stats,
-        "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+                   "row_bytes": top["row_bytes"], "rows": top["rows"], "blocks_per_sm": top["blocks_per_sm"],
+                   "prefilter": top["prefilter"], "sharding": top["sharding"],
+                   "text": "bench.py synth_text (seed 42): the same bytes in the reference arm"},
+        "matches": top["matches"], "matches_per_s": top["matches_per_s"],
+        "gchar_pattern_per_s": top["gchar_pattern_per_s"],
+        "device_ms_per_step": top["device_ms_per_step"], "step_wall_ms": top["step_wall_ms"],
+        "gpu_launches": launches_total[0], "clocks": clocks, "e2e": top.get("e2e"), "roofline": top["roofline"],
+        "cpu_baseline": top["cpu_baseline"], "checks": top["checks"], "configs": sub_recs,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

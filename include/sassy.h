@@ -16,6 +16,12 @@
  *     released with sassy_matches_free(ptr, len) with the same len; for zero
  *     matches a non-null pointer is still returned (c.rs:112-127).
  *   - one searcher per thread; not re-entrant (search takes &mut Searcher).
+ *   - Capacity limits of this implementation (the reference has none): patterns
+ *     of at most 1024 characters, texts shorter than 2^40 bytes.  A search()
+ *     beyond a limit does NOT abort: it returns 0 matches (with a valid, freeable
+ *     *out_matches), prints the reason to stderr and leaves it in
+ *     sassy_gpu_last_error() (include/sassy_gpu.h), which is empty after every
+ *     successful search().  Abort is reserved for the reference's own panics.
  * The GPU is selected with the environment variable SASSY_B200_DEVICE
  * (default 0).  There is no CPU fallback: without a B200 the constructor aborts.
  */

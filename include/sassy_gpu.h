@@ -199,6 +199,21 @@ sassy_gpu_Result *sassy_gpu_search_encoded_gathered(sassy_SearcherType *searcher
                                                     const sassy_gpu_Patterns *patterns, const sassy_gpu_Text *text,
                                                     size_t k, int all, int *complete);
 
+/* One text cut into slabs over several GPUs: every rank searches its slab plus an
+ * (m + k) halo on both sides with all = 1, the records of all ranks are gathered (text_idx =
+ * source rank, coordinates relative to that rank's window), and this function drops the records a
+ * slab does not own, makes the coordinates global and applies the local-minima rule
+ * (src/search.rs:1344-1368) to the merged list (all = 0) -- a run of minima that crosses a slab
+ * border is selected exactly as by an unsharded search.  Host code only; `ops` = the op bytes the
+ * records' ops_off refer to.  See sassy_b200/dist.py: search_text_sharded. */
+typedef struct sassy_gpu_Slab {
+  uint64_t window_off; /* global position of the first character of the rank's window */
+  uint64_t own_lo;     /* the rank owns the global text range [own_lo, own_hi) */
+  uint64_t own_hi;
+} sassy_gpu_Slab;
+sassy_gpu_Result *sassy_gpu_merge_slabs(const sassy_gpu_Match *records, size_t n_records, const char *ops,
+                                        const sassy_gpu_Slab *slabs, size_t n_slabs, uint64_t n_global, int all);
+
 size_t sassy_gpu_result_len(const sassy_gpu_Result *result);
 const sassy_gpu_Match *sassy_gpu_result_matches(const sassy_gpu_Result *result);
 const char *sassy_gpu_result_ops(const sassy_gpu_Result *result);

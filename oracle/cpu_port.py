@@ -58,6 +58,10 @@ def search_ends(alphabet: str, pattern: bytes, text, n: int, k: int, rc: bool, a
     return [(pos[i], cost[i], strand[i]) for i in range(got)], sec.value
 
 
+def kind(threads: int) -> str:
+    return f"C restatement of Sassy v1 (search.rs text-tiled u64x{lanes()} + early termination), {threads} threads"
+
+
 def search_timed(alphabet: str, patterns: Sequence[bytes], k: int, rc: bool, text_addr: int, n: int,
                  threads: int):
     """One pass of every pattern over text[0:n] with `threads` threads.  (seconds, matches, kind)."""

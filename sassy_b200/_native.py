@@ -126,6 +126,8 @@ SIGNATURES = {
                                                   ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "sassy_gpu_search_encoded_gathered": (c_void_p, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, ctypes.c_int,
                                                      ctypes.POINTER(ctypes.c_int)]),
+    "sassy_gpu_merge_slabs": (c_void_p, [c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, ctypes.c_uint64,
+                                        ctypes.c_int]),
     "sassy_gpu_result_len": (c_size_t, [c_void_p]),
     "sassy_gpu_result_matches": (ctypes.POINTER(GpuMatch), [c_void_p]),
     "sassy_gpu_result_ops": (c_void_p, [c_void_p]),

@@ -20,7 +20,7 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 
 CU_SOURCES = ["scan_kernels.cu", "post_kernels.cu", "engine.cu", "searcher.cu", "transport.cu", "peer_gather.cu"]
 HEADERS = ["profile.h", "scan_core.cuh", "host_logic.h", "kernels.cuh", "engine.h", "searcher.h", "transport.h",
-           "peer_gather.h"]
+           "peer_gather.h", "shard_merge.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -101,7 +101,11 @@ def get_patterns(args) -> List[Record]:
         return [Record("pattern", args.pattern.encode())]
     if args.pattern_file is not None:
         with open(args.pattern_file, "rb") as f:
-            return [Record(str(i + 1), line.rstrip(b"\r\n")) for i, line in enumerate(f.read().split(b"\n")[:-1] or [])]
+            # BufReader::lines(): split at \n, a trailing \r is dropped, the last line needs no newline
+            lines = f.read().split(b"\n")
+            if lines and lines[-1] == b"":
+                lines.pop()
+            return [Record(str(i + 1), line[:-1] if line.endswith(b"\r") else line) for i, line in enumerate(lines)]
     if args.pattern_fasta is not None:
         return list(read_fastx(args.pattern_fasta))
     raise SystemExit("No --pattern, --pattern-file, or --pattern-fasta provided!")

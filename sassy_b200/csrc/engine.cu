@@ -95,7 +95,7 @@ Engine::~Engine() {
 
 DeviceText* Engine::upload_text(const uint8_t* host, uint64_t n) {
   SB_CUDA(cudaSetDevice(device_));
-  if (n >= (1ull << kPosBits)) throw CudaError("text longer than 2^40 bytes is not supported");
+  if (n >= (1ull << kPosBits)) throw CapacityError("text longer than 2^40 bytes is not supported");
   DeviceText* t = new DeviceText;
   t->n = n;
   t->alloc = padded_alloc(n);
@@ -115,7 +115,7 @@ DeviceText* Engine::upload_text(const uint8_t* host, uint64_t n) {
 
 DeviceText* Engine::adopt_device_text(const void* dptr, uint64_t n) {
   SB_CUDA(cudaSetDevice(device_));
-  if (n >= (1ull << kPosBits)) throw CudaError("text longer than 2^40 bytes is not supported");
+  if (n >= (1ull << kPosBits)) throw CapacityError("text longer than 2^40 bytes is not supported");
   DeviceText* t = new DeviceText;
   t->n = n;
   t->alloc = padded_alloc(n);
@@ -141,7 +141,7 @@ void Engine::free_text(DeviceText* t) {
 
 DeviceText* Engine::stage_text(const uint8_t* host, uint64_t n) {
   SB_CUDA(cudaSetDevice(device_));
-  if (n >= (1ull << kPosBits)) throw CudaError("text longer than 2^40 bytes is not supported");
+  if (n >= (1ull << kPosBits)) throw CapacityError("text longer than 2^40 bytes is not supported");
   const size_t need = padded_alloc(n);
   if (need > staged_.alloc) {
     if (staged_.d) cudaFree(staged_.d);
@@ -486,7 +486,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   const uint32_t nq = (uint32_t)queries.size();
   if (m <= 0) throw CudaError("empty pattern");
   const int W = round_words((m + 31) / 32);
-  if (W < 0) throw CudaError("pattern longer than 1024 characters is not supported");
+  if (W < 0) throw CapacityError("pattern longer than 1024 characters is not supported");
   if (nq == 0) {
     if (pg_) throw CudaError("a gathered search needs at least one query on every rank");
     return;
@@ -632,6 +632,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   // falls back to the caller's collective.
   PeerGather* pg = pg_;
   gather_ok_ = false;
+  if (pg && pg->broken()) throw CudaError("this peer gather timed out earlier and cannot be used again");
   const bool pg_slot = pg && small_path && out.ops_words <= pg->max_ops_words() && pg->cap() >= (size_t)kSmallCandidates;
   bool pg_pushed = false, small_in_slot = false;
   auto pg_exchange = [&](bool force_overflow) {
@@ -686,7 +687,11 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   // after the synchronisation that follows a tail: did every rank deliver a complete result?
   auto pg_check = [&]() {
     if (!pg || !pg_pushed || gather_ok_) return gather_ok_;
-    if (pg->timed_out()) throw CudaError("peer gather timed out: a rank did not reach this search");
+    if (pg->timed_out()) {
+      pg->mark_broken();
+      throw CudaError("peer gather timed out (SASSY_B200_GATHER_TIMEOUT_S): a rank did not reach this search; "
+                      "the gather object cannot be used again");
+    }
     gather_ok_ = pg->ok();
     return gather_ok_;
   };
@@ -904,7 +909,7 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
   const uint32_t nq = (uint32_t)queries.size();
   if (m <= 0) throw CudaError("empty pattern");
   const int W = round_words((m + 31) / 32);
-  if (W < 0) throw CudaError("pattern longer than 1024 characters is not supported");
+  if (W < 0) throw CapacityError("pattern longer than 1024 characters is not supported");
   if (k < 0) k = 0;
   out.ops_words = (uint32_t)((m + k + 1 + 15) / 16);
   stats_.words = (uint32_t)W;
@@ -916,7 +921,7 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
   std::vector<uint64_t> meta(2 * ntexts);
   uint64_t total = 0;
   for (size_t i = 0; i < ntexts; i++) {
-    if (lens[i] >= (1ull << kPosBits)) throw CudaError("text longer than 2^40 bytes is not supported");
+    if (lens[i] >= (1ull << kPosBits)) throw CapacityError("text longer than 2^40 bytes is not supported");
     meta[i] = total;
     meta[ntexts + i] = lens[i];
     total += (lens[i] + 15) & ~15ull;

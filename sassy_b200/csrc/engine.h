@@ -21,6 +21,11 @@ namespace sb {
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
+// A size limit of this implementation (not an error of the reference): the C ABI's search()
+// reports it without aborting the process (include/sassy.h).
+struct CapacityError : CudaError {
+  using CudaError::CudaError;
+};
 
 struct DevBuf {
   void* p = nullptr;

@@ -20,6 +20,7 @@
 #include "peer_gather.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <stdexcept>
@@ -165,6 +166,14 @@ PeerGather::PeerGather(int device, int world, int rank, size_t cap, size_t max_o
   if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) throw std::invalid_argument("bad world/rank");
   if (cap == 0) throw std::invalid_argument("capacity must be positive");
   check(cudaSetDevice(device_), "cudaSetDevice");
+  // Ranks may legitimately be far apart (a multi-GB host text being staged, a candidate-buffer
+  // retry on one shard, first-launch module load): the wait for a peer's step flag is long by
+  // default and configurable.  A time-out means a rank is gone, not slow: the search fails on the
+  // ranks that waited and the PeerGather must not be used again (Engine drops it).
+  if (const char* e = getenv("SASSY_B200_GATHER_TIMEOUT_S")) {
+    const double s = atof(e);
+    if (s > 0) timeout_ns_ = (unsigned long long)(s * 1e9);
+  }
   slot_bytes_ = (sizeof(SlotHeader) + cap_ * 32 + cap_ * max_ops_words_ * 4 + 255) & ~(size_t)255;
   flags_off_ = 2 * (size_t)world_ * slot_bytes_;
   bytes_ = flags_off_ + 2 * (size_t)world_ * sizeof(unsigned long long);
@@ -249,7 +258,7 @@ cudaError_t PeerGather::exchange(const unsigned long long* d_counts, unsigned lo
   c.flags_off = flags_off_ + (step_ & 1) * (size_t)world_ * sizeof(unsigned long long);
   c.cap = cap_;
   c.step = step_;
-  c.timeout_ns = 5ull * 1000 * 1000 * 1000;
+  c.timeout_ns = timeout_ns_;
   collect_kernel<<<world_, 256, 0, stream>>>(c);
   return cudaGetLastError();
 }

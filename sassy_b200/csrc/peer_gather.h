@@ -39,6 +39,9 @@ class PeerGather {
                        cudaStream_t stream);
   bool ok() const;         // every rank delivered a complete result for the last step
   bool timed_out() const;  // some rank did not arrive within the time-out
+  // After a time-out the step counters of the ranks may differ: no further exchange is possible.
+  void mark_broken() { broken_ = true; }
+  bool broken() const { return broken_; }
   struct Slot {
     unsigned long long count, text_n, user;
     uint32_t ops_words;
@@ -56,6 +59,8 @@ class PeerGather {
   uint8_t* peer_[kMaxPeers];
   bool connected_ = false;
   unsigned long long step_ = 0;
+  unsigned long long timeout_ns_ = 120ull * 1000 * 1000 * 1000;  // SASSY_B200_GATHER_TIMEOUT_S
+  bool broken_ = false;
 };
 
 }  // namespace sb

@@ -16,6 +16,8 @@
 
 #include <stdlib.h>
 
+#include <mutex>
+
 #ifndef SB_UNROLL
 #define SB_UNROLL 2
 #endif
@@ -459,11 +461,21 @@ __global__ void __launch_bounds__(128)
 // Raises (never lowers) a kernel's dynamic shared-memory limit; one tracker per kernel
 // instantiation and device, because the attribute lives in the device's context and
 // cudaFuncSetAttribute *sets* the limit rather than maximising it.
+// One searcher per host thread is the documented usage (reference bin/grep.rs:488-498), so the
+// trackers and the occupancy / configuration caches below are shared between threads: every
+// access holds this lock (a few dozen nanoseconds per launch).
+std::mutex& config_mutex() {
+  static std::mutex m;
+  return m;
+}
+
 template <class Kern>
 cudaError_t ensure_smem(Kern kern, size_t smem, size_t (&set_dev)[64]) {
+  std::lock_guard<std::mutex> lock(config_mutex());
   int dev = 0;
   cudaGetDevice(&dev);
-  size_t& cur = set_dev[dev & 63];
+  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t& cur = set_dev[dev];
   if (smem > cur) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -585,10 +597,11 @@ struct FilterConfig {
   int bps = 0;
 };
 
-const FilterConfig& filter_config(int WF, int variant, bool pair) {
+FilterConfig filter_config(int WF, int variant, bool pair) {
   static FilterConfig cache[9][2][2];  // (all devices of a box are the same part)
-  static FilterConfig none;
-  if (WF < 1 || WF > 8) return none;
+  static std::mutex mu;                // not config_mutex(): filter_occupancy takes that one
+  if (WF < 1 || WF > 8) return FilterConfig();
+  std::lock_guard<std::mutex> lock(mu);
   FilterConfig& c = cache[WF][variant & 1][pair ? 1 : 0];
   if (c.bps) return c;
   size_t smem = (size_t)256 * WF * sizeof(uint32_t);
@@ -886,6 +899,8 @@ cudaError_t launch_scan(int W, bool rev, int variant, const CUtensorMap* tmap, c
 
 int scan_blocks_per_sm(int W, bool rev, int variant, uint32_t nrows) {
   static int cache[33][2][2][3] = {};  // occupancy queries cost tens of microseconds: ask once per shape
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   const int rb = nrows <= 4 ? 0 : (nrows <= 32 ? 1 : 2);
   int* slot = (W >= 1 && W <= 32) ? &cache[W][rev ? 1 : 0][variant & 1][rb] : nullptr;
   if (slot && *slot) return *slot;

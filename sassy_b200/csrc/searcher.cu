@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "../../include/sassy_gpu.h"
+#include "shard_merge.h"
 
 namespace sb {
 
@@ -525,7 +526,15 @@ uintptr_t search(sassy_SearcherType* searcher, const uint8_t* pattern, uintptr_t
   if (!searcher || !pattern || !text || !out_matches) die("Pointers in search() must not be null");
   std::vector<sb::Match> v;
   try {
+    g_last_error.clear();
     v = searcher->s.search(pattern, pattern_len, text, text_len, k, /*all_minima=*/false);
+  } catch (const sb::CapacityError& e) {
+    // Not one of the reference's panics: a limit of this implementation (pattern longer than
+    // 1024 characters, text of 2^40 bytes or more).  The process is not aborted: no matches are
+    // returned, the message goes to stderr and to sassy_gpu_last_error() (include/sassy.h).
+    g_last_error = e.what();
+    fprintf(stderr, "sassy_b200: search() not run: %s\n", e.what());
+    v.clear();
   } catch (const std::exception& e) {
     die(e.what());
   }
@@ -836,6 +845,27 @@ sassy_gpu_Result* sassy_gpu_search_encoded_gathered(sassy_SearcherType* searcher
     auto v = searcher->s.search_encoded_gathered(gather->g, patterns->e, *text->t, k, all != 0, &ok);
     *complete = ok ? 1 : 0;
     return to_result(v);
+  });
+}
+
+sassy_gpu_Result* sassy_gpu_merge_slabs(const sassy_gpu_Match* records, size_t n_records, const char* ops,
+                                        const sassy_gpu_Slab* slabs, size_t n_slabs, uint64_t n_global, int all) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if ((n_records && !records) || !slabs) throw std::invalid_argument("null pointer");
+    std::vector<sassy_gpu_Match> recs(records, records + n_records);
+    std::vector<sb::SlabInfo> info(n_slabs);
+    for (size_t i = 0; i < n_slabs; i++) info[i] = sb::SlabInfo{slabs[i].window_off, slabs[i].own_lo, slabs[i].own_hi};
+    const std::vector<size_t> keep = sb::merge_slab_matches(recs, info.data(), n_slabs, n_global, all != 0);
+    sassy_gpu_Result* r = new sassy_gpu_Result;
+    r->m.reserve(keep.size());
+    for (size_t i : keep) {
+      sassy_gpu_Match o = recs[i];
+      const uint64_t off = o.ops_off;
+      o.ops_off = r->ops.size();
+      if (o.ops_len && ops) r->ops.append(ops + off, o.ops_len);
+      r->m.push_back(o);
+    }
+    return r;
   });
 }
 

@@ -267,3 +267,77 @@ class PeerGather:
         res = self._lib.sassy_gpu_search_encoded_gathered(self._searcher._h, self._h, enc._h, text._h, k,
                                                           int(all_minima), ctypes.byref(ok))
         return self._finish(res, ok.value)
+
+
+# ---------------------------------------------------------------------------------------------
+# One text cut into slabs (SURVEY 8e "Partitioning"; the reference's lane chunking with overlap,
+# src/search.rs:1018-1049,1202-1240, at GPU granularity).
+
+def slab_layout(n_global: int, world: int, m: int, k: int):
+    """[(window_lo, window_hi, own_lo, own_hi)] per rank: slab r owns [own_lo, own_hi), its search
+    window adds an (m + k) halo on both sides (left: warm-up of the forward scan and the traceback
+    window; right: the same for the reverse-complement strand, which scans right to left)."""
+    halo = m + k
+    per = -(-n_global // world)
+    out = []
+    for r in range(world):
+        lo, hi = min(n_global, r * per), min(n_global, (r + 1) * per)
+        out.append((max(0, lo - halo), min(n_global, hi + halo), lo, hi))
+    return out
+
+
+def merge_slabs(matches, layout, n_global: int, all_minima: bool = False):
+    """Gathered per-slab search_all records (text_idx = source rank, window coordinates) -> the
+    matches of the unsharded search: ownership filter, global coordinates, local-minima rule on the
+    merged list (sassy_gpu_merge_slabs, host code in csrc/shard_merge.h)."""
+    import ctypes
+    from . import _native
+    from .searcher import MatchList, _REC_DTYPE
+    lib = _native.load()
+    recs, raw = _local_block(matches)
+    n = recs.size // _REC_DTYPE.itemsize
+    slabs = np.zeros((len(layout), 3), dtype=np.uint64)
+    for r, (wlo, _whi, lo, hi) in enumerate(layout):
+        slabs[r] = (wlo, lo, hi)
+    recs = np.ascontiguousarray(recs)
+    raw = np.ascontiguousarray(raw)
+    res = lib.sassy_gpu_merge_slabs(recs.ctypes.data if n else None, n, raw.ctypes.data if raw.size else None,
+                                    slabs.ctypes.data, len(layout), n_global, int(all_minima))
+    if not res:
+        raise RuntimeError(_native.last_error())
+    try:
+        cnt = lib.sassy_gpu_result_len(res)
+        if cnt == 0:
+            return MatchList(np.zeros(0, dtype=_REC_DTYPE), b"")
+        addr = ctypes.cast(lib.sassy_gpu_result_matches(res), ctypes.c_void_p).value
+        out = np.frombuffer(bytes((ctypes.c_char * (cnt * _REC_DTYPE.itemsize)).from_address(addr)), dtype=_REC_DTYPE)
+        total = int(out[-1]["ops_off"]) + int(out[-1]["ops_len"])
+        ops_ptr = lib.sassy_gpu_result_ops(res)
+        ops = bytes((ctypes.c_char * total).from_address(ops_ptr)) if ops_ptr and total else b""
+        return MatchList(out, ops)
+    finally:
+        lib.sassy_gpu_result_free(res)
+
+
+def search_text_sharded(searcher, pattern: bytes, window_text, k: int, n_global: int, all_minima: bool = False,
+                        peer_gather: "PeerGather" = None, group=None):
+    """Searcher::search / search_all of ONE text that is cut into `world` slabs, one per rank.
+
+    `window_text` holds this rank's window slab_layout(n_global, world, m, k)[rank] (a DeviceText,
+    bytes or a (address, length) tuple).  Every rank searches its window with search_all, the
+    records are exchanged (fused peer-memory gather when `peer_gather` is given, else one
+    all-gather) and merged on every rank; the result equals the unsharded search of the whole
+    text, including runs of minima that cross a slab border.  Collective: call on all ranks."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    m = len(pattern)
+    layout = slab_layout(n_global, world, m, k)
+    if peer_gather is not None:
+        ms = peer_gather.search(pattern, window_text, k, all_minima=True)
+    else:
+        ms = searcher.search_all(pattern, window_text, k)
+        if world > 1:
+            ms = gather_matches(tag_rank(ms, rank), max_ops=m + k + 1, group=group)
+        else:
+            ms = tag_rank(ms, 0)
+    return merge_slabs(ms, layout, n_global, all_minima)
