@@ -82,6 +82,8 @@ typedef struct sassy_gpu_Stats {
   float transfer_ms;        /* host->device transfer of the text (host-text entry points) */
   uint32_t transfer_packed; /* 1: (part of) the text crossed PCIe at 2 bits per character (Dna) */
   uint64_t transfer_bytes;  /* bytes that crossed PCIe for the text */
+  uint32_t filter_kind;     /* 0 none, 1 piece automaton (Shift-And), 2 q-gram bitmap, 3 SWAR suffix scan */
+  uint32_t swar_lanes;      /* patterns per 32-bit word in the scan that produced the candidates (0/1 = one) */
 } sassy_gpu_Stats;
 
 #ifdef __cplusplus

@@ -72,6 +72,8 @@ class GpuStats(ctypes.Structure):
         ("transfer_ms", ctypes.c_float),
         ("transfer_packed", ctypes.c_uint32),
         ("transfer_bytes", ctypes.c_uint64),
+        ("filter_kind", ctypes.c_uint32),
+        ("swar_lanes", ctypes.c_uint32),
     ]
 
 

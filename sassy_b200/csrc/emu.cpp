@@ -96,6 +96,47 @@ void filter_rows(const ScanArgs& a, const uint32_t* feq_q, uint32_t qs, bool pai
   }
 }
 
+// The body of qgram_kernel (scan_kernels.cu) on the host: one forward pass, hits for slot qs and,
+// with a.fused, for the reversed partner slot qs + a.nq.
+template <int Q, int S>
+void qgram_rows(const ScanArgs& a, const uint32_t* bitmap, uint32_t qs) {
+  const uint32_t total = a.g.nwarm + a.g.nstage;
+  const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
+  for (uint64_t row = 0; row < tiles * kScanThreads; row++) {
+    QLane s;
+    s.w = 0, s.prev = 0;
+    for (uint32_t it = 0; it < total; it++) {
+      int64_t r;
+      uint32_t col;
+      bool own;
+      stage_coord<false>(a.g, it, (int64_t)row, r, col, own);
+      const uint64_t stage_idx = (uint64_t)(r * (int64_t)a.g.ltot + (int64_t)col);
+      const bool valid = r >= 0 && r < (int64_t)a.g.rows;
+      uint32_t mask = 0;
+      for (int c = 0; c < kStageBytes / 16; c++) {
+        uint32_t x[4] = {0, 0, 0, 0};
+        if (valid) memcpy(x, a.text + stage_idx + 16u * c, 16);
+        if (qgram16<Q, S>(s, x, bitmap) & 1u) mask |= 1u << c;
+      }
+      if (mask) {
+        emit_stage_hits(a, HitQueue{nullptr, nullptr}, qs, stage_idx, mask, own);
+        if (a.fused) emit_stage_hits(a, HitQueue{nullptr, nullptr}, qs + a.nq, stage_idx, mask, own);
+      }
+    }
+  }
+}
+
+bool qgram_dispatch(int Q, int S, const ScanArgs& a, const uint32_t* bitmap, uint32_t qs) {
+#define EMU_Q(QQ, SS)            \
+  if (Q == QQ && S == SS) {      \
+    qgram_rows<QQ, SS>(a, bitmap, qs); \
+    return true;                 \
+  }
+  EMU_Q(8, 4) EMU_Q(8, 8) EMU_Q(8, 16) EMU_Q(7, 4) EMU_Q(6, 4)
+#undef EMU_Q
+  return false;
+}
+
 template <bool REV>
 void filter_dispatch(int WF, const ScanArgs& a, const uint32_t* feq_q, uint32_t qs, bool pair) {
   switch (WF) {
@@ -293,11 +334,47 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
   std::vector<const uint8_t*> qptr(nq);
   for (uint32_t q = 0; q < nq; q++) qptr[q] = queries + (size_t)q * m;
   FilterPlan fp;
+  // use_filter: 0 off, < 0 automatic, 1 force the piece automaton, 2 as Engine::search with the
+  // filter forced (q-gram bitmap when it can be planned, else the piece automaton)
   if (use_filter != 0) fp = plan_filter(profile, qptr.data(), nq, m, k, use_filter > 0 ? 1e30 : 0.85);
   res->hits = 0;
-  res->filter_words = fp.enabled ? fp.WF : 0;  // per strand
-  res->filter_len = fp.enabled ? fp.L : 0;
-  if (n > 0 && fp.enabled) {
+  QgramPlan qp;
+  {
+    uint32_t nf = 0;
+    while (nf < nq && !rev[nf]) nf++;
+    if (n > 0 && (use_filter == 2 || use_filter < 0) && !ov && profile == kDna && nf == 1 && nq <= 2)
+      qp = plan_qgram(m, k, (int)nq);
+  }
+  if (qp.enabled) fp.enabled = false;
+  res->filter_words = fp.enabled ? fp.WF : (qp.enabled ? 1 : 0);  // per strand
+  res->filter_len = fp.enabled ? fp.L : (qp.enabled ? qp.q : 0);
+  if (qp.enabled) {
+    std::vector<uint32_t> bitmap(qp.table_words(), 0);
+    std::vector<uint32_t> conf((size_t)nq * qp.npieces * 2);
+    for (uint32_t q = 0; q < nq; q++) {
+      add_qgram_entries(qp, qptr[q], rev[q] != 0, bitmap.data());
+      build_qgram_confirm(qp, qptr[q], rev[q] != 0, &conf[(size_t)q * qp.npieces * 2]);
+    }
+    std::vector<uint64_t> hits((size_t)nq * (n / kHitChars + 2) + 16);
+    unsigned long long nhits = 0;
+    ScanArgs f = a;
+    f.g.nwarm = 1;
+    f.fused = nq == 2 ? 1 : 0;
+    f.nq = 1;
+    f.hit_keys = hits.data();
+    f.hit_count = &nhits;
+    f.hit_cap = hits.size();
+    if (!qgram_dispatch(qp.q, qp.s, f, bitmap.data(), 0)) abort();
+    a.qconf = conf.data();
+    a.qnp = (uint32_t)qp.npieces;
+    a.qq = (uint32_t)qp.q;
+    res->hits = nhits;
+    for (unsigned long long h = 0; h < nhits; h++) {
+      const uint32_t qs = key_qs(hits[h]);
+      verify_dispatch(W, a, &eq[(size_t)qs * pp.nrows * W], qs, rev[qs] != 0, key_pos(hits[h]));
+    }
+    a.qconf = nullptr, a.qq = 0;
+  } else if (n > 0 && fp.enabled) {
     uint32_t nfwd = 0;
     while (nfwd < nq && !rev[nfwd]) nfwd++;
     const bool fused = nfwd > 0 && nq == 2 * nfwd && fp.WF <= 2;  // as Engine::search
@@ -473,6 +550,19 @@ int emu_plan_filter(int profile, const uint8_t* queries, uint32_t nq, int m, int
   };
   put(fp.enabled ? 1 : 0), put(fp.WF), put(fp.npieces), put(fp.L);
   for (int p = 0; p < fp.npieces; p++) put(fp.piece[p].off), put(fp.piece[p].len), put(fp.piece[p].word), put(fp.piece[p].bit);
+  return n;
+}
+
+// The q-gram plan for inspection in tests: out = {enabled, q, s, npieces, then (off, len) per share}.
+int emu_plan_qgram(int m, int k, int strands, int* out, int cap) {
+  const QgramPlan f = plan_qgram(m, k, strands);
+  int n = 0;
+  auto put = [&](int v) {
+    if (n < cap) out[n] = v;
+    n++;
+  };
+  put(f.enabled ? 1 : 0), put(f.q), put(f.s), put(f.npieces);
+  for (int p = 0; p < f.npieces; p++) put(f.off[p]), put(f.len[p]);
   return n;
 }
 

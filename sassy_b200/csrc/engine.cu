@@ -65,6 +65,10 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
   if (fm && !strcmp(fm, "force")) filter_mode_ = 2;
   const char* pm = getenv("SASSY_B200_PAIR_MAX_WORDS");
   if (pm) pair_max_words_ = atoi(pm);
+  const char* qm = getenv("SASSY_B200_QGRAM");
+  if (qm && !strcmp(qm, "0")) qgram_mode_ = 0;
+  const char* qq = getenv("SASSY_B200_QGRAM_MIN_Q");
+  if (qq) qgram_min_q_ = std::max(6, std::min(8, atoi(qq)));
   const char* fs = getenv("SASSY_B200_FUSE_STRANDS");
   if (fs && !strcmp(fs, "0")) fuse_strands_ = false;
   cudaDriverEntryPointQueryResult qres;
@@ -241,13 +245,16 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
 // All small per-search inputs travel in ONE host->device copy from a pinned staging
 // buffer: [4 counters][equality tables][query bytes][direction flags][prefilter tables].
 void Engine::upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair,
-                           bool fused) {
+                           bool fused, const QgramPlan* qp) {
   const size_t nq = queries.size();
   const size_t eq_bytes = nq * nrows_ * W * sizeof(uint32_t);
   const size_t pat_bytes = nq * (size_t)m;
   const int WT = fused ? 2 * fp.WF : fp.WF;  // automaton words per filter table
-  const size_t ntab = fused ? nq / 2 : nq;
-  const size_t tab_words = !fp.enabled ? 0 : (pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT);
+  // q-gram route: ONE bitmap for all queries (pattern and reversed partner), then the confirm codes
+  const size_t ntab = qp ? 1 : (fused ? nq / 2 : nq);
+  const size_t qconf_words = qp ? nq * (size_t)qp->npieces * 2 : 0;
+  const size_t tab_words = qp ? qp->table_words() + qconf_words
+                              : (!fp.enabled ? 0 : (pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT));
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   off_counts_ = 0;
   off_eq_ = align(4 * sizeof(unsigned long long));
@@ -270,7 +277,11 @@ void Engine::upload_params(const std::vector<Query>& queries, int m, int W, cons
     memcpy(h_stage_ + off_pat_ + q * m, queries[q].bytes, m);
     h_stage_[off_rev_ + q] = queries[q].rev ? 1 : 0;
     build_eq_table(profile_, queries[q].bytes, m, W, nrows_, h_eq + q * nrows_ * W);
-    if (fp.enabled && q < ntab) {
+    if (qp) {
+      if (q == 0) memset(h_feq, 0, tab_words * sizeof(uint32_t));
+      add_qgram_entries(*qp, queries[q].bytes, queries[q].rev, h_feq);
+      build_qgram_confirm(*qp, queries[q].bytes, queries[q].rev, h_feq + qp->table_words() + q * qp->npieces * 2);
+    } else if (fp.enabled && q < ntab) {
       const uint8_t* partner = fused ? queries[q + ntab].bytes : nullptr;  // the reversed partner query
       if (pair)
         build_pair_table(fp, queries[q].bytes, h_feq + q * tab_words, partner);
@@ -278,6 +289,7 @@ void Engine::upload_params(const std::vector<Query>& queries, int m, int W, cons
         build_filter_table(profile_, fp, queries[q].bytes, h_feq + q * tab_words, partner);
     }
   }
+  off_qconf_ = qp ? off_feq_ + qp->table_words() * sizeof(uint32_t) : 0;
   SB_CUDA(cudaMemcpyAsync(d_stage_.p, h_stage_, total, cudaMemcpyHostToDevice, stream_));
 }
 
@@ -519,11 +531,19 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   //  bandwidth, not instructions, would bound it -- measured 2.4x slower than the byte table)
   // Both strands of a v1 search (forward queries followed by their reversed partners) share ONE
   // forward pass: the partner's pieces, matched back to front, occupy a second set of words.
+  // Dna, one pattern (with or without its reversed partner): the q-gram bitmap finds the shares of
+  // both strands in one forward pass at a cost per character that does not depend on m or k
+  // (scan_core.cuh); it needs shares of >= 9 characters, shorter ones keep the piece automaton.
+  QgramPlan qp;
+  if (n > 0 && filter_mode_ != 0 && qgram_mode_ != 0 && !ov && profile_ == kDna && nfwd == 1 && nq <= 2)
+    qp = plan_qgram(m, k, (int)nq, qgram_min_q_);
+  const bool qgram = qp.enabled;
+  if (qgram) fp.enabled = false;
   const bool fused = fp.enabled && fuse_strands_ && nfwd > 0 && nq == 2 * nfwd && fp.WF <= 2;
   const int WT = fused ? 2 * fp.WF : fp.WF;
   const bool pair = profile_ == kDna && WT <= pair_max_words_;
   const size_t tab_words = pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT;
-  upload_params(queries, m, W, fp, pair, fused);
+  upload_params(queries, m, W, fp, pair, fused, qgram ? &qp : nullptr);
   uint8_t* dst = d_stage_.as<uint8_t>();
   unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(dst + off_counts_);
   unsigned long long* d_cand_count = d_counts;      // [0] candidates
@@ -701,16 +721,16 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   bool filtered = false;
 
   // ---- candidates, route 1: exact piece prefilter + re-scan of the hit neighbourhoods -----
-  if (fp.enabled) {
+  if (fp.enabled || qgram) {
     {  // room for 2x the expected number of hits (uniform text), within 8 M .. 128 M entries
-      const double expect = 2.0 * fp.rate * (double)n * nq;
+      const double expect = 2.0 * (qgram ? qp.rate : fp.rate) * (double)n * nq;
       uint64_t want = (uint64_t)std::min(std::max(expect, 8.0 * 1048576.0), 128.0 * 1048576.0);
       if (want > hit_cap_) hit_cap_ = want;
     }
     hits_.ensure(hit_cap_ * sizeof(uint64_t));
-    const int focc = filter_blocks_per_sm(WT, variant_, pair);
-    ScanGeom gf = choose_geom(n, m, k, nq, focc * sm_count_);
-    gf.nwarm = 1;  // a piece plus its delay line is at most 32 characters
+    const int focc = qgram ? qgram_blocks_per_sm(qp.q, qp.s, variant_) : filter_blocks_per_sm(WT, variant_, pair);
+    ScanGeom gf = choose_geom(n, m, k, qgram ? 1 : nq, focc * sm_count_);
+    gf.nwarm = 1;  // a piece plus its delay line is at most 32 characters; a q-gram window 16
     CUtensorMap ftmap;
     memset(&ftmap, 0, sizeof ftmap);
     if (variant_ == kVariantTma) make_tensor_map(&ftmap, text, gf);
@@ -725,14 +745,21 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     f.hit_count = d_hit_count;
     f.hit_cap = hit_cap_;
     SB_CUDA(cudaEventRecord(ev_[1], stream_));
-    if (nfwd) {
+    if (qgram) {
+      f.nq = 1;
+      f.qs_base = 0;
+      f.feq = d_feq;
+      f.fused = nq == 2 ? 1 : 0;  // every hit is re-scanned for the reversed partner (slot 1) too
+      SB_CUDA(launch_qgram(qp.q, qp.s, variant_, &ftmap, f, stream_));
+      stats_.scan_launches++;
+    } else if (nfwd) {
       f.nq = nfwd;
       f.qs_base = 0;
       f.feq = d_feq;
       SB_CUDA(launch_filter(WT, false, variant_, pair, &ftmap, f, stream_));
       stats_.scan_launches++;
     }
-    if (nq > nfwd && !fused) {
+    if (nq > nfwd && !fused && !qgram) {
       f.nq = nq - nfwd;
       f.qs_base = nfwd;
       f.feq = d_feq + (size_t)nfwd * tab_words;
@@ -750,6 +777,11 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     v.hit_cap = hit_cap_;
     if (fused)  // a reversed query's hit marks the START of its piece in scan direction
       for (int p = 0; p < fp.npieces; p++) v.rev_lead = std::max<uint32_t>(v.rev_lead, (uint32_t)fp.piece[p].len);
+    if (qgram) {  // hits are confirmed exactly (a whole share) before the re-scan
+      v.qconf = reinterpret_cast<const uint32_t*>(dst + off_qconf_);
+      v.qnp = (uint32_t)qp.npieces;
+      v.qq = (uint32_t)qp.q;
+    }
     SB_CUDA(launch_verify(W, v, d_rev, stream_));
     stats_.aux_launches++;
     SB_CUDA(cudaEventRecord(ev_[4], stream_));
@@ -759,10 +791,12 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     stats_.verify_ms = elapsed(ev_[2], ev_[4]);
     unsigned long long nhits = h_counts[2];
     stats_.hits = nhits;
-    stats_.filter_words = (uint32_t)WT;
-    stats_.filter_len = (uint32_t)fp.L;
+    stats_.filter_words = qgram ? 1u : (uint32_t)WT;
+    stats_.filter_len = qgram ? (uint32_t)qp.q : (uint32_t)fp.L;
+    stats_.filter_kind = qgram ? 2u : 1u;
     // too many hits (repetitive text, unlucky pieces): the re-scan costs more than the scan
-    const double rescan = (double)nhits * (2.0 * (m + k) + kHitChars);
+    // (q-gram hits are confirmed first: ~64 character-steps each unless a whole share is there)
+    const double rescan = (double)nhits * (qgram ? 64.0 : 2.0 * (m + k) + kHitChars);
     if (pg_check()) {  // every rank's result is complete and already gathered
       stats_.ltot = gf.ltot;
       stats_.rows = gf.rows;

@@ -69,6 +69,8 @@ struct SearchStats {
   float transfer_ms = 0;         // host->device transfer of the text, when the search got a host text
   uint32_t transfer_packed = 0;  // 1: sent at 2 bits per character (Dna transport encoding)
   uint64_t transfer_bytes = 0;   // bytes that crossed PCIe for the text
+  uint32_t filter_kind = 0;      // 0 none, 1 piece automaton (Shift-And), 2 q-gram bitmap, 3 SWAR suffix scan
+  uint32_t swar_lanes = 0;       // patterns per 32-bit word of the scan that produced the candidates (0/1 = one)
 };
 
 struct MatchSet {
@@ -156,7 +158,8 @@ class Engine {
   uint64_t post_process(const PostCtx& c, const SearchOpts& opts, uint64_t ncand, MatchSet& out);
   // Overhang: fills the arguments of the edge kernel (left-column deltas, wildcard steps).
   void overhang_args(const SearchOpts& opts, int m, int k, int W, OverhangArgs& o) const;
-  void upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair, bool fused);
+  void upload_params(const std::vector<Query>& queries, int m, int W, const FilterPlan& fp, bool pair, bool fused,
+                     const QgramPlan* qp = nullptr);
   void make_tensor_map(CUtensorMap* map, const DeviceText& text, const ScanGeom& g) const;
   // host -> dst (device, padded): packed transport for large Dna texts, else plain copies
   void send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint64_t n);
@@ -170,6 +173,9 @@ class Engine {
   int filter_mode_ = 1;
   bool fuse_strands_ = true;
   int pair_max_words_ = 4;  // Dna: two characters per automaton step up to this many words
+  int qgram_mode_ = 1;      // 0: never use the q-gram bitmap prefilter (SASSY_B200_QGRAM=0), 1: when planned
+  int qgram_min_q_ = 6;     // SASSY_B200_QGRAM_MIN_Q
+  size_t off_qconf_ = 0;
   int transport_mode_ = 1;
   float transfer_ms_ = 0;
   bool transfer_pending_ = false;

@@ -258,6 +258,82 @@ inline void build_pair_table(const FilterPlan& f, const uint8_t* pat, uint32_t* 
 }
 constexpr int kPairTableWords = 16 * 2;  // per automaton word
 
+// ---------------------------------------------------------------------------
+// q-gram bitmap prefilter (scan_core.cuh: qgram16 / qgram_confirm): plan and tables.
+struct QgramPlan {
+  bool enabled = false;
+  int q = 0;        // characters per q-gram: bitmap of 4^q bits
+  int s = 0;        // sampling distance in characters: 4, 8 or 16
+  int npieces = 0;  // k + 1 shares of the pattern
+  int off[kMaxPieces];
+  int len[kMaxPieces];
+  double rate = 0;  // expected hit chunks per text character on uniform ACGT text
+  size_t table_words() const { return ((size_t)1 << (2 * q)) / 32; }
+};
+
+// Shares of m / (k+1) characters (lengths differ by at most 1).  Q = min(8, shortest share - 3) so
+// that the sampling distance can be one text word; used from Q >= 6 (a 4^6-bit table is hit by
+// (k+1)/4096 of all positions, below that the exact confirmation would dominate).
+inline QgramPlan plan_qgram(int m, int k, int strands, int min_q = 6) {
+  QgramPlan f;
+  const int np = k + 1;
+  if (k < 0 || np > kMaxPieces || np > m) return f;
+  const int lmin = m / np;
+  const int q = std::min(8, lmin - 3);
+  if (q < min_q) return f;
+  f.q = q;
+  f.s = lmin >= q + 15 ? 16 : (lmin >= q + 7 ? 8 : 4);
+  f.npieces = np;
+  int off = 0;
+  for (int p = 0; p < np; p++) {
+    const int share = m / np + (p < m % np ? 1 : 0);
+    f.off[p] = off;
+    f.len[p] = share;
+    off += share;
+  }
+  f.rate = (double)np * strands / (double)((size_t)1 << (2 * q));
+  f.enabled = f.rate <= 4e-3;
+  return f;
+}
+
+// Forward-orientation class codes of share p of one query: the query bytes as the engine scans
+// them (the reversed partner = complement(pattern), scanned over the reversed text, occurs in the
+// forward text back to front).
+inline void qgram_piece_classes(const QgramPlan& f, int p, const uint8_t* query, bool reversed, uint8_t* out) {
+  for (int j = 0; j < f.len[p]; j++) {
+    const uint8_t ch = query[f.off[p] + (reversed ? f.len[p] - 1 - j : j)];
+    out[j] = (uint8_t)((ch >> 1) & 3);
+  }
+}
+
+// Sets, for every share of the query, the bits of its Q-grams at offsets 0 .. S-1.
+inline void add_qgram_entries(const QgramPlan& f, const uint8_t* query, bool reversed, uint32_t* bitmap) {
+  std::vector<uint8_t> cls;
+  for (int p = 0; p < f.npieces; p++) {
+    cls.resize(f.len[p]);
+    qgram_piece_classes(f, p, query, reversed, cls.data());
+    for (int o = 0; o < f.s && o + f.q <= f.len[p]; o++) {
+      uint32_t idx = 0;
+      for (int j = 0; j < f.q; j++) idx |= (uint32_t)cls[o + j] << (2 * j);
+      bitmap[idx >> 5] |= 1u << (idx & 31);
+    }
+  }
+}
+
+// {code, mask} of the first min(len, 16) characters of every share (qgram_confirm).
+inline void build_qgram_confirm(const QgramPlan& f, const uint8_t* query, bool reversed, uint32_t* out) {
+  std::vector<uint8_t> cls;
+  for (int p = 0; p < f.npieces; p++) {
+    cls.resize(f.len[p]);
+    qgram_piece_classes(f, p, query, reversed, cls.data());
+    const int l = std::min(f.len[p], 16);
+    uint32_t code = 0;
+    for (int j = 0; j < l; j++) code |= (uint32_t)cls[j] << (2 * j);
+    out[2 * p] = code;
+    out[2 * p + 1] = l == 16 ? 0xFFFFFFFFu : ((1u << (2 * l)) - 1u);
+  }
+}
+
 inline size_t padded_alloc(uint64_t n) {
   // room for one extra row of any tiling plus alignment slack
   return (size_t)((n + 2ull * kMaxRowBytes + 255ull) & ~255ull);

@@ -30,6 +30,10 @@ cudaError_t launch_scan(int W, bool rev, int variant, const CUtensorMap* tmap, c
 int filter_blocks_per_sm(int WF, int variant, bool pair);
 cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtensorMap* tmap, const ScanArgs& a,
                           cudaStream_t stream);
+// q-gram bitmap prefilter (Dna, one pattern, both strands in one pass): a.feq = the 4^Q-bit table,
+// a.fused = 1 reports every hit for the reversed partner slot too.  (Q, S) as planned by plan_qgram.
+int qgram_blocks_per_sm(int Q, int S, int variant);
+cudaError_t launch_qgram(int Q, int S, int variant, const CUtensorMap* tmap, const ScanArgs& a, cudaStream_t stream);
 // nhits is read from a.hit_count on the device (clipped to a.hit_cap): no host round trip.
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream);
 

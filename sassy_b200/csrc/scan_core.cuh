@@ -81,6 +81,10 @@ struct ScanArgs {
   unsigned long long* hit_count;
   uint64_t hit_cap;
   uint64_t emit_min;        // overhang: end positions <= emit_min come from the edge kernel instead
+  // q-gram bitmap prefilter (qgram_kernel): exact confirmation of a hit before its re-scan
+  const uint32_t* qconf;    // [query slot][qnp] {code, mask}: first <= 16 characters of every piece, 2 bits each
+  uint32_t qnp;             // pieces per query (k + 1)
+  uint32_t qq;              // q (characters per q-gram); 0 = hits are not q-gram hits
 };
 
 template <int W>
@@ -480,6 +484,113 @@ SB_HD void filter16_pair(FLane<WF>& s, const uint32_t (&x)[4], const EqTab& ftab
   }
 }
 
+// ---------------------------------------------------------------------------
+// q-gram bitmap prefilter (Dna profile, one pattern, both strands in one pass).
+//
+// Same pigeonhole argument as the piece automaton above -- an alignment with at most k edits
+// leaves one of the k+1 shares of the pattern intact -- but the shares are found through a
+// direct-addressed bitmap instead of an automaton whose width grows with k: the thread keeps the
+// last 16 text characters as 2-bit classes in one register (newest character in the top bits),
+// and every S characters (S = 4, 8 or 16: once per 1, 2 or 4 text words) tests ONE bit of a
+// 4^Q-bit table (Q <= 8: 8 KB of shared memory) for the Q-gram that ends there.  The table holds,
+// for every share F (forward orientation; the reverse-complement strand contributes the shares of
+// the reverse complement) the Q-grams F[o, o+Q) for o = 0..S-1; an occurrence of F covers S
+// consecutive Q-gram ends, one of which lies on the sampling grid (|F| >= Q + S - 1).  The cost per
+// text character does not depend on k or m: 3 instructions per text word to update the window
+// (LOP3, IMAD.HI, SHF) + 5 per sample (SHF, LOP3, LDS, SHF, LOP3).
+// Expected hits on uniform text: (k+1) * strands / 4^Q per character whatever S; a hit is
+// confirmed exactly (qgram_confirm: the first min(|F|, 16) characters of the share are compared
+// at the 16 possible alignments) before its neighbourhood is re-scanned.
+struct QLane {
+  uint32_t w;     // classes of the last 16 characters, character i-back at bits [30-2i, 32-2i)
+  uint32_t prev;  // IMAD.HI result of the previous text word: its low byte = that word's 4 classes
+};
+
+SB_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// 4 text bytes -> their classes ((c >> 1) & 3) as one byte, first character in the low bits, in the
+// LOW byte of the result (bits above it hold partial products: callers shift them out).
+SB_HD uint32_t pack4_classes(uint32_t x) {
+  // classes sit at bits 1-2, 9-10, 17-18, 25-26; the multiplier moves them to bits 32-39 of the
+  // 64-bit product (shifts 31, 25, 19, 13), no two partial products overlap
+  return umulhi32(x & 0x06060606u, 0x82082000u);
+}
+
+SB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // low word of (hi:lo) >> sh, sh in [0, 32)
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+// 16 text bytes.  Returns a word whose bit 0 is set iff a sampled Q-gram ending inside the chunk is
+// in the table (other bits are garbage).  tab = the bitmap (shared memory on the device).
+template <int Q, int S>
+SB_HD uint32_t qgram16(QLane& s, const uint32_t (&x)[4], const uint32_t* __restrict__ tab) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int ww = 0; ww < 4; ww++) {
+    const uint32_t hi = pack4_classes(x[ww]);
+    s.w = funnel_r(s.w, hi, 8);
+    if ((4 * (ww + 1)) % S == 0) {
+      if (Q == 8) {
+        // index = top 16 bits of the window: word = index >> 5, bit = index & 31 = the low 5 bits of
+        // the previous word's class byte (a shift uses the low 5 bits of its amount register)
+        acc |= tab[s.w >> 21] >> (s.prev & 31u);
+      } else {
+        const uint32_t idx = s.w >> (32 - 2 * Q);
+        acc |= tab[idx >> 5] >> (idx & 31u);
+      }
+    }
+    s.prev = hi;
+  }
+  return acc;
+}
+
+// Exact confirmation of a q-gram hit in the 16-byte chunk at forward index `base` (a multiple of
+// 16) for query slot `qs`: the sampled Q-gram ends at e in [base + S, base + 16] and starts at most
+// S - 1 characters into its share, so the share starts at a in [base + 1 - Q, base + 16 - Q]: 16
+// alignments, each compared with the first min(|F|, 16) characters of every share (2-bit classes,
+// one XOR + mask per share).  Both strands are tested in FORWARD orientation (the reversed
+// partner's shares are stored reversed).  A share occurrence is never missed; a false "true" only
+// costs a re-scan.
+SB_HD bool qgram_confirm(const ScanArgs& a, uint32_t qs, uint64_t base) {
+  // characters [base - 16, base + 32) as 2-bit classes, first character in the low bits
+  uint32_t c[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    uint32_t code = 0;
+    const int64_t at = (int64_t)base - 16 + 16 * j;
+    if (at >= 0) {
+      uint32_t x[4];
+#if defined(__CUDA_ARCH__)
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.text + at));
+      x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
+#else
+      memcpy(x, a.text + at, 16);
+#endif
+#pragma unroll
+      for (int ww = 0; ww < 4; ww++) code |= (pack4_classes(x[ww]) & 0xFFu) << (8 * ww);
+    }
+    c[j] = code;
+  }
+  const uint32_t* conf = a.qconf + (size_t)qs * a.qnp * 2;
+  for (int i = 0; i < 16; i++) {
+    const uint32_t off = 17u - a.qq + (uint32_t)i;  // start of the alignment relative to base - 16
+    const uint32_t val = funnel_r(c[off >> 4], c[(off >> 4) + 1], 2 * (off & 15u));
+    for (uint32_t p = 0; p < a.qnp; p++)
+      if (((val ^ conf[2 * p]) & conf[2 * p + 1]) == 0) return true;
+  }
+  return false;
+}
+
 // Re-scan of the neighbourhood of one hit with the exact recurrences.  The hit
 // is the text chunk at forward index 16*unit; in scan direction it starts at G0.
 // A piece occurrence ending inside the chunk implies end positions in
@@ -489,6 +600,7 @@ SB_HD void verify_hit(const ScanArgs& a, const uint32_t* eq /*[nrows][W] of this
                       uint64_t unit) {
   const int64_t n = (int64_t)a.n;
   const int64_t base = (int64_t)(unit * kHitChars);
+  if (a.qq && !qgram_confirm(a, qs, (uint64_t)base)) return;
   const int64_t g0 = rev ? n - kHitChars - base : base;  // may be negative for the chunk straddling the text end
   const int64_t span = (int64_t)a.m + (int64_t)a.k;
   int64_t w0 = g0 - span;

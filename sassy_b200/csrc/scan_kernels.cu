@@ -309,6 +309,57 @@ __global__ void __launch_bounds__(kScanThreads, (WF <= 4 ? 1024 : 512) / kScanTh
   flush_hits(a, hq, lane);
 }
 
+// q-gram bitmap prefilter (scan_core.cuh: qgram16): one forward pass for both strands, cost per
+// character independent of m and k.  a.feq = the bitmap (4^Q bits), copied to shared memory;
+// a.fused = 1: every hit is reported for the reversed partner slot (qs + a.nq) as well.
+template <int Q, int S, int VARIANT>
+__global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
+    qgram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a) {
+  __shared__ uint64_t hit_q[kWarpsPerBlock][kHitQueueCap];
+  __shared__ uint32_t hit_n[kWarpsPerBlock];
+  constexpr uint32_t kTabWords = (1u << (2 * Q)) / 32;
+  __shared__ __align__(16) uint32_t bitmap[kTabWords];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x % a.nq;
+  const uint32_t qs = a.qs_base + q;
+  HitQueue hq;
+  hq.q = hit_q[warp];
+  hq.n = &hit_n[warp];
+  if (lane == 0) hit_n[warp] = 0;
+  EqTab eqt;
+  eqt.rowbytes = 4u;
+  QLane s;
+  s.w = 0, s.prev = 0;
+  row_pipeline<false, VARIANT>(tmap, a, a.feq + (size_t)q * kTabWords, kTabWords, bitmap, eqt,
+                               [&](uint64_t stage_idx, bool own, auto chunk) {
+                                 uint32_t acc[kChunks];
+#pragma unroll
+                                 for (int c = 0; c < kChunks; c++) {
+                                   const uint4 v = chunk(c);
+                                   const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+                                   acc[c] = qgram16<Q, S>(s, x, bitmap);
+                                 }
+                                 uint32_t any = 0;
+#pragma unroll
+                                 for (int c = 0; c < kChunks; c++) any |= acc[c];
+                                 any &= 1u;
+                                 if (__any_sync(0xFFFFFFFFu, any != 0)) {
+                                   if (any && own) {
+#pragma unroll
+                                     for (int c = 0; c < kChunks; c++) {
+                                       const uint64_t base_idx = stage_idx + (uint64_t)(kHitChars * c);
+                                       if (!(acc[c] & 1u) || base_idx >= a.n) continue;
+                                       push_hit(a, hq, qs, base_idx);
+                                       if (a.fused) push_hit(a, hq, qs + a.nq, base_idx);
+                                     }
+                                   }
+                                   __syncwarp();
+                                   if (*hq.n >= kHitQueueCap / 2) flush_hits(a, hq, lane);  // warp-uniform
+                                 }
+                               });
+  flush_hits(a, hq, lane);
+}
+
 template <int W>
 __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __restrict__ rev_flags,
                                            unsigned long long i);
@@ -421,6 +472,7 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
 
   const int64_t n = (int64_t)a.n;
   const int64_t base = (int64_t)(key_pos(key) * kHitChars);
+  if (a.qq && !qgram_confirm(a, qs, (uint64_t)base)) return;  // a q-gram hit without a whole share behind it
   const int64_t g0 = rev ? n - kHitChars - base : base;
   const int64_t span = (int64_t)a.m + (int64_t)a.k;
   int64_t w0 = g0 - span;
@@ -654,6 +706,91 @@ cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtens
 
 namespace {
 
+template <int Q, int S, int VARIANT>
+size_t (&qgram_smem_tracker())[64] {
+  static size_t t[64] = {};
+  return t;
+}
+
+template <int Q, int S, int VARIANT>
+cudaError_t launch_qgram_one(const CUtensorMap* tmap, const ScanArgs& a, size_t smem, cudaStream_t stream,
+                             int* occupancy) {
+  auto kern = qgram_kernel<Q, S, VARIANT>;
+  {
+    cudaError_t e = ensure_smem(kern, smem, qgram_smem_tracker<Q, S, VARIANT>());
+    if (e != cudaSuccess) return e;
+  }
+  if (occupancy) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kScanThreads, smem) != cudaSuccess) nb = 1;
+    *occupancy = nb > 0 ? nb : 1;
+    return cudaSuccess;
+  }
+  const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
+  const uint64_t blocks = tiles * a.nq;
+  if (blocks == 0) return cudaSuccess;
+  if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+  CUtensorMap dummy;
+  if (!tmap) {
+    memset(&dummy, 0, sizeof dummy);
+    tmap = &dummy;
+  }
+  kern<<<(unsigned)blocks, kScanThreads, smem, stream>>>(*tmap, a);
+  return cudaGetLastError();
+}
+
+cudaError_t qgram_dispatch(int Q, int S, int variant, const CUtensorMap* tmap, const ScanArgs& a, size_t smem,
+                           cudaStream_t stream, int* occupancy) {
+#define SB_QCALL(QQ, SS)                                                                            \
+  if (Q == QQ && S == SS)                                                                           \
+    return variant == kVariantTma ? launch_qgram_one<QQ, SS, kVariantTma>(tmap, a, smem, stream, occupancy) \
+                                  : launch_qgram_one<QQ, SS, kVariantLdg>(tmap, a, smem, stream, occupancy);
+  SB_QCALL(8, 4) SB_QCALL(8, 8) SB_QCALL(8, 16)
+  SB_QCALL(7, 4) SB_QCALL(6, 4)
+#undef SB_QCALL
+  return cudaErrorInvalidValue;
+}
+
+// Resident blocks per SM of the q-gram kernel: the TMA-fed row pipeline is fastest well below
+// the register-limited residency (profiles/r01b_filter_residency.md); the dynamic shared memory is
+// padded until at most the target is resident.
+FilterConfig qgram_config(int Q, int S, int variant) {
+  static FilterConfig cache[9][17][2];
+  static std::mutex mu;
+  if (Q < 6 || Q > 8 || S < 4 || S > 16) return FilterConfig();
+  std::lock_guard<std::mutex> lock(mu);
+  FilterConfig& c = cache[Q][S][variant & 1];
+  if (c.bps) return c;
+  static const int target = [] {
+    const char* e = getenv("SASSY_B200_QGRAM_BPS");
+    const int x = e ? atoi(e) : 0;
+    return x >= 1 && x <= 16 ? x : 6;
+  }();
+  ScanArgs dummy;
+  memset(&dummy, 0, sizeof dummy);
+  size_t smem = variant == kVariantTma ? 1024 + (size_t)kRingBytes : 0;
+  int occ = 1;
+  qgram_dispatch(Q, S, variant, nullptr, dummy, smem, nullptr, &occ);
+  if (variant == kVariantTma)
+    while (occ > target && smem + 1024 <= 200 * 1024) {
+      smem += 1024;
+      qgram_dispatch(Q, S, variant, nullptr, dummy, smem, nullptr, &occ);
+    }
+  c.smem = smem;
+  c.bps = occ;
+  return c;
+}
+
+}  // namespace
+
+int qgram_blocks_per_sm(int Q, int S, int variant) { return qgram_config(Q, S, variant).bps; }
+
+cudaError_t launch_qgram(int Q, int S, int variant, const CUtensorMap* tmap, const ScanArgs& a, cudaStream_t stream) {
+  return qgram_dispatch(Q, S, variant, tmap, a, qgram_config(Q, S, variant).smem, stream, nullptr);
+}
+
+namespace {
+
 // One word of the recurrences with explicit carries (the multi-word form of myers_step): used by
 // the warp-systolic kernels, where word w of a pattern lives in lane w.
 //   cin / cout: bit 0 = carry of the addition, bit 1 = Ph carry, bit 2 = Mh carry
@@ -700,6 +837,11 @@ __global__ void __launch_bounds__(32 * kWideWarps)
     const uint32_t* __restrict__ eq = a.eq + (size_t)qs * a.nrows * W;
     const int64_t n = (int64_t)a.n;
     const int64_t base = (int64_t)(key_pos(key) * kHitChars);
+    if (a.qq) {  // q-gram hit: re-scan only behind a whole share (warp-uniform decision)
+      int okc = 0;
+      if (lane == 0) okc = qgram_confirm(a, qs, (uint64_t)base) ? 1 : 0;
+      if (!__shfl_sync(0xFFFFFFFFu, okc, 0)) continue;
+    }
     const int64_t g0 = rev ? n - kHitChars - base : base;
     const int64_t span = (int64_t)a.m + (int64_t)a.k;
     int64_t w0 = g0 - span;

@@ -641,6 +641,8 @@ int sassy_gpu_stats(const sassy_SearcherType* searcher, sassy_gpu_Stats* out) {
   out->transfer_ms = st.transfer_ms;
   out->transfer_packed = st.transfer_packed;
   out->transfer_bytes = st.transfer_bytes;
+  out->filter_kind = st.filter_kind;
+  out->swar_lanes = st.swar_lanes;
   return 0;
 }
 

@@ -22,6 +22,7 @@ def key(m):
 
 @pytest.fixture(scope="module")
 def world():
+    import argparse
     import torch
     import bench
     import sassy_b200
@@ -29,20 +30,23 @@ def world():
         pytest.skip("needs a GPU with room for the 3 GB text and its shards")
     dev = torch.device("cuda", 0)
     m, k = 20, 2
-    pats = bench.make_patterns("dna", 1, m)
-    text = bench.synth_text_device(torch, N, 42, dev)
-    plants = bench.plant_list(pats, N, k, 64, seed=44)
+    args = argparse.Namespace(c5_patterns=2048)
+    # bench.py's text: uniform ACGT with the c2 / c4 patterns planted 64 times and the c3 / c5
+    # guides twice (0..k edits each)
+    text = bench.build_window(torch, args, N, 1, 0, N, dev)
+    pat = bench.workload_patterns("c2", 1)[0]
+    plants = [(pos, q) for pos, q in bench.slab_plants(0, N, bench.planted_set(args)[:1])]
     # also plant reverse complements and copies right at the ends and at the cut
     rng = random.Random(7)
     cut = 1_400_000_123
-    extra = [(0, pats[0]), (N - m, pats[0]), (cut - 7, pats[0]), (cut + 1, oracle.reverse_complement("dna", pats[0]))]
+    extra = [(0, pat), (N - m, pat), (cut - 7, pat), (cut + 1, oracle.reverse_complement("dna", pat))]
     for i in range(16):
-        extra.append((rng.randrange(1000, N - 1000) // 64 * 64 + 61, oracle.reverse_complement("dna", pats[0])))
-    for pos, q in plants + extra:
+        extra.append((rng.randrange(1000, N - 1000) // 64 * 64 + 61, oracle.reverse_complement("dna", pat)))
+    for pos, q in extra:
         text[pos:pos + len(q)] = torch.tensor(list(q), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
     s = sassy_b200.Searcher("dna", rc=True, device=0)
-    return dict(torch=torch, s=s, text=text, pat=pats[0], m=m, k=k, plants=plants + extra, cut=cut)
+    return dict(torch=torch, s=s, text=text, pat=pat, m=m, k=k, plants=plants + extra, cut=cut, args=args)
 
 
 def test_fullsize_planted_and_sharding(world):
@@ -99,3 +103,80 @@ def test_fullsize_host_pointer_equals_resident(world):
     dt = s.text_from_device(text.data_ptr(), N)
     want = sorted(map(key, s.search(p, dt, k)))
     assert got == want and len(got) >= 64
+
+
+# ---- the other BASELINE shapes at full size --------------------------------------------------
+# c4 (Dna, m = 100, k = 8, multi-word), c3 (Iupac batch, m = 23, k = 4) and c5 (k = 3): the GPU end
+# positions and costs over the whole 3 GB equal the CPU port's (itself pinned to the oracle by
+# tests/test_cpu_port.py), every planted copy is found, and a sample of the reported matches is
+# re-derived by the oracle (coordinates, cost and CIGAR) on the match's own neighbourhood.
+
+def _host_copy(world):
+    torch, text = world["torch"], world["text"]
+    if "host" not in world:
+        host = torch.empty(N, dtype=torch.uint8, pin_memory=True)
+        host.copy_(text)
+        torch.cuda.synchronize()
+        world["host"] = host
+    return world["host"]
+
+
+def _oracle_recheck(profile, pats, text, ms, m, k, encoded, limit=300):
+    step = max(1, len(ms) // limit)
+    for x in list(ms)[::step][:limit]:
+        lo = max(0, x.text_start - 2 * (m + k))
+        hi = min(N, x.text_end + 2 * (m + k))
+        window = bytes(text[lo:hi].cpu().numpy().tobytes())
+        p = pats[x.pattern_idx]
+        if encoded:
+            want = oracle.search_encoded(profile, [p], window, k, rc=False, all_minima=True)
+        else:
+            want = oracle.search(profile, p, window, k, rc=False, all_minima=True)
+        want = [(w.text_start + lo, w.text_end + lo, w.cost, w.cigar) for w in want]
+        assert (x.text_start, x.text_end, x.cost, x.cigar) in want, (x, want[:4])
+
+
+def test_fullsize_c4_shape(world):
+    import bench
+    import sassy_b200
+    from oracle import cpu_port
+    text = world["text"]
+    host = _host_copy(world)
+    p = bench.workload_patterns("c4", 1)[0]
+    m, k = 100, 8
+    s = sassy_b200.Searcher("dna", rc=False, device=0)
+    dt = s.text_from_device(text.data_ptr(), N)
+    got = s.search(p, dt, k)
+    assert s.stats()["filter_words"] > 0 and not s.stats()["filter_fallback"]  # the production route
+    ends, _ = cpu_port.search_ends("dna", p, host.data_ptr(), N, k, False, False, threads=16)
+    assert sorted((x.text_end, x.cost) for x in got) == sorted((e, c) for e, c, _ in ends)
+    assert len(got) >= 64
+    _oracle_recheck("dna", [p], text, got, m, k, encoded=False)
+    # search_all: superset of search, and every position the CPU port reports
+    got_all = s.search_all(p, dt, k)
+    ends_all, _ = cpu_port.search_ends("dna", p, host.data_ptr(), N, k, False, True, threads=16, cap=1 << 22)
+    assert sorted((x.text_end, x.cost) for x in got_all) == sorted((e, c) for e, c, _ in ends_all)
+    dt.free()
+
+
+@pytest.mark.parametrize("k,npat", [(4, 12), (3, 24)])
+def test_fullsize_guide_batches(world, k, npat):
+    """c3 (k = 4) and c5 (k = 3) shapes: encoded Iupac guides (20 nt + NGG) over the whole text."""
+    import bench
+    import sassy_b200
+    from oracle import cpu_port
+    text = world["text"]
+    host = _host_copy(world)
+    pats = bench.workload_patterns("c3", npat)
+    m = 23
+    s = sassy_b200.Searcher("iupac", rc=False, device=0)
+    dt = s.text_from_device(text.data_ptr(), N)
+    got = s.search_encoded_patterns(s.encode_patterns(pats), dt, k)
+    want = []
+    for pi, p in enumerate(pats):
+        ends, _ = cpu_port.search_ends("iupac", p, host.data_ptr(), N, k, False, False, threads=16)
+        want += [(pi, e, c) for e, c, _ in ends]
+    assert sorted((x.pattern_idx, x.text_end, x.cost) for x in got) == sorted(want)
+    assert len(got) >= 2 * npat  # every guide was planted twice
+    _oracle_recheck("iupac", pats, text, got, m, k, encoded=True)
+    dt.free()

@@ -285,3 +285,137 @@ def test_gpu_long_patterns_many_pieces(tma):
             assert list(map(key, got)) == list(map(key, want)), (m, k, allm)
         assert len(want) >= 1
     assert s.stats()["filter_words"] in (1, 2, 4, 8)
+
+
+def test_gpu_qgram_prefilter_fuzz():
+    """The q-gram bitmap route (Dna, one pattern, shares >= 9 characters): every (Q, S) instantiation,
+    both strands in one pass, against the oracle; also checks that the route is the one taken."""
+    import sassy_b200
+    from tests.test_oracle_props import mutate
+    rng = random.Random(71)
+    seen = set()
+    searchers = {}
+    for rc_ in (False, True):
+        searchers[rc_] = sassy_b200.Searcher("dna", rc=rc_)
+        searchers[rc_].set_filter("force")
+    for it in range(90):
+        m, k = rng.choice([(20, 1), (30, 2), (36, 3), (40, 3), (60, 3), (100, 8), (100, 3), (120, 5), (64, 2),
+                           (200, 8), (18, 1), (27, 2), (150, 1), (500, 8), (1000, 8), (260, 6)])
+        n = rng.randrange(0, 60000)
+        p, t = planted(rng, m, max(n, 1), k)
+        t = bytearray(t[:n])
+        for _ in range(4):
+            q = mutate(rng, p, rng.randrange(0, k + 1))
+            if rng.random() < 0.5:
+                q = oracle.reverse_complement("dna", q)
+            pos = rng.randrange(0, max(1, n))
+            if pos + len(q) <= n:
+                t[pos:pos + len(q)] = q
+        if rng.random() < 0.15:
+            t = bytearray(c | 0x20 if rng.random() < 0.3 else c for c in t)
+        t = bytes(t)
+        rc = rng.random() < 0.7
+        s = searchers[rc]
+        for allm in (False, True):
+            want = oracle.search("dna", p, t, k, rc=rc, all_minima=allm)
+            got = (s.search_all if allm else s.search)(p, t, k)
+            assert [(x.text_start, x.text_end, x.cost, x.strand, x.cigar) for x in got] == \
+                   [(x.text_start, x.text_end, x.cost, x.strand, x.cigar) for x in want], (p, t, k, rc, allm)
+            st = s.stats()
+            if n:
+                assert st["filter_kind"] == 2 and st["filter_fallback"] == 0, st
+                seen.add((st["filter_len"], m // (k + 1) >= 8 + 15, m // (k + 1) >= 8 + 7))
+    assert len(seen) >= 5, seen  # Q in {6, 7, 8} and S in {4, 8, 16}
+
+
+def test_gpu_qgram_large_text():
+    """64 MB: thousands of false q-gram hits (rejected by the exact confirmation) next to planted
+    copies on every kind of row boundary; equals the full scan."""
+    import sassy_b200
+    rng = random.Random(72)
+    n = 1 << 26
+    base = bytes(rng.choice(b"ACGT") for _ in range(1 << 16))
+    for m, k in ((100, 8), (40, 3), (1000, 8)):
+        p = rand_seq(rng, m)
+        t = bytearray(base * (n >> 16))
+        rcp = oracle.reverse_complement("dna", p)
+        spots = [0, n - m, 13312 * 7 - 5, 9984 * 3 - m // 2, 16384 * 11 + 1, 64 * 1000 - 3, 5_000_011, 33_000_000]
+        for i, pos in enumerate(spots):
+            q = bytearray(p if i % 2 == 0 else rcp)
+            for _ in range(i % (k + 1)):
+                q[rng.randrange(m)] = rng.choice(b"ACGT")
+            t[pos:pos + m] = q
+        t = bytes(t)
+        s = sassy_b200.Searcher("dna", rc=True)
+        s.set_filter("force")
+        got = s.search(p, t, k)
+        st = s.stats()
+        assert st["filter_kind"] == 2 and st["filter_fallback"] == 0 and st["hits"] > 0, st
+        s.set_filter("off")
+        want = s.search(p, t, k)
+        assert list(map(key, got)) == list(map(key, want)) and len(got) >= len(spots)
+        # the planted copies, checked by the oracle on their own neighbourhoods
+        for pos in spots:
+            lo, hi = max(0, pos - 2 * (m + k)), min(n, pos + m + 2 * (m + k))
+            w = oracle.search("dna", p, t[lo:hi], k, rc=True, all_minima=True)
+            assert any(x.text_start >= lo and x.text_end <= hi and
+                       (x.text_start - lo, x.text_end - lo, x.cost, x.strand, x.cigar) in
+                       {(y.text_start, y.text_end, y.cost, y.strand, y.cigar) for y in w} for x in got)
+
+
+def test_gpu_ascii_fuzz(tma):
+    """Ascii profile (case-sensitive byte equality, reference src/profiles/ascii.rs): random
+    printable texts with planted, edited copies; forward strand only (the reference has no
+    reverse complement for Ascii), search and search_all."""
+    rng = random.Random(73)
+    alpha = b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789 .,;:-_!?()[]{}"
+    for it in range(80):
+        m = rng.choice([1, 3, 7, 15, 31, 32, 33, 64, 100, 200])
+        n = rng.randrange(0, 12000)
+        k = rng.randrange(0, max(1, m // 3) + 1)
+        small = rng.random() < 0.3
+        al = alpha[:4] if small else alpha
+        p = bytes(rng.choice(al) for _ in range(m))
+        t = bytearray(rng.choice(al) for _ in range(n))
+        for _ in range(3):
+            q = bytearray(p)
+            for _ in range(rng.randrange(0, k + 1)):
+                op = rng.randrange(3)
+                pos = rng.randrange(len(q))
+                if op == 0:
+                    q[pos] = rng.choice(al)
+                elif op == 1:
+                    q.insert(pos, rng.choice(al))
+                elif len(q) > 1:
+                    del q[pos]
+            pos = rng.randrange(0, max(1, n))
+            if pos + len(q) <= n:
+                t[pos:pos + len(q)] = q
+        t = bytes(t)
+        for allm in (False, True):
+            want = oracle.search("ascii", p, t, k, rc=False, all_minima=allm)
+            got = tma.search("ascii", p, t, k, rc=False, all_minima=allm)
+            assert list(map(key, got)) == list(map(key, want)), (p, t, k, allm)
+
+
+def test_c_abi_search_beyond_capacity_does_not_abort():
+    """A pattern of more than 1024 characters is a limit of this implementation, not one of the
+    reference's panics: search() returns no matches, leaves the reason in sassy_gpu_last_error()
+    and the process lives (include/sassy.h)."""
+    from sassy_b200 import _native
+    lib = _native.load()
+    s = lib.sassy_searcher(b"dna", True, math.nan)
+    assert s
+    rng = random.Random(5)
+    pat = bytes(rng.choice(b"ACGT") for _ in range(1025))
+    text = pat + bytes(rng.choice(b"ACGT") for _ in range(5000))
+    out = ctypes.POINTER(_native.CMatch)()
+    n = lib.search(s, pat, len(pat), text, len(text), 3, ctypes.byref(out))
+    assert n == 0 and bool(out)
+    assert "1024" in _native.last_error()
+    lib.sassy_matches_free(out, n)
+    n = lib.search(s, pat[:1024], 1024, text, len(text), 3, ctypes.byref(out))  # the longest supported pattern
+    assert n == 1 and out[0].text_start == 0 and out[0].text_end == 1024 and out[0].cost == 0
+    assert _native.last_error() == ""
+    lib.sassy_matches_free(out, n)
+    lib.sassy_searcher_free(s)

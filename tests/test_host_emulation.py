@@ -9,7 +9,7 @@ import pytest
 import oracle
 from tests import kat_util
 from tests.emu_backend import EmuBackend
-from tests.test_oracle_props import planted, rand_seq
+from tests.test_oracle_props import mutate, planted, rand_seq
 
 
 def key(m):
@@ -91,6 +91,67 @@ def test_emu_prefilter_fuzz(mode):
             assert list(map(key, got)) == list(map(key, want)), (alphabet, p, t, k, allm, b.last_filter)
             used += b.last_filter[0] > 0
     assert used > 50
+
+
+def test_emu_qgram_prefilter_fuzz():
+    """q-gram bitmap prefilter (sampled Q-grams of the k+1 shares, both strands in one table) + exact
+    confirmation + re-scan == oracle, for every (Q, S) the kernel is instantiated for; rc on and off,
+    planted copies with edits next to row borders, homopolymers, mixed case and non-ACGT text bytes
+    (the Dna profile searches every byte as (c >> 1) & 3)."""
+    rng = random.Random(21)
+    seen = set()
+    for it in range(260):
+        m, k = rng.choice([(20, 1), (30, 2), (36, 3), (40, 3), (60, 3), (100, 8), (100, 3), (120, 5), (64, 2),
+                           (200, 8), (99, 10), (18, 1), (27, 2), (150, 1)])
+        n = rng.randrange(0, 2500)
+        p, t = planted(rng, m, max(n, 1), k)
+        t = bytearray(t[:n])
+        for _ in range(3):  # copies (some reverse-complemented) straddling row borders of 64 / 128 / 192 bytes
+            q = mutate(rng, p, rng.randrange(0, k + 1))
+            if rng.random() < 0.5:
+                q = oracle.reverse_complement("dna", q)
+            pos = rng.choice([64, 128, 192, 256, 384]) * rng.randrange(1, 6) - rng.randrange(0, len(q) + 1)
+            if 0 <= pos and pos + len(q) <= n:
+                t[pos:pos + len(q)] = q
+        if rng.random() < 0.1:
+            t, p = bytearray(b"A" * n), b"A" * m
+        if rng.random() < 0.2:
+            t = bytearray(c | 0x20 if rng.random() < 0.3 else c for c in t)
+        t = bytes(t)
+        rc = rng.random() < 0.7
+        for allm in (False, True):
+            want = oracle.search("dna", p, t, k, rc=rc, all_minima=allm)
+            b = EmuBackend(ltot=rng.choice([0, 64, 128, 192]), use_filter=2)
+            got = b.search("dna", p, t, k, rc=rc, all_minima=allm)
+            assert list(map(key, got)) == list(map(key, want)), (p, t, k, rc, allm, b.last_filter)
+            if n and b.last_filter[0] == 1 and 6 <= b.last_filter[1] <= 8:  # else: no q-gram plan, piece automaton
+                seen.add((m, k))
+    assert len(seen) >= 11, seen
+
+
+def test_qgram_plan_and_tables():
+    """Every share is long enough for its sampled Q-gram (|share| >= Q + S - 1), the shares tile the
+    pattern, and the table holds exactly the Q-grams at offsets 0..S-1 of every share."""
+    import ctypes
+    from tests.emu_backend import _lib
+    lib = _lib()
+    lib.emu_plan_qgram.restype = ctypes.c_int
+    lib.emu_plan_qgram.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    out = (ctypes.c_int * 256)()
+    for m in range(1, 260, 3):
+        for k in range(0, 20):
+            cnt = lib.emu_plan_qgram(m, k, 2, out, 256)
+            enabled, q, s, npieces = out[0], out[1], out[2], out[3]
+            if not enabled:
+                assert m // (k + 1) < 9 or (k + 1) * 2 / 4 ** min(8, m // (k + 1) - 3) > 4e-3
+                continue
+            assert cnt == 4 + 2 * npieces and npieces == k + 1
+            assert 6 <= q <= 8 and s in (4, 8, 16)
+            pieces = [(out[4 + 2 * i], out[5 + 2 * i]) for i in range(npieces)]
+            assert pieces[0][0] == 0 and sum(l for _, l in pieces) == m
+            for (o, l), (o2, _) in zip(pieces, pieces[1:]):
+                assert o + l == o2
+            assert min(l for _, l in pieces) >= q + s - 1
 
 
 def test_emu_prefilter_encoded():
