@@ -84,6 +84,7 @@ typedef struct sassy_gpu_Stats {
   uint64_t transfer_bytes;  /* bytes that crossed PCIe for the text */
   uint32_t filter_kind;     /* 0 none, 1 piece automaton (Shift-And), 2 q-gram bitmap, 3 SWAR suffix scan */
   uint32_t swar_lanes;      /* patterns per 32-bit word in the scan that produced the candidates (0/1 = one) */
+  uint64_t confirmed;       /* prefilter hits that were re-scanned (q-gram: after the exact confirmation) */
 } sassy_gpu_Stats;
 
 #ifdef __cplusplus
@@ -213,6 +214,15 @@ typedef struct sassy_gpu_Slab {
   uint64_t own_lo;     /* the rank owns the global text range [own_lo, own_hi) */
   uint64_t own_hi;
 } sassy_gpu_Slab;
+/* The whole sharded search in one call (all ranks in lock step): search_all of this rank's
+ * window, fused gather, merge.  *complete = 0: some rank's records did not fit the exchange; the
+ * result then holds this rank's unmerged search_all matches (window coordinates) and the caller
+ * gathers them itself and calls sassy_gpu_merge_slabs. */
+sassy_gpu_Result *sassy_gpu_search_text_sharded(sassy_SearcherType *searcher, sassy_gpu_Gather *gather,
+                                                const uint8_t *pattern, size_t pattern_len,
+                                                const sassy_gpu_Text *window, size_t k, int all,
+                                                const sassy_gpu_Slab *slabs, size_t n_slabs, uint64_t n_global,
+                                                int *complete);
 sassy_gpu_Result *sassy_gpu_merge_slabs(const sassy_gpu_Match *records, size_t n_records, const char *ops,
                                         const sassy_gpu_Slab *slabs, size_t n_slabs, uint64_t n_global, int all);
 

@@ -74,6 +74,7 @@ class GpuStats(ctypes.Structure):
         ("transfer_bytes", ctypes.c_uint64),
         ("filter_kind", ctypes.c_uint32),
         ("swar_lanes", ctypes.c_uint32),
+        ("confirmed", ctypes.c_uint64),
     ]
 
 
@@ -128,6 +129,8 @@ SIGNATURES = {
                                                   ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "sassy_gpu_search_encoded_gathered": (c_void_p, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, ctypes.c_int,
                                                      ctypes.POINTER(ctypes.c_int)]),
+    "sassy_gpu_search_text_sharded": (c_void_p, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, ctypes.c_int,
+                                                c_void_p, c_size_t, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int)]),
     "sassy_gpu_merge_slabs": (c_void_p, [c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, ctypes.c_uint64,
                                         ctypes.c_int]),
     "sassy_gpu_result_len": (c_size_t, [c_void_p]),

@@ -126,6 +126,41 @@ void qgram_rows(const ScanArgs& a, const uint32_t* bitmap, uint32_t qs) {
   }
 }
 
+// The body of qgram_seq_kernel: every 64-byte block of the text is filtered on its own, the window
+// rebuilt from the 16 bytes before it (zeros before the text, as the kernel's first carry).
+template <int Q, int S>
+void qgram_seq_blocks(const ScanArgs& a, const uint32_t* bitmap, uint32_t qs) {
+  const uint64_t total_tiles = (a.n + 2047) / 2048;
+  for (uint64_t b = 0; b < total_tiles * 32; b++) {
+    const uint64_t stage_idx = b * 64;
+    uint32_t hist[4] = {0, 0, 0, 0};
+    if (b > 0) memcpy(hist, a.text + stage_idx - 16, 16);
+    QLane s;
+    qlane_init(s, hist);
+    uint32_t mask = 0;
+    for (int c = 0; c < 4; c++) {
+      uint32_t x[4];
+      memcpy(x, a.text + stage_idx + 16u * c, 16);
+      if (qgram16<Q, S>(s, x, bitmap) & 1u) mask |= 1u << c;
+    }
+    if (mask) {
+      emit_stage_hits(a, HitQueue{nullptr, nullptr}, qs, stage_idx, mask, true);
+      if (a.fused) emit_stage_hits(a, HitQueue{nullptr, nullptr}, qs + 1, stage_idx, mask, true);
+    }
+  }
+}
+
+bool qgram_seq_dispatch(int Q, int S, const ScanArgs& a, const uint32_t* bitmap, uint32_t qs) {
+#define EMU_Q(QQ, SS)                        \
+  if (Q == QQ && S == SS) {                  \
+    qgram_seq_blocks<QQ, SS>(a, bitmap, qs); \
+    return true;                             \
+  }
+  EMU_Q(8, 4) EMU_Q(8, 8) EMU_Q(8, 16) EMU_Q(7, 4) EMU_Q(6, 4)
+#undef EMU_Q
+  return false;
+}
+
 bool qgram_dispatch(int Q, int S, const ScanArgs& a, const uint32_t* bitmap, uint32_t qs) {
 #define EMU_Q(QQ, SS)            \
   if (Q == QQ && S == SS) {      \
@@ -334,15 +369,16 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
   std::vector<const uint8_t*> qptr(nq);
   for (uint32_t q = 0; q < nq; q++) qptr[q] = queries + (size_t)q * m;
   FilterPlan fp;
-  // use_filter: 0 off, < 0 automatic, 1 force the piece automaton, 2 as Engine::search with the
-  // filter forced (q-gram bitmap when it can be planned, else the piece automaton)
+  // use_filter: 0 off, < 0 automatic, 1 force the piece automaton, 2 / 3 as Engine::search with the
+  // filter forced (q-gram bitmap when it can be planned -- 2: contiguous tiles, 3: row tiles --
+  // else the piece automaton)
   if (use_filter != 0) fp = plan_filter(profile, qptr.data(), nq, m, k, use_filter > 0 ? 1e30 : 0.85);
   res->hits = 0;
   QgramPlan qp;
   {
     uint32_t nf = 0;
     while (nf < nq && !rev[nf]) nf++;
-    if (n > 0 && (use_filter == 2 || use_filter < 0) && !ov && profile == kDna && nf == 1 && nq <= 2)
+    if (n > 0 && (use_filter == 2 || use_filter == 3 || use_filter < 0) && !ov && profile == kDna && nf == 1 && nq <= 2)
       qp = plan_qgram(m, k, (int)nq);
   }
   if (qp.enabled) fp.enabled = false;
@@ -364,7 +400,10 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
     f.hit_keys = hits.data();
     f.hit_count = &nhits;
     f.hit_cap = hits.size();
-    if (!qgram_dispatch(qp.q, qp.s, f, bitmap.data(), 0)) abort();
+    // 3: the row-tiled kernel (LDG data path of the product), else the contiguous-tile kernel
+    if (!(use_filter == 3 ? qgram_dispatch(qp.q, qp.s, f, bitmap.data(), 0)
+                          : qgram_seq_dispatch(qp.q, qp.s, f, bitmap.data(), 0)))
+      abort();
     a.qconf = conf.data();
     a.qnp = (uint32_t)qp.npieces;
     a.qq = (uint32_t)qp.q;

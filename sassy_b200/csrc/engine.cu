@@ -67,8 +67,12 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
   if (pm) pair_max_words_ = atoi(pm);
   const char* qm = getenv("SASSY_B200_QGRAM");
   if (qm && !strcmp(qm, "0")) qgram_mode_ = 0;
+  const char* qsq = getenv("SASSY_B200_QGRAM_SEQ");
+  if (qsq && !strcmp(qsq, "0")) qgram_seq_ = false;
   const char* qq = getenv("SASSY_B200_QGRAM_MIN_Q");
   if (qq) qgram_min_q_ = std::max(6, std::min(8, atoi(qq)));
+  const char* rb = getenv("SASSY_B200_FILTER_ROW_BYTES");
+  if (rb) filter_row_bytes_ = atoi(rb);
   const char* fs = getenv("SASSY_B200_FUSE_STRANDS");
   if (fs && !strcmp(fs, "0")) fuse_strands_ = false;
   cudaDriverEntryPointQueryResult qres;
@@ -83,7 +87,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   for (DevBuf* b : {&keys_, &cost_, &keys2_, &cost2_, &flags_, &sel_, &cubtmp_, &scratch_, &ops_, &out_, &hits_,
-                    &d_stage_, &best_, &sel_cost_, &d_texts_})
+                    &d_stage_, &best_, &sel_cost_, &d_texts_, &hits2_})
     b->release();
   if (staged_.d) cudaFree(staged_.d);
   if (h_stage_) cudaFreeHost(h_stage_);
@@ -257,7 +261,7 @@ void Engine::upload_params(const std::vector<Query>& queries, int m, int W, cons
                               : (!fp.enabled ? 0 : (pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT));
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   off_counts_ = 0;
-  off_eq_ = align(4 * sizeof(unsigned long long));
+  off_eq_ = align(8 * sizeof(unsigned long long));
   off_pat_ = off_eq_ + align(eq_bytes);
   off_rev_ = off_pat_ + align(pat_bytes);
   off_feq_ = off_rev_ + align(nq);
@@ -270,7 +274,7 @@ void Engine::upload_params(const std::vector<Query>& queries, int m, int W, cons
     stage_cap_ = total * 2;
   }
   d_stage_.ensure(stage_cap_);
-  memset(h_stage_ + off_counts_, 0, 4 * sizeof(unsigned long long));
+  memset(h_stage_ + off_counts_, 0, 8 * sizeof(unsigned long long));
   uint32_t* h_eq = reinterpret_cast<uint32_t*>(h_stage_ + off_eq_);
   uint32_t* h_feq = reinterpret_cast<uint32_t*>(h_stage_ + off_feq_);
   for (size_t q = 0; q < nq; q++) {
@@ -610,7 +614,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     a.cand_cost = cost_.as<uint32_t>();
     a.cand_cap = cand_cap_;
   };
-  unsigned long long h_counts[4] = {0, 0, 0, 0};
+  unsigned long long h_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [4] = q-gram hits that passed the confirmation
   auto read_counts = [&]() {
     SB_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, stream_));
     SB_CUDA(cudaStreamSynchronize(stream_));
@@ -731,9 +735,15 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     const int focc = qgram ? qgram_blocks_per_sm(qp.q, qp.s, variant_) : filter_blocks_per_sm(WT, variant_, pair);
     ScanGeom gf = choose_geom(n, m, k, qgram ? 1 : nq, focc * sm_count_);
     gf.nwarm = 1;  // a piece plus its delay line is at most 32 characters; a q-gram window 16
+    if (filter_row_bytes_ >= 128 && n > 0) {  // SASSY_B200_FILTER_ROW_BYTES: tiling experiments
+      gf.ltot = std::min<uint32_t>(kMaxRowBytes, (uint32_t)filter_row_bytes_ / kRowAlign * kRowAlign);
+      gf.rows = (uint32_t)((n + gf.ltot - 1) / gf.ltot);
+      gf.nstage = gf.ltot / kStageBytes;
+    }
+    const bool qseq = qgram && variant_ == kVariantTma && qgram_seq_ && n < (1ull << 36);
     CUtensorMap ftmap;
     memset(&ftmap, 0, sizeof ftmap);
-    if (variant_ == kVariantTma) make_tensor_map(&ftmap, text, gf);
+    if (variant_ == kVariantTma && !qseq) make_tensor_map(&ftmap, text, gf);
     reset_candidates();
     ScanArgs f = a;
     f.g = gf;
@@ -750,7 +760,18 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       f.qs_base = 0;
       f.feq = d_feq;
       f.fused = nq == 2 ? 1 : 0;  // every hit is re-scanned for the reversed partner (slot 1) too
-      SB_CUDA(launch_qgram(qp.q, qp.s, variant_, &ftmap, f, stream_));
+      if (qseq) {  // contiguous 2 KB tiles: the text as [ceil(n / 64)][64] bytes
+        ScanGeom gs;
+        gs.ltot = kStageBytes;
+        gs.rows = (uint32_t)((n + 2047) / 2048 * 32);
+        gs.nstage = 1, gs.nwarm = 0;
+        make_tensor_map(&ftmap, text, gs);
+        SB_CUDA(launch_qgram_seq(qp.q, qp.s, &ftmap, f, sm_count_, stream_));
+        gf.ltot = 2048;
+        gf.rows = gs.rows / 32;
+      } else {
+        SB_CUDA(launch_qgram(qp.q, qp.s, variant_, &ftmap, f, stream_));
+      }
       stats_.scan_launches++;
     } else if (nfwd) {
       f.nq = nfwd;
@@ -777,10 +798,19 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     v.hit_cap = hit_cap_;
     if (fused)  // a reversed query's hit marks the START of its piece in scan direction
       for (int p = 0; p < fp.npieces; p++) v.rev_lead = std::max<uint32_t>(v.rev_lead, (uint32_t)fp.piece[p].len);
-    if (qgram) {  // hits are confirmed exactly (a whole share) before the re-scan
-      v.qconf = reinterpret_cast<const uint32_t*>(dst + off_qconf_);
-      v.qnp = (uint32_t)qp.npieces;
-      v.qq = (uint32_t)qp.q;
+    if (qgram) {
+      // q-gram hits are confirmed exactly (a whole share of the pattern behind them) by one thread
+      // each; the survivors -- a small fraction -- are compacted into a second list, so that the
+      // re-scan runs on dense warps instead of one live lane per warp
+      hits2_.ensure(hit_cap_ * sizeof(uint64_t));
+      ScanArgs cf = v;
+      cf.qconf = reinterpret_cast<const uint32_t*>(dst + off_qconf_);
+      cf.qnp = (uint32_t)qp.npieces;
+      cf.qq = (uint32_t)qp.q;
+      SB_CUDA(launch_confirm(cf, hits2_.as<uint64_t>(), d_counts + 4, stream_));
+      stats_.aux_launches++;
+      v.hit_keys = hits2_.as<uint64_t>();
+      v.hit_count = d_counts + 4;
     }
     SB_CUDA(launch_verify(W, v, d_rev, stream_));
     stats_.aux_launches++;
@@ -791,6 +821,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     stats_.verify_ms = elapsed(ev_[2], ev_[4]);
     unsigned long long nhits = h_counts[2];
     stats_.hits = nhits;
+    stats_.confirmed = qgram ? h_counts[4] : nhits;
     stats_.filter_words = qgram ? 1u : (uint32_t)WT;
     stats_.filter_len = qgram ? (uint32_t)qp.q : (uint32_t)fp.L;
     stats_.filter_kind = qgram ? 2u : 1u;

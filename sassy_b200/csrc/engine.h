@@ -71,6 +71,7 @@ struct SearchStats {
   uint64_t transfer_bytes = 0;   // bytes that crossed PCIe for the text
   uint32_t filter_kind = 0;      // 0 none, 1 piece automaton (Shift-And), 2 q-gram bitmap, 3 SWAR suffix scan
   uint32_t swar_lanes = 0;       // patterns per 32-bit word of the scan that produced the candidates (0/1 = one)
+  uint64_t confirmed = 0;        // prefilter hits that were re-scanned (q-gram: after the exact confirmation)
 };
 
 struct MatchSet {
@@ -175,7 +176,9 @@ class Engine {
   int pair_max_words_ = 4;  // Dna: two characters per automaton step up to this many words
   int qgram_mode_ = 1;      // 0: never use the q-gram bitmap prefilter (SASSY_B200_QGRAM=0), 1: when planned
   int qgram_min_q_ = 6;     // SASSY_B200_QGRAM_MIN_Q
+  bool qgram_seq_ = true;   // contiguous-tile q-gram kernel (SASSY_B200_QGRAM_SEQ=0: row-tiled kernel)
   size_t off_qconf_ = 0;
+  int filter_row_bytes_ = 0;  // SASSY_B200_FILTER_ROW_BYTES (experiments): bytes per thread row of the prefilter
   int transport_mode_ = 1;
   float transfer_ms_ = 0;
   bool transfer_pending_ = false;
@@ -194,7 +197,7 @@ class Engine {
 
   DevBuf keys_, cost_, keys2_, cost2_, flags_, sel_, cubtmp_;
   DevBuf scratch_, ops_, out_;
-  DevBuf hits_, d_stage_, sel_small_, best_, sel_cost_, d_texts_;
+  DevBuf hits_, hits2_, d_stage_, sel_small_, best_, sel_cost_, d_texts_;
   uint8_t* h_small_ = nullptr;  // pinned: results of the small-list fast path, written by the GPU
   size_t h_small_cap_ = 0;
   uint8_t* h_stage_ = nullptr;  // pinned staging for the per-search parameter block

@@ -34,6 +34,13 @@ cudaError_t launch_filter(int WF, bool rev, int variant, bool pair, const CUtens
 // a.fused = 1 reports every hit for the reversed partner slot too.  (Q, S) as planned by plan_qgram.
 int qgram_blocks_per_sm(int Q, int S, int variant);
 cudaError_t launch_qgram(int Q, int S, int variant, const CUtensorMap* tmap, const ScanArgs& a, cudaStream_t stream);
+// The same filter over contiguous 2 KB tiles (tmap = the text as [ceil(n / 64)][64] bytes, box
+// [32][64]); TMA data path only.
+cudaError_t launch_qgram_seq(int Q, int S, const CUtensorMap* tmap, const ScanArgs& a, int sm_count,
+                             cudaStream_t stream);
+// Exact confirmation of q-gram hits (qgram_confirm): hits that have a whole share of their query
+// behind them are appended to `out` (same capacity as a.hit_keys), *out_count counts them.
+cudaError_t launch_confirm(const ScanArgs& a, uint64_t* out, unsigned long long* out_count, cudaStream_t stream);
 // nhits is read from a.hit_count on the device (clipped to a.hit_cap): no host round trip.
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream);
 

@@ -554,6 +554,19 @@ SB_HD uint32_t qgram16(QLane& s, const uint32_t (&x)[4], const uint32_t* __restr
   return acc;
 }
 
+// Window state of a thread that starts in the middle of the text: the 16 characters before its
+// first character (hist = 16 text bytes, little endian words in text order).
+SB_HD void qlane_init(QLane& s, const uint32_t (&hist)[4]) {
+  uint32_t w = 0, hi = 0;
+#pragma unroll
+  for (int ww = 0; ww < 4; ww++) {
+    hi = pack4_classes(hist[ww]);
+    w = funnel_r(w, hi, 8);
+  }
+  s.w = w;
+  s.prev = hi;
+}
+
 // Exact confirmation of a q-gram hit in the 16-byte chunk at forward index `base` (a multiple of
 // 16) for query slot `qs`: the sampled Q-gram ends at e in [base + S, base + 16] and starts at most
 // S - 1 characters into its share, so the share starts at a in [base + 1 - Q, base + 16 - Q]: 16

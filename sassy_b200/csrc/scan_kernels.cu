@@ -76,6 +76,10 @@ constexpr int kWarpStageBytes = 32 * kStageBytes;                  // one TMA bo
 constexpr int kWarpRingBytes = kScanStages * kWarpStageBytes;      // per warp
 constexpr int kRingBytes = kWarpsPerBlock * kWarpRingBytes;        // per block
 constexpr int kChunks = kStageBytes / 16;
+#ifndef SB_SEQ_STAGES
+#define SB_SEQ_STAGES 3
+#endif
+constexpr int kSeqStages = SB_SEQ_STAGES;  // ring depth of the contiguous-tile kernels (2 KB tiles)
 constexpr int kUnroll = SB_UNROLL;  // 16-byte chunks unrolled per loop trip (narrow patterns)
 
 template <int W>
@@ -357,6 +361,117 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
                                    if (*hq.n >= kHitQueueCap / 2) flush_hits(a, hq, lane);  // warp-uniform
                                  }
                                });
+  flush_hits(a, hq, lane);
+}
+
+// The same filter over CONTIGUOUS memory.  The q-gram window only needs the 16 previous
+// characters, so a thread does not have to own a long row: a warp streams a contiguous segment of
+// the text in 2 KB tiles (one TMA box of 32 "rows" of 64 consecutive bytes each, 64-byte swizzle,
+// the same conflict-free shared-memory reads as the row pipeline), lane t takes bytes
+// [64 t, 64 t + 64) of the tile and rebuilds its window from the last 16 bytes of lane t - 1 (one
+// shuffle of a 16-byte chunk; lane 0 gets them from lane 31 of the previous tile).  DRAM sees long
+// sequential bursts instead of 64-byte pieces of 32 rows that lie kilobytes apart, and there is no
+// per-row warm-up stage.  tmap: the text as [ceil(n / 64)][64] bytes.
+template <int Q, int S>
+__global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
+    qgram_seq_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a,
+                     const uint64_t total_tiles, const uint32_t tiles_per_warp) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kWarpsPerBlock * kSeqStages];
+  __shared__ uint64_t hit_q[kWarpsPerBlock][kHitQueueCap];
+  __shared__ uint32_t hit_n[kWarpsPerBlock];
+  constexpr uint32_t kTabWords = (1u << (2 * Q)) / 32;
+  __shared__ __align__(16) uint32_t bitmap[kTabWords];
+  static_assert(kStageBytes == 64, "tiles are 32 x 64 bytes");
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t qs = a.qs_base;
+  HitQueue hq;
+  hq.q = hit_q[warp];
+  hq.n = &hit_n[warp];
+  if (lane == 0) hit_n[warp] = 0;
+  for (uint32_t i = tid; i < kTabWords; i += kScanThreads) bitmap[i] = a.feq[i];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* ring = smem_raw + (((base + 1023u) & ~1023u) - base) + warp * (kSeqStages * kWarpStageBytes);
+  uint64_t* wbar = &full_bar[warp * kSeqStages];
+  const uint32_t wbar_addr = smem_u32(wbar);
+  if (lane == 0) {
+    for (int st = 0; st < kSeqStages; st++) mbar_init(&wbar[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const uint64_t tile0 = gwarp * tiles_per_warp;
+  uint64_t tile1 = tile0 + tiles_per_warp;
+  if (tile1 > total_tiles) tile1 = total_tiles;
+  const uint32_t ntiles = tile0 < tile1 ? (uint32_t)(tile1 - tile0) : 0u;
+  auto issue = [&](uint32_t it) {  // lane 0 only
+    const uint32_t slot = it % kSeqStages;
+    mbar_expect_tx(&wbar[slot], kWarpStageBytes);
+    tma_load_2d(ring + slot * kWarpStageBytes, &tmap, 0, (int32_t)((tile0 + it) * 32), &wbar[slot]);
+  };
+  if (lane == 0)
+    for (uint32_t it = 0; it < (uint32_t)kSeqStages && it < ntiles; it++) issue(it);
+
+  // the 16 bytes before this warp's segment (for lane 0 of the first tile)
+  uint4 carry = make_uint4(0, 0, 0, 0);
+  if (lane == 0 && tile0 > 0 && ntiles) carry = __ldg(reinterpret_cast<const uint4*>(a.text + tile0 * 2048 - 16));
+  const uint32_t sw = (lane >> 1) & 3u;
+  const uint32_t lane_buf = smem_u32(ring) + lane * kStageBytes;
+  for (uint32_t it = 0; it < ntiles; it++) {
+    const uint32_t st = it % kSeqStages;
+    mbar_wait(wbar_addr + st * 8u, (it / kSeqStages) & 1u);
+    const uint32_t buf = lane_buf + st * kWarpStageBytes;
+    uint4 v[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; c++)
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(v[c].x), "=r"(v[c].y), "=r"(v[c].z), "=r"(v[c].w)
+                   : "r"(buf + (((uint32_t)c ^ sw) << 4)));
+    __syncwarp();  // every lane has read this warp's ring[st]
+    if (lane == 0 && it + kSeqStages < ntiles) issue(it + kSeqStages);
+    // history: the last chunk of the lane to the left (of the previous tile for lane 0)
+    uint4 h;
+    h.x = __shfl_up_sync(0xFFFFFFFFu, v[kChunks - 1].x, 1);
+    h.y = __shfl_up_sync(0xFFFFFFFFu, v[kChunks - 1].y, 1);
+    h.z = __shfl_up_sync(0xFFFFFFFFu, v[kChunks - 1].z, 1);
+    h.w = __shfl_up_sync(0xFFFFFFFFu, v[kChunks - 1].w, 1);
+    if (lane == 0) h = carry;
+    carry.x = __shfl_sync(0xFFFFFFFFu, v[kChunks - 1].x, 31);
+    carry.y = __shfl_sync(0xFFFFFFFFu, v[kChunks - 1].y, 31);
+    carry.z = __shfl_sync(0xFFFFFFFFu, v[kChunks - 1].z, 31);
+    carry.w = __shfl_sync(0xFFFFFFFFu, v[kChunks - 1].w, 31);
+    QLane s;
+    {
+      const uint32_t hist[4] = {h.x, h.y, h.z, h.w};
+      qlane_init(s, hist);
+    }
+    uint32_t acc[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; c++) {
+      const uint32_t x[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+      acc[c] = qgram16<Q, S>(s, x, bitmap);
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (int c = 0; c < kChunks; c++) any |= acc[c];
+    any &= 1u;
+    if (__any_sync(0xFFFFFFFFu, any != 0)) {
+      if (any) {
+        const uint64_t stage_idx = (tile0 + it) * 2048ull + (uint64_t)lane * kStageBytes;
+#pragma unroll
+        for (int c = 0; c < kChunks; c++) {
+          const uint64_t base_idx = stage_idx + (uint64_t)(kHitChars * c);
+          if (!(acc[c] & 1u) || base_idx >= a.n) continue;
+          push_hit(a, hq, qs, base_idx);
+          if (a.fused) push_hit(a, hq, qs + 1, base_idx);
+        }
+      }
+      __syncwarp();
+      if (*hq.n >= kHitQueueCap / 2) flush_hits(a, hq, lane);  // warp-uniform
+    }
+  }
   flush_hits(a, hq, lane);
 }
 
@@ -785,6 +900,72 @@ FilterConfig qgram_config(int Q, int S, int variant) {
 
 int qgram_blocks_per_sm(int Q, int S, int variant) { return qgram_config(Q, S, variant).bps; }
 
+namespace {
+
+template <int Q, int S>
+cudaError_t launch_qgram_seq_one(const CUtensorMap* tmap, const ScanArgs& a, int sm_count, cudaStream_t stream) {
+  auto kern = qgram_seq_kernel<Q, S>;
+  static size_t tracker[64] = {};
+  static const int target = [] {  // SASSY_B200_QSEQ_BPS: cap on resident blocks per SM (0 = whatever fits)
+    const char* e = getenv("SASSY_B200_QSEQ_BPS");
+    const int x = e ? atoi(e) : 0;
+    return x >= 1 && x <= 16 ? x : 0;
+  }();
+  static const int waves = [] {
+    const char* e = getenv("SASSY_B200_QSEQ_WAVES");
+    const int x = e ? atoi(e) : 0;
+    return x >= 1 && x <= 64 ? x : 4;
+  }();
+  // occupancy queries cost tens of microseconds: once per instantiation (all devices are the same part)
+  static std::mutex mu;
+  static size_t cfg_smem = 0;
+  static int cfg_nb = 0;
+  size_t smem;
+  int nb;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!cfg_nb) {
+      size_t sm = 1024 + (size_t)kWarpsPerBlock * kSeqStages * kWarpStageBytes;
+      int occ = 1;
+      for (;;) {
+        cudaError_t e = ensure_smem(kern, sm, tracker);
+        if (e != cudaSuccess) return e;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kScanThreads, sm) != cudaSuccess || occ < 1) occ = 1;
+        if (!target || occ <= target || sm + 2048 > 200 * 1024) break;
+        sm += 2048;  // pad until at most `target` blocks are resident
+      }
+      cfg_smem = sm, cfg_nb = occ;
+    }
+    smem = cfg_smem, nb = cfg_nb;
+  }
+  {
+    cudaError_t e = ensure_smem(kern, smem, tracker);  // another device of the box
+    if (e != cudaSuccess) return e;
+  }
+  const uint64_t total_tiles = (a.n + 2047) / 2048;
+  if (total_tiles == 0) return cudaSuccess;
+  // `waves` segments per resident warp: long sequential segments, a short tail
+  const uint64_t warps = (uint64_t)sm_count * nb * kWarpsPerBlock * waves;
+  uint64_t tpw = (total_tiles + warps - 1) / warps;
+  if (tpw < 8) tpw = 8;
+  const uint64_t blocks = (total_tiles + tpw * kWarpsPerBlock - 1) / (tpw * kWarpsPerBlock);
+  if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+  kern<<<(unsigned)blocks, kScanThreads, smem, stream>>>(*tmap, a, total_tiles, (uint32_t)tpw);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_qgram_seq(int Q, int S, const CUtensorMap* tmap, const ScanArgs& a, int sm_count,
+                             cudaStream_t stream) {
+#define SB_QCALL(QQ, SS) \
+  if (Q == QQ && S == SS) return launch_qgram_seq_one<QQ, SS>(tmap, a, sm_count, stream);
+  SB_QCALL(8, 4) SB_QCALL(8, 8) SB_QCALL(8, 16)
+  SB_QCALL(7, 4) SB_QCALL(6, 4)
+#undef SB_QCALL
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_qgram(int Q, int S, int variant, const CUtensorMap* tmap, const ScanArgs& a, cudaStream_t stream) {
   return qgram_dispatch(Q, S, variant, tmap, a, qgram_config(Q, S, variant).smem, stream, nullptr);
 }
@@ -893,6 +1074,43 @@ __global__ void __launch_bounds__(32 * kWideWarps)
 }
 
 }  // namespace
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+    confirm_kernel(const __grid_constant__ ScanArgs a, uint64_t* __restrict__ out, unsigned long long* out_count) {
+  unsigned long long nhits = *a.hit_count;
+  if (nhits > a.hit_cap) nhits = a.hit_cap;
+  const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long rounds = (nhits + nthreads - 1) / nthreads;  // whole warps stay in the loop
+  const uint32_t lane = threadIdx.x & 31;
+  for (unsigned long long r = 0; r < rounds; r++) {
+    const unsigned long long i = r * nthreads + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t key = 0;
+    bool ok = false;
+    if (i < nhits) {
+      key = a.hit_keys[i];
+      ok = qgram_confirm(a, key_qs(key), key_pos(key) * kHitChars);
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+    if (m) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(out_count, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (ok) {
+        const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+        if (at < a.hit_cap) out[at] = key;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_confirm(const ScanArgs& a, uint64_t* out, unsigned long long* out_count, cudaStream_t stream) {
+  confirm_kernel<<<148 * 8, 256, 0, stream>>>(a, out, out_count);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream) {
   const unsigned threads = 128;

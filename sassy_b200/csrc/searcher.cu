@@ -360,6 +360,19 @@ std::vector<Match> Searcher::search_gathered(PeerGather& pg, const uint8_t* patt
   return out;
 }
 
+std::vector<Match> Searcher::search_sharded_gathered(PeerGather& pg, const uint8_t* pattern, size_t m,
+                                                     const DeviceText& window, size_t k, bool all_minima,
+                                                     const SlabInfo* slabs, size_t n_slabs, uint64_t n_global,
+                                                     bool* complete) {
+  std::vector<Match> all = search_gathered(pg, pattern, m, window, k, /*all_minima=*/true, complete);
+  if (!*complete) return all;
+  const std::vector<size_t> keep = merge_slab_matches(all, slabs, n_slabs, n_global, all_minima);
+  std::vector<Match> out;
+  out.reserve(keep.size());
+  for (size_t i : keep) out.push_back(std::move(all[i]));
+  return out;
+}
+
 std::vector<Match> Searcher::search_encoded_gathered(PeerGather& pg, const EncodedPatterns& enc,
                                                      const DeviceText& text, size_t k, bool all_minima,
                                                      bool* complete) {
@@ -643,6 +656,7 @@ int sassy_gpu_stats(const sassy_SearcherType* searcher, sassy_gpu_Stats* out) {
   out->transfer_bytes = st.transfer_bytes;
   out->filter_kind = st.filter_kind;
   out->swar_lanes = st.swar_lanes;
+  out->confirmed = st.confirmed;
   return 0;
 }
 
@@ -845,6 +859,23 @@ sassy_gpu_Result* sassy_gpu_search_encoded_gathered(sassy_SearcherType* searcher
     if (!searcher || !gather || !patterns || !text || !complete) throw std::invalid_argument("null pointer");
     bool ok = false;
     auto v = searcher->s.search_encoded_gathered(gather->g, patterns->e, *text->t, k, all != 0, &ok);
+    *complete = ok ? 1 : 0;
+    return to_result(v);
+  });
+}
+
+sassy_gpu_Result* sassy_gpu_search_text_sharded(sassy_SearcherType* searcher, sassy_gpu_Gather* gather,
+                                                const uint8_t* pattern, size_t pattern_len,
+                                                const sassy_gpu_Text* window, size_t k, int all,
+                                                const sassy_gpu_Slab* slabs, size_t n_slabs, uint64_t n_global,
+                                                int* complete) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !gather || !pattern || !window || !slabs || !complete) throw std::invalid_argument("null pointer");
+    std::vector<sb::SlabInfo> info(n_slabs);
+    for (size_t i = 0; i < n_slabs; i++) info[i] = sb::SlabInfo{slabs[i].window_off, slabs[i].own_lo, slabs[i].own_hi};
+    bool ok = false;
+    auto v = searcher->s.search_sharded_gathered(gather->g, pattern, pattern_len, *window->t, k, all != 0, info.data(),
+                                                 n_slabs, n_global, &ok);
     *complete = ok ? 1 : 0;
     return to_result(v);
   });

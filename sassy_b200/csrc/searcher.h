@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "shard_merge.h"
 
 namespace sb {
 
@@ -107,6 +108,15 @@ class Searcher {
                                      size_t k, bool all_minima, bool* complete);
   std::vector<Match> search_encoded_gathered(PeerGather& pg, const EncodedPatterns& enc, const DeviceText& text,
                                              size_t k, bool all_minima, bool* complete);
+  // ONE text cut into world slabs (csrc/shard_merge.h): `window` = this rank's slab plus (m + k)
+  // halos; every rank searches its window with search_all, the records travel through the fused
+  // gather and the ownership filter + local-minima rule run on the merged list.  *complete = false:
+  // this rank's unmerged search_all matches (window coordinates) are returned for the caller's own
+  // collective + sassy_gpu_merge_slabs.
+  std::vector<Match> search_sharded_gathered(PeerGather& pg, const uint8_t* pattern, size_t m,
+                                             const DeviceText& window, size_t k, bool all_minima,
+                                             const SlabInfo* slabs, size_t n_slabs, uint64_t n_global,
+                                             bool* complete);
 
   void validate_pattern(const uint8_t* p, size_t m) const;
 

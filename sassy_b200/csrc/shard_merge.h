@@ -33,8 +33,9 @@ struct SlabInfo {
 // Returns the indices of the kept records in output order (forward matches by ascending end,
 // then reverse-complement matches by ascending end on the reversed text, per pattern) and
 // rewrites their coordinates to the global text.
-inline std::vector<size_t> merge_slab_matches(std::vector<sassy_gpu_Match>& recs, const SlabInfo* slabs,
-                                              size_t n_slabs, uint64_t n_global, bool all_minima) {
+template <class Rec>
+inline std::vector<size_t> merge_slab_matches(std::vector<Rec>& recs, const SlabInfo* slabs, size_t n_slabs,
+                                              uint64_t n_global, bool all_minima) {
   struct Item {
     uint64_t key;  // (pattern, strand) slot << kPosBits | end position in scan direction
     uint32_t cost;
@@ -43,7 +44,7 @@ inline std::vector<size_t> merge_slab_matches(std::vector<sassy_gpu_Match>& recs
   std::vector<Item> items;
   items.reserve(recs.size());
   for (size_t i = 0; i < recs.size(); i++) {
-    sassy_gpu_Match& r = recs[i];
+    Rec& r = recs[i];
     if (r.text_idx >= n_slabs) continue;
     const SlabInfo& s = slabs[r.text_idx];
     r.text_start += s.window_off;
@@ -51,7 +52,7 @@ inline std::vector<size_t> merge_slab_matches(std::vector<sassy_gpu_Match>& recs
     r.text_idx = 0;
     uint64_t pos;
     bool own;
-    if (r.strand == 0) {
+    if ((int)r.strand == 0) {
       // forward: end position e in (own_lo, own_hi]; e = 0 (empty prefix, m <= k) belongs to the first slab
       pos = r.text_end;
       own = (pos > s.own_lo && pos <= s.own_hi) || (pos == 0 && s.own_lo == 0);
@@ -62,7 +63,7 @@ inline std::vector<size_t> merge_slab_matches(std::vector<sassy_gpu_Match>& recs
       own = (r.text_start >= s.own_lo && r.text_start < s.own_hi) || (r.text_start == n_global && s.own_hi == n_global);
     }
     if (!own) continue;
-    const uint64_t slot = r.pattern_idx * 2 + r.strand;
+    const uint64_t slot = r.pattern_idx * 2 + (uint64_t)(int)r.strand;
     items.push_back(Item{cand_key((uint32_t)slot, pos), (uint32_t)r.cost, i});
   }
   std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.key < b.key; });

@@ -261,6 +261,27 @@ class PeerGather:
                                                        int(all_minima), ctypes.byref(ok))
         return self._finish(res, ok.value)
 
+    def search_sharded(self, pattern: bytes, window_text, k: int, layout, n_global: int, all_minima: bool = False):
+        """One text cut into slabs (slab_layout): this rank's window -> the matches of the unsharded
+        search (sassy_gpu_search_text_sharded); NCCL all-gather + merge_slabs when the records of
+        some rank do not fit the fused exchange."""
+        import ctypes
+        from .searcher import _as_buffer
+        paddr, plen, keep = _as_buffer(pattern)
+        slabs = np.zeros((len(layout), 3), dtype=np.uint64)
+        for r, (wlo, _whi, lo, hi) in enumerate(layout):
+            slabs[r] = (wlo, lo, hi)
+        ok = ctypes.c_int(0)
+        res = self._lib.sassy_gpu_search_text_sharded(self._searcher._h, self._h, paddr, plen, window_text._h, k,
+                                                      int(all_minima), slabs.ctypes.data, len(layout), n_global,
+                                                      ctypes.byref(ok))
+        ms = self._searcher._collect(res)
+        if ok.value:
+            return ms
+        self.fallbacks += 1
+        allm = gather_matches(tag_rank(ms, self.rank), self.max_ops, group=self._group)
+        return merge_slabs(allm, layout, n_global, all_minima)
+
     def search_encoded(self, enc, text, k: int, all_minima: bool = False):
         import ctypes
         ok = ctypes.c_int(0)
@@ -333,7 +354,8 @@ def search_text_sharded(searcher, pattern: bytes, window_text, k: int, n_global:
     m = len(pattern)
     layout = slab_layout(n_global, world, m, k)
     if peer_gather is not None:
-        ms = peer_gather.search(pattern, window_text, k, all_minima=True)
+        # search_all + fused gather + merge inside the library (one call, one host synchronisation)
+        return peer_gather.search_sharded(pattern, window_text, k, layout, n_global, all_minima)
     else:
         ms = searcher.search_all(pattern, window_text, k)
         if world > 1:

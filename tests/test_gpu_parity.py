@@ -323,15 +323,18 @@ def test_gpu_qgram_prefilter_fuzz():
                    [(x.text_start, x.text_end, x.cost, x.strand, x.cigar) for x in want], (p, t, k, rc, allm)
             st = s.stats()
             if n:
-                assert st["filter_kind"] == 2 and st["filter_fallback"] == 0, st
+                assert st["filter_kind"] == 2 and (st["filter_fallback"] == 0 or n < 20000), st
                 seen.add((st["filter_len"], m // (k + 1) >= 8 + 15, m // (k + 1) >= 8 + 7))
     assert len(seen) >= 5, seen  # Q in {6, 7, 8} and S in {4, 8, 16}
 
 
-def test_gpu_qgram_large_text():
+@pytest.mark.parametrize("seq", ["1", "0"], ids=["contiguous-tiles", "row-tiles"])
+def test_gpu_qgram_large_text(seq, monkeypatch):
     """64 MB: thousands of false q-gram hits (rejected by the exact confirmation) next to planted
-    copies on every kind of row boundary; equals the full scan."""
+    copies on every kind of row / tile boundary; equals the full scan.  Both q-gram kernels: the
+    contiguous-tile one (default) and the row-tiled one (SASSY_B200_QGRAM_SEQ=0)."""
     import sassy_b200
+    monkeypatch.setenv("SASSY_B200_QGRAM_SEQ", seq)  # read when the searcher is constructed
     rng = random.Random(72)
     n = 1 << 26
     base = bytes(rng.choice(b"ACGT") for _ in range(1 << 16))
@@ -339,7 +342,8 @@ def test_gpu_qgram_large_text():
         p = rand_seq(rng, m)
         t = bytearray(base * (n >> 16))
         rcp = oracle.reverse_complement("dna", p)
-        spots = [0, n - m, 13312 * 7 - 5, 9984 * 3 - m // 2, 16384 * 11 + 1, 64 * 1000 - 3, 5_000_011, 33_000_000]
+        spots = [0, n - m, 13312 * 7 - 5, 9984 * 3 - m // 2, 16384 * 11 + 1, 64 * 1000 - 3, 5_000_011, 33_000_000,
+                 2048 * 4001 - 9, 2048 * 9000 - m + 3, 64 * 77777 - 1]
         for i, pos in enumerate(spots):
             q = bytearray(p if i % 2 == 0 else rcp)
             for _ in range(i % (k + 1)):

@@ -121,7 +121,8 @@ def test_emu_qgram_prefilter_fuzz():
         rc = rng.random() < 0.7
         for allm in (False, True):
             want = oracle.search("dna", p, t, k, rc=rc, all_minima=allm)
-            b = EmuBackend(ltot=rng.choice([0, 64, 128, 192]), use_filter=2)
+            # 2: contiguous-tile kernel (product default), 3: row-tiled kernel
+            b = EmuBackend(ltot=rng.choice([0, 64, 128, 192]), use_filter=2 + (it + allm) % 2)
             got = b.search("dna", p, t, k, rc=rc, all_minima=allm)
             assert list(map(key, got)) == list(map(key, want)), (p, t, k, rc, allm, b.last_filter)
             if n and b.last_filter[0] == 1 and 6 <= b.last_filter[1] <= 8:  # else: no q-gram plan, piece automaton

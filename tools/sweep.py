@@ -32,11 +32,11 @@ def main():
     n = args.text_bytes
     lens = [int(x) for x in args.lens.split(",")]
     ks = [int(x) for x in args.ks.split(",")]
-    text = bench.synth_text_device(torch, n, 42, dev)
+    text = bench.synth_text(torch, n, 0, 42, dev)
     pats = {m: bench.make_patterns("dna", 1, m, seed=43 + m)[0] for m in lens}
-    for m in lens:  # plant for the largest k: copies with 0..8 edits
-        for pos, q in bench.plant_list([pats[m]], n, max(ks), 64, seed=44 + m):
-            text[pos:pos + len(q)] = torch.tensor(list(q), dtype=torch.uint8, device=dev)
+    # plant for the largest k: 64 copies per pattern with 0..8 edits (slots of 4 KB: m <= 1000)
+    bench.PLANT_SLOT = 4096
+    bench.apply_plants(torch, text, 0, bench.slab_plants(0, n, [(pats[m], max(ks), 64) for m in lens]))
     torch.cuda.synchronize()
     s = sassy_b200.Searcher("dna", rc=args.rc, device=0)
     dt = s.text_from_device(text.data_ptr(), n)
@@ -72,8 +72,11 @@ def main():
                 kern.append(s.stats()["scan_ms"])
             el = (time.perf_counter() - t0) / steps
             st = s.stats()
-            route = (f"prefilter ({st['filter_words']} words, pieces >= {st['filter_len']}) + re-scan of {st['hits']} hits"
-                     if st["filter_words"] and not st["filter_fallback"] else f"full scan ({st['words']} words)")
+            if st["filter_words"] and not st["filter_fallback"]:
+                route = (f"q-gram bitmap (q = {st['filter_len']}), {st['hits']} hits confirmed + re-scanned" if st["filter_kind"] == 2
+                         else f"piece automaton ({st['filter_words']} words, pieces >= {st['filter_len']}) + re-scan of {st['hits']} hits")
+            else:
+                route = f"full scan ({st['words']} words)"
             kms = sum(kern) / len(kern)
             print(f"| {m} | {k} | {n / el / 1e9:.0f} | {el * 1e3:.3f} | {len(ms)} | {len(ms) / el:.0f} | {route} | "
                   f"{kms:.3f} | {n / (kms * 1e-3) / 1e9 / peak * 100:.1f} % |", flush=True)
