@@ -735,8 +735,13 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     const int focc = qgram ? qgram_blocks_per_sm(qp.q, qp.s, variant_) : filter_blocks_per_sm(WT, variant_, pair);
     ScanGeom gf = choose_geom(n, m, k, qgram ? 1 : nq, focc * sm_count_);
     gf.nwarm = 1;  // a piece plus its delay line is at most 32 characters; a q-gram window 16
-    if (filter_row_bytes_ >= 128 && n > 0) {  // SASSY_B200_FILTER_ROW_BYTES: tiling experiments
-      gf.ltot = std::min<uint32_t>(kMaxRowBytes, (uint32_t)filter_row_bytes_ / kRowAlign * kRowAlign);
+    // Short rows keep the rows of a warp close together in memory (a warp's TMA box gathers 64 bytes
+    // of each of its 32 rows): 4 KB rows read 4-5 % faster than the 13-16 KB rows that fill whole
+    // waves, at 1.6 % warm-up overhead (profiles/r02_tile_experiments.txt).  SASSY_B200_FILTER_ROW_BYTES
+    // overrides (tiling experiments).
+    const int row_bytes = filter_row_bytes_ >= 128 ? filter_row_bytes_ : (gf.ltot > 4096 ? 4096 : 0);
+    if (row_bytes >= 128 && n > 0) {
+      gf.ltot = std::min<uint32_t>(kMaxRowBytes, (uint32_t)row_bytes / kRowAlign * kRowAlign);
       gf.rows = (uint32_t)((n + gf.ltot - 1) / gf.ltot);
       gf.nstage = gf.ltot / kStageBytes;
     }
