@@ -183,16 +183,17 @@ void filter_dispatch(int WF, const ScanArgs& a, const uint32_t* feq_q, uint32_t 
   }
 }
 
-void verify_dispatch(int W, const ScanArgs& a, const uint32_t* eq_q, uint32_t qs, bool rev, uint64_t word) {
+void verify_dispatch(int W, const ScanArgs& a, const uint32_t* eq_q, uint32_t qs, bool rev, uint64_t word,
+                     uint32_t span = 0) {
   switch (W) {
-    case 1: verify_hit<1>(a, eq_q, qs, rev, word); break;
-    case 2: verify_hit<2>(a, eq_q, qs, rev, word); break;
-    case 3: verify_hit<3>(a, eq_q, qs, rev, word); break;
-    case 4: verify_hit<4>(a, eq_q, qs, rev, word); break;
-    case 6: verify_hit<6>(a, eq_q, qs, rev, word); break;
-    case 8: verify_hit<8>(a, eq_q, qs, rev, word); break;
-    case 16: verify_hit<16>(a, eq_q, qs, rev, word); break;
-    case 32: verify_hit<32>(a, eq_q, qs, rev, word); break;
+    case 1: verify_hit<1>(a, eq_q, qs, rev, word, span); break;
+    case 2: verify_hit<2>(a, eq_q, qs, rev, word, span); break;
+    case 3: verify_hit<3>(a, eq_q, qs, rev, word, span); break;
+    case 4: verify_hit<4>(a, eq_q, qs, rev, word, span); break;
+    case 6: verify_hit<6>(a, eq_q, qs, rev, word, span); break;
+    case 8: verify_hit<8>(a, eq_q, qs, rev, word, span); break;
+    case 16: verify_hit<16>(a, eq_q, qs, rev, word, span); break;
+    case 32: verify_hit<32>(a, eq_q, qs, rev, word, span); break;
     default: abort();
   }
 }
@@ -213,6 +214,26 @@ void scan_dispatch(int W, const ScanArgs& a, const uint32_t* eq_q, uint32_t qs) 
 }
 
 }  // namespace
+
+// refine_kernel + verify on the refined list (Engine::search, Dna): every hit chunk becomes zero or
+// more nominal end positions, each re-scanned over 2k + 1 end positions.
+void refine_and_verify(int W, ScanArgs& a, const std::vector<uint32_t>& eq, const ProfileParams& pp, const uint8_t* rev,
+                       const std::vector<uint64_t>& hits, unsigned long long nhits) {
+  std::vector<uint64_t> exact;
+  std::vector<uint32_t> spans;
+  for (unsigned long long h = 0; h < nhits; h++) {
+    const uint32_t qs = key_qs(hits[h]);
+    int64_t lo, hi;
+    if (refine_hit(a, qs, rev[qs] != 0, key_pos(hits[h]) * kHitChars, lo, hi))
+      exact.push_back(cand_key(qs, (uint64_t)lo)), spans.push_back((uint32_t)(hi - lo));
+  }
+  a.hit_exact = 1;
+  for (size_t i = 0; i < exact.size(); i++) {
+    const uint32_t qs = key_qs(exact[i]);
+    verify_dispatch(W, a, &eq[(size_t)qs * pp.nrows * W], qs, rev[qs] != 0, key_pos(exact[i]), spans[i]);
+  }
+  a.hit_exact = 0;
+}
 
 struct EmuResult {
   std::vector<GpuMatch> m;
@@ -386,10 +407,10 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
   res->filter_len = fp.enabled ? fp.L : (qp.enabled ? qp.q : 0);
   if (qp.enabled) {
     std::vector<uint32_t> bitmap(qp.table_words(), 0);
-    std::vector<uint32_t> conf((size_t)nq * qp.npieces * 2);
+    std::vector<uint32_t> conf((size_t)nq * qp.npieces * kConfWords);
     for (uint32_t q = 0; q < nq; q++) {
       add_qgram_entries(qp, qptr[q], rev[q] != 0, bitmap.data());
-      build_qgram_confirm(qp, qptr[q], rev[q] != 0, &conf[(size_t)q * qp.npieces * 2]);
+      build_qgram_confirm(qp, qptr[q], rev[q] != 0, &conf[(size_t)q * qp.npieces * kConfWords]);
     }
     std::vector<uint64_t> hits((size_t)nq * (n / kHitChars + 2) + 16);
     unsigned long long nhits = 0;
@@ -406,13 +427,9 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
       abort();
     a.qconf = conf.data();
     a.qnp = (uint32_t)qp.npieces;
-    a.qq = (uint32_t)qp.q;
     res->hits = nhits;
-    for (unsigned long long h = 0; h < nhits; h++) {
-      const uint32_t qs = key_qs(hits[h]);
-      verify_dispatch(W, a, &eq[(size_t)qs * pp.nrows * W], qs, rev[qs] != 0, key_pos(hits[h]));
-    }
-    a.qconf = nullptr, a.qq = 0;
+    refine_and_verify(W, a, eq, pp, rev, hits, nhits);
+    a.qconf = nullptr, a.qnp = 0;
   } else if (n > 0 && fp.enabled) {
     uint32_t nfwd = 0;
     while (nfwd < nq && !rev[nfwd]) nfwd++;
@@ -451,9 +468,20 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
     if (fused)
       for (int p = 0; p < fp.npieces; p++) a.rev_lead = std::max<uint32_t>(a.rev_lead, (uint32_t)fp.piece[p].len);
     res->hits = nhits;
-    for (unsigned long long h = 0; h < nhits; h++) {
-      const uint32_t qs = key_qs(hits[h]);
-      verify_dispatch(W, a, &eq[(size_t)qs * pp.nrows * W], qs, rev[qs] != 0, key_pos(hits[h]));
+    if (profile == kDna) {  // as Engine::search: hits are refined to nominal end positions first
+      std::vector<uint32_t> conf((size_t)nq * fp.npieces * kConfWords);
+      for (uint32_t q = 0; q < nq; q++)
+        build_filter_confirm(fp, qptr[q], rev[q] != 0, rev[q] != 0 && !fused, &conf[(size_t)q * fp.npieces * kConfWords]);
+      a.qconf = conf.data();
+      a.qnp = (uint32_t)fp.npieces;
+      a.rev_lead = 0;
+      refine_and_verify(W, a, eq, pp, rev, hits, nhits);
+      a.qconf = nullptr, a.qnp = 0;
+    } else {
+      for (unsigned long long h = 0; h < nhits; h++) {
+        const uint32_t qs = key_qs(hits[h]);
+        verify_dispatch(W, a, &eq[(size_t)qs * pp.nrows * W], qs, rev[qs] != 0, key_pos(hits[h]));
+      }
     }
   } else if (n > 0) {
     for (uint32_t q = 0; q < nq; q++) {

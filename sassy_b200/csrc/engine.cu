@@ -71,6 +71,8 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
   if (qsq && !strcmp(qsq, "0")) qgram_seq_ = false;
   const char* qq = getenv("SASSY_B200_QGRAM_MIN_Q");
   if (qq) qgram_min_q_ = std::max(6, std::min(8, atoi(qq)));
+  const char* rf = getenv("SASSY_B200_REFINE");
+  if (rf && !strcmp(rf, "0")) refine_mode_ = false;
   const char* rb = getenv("SASSY_B200_FILTER_ROW_BYTES");
   if (rb) filter_row_bytes_ = atoi(rb);
   const char* fs = getenv("SASSY_B200_FUSE_STRANDS");
@@ -256,16 +258,19 @@ void Engine::upload_params(const std::vector<Query>& queries, int m, int W, cons
   const int WT = fused ? 2 * fp.WF : fp.WF;  // automaton words per filter table
   // q-gram route: ONE bitmap for all queries (pattern and reversed partner), then the confirm codes
   const size_t ntab = qp ? 1 : (fused ? nq / 2 : nq);
-  const size_t qconf_words = qp ? nq * (size_t)qp->npieces * 2 : 0;
-  const size_t tab_words = qp ? qp->table_words() + qconf_words
+  const size_t tab_words = qp ? qp->table_words()
                               : (!fp.enabled ? 0 : (pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT));
+  // piece records of the exact hit refinement (Dna): [query][piece][kConfWords], behind the tables
+  const int conf_pieces = profile_ != kDna ? 0 : (qp ? qp->npieces : (fp.enabled ? fp.npieces : 0));
+  const size_t conf_words = nq * (size_t)conf_pieces * kConfWords;
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   off_counts_ = 0;
   off_eq_ = align(8 * sizeof(unsigned long long));
   off_pat_ = off_eq_ + align(eq_bytes);
   off_rev_ = off_pat_ + align(pat_bytes);
   off_feq_ = off_rev_ + align(nq);
-  const size_t total = off_feq_ + align(ntab * tab_words * sizeof(uint32_t));
+  off_qconf_ = off_feq_ + align(ntab * tab_words * sizeof(uint32_t));
+  const size_t total = off_qconf_ + align(conf_words * sizeof(uint32_t));
   if (total > stage_cap_) {
     if (h_stage_) cudaFreeHost(h_stage_);
     h_stage_ = nullptr;
@@ -281,11 +286,17 @@ void Engine::upload_params(const std::vector<Query>& queries, int m, int W, cons
     memcpy(h_stage_ + off_pat_ + q * m, queries[q].bytes, m);
     h_stage_[off_rev_ + q] = queries[q].rev ? 1 : 0;
     build_eq_table(profile_, queries[q].bytes, m, W, nrows_, h_eq + q * nrows_ * W);
+    uint32_t* h_conf = reinterpret_cast<uint32_t*>(h_stage_ + off_qconf_) + q * (size_t)conf_pieces * kConfWords;
     if (qp) {
       if (q == 0) memset(h_feq, 0, tab_words * sizeof(uint32_t));
       add_qgram_entries(*qp, queries[q].bytes, queries[q].rev, h_feq);
-      build_qgram_confirm(*qp, queries[q].bytes, queries[q].rev, h_feq + qp->table_words() + q * qp->npieces * 2);
-    } else if (fp.enabled && q < ntab) {
+      if (conf_pieces) build_qgram_confirm(*qp, queries[q].bytes, queries[q].rev, h_conf);
+    } else if (fp.enabled && conf_pieces) {
+      // reversed queries: matched back to front by the forward pass when the strands share it
+      // (fused), by their own right-to-left pass otherwise
+      build_filter_confirm(fp, queries[q].bytes, queries[q].rev, queries[q].rev && !fused, h_conf);
+    }
+    if (!qp && fp.enabled && q < ntab) {
       const uint8_t* partner = fused ? queries[q + ntab].bytes : nullptr;  // the reversed partner query
       if (pair)
         build_pair_table(fp, queries[q].bytes, h_feq + q * tab_words, partner);
@@ -293,7 +304,7 @@ void Engine::upload_params(const std::vector<Query>& queries, int m, int W, cons
         build_filter_table(profile_, fp, queries[q].bytes, h_feq + q * tab_words, partner);
     }
   }
-  off_qconf_ = qp ? off_feq_ + qp->table_words() * sizeof(uint32_t) : 0;
+  conf_pieces_ = conf_pieces;
   SB_CUDA(cudaMemcpyAsync(d_stage_.p, h_stage_, total, cudaMemcpyHostToDevice, stream_));
 }
 
@@ -803,19 +814,24 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     v.hit_cap = hit_cap_;
     if (fused)  // a reversed query's hit marks the START of its piece in scan direction
       for (int p = 0; p < fp.npieces; p++) v.rev_lead = std::max<uint32_t>(v.rev_lead, (uint32_t)fp.piece[p].len);
-    if (qgram) {
-      // q-gram hits are confirmed exactly (a whole share of the pattern behind them) by one thread
-      // each; the survivors -- a small fraction -- are compacted into a second list, so that the
-      // re-scan runs on dense warps instead of one live lane per warp
-      hits2_.ensure(hit_cap_ * sizeof(uint64_t));
+    const bool refine = conf_pieces_ > 0 && refine_mode_;
+    if (refine) {
+      // Dna: every hit is refined exactly by one thread -- which share of the pattern occurs behind
+      // it, and where -- and the (few) survivors are written to a second list as nominal end
+      // positions: the re-scan covers 2k + 1 end positions per entry instead of 16 + m + k, on
+      // dense warps (refine_hit in scan_core.cuh)
+      hits2_.ensure(hit_cap_ * (sizeof(uint64_t) + sizeof(uint32_t)));
+      uint32_t* spans = reinterpret_cast<uint32_t*>(hits2_.as<uint64_t>() + hit_cap_);
       ScanArgs cf = v;
       cf.qconf = reinterpret_cast<const uint32_t*>(dst + off_qconf_);
-      cf.qnp = (uint32_t)qp.npieces;
-      cf.qq = (uint32_t)qp.q;
-      SB_CUDA(launch_confirm(cf, hits2_.as<uint64_t>(), d_counts + 4, stream_));
+      cf.qnp = (uint32_t)conf_pieces_;
+      SB_CUDA(launch_refine(cf, d_rev, hits2_.as<uint64_t>(), spans, d_counts + 4, stream_));
       stats_.aux_launches++;
       v.hit_keys = hits2_.as<uint64_t>();
+      v.hit_span = spans;
       v.hit_count = d_counts + 4;
+      v.hit_exact = 1;
+      v.rev_lead = 0;
     }
     SB_CUDA(launch_verify(W, v, d_rev, stream_));
     stats_.aux_launches++;
@@ -826,13 +842,15 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     stats_.verify_ms = elapsed(ev_[2], ev_[4]);
     unsigned long long nhits = h_counts[2];
     stats_.hits = nhits;
-    stats_.confirmed = qgram ? h_counts[4] : nhits;
+    stats_.confirmed = refine ? h_counts[4] : nhits;
     stats_.filter_words = qgram ? 1u : (uint32_t)WT;
     stats_.filter_len = qgram ? (uint32_t)qp.q : (uint32_t)fp.L;
     stats_.filter_kind = qgram ? 2u : 1u;
     // too many hits (repetitive text, unlucky pieces): the re-scan costs more than the scan
     // (q-gram hits are confirmed first: ~64 character-steps each unless a whole share is there)
-    const double rescan = (double)nhits * (qgram ? 64.0 : 2.0 * (m + k) + kHitChars);
+    const double rescan = refine ? (double)nhits * 24.0 + (double)h_counts[4] * (2.0 * m + 3.0 * k)
+                                 : (double)nhits * (2.0 * (m + k) + kHitChars);
+    if (refine && h_counts[4] > hit_cap_) nhits = hit_cap_ + 1;  // refined list overflowed: as a hit overflow
     if (pg_check()) {  // every rank's result is complete and already gathered
       stats_.ltot = gf.ltot;
       stats_.rows = gf.rows;

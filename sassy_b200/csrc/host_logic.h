@@ -320,18 +320,35 @@ inline void add_qgram_entries(const QgramPlan& f, const uint8_t* query, bool rev
   }
 }
 
-// {code, mask} of the first min(len, 16) characters of every share (qgram_confirm).
-inline void build_qgram_confirm(const QgramPlan& f, const uint8_t* query, bool reversed, uint32_t* out) {
-  std::vector<uint8_t> cls;
-  for (int p = 0; p < f.npieces; p++) {
-    cls.resize(f.len[p]);
-    qgram_piece_classes(f, p, query, reversed, cls.data());
-    const int l = std::min(f.len[p], 16);
-    uint32_t code = 0;
-    for (int j = 0; j < l; j++) code |= (uint32_t)cls[j] << (2 * j);
-    out[2 * p] = code;
-    out[2 * p + 1] = l == 16 ? 0xFFFFFFFFu : ((1u << (2 * l)) - 1u);
+// Piece records for refine_hit (scan_core.cuh): the first min(len, 16) characters of a piece in forward
+// orientation as 2-bit classes, the first start position a hit allows relative to its chunk, and where
+// the piece sits in the pattern.
+inline void piece_conf(const uint8_t* query, bool reversed, int off, int len, int rel0, uint32_t* out) {
+  const int l = std::min(len, 16);
+  uint32_t code = 0;
+  for (int j = 0; j < l; j++) {
+    const uint8_t ch = query[off + (reversed ? len - 1 - j : j)];
+    code |= (uint32_t)((ch >> 1) & 3) << (2 * j);
   }
+  out[0] = code;
+  out[1] = l == 16 ? 0xFFFFFFFFu : ((1u << (2 * l)) - 1u);
+  out[2] = (uint32_t)rel0;
+  out[3] = (uint32_t)off;
+  out[4] = (uint32_t)len;
+}
+
+inline void build_qgram_confirm(const QgramPlan& f, const uint8_t* query, bool reversed, uint32_t* out) {
+  for (int p = 0; p < f.npieces; p++) piece_conf(query, reversed, f.off[p], f.len[p], 1 - f.q, out + p * kConfWords);
+}
+
+// Piece automaton: the hit chunk holds the last character of a piece in scan direction of the KERNEL
+// (rtl_kernel: the right-to-left pass of reversed queries, whose hit chunk holds the first character
+// of the piece in forward orientation).
+inline void build_filter_confirm(const FilterPlan& f, const uint8_t* query, bool reversed, bool rtl_kernel,
+                                 uint32_t* out) {
+  for (int p = 0; p < f.npieces; p++)
+    piece_conf(query, reversed, f.piece[p].off, f.piece[p].len, rtl_kernel ? 0 : 1 - f.piece[p].len,
+               out + p * kConfWords);
 }
 
 inline size_t padded_alloc(uint64_t n) {

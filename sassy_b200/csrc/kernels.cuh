@@ -38,9 +38,11 @@ cudaError_t launch_qgram(int Q, int S, int variant, const CUtensorMap* tmap, con
 // [32][64]); TMA data path only.
 cudaError_t launch_qgram_seq(int Q, int S, const CUtensorMap* tmap, const ScanArgs& a, int sm_count,
                              cudaStream_t stream);
-// Exact confirmation of q-gram hits (qgram_confirm): hits that have a whole share of their query
-// behind them are appended to `out` (same capacity as a.hit_keys), *out_count counts them.
-cudaError_t launch_confirm(const ScanArgs& a, uint64_t* out, unsigned long long* out_count, cudaStream_t stream);
+// Exact refinement of prefilter hits (refine_hit, Dna): every (share, alignment) that matches behind a
+// hit becomes one entry (query slot, nominal end position) in `out` (capacity a.hit_cap, *out_count
+// counts them); launch_verify then runs with ScanArgs::hit_exact = 1 on that list.
+cudaError_t launch_refine(const ScanArgs& a, const uint8_t* rev_flags, uint64_t* out, uint32_t* out_span,
+                          unsigned long long* out_count, cudaStream_t stream);
 // nhits is read from a.hit_count on the device (clipped to a.hit_cap): no host round trip.
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream);
 

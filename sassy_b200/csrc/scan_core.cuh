@@ -82,9 +82,11 @@ struct ScanArgs {
   uint64_t hit_cap;
   uint64_t emit_min;        // overhang: end positions <= emit_min come from the edge kernel instead
   // q-gram bitmap prefilter (qgram_kernel): exact confirmation of a hit before its re-scan
-  const uint32_t* qconf;    // [query slot][qnp] {code, mask}: first <= 16 characters of every piece, 2 bits each
-  uint32_t qnp;             // pieces per query (k + 1)
-  uint32_t qq;              // q (characters per q-gram); 0 = hits are not q-gram hits
+  // exact refinement of prefilter hits (refine_hit): Dna only
+  const uint32_t* qconf;    // [query slot][qnp][kConfWords] piece records, see PieceConf
+  uint32_t qnp;             // pieces per query (k + 1); 0 = hits are not refined
+  uint32_t hit_exact;       // 1: hit keys hold a nominal END POSITION (scan direction) instead of a 16-byte chunk
+  const uint32_t* hit_span; // hit_exact: per entry, how many positions beyond the nominal one the entry covers
 };
 
 template <int W>
@@ -567,20 +569,40 @@ SB_HD void qlane_init(QLane& s, const uint32_t (&hist)[4]) {
   s.prev = hi;
 }
 
-// Exact confirmation of a q-gram hit in the 16-byte chunk at forward index `base` (a multiple of
-// 16) for query slot `qs`: the sampled Q-gram ends at e in [base + S, base + 16] and starts at most
-// S - 1 characters into its share, so the share starts at a in [base + 1 - Q, base + 16 - Q]: 16
-// alignments, each compared with the first min(|F|, 16) characters of every share (2-bit classes,
-// one XOR + mask per share).  Both strands are tested in FORWARD orientation (the reversed
-// partner's shares are stored reversed).  A share occurrence is never missed; a false "true" only
-// costs a re-scan.
-SB_HD bool qgram_confirm(const ScanArgs& a, uint32_t qs, uint64_t base) {
-  // characters [base - 16, base + 32) as 2-bit classes, first character in the low bits
-  uint32_t c[3];
+// Exact refinement of a prefilter hit (Dna).  A hit only says "some share of the pattern may occur
+// around this 16-byte chunk"; here the first min(|F|, 16) characters of every share F (forward
+// orientation, 2-bit classes) are compared at the 16 alignments the hit allows, and every
+// (share, alignment) that matches is turned into the NOMINAL END POSITION of the pattern,
+//   E0 = start of F - offset of F in the pattern + m        (scan direction of the query slot):
+// in an alignment with at most k edits that leaves this share intact, the pattern ends within k
+// characters of E0.  The re-scan then covers end positions E0 - k .. E0 + k only (plus m + k
+// characters of warm-up) instead of the 16 + m + k positions behind an unrefined hit.
+// Which alignments a hit allows (start of F relative to the chunk, rel0 .. rel0 + 15):
+//   q-gram bitmap: the sampled Q-gram ends in the chunk and starts < S characters into F: rel0 = 1 - Q;
+//   piece automaton, forward pass: the LAST character of F lies in the chunk: rel0 = 1 - |F|;
+//   piece automaton, right-to-left pass (reversed queries): the FIRST character of F does: rel0 = 0.
+// A share occurrence is never missed (the tests force every route); a false match costs a re-scan.
+constexpr int kConfWords = 5;  // code, mask, rel0 (int32), offset in the pattern, length
+struct PieceConf {
+  uint32_t code, mask;
+  int32_t rel0;
+  uint32_t off, len;
+};
+
+// Returns false when no share matches behind the hit; else [lo, hi] = the smallest and the largest
+// nominal end position over all matching (share, alignment) pairs of this chunk: ONE refined entry
+// per hit, whose re-scan reports end positions lo - k .. hi + k.  (Almost always lo == hi; on
+// repetitive text, where every alignment of every share matches, the entry degrades to about the
+// window of an unrefined hit instead of multiplying.)
+SB_HD bool refine_hit(const ScanArgs& a, uint32_t qs, bool rev, uint64_t base, int64_t& lo, int64_t& hi) {
+  bool found = false;
+  lo = hi = 0;
+  // characters [base - 32, base + 32) as 2-bit classes, first character in the low bits
+  uint32_t c[4];
 #pragma unroll
-  for (int j = 0; j < 3; j++) {
+  for (int j = 0; j < 4; j++) {
     uint32_t code = 0;
-    const int64_t at = (int64_t)base - 16 + 16 * j;
+    const int64_t at = (int64_t)base - 32 + 16 * j;
     if (at >= 0) {
       uint32_t x[4];
 #if defined(__CUDA_ARCH__)
@@ -594,34 +616,66 @@ SB_HD bool qgram_confirm(const ScanArgs& a, uint32_t qs, uint64_t base) {
     }
     c[j] = code;
   }
-  const uint32_t* conf = a.qconf + (size_t)qs * a.qnp * 2;
-  for (int i = 0; i < 16; i++) {
-    const uint32_t off = 17u - a.qq + (uint32_t)i;  // start of the alignment relative to base - 16
-    const uint32_t val = funnel_r(c[off >> 4], c[(off >> 4) + 1], 2 * (off & 15u));
-    for (uint32_t p = 0; p < a.qnp; p++)
-      if (((val ^ conf[2 * p]) & conf[2 * p + 1]) == 0) return true;
+  const uint32_t* conf = a.qconf + (size_t)qs * a.qnp * kConfWords;
+  for (uint32_t p = 0; p < a.qnp; p++) {
+    const uint32_t code = conf[p * kConfWords], mask = conf[p * kConfWords + 1];
+    const int32_t rel0 = (int32_t)conf[p * kConfWords + 2];
+    const uint32_t off = conf[p * kConfWords + 3], len = conf[p * kConfWords + 4];
+    for (int i = 0; i < 16; i++) {
+      const uint32_t o = (uint32_t)(32 + rel0 + i);  // start of the alignment relative to base - 32: 4 .. 47
+      const uint32_t w0 = c[o >> 4], w1 = (o >> 4) < 3 ? c[(o >> 4) + 1] : 0u;
+      const uint32_t val = funnel_r(w0, w1, 2 * (o & 15u));
+      if (((val ^ code) & mask) != 0) continue;
+      const int64_t start = (int64_t)base + rel0 + i;  // forward index of the first character of F
+      if (start < 0 || start + (int64_t)len > (int64_t)a.n) continue;
+      // nominal end position of the whole pattern in the slot's scan direction
+      const int64_t e0 = rev ? (int64_t)a.n - start - (int64_t)len + ((int64_t)a.m - (int64_t)off)
+                             : start - (int64_t)off + (int64_t)a.m;
+      if (!found || e0 < lo) lo = e0;
+      if (!found || e0 > hi) hi = e0;
+      found = true;
+    }
   }
-  return false;
+  if (!found || hi + a.k < 1) return false;
+  if (lo < 0) lo = 0;
+  if (hi < lo) hi = lo;
+  return true;
 }
 
 // Re-scan of the neighbourhood of one hit with the exact recurrences.  The hit
 // is the text chunk at forward index 16*unit; in scan direction it starts at G0.
 // A piece occurrence ending inside the chunk implies end positions in
 // (G0, G0 + 16 + m + k]; starting m+k characters before G0 makes them exact.
+// Window of a refined hit (nominal end position e0): scan [w0, end), report end positions > emit_from.
+SB_HD void hit_window_exact(const ScanArgs& a, uint64_t e0, uint32_t span, int64_t& w0, int64_t& end,
+                            int64_t& emit_from) {
+  const int64_t n = (int64_t)a.n;
+  emit_from = (int64_t)e0 - (int64_t)a.k - 1;
+  if (emit_from < 0) emit_from = 0;
+  w0 = emit_from - ((int64_t)a.m + (int64_t)a.k);
+  if (w0 < 0) w0 = 0;
+  end = (int64_t)e0 + (int64_t)span + (int64_t)a.k;
+  if (end > n) end = n;
+}
+
 template <int W>
 SB_HD void verify_hit(const ScanArgs& a, const uint32_t* eq /*[nrows][W] of this query*/, uint32_t qs, bool rev,
-                      uint64_t unit) {
+                      uint64_t unit, uint32_t span = 0) {
   const int64_t n = (int64_t)a.n;
-  const int64_t base = (int64_t)(unit * kHitChars);
-  if (a.qq && !qgram_confirm(a, qs, (uint64_t)base)) return;
-  const int64_t g0 = rev ? n - kHitChars - base : base;  // may be negative for the chunk straddling the text end
-  const int64_t span = (int64_t)a.m + (int64_t)a.k;
-  int64_t w0 = g0 - span;
-  if (w0 < 0) w0 = 0;
-  // strand-fused prefilter: a reversed query's hit marks where its piece STARTS in scan direction
-  int64_t end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
-  if (end > n) end = n;
-  const int64_t emit_from = g0 < 0 ? 0 : g0;
+  const int64_t reach = (int64_t)a.m + (int64_t)a.k;
+  int64_t w0, end, emit_from;
+  if (a.hit_exact) {  // refined hit: `unit` is the nominal end position E0; end positions E0 - k .. E0 + span + k
+    hit_window_exact(a, unit, span, w0, end, emit_from);
+  } else {
+    const int64_t base = (int64_t)(unit * kHitChars);
+    const int64_t g0 = rev ? n - kHitChars - base : base;  // may be negative for the chunk straddling the text end
+    w0 = g0 - reach;
+    if (w0 < 0) w0 = 0;
+    // strand-fused prefilter: a reversed query's hit marks where its piece STARTS in scan direction
+    end = g0 + kHitChars + reach + (rev ? (int64_t)a.rev_lead : 0);
+    if (end > n) end = n;
+    emit_from = g0 < 0 ? 0 : g0;
+  }
   Lane<W> s;
   lane_reset<W>(s, a.m);
   for (int64_t idx = w0; idx < end; idx++) {
@@ -832,7 +886,9 @@ SB_HD uint8_t text_at_dir(const uint8_t* text, uint64_t n, bool rev, uint64_t i)
 // for patterns of more than 4 words also the horizontal deltas (ph, mh) of the step that produced
 // the column, so that the greedy walk looks its three neighbours up with single-bit reads instead
 // of prefix popcounts over up to 32 words (a 1000-character pattern walks 1000 steps).
-SB_HD int trace_fields(int W) { return W > 4 ? 4 : 2; }
+// (from 3 words on: a 100-character pattern walks ~100 steps, each of which would otherwise read and
+// popcount up to 3 x W x 2 words of the column store)
+SB_HD int trace_fields(int W) { return W > 2 ? 4 : 2; }
 SB_HD uint64_t trace_words_per_match(int m, int k, int W) {
   return (uint64_t)(m + k + 1) * (uint64_t)W * (uint64_t)trace_fields(W);
 }

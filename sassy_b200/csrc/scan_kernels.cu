@@ -586,15 +586,19 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
   const uint32_t* __restrict__ eq = a.eq + (size_t)qs * a.nrows * W;
 
   const int64_t n = (int64_t)a.n;
-  const int64_t base = (int64_t)(key_pos(key) * kHitChars);
-  if (a.qq && !qgram_confirm(a, qs, (uint64_t)base)) return;  // a q-gram hit without a whole share behind it
-  const int64_t g0 = rev ? n - kHitChars - base : base;
-  const int64_t span = (int64_t)a.m + (int64_t)a.k;
-  int64_t w0 = g0 - span;
-  if (w0 < 0) w0 = 0;
-  int64_t end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
-  if (end > n) end = n;
-  const int64_t emit_from = g0 < 0 ? 0 : g0;
+  int64_t w0, end, emit_from;
+  if (a.hit_exact) {  // refined hit: nominal end position
+    hit_window_exact(a, key_pos(key), a.hit_span[i], w0, end, emit_from);
+  } else {
+    const int64_t base = (int64_t)(key_pos(key) * kHitChars);
+    const int64_t g0 = rev ? n - kHitChars - base : base;
+    const int64_t span = (int64_t)a.m + (int64_t)a.k;
+    w0 = g0 - span;
+    if (w0 < 0) w0 = 0;
+    end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
+    if (end > n) end = n;
+    emit_from = g0 < 0 ? 0 : g0;
+  }
   scan_window<W>(a, eq, qs, rev, a.text, n, w0, end, emit_from);
 }
 
@@ -1017,19 +1021,19 @@ __global__ void __launch_bounds__(32 * kWideWarps)
     const bool rev = rev_flags[qs] != 0;
     const uint32_t* __restrict__ eq = a.eq + (size_t)qs * a.nrows * W;
     const int64_t n = (int64_t)a.n;
-    const int64_t base = (int64_t)(key_pos(key) * kHitChars);
-    if (a.qq) {  // q-gram hit: re-scan only behind a whole share (warp-uniform decision)
-      int okc = 0;
-      if (lane == 0) okc = qgram_confirm(a, qs, (uint64_t)base) ? 1 : 0;
-      if (!__shfl_sync(0xFFFFFFFFu, okc, 0)) continue;
+    int64_t w0, end, emit_from;
+    if (a.hit_exact) {
+      hit_window_exact(a, key_pos(key), a.hit_span[h], w0, end, emit_from);
+    } else {
+      const int64_t base = (int64_t)(key_pos(key) * kHitChars);
+      const int64_t g0 = rev ? n - kHitChars - base : base;
+      const int64_t span = (int64_t)a.m + (int64_t)a.k;
+      w0 = g0 - span;
+      if (w0 < 0) w0 = 0;
+      end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
+      if (end > n) end = n;
+      emit_from = g0 < 0 ? 0 : g0;
     }
-    const int64_t g0 = rev ? n - kHitChars - base : base;
-    const int64_t span = (int64_t)a.m + (int64_t)a.k;
-    int64_t w0 = g0 - span;
-    if (w0 < 0) w0 = 0;
-    int64_t end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
-    if (end > n) end = n;
-    const int64_t emit_from = g0 < 0 ? 0 : g0;
     if (end <= w0) continue;
     const int32_t L = (int32_t)(end - w0);
     // stage the window in scan order; a window beyond the buffer is processed in pieces below
@@ -1078,37 +1082,30 @@ __global__ void __launch_bounds__(32 * kWideWarps)
 namespace {
 
 __global__ void __launch_bounds__(256)
-    confirm_kernel(const __grid_constant__ ScanArgs a, uint64_t* __restrict__ out, unsigned long long* out_count) {
+    refine_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags, uint64_t* __restrict__ out,
+                  uint32_t* __restrict__ out_span, unsigned long long* out_count) {
   unsigned long long nhits = *a.hit_count;
   if (nhits > a.hit_cap) nhits = a.hit_cap;
   const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
-  const unsigned long long rounds = (nhits + nthreads - 1) / nthreads;  // whole warps stay in the loop
-  const uint32_t lane = threadIdx.x & 31;
-  for (unsigned long long r = 0; r < rounds; r++) {
-    const unsigned long long i = r * nthreads + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t key = 0;
-    bool ok = false;
-    if (i < nhits) {
-      key = a.hit_keys[i];
-      ok = qgram_confirm(a, key_qs(key), key_pos(key) * kHitChars);
-    }
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-    if (m) {
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(out_count, (unsigned long long)__popc(m));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (ok) {
-        const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
-        if (at < a.hit_cap) out[at] = key;
-      }
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nhits; i += nthreads) {
+    const uint64_t key = a.hit_keys[i];
+    const uint32_t qs = key_qs(key);
+    int64_t lo, hi;
+    if (!refine_hit(a, qs, rev_flags[qs] != 0, key_pos(key) * kHitChars, lo, hi)) continue;
+    // survivors are rare (a whole share of the pattern behind the hit): one atomic each
+    const unsigned long long at = atomicAdd(out_count, 1ull);
+    if (at < a.hit_cap) {
+      out[at] = cand_key(qs, (uint64_t)lo);
+      out_span[at] = (uint32_t)(hi - lo);
     }
   }
 }
 
 }  // namespace
 
-cudaError_t launch_confirm(const ScanArgs& a, uint64_t* out, unsigned long long* out_count, cudaStream_t stream) {
-  confirm_kernel<<<148 * 8, 256, 0, stream>>>(a, out, out_count);
+cudaError_t launch_refine(const ScanArgs& a, const uint8_t* rev_flags, uint64_t* out, uint32_t* out_span,
+                          unsigned long long* out_count, cudaStream_t stream) {
+  refine_kernel<<<148 * 8, 256, 0, stream>>>(a, rev_flags, out, out_span, out_count);
   return cudaGetLastError();
 }
 
@@ -1116,7 +1113,9 @@ cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cu
   const unsigned threads = 128;
   const unsigned blocks = 148 * 12;  // grid-stride over the device-side hit count
   // many words: one warp per hit (systolic), when the window fits the staging buffer
-  const int64_t window = 2 * ((int64_t)a.m + a.k) + kHitChars + (int64_t)a.rev_lead;
+  // (refined entries: warm-up m + k, 2k + 1 end positions, and a span of at most 16 + m on repetitive text)
+  const int64_t window = a.hit_exact ? 2 * (int64_t)a.m + 3 * (int64_t)a.k + 18
+                                     : 2 * ((int64_t)a.m + a.k) + kHitChars + (int64_t)a.rev_lead;
   if (W >= 8 && window <= kWideWindow) {
     const unsigned wblocks = 148 * 8;
     switch (W) {
