@@ -390,7 +390,7 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
   std::vector<const uint8_t*> qptr(nq);
   for (uint32_t q = 0; q < nq; q++) qptr[q] = queries + (size_t)q * m;
   FilterPlan fp;
-  // use_filter: 0 off, < 0 automatic, 1 force the piece automaton, 2 / 3 as Engine::search with the
+  // use_filter: 0 off, < 0 automatic, 1 force the piece automaton (4: and refine its hits), 2 / 3 as Engine::search with the
   // filter forced (q-gram bitmap when it can be planned -- 2: contiguous tiles, 3: row tiles --
   // else the piece automaton)
   if (use_filter != 0) fp = plan_filter(profile, qptr.data(), nq, m, k, use_filter > 0 ? 1e30 : 0.85);
@@ -468,7 +468,7 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
     if (fused)
       for (int p = 0; p < fp.npieces; p++) a.rev_lead = std::max<uint32_t>(a.rev_lead, (uint32_t)fp.piece[p].len);
     res->hits = nhits;
-    if (profile == kDna) {  // as Engine::search: hits are refined to nominal end positions first
+    if (profile == kDna && use_filter == 4) {  // SASSY_B200_REFINE=2: piece-automaton hits are refined too
       std::vector<uint32_t> conf((size_t)nq * fp.npieces * kConfWords);
       for (uint32_t q = 0; q < nq; q++)
         build_filter_confirm(fp, qptr[q], rev[q] != 0, rev[q] != 0 && !fused, &conf[(size_t)q * fp.npieces * kConfWords]);

@@ -72,7 +72,7 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
   const char* qq = getenv("SASSY_B200_QGRAM_MIN_Q");
   if (qq) qgram_min_q_ = std::max(6, std::min(8, atoi(qq)));
   const char* rf = getenv("SASSY_B200_REFINE");
-  if (rf && !strcmp(rf, "0")) refine_mode_ = false;
+  if (rf) refine_mode_ = std::max(0, std::min(2, atoi(rf)));
   const char* rb = getenv("SASSY_B200_FILTER_ROW_BYTES");
   if (rb) filter_row_bytes_ = atoi(rb);
   const char* fs = getenv("SASSY_B200_FUSE_STRANDS");
@@ -814,7 +814,9 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     v.hit_cap = hit_cap_;
     if (fused)  // a reversed query's hit marks the START of its piece in scan direction
       for (int p = 0; p < fp.npieces; p++) v.rev_lead = std::max<uint32_t>(v.rev_lead, (uint32_t)fp.piece[p].len);
-    const bool refine = conf_pieces_ > 0 && refine_mode_;
+    // (piece-automaton hits ARE share occurrences: refining them costs a pass over ~10^6 hits and
+    //  buys shorter but unaligned windows -- measured slower on c2; q-gram hits are mostly false)
+    const bool refine = conf_pieces_ > 0 && (refine_mode_ == 2 || (refine_mode_ == 1 && qgram));
     if (refine) {
       // Dna: every hit is refined exactly by one thread -- which share of the pattern occurs behind
       // it, and where -- and the (few) survivors are written to a second list as nominal end

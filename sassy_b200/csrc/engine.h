@@ -179,7 +179,7 @@ class Engine {
   bool qgram_seq_ = true;   // contiguous-tile q-gram kernel (SASSY_B200_QGRAM_SEQ=0: row-tiled kernel)
   size_t off_qconf_ = 0;
   int conf_pieces_ = 0;       // pieces per query in the refinement records of the last upload (0: none)
-  bool refine_mode_ = true;   // SASSY_B200_REFINE=0: re-scan the unrefined 16-byte hit chunks
+  int refine_mode_ = 1;       // SASSY_B200_REFINE: 0 never refine hits, 1 q-gram hits (default), 2 piece-automaton hits too
   int filter_row_bytes_ = 0;  // SASSY_B200_FILTER_ROW_BYTES (experiments): bytes per thread row of the prefilter
   int transport_mode_ = 1;
   float transfer_ms_ = 0;

@@ -297,8 +297,10 @@ __global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const 
 
 }  // namespace
 
-// Wide path: patterns of >= 8 words, traced (not cost-only), no overhang.
-static bool trace_is_wide(const TraceArgs& t) { return t.W >= 8 && !t.costs && !(t.alpha >= 0.f); }
+// Wide path (one warp per match): patterns of >= 3 words, traced (not cost-only), no overhang.  One
+// thread needs ~120 us for a 100-character pattern (430 dependent word-steps, then a walk whose
+// every step reads the column store), a warp ~20 us.
+static bool trace_is_wide(const TraceArgs& t) { return t.W >= 3 && !t.costs && !(t.alpha >= 0.f); }
 
 cudaError_t launch_minima(const uint64_t* keys, const uint32_t* cost, uint64_t n, uint8_t* flags, bool all_minima,
                           const EndFilter* filter, cudaStream_t stream) {

@@ -628,6 +628,25 @@ SB_HD bool refine_hit(const ScanArgs& a, uint32_t qs, bool rev, uint64_t base, i
       if (((val ^ code) & mask) != 0) continue;
       const int64_t start = (int64_t)base + rel0 + i;  // forward index of the first character of F
       if (start < 0 || start + (int64_t)len > (int64_t)a.n) continue;
+      // An intact copy of the pattern matches with ALL its shares, on one diagonal, and every share
+      // would contribute an entry with the same nominal end.  Keep the entry of the first share
+      // only: skip when an earlier share (one that fits the 16 compared characters entirely, so
+      // that its own hit and refinement are certain) also matches on this diagonal.
+      {
+        const int64_t diag = start - (rev ? (int64_t)a.m - (int64_t)off - (int64_t)len : (int64_t)off);
+        bool covered = false;
+        for (uint32_t p2 = 0; p2 < p && !covered; p2++) {
+          const uint32_t len2 = conf[p2 * kConfWords + 4];
+          if (len2 > 16) continue;
+          const uint32_t off2 = conf[p2 * kConfWords + 3];
+          const int64_t s2 = diag + (rev ? (int64_t)a.m - (int64_t)off2 - (int64_t)len2 : (int64_t)off2);
+          if (s2 < 0 || s2 + (int64_t)len2 > (int64_t)a.n) continue;
+          uint32_t v2 = 0;
+          for (uint32_t j = 0; j < len2; j++) v2 |= (((uint32_t)a.text[s2 + j] >> 1) & 3u) << (2 * j);
+          covered = v2 == conf[p2 * kConfWords];
+        }
+        if (covered) continue;
+      }
       // nominal end position of the whole pattern in the slot's scan direction
       const int64_t e0 = rev ? (int64_t)a.n - start - (int64_t)len + ((int64_t)a.m - (int64_t)off)
                              : start - (int64_t)off + (int64_t)a.m;

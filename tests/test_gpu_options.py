@@ -300,3 +300,46 @@ def test_gpu_encoded_overhang():
             want = oracle.search_encoded("iupac", pats, t, k, rc=True, all_minima=allm, alpha=0.5)
             got = s.search_all_encoded_patterns(enc, t, k) if allm else s.search_encoded_patterns(enc, t, k)
             assert sorted(map(kk, got)) == sorted(map(kk, want)), (it, m, n, k, allm)
+
+
+def test_two_searchers_on_two_host_threads():
+    """The reference's documented usage is one searcher per worker thread (bin/grep.rs:488-498).
+    Two threads, each with its own searchers (different pattern lengths -> different kernel
+    instantiations and shared-memory limits), search concurrently; every result equals the
+    oracle's.  Exercises the guarded launch-configuration caches (scan_kernels.cu)."""
+    import threading
+    import random
+    import oracle
+    import sassy_b200
+    rng = random.Random(91)
+    n = 300_000
+    base = bytes(rng.choice(b"ACGT") for _ in range(n))
+    jobs = []
+    for m, k, alphabet in [(20, 2, "dna"), (100, 8, "dna"), (23, 3, "iupac"), (64, 4, "dna"), (200, 6, "iupac"), (12, 1, "dna")]:
+        p = bytes(rng.choice(b"ACGT") for _ in range(m))
+        t = bytearray(base)
+        for _ in range(5):
+            pos = rng.randrange(0, n - m)
+            t[pos:pos + m] = p
+        t = bytes(t)
+        want = [(x.text_start, x.text_end, x.cost, x.strand, x.cigar) for x in oracle.search(alphabet, p, t, k, rc=True)]
+        jobs.append((alphabet, p, t, k, want))
+    errors = []
+
+    def worker(my_jobs):
+        try:
+            for rep in range(3):
+                for alphabet, p, t, k, want in my_jobs:
+                    s = sassy_b200.Searcher(alphabet, rc=True)
+                    got = [(x.text_start, x.text_end, x.cost, x.strand, x.cigar) for x in s.search(p, t, k)]
+                    if got != want:
+                        errors.append((alphabet, len(p), k, len(got), len(want)))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(jobs[i::2],)) for i in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

@@ -70,7 +70,7 @@ def test_emu_v2_fuzz():
             assert list(map(key, got)) == list(map(key, want))  # same order: query slot, then end
 
 
-@pytest.mark.parametrize("mode", [1, -1])
+@pytest.mark.parametrize("mode", [1, -1, 4])
 def test_emu_prefilter_fuzz(mode):
     """Exact piece prefilter + re-scan of the hit neighbourhoods == full scan == oracle."""
     rng = random.Random(14)
