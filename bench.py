@@ -297,33 +297,50 @@ class ClockSampler:
 def cpu_sample(profile, pats, k, rc, text_addr, n, cores, seconds, runs=3):
     """Times the CPU port on a bounded sample of the workload: all of the text, as many of the
     patterns as fit the time budget (at least 1); one warm-up run, then the median of `runs`.
-    Returns (dict for cpu_baseline, sample patterns, {(pattern index, end, cost)})."""
+    Batches (Iupac, forward strand) run the pattern-tiled v2 restatement (u32 pattern lanes, u16
+    suffix prefilter for k <= 3, traceback); single patterns the text-tiled v1 restatement.
+    Returns (dict for cpu_baseline, sample patterns, {(pattern index, end, cost, strand)}, starts)."""
     from oracle import cpu_port
-    rate = cpu_port.calibrate(profile, pats[:1], k, rc)  # text bytes x patterns / s / thread
-    per_pattern = n / max(rate * cores * 0.6, 1.0)  # seconds per pattern over the whole text
-    np_sample = int(max(1, min(len(pats), 64, seconds / (runs + 1) / max(per_pattern, 1e-3))))
+    batch = len(pats) > 1 and profile == "iupac" and not rc and len(pats[0]) <= 32
+    if batch:
+        probe = pats[:32]
+        _, sec = cpu_port.search_batch(probe, text_addr, min(n, 1 << 26), k, threads=cores)
+        per_pattern = sec / len(probe) * (n / min(n, 1 << 26))
+        np_sample = int(max(1, min(len(pats), 128, seconds / (runs + 1) / max(per_pattern, 1e-4))))
+        np_sample = max(32, np_sample // 32 * 32) if len(pats) >= 32 else np_sample
+    else:
+        rate = cpu_port.calibrate(profile, pats[:1], k, rc)  # text bytes x patterns / s / thread
+        per_pattern = n / max(rate * cores * 0.6, 1.0)  # seconds per pattern over the whole text
+        np_sample = int(max(1, min(len(pats), 64, seconds / (runs + 1) / max(per_pattern, 1e-3))))
     sample = pats[:np_sample]
-    ends = set()
+    ends, starts = set(), {}
     times = []
-    kind = ""
     for it in range(runs + 1):
         t0 = time.perf_counter()
-        got = []
-        for pi, p in enumerate(sample):
-            e, _ = cpu_port.search_ends(profile, p, text_addr, n, k, rc, False, cores)
-            got += [(pi, pos, cost, strand) for pos, cost, strand in e]
-        sec = time.perf_counter() - t0
+        if batch:
+            got, _ = cpu_port.search_batch(sample, text_addr, n, k, threads=cores)
+            sec = time.perf_counter() - t0
+            if it == runs:
+                ends = {(pi, pos, cost, 0) for pi, pos, cost, _ in got}
+                starts = {(pi, pos): st for pi, pos, _, st in got}
+        else:
+            got = []
+            for pi, p in enumerate(sample):
+                e, _ = cpu_port.search_ends(profile, p, text_addr, n, k, rc, False, cores)
+                got += [(pi, pos, cost, strand) for pos, cost, strand in e]
+            sec = time.perf_counter() - t0
+            ends = set(got)
         if it > 0:
             times.append(sec)
-        ends = set(got)
-    kind = cpu_port.kind(cores)
+    kind = cpu_port.kind_v2(cores, k, len(pats[0])) if batch else cpu_port.kind(cores)
     sec = statistics.median(times)
-    return {"seconds": sec, "patterns": np_sample, "kind": kind, "runs": runs, "times": times}, sample, ends
+    return {"seconds": sec, "patterns": np_sample, "kind": kind, "runs": runs, "times": times}, sample, ends, starts
 
 
-def check_against_cpu(name, matches, ends, n_sample_patterns, n_text, rc):
-    """GPU end positions and costs == the CPU port's, for the sampled patterns (both arms searched
-    the same bytes).  v1 semantics: a reverse-complement match ends at n - text_start."""
+def check_against_cpu(name, matches, ends, n_sample_patterns, n_text, rc, starts=None):
+    """GPU end positions and costs (and, where the CPU port traces, start positions) == the CPU
+    port's, for the sampled patterns (both arms searched the same bytes).  v1 semantics: a
+    reverse-complement match ends at n - text_start."""
     got = set()
     for r in matches.records if hasattr(matches, "records") else []:
         pi = int(r["pattern_idx"])
@@ -333,6 +350,9 @@ def check_against_cpu(name, matches, ends, n_sample_patterns, n_text, rc):
             got.add((pi, n_text - int(r["text_start"]), int(r["cost"]), 1))
         else:
             got.add((pi, int(r["text_end"]), int(r["cost"]), 0))
+            if starts and starts.get((pi, int(r["text_end"]))) != int(r["text_start"]):
+                raise SystemExit(f"PARITY FAILURE [{name}]: traced start of pattern {pi} ending at {int(r['text_end'])}: "
+                                 f"GPU {int(r['text_start'])}, CPU port {starts.get((pi, int(r['text_end'])))}")
     if got != ends:
         only_g = sorted(got - ends)[:5]
         only_c = sorted(ends - got)[:5]
@@ -366,24 +386,39 @@ def run_reference(args):
         if n_patterns:
             np_full = n_patterns
         pats = workload_patterns(name, min(np_full, 4096))
-        rate = cpu_port.calibrate(profile, pats[:1], k, args.rc)
-        budget = min(seconds, 150.0 / max(1, steps + warmup))
-        per_pattern = n / max(rate * cores * 0.6, 1.0)
-        sample_pats = pats[:int(max(1, min(len(pats), 64, budget / max(per_pattern, 1e-3))))]
-        sample_n = n if per_pattern <= budget else int(max(1 << 24, n * budget / per_pattern))
         if n not in texts:
             texts[n] = build_window(torch, args, n, 1, 0, n, "cpu")
         addr = texts[n].data_ptr()  # the sample is a prefix of the same text
+        batch = len(pats) > 1 and profile == "iupac" and not args.rc and m <= 32
+        budget = min(seconds, 150.0 / max(1, steps + warmup))
+        if batch:  # v2: pattern-tiled engine, 32-pattern chunks
+            probe_n = min(n, 1 << 26)
+            _, sec = cpu_port.search_batch(pats[:32], addr, probe_n, k, threads=cores)
+            per_pattern = sec / min(32, len(pats)) * (n / probe_n)
+            cnt = int(max(1, min(len(pats), 128, budget / max(per_pattern, 1e-4))))
+            sample_pats = pats[:max(32, cnt // 32 * 32) if len(pats) >= 32 else cnt]
+            per_step = per_pattern * len(sample_pats)
+            sample_n = n if per_step <= budget else int(max(1 << 24, n * budget / per_step))
+        else:
+            rate = cpu_port.calibrate(profile, pats[:1], k, args.rc)
+            per_pattern = n / max(rate * cores * 0.6, 1.0)
+            sample_pats = pats[:int(max(1, min(len(pats), 64, budget / max(per_pattern, 1e-3))))]
+            sample_n = n if per_pattern <= budget else int(max(1 << 24, n * budget / per_pattern))
         times = []
         nm = 0
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            nm = 0
-            for p in sample_pats:
-                e, _ = cpu_port.search_ends(profile, p, addr, sample_n, k, args.rc, False, cores)
-                nm += len(e)
+            if batch:
+                got, _ = cpu_port.search_batch(sample_pats, addr, sample_n, k, threads=cores)
+                nm = len(got)
+            else:
+                nm = 0
+                for p in sample_pats:
+                    e, _ = cpu_port.search_ends(profile, p, addr, sample_n, k, args.rc, False, cores)
+                    nm += len(e)
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
+        kinds[name] = cpu_port.kind_v2(cores, k, m) if batch else cpu_port.kind(cores)
         sec = sum(times) / len(times)
         value = sample_n / sec / 1e9 * len(sample_pats) / np_full  # text GB/s for the whole pattern set
         return {"workload": desc, "value": value, "unit": "GB/s", "ms_per_step": sec * 1e3,
@@ -393,6 +428,7 @@ def run_reference(args):
                 "pattern_len": m, "k": k}
 
     texts = {}
+    kinds = {}
     profile, np_full, m, k, n, desc = WORKLOADS[args.workload]
     if args.text_bytes:
         n = args.text_bytes
@@ -401,7 +437,9 @@ def run_reference(args):
     subs = {}
     for name in sub_list(args, 1):
         subs[name] = one(name, 2, 1, 4.0, args.c5_patterns if name == "c5" else 0)
-    kind = cpu_port.kind(cores)
+    kind = kinds[args.workload]
+    for name in subs:
+        subs[name]["kind"] = kinds[name]
     line = {
         "impl": "reference", "metric": METRIC, "value": top["value"], "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": top["ms_per_step"], "higher_is_better": True,
@@ -711,8 +749,8 @@ def main():
         if rank == 0 and world == 1 and host0 is not None and not args.no_cpu:
             # CPU port on the same bytes (text0): timing for cpu_baseline + the parity check
             try:
-                info, sample, ends = cpu_sample(profile, all_pats, k, args.rc, host0.data_ptr(), n, cores,
-                                                args.cpu_seconds if top else min(args.cpu_seconds, 8.0))
+                info, sample, ends, starts = cpu_sample(profile, all_pats, k, args.rc, host0.data_ptr(), n, cores,
+                                                        args.cpu_seconds if top else min(args.cpu_seconds, 8.0))
                 cpu = {"value": n / info["seconds"] / 1e9 * info["patterns"] / np_full, "unit": "GB/s", "cores": cores,
                        "kind": "port", "gchar_pattern_per_s": n * info["patterns"] / info["seconds"] / 1e9,
                        "sample": f"whole {n}-byte text x first {info['patterns']} of {np_full} patterns, median of "
@@ -725,7 +763,8 @@ def main():
                     else:
                         gm = s.search(sample[0], text0_for(profile), k)
                     checks["gpu_equals_cpu_port"] = {
-                        "end_positions": check_against_cpu(name, gm, ends, len(sample), n, args.rc),
+                        "end_positions": check_against_cpu(name, gm, ends, len(sample), n, args.rc, starts),
+                        "traced_starts_compared": len(starts),
                         "patterns": len(sample), "text_bytes": n, "ok": True}
             except SystemExit:
                 raise

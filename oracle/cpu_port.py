@@ -35,6 +35,12 @@ def _lib():
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                         ctypes.POINTER(ctypes.c_double)]
         lib.cpu_port_lanes.restype = ctypes.c_int
+        lib.cpu_port_v2_lanes.restype = ctypes.c_int
+        lib.cpu_port_search_batch.restype = ctypes.c_size_t
+        lib.cpu_port_search_batch.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p,
+                                              ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double)]
         _LIB = lib
     return _LIB
 
@@ -85,3 +91,31 @@ def calibrate(alphabet: str, patterns: Sequence[bytes], k: int, rc: bool) -> flo
     _, sec = search_ends(alphabet, p, text, n, k, rc, False, 1)
     _, sec = search_ends(alphabet, p, text, n, k, rc, False, 1)
     return n / max(sec, 1e-6)
+
+
+def search_batch(patterns: Sequence[bytes], text, n: int, k: int, all_minima: bool = False, trace: bool = True,
+                 prefilter: bool = True, threads: int = 1, cap: int = 1 << 22):
+    """v2 engine (pattern tiling, forward strand, Iupac): [(pattern index, end, cost, text_start)], seconds."""
+    import numpy as np
+    lib = _lib()
+    m = len(patterns[0])
+    assert all(len(p) == m for p in patterns) and m <= 32
+    pat = np.zeros(cap, dtype=np.uint32)
+    pos = np.zeros(cap, dtype=np.uint64)
+    cost = np.zeros(cap, dtype=np.int32)
+    start = np.zeros(cap, dtype=np.uint64)
+    sec = ctypes.c_double()
+    addr = ctypes.cast(ctypes.c_char_p(text), ctypes.c_void_p) if isinstance(text, bytes) else ctypes.c_void_p(text)
+    total = lib.cpu_port_search_batch(b"".join(patterns), len(patterns), m, addr, n, k, int(all_minima), int(trace),
+                                      int(prefilter), threads, pat.ctypes.data, pos.ctypes.data, cost.ctypes.data,
+                                      start.ctypes.data, cap, ctypes.byref(sec))
+    if total > cap:
+        return search_batch(patterns, text, n, k, all_minima, trace, prefilter, threads, cap=int(total) + 16)
+    got = int(total)
+    return list(zip(pat[:got].tolist(), pos[:got].tolist(), cost[:got].tolist(), start[:got].tolist())), sec.value
+
+
+def kind_v2(threads: int, k: int, m: int) -> str:
+    pf = ", 16-character suffix prefilter in u16 lanes" if 1 <= k <= 3 and m > 16 else ""
+    return (f"C restatement of Sassy v2 (pattern_tiling/search.rs: u32x{_lib().cpu_port_v2_lanes()} pattern lanes{pf}) "
+            f"+ traceback, {threads} threads")

@@ -481,3 +481,373 @@ size_t cpu_port_search(int profile, const uint8_t *pattern, int m, const uint8_t
 }
 
 int cpu_port_lanes(void) { return LANES; }
+
+/* =====================================================================================
+ * v2: the pattern-tiled engine for batches of equal-length patterns (BASELINE configs 3, 5).
+ *
+ * Restates (reference file:line):
+ *   - TQueries: one equality vector per text symbol, patterns across SIMD lanes
+ *                                              src/pattern_tiling/tqueries.rs:53-134
+ *   - search_ranges / myers_step: per text character and lane block
+ *       xh = (((eq & vp) + vp) ^ vp) | eq;  mh = vp & xh;  ph = vn | ~(xh | vp);  xv = eq | vn;
+ *       vp' = (mh << 1) | ~(xv | (ph << 1));  vn' = (ph << 1) & xv;  cost += ph[m-1] - mh[m-1]
+ *     lanes with cost <= k are hits                   src/pattern_tiling/search.rs:148-175,326-407
+ *   - lane width by pattern length (u32 for m <= 32, u16 for m <= 16)
+ *                                              src/pattern_tiling/backend.rs, general.rs:247-292
+ *   - hierarchical suffix prefilter: for 1 <= k <= 3 and m > 16 the 16-character SUFFIX of every
+ *     pattern is searched first in u16 lanes (twice the patterns per register); only where the
+ *     suffix has cost <= k is the full pattern evaluated    general.rs:60-102,294-313
+ *   - end positions per pattern -> run-based local-minima rule   src/pattern_tiling/minima.rs:9-52
+ * The reference gathers maximal ranges of hit positions and re-runs a forward pass with history per
+ * range for the traceback; here every hit position is recorded with its cost and the traceback
+ * below (trace_start) is run per reported match.  Forward strand only (bench.py's default, as the
+ * reference's evals); Iupac profile.
+ * Work split: 32-pattern x text-piece tasks over the threads, pieces with (m + k) overlap -- the
+ * shape of the reference's own benchmark driver (evals/src/benchsuite/bench.rs:244-299).
+ */
+#if defined(__AVX512F__) && defined(__AVX512BW__)
+#define V2_BYTES 64
+#else
+#define V2_BYTES 32
+#endif
+typedef uint32_t v32 __attribute__((vector_size(V2_BYTES)));
+typedef int32_t s32 __attribute__((vector_size(V2_BYTES)));
+typedef uint16_t v16 __attribute__((vector_size(V2_BYTES)));
+typedef int16_t s16 __attribute__((vector_size(V2_BYTES)));
+#define L32 (V2_BYTES / 4)
+#define L16 (V2_BYTES / 2)
+
+/* lanes with a <= b as a bit mask (one movemask instead of a lane loop) */
+static inline uint64_t le_mask32(s32 a, s32 b) {
+#if V2_BYTES == 64
+  return (uint64_t)_mm512_cmple_epi32_mask((__m512i)a, (__m512i)b);
+#elif defined(__AVX2__)
+  return (uint64_t)(uint32_t)_mm256_movemask_ps((__m256)~_mm256_cmpgt_epi32((__m256i)a, (__m256i)b)) & 0xFFu;
+#else
+  uint64_t r = 0;
+  for (int l = 0; l < L32; l++) r |= (uint64_t)(a[l] <= b[l]) << l;
+  return r;
+#endif
+}
+static inline uint64_t le_mask16(s16 a, s16 b) {
+#if V2_BYTES == 64
+  return (uint64_t)_mm512_cmple_epi16_mask((__m512i)a, (__m512i)b);
+#elif defined(__AVX2__)
+  const uint32_t bytes = (uint32_t)_mm256_movemask_epi8(~_mm256_cmpgt_epi16((__m256i)a, (__m256i)b));
+  return (uint64_t)_pext_u32(bytes, 0x55555555u);
+#else
+  uint64_t r = 0;
+  for (int l = 0; l < L16; l++) r |= (uint64_t)(a[l] <= b[l]) << l;
+  return r;
+#endif
+}
+
+typedef struct {
+  uint32_t pat;
+  uint64_t pos;
+  int32_t cost;
+} Hit2;
+typedef struct {
+  Hit2 *h;
+  size_t n, cap;
+} HitList;
+static void hit_push(HitList *l, uint32_t pat, uint64_t pos, int32_t cost) {
+  if (l->n == l->cap) {
+    l->cap = l->cap ? l->cap * 2 : 1024;
+    l->h = (Hit2 *)realloc(l->h, l->cap * sizeof(Hit2));
+  }
+  l->h[l->n].pat = pat, l->h[l->n].pos = pos, l->h[l->n].cost = cost;
+  l->n++;
+}
+
+static inline uint32_t iupac_eq_word(const uint8_t *p, int m, int sym /* text byte & 31 */) {
+  uint32_t w = 0;
+  const uint8_t tc = IUPAC_CODE[sym] == 255 ? 0x0F : (IUPAC_CODE[sym] & 0x0F); /* non-letters act as N */
+  for (int j = 0; j < m; j++)
+    if (IUPAC_CODE[p[j] & 31] & tc) w |= 1u << j;
+  return w;
+}
+
+/* Scalar full-pattern pass over t[from, to): end positions e in (own_from, to] with cost <= k. */
+static void v2_scalar_window(const uint32_t *peq /*[32]*/, int m, int k, const uint8_t *t, size_t from, size_t to,
+                             size_t own_from, uint32_t pat, HitList *out) {
+  uint32_t vp = ~0u, vn = 0;
+  int cost = m;
+  const uint32_t top = 1u << (m - 1);
+  for (size_t i = from; i < to; i++) {
+    const uint32_t eq = peq[t[i] & 31];
+    const uint32_t xh = (((eq & vp) + vp) ^ vp) | eq;
+    const uint32_t mh = vp & xh, ph = vn | ~(xh | vp), xv = eq | vn;
+    cost += ((ph & top) != 0) - ((mh & top) != 0);
+    vp = (mh << 1) | ~(xv | (ph << 1));
+    vn = (ph << 1) & xv;
+    if (cost <= k && i + 1 > own_from) hit_push(out, pat, i + 1, cost);
+  }
+}
+
+typedef struct {
+  const uint8_t *pats; /* P x m */
+  int m, k;
+  uint32_t p0, p1;     /* patterns [p0, p1) */
+  const uint8_t *text;
+  size_t n, from, to;  /* owns end positions in (from, to] */
+  int prefilter;
+  HitList out;
+} Job2;
+
+static void *job2_main(void *arg) {
+  Job2 *jb = (Job2 *)arg;
+  const int m = jb->m, k = jb->k;
+  const size_t halo = (size_t)m + (size_t)k;
+  const size_t s = jb->from > halo ? jb->from - halo : 0;
+  const uint32_t np = jb->p1 - jb->p0;
+  /* scalar eq words of the full patterns (verification / narrow path) */
+  uint32_t *peq = (uint32_t *)malloc((size_t)np * 32 * sizeof(uint32_t));
+  for (uint32_t q = 0; q < np; q++)
+    for (int sym = 0; sym < 32; sym++) peq[(size_t)q * 32 + sym] = iupac_eq_word(jb->pats + (size_t)(jb->p0 + q) * m, m, sym);
+  if (jb->prefilter && m > 16) {
+    /* pass 1: 16-character suffixes in u16 lanes */
+    const int ms = 16;
+    const uint32_t nb = (np + L16 - 1) / L16;
+    v16 *eqv = (v16 *)aligned_alloc(64, sizeof(v16) * 32 * nb);
+    for (int sym = 0; sym < 32; sym++)
+      for (uint32_t b = 0; b < nb; b++) {
+        v16 e = {0};
+        for (int l = 0; l < L16; l++) {
+          const uint32_t q = b * L16 + (uint32_t)l;
+          if (q < np) e[l] = (uint16_t)(peq[(size_t)q * 32 + sym] >> (m - ms));
+        }
+        eqv[(size_t)sym * nb + b] = e;
+      }
+    v16 *vp = (v16 *)aligned_alloc(64, sizeof(v16) * nb), *vn = (v16 *)aligned_alloc(64, sizeof(v16) * nb);
+    s16 *cost = (s16 *)aligned_alloc(64, sizeof(s16) * nb);
+    for (uint32_t b = 0; b < nb; b++) vp[b] = (v16){0} - 1, vn[b] = (v16){0}, cost[b] = (s16){0} + (int16_t)ms;
+    const s16 kk = (s16){0} + (int16_t)k;
+    /* per pattern: end of the last verified window, so that overlapping windows are scanned once */
+    size_t *done = (size_t *)calloc(np, sizeof(size_t));
+    for (size_t i = s; i < jb->to; i++) {
+      const v16 *e = eqv + (size_t)(jb->text[i] & 31) * nb;
+      for (uint32_t b = 0; b < nb; b++) {
+        const v16 eq = e[b], p = vp[b], nn = vn[b];
+        const v16 xh = (((eq & p) + p) ^ p) | eq;
+        const v16 mh = p & xh, ph = nn | ~(xh | p), xv = eq | nn;
+        cost[b] += (s16)(ph >> (ms - 1)) - (s16)(mh >> (ms - 1));
+        vp[b] = (mh << 1) | ~(xv | (ph << 1));
+        vn[b] = (ph << 1) & xv;
+        uint64_t lem = le_mask16(cost[b], kk);
+        if (!lem || i + 1 <= jb->from) continue;
+        for (; lem; lem &= lem - 1) {
+          const int l = __builtin_ctzll(lem);
+          const uint32_t q = b * L16 + (uint32_t)l;
+          if (q >= np) continue;
+          /* the full pattern can only end here with cost <= k: evaluate it on this end position
+           * (window of m + k characters; consecutive hit positions extend the same window) */
+          const size_t e1 = i + 1;
+          if (done[q] >= e1) continue;
+          size_t wfrom = e1 > halo ? e1 - halo : 0;
+          size_t own = e1 - 1;
+          if (done[q] > own) own = done[q];
+          /* extend over the run of positions the suffix filter will report next (cheap look-ahead is
+           * not available: verify position by position, sharing the warm-up through `done`) */
+          v2_scalar_window(peq + (size_t)q * 32, m, k, jb->text, wfrom, e1, own > jb->from ? own : jb->from,
+                           jb->p0 + q, &jb->out);
+          done[q] = e1;
+        }
+      }
+    }
+    free(done);
+    free(eqv), free(vp), free(vn), free(cost);
+  } else {
+    const uint32_t nb = (np + L32 - 1) / L32;
+    v32 *eqv = (v32 *)aligned_alloc(64, sizeof(v32) * 32 * nb);
+    for (int sym = 0; sym < 32; sym++)
+      for (uint32_t b = 0; b < nb; b++) {
+        v32 e = {0};
+        for (int l = 0; l < L32; l++) {
+          const uint32_t q = b * L32 + (uint32_t)l;
+          if (q < np) e[l] = peq[(size_t)q * 32 + sym];
+        }
+        eqv[(size_t)sym * nb + b] = e;
+      }
+    v32 *vp = (v32 *)aligned_alloc(64, sizeof(v32) * nb), *vn = (v32 *)aligned_alloc(64, sizeof(v32) * nb);
+    s32 *cost = (s32 *)aligned_alloc(64, sizeof(s32) * nb);
+    for (uint32_t b = 0; b < nb; b++) vp[b] = (v32){0} - 1, vn[b] = (v32){0}, cost[b] = (s32){0} + m;
+    const s32 kk = (s32){0} + k;
+    for (size_t i = s; i < jb->to; i++) {
+      const v32 *e = eqv + (size_t)(jb->text[i] & 31) * nb;
+      for (uint32_t b = 0; b < nb; b++) {
+        const v32 eq = e[b], p = vp[b], nn = vn[b];
+        const v32 xh = (((eq & p) + p) ^ p) | eq;
+        const v32 mh = p & xh, ph = nn | ~(xh | p), xv = eq | nn;
+        cost[b] += (s32)((ph >> (m - 1)) & 1) - (s32)((mh >> (m - 1)) & 1);
+        vp[b] = (mh << 1) | ~(xv | (ph << 1));
+        vn[b] = (ph << 1) & xv;
+        uint64_t lem = le_mask32(cost[b], kk);
+        if (!lem || i + 1 <= jb->from) continue;
+        for (; lem; lem &= lem - 1) {
+          const int l = __builtin_ctzll(lem);
+          if (b * L32 + (uint32_t)l < np) hit_push(&jb->out, jb->p0 + b * L32 + (uint32_t)l, i + 1, cost[b][l]);
+        }
+      }
+    }
+    free(eqv), free(vp), free(vn), free(cost);
+  }
+  free(peq);
+  return NULL;
+}
+
+/* Traceback start of the match ending at `end` (reference src/trace.rs:273-406 on the window of
+ * m + k characters, src/search.rs:1477-1478): scalar DP + the greedy walk, Iupac matching.
+ * Returns text_start. */
+static size_t trace_start_iupac(const uint8_t *p, int m, int k, const uint8_t *t, size_t end) {
+  const size_t fill = (size_t)m + (size_t)k;
+  const size_t off = end > fill ? end - fill : 0;
+  const int w = (int)(end - off);
+  static __thread int *D = NULL;
+  static __thread size_t Dcap = 0;
+  const size_t need = (size_t)(m + 1) * (size_t)(w + 1);
+  if (need > Dcap) {
+    D = (int *)realloc(D, need * sizeof(int));
+    Dcap = need;
+  }
+#define DD(j, i) D[(size_t)(j) * (size_t)(w + 1) + (size_t)(i)]
+  for (int i = 0; i <= w; i++) DD(0, i) = 0;
+  for (int j = 1; j <= m; j++) {
+    DD(j, 0) = j;
+    const uint8_t pc = IUPAC_CODE[p[j - 1] & 31];
+    for (int i = 1; i <= w; i++) {
+      const uint8_t c = IUPAC_CODE[t[off + (size_t)i - 1] & 31];
+      const uint8_t tc = c == 255 ? 0x0F : (c & 0x0F);
+      const int mt = (pc & tc) != 0;
+      int v = DD(j - 1, i - 1) + !mt;
+      if (DD(j - 1, i) + 1 < v) v = DD(j - 1, i) + 1;
+      if (DD(j, i - 1) + 1 < v) v = DD(j, i - 1) + 1;
+      DD(j, i) = v;
+    }
+  }
+  int j = m, i = w, g = DD(m, w);
+  while (j > 0) {
+    const uint8_t pc = IUPAC_CODE[p[j - 1] & 31];
+    uint8_t tc = 0;
+    if (i > 0) {
+      const uint8_t c = IUPAC_CODE[t[off + (size_t)i - 1] & 31];
+      tc = c == 255 ? 0x0F : (c & 0x0F);
+    }
+    if (i > 0 && DD(j - 1, i - 1) == g && (pc & tc)) {
+      j--, i--;
+    } else {
+      g -= 1;
+      if (i > 0 && DD(j - 1, i - 1) == g) j--, i--;
+      else if (i > 0 && DD(j, i - 1) == g) i--;
+      else if (DD(j - 1, i) == g) j--;
+      else break;
+    }
+  }
+#undef DD
+  return off + (size_t)i;
+}
+
+typedef struct {
+  Job2 *jobs;
+  size_t ntasks;
+  size_t *next;
+  pthread_mutex_t *mu;
+} Pool2;
+
+static void *pool2_worker(void *arg) {
+  Pool2 *pl = (Pool2 *)arg;
+  for (;;) {
+    pthread_mutex_lock(pl->mu);
+    const size_t t = (*pl->next)++;
+    pthread_mutex_unlock(pl->mu);
+    if (t >= pl->ntasks) return NULL;
+    job2_main(&pl->jobs[t]);
+  }
+}
+
+static int hit_cmp(const void *a, const void *b) {
+  const Hit2 *x = (const Hit2 *)a, *y = (const Hit2 *)b;
+  if (x->pat != y->pat) return x->pat < y->pat ? -1 : 1;
+  if (x->pos != y->pos) return x->pos < y->pos ? -1 : 1;
+  return 0;
+}
+
+/* Public: search_encoded_patterns (forward strand) of P equal-length Iupac patterns (m <= 32).
+ * all = 0: local minima per pattern; trace = 1: also compute text_start of every reported match.
+ * Writes up to cap (pattern, end, cost, start) records; returns the total.  prefilter: 1 = the
+ * reference's rule (suffix filter for 1 <= k <= 3, m > 16), 0 = never. */
+size_t cpu_port_search_batch(const uint8_t *patterns, uint32_t n_patterns, int m, const uint8_t *text, size_t n, int k,
+                             int all, int trace, int prefilter, int threads, uint32_t *out_pat, uint64_t *out_pos,
+                             int32_t *out_cost, uint64_t *out_start, size_t cap, double *seconds) {
+  init_tables();
+  if (m < 1 || m > 32 || n_patterns == 0) return 0;
+  const double t0 = now_s();
+  if (threads < 1) threads = 1;
+  const int use_pf = prefilter && k >= 1 && k <= 3 && m > 16;
+  /* tasks: 32-pattern chunks x text pieces (evals/src/benchsuite/bench.rs:244-299) */
+  const uint32_t chunk = 32 > L16 ? 32 : L16;
+  const uint32_t nchunks = (n_patterns + chunk - 1) / chunk;
+  size_t pieces = ((size_t)threads * 4 + nchunks - 1) / nchunks;
+  if (pieces < 1) pieces = 1;
+  if (pieces > n / (1 << 20) + 1) pieces = n / (1 << 20) + 1;
+  const size_t ntasks = (size_t)nchunks * pieces;
+  Job2 *jobs = (Job2 *)calloc(ntasks, sizeof(Job2));
+  for (uint32_t c = 0; c < nchunks; c++)
+    for (size_t pc = 0; pc < pieces; pc++) {
+      Job2 *jb = &jobs[(size_t)c * pieces + pc];
+      jb->pats = patterns, jb->m = m, jb->k = k;
+      jb->p0 = c * chunk, jb->p1 = (c + 1) * chunk < n_patterns ? (c + 1) * chunk : n_patterns;
+      jb->text = text, jb->n = n;
+      jb->from = n * pc / pieces, jb->to = n * (pc + 1) / pieces;
+      jb->prefilter = use_pf;
+    }
+  /* a pool of `threads` workers pulling tasks */
+  size_t next = 0;
+  pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  Pool2 pool = {jobs, ntasks, &next, &mu};
+  pthread_t *th = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+  for (int i = 1; i < threads; i++) pthread_create(&th[i], NULL, pool2_worker, &pool);
+  pool2_worker(&pool);
+  for (int i = 1; i < threads; i++) pthread_join(th[i], NULL);
+  free(th);
+  size_t total_hits = 0;
+  for (size_t t = 0; t < ntasks; t++) total_hits += jobs[t].out.n;
+  Hit2 *hits = (Hit2 *)malloc((total_hits ? total_hits : 1) * sizeof(Hit2));
+  size_t o = 0;
+  for (size_t t = 0; t < ntasks; t++) {
+    memcpy(hits + o, jobs[t].out.h, jobs[t].out.n * sizeof(Hit2));
+    o += jobs[t].out.n;
+    free(jobs[t].out.h);
+  }
+  free(jobs);
+  qsort(hits, total_hits, sizeof(Hit2), hit_cmp);
+  /* de-duplicate (overlapping verification windows), then the run-based rule per pattern */
+  size_t nh = 0;
+  for (size_t a = 0; a < total_hits; a++)
+    if (nh == 0 || hits[nh - 1].pat != hits[a].pat || hits[nh - 1].pos != hits[a].pos) hits[nh++] = hits[a];
+  size_t total = 0;
+  for (size_t a = 0; a < nh;) {
+    size_t b = a;
+    while (b < nh && hits[b].pat == hits[a].pat) b++;
+    size_t cnt = b - a;
+    Cand *c = (Cand *)malloc(cnt * sizeof(Cand));
+    for (size_t x = 0; x < cnt; x++) c[x].pos = hits[a + x].pos, c[x].cost = hits[a + x].cost;
+    if (!all) cnt = select_minima(c, cnt);
+    for (size_t x = 0; x < cnt; x++) {
+      if (total < cap) {
+        out_pat[total] = hits[a].pat;
+        out_pos[total] = c[x].pos;
+        out_cost[total] = c[x].cost;
+        out_start[total] = trace ? trace_start_iupac(patterns + (size_t)hits[a].pat * m, m, k, text, c[x].pos) : 0;
+      }
+      total++;
+    }
+    free(c);
+    a = b;
+  }
+  free(hits);
+  if (seconds) *seconds = now_s() - t0;
+  return total;
+}
+
+int cpu_port_v2_lanes(void) { return L32; }

@@ -919,11 +919,17 @@ SB_HD int delta_at(uint32_t p, uint32_t mn, int bit) { return (int)((p >> bit) &
 // window starting at `off`): '=' > 'X' > 'D' (text only) > 'I' (pattern only).
 template <int P>
 SB_HD void trace_walk(const uint8_t* text, uint64_t n, bool rev, const uint8_t* pattern, int m, int W, uint64_t off,
-                      uint32_t wlen, uint64_t end, const ColStore& cs, uint32_t* ops, uint32_t ops_words,
+                      uint32_t wlen, uint64_t end, const ColStore& cs, uint32_t* ops_out, uint32_t ops_words,
                       TraceOut& out) {
   const int pad = 32 * W - m;
   const int F = trace_fields(W);
   const bool wide = F == 4;
+  // The op codes are built (and reversed) in a local buffer and written out once: `ops_out` may be
+  // pinned host memory (the single-synchronisation tail writes results over PCIe), where every
+  // read-modify-write of a word would cost a round trip.
+  constexpr uint32_t kLocalOpsWords = 80;  // 1280 ops: any m + k the wide kernels accept
+  uint32_t local_ops[kLocalOpsWords];
+  uint32_t* const ops = ops_words <= kLocalOpsWords ? local_ops : ops_out;
   for (uint32_t w = 0; w < ops_words; w++) ops[w] = 0;
   // D[j][i] for the narrow layout: column 0 is j, row 0 is 0, else the sum of the vertical deltas
   auto cost = [&](int j, uint32_t i) -> int {
@@ -1007,6 +1013,8 @@ SB_HD void trace_walk(const uint8_t* text, uint64_t n, bool rev, const uint8_t* 
     ops[a >> 4] = (ops[a >> 4] & ~(3u << ((a & 15) * 2))) | (ob << ((a & 15) * 2));
     ops[(b - 1) >> 4] = (ops[(b - 1) >> 4] & ~(3u << (((b - 1) & 15) * 2))) | (oa << (((b - 1) & 15) * 2));
   }
+  if (ops != ops_out)
+    for (uint32_t w = 0; w < ops_words; w++) ops_out[w] = ops[w];
   out.text_start = off + i;
   out.text_end = end;
   out.nops = nops;
@@ -1163,6 +1171,10 @@ SB_HD void trace_one_ov(const uint8_t* text, uint64_t n, bool rev, const uint8_t
     }
     return v;
   };
+  constexpr uint32_t kLocalOpsWords = 80;
+  uint32_t local_ops[kLocalOpsWords];
+  uint32_t* const ops_out = ops;
+  if (ops_words <= kLocalOpsWords) ops = local_ops;
   for (uint32_t w = 0; w < ops_words; w++) ops[w] = 0;
   int j = m;
   uint32_t i = wlen;
@@ -1218,6 +1230,8 @@ SB_HD void trace_one_ov(const uint8_t* text, uint64_t n, bool rev, const uint8_t
     ops[a >> 4] = (ops[a >> 4] & ~(3u << ((a & 15) * 2))) | (ob << ((a & 15) * 2));
     ops[(b - 1) >> 4] = (ops[(b - 1) >> 4] & ~(3u << (((b - 1) & 15) * 2))) | (oa << (((b - 1) & 15) * 2));
   }
+  if (ops != ops_out)
+    for (uint32_t w = 0; w < ops_words; w++) ops_out[w] = ops[w];
   out.cost = total;
   out.text_start = off + i;
   out.text_end = off + slice;

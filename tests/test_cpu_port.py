@@ -52,3 +52,38 @@ def test_cpu_port_threads():
     assert one == four and len(one) >= 50
     want = ends_of(oracle.search("dna", p, t, k, rc=True), n)
     assert one == want
+
+
+@pytest.mark.parametrize("prefilter", [True, False])
+def test_cpu_port_v2_equals_oracle(prefilter):
+    """The pattern-tiled CPU baseline (u32 lanes, u16 suffix prefilter for 1 <= k <= 3) reports the
+    oracle's end positions, costs and traced start positions of search_encoded_patterns."""
+    rng = random.Random(41)
+    for it in range(60):
+        m = rng.choice([17, 20, 23, 32, 8, 16])
+        n = rng.randrange(1, 3000)
+        k = rng.randrange(0, 5)
+        P = rng.randrange(1, 70)
+        pats = []
+        t = bytearray(rand_text(rng, n))
+        for _ in range(P):
+            p = bytes(rng.choice(b"ACGT") for _ in range(m - 3)) + (b"NGG" if rng.random() < 0.7 else b"ACG")
+            pats.append(p)
+            q = bytearray(p.replace(b"N", b"A"))
+            for _ in range(rng.randrange(0, k + 1)):
+                q[rng.randrange(len(q))] = rng.choice(b"ACGT")
+            pos = rng.randrange(0, max(1, n - m))
+            t[pos:pos + len(q)] = q
+        if rng.random() < 0.3:
+            t = bytearray(c if rng.random() > 0.03 else ord(rng.choice("NRYK")) for c in t)
+        t = bytes(t[:n])
+        for allm in (False, True):
+            want = sorted((x.pattern_idx, x.text_end, x.cost, x.text_start)
+                          for x in oracle.search_encoded("iupac", pats, t, k, rc=False, all_minima=allm))
+            got, _ = cpu_port.search_batch(pats, t, len(t), k, all_minima=allm, prefilter=prefilter,
+                                           threads=rng.choice([1, 3]))
+            assert sorted(got) == want, (pats, t, k, allm)
+
+
+def rand_text(rng, n):
+    return bytes(rng.choice(b"ACGT") for _ in range(n))

@@ -4,7 +4,7 @@
 #   tools/profile_r02.sh launches c2 c4 ...      tools/profile_r02.sh full <kernel regex> <workload> <out name>
 cd "$(dirname "$0")/.."
 B="python bench.py --sub none --no-e2e --no-cpu --no-check --steps 2 --warmup 1"
-OURS='regex:qgram|filter_kernel|verify|confirm|scan|trace|post_small|minima|push_kernel|collect_kernel|unpack|texts_kernel|overhang|best|DeviceRadixSort|DeviceSelect|DeviceCompact|DeviceScan|suffix'
+OURS='regex:qgram|filter_kernel|verify|refine|scan|trace|post_small|minima|push_kernel|collect_kernel|unpack|texts_kernel|overhang|best|DeviceRadixSort|DeviceSelect|DeviceCompact|DeviceScan|suffix'
 mode=$1; shift
 if [ "$mode" = launches ]; then
   for w in "$@"; do
