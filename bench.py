@@ -75,6 +75,9 @@ def parse_args():
     ap.add_argument("--rc", action="store_true", help="search both strands (default: forward only, as the reference's evals)")
     ap.add_argument("--transport", default="packed", choices=["packed", "bytes"],
                     help="host->device transport of Dna texts in the e2e leg (2 bits per character, or bytes)")
+    ap.add_argument("--exchange", default="pipelined", choices=["pipelined", "lockstep"],
+                    help="N > 1, text-sharded top level: collect the peers' records one search behind (default) or "
+                         "wait for them inside every step")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: fused peer-memory exchange of the match records (default) or NCCL all-gather")
     ap.add_argument("--no-e2e", action="store_true")
@@ -579,16 +582,18 @@ def main():
 
     pgs = {}
 
-    def peer_gather(s, max_ops):
-        key = (id(s), max_ops)
+    def peer_gather(s, max_ops, pipelined=False):
+        key = (id(s), max_ops, pipelined)
         if key not in pgs:
-            pgs[key] = sdist.PeerGather.create_or_none(s, max_ops=max_ops, device=dev) \
+            pgs[key] = sdist.PeerGather.create_or_none(s, max_ops=max_ops, device=dev, pipelined=pipelined) \
                 if (world > 1 and args.gather == "peer") else None
         return pgs[key]
 
     launches_total = [0]
 
-    def timed(fn, s, steps, warmup):
+    def timed(fn, s, steps, warmup, finish=None):
+        """finish: pipelined exchange -- fn() returns the result of the previous call, finish() the
+        last one; it runs inside the timed region, so every timed search delivers its result there."""
         for _ in range(warmup):
             ms = fn()
         barrier()
@@ -606,6 +611,8 @@ def main():
             scan_ms.append(st["scan_ms"])
             total_ms.append(st["total_ms"])
             launches += st["scan_launches"] + st["aux_launches"]
+        if finish is not None:
+            ms = finish()
         barrier()
         el = max_over_ranks(time.perf_counter() - t0)
         launches_total[0] += launches
@@ -663,7 +670,9 @@ def main():
         enc = s.encode_patterns(pats) if batch else None
         dt = dt_window if tshard else text0_for(profile)
         n_text = n_global if tshard else n
-        pg = peer_gather(s, m + k + 1) if (pshard or tshard) else None
+        pipelined = tshard and args.exchange == "pipelined"
+        pg = peer_gather(s, m + k + 1, pipelined) if (pshard or tshard) else None
+        pipelined = pipelined and pg is not None
 
         def step_resident():
             if tshard:
@@ -675,7 +684,8 @@ def main():
                 ms = sdist.gather_matches(sdist.tag_rank(ms, rank), max_ops=m + k + 1, device=dev)
             return ms
 
-        r = timed(step_resident, s, steps, warmup)
+        r = timed(step_resident, s, steps, warmup,
+                  finish=(lambda: pg.flush_sharded(m, layout, n_global)) if pipelined else None)
         st = r["stats"]
         matches = r["matches"]
         ms_per_step = r["el"] / steps * 1e3
@@ -708,8 +718,10 @@ def main():
         if tshard:
             rec["sharding"] = ("ONE text of %d bytes cut into %d slabs with (m+k) halos; per-slab search_all, records "
                                "exchanged by %s, local-minima rule on the merged list" %
-                               (n_global, world, ("peer-memory stores over NVLink fused behind the traceback (%d NCCL "
-                                                  "fall-backs)" % pg.fallbacks) if pg is not None else "an NCCL all-gather"))
+                               (n_global, world, ("peer-memory stores over NVLink fused behind the traceback (%s, %d NCCL "
+                                                  "fall-backs)" % ("collected one search behind" if pipelined else
+                                                                   "lock step", pg.fallbacks))
+                                if pg is not None else "an NCCL all-gather"))
 
         # ---- parity inside the run -------------------------------------------------------------
         checks = {}

@@ -223,6 +223,18 @@ sassy_gpu_Result *sassy_gpu_search_text_sharded(sassy_SearcherType *searcher, sa
                                                 const sassy_gpu_Text *window, size_t k, int all,
                                                 const sassy_gpu_Slab *slabs, size_t n_slabs, uint64_t n_global,
                                                 int *complete);
+/* Pipelined exchange (set on every rank before the first gathered search): a gathered search of
+ * step s pushes its records and collects those of step s - 1, which the peers pushed a whole search
+ * earlier -- the wait for the slowest rank leaves the step, the ranks may drift one step apart.  The
+ * *_gathered / text_sharded calls then return the result of the PREVIOUS call (*complete = 2 and an
+ * empty result on the first call), and sassy_gpu_text_sharded_flush returns the last one (*state = 1;
+ * 2 = nothing pending).  A result that does not fit a rank's slot is an error in this mode (NULL):
+ * use the lock-step mode for result sets beyond cap_records per rank. */
+int sassy_gpu_gather_set_pipelined(sassy_gpu_Gather *gather, int on);
+int sassy_gpu_gather_has_result(const sassy_gpu_Gather *gather);
+sassy_gpu_Result *sassy_gpu_text_sharded_flush(sassy_SearcherType *searcher, sassy_gpu_Gather *gather,
+                                               size_t pattern_len, int all, const sassy_gpu_Slab *slabs,
+                                               size_t n_slabs, uint64_t n_global, int *state);
 sassy_gpu_Result *sassy_gpu_merge_slabs(const sassy_gpu_Match *records, size_t n_records, const char *ops,
                                         const sassy_gpu_Slab *slabs, size_t n_slabs, uint64_t n_global, int all);
 

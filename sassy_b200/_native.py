@@ -131,6 +131,10 @@ SIGNATURES = {
                                                      ctypes.POINTER(ctypes.c_int)]),
     "sassy_gpu_search_text_sharded": (c_void_p, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, ctypes.c_int,
                                                 c_void_p, c_size_t, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int)]),
+    "sassy_gpu_gather_set_pipelined": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "sassy_gpu_gather_has_result": (ctypes.c_int, [c_void_p]),
+    "sassy_gpu_text_sharded_flush": (c_void_p, [c_void_p, c_void_p, c_size_t, ctypes.c_int, c_void_p, c_size_t,
+                                               ctypes.c_uint64, ctypes.POINTER(ctypes.c_int)]),
     "sassy_gpu_merge_slabs": (c_void_p, [c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, ctypes.c_uint64,
                                         ctypes.c_int]),
     "sassy_gpu_result_len": (c_size_t, [c_void_p]),

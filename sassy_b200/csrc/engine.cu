@@ -721,6 +721,17 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   };
   // after the synchronisation that follows a tail: did every rank deliver a complete result?
   auto pg_check = [&]() {
+    if (pg && pg_pushed && pg->pipelined()) {
+      // pipelined exchange: the host mirror holds the PREVIOUS step (Searcher reads it); whether
+      // this step's own records are complete in the slot follows from the counters
+      if (pg->has_result() && pg->timed_out()) {
+        pg->mark_broken();
+        throw CudaError("peer gather timed out (SASSY_B200_GATHER_TIMEOUT_S): a rank did not reach the previous search");
+      }
+      gather_ok_ = small_in_slot && h_counts[3] == 0 && h_counts[0] <= a.cand_cap &&
+                   (!(fp.enabled || qgram) || h_counts[2] <= hit_cap_) && h_counts[1] <= pg->cap();
+      return gather_ok_;
+    }
     if (!pg || !pg_pushed || gather_ok_) return gather_ok_;
     if (pg->timed_out()) {
       pg->mark_broken();
@@ -953,7 +964,9 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     nsel = h_counts[1];
     const GpuMatch* src_m = h_small_out;
     const uint32_t* src_ops = h_small_ops;
-    if (small_in_slot) {  // the collect kernel mirrored this rank's slot into pinned host memory
+    if (small_in_slot && pg->pipelined()) {
+      nsel = 0;  // this step's records stay in the device slot; they reach the host with the next collect
+    } else if (small_in_slot) {  // the collect kernel mirrored this rank's slot into pinned host memory
       const PeerGather::Slot sl = pg->slot(pg->rank());
       src_m = sl.records;
       src_ops = sl.ops;
@@ -983,6 +996,16 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     stats_.transfer_ms = transfer_ms_;
     stats_.transfer_packed = transfer_packed_ ? 1 : 0;
     stats_.transfer_bytes = transfer_bytes_;
+  }
+}
+
+void Engine::flush_gather(PeerGather& pg) {
+  SB_CUDA(cudaSetDevice(device_));
+  SB_CUDA(pg.flush(stream_));
+  SB_CUDA(cudaStreamSynchronize(stream_));
+  if (pg.has_result() && pg.timed_out()) {
+    pg.mark_broken();
+    throw CudaError("peer gather timed out (SASSY_B200_GATHER_TIMEOUT_S) while flushing the pipeline");
   }
 }
 

@@ -136,6 +136,8 @@ class Engine {
   // holds the local result and the caller falls back to its own collective.
   void set_gather(PeerGather* pg, uint64_t user) { pg_ = pg, pg_user_ = user; }
   bool gather_ok() const { return gather_ok_; }
+  // Pipelined PeerGather: collect the last pushed step into the host mirror (one synchronisation).
+  void flush_gather(PeerGather& pg);
 
   const SearchStats& stats() const { return stats_; }
   void set_variant(int v) { variant_ = v; }

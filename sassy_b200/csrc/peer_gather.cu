@@ -224,10 +224,38 @@ uint8_t* PeerGather::local_records(size_t* ops_offset) {
   return slot + sizeof(SlotHeader);
 }
 
+cudaError_t PeerGather::collect(unsigned long long step, cudaStream_t stream) {
+  const size_t parity_off = (step & 1) * (size_t)world_ * slot_bytes_;
+  CollectArgs c;
+  memset(&c, 0, sizeof c);
+  c.local = local_;
+  c.host = host_;
+  c.world = (uint32_t)world_;
+  c.slot_bytes = slot_bytes_;
+  c.parity_off = parity_off;
+  c.flags_off = flags_off_ + (step & 1) * (size_t)world_ * sizeof(unsigned long long);
+  c.cap = cap_;
+  c.step = step;
+  c.timeout_ns = timeout_ns_;
+  collect_kernel<<<world_, 256, 0, stream>>>(c);
+  collected_step_ = step;
+  return cudaGetLastError();
+}
+
+cudaError_t PeerGather::flush(cudaStream_t stream) {
+  if (!pipelined_ || step_ == 0 || collected_step_ == step_) return cudaSuccess;
+  return collect(step_, stream);
+}
+
 cudaError_t PeerGather::exchange(const unsigned long long* d_counts, unsigned long long cand_cap,
                                  unsigned long long hit_cap, uint32_t ops_words, bool force_overflow,
                                  unsigned long long text_n, unsigned long long user, cudaStream_t stream) {
   if (!connected_ && world_ > 1) return cudaErrorNotReady;
+  if (pipelined_ && step_ >= 1 && collected_step_ != step_) {
+    // the previous step: its flags were released a whole search ago
+    cudaError_t e = collect(step_, stream);
+    if (e != cudaSuccess) return e;
+  }
   step_++;
   const size_t parity_off = (step_ & 1) * (size_t)world_ * slot_bytes_;
   PushArgs p;
@@ -248,25 +276,15 @@ cudaError_t PeerGather::exchange(const unsigned long long* d_counts, unsigned lo
   p.cand_cap = cand_cap;
   p.hit_cap = hit_cap;
   push_kernel<<<world_, 256, 0, stream>>>(p);
-  CollectArgs c;
-  memset(&c, 0, sizeof c);
-  c.local = local_;
-  c.host = host_;
-  c.world = (uint32_t)world_;
-  c.slot_bytes = slot_bytes_;
-  c.parity_off = parity_off;
-  c.flags_off = flags_off_ + (step_ & 1) * (size_t)world_ * sizeof(unsigned long long);
-  c.cap = cap_;
-  c.step = step_;
-  c.timeout_ns = timeout_ns_;
-  collect_kernel<<<world_, 256, 0, stream>>>(c);
-  return cudaGetLastError();
+  if (pipelined_) return cudaGetLastError();
+  return collect(step_, stream);
 }
 
 bool PeerGather::ok() const {
+  if (collected_step_ == 0) return false;
   for (int r = 0; r < world_; r++) {
     const SlotHeader* h = reinterpret_cast<const SlotHeader*>(host_ + (size_t)r * slot_bytes_);
-    if (h->overflow || h->step != step_) return false;
+    if (h->overflow || h->step != collected_step_) return false;
   }
   return true;
 }

@@ -37,7 +37,16 @@ class PeerGather {
   cudaError_t exchange(const unsigned long long* d_counts, unsigned long long cand_cap, unsigned long long hit_cap,
                        uint32_t ops_words, bool force_overflow, unsigned long long text_n, unsigned long long user,
                        cudaStream_t stream);
-  bool ok() const;         // every rank delivered a complete result for the last step
+  // Pipelined mode (all ranks alike, before the first exchange): exchange() of step s first collects
+  // step s - 1 -- whose records the peers pushed a whole search ago, so the wait for the slowest
+  // rank disappears from the step -- and then pushes step s; ok() / slot() then describe step s - 1.
+  // flush() collects the last pushed step.  The ranks may drift one step apart (not more: pushing
+  // step s needs every peer's flag of step s - 1), which is what the two slot parities allow.
+  void set_pipelined(bool on) { pipelined_ = on; }
+  bool pipelined() const { return pipelined_; }
+  bool has_result() const { return collected_step_ > 0; }  // a collected step is in the host mirror
+  cudaError_t flush(cudaStream_t stream);
+  bool ok() const;         // every rank delivered a complete result for the collected step
   bool timed_out() const;  // some rank did not arrive within the time-out
   // After a time-out the step counters of the ranks may differ: no further exchange is possible.
   void mark_broken() { broken_ = true; }
@@ -61,6 +70,9 @@ class PeerGather {
   unsigned long long step_ = 0;
   unsigned long long timeout_ns_ = 120ull * 1000 * 1000 * 1000;  // SASSY_B200_GATHER_TIMEOUT_S
   bool broken_ = false;
+  bool pipelined_ = false;
+  unsigned long long collected_step_ = 0;  // step whose records the host mirror holds (after a sync)
+  cudaError_t collect(unsigned long long step, cudaStream_t stream);
 };
 
 }  // namespace sb

@@ -348,9 +348,32 @@ std::vector<Match> Searcher::search_gathered(PeerGather& pg, const uint8_t* patt
     throw;
   }
   engine_->set_gather(nullptr, 0);
+  if (pg.pipelined()) {
+    // the host mirror holds the records of the PREVIOUS search (same pattern length expected)
+    if (!engine_->gather_ok())
+      throw std::runtime_error("pipelined gather: this rank's result did not fit the exchange; use the lock-step mode");
+    return collected_v1(pg, m, complete);
+  }
   *complete = engine_->gather_ok();
   if (!*complete) return local;
+  return collected_v1(pg, m, complete);
+}
+
+// All ranks' records of the collected step as v1 matches (text_idx = source rank).  Pipelined mode:
+// *complete = 2 while the pipeline is being primed (nothing collected yet).
+std::vector<Match> Searcher::collected_v1(PeerGather& pg, size_t m, bool* complete, int* state) {
   std::vector<Match> out;
+  if (state) *state = 1;
+  if (pg.pipelined()) {
+    if (!pg.has_result()) {
+      *complete = true;
+      if (state) *state = 2;
+      return out;
+    }
+    if (!pg.ok())
+      throw std::runtime_error("pipelined gather: some rank's result did not fit the exchange; use the lock-step mode");
+  }
+  *complete = true;
   for (int r = 0; r < pg.world(); r++) {
     const uint64_t n = pg.slot(r).text_n;
     std::vector<Match> part = convert_v1(slot_set(pg, r), 1, m, [n](size_t) { return n; });
@@ -360,12 +383,23 @@ std::vector<Match> Searcher::search_gathered(PeerGather& pg, const uint8_t* patt
   return out;
 }
 
+std::vector<Match> Searcher::flush_gathered(PeerGather& pg, size_t m, int* state) {
+  bool complete = false;
+  engine_->flush_gather(pg);
+  return collected_v1(pg, m, &complete, state);
+}
+
 std::vector<Match> Searcher::search_sharded_gathered(PeerGather& pg, const uint8_t* pattern, size_t m,
                                                      const DeviceText& window, size_t k, bool all_minima,
                                                      const SlabInfo* slabs, size_t n_slabs, uint64_t n_global,
                                                      bool* complete) {
   std::vector<Match> all = search_gathered(pg, pattern, m, window, k, /*all_minima=*/true, complete);
   if (!*complete) return all;
+  return merge_gathered(all, all_minima, slabs, n_slabs, n_global);
+}
+
+std::vector<Match> Searcher::merge_gathered(std::vector<Match>& all, bool all_minima, const SlabInfo* slabs,
+                                            size_t n_slabs, uint64_t n_global) {
   const std::vector<size_t> keep = merge_slab_matches(all, slabs, n_slabs, n_global, all_minima);
   std::vector<Match> out;
   out.reserve(keep.size());
@@ -874,10 +908,35 @@ sassy_gpu_Result* sassy_gpu_search_text_sharded(sassy_SearcherType* searcher, sa
     std::vector<sb::SlabInfo> info(n_slabs);
     for (size_t i = 0; i < n_slabs; i++) info[i] = sb::SlabInfo{slabs[i].window_off, slabs[i].own_lo, slabs[i].own_hi};
     bool ok = false;
+    const bool primed = !gather->g.pipelined() || gather->g.has_result() || false;
     auto v = searcher->s.search_sharded_gathered(gather->g, pattern, pattern_len, *window->t, k, all != 0, info.data(),
                                                  n_slabs, n_global, &ok);
+    (void)primed;
     *complete = ok ? 1 : 0;
+    if (gather->g.pipelined() && !gather->g.has_result()) *complete = 2;  // pipeline priming: no result yet
     return to_result(v);
+  });
+}
+
+int sassy_gpu_gather_set_pipelined(sassy_gpu_Gather* gather, int on) {
+  if (!gather) return 1;
+  gather->g.set_pipelined(on != 0);
+  return 0;
+}
+
+int sassy_gpu_gather_has_result(const sassy_gpu_Gather* gather) { return gather && gather->g.has_result() ? 1 : 0; }
+
+sassy_gpu_Result* sassy_gpu_text_sharded_flush(sassy_SearcherType* searcher, sassy_gpu_Gather* gather,
+                                               size_t pattern_len, int all, const sassy_gpu_Slab* slabs,
+                                               size_t n_slabs, uint64_t n_global, int* state) {
+  return guarded([&]() -> sassy_gpu_Result* {
+    if (!searcher || !gather || !slabs || !state) throw std::invalid_argument("null pointer");
+    std::vector<sb::SlabInfo> info(n_slabs);
+    for (size_t i = 0; i < n_slabs; i++) info[i] = sb::SlabInfo{slabs[i].window_off, slabs[i].own_lo, slabs[i].own_hi};
+    auto v = searcher->s.flush_gathered(gather->g, pattern_len, state);
+    if (*state == 2) return to_result(v);
+    auto merged = searcher->s.merge_gathered(v, all != 0, info.data(), n_slabs, n_global);
+    return to_result(merged);
   });
 }
 

@@ -118,6 +118,12 @@ class Searcher {
                                              const SlabInfo* slabs, size_t n_slabs, uint64_t n_global,
                                              bool* complete);
 
+  // Pipelined PeerGather: the records of the collected (previous) step / of the last pushed step.
+  std::vector<Match> collected_v1(PeerGather& pg, size_t m, bool* complete, int* state = nullptr);
+  std::vector<Match> flush_gathered(PeerGather& pg, size_t m, int* state);
+  std::vector<Match> merge_gathered(std::vector<Match>& all, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
+                                    uint64_t n_global);
+
   void validate_pattern(const uint8_t* p, size_t m) const;
 
  private:

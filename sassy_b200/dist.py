@@ -169,10 +169,16 @@ class PeerGather:
     fall-back all-gather when some rank's result does not fit the exchange.
 
     All ranks must call search()/search_encoded() in lock step.  Results: all ranks' matches in
-    rank order, text_idx = source rank, pattern_idx local to the source rank's pattern set."""
+    rank order, text_idx = source rank, pattern_idx local to the source rank's pattern set.
 
-    def __init__(self, searcher, max_ops: int, cap: int = 2048, group=None):
+    pipelined=True (search_sharded / flush_sharded only): a call pushes its records and collects
+    those of the PREVIOUS call, which the peers pushed a whole search earlier, so no rank waits for
+    the slowest one inside a step; calls return the previous call's result (None at first),
+    flush_sharded() the last one.  Results must fit the slots (cap records per rank)."""
+
+    def __init__(self, searcher, max_ops: int, cap: int = 2048, group=None, pipelined: bool = False):
         import ctypes
+        self.pipelined = bool(pipelined)
         from . import _native
         self._lib = _native.load()
         self._searcher = searcher
@@ -209,14 +215,16 @@ class PeerGather:
         if err is not None:
             self._free_local()
             raise RuntimeError(err)
+        if self.pipelined:
+            self._lib.sassy_gpu_gather_set_pipelined(self._h, 1)
 
     @classmethod
-    def create_or_none(cls, searcher, max_ops: int, device=None, group=None):
+    def create_or_none(cls, searcher, max_ops: int, device=None, group=None, pipelined: bool = False):
         """Collective constructor: every rank gets a PeerGather, or -- if peer memory cannot be
         mapped on some rank (no P2P path between two GPUs) -- every rank gets None and the caller
         uses gather_matches (NCCL) instead."""
         try:
-            return cls(searcher, max_ops, group=group)  # raises on every rank or on none
+            return cls(searcher, max_ops, group=group, pipelined=pipelined)  # raises on every rank or on none
         except RuntimeError as e:
             rank = dist.get_rank(group) if dist.is_initialized() else 0
             import sys
@@ -276,11 +284,25 @@ class PeerGather:
                                                       int(all_minima), slabs.ctypes.data, len(layout), n_global,
                                                       ctypes.byref(ok))
         ms = self._searcher._collect(res)
+        if ok.value == 2:  # pipelined mode, first call: nothing collected yet
+            return None
         if ok.value:
             return ms
         self.fallbacks += 1
         allm = gather_matches(tag_rank(ms, self.rank), self.max_ops, group=self._group)
         return merge_slabs(allm, layout, n_global, all_minima)
+
+    def flush_sharded(self, pattern_len: int, layout, n_global: int, all_minima: bool = False):
+        """Pipelined mode: the result of the last search_sharded call (None if nothing is pending)."""
+        import ctypes
+        slabs = np.zeros((len(layout), 3), dtype=np.uint64)
+        for r, (wlo, _whi, lo, hi) in enumerate(layout):
+            slabs[r] = (wlo, lo, hi)
+        state = ctypes.c_int(0)
+        res = self._lib.sassy_gpu_text_sharded_flush(self._searcher._h, self._h, pattern_len, int(all_minima),
+                                                     slabs.ctypes.data, len(layout), n_global, ctypes.byref(state))
+        ms = self._searcher._collect(res)
+        return None if state.value == 2 else ms
 
     def search_encoded(self, enc, text, k: int, all_minima: bool = False):
         import ctypes

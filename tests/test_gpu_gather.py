@@ -123,3 +123,94 @@ def test_gather_world2_peer_memory():
         assert after == want
         assert nfb == (30_000 - 5) + (3_000 - 5)
         assert fallbacks == 1
+
+
+def test_sharded_world1_pipelined_equals_plain_search():
+    """One slab = the whole text: the pipelined exchange returns the result of the previous call,
+    flush the last one; all equal the plain search."""
+    import sassy_b200
+    from sassy_b200 import dist as sd
+    rng = random.Random(43)
+    s = sassy_b200.Searcher("dna", rc=True)
+    p = rand_seq(rng, 20)
+    t = _text_with_plants(rng, 400_000, [p], 2)
+    dt = s.upload_text(t)
+    want = list(map(key, s.search(p, dt, 2)))
+    layout = sd.slab_layout(len(t), 1, 20, 2)
+    for pipelined in (False, True):
+        pg = sd.PeerGather(s, max_ops=20 + 2 + 1, pipelined=pipelined)
+        got = [pg.search_sharded(p, dt, 2, layout, len(t)) for _ in range(4)]
+        if pipelined:
+            assert got[0] is None
+            got = got[1:] + [pg.flush_sharded(20, layout, len(t))]
+            assert pg.flush_sharded(20, layout, len(t)) is not None  # idempotent: the same last result
+        for g in got:
+            assert list(map(key, g)) == want and len(want) >= 3
+        pg.close()
+
+
+def _shard_worker(rank, world, port, q, pipelined):
+    import torch
+    import torch.distributed as dist
+    import sassy_b200
+    from sassy_b200 import dist as sd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["SASSY_B200_GATHER_TIMEOUT_S"] = "20"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    rng = random.Random(300)  # the same global text on every rank
+    m, k = 20, 2
+    p = rand_seq(rng, m)
+    n = 600_001
+    t = bytearray(_text_with_plants(rng, n, [p], k))
+    cut = -(-n // world)
+    rcp = oracle.reverse_complement("dna", p)
+    t[cut - 7:cut - 7 + m] = p            # copies across the slab border, both strands
+    t[cut + 40 - 3:cut + 40 - 3 + m] = rcp
+    t[cut + 200 - m:cut + 200] = p[:10] + bytes([p[10]]) * 1 + p[10:19]  # a plateau next to the border
+    t = bytes(t)
+    layout = sd.slab_layout(n, world, m, k)
+    wlo, whi, lo, hi = layout[rank]
+    s = sassy_b200.Searcher("dna", rc=True, device=rank)
+    dt = s.upload_text(t[wlo:whi])
+    pg = sd.PeerGather(s, max_ops=m + k + 1, pipelined=pipelined)
+    outs = []
+    for step in range(4):
+        r = sd.search_text_sharded(s, p, dt, k, n, peer_gather=pg)
+        if r is not None:
+            outs.append(list(map(key, r)))
+    if pipelined:
+        outs.append(list(map(key, pg.flush_sharded(m, layout, n))))
+    nccl = list(map(key, sd.search_text_sharded(s, p, dt, k, n)))  # all-gather route
+    want = [(x.pattern_idx, 0, x.text_start, x.text_end, x.cost, x.strand, x.cigar)
+            for x in oracle.search("dna", p, t, k, rc=True)]
+    q.put((rank, outs, nccl, want))
+    dist.barrier()
+    pg.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("pipelined", [False, True], ids=["lockstep", "pipelined"])
+def test_text_sharded_world2_equals_unsharded(pipelined):
+    """ONE text cut into 2 slabs on 2 GPUs (halo, fused gather, merged local-minima rule) == the
+    oracle's search of the whole text, with matches and a plateau across the cut."""
+    import sassy_b200
+    if sassy_b200.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q, pipelined)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, outs, nccl, want in res:
+        assert len(want) >= 5 and len(outs) == 4
+        for o in outs:
+            assert o == want
+        assert nccl == want
