@@ -85,6 +85,8 @@ typedef struct sassy_gpu_Stats {
   uint32_t filter_kind;     /* 0 none, 1 piece automaton (Shift-And), 2 q-gram bitmap, 3 SWAR suffix scan */
   uint32_t swar_lanes;      /* patterns per 32-bit word in the scan that produced the candidates (0/1 = one) */
   uint64_t confirmed;       /* prefilter hits that were re-scanned (q-gram: after the exact confirmation) */
+  uint32_t dense_tiles;     /* regional fallback: tiles with too many hits, scanned whole with the exact recurrences */
+  uint32_t reserved3;
 } sassy_gpu_Stats;
 
 #ifdef __cplusplus

@@ -75,6 +75,8 @@ class GpuStats(ctypes.Structure):
         ("filter_kind", ctypes.c_uint32),
         ("swar_lanes", ctypes.c_uint32),
         ("confirmed", ctypes.c_uint64),
+        ("dense_tiles", ctypes.c_uint32),
+        ("reserved3", ctypes.c_uint32),
     ]
 
 

@@ -31,6 +31,7 @@ void scan_rows(const ScanArgs& a, const uint32_t* eq_q, uint32_t qs) {
   const uint32_t total = a.g.nwarm + a.g.nstage;
   const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
   for (uint64_t row = 0; row < tiles * kScanThreads; row++) {  // includes the idle threads of the last tile
+    if (a.tile_list && !a.dense[row / kScanThreads]) continue;  // regional fallback: the listed tiles only
     Lane<W> s;
     lane_reset<W>(s, a.m);
     int prev_score = a.m;
@@ -223,6 +224,7 @@ void refine_and_verify(int W, ScanArgs& a, const std::vector<uint32_t>& eq, cons
   std::vector<uint32_t> spans;
   for (unsigned long long h = 0; h < nhits; h++) {
     const uint32_t qs = key_qs(hits[h]);
+    if (hit_in_dense_tile(a, key_pos(hits[h]) * kHitChars)) continue;
     int64_t lo, hi;
     if (refine_hit(a, qs, rev[qs] != 0, key_pos(hits[h]) * kHitChars, lo, hi))
       exact.push_back(cand_key(qs, (uint64_t)lo)), spans.push_back((uint32_t)(hi - lo));
@@ -243,6 +245,7 @@ struct EmuResult {
   uint64_t hits;
   int filter_words;  // 0 = full scan
   int filter_len;
+  uint32_t dense_tiles = 0;
   ScanGeom g;
 };
 
@@ -389,6 +392,41 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
   if (ov) a.emit_min = std::min<uint64_t>(n, (uint64_t)m + (uint64_t)k);
   std::vector<const uint8_t*> qptr(nq);
   for (uint32_t q = 0; q < nq; q++) qptr[q] = queries + (size_t)q * m;
+  // Regional fallback of Engine::search: tiles of the scan geometry with more hits than a re-scan is
+  // worth are marked dense (their hits are skipped) and scanned whole.
+  std::vector<uint8_t> dense_flags;
+  std::vector<uint32_t> dense_list(1, 0);
+  uint32_t dense_count = 0;
+  auto mark_dense = [&](const std::vector<uint64_t>& hits, unsigned long long nhits, bool qgram) {
+    const uint32_t ntiles = (g.rows + kScanThreads - 1) / kScanThreads;
+    const uint64_t tile_bytes = (uint64_t)kScanThreads * g.ltot;
+    const double hit_cost = qgram ? 32.0 + 0.25 * (2.0 * (m + k) + kHitChars) : 2.0 * (m + k) + kHitChars;
+    const double max_hits = 0.5 * (double)tile_bytes * nq / hit_cost;
+    dense_flags.assign(ntiles + 1, 0);
+    a.tile_bytes = tile_bytes;
+    a.dense = dense_flags.data();
+    if ((double)nhits < std::max(1.0, max_hits)) return;
+    std::vector<uint32_t> counts(ntiles + 1, 0);
+    for (unsigned long long h = 0; h < nhits; h++) counts[(key_pos(hits[h]) * kHitChars) / tile_bytes]++;
+    for (uint32_t t = 0; t < ntiles; t++)
+      if ((double)counts[t] > (double)(uint32_t)std::min(max_hits, 4.0e9)) dense_flags[t] = 1, dense_count++;
+  };
+  auto scan_dense = [&](ScanArgs& aa) {
+    res->dense_tiles = dense_count;
+    if (!dense_count) return;
+    aa.tile_list = dense_list.data();  // marker: scan_rows visits the rows of dense tiles only
+    for (uint32_t q = 0; q < nq; q++) {
+      const uint32_t* eq_q = &eq[(size_t)q * pp.nrows * W];
+      if (rev[q]) {
+        aa.reset_idx = n - 1;
+        scan_dispatch<true>(W, aa, eq_q, q);
+      } else {
+        aa.reset_idx = 0;
+        scan_dispatch<false>(W, aa, eq_q, q);
+      }
+    }
+    aa.tile_list = nullptr;
+  };
   FilterPlan fp;
   // use_filter: 0 off, < 0 automatic, 1 force the piece automaton (4: and refine its hits), 2 / 3 as Engine::search with the
   // filter forced (q-gram bitmap when it can be planned -- 2: contiguous tiles, 3: row tiles --
@@ -428,8 +466,10 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
     a.qconf = conf.data();
     a.qnp = (uint32_t)qp.npieces;
     res->hits = nhits;
+    mark_dense(hits, nhits, true);
     refine_and_verify(W, a, eq, pp, rev, hits, nhits);
     a.qconf = nullptr, a.qnp = 0;
+    scan_dense(a);
   } else if (n > 0 && fp.enabled) {
     uint32_t nfwd = 0;
     while (nfwd < nq && !rev[nfwd]) nfwd++;
@@ -468,6 +508,7 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
     if (fused)
       for (int p = 0; p < fp.npieces; p++) a.rev_lead = std::max<uint32_t>(a.rev_lead, (uint32_t)fp.piece[p].len);
     res->hits = nhits;
+    mark_dense(hits, nhits, false);
     if (profile == kDna && use_filter == 4) {  // SASSY_B200_REFINE=2: piece-automaton hits are refined too
       std::vector<uint32_t> conf((size_t)nq * fp.npieces * kConfWords);
       for (uint32_t q = 0; q < nq; q++)
@@ -480,9 +521,11 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
     } else {
       for (unsigned long long h = 0; h < nhits; h++) {
         const uint32_t qs = key_qs(hits[h]);
+        if (hit_in_dense_tile(a, key_pos(hits[h]) * kHitChars)) continue;
         verify_dispatch(W, a, &eq[(size_t)qs * pp.nrows * W], qs, rev[qs] != 0, key_pos(hits[h]));
       }
     }
+    scan_dense(a);
   } else if (n > 0) {
     for (uint32_t q = 0; q < nq; q++) {
       const uint32_t* eq_q = &eq[(size_t)q * pp.nrows * W];
@@ -641,6 +684,7 @@ uint64_t emu_candidates(const EmuResult* r) { return r->candidates; }
 uint64_t emu_hits(const EmuResult* r) { return r->hits; }
 int emu_filter_words(const EmuResult* r) { return r->filter_words; }
 int emu_filter_len(const EmuResult* r) { return r->filter_len; }
+uint32_t emu_dense_tiles(const EmuResult* r) { return r->dense_tiles; }
 uint32_t emu_ltot(const EmuResult* r) { return r->g.ltot; }
 uint32_t emu_rows(const EmuResult* r) { return r->g.rows; }
 void emu_free(EmuResult* r) { delete r; }

@@ -89,7 +89,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   for (DevBuf* b : {&keys_, &cost_, &keys2_, &cost2_, &flags_, &sel_, &cubtmp_, &scratch_, &ops_, &out_, &hits_,
-                    &d_stage_, &best_, &sel_cost_, &d_texts_, &hits2_})
+                    &d_stage_, &best_, &sel_cost_, &d_texts_, &hits2_, &tiles_})
     b->release();
   if (staged_.d) cudaFree(staged_.d);
   if (h_stage_) cudaFreeHost(h_stage_);
@@ -823,6 +823,48 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     v.hit_keys = hits_.as<uint64_t>();
     v.hit_count = d_hit_count;
     v.hit_cap = hit_cap_;
+    // Regional fallback (device-side decision, no host round trip): tiles of the scan geometry with
+    // more hits than re-scanning is worth are marked dense; their hits are skipped below and the
+    // bit-parallel scan runs over exactly those tiles.  Uniform text marks nothing (three tiny
+    // launches); a satellite or a poly-A stretch costs the scan of its own tiles, not of the text.
+    const uint32_t ntiles = (g.rows + kScanThreads - 1) / kScanThreads;
+    const uint64_t tile_bytes = (uint64_t)kScanThreads * g.ltot;
+    uint32_t* d_dense_count = nullptr;
+    {
+      // per-hit cost in scanned characters: an unrefined hit re-scans 2(m+k)+16 characters; a q-gram
+      // hit costs its refinement plus, in a repeat, a re-scan of about that size
+      const double hit_cost = qgram ? 32.0 + 0.25 * (2.0 * (m + k) + kHitChars) : 2.0 * (m + k) + kHitChars;
+      const double max_hits = 0.5 * (double)tile_bytes * nq * W / (hit_cost * W);  // re-scan <= half a tile scan
+      tiles_.ensure((size_t)ntiles * 9 + 64);
+      uint32_t* d_tile_counts = tiles_.as<uint32_t>();
+      uint32_t* d_tile_list = d_tile_counts + ntiles;
+      uint8_t* d_dense = reinterpret_cast<uint8_t*>(d_tile_list + ntiles);
+      d_dense_count = reinterpret_cast<uint32_t*>(d_counts + 5);
+      SB_CUDA(cudaMemsetAsync(d_tile_counts, 0, (size_t)ntiles * 9, stream_));
+      v.tile_bytes = tile_bytes;
+      SB_CUDA(launch_tile_marks(v, ntiles, d_tile_counts, /*min_hits=*/(unsigned long long)std::max(1.0, max_hits),
+                                (uint32_t)std::min(max_hits, 4.0e9), d_dense, d_tile_list, d_dense_count, stream_));
+      stats_.aux_launches += 2;
+      v.dense = d_dense;
+      a.tile_list = d_tile_list;
+      a.tile_count = d_dense_count;
+    }
+    auto scan_dense_tiles = [&]() {  // the listed tiles, with the exact recurrences (both directions)
+      CUtensorMap tmap;
+      memset(&tmap, 0, sizeof tmap);
+      if (variant_ == kVariantTma) make_tensor_map(&tmap, text, g);
+      ScanArgs sd = a;
+      if (nfwd) {
+        sd.reset_idx = 0, sd.nq = nfwd, sd.qs_base = 0, sd.eq = d_eq;
+        SB_CUDA(launch_scan(W, false, variant_, &tmap, sd, stream_));
+        stats_.scan_launches++;
+      }
+      if (nq > nfwd) {
+        sd.reset_idx = n - 1, sd.nq = nq - nfwd, sd.qs_base = nfwd, sd.eq = d_eq + (size_t)nfwd * nrows_ * W;
+        SB_CUDA(launch_scan(W, true, variant_, &tmap, sd, stream_));
+        stats_.scan_launches++;
+      }
+    };
     if (fused)  // a reversed query's hit marks the START of its piece in scan direction
       for (int p = 0; p < fp.npieces; p++) v.rev_lead = std::max<uint32_t>(v.rev_lead, (uint32_t)fp.piece[p].len);
     // (piece-automaton hits ARE share occurrences: refining them costs a pass over ~10^6 hits and
@@ -848,9 +890,11 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     }
     SB_CUDA(launch_verify(W, v, d_rev, stream_));
     stats_.aux_launches++;
+    scan_dense_tiles();
     SB_CUDA(cudaEventRecord(ev_[4], stream_));
     queue_small_tail();
     read_counts();
+    stats_.dense_tiles = (uint32_t)(h_counts[5] & 0xFFFFFFFFu);
     stats_.filter_ms = elapsed(ev_[1], ev_[2]);
     stats_.verify_ms = elapsed(ev_[2], ev_[4]);
     unsigned long long nhits = h_counts[2];
@@ -872,7 +916,8 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       filtered = true;
       small_done = true;
       stats_.scan_ms = stats_.filter_ms;
-    } else if (nhits > hit_cap_ || rescan > 0.5 * (double)n * nq) {
+    } else if (nhits > hit_cap_) {  // the hit list overflowed: hits are lost, only the full scan is exact
+      (void)rescan;
       stats_.filter_fallback = 1;
     } else {
       stats_.ltot = gf.ltot;
@@ -892,6 +937,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
         SB_CUDA(cudaEventRecord(ev_[2], stream_));
         SB_CUDA(launch_verify(W, v, d_rev, stream_));
         stats_.aux_launches++;
+        scan_dense_tiles();
         SB_CUDA(cudaEventRecord(ev_[4], stream_));
         queue_small_tail();
         read_counts();
@@ -904,6 +950,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   }
 
   // ---- candidates, route 2: full scan with the bit-parallel recurrences ---------------------
+  a.tile_list = nullptr, a.tile_count = nullptr;
   if (!filtered) {
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);

@@ -72,6 +72,7 @@ struct SearchStats {
   uint32_t filter_kind = 0;      // 0 none, 1 piece automaton (Shift-And), 2 q-gram bitmap, 3 SWAR suffix scan
   uint32_t swar_lanes = 0;       // patterns per 32-bit word of the scan that produced the candidates (0/1 = one)
   uint64_t confirmed = 0;        // prefilter hits that were re-scanned (q-gram: after the exact confirmation)
+  uint32_t dense_tiles = 0;      // tiles of the scan geometry that were scanned whole (regional fallback)
 };
 
 struct MatchSet {
@@ -201,7 +202,7 @@ class Engine {
 
   DevBuf keys_, cost_, keys2_, cost2_, flags_, sel_, cubtmp_;
   DevBuf scratch_, ops_, out_;
-  DevBuf hits_, hits2_, d_stage_, sel_small_, best_, sel_cost_, d_texts_;
+  DevBuf hits_, hits2_, tiles_, d_stage_, sel_small_, best_, sel_cost_, d_texts_;
   uint8_t* h_small_ = nullptr;  // pinned: results of the small-list fast path, written by the GPU
   size_t h_small_cap_ = 0;
   uint8_t* h_stage_ = nullptr;  // pinned staging for the per-search parameter block

@@ -43,6 +43,12 @@ cudaError_t launch_qgram_seq(int Q, int S, const CUtensorMap* tmap, const ScanAr
 // counts them); launch_verify then runs with ScanArgs::hit_exact = 1 on that list.
 cudaError_t launch_refine(const ScanArgs& a, const uint8_t* rev_flags, uint64_t* out, uint32_t* out_span,
                           unsigned long long* out_count, cudaStream_t stream);
+// Regional fallback: counts the prefilter hits per tile (a.tile_bytes) and marks / lists the tiles with
+// more than max_hits_per_tile of them (nothing is marked when there are fewer than min_hits hits in
+// all).  counts [ntiles] and *list_count must be zero on entry.
+cudaError_t launch_tile_marks(const ScanArgs& a, uint32_t ntiles, uint32_t* counts, unsigned long long min_hits,
+                              uint32_t max_hits_per_tile, uint8_t* dense, uint32_t* list, uint32_t* list_count,
+                              cudaStream_t stream);
 // nhits is read from a.hit_count on the device (clipped to a.hit_cap): no host round trip.
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream);
 

@@ -87,7 +87,29 @@ struct ScanArgs {
   uint32_t qnp;             // pieces per query (k + 1); 0 = hits are not refined
   uint32_t hit_exact;       // 1: hit keys hold a nominal END POSITION (scan direction) instead of a 16-byte chunk
   const uint32_t* hit_span; // hit_exact: per entry, how many positions beyond the nominal one the entry covers
+  // Regional fallback of the prefilter routes.  A tile = the kScanThreads rows of one block of the
+  // scan geometry.  Tiles with so many hits that re-scanning their neighbourhoods would cost more
+  // than scanning the tile (repeats, low-complexity sequence) are marked dense: their hits are
+  // dropped and the scan kernels run over exactly those tiles (tile_list) instead.
+  uint64_t tile_bytes;         // text bytes per tile (kScanThreads * ltot of the SCAN geometry); 0 = no tiles
+  const uint8_t* dense;        // refine / verify: [tile] != 0 -> skip the hit
+  const uint32_t* tile_list;   // scan kernels: block b scans tile tile_list[b / nq] if b / nq < *tile_count
+  const uint32_t* tile_count;
 };
+
+// May the hit (16-byte chunk at forward index `fwd_pos`) be dropped because the scan of dense tiles
+// covers everything it stands for?  A hit speaks for end positions up to 16 + m + k characters away
+// (to the right for forward queries, to the left for reversed ones), so it is dropped only when the
+// tiles at both ends of that reach are dense (tiles are much longer than the reach: at most two are
+// involved).  Hits near the border between a dense and a sparse tile are verified as usual.
+SB_HD bool hit_in_dense_tile(const ScanArgs& a, uint64_t fwd_pos) {
+  if (!a.dense || !a.tile_bytes || a.n == 0) return false;
+  const uint64_t reach = (uint64_t)a.m + (uint64_t)a.k + 32;
+  const uint64_t lo = fwd_pos > reach ? fwd_pos - reach : 0;
+  uint64_t hi = fwd_pos + reach;
+  if (hi > a.n - 1) hi = a.n - 1;
+  return a.dense[lo / a.tile_bytes] != 0 && a.dense[hi / a.tile_bytes] != 0;
+}
 
 template <int W>
 struct Lane {
@@ -641,6 +663,7 @@ SB_HD bool refine_hit(const ScanArgs& a, uint32_t qs, bool rev, uint64_t base, i
           const uint32_t off2 = conf[p2 * kConfWords + 3];
           const int64_t s2 = diag + (rev ? (int64_t)a.m - (int64_t)off2 - (int64_t)len2 : (int64_t)off2);
           if (s2 < 0 || s2 + (int64_t)len2 > (int64_t)a.n) continue;
+          if (hit_in_dense_tile(a, (uint64_t)s2)) continue;  // that share's own hit may have been dropped
           uint32_t v2 = 0;
           for (uint32_t j = 0; j < len2; j++) v2 |= (((uint32_t)a.text[s2 + j] >> 1) & 3u) << (2 * j);
           covered = v2 == conf[p2 * kConfWords];

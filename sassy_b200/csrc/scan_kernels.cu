@@ -101,7 +101,11 @@ __device__ __forceinline__ void row_pipeline(const CUtensorMap& tmap, const Scan
 
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5, lane = tid & 31;
-  const uint32_t tile = blockIdx.x / a.nq;
+  uint32_t tile = blockIdx.x / a.nq;
+  if (a.tile_list) {  // regional fallback: only the listed tiles (block-uniform exit)
+    if (tile >= *a.tile_count) return;
+    tile = a.tile_list[tile];
+  }
   const int64_t row0 = (int64_t)tile * kScanThreads + 32 * warp;  // first row of this warp
   const int64_t row = row0 + lane;
 
@@ -591,6 +595,7 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
     hit_window_exact(a, key_pos(key), a.hit_span[i], w0, end, emit_from);
   } else {
     const int64_t base = (int64_t)(key_pos(key) * kHitChars);
+    if (hit_in_dense_tile(a, (uint64_t)base)) return;  // its tile is scanned whole
     const int64_t g0 = rev ? n - kHitChars - base : base;
     const int64_t span = (int64_t)a.m + (int64_t)a.k;
     w0 = g0 - span;
@@ -1026,6 +1031,7 @@ __global__ void __launch_bounds__(32 * kWideWarps)
       hit_window_exact(a, key_pos(key), a.hit_span[h], w0, end, emit_from);
     } else {
       const int64_t base = (int64_t)(key_pos(key) * kHitChars);
+      if (hit_in_dense_tile(a, (uint64_t)base)) continue;  // its tile is scanned whole (warp-uniform)
       const int64_t g0 = rev ? n - kHitChars - base : base;
       const int64_t span = (int64_t)a.m + (int64_t)a.k;
       w0 = g0 - span;
@@ -1090,6 +1096,7 @@ __global__ void __launch_bounds__(256)
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nhits; i += nthreads) {
     const uint64_t key = a.hit_keys[i];
     const uint32_t qs = key_qs(key);
+    if (hit_in_dense_tile(a, key_pos(key) * kHitChars)) continue;
     int64_t lo, hi;
     if (!refine_hit(a, qs, rev_flags[qs] != 0, key_pos(key) * kHitChars, lo, hi)) continue;
     // survivors are rare (a whole share of the pattern behind the hit): one atomic each
@@ -1102,6 +1109,40 @@ __global__ void __launch_bounds__(256)
 }
 
 }  // namespace
+
+namespace {
+
+// Hits per tile (a prefilter hit = a 16-byte chunk; all query slots together).
+__global__ void __launch_bounds__(256)
+    tile_hist_kernel(const __grid_constant__ ScanArgs a, uint32_t* __restrict__ counts, unsigned long long min_hits) {
+  unsigned long long nhits = *a.hit_count;
+  if (nhits < min_hits) return;  // few hits overall: no tile can be dense enough to matter
+  if (nhits > a.hit_cap) nhits = a.hit_cap;
+  const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nhits; i += nthreads)
+    atomicAdd(&counts[(key_pos(a.hit_keys[i]) * kHitChars) / a.tile_bytes], 1u);
+}
+
+// dense[t] = 1 and t appended to the list when the tile's hits exceed `max_hits_per_tile`.
+__global__ void __launch_bounds__(256)
+    tile_mark_kernel(const uint32_t* __restrict__ counts, uint32_t ntiles, uint32_t max_hits_per_tile,
+                     uint8_t* __restrict__ dense, uint32_t* __restrict__ list, uint32_t* __restrict__ list_count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const bool d = counts[t] > max_hits_per_tile;
+  dense[t] = d ? 1 : 0;
+  if (d) list[atomicAdd(list_count, 1u)] = t;
+}
+
+}  // namespace
+
+cudaError_t launch_tile_marks(const ScanArgs& a, uint32_t ntiles, uint32_t* counts, unsigned long long min_hits,
+                              uint32_t max_hits_per_tile, uint8_t* dense, uint32_t* list, uint32_t* list_count,
+                              cudaStream_t stream) {
+  tile_hist_kernel<<<148 * 4, 256, 0, stream>>>(a, counts, min_hits);
+  tile_mark_kernel<<<(ntiles + 255) / 256, 256, 0, stream>>>(counts, ntiles, max_hits_per_tile, dense, list, list_count);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_refine(const ScanArgs& a, const uint8_t* rev_flags, uint64_t* out, uint32_t* out_span,
                           unsigned long long* out_count, cudaStream_t stream) {

@@ -135,6 +135,7 @@ std::vector<Match> Searcher::search_with_pam(const uint8_t* pattern, size_t m, c
   o.pam = pam;
   o.pam_len = (int)pam_len;
   engine_->search(text, qs, (int)m, kk, o, ms_);
+  if (raw_only_) return {};  // the caller reads ms_ / the gathered records itself
   const uint64_t n = text.n;
   return convert_v1(ms_, 1, m, [n](size_t) { return n; });
 }
@@ -383,6 +384,19 @@ std::vector<Match> Searcher::collected_v1(PeerGather& pg, size_t m, bool* comple
   return out;
 }
 
+std::vector<Match> Searcher::flush_sharded(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs,
+                                           size_t n_slabs, uint64_t n_global, int* state) {
+  engine_->flush_gather(pg);
+  *state = 1;
+  if (!pg.pipelined() || !pg.has_result()) {
+    *state = 2;
+    return {};
+  }
+  if (!pg.ok())
+    throw std::runtime_error("pipelined gather: some rank's result did not fit the exchange; use the lock-step mode");
+  return merge_collected(pg, m, all_minima, slabs, n_slabs, n_global);
+}
+
 std::vector<Match> Searcher::flush_gathered(PeerGather& pg, size_t m, int* state) {
   bool complete = false;
   engine_->flush_gather(pg);
@@ -393,9 +407,92 @@ std::vector<Match> Searcher::search_sharded_gathered(PeerGather& pg, const uint8
                                                      const DeviceText& window, size_t k, bool all_minima,
                                                      const SlabInfo* slabs, size_t n_slabs, uint64_t n_global,
                                                      bool* complete) {
-  std::vector<Match> all = search_gathered(pg, pattern, m, window, k, /*all_minima=*/true, complete);
-  if (!*complete) return all;
-  return merge_gathered(all, all_minima, slabs, n_slabs, n_global);
+  // search_all of the window; in lock-step mode the records of THIS search are in the host mirror
+  // afterwards, in pipelined mode those of the previous one
+  engine_->set_gather(&pg, 1);
+  raw_only_ = true;  // no Match objects for this rank's own records: the merge reads the raw ones
+  try {
+    search_with_pam(pattern, m, window, k, /*all_minima=*/true, nullptr, 0);
+  } catch (...) {
+    raw_only_ = false;
+    engine_->set_gather(nullptr, 0);
+    throw;
+  }
+  raw_only_ = false;
+  engine_->set_gather(nullptr, 0);
+  if (pg.pipelined()) {
+    if (!engine_->gather_ok())
+      throw std::runtime_error("pipelined gather: this rank's result did not fit the exchange; use the lock-step mode");
+    *complete = true;
+    if (!pg.has_result()) return {};
+    if (!pg.ok())
+      throw std::runtime_error("pipelined gather: some rank's result did not fit the exchange; use the lock-step mode");
+  } else {
+    *complete = engine_->gather_ok();
+    if (!*complete) {  // the caller's own collective: this rank's search_all matches, window coordinates
+      const uint64_t wn = window.n;
+      return convert_v1(ms_, 1, m, [wn](size_t) { return wn; });
+    }
+  }
+  return merge_collected(pg, m, all_minima, slabs, n_slabs, n_global);
+}
+
+// Ownership filter + local-minima rule on the RAW records of the collected step (scan-direction
+// coordinates, 32 bytes each); only the selected records are turned into Matches (CIGAR strings).
+// Every rank merges all ranks' search_all records every step: this is the host cost of a sharded
+// search, so it avoids per-record allocations.
+std::vector<Match> Searcher::merge_collected(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs,
+                                             size_t n_slabs, uint64_t n_global) {
+  struct Item {
+    uint64_t key;
+    uint32_t cost, rank, idx;
+  };
+  std::vector<Item> items;
+  const size_t nq = rc_ ? 2 : 1;
+  for (int r = 0; r < pg.world() && (size_t)r < n_slabs; r++) {
+    const PeerGather::Slot sl = pg.slot(r);
+    const SlabInfo& sb_ = slabs[r];
+    const uint64_t wlen = sl.text_n;
+    for (unsigned long long i = 0; i < sl.count; i++) {
+      const GpuMatch& g = sl.records[i];
+      uint64_t pos;
+      bool own;
+      if (g.qs % nq == 0) {  // forward: end position in the global text
+        pos = sb_.window_off + g.text_end;
+        own = (pos > sb_.own_lo && pos <= sb_.own_hi) || (pos == 0 && sb_.own_lo == 0);
+      } else {  // reversed window: scan-direction end e' -> forward start of the match
+        const uint64_t start = sb_.window_off + (wlen - g.text_end);
+        pos = n_global - start;
+        own = (start >= sb_.own_lo && start < sb_.own_hi) || (start == n_global && sb_.own_hi == n_global);
+      }
+      if (own) items.push_back(Item{cand_key((uint32_t)(g.qs % nq), pos), (uint32_t)g.cost, (uint32_t)r, (uint32_t)i});
+    }
+  }
+  std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.key < b.key; });
+  std::vector<uint64_t> keys(items.size());
+  std::vector<uint32_t> cost(items.size());
+  for (size_t i = 0; i < items.size(); i++) keys[i] = items[i].key, cost[i] = items[i].cost;
+  // the kept records as one MatchSet whose "text index" is the source rank
+  MatchSet kept;
+  std::vector<uint32_t> kept_rank;
+  for (size_t i = 0; i < items.size(); i++) {
+    if (!select_candidate(keys.data(), cost.data(), i, items.size(), all_minima)) continue;
+    const PeerGather::Slot sl = pg.slot((int)items[i].rank);
+    if (kept.m.empty()) kept.ops_words = sl.ops_words;
+    GpuMatch g = sl.records[items[i].idx];
+    g.qs = (uint32_t)(items[i].rank * nq + g.qs % nq);
+    kept.m.push_back(g);
+    kept.ops.insert(kept.ops.end(), sl.ops + (size_t)items[i].idx * sl.ops_words,
+                    sl.ops + (size_t)(items[i].idx + 1) * sl.ops_words);
+  }
+  std::vector<Match> out = convert_v1(kept, 1, m, [&](size_t ti) { return (uint64_t)pg.slot((int)ti).text_n; });
+  for (auto& mm : out) {
+    const SlabInfo& sb_ = slabs[mm.text_idx];
+    mm.text_start += sb_.window_off;
+    mm.text_end += sb_.window_off;
+    mm.text_idx = 0;
+  }
+  return out;
 }
 
 std::vector<Match> Searcher::merge_gathered(std::vector<Match>& all, bool all_minima, const SlabInfo* slabs,
@@ -691,6 +788,8 @@ int sassy_gpu_stats(const sassy_SearcherType* searcher, sassy_gpu_Stats* out) {
   out->filter_kind = st.filter_kind;
   out->swar_lanes = st.swar_lanes;
   out->confirmed = st.confirmed;
+  out->dense_tiles = st.dense_tiles;
+  out->reserved3 = 0;
   return 0;
 }
 
@@ -933,9 +1032,7 @@ sassy_gpu_Result* sassy_gpu_text_sharded_flush(sassy_SearcherType* searcher, sas
     if (!searcher || !gather || !slabs || !state) throw std::invalid_argument("null pointer");
     std::vector<sb::SlabInfo> info(n_slabs);
     for (size_t i = 0; i < n_slabs; i++) info[i] = sb::SlabInfo{slabs[i].window_off, slabs[i].own_lo, slabs[i].own_hi};
-    auto v = searcher->s.flush_gathered(gather->g, pattern_len, state);
-    if (*state == 2) return to_result(v);
-    auto merged = searcher->s.merge_gathered(v, all != 0, info.data(), n_slabs, n_global);
+    auto merged = searcher->s.flush_sharded(gather->g, pattern_len, all != 0, info.data(), n_slabs, n_global, state);
     return to_result(merged);
   });
 }

@@ -123,6 +123,10 @@ class Searcher {
   std::vector<Match> flush_gathered(PeerGather& pg, size_t m, int* state);
   std::vector<Match> merge_gathered(std::vector<Match>& all, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
                                     uint64_t n_global);
+  std::vector<Match> merge_collected(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
+                                     uint64_t n_global);
+  std::vector<Match> flush_sharded(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
+                                   uint64_t n_global, int* state);
 
   void validate_pattern(const uint8_t* p, size_t m) const;
 
@@ -144,6 +148,7 @@ class Searcher {
   int max_overhang_ = -1;
   std::unique_ptr<Engine> engine_;
   MatchSet ms_;
+  bool raw_only_ = false;  // search_with_pam leaves the records in ms_ without building Matches
 };
 
 int parse_alphabet(const std::string& alphabet);  // -1 if unknown

@@ -66,6 +66,8 @@ def _lib():
         lib.emu_filter_words.argtypes = [ctypes.c_void_p]
         lib.emu_filter_len.restype = ctypes.c_int
         lib.emu_filter_len.argtypes = [ctypes.c_void_p]
+        lib.emu_dense_tiles.restype = ctypes.c_uint32
+        lib.emu_dense_tiles.argtypes = [ctypes.c_void_p]
         lib.emu_free.argtypes = [ctypes.c_void_p]
         _LIB = lib
     return _LIB
@@ -98,6 +100,7 @@ class EmuBackend:
             ow = lib.emu_ops_words(r)
             self.last_geom = (lib.emu_ltot(r), lib.emu_rows(r))
             self.last_filter = (lib.emu_filter_words(r), lib.emu_filter_len(r), lib.emu_hits(r))
+            self.last_dense_tiles = lib.emu_dense_tiles(r)
             out = []
             for i in range(n):
                 g = ms[i]

@@ -434,3 +434,37 @@ def test_c_abi_search_beyond_capacity_does_not_abort():
     assert _native.last_error() == ""
     lib.sassy_matches_free(out, n)
     lib.sassy_searcher_free(s)
+
+
+@pytest.mark.parametrize("refine", ["1", "2"], ids=["default", "refine-all"])
+def test_gpu_regional_fallback_low_complexity(refine, monkeypatch):
+    """Repeat-rich text (poly-A, di-/tri-nucleotide repeats, a 7-mer satellite, up to 200 KB each)
+    and patterns holding the repeat unit: the tiles the prefilter fires all over are scanned whole,
+    the rest is prefiltered; results equal the full scan (and the oracle on a sub-range)."""
+    import sassy_b200
+    from tests.test_host_emulation import _low_complexity_case
+    monkeypatch.setenv("SASSY_B200_REFINE", refine)
+    rng = random.Random(88)
+    dense_seen = 0
+    for it in range(10):
+        n = rng.randrange(2_000_000, 6_000_000)
+        p, t, k = _low_complexity_case(rng, n)
+        s = sassy_b200.Searcher("dna", rc=True)
+        s.set_filter("force")
+        full = sassy_b200.Searcher("dna", rc=True)
+        full.set_filter("off")
+        for allm in (False, True):
+            got = (s.search_all if allm else s.search)(p, t, k)
+            st = s.stats()
+            want = (full.search_all if allm else full.search)(p, t, k)
+            assert list(map(key, got)) == list(map(key, want)), (p, k, allm, st)
+            assert st["filter_words"] > 0 and st["filter_fallback"] == 0, st
+            dense_seen += st["dense_tiles"] > 0
+        # the oracle on a window around the first repeat-borne match
+        if want:
+            x = want[len(want) // 2]
+            lo, hi = max(0, x.text_start - 3000), min(n, x.text_end + 3000)
+            w = {(y.text_start + lo, y.text_end + lo, y.cost, y.strand, y.cigar)
+                 for y in oracle.search("dna", p, t[lo:hi], k, rc=True, all_minima=True)}
+            assert (x.text_start, x.text_end, x.cost, x.strand, x.cigar) in w
+    assert dense_seen >= 5, dense_seen

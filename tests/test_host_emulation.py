@@ -339,3 +339,46 @@ def test_emu_encoded_overhang_fuzz():
             got = b.search_encoded("iupac", pats, t, k, rc=True, all_minima=allm, alpha=0.5)
             kk = lambda x: (x.pattern_idx, x.text_start, x.text_end, x.pattern_start, x.pattern_end, x.cost, x.strand, x.cigar)
             assert sorted(map(kk, got)) == sorted(map(kk, want)), (pats, t, k, allm)
+
+
+def _low_complexity_case(rng, n):
+    """A pattern with a low-complexity stretch and a text that holds long repeats of exactly that
+    stretch (poly-A, a dinucleotide repeat, a 7-mer satellite) between random sequence, plus planted
+    copies of the pattern: the prefilter fires at (almost) every position of the repeats."""
+    unit = rng.choice([b"A", b"AC", b"AAT", b"ACGTTGA"])
+    m = rng.choice([20, 24, 40, 64, 100])
+    k = rng.choice([1, 2, 3]) if m < 40 else rng.choice([2, 4, 8])
+    rep = (unit * (m // len(unit) + 1))[:rng.randrange(m // 2, m - 2)]
+    p = bytearray(rand_seq(rng, m))
+    at = rng.randrange(0, m - len(rep) + 1)
+    p[at:at + len(rep)] = rep
+    p = bytes(p)
+    t = bytearray(rand_seq(rng, n))
+    for _ in range(rng.randrange(1, 4)):
+        ln = rng.randrange(200, max(400, n // 3))
+        pos = rng.randrange(0, max(1, n - ln))
+        t[pos:pos + ln] = (unit * (ln // len(unit) + 1))[:ln]
+    for _ in range(4):
+        q = mutate(rng, p, rng.randrange(0, k + 1))
+        pos = rng.randrange(0, max(1, n - len(q)))
+        t[pos:pos + len(q)] = q
+    return p, bytes(t[:n]), k
+
+
+@pytest.mark.parametrize("mode", [1, 2, 4])
+def test_emu_regional_fallback_low_complexity(mode):
+    """Repeat-rich text: tiles whose hits would cost more to re-scan than the tile itself are scanned
+    whole, the rest goes through the prefilter; the union equals the oracle (both prefilter routes,
+    both strands)."""
+    rng = random.Random(77 + mode)
+    dense_seen = 0
+    for it in range(24):
+        n = rng.randrange(20_000, 70_000)
+        p, t, k = _low_complexity_case(rng, n)
+        for allm in (False, True):
+            want = oracle.search("dna", p, t, k, rc=True, all_minima=allm)
+            b = EmuBackend(ltot=rng.choice([64, 128]), use_filter=mode)
+            got = b.search("dna", p, t, k, rc=True, all_minima=allm)
+            assert list(map(key, got)) == list(map(key, want)), (p, k, allm, b.last_filter, b.last_dense_tiles)
+            dense_seen += b.last_dense_tiles > 0
+    assert dense_seen >= 8, dense_seen
