@@ -56,6 +56,49 @@ void scan_rows(const ScanArgs& a, const uint32_t* eq_q, uint32_t qs) {
   }
 }
 
+// The body of scan2_kernel: two one-word patterns per "thread" through the raw-byte pair table.
+template <bool REV>
+void scan2_rows(const ScanArgs& a, const uint32_t* eq_all /*[queries][nrows]*/, uint32_t nqueries, uint32_t qs_base) {
+  const uint32_t npairs = (nqueries + 1) / 2;
+  const uint32_t total = a.g.nwarm + a.g.nstage;
+  const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
+  for (uint32_t pq = 0; pq < npairs; pq++) {
+    const uint32_t qa = 2 * pq;
+    const bool has_b = qa + 1 < nqueries;
+    const uint32_t qb = has_b ? qa + 1 : qa;
+    EqPair pair[256];
+    for (uint32_t c = 0; c < 256; c++) {
+      const uint32_t row = (c >> a.sh0) & (a.msk0 & 0xFFu);
+      pair[c].x = eq_all[(size_t)qa * a.nrows + row];
+      pair[c].y = eq_all[(size_t)qb * a.nrows + row];
+    }
+    for (uint64_t row = 0; row < tiles * kScanThreads; row++) {
+      if (a.tile_list && !a.dense[row / kScanThreads]) continue;
+      Lane2 s;
+      lane2_reset(s, a.m);
+      int prev_a = a.m, prev_b = a.m;
+      for (uint32_t it = 0; it < total; it++) {
+        int64_t r;
+        uint32_t col;
+        bool own;
+        stage_coord<REV>(a.g, it, (int64_t)row, r, col, own);
+        const uint64_t stage_idx = (uint64_t)(r * (int64_t)a.g.ltot + (int64_t)col);
+        const bool special = stage_is_special(a, stage_idx);
+        const bool valid = r >= 0 && r < (int64_t)a.g.rows;
+        for (int cc = 0; cc < kStageBytes / 16; cc++) {
+          const int c = REV ? (kStageBytes / 16 - 1 - cc) : cc;
+          uint32_t x[4] = {0, 0, 0, 0};
+          if (valid) memcpy(x, a.text + stage_idx + 16u * c, 16);
+          if (special)
+            process16_2<REV, true>(s, prev_a, prev_b, x, stage_idx + 16u * c, a, pair, 0, qs_base + qa, has_b, own);
+          else
+            process16_2<REV, false>(s, prev_a, prev_b, x, stage_idx + 16u * c, a, pair, 0, qs_base + qa, has_b, own);
+        }
+      }
+    }
+  }
+}
+
 template <int WF, bool REV>
 void filter_rows(const ScanArgs& a, const uint32_t* feq_q, uint32_t qs, bool pair) {
   EqTab eqt;
@@ -394,6 +437,7 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
   for (uint32_t q = 0; q < nq; q++) qptr[q] = queries + (size_t)q * m;
   // Regional fallback of Engine::search: tiles of the scan geometry with more hits than a re-scan is
   // worth are marked dense (their hits are skipped) and scanned whole.
+  const bool force_regional = getenv("SASSY_EMU_FORCE_REGIONAL") != nullptr;  // tests: small texts never reach heavy_hits
   std::vector<uint8_t> dense_flags;
   std::vector<uint32_t> dense_list(1, 0);
   uint32_t dense_count = 0;
@@ -405,7 +449,8 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
     dense_flags.assign(ntiles + 1, 0);
     a.tile_bytes = tile_bytes;
     a.dense = dense_flags.data();
-    if ((double)nhits < std::max(1.0, max_hits)) return;
+    // Engine::search: the regional pass runs only above `heavy_hits`
+    if ((double)nhits <= std::max(1024.0, 0.25 * (double)n * nq / hit_cost) && !force_regional) return;
     std::vector<uint32_t> counts(ntiles + 1, 0);
     for (unsigned long long h = 0; h < nhits; h++) counts[(key_pos(hits[h]) * kHitChars) / tile_bytes]++;
     for (uint32_t t = 0; t < ntiles; t++)
@@ -527,7 +572,21 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
     }
     scan_dense(a);
   } else if (n > 0) {
+    uint32_t nf = 0;
+    while (nf < nq && !rev[nf]) nf++;
+    const bool no_scan2 = getenv("SASSY_EMU_NO_SCAN2") != nullptr;
+    // as Engine::search: batches of one-word patterns take two patterns per thread
+    if (W == 1 && nf >= 2 && !no_scan2) {
+      a.reset_idx = 0;
+      scan2_rows<false>(a, &eq[0], nf, 0);
+    }
+    if (W == 1 && nq - nf >= 2 && !no_scan2) {
+      a.reset_idx = n - 1;
+      scan2_rows<true>(a, &eq[(size_t)nf * pp.nrows], nq - nf, nf);
+    }
     for (uint32_t q = 0; q < nq; q++) {
+      const bool paired = W == 1 && !no_scan2 && (rev[q] ? nq - nf >= 2 : nf >= 2);
+      if (paired) continue;
       const uint32_t* eq_q = &eq[(size_t)q * pp.nrows * W];
       if (rev[q]) {
         a.reset_idx = n - 1;

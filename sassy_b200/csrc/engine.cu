@@ -71,6 +71,8 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
   if (qsq && !strcmp(qsq, "0")) qgram_seq_ = false;
   const char* qq = getenv("SASSY_B200_QGRAM_MIN_Q");
   if (qq) qgram_min_q_ = std::max(6, std::min(8, atoi(qq)));
+  const char* s2 = getenv("SASSY_B200_SCAN2");
+  if (s2 && !strcmp(s2, "0")) scan2_ = false;
   const char* rf = getenv("SASSY_B200_REFINE");
   if (rf) refine_mode_ = std::max(0, std::min(2, atoi(rf)));
   const char* rb = getenv("SASSY_B200_FILTER_ROW_BYTES");
@@ -177,9 +179,14 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
   bool sent = false;
   if (transport_mode_ == 1 && profile_ == kDna && n >= (8ull << 20)) {
     if (!pool_) {
+      // one process per GPU (torchrun): the host cores are shared by LOCAL_WORLD_SIZE packing pools
       int nt = (int)std::thread::hardware_concurrency();
       const char* e = getenv("SASSY_B200_PACK_THREADS");
-      if (e) nt = atoi(e);
+      const char* lw = getenv("LOCAL_WORLD_SIZE");
+      if (e)
+        nt = atoi(e);
+      else if (lw && atoi(lw) > 1)
+        nt = std::max(2, nt / atoi(lw));
       nt = std::max(1, std::min(nt, 64));
       pool_ = new PackPool(nt);
       pack_gbps_ = 5.0 * nt;  // first guess; refined from every transfer
@@ -670,10 +677,11 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   if (pg && pg->broken()) throw CudaError("this peer gather timed out earlier and cannot be used again");
   const bool pg_slot = pg && small_path && out.ops_words <= pg->max_ops_words() && pg->cap() >= (size_t)kSmallCandidates;
   bool pg_pushed = false, small_in_slot = false;
+  unsigned long long pg_hit_limit = ~0ull;  // prefilter routes: more hits than this -> the slot is marked incomplete
   auto pg_exchange = [&](bool force_overflow) {
     if (!pg || pg_pushed) return;
     pg_pushed = true;
-    SB_CUDA(pg->exchange(d_counts, a.cand_cap, fp.enabled ? hit_cap_ : ~0ull, out.ops_words, force_overflow, n,
+    SB_CUDA(pg->exchange(d_counts, a.cand_cap, pg_hit_limit, out.ops_words, force_overflow, n,
                          pg_user_, stream_));
     stats_.aux_launches += 2;
   };
@@ -729,7 +737,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
         throw CudaError("peer gather timed out (SASSY_B200_GATHER_TIMEOUT_S): a rank did not reach the previous search");
       }
       gather_ok_ = small_in_slot && h_counts[3] == 0 && h_counts[0] <= a.cand_cap &&
-                   (!(fp.enabled || qgram) || h_counts[2] <= hit_cap_) && h_counts[1] <= pg->cap();
+                   h_counts[2] <= pg_hit_limit && h_counts[1] <= pg->cap();
       return gather_ok_;
     }
     if (!pg || !pg_pushed || gather_ok_) return gather_ok_;
@@ -823,33 +831,46 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     v.hit_keys = hits_.as<uint64_t>();
     v.hit_count = d_hit_count;
     v.hit_cap = hit_cap_;
-    // Regional fallback (device-side decision, no host round trip): tiles of the scan geometry with
-    // more hits than re-scanning is worth are marked dense; their hits are skipped below and the
-    // bit-parallel scan runs over exactly those tiles.  Uniform text marks nothing (three tiny
-    // launches); a satellite or a poly-A stretch costs the scan of its own tiles, not of the text.
+    // Regional fallback.  A tile = the kScanThreads rows of one block of the scan geometry.  When the
+    // prefilter fires so often that re-scanning the hit neighbourhoods would cost a sizeable part of
+    // a full scan (repeats, low-complexity sequence), a second pass marks the tiles whose hits are
+    // not worth re-scanning as dense, drops their hits and runs the bit-parallel scan over exactly
+    // those tiles: a satellite or a poly-A stretch then costs the scan of its own tiles, not of the
+    // whole text.  The first pass carries a device-side guard (refine / verify return at once above
+    // `heavy_hits`), so a pathological text does not pay for a useless re-scan first.
     const uint32_t ntiles = (g.rows + kScanThreads - 1) / kScanThreads;
     const uint64_t tile_bytes = (uint64_t)kScanThreads * g.ltot;
-    uint32_t* d_dense_count = nullptr;
-    {
-      // per-hit cost in scanned characters: an unrefined hit re-scans 2(m+k)+16 characters; a q-gram
-      // hit costs its refinement plus, in a repeat, a re-scan of about that size
-      const double hit_cost = qgram ? 32.0 + 0.25 * (2.0 * (m + k) + kHitChars) : 2.0 * (m + k) + kHitChars;
-      const double max_hits = 0.5 * (double)tile_bytes * nq * W / (hit_cost * W);  // re-scan <= half a tile scan
+    // per-hit cost in scanned characters: an unrefined hit re-scans 2(m+k)+16 characters; a q-gram
+    // hit costs its refinement plus, in a repeat, a re-scan of about that size
+    const double hit_cost = qgram ? 32.0 + 0.25 * (2.0 * (m + k) + kHitChars) : 2.0 * (m + k) + kHitChars;
+    const unsigned long long heavy_hits = (unsigned long long)std::max(1024.0, 0.25 * (double)n * nq / hit_cost);
+    v.guard_count = d_hit_count;
+    v.guard_limit = heavy_hits;
+    pg_hit_limit = std::min<unsigned long long>(hit_cap_, heavy_hits);
+    auto enable_regional = [&]() {
+      const double max_hits = 0.5 * (double)tile_bytes * nq / hit_cost;  // re-scan <= half a tile scan
       tiles_.ensure((size_t)ntiles * 9 + 64);
       uint32_t* d_tile_counts = tiles_.as<uint32_t>();
       uint32_t* d_tile_list = d_tile_counts + ntiles;
       uint8_t* d_dense = reinterpret_cast<uint8_t*>(d_tile_list + ntiles);
-      d_dense_count = reinterpret_cast<uint32_t*>(d_counts + 5);
+      uint32_t* d_dense_count = reinterpret_cast<uint32_t*>(d_counts + 5);
       SB_CUDA(cudaMemsetAsync(d_tile_counts, 0, (size_t)ntiles * 9, stream_));
-      v.tile_bytes = tile_bytes;
-      SB_CUDA(launch_tile_marks(v, ntiles, d_tile_counts, /*min_hits=*/(unsigned long long)std::max(1.0, max_hits),
-                                (uint32_t)std::min(max_hits, 4.0e9), d_dense, d_tile_list, d_dense_count, stream_));
+      SB_CUDA(cudaMemsetAsync(d_dense_count, 0, sizeof(unsigned long long), stream_));
+      ScanArgs h = v;
+      h.hit_keys = hits_.as<uint64_t>();
+      h.hit_count = d_hit_count;
+      h.tile_bytes = tile_bytes;
+      SB_CUDA(launch_tile_marks(h, ntiles, d_tile_counts, /*min_hits=*/0, (uint32_t)std::min(max_hits, 4.0e9), d_dense,
+                                d_tile_list, d_dense_count, stream_));
       stats_.aux_launches += 2;
+      v.tile_bytes = tile_bytes;
       v.dense = d_dense;
+      v.guard_limit = 0;
       a.tile_list = d_tile_list;
       a.tile_count = d_dense_count;
-    }
+    };
     auto scan_dense_tiles = [&]() {  // the listed tiles, with the exact recurrences (both directions)
+      if (!a.tile_list) return;
       CUtensorMap tmap;
       memset(&tmap, 0, sizeof tmap);
       if (variant_ == kVariantTma) make_tensor_map(&tmap, text, g);
@@ -870,31 +891,46 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     // (piece-automaton hits ARE share occurrences: refining them costs a pass over ~10^6 hits and
     //  buys shorter but unaligned windows -- measured slower on c2; q-gram hits are mostly false)
     const bool refine = conf_pieces_ > 0 && (refine_mode_ == 2 || (refine_mode_ == 1 && qgram));
-    if (refine) {
-      // Dna: every hit is refined exactly by one thread -- which share of the pattern occurs behind
-      // it, and where -- and the (few) survivors are written to a second list as nominal end
-      // positions: the re-scan covers 2k + 1 end positions per entry instead of 16 + m + k, on
-      // dense warps (refine_hit in scan_core.cuh)
-      hits2_.ensure(hit_cap_ * (sizeof(uint64_t) + sizeof(uint32_t)));
-      uint32_t* spans = reinterpret_cast<uint32_t*>(hits2_.as<uint64_t>() + hit_cap_);
-      ScanArgs cf = v;
-      cf.qconf = reinterpret_cast<const uint32_t*>(dst + off_qconf_);
-      cf.qnp = (uint32_t)conf_pieces_;
-      SB_CUDA(launch_refine(cf, d_rev, hits2_.as<uint64_t>(), spans, d_counts + 4, stream_));
+    // refine (Dna q-gram hits) -> verify -> scan of dense tiles (regional pass only) -> tail -> counters
+    auto rescan_pass = [&]() {
+      ScanArgs vv = v;
+      if (refine) {
+        // every hit is refined exactly by one thread -- which share of the pattern occurs behind it,
+        // and where -- and the (few) survivors are written to a second list as nominal end
+        // positions: the re-scan covers 2k + 1 end positions per entry instead of 16 + m + k, on
+        // dense warps (refine_hit in scan_core.cuh)
+        hits2_.ensure(hit_cap_ * (sizeof(uint64_t) + sizeof(uint32_t)));
+        uint32_t* spans = reinterpret_cast<uint32_t*>(hits2_.as<uint64_t>() + hit_cap_);
+        ScanArgs cf = v;
+        cf.qconf = reinterpret_cast<const uint32_t*>(dst + off_qconf_);
+        cf.qnp = (uint32_t)conf_pieces_;
+        SB_CUDA(cudaMemsetAsync(d_counts + 4, 0, sizeof(unsigned long long), stream_));
+        SB_CUDA(launch_refine(cf, d_rev, hits2_.as<uint64_t>(), spans, d_counts + 4, stream_));
+        stats_.aux_launches++;
+        vv.hit_keys = hits2_.as<uint64_t>();
+        vv.hit_span = spans;
+        vv.hit_count = d_counts + 4;
+        vv.hit_exact = 1;
+        vv.rev_lead = 0;
+        vv.dense = nullptr;  // dropped during the refinement already
+      }
+      vv.cand_keys = a.cand_keys, vv.cand_cost = a.cand_cost, vv.cand_cap = a.cand_cap;
+      SB_CUDA(launch_verify(W, vv, d_rev, stream_));
       stats_.aux_launches++;
-      v.hit_keys = hits2_.as<uint64_t>();
-      v.hit_span = spans;
-      v.hit_count = d_counts + 4;
-      v.hit_exact = 1;
-      v.rev_lead = 0;
+      scan_dense_tiles();
+      SB_CUDA(cudaEventRecord(ev_[4], stream_));
+      queue_small_tail();
+      read_counts();
+    };
+    rescan_pass();
+    if (h_counts[2] > heavy_hits && h_counts[2] <= hit_cap_) {
+      // many hits: second pass with the dense tiles scanned whole (the hit list is still valid)
+      stats_.retries++;
+      reset_candidates();
+      enable_regional();
+      rescan_pass();
     }
-    SB_CUDA(launch_verify(W, v, d_rev, stream_));
-    stats_.aux_launches++;
-    scan_dense_tiles();
-    SB_CUDA(cudaEventRecord(ev_[4], stream_));
-    queue_small_tail();
-    read_counts();
-    stats_.dense_tiles = (uint32_t)(h_counts[5] & 0xFFFFFFFFu);
+    stats_.dense_tiles = a.tile_list ? (uint32_t)(h_counts[5] & 0xFFFFFFFFu) : 0u;
     stats_.filter_ms = elapsed(ev_[1], ev_[2]);
     stats_.verify_ms = elapsed(ev_[2], ev_[4]);
     unsigned long long nhits = h_counts[2];
@@ -933,14 +969,8 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
         cand_cap_ = (size_t)(cnt + cnt / 8 + 1024);
         stats_.retries++;
         reset_candidates();
-        v.cand_keys = a.cand_keys, v.cand_cost = a.cand_cost, v.cand_cap = a.cand_cap;
         SB_CUDA(cudaEventRecord(ev_[2], stream_));
-        SB_CUDA(launch_verify(W, v, d_rev, stream_));
-        stats_.aux_launches++;
-        scan_dense_tiles();
-        SB_CUDA(cudaEventRecord(ev_[4], stream_));
-        queue_small_tail();
-        read_counts();
+        rescan_pass();
         stats_.verify_ms += elapsed(ev_[2], ev_[4]);
       }
       filtered = true;
@@ -959,12 +989,16 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       reset_candidates();
       SB_CUDA(cudaEventRecord(ev_[1], stream_));
       if (n > 0) {
+        // batches of one-word patterns: two patterns per thread (scan2_kernel)
         if (nfwd) {
           a.reset_idx = 0;
           a.nq = nfwd;
           a.qs_base = 0;
           a.eq = d_eq;
-          SB_CUDA(launch_scan(W, false, variant_, &tmap, a, stream_));
+          if (W == 1 && nfwd >= 2 && scan2_)
+            SB_CUDA(launch_scan2(false, variant_, &tmap, a, stream_));
+          else
+            SB_CUDA(launch_scan(W, false, variant_, &tmap, a, stream_));
           stats_.scan_launches++;
         }
         if (nq > nfwd) {
@@ -972,9 +1006,13 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
           a.nq = nq - nfwd;
           a.qs_base = nfwd;
           a.eq = d_eq + (size_t)nfwd * nrows_ * W;
-          SB_CUDA(launch_scan(W, true, variant_, &tmap, a, stream_));
+          if (W == 1 && nq - nfwd >= 2 && scan2_)
+            SB_CUDA(launch_scan2(true, variant_, &tmap, a, stream_));
+          else
+            SB_CUDA(launch_scan(W, true, variant_, &tmap, a, stream_));
           stats_.scan_launches++;
         }
+        stats_.swar_lanes = (W == 1 && scan2_ && (nfwd >= 2 || nq - nfwd >= 2)) ? 2u : 1u;
       }
       if (ov) {
         a.nq = nq;

@@ -70,7 +70,7 @@ struct SearchStats {
   uint32_t transfer_packed = 0;  // 1: sent at 2 bits per character (Dna transport encoding)
   uint64_t transfer_bytes = 0;   // bytes that crossed PCIe for the text
   uint32_t filter_kind = 0;      // 0 none, 1 piece automaton (Shift-And), 2 q-gram bitmap, 3 SWAR suffix scan
-  uint32_t swar_lanes = 0;       // patterns per 32-bit word of the scan that produced the candidates (0/1 = one)
+  uint32_t swar_lanes = 0;       // patterns per THREAD of the scan that produced the candidates (0/1 = one, 2 = scan2_kernel)
   uint64_t confirmed = 0;        // prefilter hits that were re-scanned (q-gram: after the exact confirmation)
   uint32_t dense_tiles = 0;      // tiles of the scan geometry that were scanned whole (regional fallback)
 };
@@ -182,6 +182,7 @@ class Engine {
   bool qgram_seq_ = true;   // contiguous-tile q-gram kernel (SASSY_B200_QGRAM_SEQ=0: row-tiled kernel)
   size_t off_qconf_ = 0;
   int conf_pieces_ = 0;       // pieces per query in the refinement records of the last upload (0: none)
+  bool scan2_ = true;         // SASSY_B200_SCAN2=0: one pattern per thread for batches of one-word patterns too
   int refine_mode_ = 1;       // SASSY_B200_REFINE: 0 never refine hits, 1 q-gram hits (default), 2 piece-automaton hits too
   int filter_row_bytes_ = 0;  // SASSY_B200_FILTER_ROW_BYTES (experiments): bytes per thread row of the prefilter
   int transport_mode_ = 1;

@@ -25,6 +25,10 @@ int scan_blocks_per_sm(int W, bool rev, int variant, uint32_t nrows);
 cudaError_t launch_scan(int W, bool rev, int variant, const CUtensorMap* tmap, const ScanArgs& a,
                         cudaStream_t stream);
 
+// Batches of one-word patterns (m <= 32): two patterns per thread share the text bytes, the row
+// extraction and one 8-byte table load per character (scan2_kernel).  a.nq = number of patterns.
+cudaError_t launch_scan2(bool rev, int variant, const CUtensorMap* tmap, const ScanArgs& a, cudaStream_t stream);
+
 // Exact piece prefilter (scan_core.cuh): hits -> a.hit_keys; then one thread per hit re-scans
 // the hit's neighbourhood with the full recurrences -> a.cand_*.
 int filter_blocks_per_sm(int WF, int variant, bool pair);

@@ -64,7 +64,8 @@ struct ScanArgs {
   uint32_t rowbytes;  // W * 4
   int32_t m;       // pattern length
   int32_t k;       // threshold
-  uint32_t nq;       // queries in this launch
+  uint32_t nq;       // queries in this launch (scan2_kernel: pattern PAIRS)
+  uint32_t nq_odd;   // scan2_kernel: 1 = the last pair's second pattern is a padding copy
   uint32_t qs_base;  // query slot of the first query (strand * n_patterns + pattern)
   const uint32_t* eq;  // [nq][nrows][W] equality words
   uint64_t* cand_keys;
@@ -91,6 +92,10 @@ struct ScanArgs {
   // scan geometry.  Tiles with so many hits that re-scanning their neighbourhoods would cost more
   // than scanning the tile (repeats, low-complexity sequence) are marked dense: their hits are
   // dropped and the scan kernels run over exactly those tiles (tile_list) instead.
+  // First pass of a prefilter route: refine / verify do nothing when the prefilter produced more than
+  // guard_limit hits (the host then runs the regional pass); guard_limit = 0: no guard.
+  const unsigned long long* guard_count;
+  unsigned long long guard_limit;
   uint64_t tile_bytes;         // text bytes per tile (kScanThreads * ltot of the SCAN geometry); 0 = no tiles
   const uint8_t* dense;        // refine / verify: [tile] != 0 -> skip the hit
   const uint32_t* tile_list;   // scan kernels: block b scans tile tile_list[b / nq] if b / nq < *tile_count
@@ -323,6 +328,135 @@ SB_HD void process16(Lane<W>& s, int& prev_score, const uint32_t (&x)[4], uint64
   for (int gg = 0; gg < NG; gg++) {
     const int g = REV ? NG - 1 - gg : gg;
     fast_group<W, REV>(s, prev_score, &x[g * NW], base_idx + 4 * NW * g, a, eqs, qs, own);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Two one-word patterns per thread (batches of patterns of at most 32 characters): the text bytes
+// are fetched, the row is extracted and the table address is formed ONCE for both patterns -- the
+// pair table holds {eq of pattern A, eq of pattern B} per text byte, so one 8-byte shared-memory
+// load feeds two recurrences -- and the two dependency chains interleave.  The pair table is
+// indexed by the RAW text byte (256 rows, expanded from the per-class tables when the block
+// starts), which also removes the per-word class extraction.
+struct EqPair {
+  uint32_t x, y;  // equality words of pattern A and pattern B for one text byte
+};
+struct Lane2 {
+  uint32_t pv[2], mv[2];
+};
+
+SB_HD void lane2_reset(Lane2& s, int m) {
+  const int pad = 32 - m;
+  s.pv[0] = s.pv[1] = pad <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << pad);
+  s.mv[0] = s.mv[1] = 0;
+}
+
+SB_HD void myers_step2(Lane2& s, uint32_t eqa, uint32_t eqb) {
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const uint32_t eq = q ? eqb : eqa;
+    const uint32_t pv = s.pv[q], mv = s.mv[q];
+    const uint32_t x = eq | mv;
+    const uint32_t u = (x & pv) + pv;
+    const uint32_t d0 = (u ^ pv) | x;
+    const uint32_t ph = mv | ~(d0 | pv);
+    const uint32_t mh = pv & d0;
+    const uint32_t ph1 = ph << 1, mh1 = mh << 1;
+    s.pv[q] = mh1 | ~(d0 | ph1);
+    s.mv[q] = ph1 & d0;
+  }
+}
+
+// pair = the 256-entry table {eqA, eqB} indexed by the raw text byte (shared memory on the device)
+SB_HD void load_eq2(uint32_t& eqa, uint32_t& eqb, const EqPair* pair, uint32_t saddr, uint32_t x, int b) {
+#if defined(__CUDA_ARCH__)
+  (void)pair;
+  const uint32_t row = __byte_perm(x, 0u, 0x4440u + (uint32_t)b);
+  uint32_t addr;
+  asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(row), "r"(saddr));
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(eqa), "=r"(eqb) : "r"(addr));
+#else
+  (void)saddr;
+  const EqPair e = pair[(x >> (8 * b)) & 0xFFu];
+  eqa = e.x, eqb = e.y;
+#endif
+}
+
+// Exact path of one text word for both patterns (rare: a group that may hold a position <= k, or the
+// stage with the restart index).  qs = slot of pattern A, B = qs + 1 (B is a padding copy when
+// `has_b` is false: nothing is reported for it).
+template <bool REV>
+SB_SLOW Lane2 slow_word2(Lane2 s, uint32_t x, uint64_t base_idx, const ScanArgs& a, const EqPair* pair, uint32_t saddr,
+                         uint32_t qs, bool has_b, bool own) {
+  for (int bb = 0; bb < 4; bb++) {
+    const int b = REV ? 3 - bb : bb;
+    const uint64_t idx = base_idx + (uint64_t)b;
+    if (idx == a.reset_idx) lane2_reset(s, a.m);
+    uint32_t eqa, eqb;
+    load_eq2(eqa, eqb, pair, saddr, x, b);
+    myers_step2(s, eqa, eqb);
+    if (own && idx < a.n) {
+      const uint64_t pos = REV ? a.n - idx : idx + 1;
+      if (pos > a.emit_min) {
+        const int sa = popc32(s.pv[0]) - popc32(s.mv[0]);
+        if (sa <= a.k) emit_candidate(a, qs, pos, sa);
+        const int sb = popc32(s.pv[1]) - popc32(s.mv[1]);
+        if (has_b && sb <= a.k) emit_candidate(a, qs + 1, pos, sb);
+      }
+    }
+  }
+  return s;
+}
+
+// kGroup characters (as fast_group): both scores are checked once per group.
+template <bool REV>
+SB_HD void fast_group2(Lane2& s, int& prev_a, int& prev_b, const uint32_t* xs, uint64_t base_idx, const ScanArgs& a,
+                       const EqPair* pair, uint32_t saddr, uint32_t qs, bool has_b, bool own) {
+  constexpr int NW = kGroup / 4;
+  const Lane2 saved = s;
+#pragma unroll
+  for (int ww = 0; ww < NW; ww++) {
+    const int w = REV ? NW - 1 - ww : ww;
+#pragma unroll
+    for (int bb = 0; bb < 4; bb++) {
+      const int b = REV ? 3 - bb : bb;
+      uint32_t eqa, eqb;
+      load_eq2(eqa, eqb, pair, saddr, xs[w], b);
+      myers_step2(s, eqa, eqb);
+    }
+  }
+  const int sa = popc32(s.pv[0]) - popc32(s.mv[0]);
+  const int sb = popc32(s.pv[1]) - popc32(s.mv[1]);
+  const int lim = 2 * a.k + kGroup;
+  if (prev_a + sa <= lim || prev_b + sb <= lim) {
+    s = saved;
+    for (int ww = 0; ww < NW; ww++) {
+      const int w = REV ? NW - 1 - ww : ww;
+      s = slow_word2<REV>(s, xs[w], base_idx + 4 * w, a, pair, saddr, qs, has_b, own);
+    }
+  }
+  prev_a = sa;
+  prev_b = sb;
+}
+
+template <bool REV, bool EXACT>
+SB_HD void process16_2(Lane2& s, int& prev_a, int& prev_b, const uint32_t (&x)[4], uint64_t base_idx,
+                       const ScanArgs& a, const EqPair* pair, uint32_t saddr, uint32_t qs, bool has_b, bool own) {
+  if (EXACT) {
+    for (int ww = 0; ww < 4; ww++) {
+      const int w = REV ? 3 - ww : ww;
+      s = slow_word2<REV>(s, x[w], base_idx + 4 * w, a, pair, saddr, qs, has_b, own);
+    }
+    prev_a = popc32(s.pv[0]) - popc32(s.mv[0]);
+    prev_b = popc32(s.pv[1]) - popc32(s.mv[1]);
+    return;
+  }
+  constexpr int NW = kGroup / 4;
+  constexpr int NG = 4 / NW;
+#pragma unroll
+  for (int gg = 0; gg < NG; gg++) {
+    const int g = REV ? NG - 1 - gg : gg;
+    fast_group2<REV>(s, prev_a, prev_b, &x[g * NW], base_idx + 4 * NW * g, a, pair, saddr, qs, has_b, own);
   }
 }
 

@@ -231,6 +231,55 @@ __global__ void __launch_bounds__(kScanThreads, min_blocks<W>())
       });
 }
 
+// Batches of one-word patterns: two patterns per thread (scan_core.cuh: Lane2).  Block = (row tile,
+// pattern pair); a.nq counts PAIRS here, a.eq holds the per-class tables of 2 * a.nq - (odd ? 1 : 0)
+// queries (a.nq_odd: the last pair's second pattern is a padding copy of the first).
+template <bool REV, int VARIANT>
+__global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
+    scan2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanArgs a) {
+  __shared__ __align__(16) EqPair pair[256];
+  const uint32_t pq = blockIdx.x % a.nq;  // pattern pair
+  const uint32_t qa = 2 * pq;
+  const bool has_b = !(a.nq_odd && pq + 1 == a.nq);
+  const uint32_t qb = has_b ? qa + 1 : qa;
+  const uint32_t qs = a.qs_base + qa;
+  // expand the two per-class tables to one table indexed by the raw text byte
+  for (uint32_t c = threadIdx.x; c < 256; c += kScanThreads) {
+    const uint32_t row = (c >> a.sh0) & (a.msk0 & 0xFFu);
+    EqPair e;
+    e.x = a.eq[(size_t)qa * a.nrows + row];
+    e.y = a.eq[(size_t)qb * a.nrows + row];
+    pair[c] = e;
+  }
+  const uint32_t saddr = smem_u32(pair);
+  EqTab dummy;
+  dummy.rowbytes = 4;
+  Lane2 s;
+  lane2_reset(s, a.m);
+  int prev_a = a.m, prev_b = a.m;
+  row_pipeline<REV, VARIANT>(
+      tmap, a, nullptr, 0, reinterpret_cast<uint32_t*>(pair), dummy,
+      [&](uint64_t stage_idx, bool own, auto chunk) {
+        if (!stage_is_special(a, stage_idx)) {
+#pragma unroll(kUnroll)
+          for (int cc = 0; cc < kChunks; cc++) {
+            const int c = REV ? (kChunks - 1 - cc) : cc;
+            const uint4 v = chunk(c);
+            const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+            process16_2<REV, false>(s, prev_a, prev_b, x, stage_idx + 16u * c, a, pair, saddr, qs, has_b, own);
+          }
+        } else {
+#pragma unroll 1
+          for (int cc = 0; cc < kChunks; cc++) {
+            const int c = REV ? (kChunks - 1 - cc) : cc;
+            const uint4 v = chunk(c);
+            const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+            process16_2<REV, true>(s, prev_a, prev_b, x, stage_idx + 16u * c, a, pair, saddr, qs, has_b, own);
+          }
+        }
+      });
+}
+
 // Moves a warp's staged hits to the global list with one global atomic.
 __device__ __forceinline__ void flush_hits(const ScanArgs& a, const HitQueue& hq, uint32_t lane) {
   __syncwarp();
@@ -492,6 +541,7 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
 template <int W>
 __global__ void __launch_bounds__(128)
     verify_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags) {
+  if (a.guard_limit && *a.guard_count > a.guard_limit) return;  // too many hits: the regional pass follows
   unsigned long long nhits = *a.hit_count;
   if (nhits > a.hit_cap) nhits = a.hit_cap;
   const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
@@ -1016,6 +1066,7 @@ __global__ void __launch_bounds__(32 * kWideWarps)
     verify_wide_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags) {
   __shared__ uint8_t win[kWideWarps][kWideWindow];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (a.guard_limit && *a.guard_count > a.guard_limit) return;  // too many hits: the regional pass follows
   unsigned long long nhits = *a.hit_count;
   if (nhits > a.hit_cap) nhits = a.hit_cap;
   const unsigned long long nwarps = (unsigned long long)gridDim.x * kWideWarps;
@@ -1090,6 +1141,7 @@ namespace {
 __global__ void __launch_bounds__(256)
     refine_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags, uint64_t* __restrict__ out,
                   uint32_t* __restrict__ out_span, unsigned long long* out_count) {
+  if (a.guard_limit && *a.guard_count > a.guard_limit) return;  // too many hits: the regional pass follows
   unsigned long long nhits = *a.hit_count;
   if (nhits > a.hit_cap) nhits = a.hit_cap;
   const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
@@ -1260,6 +1312,42 @@ cudaError_t launch_texts(int W, const ScanArgs& a, const TextsArgs& t, cudaStrea
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
+}
+
+namespace {
+
+template <bool REV, int VARIANT>
+cudaError_t launch_scan2_one(const CUtensorMap* tmap, const ScanArgs& a, cudaStream_t stream) {
+  auto kern = scan2_kernel<REV, VARIANT>;
+  static size_t tracker[64] = {};
+  const size_t smem = VARIANT == kVariantTma ? 1024 + (size_t)kRingBytes : 0;
+  {
+    cudaError_t e = ensure_smem(kern, smem, tracker);
+    if (e != cudaSuccess) return e;
+  }
+  const uint64_t tiles = ((uint64_t)a.g.rows + kScanThreads - 1) / kScanThreads;
+  const uint64_t blocks = tiles * a.nq;
+  if (blocks == 0) return cudaSuccess;
+  if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+  CUtensorMap dummy;
+  if (!tmap) {
+    memset(&dummy, 0, sizeof dummy);
+    tmap = &dummy;
+  }
+  kern<<<(unsigned)blocks, kScanThreads, smem, stream>>>(*tmap, a);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// a.nq = number of PATTERNS here; pairs are formed inside.
+cudaError_t launch_scan2(bool rev, int variant, const CUtensorMap* tmap, const ScanArgs& a0, cudaStream_t stream) {
+  ScanArgs a = a0;
+  a.nq_odd = a0.nq & 1u;
+  a.nq = (a0.nq + 1) / 2;
+  if (variant == kVariantTma)
+    return rev ? launch_scan2_one<true, kVariantTma>(tmap, a, stream) : launch_scan2_one<false, kVariantTma>(tmap, a, stream);
+  return rev ? launch_scan2_one<true, kVariantLdg>(tmap, a, stream) : launch_scan2_one<false, kVariantLdg>(tmap, a, stream);
 }
 
 size_t scan_smem_bytes(int W, int variant, uint32_t nrows) {

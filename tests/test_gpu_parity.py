@@ -467,4 +467,4 @@ def test_gpu_regional_fallback_low_complexity(refine, monkeypatch):
             w = {(y.text_start + lo, y.text_end + lo, y.cost, y.strand, y.cigar)
                  for y in oracle.search("dna", p, t[lo:hi], k, rc=True, all_minima=True)}
             assert (x.text_start, x.text_end, x.cost, x.strand, x.cigar) in w
-    assert dense_seen >= 5, dense_seen
+    assert dense_seen >= 3, dense_seen

@@ -366,10 +366,11 @@ def _low_complexity_case(rng, n):
 
 
 @pytest.mark.parametrize("mode", [1, 2, 4])
-def test_emu_regional_fallback_low_complexity(mode):
+def test_emu_regional_fallback_low_complexity(mode, monkeypatch):
     """Repeat-rich text: tiles whose hits would cost more to re-scan than the tile itself are scanned
     whole, the rest goes through the prefilter; the union equals the oracle (both prefilter routes,
     both strands)."""
+    monkeypatch.setenv("SASSY_EMU_FORCE_REGIONAL", "1")  # the engine takes this pass above `heavy_hits` only
     rng = random.Random(77 + mode)
     dense_seen = 0
     for it in range(24):
