@@ -161,7 +161,11 @@ def test_gpu_candidate_overflow_retry(tma):
     t = b"N" * n
     ms = s.search(b"ACGTACGT", t, 0)  # one plateau -> a single local minimum at the text end
     assert [(m.text_start, m.text_end, m.cost) for m in ms] == [(n - 8, n, 0)]
-    assert s.stats()["retries"] >= 1 and s.stats()["candidates"] == n - 7
+    # every end position is a candidate (the regional pass scans the dense tiles whole; the hits of a
+    # sparse last tile are re-scanned, which may list a few positions twice)
+    st = s.stats()
+    assert st["retries"] >= 1 and n - 7 <= st["candidates"] <= n - 7 + 20000, st
+    assert st["dense_tiles"] >= 1
 
 
 def test_prefilter_routes(tma):
