@@ -676,7 +676,7 @@ def main():
 
         def step_resident():
             if tshard:
-                return sdist.search_text_sharded(s, pats[0], dt, k, n_global, peer_gather=pg)
+                return sdist.search_text_sharded(s, pats[0], dt, k, n_global, peer_gather=pg, layout=layout)
             if pg is not None:
                 return pg.search_encoded(enc, dt, k)
             ms = s.search_encoded_patterns(enc, dt, k) if batch else s.search(pats[0], dt, k)

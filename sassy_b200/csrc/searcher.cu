@@ -449,26 +449,39 @@ std::vector<Match> Searcher::merge_collected(PeerGather& pg, size_t m, bool all_
   };
   std::vector<Item> items;
   const size_t nq = rc_ ? 2 : 1;
-  for (int r = 0; r < pg.world() && (size_t)r < n_slabs; r++) {
-    const PeerGather::Slot sl = pg.slot(r);
-    const SlabInfo& sb_ = slabs[r];
-    const uint64_t wlen = sl.text_n;
-    for (unsigned long long i = 0; i < sl.count; i++) {
-      const GpuMatch& g = sl.records[i];
-      uint64_t pos;
-      bool own;
-      if (g.qs % nq == 0) {  // forward: end position in the global text
-        pos = sb_.window_off + g.text_end;
-        own = (pos > sb_.own_lo && pos <= sb_.own_hi) || (pos == 0 && sb_.own_lo == 0);
-      } else {  // reversed window: scan-direction end e' -> forward start of the match
-        const uint64_t start = sb_.window_off + (wlen - g.text_end);
-        pos = n_global - start;
-        own = (start >= sb_.own_lo && start < sb_.own_hi) || (start == n_global && sb_.own_hi == n_global);
+  const int nr = std::min<int>(pg.world(), (int)n_slabs);
+  // Every rank's records are sorted by (strand, scan-direction end) and the slabs own disjoint,
+  // increasing ranges: forward records in rank order, reverse-complement records (whose scan runs
+  // right to left) in reverse rank order, are sorted as they come -- the sort below only runs if a
+  // caller's slabs break that order.
+  bool sorted = true;
+  for (size_t strand = 0; strand < nq; strand++) {
+    for (int rr = 0; rr < nr; rr++) {
+      const int r = strand == 0 ? rr : nr - 1 - rr;
+      const PeerGather::Slot sl = pg.slot(r);
+      const SlabInfo& sb_ = slabs[r];
+      const uint64_t wlen = sl.text_n;
+      for (unsigned long long i = 0; i < sl.count; i++) {
+        const GpuMatch& g = sl.records[i];
+        if (g.qs % nq != strand) continue;
+        uint64_t pos;
+        bool own;
+        if (strand == 0) {  // forward: end position in the global text
+          pos = sb_.window_off + g.text_end;
+          own = (pos > sb_.own_lo && pos <= sb_.own_hi) || (pos == 0 && sb_.own_lo == 0);
+        } else {  // reversed window: scan-direction end e' -> forward start of the match
+          const uint64_t start = sb_.window_off + (wlen - g.text_end);
+          pos = n_global - start;
+          own = (start >= sb_.own_lo && start < sb_.own_hi) || (start == n_global && sb_.own_hi == n_global);
+        }
+        if (!own) continue;
+        const uint64_t key = cand_key((uint32_t)strand, pos);
+        if (!items.empty() && items.back().key > key) sorted = false;
+        items.push_back(Item{key, (uint32_t)g.cost, (uint32_t)r, (uint32_t)i});
       }
-      if (own) items.push_back(Item{cand_key((uint32_t)(g.qs % nq), pos), (uint32_t)g.cost, (uint32_t)r, (uint32_t)i});
     }
   }
-  std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.key < b.key; });
+  if (!sorted) std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.key < b.key; });
   std::vector<uint64_t> keys(items.size());
   std::vector<uint32_t> cost(items.size());
   for (size_t i = 0; i < items.size(); i++) keys[i] = items[i].key, cost[i] = items[i].cost;

@@ -276,9 +276,7 @@ class PeerGather:
         import ctypes
         from .searcher import _as_buffer
         paddr, plen, keep = _as_buffer(pattern)
-        slabs = np.zeros((len(layout), 3), dtype=np.uint64)
-        for r, (wlo, _whi, lo, hi) in enumerate(layout):
-            slabs[r] = (wlo, lo, hi)
+        slabs = self._slabs(layout)
         ok = ctypes.c_int(0)
         res = self._lib.sassy_gpu_search_text_sharded(self._searcher._h, self._h, paddr, plen, window_text._h, k,
                                                       int(all_minima), slabs.ctypes.data, len(layout), n_global,
@@ -292,12 +290,21 @@ class PeerGather:
         allm = gather_matches(tag_rank(ms, self.rank), self.max_ops, group=self._group)
         return merge_slabs(allm, layout, n_global, all_minima)
 
+    def _slabs(self, layout):
+        """sassy_gpu_Slab array of a slab_layout() (cached: the layout of a sharded text does not change)."""
+        key = id(layout)
+        cached = getattr(self, "_slab_cache", None)
+        if cached is None or cached[0] != key or cached[1] != len(layout):
+            slabs = np.zeros((len(layout), 3), dtype=np.uint64)
+            for r, (wlo, _whi, lo, hi) in enumerate(layout):
+                slabs[r] = (wlo, lo, hi)
+            self._slab_cache = cached = (key, len(layout), slabs, layout)
+        return cached[2]
+
     def flush_sharded(self, pattern_len: int, layout, n_global: int, all_minima: bool = False):
         """Pipelined mode: the result of the last search_sharded call (None if nothing is pending)."""
         import ctypes
-        slabs = np.zeros((len(layout), 3), dtype=np.uint64)
-        for r, (wlo, _whi, lo, hi) in enumerate(layout):
-            slabs[r] = (wlo, lo, hi)
+        slabs = self._slabs(layout)
         state = ctypes.c_int(0)
         res = self._lib.sassy_gpu_text_sharded_flush(self._searcher._h, self._h, pattern_len, int(all_minima),
                                                      slabs.ctypes.data, len(layout), n_global, ctypes.byref(state))
@@ -363,7 +370,7 @@ def merge_slabs(matches, layout, n_global: int, all_minima: bool = False):
 
 
 def search_text_sharded(searcher, pattern: bytes, window_text, k: int, n_global: int, all_minima: bool = False,
-                        peer_gather: "PeerGather" = None, group=None):
+                        peer_gather: "PeerGather" = None, group=None, layout=None):
     """Searcher::search / search_all of ONE text that is cut into `world` slabs, one per rank.
 
     `window_text` holds this rank's window slab_layout(n_global, world, m, k)[rank] (a DeviceText,
@@ -374,7 +381,8 @@ def search_text_sharded(searcher, pattern: bytes, window_text, k: int, n_global:
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     m = len(pattern)
-    layout = slab_layout(n_global, world, m, k)
+    if layout is None:
+        layout = slab_layout(n_global, world, m, k)
     if peer_gather is not None:
         # search_all + fused gather + merge inside the library (one call, one host synchronisation)
         return peer_gather.search_sharded(pattern, window_text, k, layout, n_global, all_minima)
