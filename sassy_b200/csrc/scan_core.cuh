@@ -371,7 +371,17 @@ SB_HD void myers_step2(Lane2& s, uint32_t eqa, uint32_t eqb) {
 SB_HD void load_eq2(uint32_t& eqa, uint32_t& eqb, const EqPair* pair, uint32_t saddr, uint32_t x, int b) {
 #if defined(__CUDA_ARCH__)
   (void)pair;
+  // The ALU pipe (LOP3) is the bottleneck of this kernel (ncu: 90 % busy), the FMA pipe is not: the
+  // text byte is extracted with integer multiplies (x * 2^(24-8b) keeps byte b on top, the high
+  // word of that times 2^8 is the byte) instead of a PRMT.
+#ifndef SB_EQ2_PRMT
+  uint32_t top = x;
+  if (b < 3) asm("mul.lo.u32 %0, %1, %2;" : "=r"(top) : "r"(x), "r"(1u << (8 * (3 - b))));
+  uint32_t row;
+  asm("mul.hi.u32 %0, %1, 256;" : "=r"(row) : "r"(top));
+#else
   const uint32_t row = __byte_perm(x, 0u, 0x4440u + (uint32_t)b);
+#endif
   uint32_t addr;
   asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(row), "r"(saddr));
   asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(eqa), "=r"(eqb) : "r"(addr));
