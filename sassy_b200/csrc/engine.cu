@@ -97,6 +97,7 @@ Engine::~Engine() {
   if (h_stage_) cudaFreeHost(h_stage_);
   if (h_pack_) cudaFreeHost(h_pack_);
   if (h_small_) cudaFreeHost(h_small_);
+  if (h_texts_) cudaFreeHost(h_texts_);
   sel_small_.release();
   d_pack_.release();
   delete pool_;
@@ -1126,13 +1127,41 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
   }
   const size_t text_bytes = (size_t)total + 64;
   const size_t meta_off = (text_bytes + 255) & ~(size_t)255;
-  std::vector<uint8_t> packed(meta_off + meta.size() * sizeof(uint64_t), 0);
-  for (size_t i = 0; i < ntexts; i++)
-    if (lens[i]) memcpy(&packed[meta[i]], texts[i], lens[i]);
-  memcpy(&packed[meta_off], meta.data(), meta.size() * sizeof(uint64_t));
-  d_texts_.ensure(packed.size());
+  const size_t packed_bytes = meta_off + meta.size() * sizeof(uint64_t);
+  // staged in PINNED memory (kept between calls) by a few threads: hundreds of megabytes of reads
+  // would otherwise cross PCIe from pageable memory at a fraction of the link rate
+  if (packed_bytes > h_texts_cap_) {
+    if (h_texts_) cudaFreeHost(h_texts_);
+    h_texts_ = nullptr;
+    h_texts_cap_ = 0;
+    SB_CUDA(cudaHostAlloc((void**)&h_texts_, packed_bytes + packed_bytes / 4, cudaHostAllocDefault));
+    h_texts_cap_ = packed_bytes + packed_bytes / 4;
+  }
+  uint8_t* packed = h_texts_;
+  {
+    const size_t nthreads = total > (8u << 20) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    auto copy_range = [&](size_t t0, size_t t1) {
+      for (size_t i = t0; i < t1; i++) {
+        if (lens[i]) memcpy(packed + meta[i], texts[i], lens[i]);
+        const uint64_t end = meta[i] + lens[i];
+        const uint64_t next = i + 1 < ntexts ? meta[i + 1] : text_bytes;
+        if (next > end) memset(packed + end, 0, next - end);  // alignment padding reads as zero bytes
+      }
+    };
+    if (nthreads == 1) {
+      copy_range(0, ntexts);
+    } else {
+      std::vector<std::thread> th;
+      for (size_t t = 0; t < nthreads; t++)
+        th.emplace_back(copy_range, ntexts * t / nthreads, ntexts * (t + 1) / nthreads);
+      for (auto& x : th) x.join();
+    }
+    if (meta_off > text_bytes) memset(packed + text_bytes, 0, meta_off - text_bytes);
+  }
+  memcpy(packed + meta_off, meta.data(), meta.size() * sizeof(uint64_t));
+  d_texts_.ensure(packed_bytes);
   SB_CUDA(cudaEventRecord(ev_[0], stream_));
-  SB_CUDA(cudaMemcpyAsync(d_texts_.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, stream_));
+  SB_CUDA(cudaMemcpyAsync(d_texts_.p, packed, packed_bytes, cudaMemcpyHostToDevice, stream_));
   const uint8_t* d_base = d_texts_.as<uint8_t>();
   const uint64_t* d_offs = reinterpret_cast<const uint64_t*>(d_base + meta_off);
   const uint64_t* d_lens = d_offs + ntexts;

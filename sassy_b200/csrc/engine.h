@@ -206,6 +206,8 @@ class Engine {
   DevBuf hits_, hits2_, tiles_, d_stage_, sel_small_, best_, sel_cost_, d_texts_;
   uint8_t* h_small_ = nullptr;  // pinned: results of the small-list fast path, written by the GPU
   size_t h_small_cap_ = 0;
+  uint8_t* h_texts_ = nullptr;  // pinned staging of search_texts (texts back to back + offsets)
+  size_t h_texts_cap_ = 0;
   uint8_t* h_stage_ = nullptr;  // pinned staging for the per-search parameter block
   size_t stage_cap_ = 0;
   size_t off_counts_ = 0, off_eq_ = 0, off_pat_ = 0, off_rev_ = 0, off_feq_ = 0;

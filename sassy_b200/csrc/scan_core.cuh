@@ -371,10 +371,11 @@ SB_HD void myers_step2(Lane2& s, uint32_t eqa, uint32_t eqb) {
 SB_HD void load_eq2(uint32_t& eqa, uint32_t& eqb, const EqPair* pair, uint32_t saddr, uint32_t x, int b) {
 #if defined(__CUDA_ARCH__)
   (void)pair;
-  // The ALU pipe (LOP3) is the bottleneck of this kernel (ncu: 90 % busy), the FMA pipe is not: the
-  // text byte is extracted with integer multiplies (x * 2^(24-8b) keeps byte b on top, the high
-  // word of that times 2^8 is the byte) instead of a PRMT.
-#ifndef SB_EQ2_PRMT
+  // The ALU pipe (LOP3 + PRMT) is the bottleneck of this kernel (ncu: 90 % busy).  Extracting the
+  // text byte with integer multiplies on the FMA pipe instead (x * 2^(24-8b), then the high word of
+  // that times 2^8) was measured 3.4 % SLOWER (1.97 vs 2.04 T lane-steps/s on c3: IMAD.HI is not a
+  // full-rate instruction), so the PRMT stays; -DSB_EQ2_IMAD builds the other form.
+#ifdef SB_EQ2_IMAD
   uint32_t top = x;
   if (b < 3) asm("mul.lo.u32 %0, %1, %2;" : "=r"(top) : "r"(x), "r"(1u << (8 * (3 - b))));
   uint32_t row;
