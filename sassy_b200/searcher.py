@@ -165,6 +165,21 @@ class EncodedPatterns:
             pass
 
 
+def _bytes_data_offset() -> int:
+    """Offset of the character data inside a CPython bytes object (0 if this is not CPython or the
+    layout is not the expected one: then every buffer goes through ctypes)."""
+    import platform
+    if platform.python_implementation() != "CPython":
+        return 0
+    off = bytes.__basicsize__ - 1
+    probe = b"sassy_b200 probe"
+    addr = ctypes.cast(ctypes.c_char_p(probe), ctypes.c_void_p).value
+    return off if addr == id(probe) + off else 0
+
+
+_BYTES_DATA_OFFSET = _bytes_data_offset()
+
+
 def _as_buffer(b):
     """Returns (address, length, keepalive) for bytes-like objects and (ptr, len) tuples."""
     if isinstance(b, tuple):  # (host address, length), e.g. pinned memory from host_alloc()
@@ -350,15 +365,14 @@ class Searcher:
     def _ptr_array(items):
         """(void* array, size_t array, keepalives) for a sequence of bytes-like objects."""
         n = len(items)
-        if n > 64 and all(type(x) is bytes for x in items):
-            # many texts (reads): one join + vectorised address arithmetic instead of n ctypes casts
-            joined = b"".join(items)
+        if n > 64 and _BYTES_DATA_OFFSET and all(type(x) is bytes for x in items):
+            # many texts (reads): the buffer of a CPython bytes object lies at a fixed offset behind
+            # id(obj), so the pointer array is one vectorised add instead of n ctypes casts (the
+            # library copies the texts into its pinned staging buffer with several threads)
             lens_np = np.fromiter(map(len, items), dtype=np.uint64, count=n)
-            base = ctypes.cast(ctypes.c_char_p(joined), ctypes.c_void_p).value or 0
-            ptrs_np = np.uint64(base) + np.concatenate(([np.uint64(0)], np.cumsum(lens_np[:-1], dtype=np.uint64)))
-            ptrs_np = np.ascontiguousarray(ptrs_np, dtype=np.uint64)
+            ptrs_np = np.fromiter(map(id, items), dtype=np.uint64, count=n) + np.uint64(_BYTES_DATA_OFFSET)
             return (ctypes.c_void_p(ptrs_np.ctypes.data), ctypes.c_void_p(lens_np.ctypes.data),
-                    (joined, ptrs_np, lens_np))
+                    (items, ptrs_np, lens_np))
         bufs = [_as_buffer(x) for x in items]
         ptrs = (ctypes.c_void_p * max(1, len(bufs)))(*[b[0] for b in bufs])
         lens = (ctypes.c_size_t * max(1, len(bufs)))(*[b[1] for b in bufs])
