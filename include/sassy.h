@@ -17,7 +17,8 @@
  *     matches a non-null pointer is still returned (c.rs:112-127).
  *   - one searcher per thread; not re-entrant (search takes &mut Searcher).
  *   - Capacity limits of this implementation (the reference has none): patterns
- *     of at most 1024 characters, texts shorter than 2^40 bytes.  A search()
+ *     of at most 4096 characters (1024 with overhang, or in a search over many
+ *     texts), texts shorter than 2^40 bytes.  A search()
  *     beyond a limit does NOT abort: it returns 0 matches (with a valid, freeable
  *     *out_matches), prints the reason to stderr and leaves it in
  *     sassy_gpu_last_error() (include/sassy_gpu.h), which is empty after every

@@ -19,7 +19,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 
 CU_SOURCES = ["scan_kernels.cu", "post_kernels.cu", "engine.cu", "searcher.cu", "transport.cu", "peer_gather.cu"]
-HEADERS = ["profile.h", "scan_core.cuh", "host_logic.h", "kernels.cuh", "engine.h", "searcher.h", "transport.h",
+HEADERS = ["profile.h", "scan_core.cuh", "host_logic.h", "kernels.cuh", "engine.h", "searcher.h", "transport.h", "dna_pack.h",
            "peer_gather.h", "shard_merge.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
@@ -82,7 +82,7 @@ def build_variant(name: str, defines) -> str:
 def build_emu(force: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     src = os.path.join(CSRC, "emu.cpp")
-    deps = [src] + [os.path.join(CSRC, h) for h in ("profile.h", "scan_core.cuh", "host_logic.h")]
+    deps = [src] + [os.path.join(CSRC, h) for h in ("profile.h", "scan_core.cuh", "host_logic.h", "dna_pack.h", "shard_merge.h")]
     if force or _newer(EMU, deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                                "-x", "c++", src, "-o", EMU])

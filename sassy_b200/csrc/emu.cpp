@@ -16,6 +16,7 @@
 #include <numeric>
 #include <vector>
 
+#include "dna_pack.h"
 #include "host_logic.h"
 
 using namespace sb;
@@ -238,6 +239,8 @@ void verify_dispatch(int W, const ScanArgs& a, const uint32_t* eq_q, uint32_t qs
     case 8: verify_hit<8>(a, eq_q, qs, rev, word, span); break;
     case 16: verify_hit<16>(a, eq_q, qs, rev, word, span); break;
     case 32: verify_hit<32>(a, eq_q, qs, rev, word, span); break;
+    case 64: verify_hit<64>(a, eq_q, qs, rev, word, span); break;
+    case 128: verify_hit<128>(a, eq_q, qs, rev, word, span); break;
     default: abort();
   }
 }
@@ -449,7 +452,8 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
     dense_flags.assign(ntiles + 1, 0);
     a.tile_bytes = tile_bytes;
     a.dense = dense_flags.data();
-    // Engine::search: the regional pass runs only above `heavy_hits`
+    // Engine::search: the regional pass runs only above `heavy_hits` (and only up to 32 words)
+    if (W > kMaxScanWords) return;
     if ((double)nhits <= std::max(1024.0, 0.25 * (double)n * nq / hit_cost) && !force_regional) return;
     std::vector<uint32_t> counts(ntiles + 1, 0);
     for (unsigned long long h = 0; h < nhits; h++) counts[(key_pos(hits[h]) * kHitChars) / tile_bytes]++;
@@ -571,6 +575,15 @@ EmuResult* emu_search_opts(int profile, const uint8_t* queries, const uint8_t* r
       }
     }
     scan_dense(a);
+  } else if (n > 0 && W > kMaxScanWords) {
+    // as Engine::search: windows of kCoverStride end positions cover the text (cover_kernel)
+    a.hit_exact = 1;
+    const uint64_t per = (n + kCoverStride - 1) / kCoverStride;
+    for (uint32_t q = 0; q < nq; q++)
+      for (uint64_t j = 0; j < per; j++)
+        verify_dispatch(W, a, &eq[(size_t)q * pp.nrows * W], q, rev[q] != 0, j * kCoverStride + (uint64_t)k + 1,
+                        (uint32_t)(kCoverStride - 1 - 2 * (uint64_t)k));
+    a.hit_exact = 0;
   } else if (n > 0) {
     uint32_t nf = 0;
     while (nf < nq && !rev[nf]) nf++;
@@ -733,6 +746,20 @@ int emu_plan_qgram(int m, int k, int strands, int* out, int cap) {
   put(f.enabled ? 1 : 0), put(f.q), put(f.s), put(f.npieces);
   for (int p = 0; p < f.npieces; p++) put(f.off[p]), put(f.len[p]);
   return n;
+}
+
+// Transport encoding (dna_pack.h): every host packer against the device-side decoder.
+int emu_dna_pack_best() { return dna_pack_best_level(); }
+int emu_dna_pack(int level, const uint8_t* src, size_t n, uint8_t* dst) {
+  if (level > dna_pack_best_level()) return -1;
+  return dna_pack(src, dst, n, level) ? 1 : 0;
+}
+void emu_dna_unpack(const uint8_t* packed, size_t n, uint8_t* out) {
+  for (size_t i = 0; i < n; i++) {
+    const size_t g = i / 8;
+    const uint32_t planes = (uint32_t)packed[2 * g] | ((uint32_t)packed[2 * g + 1] << 8);
+    out[i] = (uint8_t)(dna_unpack4(planes, (int)((i % 8) / 4)) >> (8 * (i % 4)));
+  }
 }
 
 size_t emu_len(const EmuResult* r) { return r->m.size(); }

@@ -96,6 +96,8 @@ Engine::~Engine() {
   if (staged_.d) cudaFree(staged_.d);
   if (h_stage_) cudaFreeHost(h_stage_);
   if (h_pack_) cudaFreeHost(h_pack_);
+  for (cudaEvent_t e : unpack_ev_) cudaEventDestroy(e);
+  if (unpack_stream_) cudaStreamDestroy(unpack_stream_);
   if (h_small_) cudaFreeHost(h_small_);
   if (h_texts_) cudaFreeHost(h_texts_);
   sel_small_.release();
@@ -223,19 +225,47 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
       const uint64_t len = std::min(slice, n - off);
       SB_CUDA(cudaMemcpyAsync(dst + off, host + off, len, cudaMemcpyHostToDevice, stream_));
     }
-    bool clean = true;
-    for (size_t c = 0; c < pool_->chunks(); c++) {
+    // The expansion runs on a second stream, group by group behind the copies, so that only the
+    // last group's expansion is left when the last byte has crossed PCIe.
+    if (!unpack_stream_) SB_CUDA(cudaStreamCreateWithFlags(&unpack_stream_, cudaStreamNonBlocking));
+    const size_t group = 8;  // chunks per expansion launch (64 Mi characters)
+    size_t ev_used = 0;
+    auto next_event = [&]() {
+      if (ev_used == unpack_ev_.size()) {
+        cudaEvent_t e;
+        SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        unpack_ev_.push_back(e);
+      }
+      return unpack_ev_[ev_used++];
+    };
+    bool clean = true, expanded = false;
+    const size_t nchunks = pool_->chunks();
+    for (size_t c = 0; c < nchunks; c++) {
       clean &= pool_->wait_chunk(c);
       if (!clean) break;
       const size_t off = c * (chunk / 4);
       const size_t len = std::min(chunk / 4, packed_bytes - off);
       SB_CUDA(cudaMemcpyAsync(d_pack_.as<uint8_t>() + off, h_pack_ + off, len, cudaMemcpyHostToDevice, stream_));
+      if ((c + 1) % group == 0 || c + 1 == nchunks) {
+        const size_t c0 = c / group * group;
+        const uint64_t char0 = (uint64_t)c0 * chunk;
+        const uint64_t chars = std::min<uint64_t>((uint64_t)(c + 1) * chunk, n_packed) - char0;
+        cudaEvent_t e = next_event();
+        SB_CUDA(cudaEventRecord(e, stream_));
+        SB_CUDA(cudaStreamWaitEvent(unpack_stream_, e, 0));
+        SB_CUDA(launch_unpack_dna(d_pack_.as<uint8_t>() + char0 / 4, dst + char0, chars, unpack_stream_));
+        expanded = true;
+      }
     }
     const double pack_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     pool_->finish();
+    if (expanded) {  // everything later in stream_ (also the byte copies of a fallback) follows the expansion
+      cudaEvent_t e = next_event();
+      SB_CUDA(cudaEventRecord(e, unpack_stream_));
+      SB_CUDA(cudaStreamWaitEvent(stream_, e, 0));
+    }
     if (clean) {
       if (pack_s > 1e-4) pack_gbps_ = 0.5 * pack_gbps_ + 0.5 * ((double)n_packed / pack_s / 1e9);
-      SB_CUDA(launch_unpack_dna(d_pack_.as<uint8_t>(), dst, n_packed, stream_));
       // the expansion wrote whole groups of 64: clear what lies beyond the text
       SB_CUDA(cudaMemsetAsync(dst + n, 0, pad, stream_));
       transfer_packed_ = true;
@@ -438,10 +468,12 @@ uint64_t Engine::post_process(const PostCtx& c, const SearchOpts& opts, uint64_t
   uint64_t nsel = 0;
   if (bound > 0) {
     const uint64_t words_per_match = opts.without_trace ? 0 : trace_words_per_match(m, k, W);
-    const uint64_t max_scratch_words = (512ull << 20) / 4;  // 512 MiB of scratch per slice
+    const uint64_t max_scratch_words = ((W > kMaxScanWords ? 4096ull : 512ull) << 20) / 4;  // scratch per slice
     uint64_t slice = bound;
-    while (slice > 1 && trace_threads(slice) * words_per_match > max_scratch_words) slice = (slice + 1) / 2;
-    scratch_.ensure(trace_threads(slice) * words_per_match * sizeof(uint32_t));
+    const bool ovt = opts.alpha >= 0.f;
+    while (slice > 1 && trace_slots(slice, W, opts.without_trace, ovt) * words_per_match > max_scratch_words)
+      slice = (slice + 1) / 2;
+    scratch_.ensure(trace_slots(slice, W, opts.without_trace, ovt) * words_per_match * sizeof(uint32_t));
     out_.ensure(bound * sizeof(GpuMatch));
     const uint32_t ops_words = opts.without_trace ? 0 : out.ops_words;
     ops_.ensure(bound * ops_words * sizeof(uint32_t));
@@ -521,7 +553,12 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   const uint32_t nq = (uint32_t)queries.size();
   if (m <= 0) throw CudaError("empty pattern");
   const int W = round_words((m + 31) / 32);
-  if (W < 0) throw CapacityError("pattern longer than 1024 characters is not supported");
+  if (W < 0) throw CapacityError("pattern longer than 4096 characters is not supported");
+  // more than 32 words: no row-tiled kernels (prefilter hits and, without a prefilter, windows that
+  // cover the text are re-scanned one warp per window), no overhang
+  const bool huge = W > kMaxScanWords;
+  if (huge && opts.alpha >= 0.f)
+    throw CapacityError("overhang is not supported for patterns longer than 1024 characters");
   if (nq == 0) {
     if (pg_) throw CudaError("a gathered search needs at least one query on every rank");
     return;
@@ -577,7 +614,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   const uint8_t* d_rev = dst + off_rev_;
   const uint32_t* d_feq = reinterpret_cast<const uint32_t*>(dst + off_feq_);
 
-  const int occ = scan_blocks_per_sm(W, false, variant_, nrows_);
+  const int occ = scan_blocks_per_sm(std::min(W, kMaxScanWords), false, variant_, nrows_);
   stats_.blocks_per_sm = (uint32_t)occ;
   const ScanGeom g = choose_geom(n, m, k, nq, occ * sm_count_);
   if ((uint64_t)g.rows * g.ltot > text.alloc) throw CudaError("internal: text padding too small for tiling");
@@ -924,7 +961,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       read_counts();
     };
     rescan_pass();
-    if (h_counts[2] > heavy_hits && h_counts[2] <= hit_cap_) {
+    if (h_counts[2] > heavy_hits && h_counts[2] <= hit_cap_ && !huge) {
       // many hits: second pass with the dense tiles scanned whole (the hit list is still valid)
       stats_.retries++;
       reset_candidates();
@@ -953,7 +990,9 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       filtered = true;
       small_done = true;
       stats_.scan_ms = stats_.filter_ms;
-    } else if (nhits > hit_cap_) {  // the hit list overflowed: hits are lost, only the full scan is exact
+    } else if (nhits > hit_cap_ || (huge && nhits > heavy_hits)) {
+      // the hit list overflowed: hits are lost, only the full scan is exact (more than 32 words: there
+      // is no regional pass, the guarded first pass did not run)
       (void)rescan;
       stats_.filter_fallback = 1;
     } else {
@@ -989,7 +1028,27 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     for (int attempt = 0;; attempt++) {
       reset_candidates();
       SB_CUDA(cudaEventRecord(ev_[1], stream_));
-      if (n > 0) {
+      if (n > 0 && huge) {
+        // more than 32 words: windows of kCoverStride end positions (plus m + k characters of
+        // warm-up each) cover the text, one warp per window and query (verify_wide_kernel)
+        const uint64_t per = (n + kCoverStride - 1) / kCoverStride;
+        const uint64_t entries = per * nq;
+        hits_.ensure(entries * sizeof(uint64_t));
+        hits2_.ensure(entries * sizeof(uint32_t));
+        SB_CUDA(launch_cover(hits_.as<uint64_t>(), hits2_.as<uint32_t>(), d_counts + 4, nq, n, kCoverStride,
+                             (uint32_t)k, stream_));
+        ScanArgs vv = a;
+        vv.nq = nq, vv.qs_base = 0, vv.eq = d_eq;
+        vv.hit_keys = hits_.as<uint64_t>();
+        vv.hit_span = hits2_.as<uint32_t>();
+        vv.max_span = (uint32_t)kCoverStride;
+        vv.hit_count = d_counts + 4;
+        vv.hit_cap = entries;
+        vv.hit_exact = 1;
+        SB_CUDA(launch_verify(W, vv, d_rev, stream_));
+        stats_.aux_launches++;
+        stats_.scan_launches++;
+      } else if (n > 0) {
         // batches of one-word patterns: two patterns per thread (scan2_kernel)
         if (nfwd) {
           a.reset_idx = 0;
@@ -1108,7 +1167,8 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
   const uint32_t nq = (uint32_t)queries.size();
   if (m <= 0) throw CudaError("empty pattern");
   const int W = round_words((m + 31) / 32);
-  if (W < 0) throw CapacityError("pattern longer than 1024 characters is not supported");
+  if (W < 0 || W > kMaxScanWords)
+    throw CapacityError("pattern longer than 1024 characters is not supported in a search over many texts");
   if (k < 0) k = 0;
   out.ops_words = (uint32_t)((m + k + 1 + 15) / 16);
   stats_.words = (uint32_t)W;

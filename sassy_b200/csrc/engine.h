@@ -196,6 +196,8 @@ class Engine {
   uint8_t* h_pack_ = nullptr;  // pinned staging of the packed text
   size_t h_pack_cap_ = 0;
   DevBuf d_pack_;
+  cudaStream_t unpack_stream_ = nullptr;  // expansion of the packed text, group by group behind the copies
+  std::vector<cudaEvent_t> unpack_ev_;
   int sm_count_ = 148;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -17,11 +17,14 @@ namespace sb {
 constexpr int kScanThreads = SB_THREADS;  // rows (threads) per block; each warp has its own 32-row TMA box
 constexpr uint32_t kMaxRowBytes = 16384;
 constexpr uint32_t kRowAlign = 128;  // rows start on 128-byte lines
-constexpr int kMaxWords = 32;  // patterns up to 32*32 = 1024 characters
+constexpr int kMaxWords = 128;       // patterns up to 128 * 32 = 4096 characters
+constexpr int kMaxScanWords = 32;    // the row-tiled scan kernels (one thread per text row) stop here: longer
+                                     // patterns run on the warp-per-window kernels only (Engine::search)
+constexpr uint64_t kCoverStride = 8192;  // end positions per window of their full scan
 
 // Supported word counts (kernel template instantiations).
 inline int round_words(int w) {
-  const int opts[] = {1, 2, 3, 4, 6, 8, 16, 32};
+  const int opts[] = {1, 2, 3, 4, 6, 8, 16, 32, 64, 128};
   for (int o : opts)
     if (w <= o) return o;
   return -1;
@@ -95,7 +98,7 @@ inline ScanGeom choose_geom(uint64_t n, int m, int k, uint32_t nq, int bpw) {
 
 // ---------------------------------------------------------------------------
 // Exact piece prefilter: layout and tables (see scan_core.cuh).
-constexpr int kMaxPieces = 64;  // >= kMaxFilterWords * (32 / (1 + kFilterDelay))
+constexpr int kMaxPieces = 256;  // >= kMaxFilterWords * (32 / (1 + kFilterDelay))
 
 struct FilterPiece {
   int off;   // first pattern position of the piece

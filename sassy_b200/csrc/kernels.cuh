@@ -53,6 +53,10 @@ cudaError_t launch_refine(const ScanArgs& a, const uint8_t* rev_flags, uint64_t*
 cudaError_t launch_tile_marks(const ScanArgs& a, uint32_t ntiles, uint32_t* counts, unsigned long long min_hits,
                               uint32_t max_hits_per_tile, uint8_t* dense, uint32_t* list, uint32_t* list_count,
                               cudaStream_t stream);
+// Entries (query slot, nominal end, span) that cover a whole text in stretches of `stride` end
+// positions: the full scan of patterns with more than 32 words runs as a re-scan of these.
+cudaError_t launch_cover(uint64_t* keys, uint32_t* spans, unsigned long long* count, uint32_t nq, uint64_t n,
+                         uint64_t stride, uint32_t k, cudaStream_t stream);
 // nhits is read from a.hit_count on the device (clipped to a.hit_cap): no host round trip.
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream);
 
@@ -76,7 +80,7 @@ struct OverhangArgs {
   TextRef text;
   const uint8_t* rev_flags;  // [nq]
   uint32_t nslots;
-  uint32_t init_pv[kMaxWords];  // vertical deltas of the left column L(j)
+  uint32_t init_pv[kMaxScanWords];  // vertical deltas of the left column L(j)
   int32_t left_total;           // L(m): cost of end position 0
   uint32_t steps;               // wildcard columns beyond the text
   float alpha;
@@ -125,5 +129,7 @@ struct TraceArgs {
 };
 cudaError_t launch_trace(const TraceArgs& t, cudaStream_t stream);
 uint64_t trace_threads(uint64_t count);  // threads launch_trace uses for a slice of `count` matches
+// column stores launch_trace needs for a slice of `count` matches (one per thread, or per warp on the wide path)
+uint64_t trace_slots(uint64_t count, int W, bool cost_only, bool overhang);
 
 }  // namespace sb

@@ -205,7 +205,9 @@ constexpr int kTraceWideWindow = 1280;  // characters of a traceback window stag
 // systolically -- word w in lane w, lane w one column behind lane w-1, carries by shuffle -- in
 // m + k + W steps instead of (m + k) x W word-steps of one thread; lane 0 then walks the path
 // (single-bit look-ups in the wide layout).
-template <int P>
+// WL = words per lane (1 up to 32 words, 2 / 4 for patterns of 64 / 128 words): a lane runs its WL
+// words one after the other, the carries leave it after the last one.
+template <int P, int WL>
 __global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const __grid_constant__ TraceArgs t) {
   __shared__ uint8_t win[kTraceWideWarps][kTraceWideWindow];
   uint64_t count = t.count;
@@ -217,6 +219,8 @@ __global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const 
   const uint64_t nwarps = (uint64_t)gridDim.x * kTraceWideWarps;
   const int W = t.W, m = t.m, k = t.k;
   const int pad = 32 * W - m;
+  const uint32_t nl = (uint32_t)(W / WL);      // active lanes
+  const uint32_t w_first = lane * (uint32_t)WL;  // first word of this lane
   constexpr int F = 4;
   for (uint64_t li = (uint64_t)blockIdx.x * kTraceWideWarps + (threadIdx.x >> 5); li < count; li += nwarps) {
     const uint64_t gi = t.first + li;
@@ -244,31 +248,47 @@ __global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const 
     if (staged)
       for (uint32_t i = lane; i < wlen; i += 32) wbuf[i] = text_at_dir(text, n, rev, off + i);
     __syncwarp();
-    uint32_t pv = 0, mv = 0;
-    if (lane < (uint32_t)W) {
-      const int lo = pad - 32 * (int)lane;
-      pv = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
-      cs.at((0 * W + lane) * F) = pv;  // column 0: D[j][0] = j
-      cs.at((0 * W + lane) * F + 1) = 0;
+    uint32_t pv[WL], mv[WL];
+#pragma unroll
+    for (int j = 0; j < WL; j++) {
+      pv[j] = mv[j] = 0;
+      if (lane < nl) {
+        const int lo = pad - 32 * (int)(w_first + j);
+        pv[j] = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
+        cs.at((0 * W + w_first + j) * F) = pv[j];  // column 0: D[j][0] = j
+        cs.at((0 * W + w_first + j) * F + 1) = 0;
+      }
     }
     uint32_t carry = 0;
-    // equality word of the next step fetched one step ahead (it does not depend on the carries)
-    auto fetch = [&](int32_t c) -> uint32_t {
-      if (lane >= (uint32_t)W || c < 0 || c >= (int32_t)wlen) return 0u;
+    // equality words of the next step fetched one step ahead (they do not depend on the carries)
+    auto fetch = [&](int32_t c, uint32_t (&e)[WL]) {
+#pragma unroll
+      for (int j = 0; j < WL; j++) e[j] = 0u;
+      if (lane >= nl || c < 0 || c >= (int32_t)wlen) return;
       const uint8_t tc = staged ? wbuf[c] : text_at_dir(text, n, rev, off + (uint64_t)c);
-      return __ldg(eq + (((uint32_t)tc >> t.sh0) & (t.msk0 & 0xFFu)) * W + lane);
+      const uint32_t row = ((uint32_t)tc >> t.sh0) & (t.msk0 & 0xFFu);
+#pragma unroll
+      for (int j = 0; j < WL; j++) e[j] = __ldg(eq + row * W + w_first + j);
     };
-    uint32_t eq_next = fetch(-(int32_t)lane);
-    for (uint32_t step = 0; step < wlen + (uint32_t)W - 1; step++) {
+    uint32_t eq_next[WL];
+    fetch(-(int32_t)lane, eq_next);
+    for (uint32_t step = 0; step < wlen + nl - 1; step++) {
       const int32_t c = (int32_t)step - (int32_t)lane;  // this lane's column is c + 1
-      const uint32_t eq_cur = eq_next;
-      eq_next = fetch(c + 1);
+      uint32_t eq_cur[WL];
+#pragma unroll
+      for (int j = 0; j < WL; j++) eq_cur[j] = eq_next[j];
+      fetch(c + 1, eq_next);
       uint32_t cout = 0;
-      if (lane < (uint32_t)W && c >= 0 && c < (int32_t)wlen) {
-        uint32_t ph, mh;
-        trace_word(pv, mv, eq_cur, carry, cout, ph, mh);
-        const uint32_t slot = (((uint32_t)c + 1) * W + lane) * F;
-        *reinterpret_cast<uint4*>(&cs.at(slot)) = make_uint4(pv, mv, ph, mh);  // 16-byte aligned: slot % 4 == 0
+      if (lane < nl && c >= 0 && c < (int32_t)wlen) {
+        uint32_t cin = carry;
+#pragma unroll
+        for (int j = 0; j < WL; j++) {
+          uint32_t ph, mh;
+          trace_word(pv[j], mv[j], eq_cur[j], cin, cout, ph, mh);
+          cin = cout;
+          const uint32_t slot = (((uint32_t)c + 1) * W + w_first + j) * F;
+          *reinterpret_cast<uint4*>(&cs.at(slot)) = make_uint4(pv[j], mv[j], ph, mh);  // 16-byte aligned: slot % 4 == 0
+        }
       }
       carry = __shfl_up_sync(0xFFFFFFFFu, cout, 1);
       if (lane == 0) carry = 0;
@@ -346,6 +366,10 @@ uint64_t trace_threads(uint64_t count) {
 }
 
 // matches in flight of the one-warp-per-match kernel (each needs a column store)
+static uint64_t trace_wide_warps(uint64_t count);
+uint64_t trace_slots(uint64_t count, int W, bool cost_only, bool overhang) {
+  return (W >= 3 && !cost_only && !overhang) ? trace_wide_warps(count) : trace_threads(count);
+}
 static uint64_t trace_wide_warps(uint64_t count) {
   uint64_t blocks = (count + kTraceWideWarps - 1) / kTraceWideWarps;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -359,12 +383,22 @@ cudaError_t launch_trace(const TraceArgs& t0, cudaStream_t stream) {
   if (trace_is_wide(t)) {
     // the scratch holds trace_threads(count) column stores, the warps in flight need fewer
     const unsigned blocks = (unsigned)(trace_wide_warps(t.count) / kTraceWideWarps);
+#define SB_TW(PP)                                                                                     \
+  if (t.W <= 32)                                                                                      \
+    trace_wide_kernel<PP, 1><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t);                         \
+  else if (t.W == 64)                                                                                 \
+    trace_wide_kernel<PP, 2><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t);                         \
+  else if (t.W == 128)                                                                                \
+    trace_wide_kernel<PP, 4><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t);                         \
+  else                                                                                                \
+    return cudaErrorInvalidValue;
     switch (t.profile) {
-      case kDna: trace_wide_kernel<kDna><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t); break;
-      case kIupac: trace_wide_kernel<kIupac><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t); break;
-      case kAscii: trace_wide_kernel<kAscii><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t); break;
+      case kDna: SB_TW(kDna) break;
+      case kIupac: SB_TW(kIupac) break;
+      case kAscii: SB_TW(kAscii) break;
       default: return cudaErrorInvalidValue;
     }
+#undef SB_TW
     return cudaGetLastError();
   }
   const unsigned threads = 128;

@@ -88,6 +88,7 @@ struct ScanArgs {
   uint32_t qnp;             // pieces per query (k + 1); 0 = hits are not refined
   uint32_t hit_exact;       // 1: hit keys hold a nominal END POSITION (scan direction) instead of a 16-byte chunk
   const uint32_t* hit_span; // hit_exact: per entry, how many positions beyond the nominal one the entry covers
+  uint32_t max_span;        // upper bound of hit_span (sizes the window staging of the wide re-scan kernel)
   // Regional fallback of the prefilter routes.  A tile = the kScanThreads rows of one block of the
   // scan geometry.  Tiles with so many hits that re-scanning their neighbourhoods would cost more
   // than scanning the tile (repeats, low-complexity sequence) are marked dense: their hits are
@@ -1200,7 +1201,12 @@ SB_HD void trace_one(const uint8_t* text, uint64_t n, bool rev, const uint8_t* p
   const uint64_t off = end > fill ? end - fill : 0;
   const uint32_t wlen = (uint32_t)(end - off);
   // previous column: registers for the first 4 words, a local array beyond
+  // (the device runs this one-thread fill up to 32 words only; the emulation library up to 128)
+#if defined(__CUDACC__)
   constexpr int kRegW = 4, kMaxW = 32;
+#else
+  constexpr int kRegW = 4, kMaxW = 128;
+#endif
   uint32_t ppv[kRegW], pmv[kRegW];
   uint32_t lpv[kMaxW - kRegW], lmv[kMaxW - kRegW];
   for (int w = 0; w < W; w++) {

@@ -1061,16 +1061,23 @@ constexpr int kWideWindow = 2304;    // >= 2 (m + k) + 16 + piece length for m +
 // shuffle per step and all lanes are busy: a window of L characters takes L + W steps instead of
 // L x W word-steps of a single thread.  Lane W-1 follows the score through the horizontal delta of
 // the pattern's last row and emits the candidates.
-template <int W>
+// WL = words per lane: word w lives in lane w / WL (patterns of up to 32 * WL words: WL = 1 up to 1024
+// characters, 2 up to 2048, 4 up to 4096); a lane runs its WL words one after the other, the carries
+// leave it after the last one.  wcap = bytes of window staging per warp (dynamic shared memory).
+template <int WL>
 __global__ void __launch_bounds__(32 * kWideWarps)
-    verify_wide_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags) {
-  __shared__ uint8_t win[kWideWarps][kWideWindow];
+    verify_wide_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags, const int W,
+                       const int32_t wcap) {
+  extern __shared__ uint8_t win_dyn[];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* const win = win_dyn + (size_t)warp * (size_t)wcap;
   if (a.guard_limit && *a.guard_count > a.guard_limit) return;  // too many hits: the regional pass follows
   unsigned long long nhits = *a.hit_count;
   if (nhits > a.hit_cap) nhits = a.hit_cap;
   const unsigned long long nwarps = (unsigned long long)gridDim.x * kWideWarps;
   const int pad = 32 * W - a.m;
+  const int nl = W / WL;                 // active lanes
+  const int w_first = (int)lane * WL;    // first word of this lane
   for (unsigned long long h = (unsigned long long)blockIdx.x * kWideWarps + warp; h < nhits; h += nwarps) {
     const uint64_t key = a.hit_keys[h];
     const uint32_t qs = key_qs(key);
@@ -1079,7 +1086,7 @@ __global__ void __launch_bounds__(32 * kWideWarps)
     const int64_t n = (int64_t)a.n;
     int64_t w0, end, emit_from;
     if (a.hit_exact) {
-      hit_window_exact(a, key_pos(key), a.hit_span[h], w0, end, emit_from);
+      hit_window_exact(a, key_pos(key), a.hit_span ? a.hit_span[h] : 0u, w0, end, emit_from);
     } else {
       const int64_t base = (int64_t)(key_pos(key) * kHitChars);
       if (hit_in_dense_tile(a, (uint64_t)base)) continue;  // its tile is scanned whole (warp-uniform)
@@ -1093,37 +1100,51 @@ __global__ void __launch_bounds__(32 * kWideWarps)
     }
     if (end <= w0) continue;
     const int32_t L = (int32_t)(end - w0);
-    // stage the window in scan order; a window beyond the buffer is processed in pieces below
+    // stage the window in scan order (launch_verify sizes wcap for the longest possible window)
     __syncwarp();
-    for (int32_t i = (int32_t)lane; i < L && i < kWideWindow; i += 32)
-      win[warp][i] = text_at_dir(a.text, (uint64_t)n, rev, (uint64_t)(w0 + i));
+    for (int32_t i = (int32_t)lane; i < L && i < wcap; i += 32)
+      win[i] = text_at_dir(a.text, (uint64_t)n, rev, (uint64_t)(w0 + i));
     __syncwarp();
-    const int32_t Lc = L < kWideWindow ? L : kWideWindow;  // (engine guarantees L <= kWideWindow for W <= 32)
-    uint32_t pv = 0, mv = 0;
-    if (lane < (uint32_t)W) {
-      const int lo = pad - 32 * (int)lane;
-      pv = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
+    const int32_t Lc = L < wcap ? L : wcap;
+    uint32_t pv[WL], mv[WL];
+#pragma unroll
+    for (int j = 0; j < WL; j++) {
+      pv[j] = mv[j] = 0;
+      if ((int)lane < nl) {
+        const int lo = pad - 32 * (w_first + j);
+        pv[j] = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
+      }
     }
     uint32_t carry = 0;  // carries handed over by the previous lane for the character of this step
     int score = a.m;
     const int32_t emit_rel = (int32_t)(emit_from - w0);
-    // the equality word of a step does not depend on the carries: it is fetched one step ahead, so
-    // the chain between two steps is the word step and the shuffle only
-    auto fetch = [&](int32_t idx) -> uint32_t {
-      if (lane >= (uint32_t)W || idx < 0 || idx >= Lc) return 0u;
-      const uint32_t row = ((uint32_t)win[warp][idx] >> a.sh0) & (a.msk0 & 0xFFu);
-      return __ldg(eq + row * W + lane);
+    // the equality words of a step do not depend on the carries: they are fetched one step ahead, so
+    // the chain between two steps is the word steps and the shuffle only
+    auto fetch = [&](int32_t idx, uint32_t (&e)[WL]) {
+#pragma unroll
+      for (int j = 0; j < WL; j++) e[j] = 0u;
+      if ((int)lane >= nl || idx < 0 || idx >= Lc) return;
+      const uint32_t row = ((uint32_t)win[idx] >> a.sh0) & (a.msk0 & 0xFFu);
+#pragma unroll
+      for (int j = 0; j < WL; j++) e[j] = __ldg(eq + row * W + w_first + j);
     };
-    uint32_t eq_next = fetch(-(int32_t)lane);
-    for (int32_t t = 0; t < Lc + W - 1; t++) {
+    uint32_t eq_next[WL];
+    fetch(-(int32_t)lane, eq_next);
+    for (int32_t t = 0; t < Lc + nl - 1; t++) {
       const int32_t idx = t - (int32_t)lane;
-      const uint32_t eq_cur = eq_next;
-      eq_next = fetch(idx + 1);
+      uint32_t eq_cur[WL];
+#pragma unroll
+      for (int j = 0; j < WL; j++) eq_cur[j] = eq_next[j];
+      fetch(idx + 1, eq_next);
       uint32_t cout = 0;
-      if (lane < (uint32_t)W && idx >= 0 && idx < Lc) {
-        uint32_t ph, mh;
-        myers_word(pv, mv, eq_cur, carry, cout, ph, mh);
-        if (lane == (uint32_t)(W - 1)) {
+      if ((int)lane < nl && idx >= 0 && idx < Lc) {
+        uint32_t c = carry, ph = 0, mh = 0;
+#pragma unroll
+        for (int j = 0; j < WL; j++) {
+          myers_word(pv[j], mv[j], eq_cur[j], c, cout, ph, mh);
+          c = cout;
+        }
+        if ((int)lane == nl - 1) {
           score += (int)(ph >> 31) - (int)(mh >> 31);
           if (idx >= emit_rel && score <= a.k) emit_candidate(a, qs, (uint64_t)(w0 + idx) + 1, score);
         }
@@ -1132,6 +1153,26 @@ __global__ void __launch_bounds__(32 * kWideWarps)
       if (lane == 0) carry = 0;
     }
   }
+}
+
+// Entries that cover a whole text for the re-scan kernels (patterns of more than 32 words have no
+// row-tiled scan kernel: the "full scan" is a re-scan of consecutive stretches of `stride` end
+// positions, each with its own m + k characters of warm-up).
+__global__ void __launch_bounds__(256)
+    cover_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ spans, unsigned long long* __restrict__ count,
+                 uint32_t nq, uint64_t n, uint64_t stride, uint32_t k) {
+  const uint64_t per = (n + stride - 1) / stride;
+  const uint64_t total = per * nq;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t q = (uint32_t)(i / per);
+    const uint64_t j = i - (uint64_t)q * per;
+    // an entry reports end positions e0 - k .. e0 + span + k: e0 = j * stride + k + 1 and
+    // span = stride - 1 - 2k make that j * stride + 1 .. (j + 1) * stride, a partition (stride > 2k + 1)
+    const uint64_t e0 = j * stride + k + 1;
+    keys[i] = cand_key(q, e0);
+    spans[i] = (uint32_t)(stride - 1 - 2 * (uint64_t)k);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count = total;
 }
 
 }  // namespace
@@ -1202,6 +1243,12 @@ cudaError_t launch_refine(const ScanArgs& a, const uint8_t* rev_flags, uint64_t*
   return cudaGetLastError();
 }
 
+cudaError_t launch_cover(uint64_t* keys, uint32_t* spans, unsigned long long* count, uint32_t nq, uint64_t n,
+                         uint64_t stride, uint32_t k, cudaStream_t stream) {
+  cover_kernel<<<148 * 2, 256, 0, stream>>>(keys, spans, count, nq, n, stride, k);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cudaStream_t stream) {
   const unsigned threads = 128;
   const unsigned blocks = 148 * 12;  // grid-stride over the device-side hit count
@@ -1209,14 +1256,33 @@ cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cu
   // (refined entries: warm-up m + k, 2k + 1 end positions, and a span of at most 16 + m on repetitive text)
   const int64_t window = a.hit_exact ? 2 * (int64_t)a.m + 3 * (int64_t)a.k + 18
                                      : 2 * ((int64_t)a.m + a.k) + kHitChars + (int64_t)a.rev_lead;
-  if (W >= 8 && window <= kWideWindow) {
+  if (W >= 8 && (window <= kWideWindow || W > 32)) {
     const unsigned wblocks = 148 * 8;
-    switch (W) {
-      case 8: verify_wide_kernel<8><<<wblocks, 32 * kWideWarps, 0, stream>>>(a, rev_flags); break;
-      case 16: verify_wide_kernel<16><<<wblocks, 32 * kWideWarps, 0, stream>>>(a, rev_flags); break;
-      case 32: verify_wide_kernel<32><<<wblocks, 32 * kWideWarps, 0, stream>>>(a, rev_flags); break;
-      default: return cudaErrorInvalidValue;
+    // window staging per warp: the fixed 2304 bytes up to 32 words, the longest window beyond
+    int32_t wcap = kWideWindow;
+    if (W > 32) {
+      // warm-up m + k, 2k + 1 end positions, the span (refined hits: at most 16 + m; cover: the stride)
+      const int64_t longest = a.hit_exact ? (int64_t)a.m + 3 * (int64_t)a.k + 2 + std::max<int64_t>(a.max_span, a.m + 16)
+                                          : window;
+      wcap = (int32_t)((longest + 64 + 127) / 128 * 128);
     }
+    const size_t smem = (size_t)kWideWarps * (size_t)wcap;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    static size_t tr1[64] = {}, tr2[64] = {}, tr4[64] = {};
+    cudaError_t e = cudaSuccess;
+    if (W <= 32) {
+      e = ensure_smem(verify_wide_kernel<1>, smem, tr1);
+      if (e == cudaSuccess) verify_wide_kernel<1><<<wblocks, 32 * kWideWarps, smem, stream>>>(a, rev_flags, W, wcap);
+    } else if (W == 64) {
+      e = ensure_smem(verify_wide_kernel<2>, smem, tr2);
+      if (e == cudaSuccess) verify_wide_kernel<2><<<wblocks, 32 * kWideWarps, smem, stream>>>(a, rev_flags, W, wcap);
+    } else if (W == 128) {
+      e = ensure_smem(verify_wide_kernel<4>, smem, tr4);
+      if (e == cudaSuccess) verify_wide_kernel<4><<<wblocks, 32 * kWideWarps, smem, stream>>>(a, rev_flags, W, wcap);
+    } else {
+      return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
   }
   switch (W) {

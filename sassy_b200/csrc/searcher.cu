@@ -259,7 +259,7 @@ std::vector<Match> Searcher::search_many(const uint8_t* const* patterns, const u
 // always uses the IUPAC complement table, tqueries.rs:2).
 EncodedPatterns Searcher::encode_patterns(const uint8_t* const* patterns, size_t n_patterns, size_t m) const {
   if (m == 0) throw std::invalid_argument("empty pattern");
-  if (m > 32 * kMaxWords) throw std::invalid_argument("pattern longer than 1024 characters");
+  if (m > 32 * kMaxWords) throw std::invalid_argument("pattern longer than 4096 characters");
   EncodedPatterns e;
   e.n_patterns = n_patterns;
   e.m = (int)m;

@@ -22,14 +22,12 @@
 #include <thread>
 #include <vector>
 
-#if defined(__x86_64__)
-#include <immintrin.h>
-#endif
 #if defined(__linux__)
 #include <pthread.h>
 #include <sched.h>
 #endif
 
+#include "dna_pack.h"
 #include "transport.h"
 
 namespace sb {
@@ -39,99 +37,7 @@ namespace sb {
 
 namespace {
 
-// 4 characters -> 1 byte, character i at bits 2i..2i+1, code = (c >> 1) & 3.
-// Returns false if a byte outside ACGTacgt was seen (the output is still written).
-bool pack_scalar(const uint8_t* src, uint8_t* dst, size_t n) {
-  bool ok = true;
-  size_t i = 0;
-  for (; i + 4 <= n; i += 4) {
-    uint8_t b = 0;
-    for (int j = 0; j < 4; j++) {
-      const uint8_t c = src[i + j], u = c & 0xDF;
-      ok &= (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T');
-      b |= (uint8_t)(((c >> 1) & 3) << (2 * j));
-    }
-    dst[i >> 2] = b;
-  }
-  if (i < n) {
-    uint8_t b = 0;
-    for (int j = 0; i + j < n; j++) {
-      const uint8_t c = src[i + j], u = c & 0xDF;
-      ok &= (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T');
-      b |= (uint8_t)(((c >> 1) & 3) << (2 * j));
-    }
-    dst[i >> 2] = b;
-  }
-  return ok;
-}
-
-#if defined(__x86_64__)
-// 32 characters per iteration: codes = (v >> 1) & 3, then two multiply-adds fold four
-// codes into one byte per 32-bit lane (c0 + 4 c1 + 16 c2 + 64 c3), a byte shuffle gathers them.
-__attribute__((target("avx2"))) bool pack_avx2(const uint8_t* src, uint8_t* dst, size_t n) {
-  const __m256i up = _mm256_set1_epi8((char)0xDF), three = _mm256_set1_epi8(3);
-  const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'),
-                cT = _mm256_set1_epi8('T');
-  const __m256i m1 = _mm256_set1_epi16(0x0401), m2 = _mm256_set1_epi32(0x00100001);
-  const __m256i gather = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,  //
-                                          0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
-  __m256i all_ok = _mm256_set1_epi8((char)0xFF);
-  size_t i = 0;
-  for (; i + 32 <= n; i += 32) {
-    const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
-    const __m256i u = _mm256_and_si256(v, up);
-    const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, cA), _mm256_cmpeq_epi8(u, cC)),
-                                       _mm256_or_si256(_mm256_cmpeq_epi8(u, cG), _mm256_cmpeq_epi8(u, cT)));
-    all_ok = _mm256_and_si256(all_ok, ok);
-    const __m256i codes = _mm256_and_si256(_mm256_srli_epi16(v, 1), three);
-    const __m256i pairs = _mm256_maddubs_epi16(codes, m1);  // c0 + 4 c1 per 16-bit lane
-    const __m256i quads = _mm256_madd_epi16(pairs, m2);     // + 16 (c2 + 4 c3) per 32-bit lane
-    const __m256i g = _mm256_shuffle_epi8(quads, gather);
-    const uint32_t lo = (uint32_t)_mm256_cvtsi256_si32(g);
-    const uint32_t hi = (uint32_t)_mm256_extract_epi32(g, 4);
-    const uint64_t packed = (uint64_t)lo | ((uint64_t)hi << 32);
-    memcpy(dst + (i >> 2), &packed, 8);
-  }
-  bool ok = _mm256_movemask_epi8(all_ok) == -1;
-  if (i < n) ok &= pack_scalar(src + i, dst + (i >> 2), n - i);
-  return ok;
-}
-
-// 64 characters per iteration; VPMOVDB truncates the sixteen 32-bit lanes to 16 bytes.
-__attribute__((target("avx512f,avx512bw"))) bool pack_avx512(const uint8_t* src, uint8_t* dst, size_t n) {
-  const __m512i up = _mm512_set1_epi8((char)0xDF), three = _mm512_set1_epi8(3);
-  const __m512i cA = _mm512_set1_epi8('A'), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'),
-                cT = _mm512_set1_epi8('T');
-  const __m512i m1 = _mm512_set1_epi16(0x0401), m2 = _mm512_set1_epi32(0x00100001);
-  __mmask64 all_ok = ~(__mmask64)0;
-  size_t i = 0;
-  for (; i + 64 <= n; i += 64) {
-    _mm_prefetch(reinterpret_cast<const char*>(src + i + 1024), _MM_HINT_NTA);
-    const __m512i v = _mm512_loadu_si512(src + i);
-    const __m512i u = _mm512_and_si512(v, up);
-    all_ok &= _mm512_cmpeq_epi8_mask(u, cA) | _mm512_cmpeq_epi8_mask(u, cC) | _mm512_cmpeq_epi8_mask(u, cG) |
-              _mm512_cmpeq_epi8_mask(u, cT);
-    const __m512i codes = _mm512_and_si512(_mm512_srli_epi16(v, 1), three);
-    const __m512i pairs = _mm512_maddubs_epi16(codes, m1);
-    const __m512i quads = _mm512_madd_epi16(pairs, m2);
-    // dst chunks start on 16-byte boundaries: streaming store, no read-for-ownership
-    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + (i >> 2)), _mm512_cvtepi32_epi8(quads));
-  }
-  _mm_sfence();
-  bool ok = all_ok == ~(__mmask64)0;
-  if (i < n) ok &= pack_scalar(src + i, dst + (i >> 2), n - i);
-  return ok;
-}
-#endif
-
-bool pack_range(const uint8_t* src, uint8_t* dst, size_t n) {
-#if defined(__x86_64__)
-  static const int level = __builtin_cpu_supports("avx512bw") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
-  if (level == 2) return pack_avx512(src, dst, n);
-  if (level == 1) return pack_avx2(src, dst, n);
-#endif
-  return pack_scalar(src, dst, n);
-}
+bool pack_range(const uint8_t* src, uint8_t* dst, size_t n) { return dna_pack(src, dst, n); }
 
 }  // namespace
 
@@ -248,25 +154,17 @@ void PackPool::finish() {
 
 namespace {
 
-// 16 packed bytes (64 characters) per thread -> four 16-byte stores of canonical bytes.
-// Code -> byte through PRMT on the 4-byte table "ACTG" (A=0,C=1,T=2,G=3 as (c>>1)&3).
+// 16 packed bytes (64 characters: 8 groups of two plane bytes) per thread -> four 16-byte stores
+// of canonical bytes (dna_pack.h: dna_unpack4).
 __global__ void unpack_dna_kernel(const uint4* __restrict__ packed, uint4* __restrict__ out, size_t n_vec) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_vec) return;
   const uint4 p = __ldg(packed + i);
   const uint32_t w[4] = {p.x, p.y, p.z, p.w};
-  const uint32_t table = 0x47544341u;  // 'A','C','T','G'
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    uint32_t o[4];
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      const uint32_t byte = (w[j] >> (8 * b)) & 0xFFu;
-      // spread the four 2-bit codes to the four selector nibbles
-      const uint32_t sel = (byte & 3u) | ((byte & 0xCu) << 2) | ((byte & 0x30u) << 4) | ((byte & 0xC0u) << 6);
-      o[b] = __byte_perm(table, 0u, sel);
-    }
-    out[i * 4 + j] = make_uint4(o[0], o[1], o[2], o[3]);
+    const uint32_t g0 = w[j] & 0xFFFFu, g1 = w[j] >> 16;  // characters 16 j .. + 7 and + 8 .. + 15
+    out[i * 4 + j] = make_uint4(dna_unpack4(g0, 0), dna_unpack4(g0, 1), dna_unpack4(g1, 0), dna_unpack4(g1, 1));
   }
 }
 

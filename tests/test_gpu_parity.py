@@ -302,6 +302,52 @@ def test_gpu_long_patterns_many_pieces(tma):
     assert s.stats()["filter_words"] in (1, 2, 4, 8)
 
 
+def test_gpu_patterns_beyond_32_words():
+    """Patterns of 1025..4096 characters: several words per lane in the warp-systolic re-scan and
+    traceback; q-gram / piece-automaton hits, or (prefilter off, k too large) windows covering the text."""
+    import sassy_b200
+    from tests.test_oracle_props import mutate
+    rng = random.Random(37)
+    s = sassy_b200.Searcher("dna", rc=True)
+    si = sassy_b200.Searcher("iupac", rc=True)
+    routes = set()
+    for m, k, n, mode in ((1025, 5, 90_000, "auto"), (1500, 12, 200_000, "auto"), (2048, 3, 70_000, "off"),
+                          (2049, 20, 170_000, "auto"), (3000, 40, 50_000, "auto"), (4096, 9, 300_000, "auto"),
+                          (4096, 63, 40_000, "off"), (1100, 300, 20_000, "auto")):
+        p, t = planted(rng, m, n, k)
+        t = bytearray(t)
+        for at in (max(0, 8192 - m // 2), n // 2):
+            q = bytearray(mutate(rng, p, rng.randrange(0, k + 1)))
+            if at + len(q) < n:
+                t[at:at + len(q)] = q
+        t = bytes(t[:n])
+        s.set_filter(mode)
+        for allm in (False, True):
+            want = oracle.search("dna", p, t, k, rc=True, all_minima=allm)
+            got = s.search_all(p, t, k) if allm else s.search(p, t, k)
+            assert list(map(key, got)) == list(map(key, want)), (m, k, mode, allm)
+            for a, b in zip(got, want):
+                assert a.cigar == b.cigar
+        assert want, m
+        routes.add(s.stats()["filter_kind"])
+    assert routes >= {0, 2}, routes
+    # Iupac pattern with ambiguity codes (piece automaton or cover), text with N
+    m, k, n = 1300, 6, 60_000
+    p, t = planted(rng, m, n, k)
+    p, t = bytearray(p), bytearray(t)
+    for _ in range(20):
+        p[rng.randrange(m)] = rng.choice(b"NRYSW")
+    p = bytes(p)
+    concrete = bytes({"N": b"ACGT", "R": b"AG", "Y": b"CT", "S": b"CG", "W": b"AT"}.get(chr(c), bytes([c]))[0] for c in p)
+    t[20_000:20_000 + m] = mutate(rng, concrete, 4)
+    t[30_000] = ord("N")
+    t = bytes(t[:n])
+    for allm in (False, True):
+        want = oracle.search("iupac", p, t, k, rc=True, all_minima=allm)
+        got = si.search_all(p, t, k) if allm else si.search(p, t, k)
+        assert want and list(map(key, got)) == list(map(key, want)), allm
+
+
 def test_gpu_qgram_prefilter_fuzz():
     """The q-gram bitmap route (Dna, one pattern, shares >= 9 characters): every (Q, S) instantiation,
     both strands in one pass, against the oracle; also checks that the route is the one taken."""
@@ -418,7 +464,7 @@ def test_gpu_ascii_fuzz(tma):
 
 
 def test_c_abi_search_beyond_capacity_does_not_abort():
-    """A pattern of more than 1024 characters is a limit of this implementation, not one of the
+    """A pattern of more than 4096 characters is a limit of this implementation, not one of the
     reference's panics: search() returns no matches, leaves the reason in sassy_gpu_last_error()
     and the process lives (include/sassy.h)."""
     from sassy_b200 import _native
@@ -426,15 +472,15 @@ def test_c_abi_search_beyond_capacity_does_not_abort():
     s = lib.sassy_searcher(b"dna", True, math.nan)
     assert s
     rng = random.Random(5)
-    pat = bytes(rng.choice(b"ACGT") for _ in range(1025))
+    pat = bytes(rng.choice(b"ACGT") for _ in range(4097))
     text = pat + bytes(rng.choice(b"ACGT") for _ in range(5000))
     out = ctypes.POINTER(_native.CMatch)()
     n = lib.search(s, pat, len(pat), text, len(text), 3, ctypes.byref(out))
     assert n == 0 and bool(out)
-    assert "1024" in _native.last_error()
+    assert "4096" in _native.last_error()
     lib.sassy_matches_free(out, n)
-    n = lib.search(s, pat[:1024], 1024, text, len(text), 3, ctypes.byref(out))  # the longest supported pattern
-    assert n == 1 and out[0].text_start == 0 and out[0].text_end == 1024 and out[0].cost == 0
+    n = lib.search(s, pat[:4096], 4096, text, len(text), 3, ctypes.byref(out))  # the longest supported pattern
+    assert n == 1 and out[0].text_start == 0 and out[0].text_end == 4096 and out[0].cost == 0
     assert _native.last_error() == ""
     lib.sassy_matches_free(out, n)
     lib.sassy_searcher_free(s)

@@ -188,6 +188,26 @@ def test_emu_long_pattern_words():
         assert want, m
 
 
+def test_emu_patterns_beyond_32_words():
+    """Patterns of 1025..4096 characters (64 / 128 words): no row-tiled kernels; the prefilter routes
+    re-scan their hits, the route without prefilter re-scans windows that cover the text."""
+    rng = random.Random(19)
+    for m, k, n, uf in ((1025, 5, 9000, 0), (1500, 12, 20000, 0), (2048, 3, 17000, -1), (2049, 20, 17000, -1),
+                        (3000, 40, 9000, 1), (4096, 9, 30000, 0), (4096, 63, 10000, -1), (1100, 300, 5000, -1)):
+        p, t = planted(rng, m, n, k)
+        t = bytearray(t)
+        q = bytearray(mutate(rng, p, rng.randrange(0, k + 1)))  # a second copy that straddles a window border
+        at = max(0, 8192 - m // 2)
+        if at + len(q) < n:
+            t[at:at + len(q)] = q
+        t = bytes(t[:n])
+        for allm in (False, True):
+            want = oracle.search("dna", p, t, k, rc=True, all_minima=allm)
+            got = EmuBackend(use_filter=uf).search("dna", p, t, k, rc=True, all_minima=allm)
+            assert list(map(key, got)) == list(map(key, want)), (m, k, uf, allm)
+        assert want, m
+
+
 def test_emu_k_ge_m_and_empty():
     b = EmuBackend()
     assert b.search("dna", b"ACG", b"", 1) == []
@@ -383,3 +403,41 @@ def test_emu_regional_fallback_low_complexity(mode, monkeypatch):
             assert list(map(key, got)) == list(map(key, want)), (p, k, allm, b.last_filter, b.last_dense_tiles)
             dense_seen += b.last_dense_tiles > 0
     assert dense_seen >= 8, dense_seen
+
+
+def test_dna_transport_encoding():
+    """Host->device transport of Dna texts (csrc/dna_pack.h): every host packer (scalar, AVX2,
+    AVX-512 + GFNI where the CPU has them) writes the same bytes, the device-side decoder returns
+    the canonical upper-case text, and a byte outside ACGTacgt is reported wherever it sits."""
+    import ctypes
+    from tests.emu_backend import _lib
+    lib = _lib()
+    lib.emu_dna_pack.restype = ctypes.c_int
+    lib.emu_dna_pack.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+    lib.emu_dna_unpack.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+    best = lib.emu_dna_pack_best()
+    rng = random.Random(77)
+    for n in [0, 1, 7, 8, 9, 31, 32, 33, 63, 64, 255, 256, 257, 511, 1000, 4096 + 5, 70001]:
+        text = bytes(rng.choice(b"ACGTacgt") for _ in range(n))
+        size = (n + 7) // 8 * 2
+        ref = None
+        for level in range(best + 1):
+            # an unaligned destination exercises the non-streaming store of the widest packer
+            for shift in (0, 2):
+                dst = ctypes.create_string_buffer(size + 64 + shift)
+                buf = (ctypes.c_char * (size + 64)).from_buffer(dst, shift)
+                assert lib.emu_dna_pack(level, text, n, ctypes.cast(buf, ctypes.c_char_p)) == 1
+                got = bytes(buf[:size])
+                if ref is None:
+                    ref = got
+                assert got == ref, (n, level, shift)
+        out = ctypes.create_string_buffer(max(n, 1))
+        lib.emu_dna_unpack(ref, n, out)
+        assert out.raw[:n] == text.upper(), n
+        if n:
+            for bad in (b"N", b"\xc1", b"B", b"\x00", b"U"):
+                pos = rng.randrange(n)
+                t2 = text[:pos] + bad + text[pos + 1:]
+                for level in range(best + 1):
+                    dst = ctypes.create_string_buffer(size + 64)
+                    assert lib.emu_dna_pack(level, t2, n, dst) == 0, (n, level, bad, pos)
