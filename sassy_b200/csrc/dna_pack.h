@@ -99,8 +99,10 @@ inline size_t dna_pack_ahead() {
   }();
   return ahead;
 }
+// `stream`: full-line non-temporal stores (a staging buffer that is written once and read by the copy
+// engine from memory); false keeps the lines in the cache (a small staging ring that is re-used).
 __attribute__((target("avx512f,avx512bw,gfni"))) inline bool dna_pack_gfni(const uint8_t* src, uint8_t* dst,
-                                                                            size_t n) {
+                                                                            size_t n, bool stream = true) {
   const __m512i up = _mm512_set1_epi8((char)0xDF);
   const __m512i lut =
       _mm512_broadcast_i32x4(_mm_setr_epi8((char)0xFF, 0x41, 0, 0x43, 0x54, 0, 0, 0x47, 0, 0, 0, 0, 0, 0, 0, 0));
@@ -110,7 +112,7 @@ __attribute__((target("avx512f,avx512bw,gfni"))) inline bool dna_pack_gfni(const
   const __m512i gather = _mm512_load_si512(idx);
   __m512i bad = _mm512_setzero_si512();
   size_t i = 0;
-  const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 63) == 0;
+  const bool aligned = stream && (reinterpret_cast<uintptr_t>(dst) & 63) == 0;
   const size_t kDnaPackAhead = dna_pack_ahead();
   for (; i + 256 <= n; i += 256) {
     for (int q = 0; q < 4; q++) _mm_prefetch(reinterpret_cast<const char*>(src + i + kDnaPackAhead + 64 * q), _MM_HINT_T1);
@@ -148,11 +150,11 @@ inline int dna_pack_best_level() {
   return 0;
 }
 
-inline bool dna_pack(const uint8_t* src, uint8_t* dst, size_t n, int level = -1) {
+inline bool dna_pack(const uint8_t* src, uint8_t* dst, size_t n, int level = -1, bool stream = true) {
   static const int best = dna_pack_best_level();
   if (level < 0 || level > best) level = best;
 #if defined(SB_PACK_X86)
-  if (level == 2) return dna_pack_gfni(src, dst, n);
+  if (level == 2) return dna_pack_gfni(src, dst, n, stream);
   if (level == 1) return dna_pack_avx2(src, dst, n);
 #endif
   return dna_pack_scalar(src, dst, n);

@@ -1,5 +1,8 @@
 #include "engine.h"
 
+#if defined(__linux__)
+#include <sys/prctl.h>
+#endif
 #include <cudaTypedefs.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -96,7 +99,7 @@ Engine::~Engine() {
   if (staged_.d) cudaFree(staged_.d);
   if (h_stage_) cudaFreeHost(h_stage_);
   if (h_pack_) cudaFreeHost(h_pack_);
-  for (cudaEvent_t e : unpack_ev_) cudaEventDestroy(e);
+  for (cudaEvent_t e : copy_ev_) cudaEventDestroy(e);
   if (unpack_stream_) cudaStreamDestroy(unpack_stream_);
   if (h_small_) cudaFreeHost(h_small_);
   if (h_texts_) cudaFreeHost(h_texts_);
@@ -192,84 +195,143 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
         nt = std::max(2, nt / atoi(lw));
       nt = std::max(1, std::min(nt, 64));
       pool_ = new PackPool(nt);
-      pack_gbps_ = 5.0 * nt;  // first guess; refined from every transfer
     }
-    const size_t chunk = 8ull << 20;  // characters per chunk (2 MiB packed): the first copy starts early
-    // Packing (host cores) and PCIe run concurrently; when the source is pinned the tail of the
-    // text is sent as plain bytes so that both finish together:
-    //   f * n / Rp = (f * n / 4 + (1 - f) * n) / Rc   =>   f = Rp / (Rc + 0.75 Rp)
+    // Chunks of 2 Mi characters (512 KiB packed).  The workers pack from the front of the text into
+    // a staging ring that stays in the host's caches; this thread hands every packed chunk to the
+    // copy engine, and -- when the source is pinned and the next chunk is not ready while the copy
+    // queue runs dry -- takes a chunk from the BACK of the text and sends it as plain bytes, so the
+    // split between packed and plain bytes follows the speed of the host cores by itself.
+    // SASSY_B200_PACK_CHUNK (characters) / SASSY_B200_PACK_RING (slots, 0 = one staging buffer
+    // for the whole text, streaming stores) are tuning knobs.
+    static const size_t chunk = [] {
+      const char* e = getenv("SASSY_B200_PACK_CHUNK");
+      size_t c = e ? (size_t)strtoull(e, nullptr, 10) : (size_t)2 << 20;
+      return std::max<size_t>(c / 4096 * 4096, 65536);
+    }();
+    static const size_t ring = [] {
+      const char* e = getenv("SASSY_B200_PACK_RING");
+      return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)48;
+    }();
     cudaPointerAttributes at;
     const bool pinned = cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();  // unregistered memory is not an error here
-    double f = 1.0;
-    if (pinned) f = std::min(1.0, pack_gbps_ / (pcie_gbps_ + 0.75 * pack_gbps_));
-    uint64_t n_packed = (uint64_t)(f * (double)n) / chunk * chunk;
-    if (n_packed + chunk > n) n_packed = n;  // no tiny raw tail
-    const size_t packed_bytes = (size_t)((n_packed + 63) / 64 * 16);
-    if (packed_bytes > h_pack_cap_) {
+    const size_t nchunks = (size_t)((n + chunk - 1) / chunk);
+    const size_t slots = ring ? std::min(ring, nchunks) : nchunks;
+    const size_t stage_bytes = slots * (chunk / 4);
+    if (stage_bytes > h_pack_cap_) {
       if (h_pack_) cudaFreeHost(h_pack_);
       h_pack_ = nullptr;
       h_pack_cap_ = 0;
-      const size_t want = (size_t)((n + 63) / 64 * 16);
-      SB_CUDA(cudaHostAlloc((void**)&h_pack_, want, cudaHostAllocDefault));
-      h_pack_cap_ = want;
+      SB_CUDA(cudaHostAlloc((void**)&h_pack_, stage_bytes, cudaHostAllocDefault));
+      h_pack_cap_ = stage_bytes;
     }
-    d_pack_.ensure(h_pack_cap_);
-    // the last group of 64 characters is zero-padded in the staging buffer
-    if (n_packed % 64) memset(h_pack_ + (n_packed / 64) * 16, 0, 16);
-    const auto t0 = std::chrono::steady_clock::now();
-    pool_->start(host, h_pack_, n_packed, chunk);
-    // plain-byte tail first: it keeps the copy engine busy while the first chunks are packed
-    const uint64_t slice = 64ull << 20;
-    for (uint64_t off = n_packed; off < n; off += slice) {
-      const uint64_t len = std::min(slice, n - off);
-      SB_CUDA(cudaMemcpyAsync(dst + off, host + off, len, cudaMemcpyHostToDevice, stream_));
-    }
+    d_pack_.ensure(nchunks * (chunk / 4));
     // The expansion runs on a second stream, group by group behind the copies, so that only the
     // last group's expansion is left when the last byte has crossed PCIe.
     if (!unpack_stream_) SB_CUDA(cudaStreamCreateWithFlags(&unpack_stream_, cudaStreamNonBlocking));
-    const size_t group = 8;  // chunks per expansion launch (64 Mi characters)
-    size_t ev_used = 0;
-    auto next_event = [&]() {
-      if (ev_used == unpack_ev_.size()) {
-        cudaEvent_t e;
-        SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        unpack_ev_.push_back(e);
-      }
-      return unpack_ev_[ev_used++];
-    };
-    bool clean = true, expanded = false;
-    const size_t nchunks = pool_->chunks();
-    for (size_t c = 0; c < nchunks; c++) {
-      clean &= pool_->wait_chunk(c);
-      if (!clean) break;
-      const size_t off = c * (chunk / 4);
-      const size_t len = std::min(chunk / 4, packed_bytes - off);
-      SB_CUDA(cudaMemcpyAsync(d_pack_.as<uint8_t>() + off, h_pack_ + off, len, cudaMemcpyHostToDevice, stream_));
-      if ((c + 1) % group == 0 || c + 1 == nchunks) {
-        const size_t c0 = c / group * group;
-        const uint64_t char0 = (uint64_t)c0 * chunk;
-        const uint64_t chars = std::min<uint64_t>((uint64_t)(c + 1) * chunk, n_packed) - char0;
-        cudaEvent_t e = next_event();
-        SB_CUDA(cudaEventRecord(e, stream_));
-        SB_CUDA(cudaStreamWaitEvent(unpack_stream_, e, 0));
-        SB_CUDA(launch_unpack_dna(d_pack_.as<uint8_t>() + char0 / 4, dst + char0, chars, unpack_stream_));
-        expanded = true;
-      }
+    constexpr size_t kCopyEvents = 64;  // copies in flight that are tracked
+    while (copy_ev_.size() < kCopyEvents + 2) {
+      cudaEvent_t e;
+      SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      copy_ev_.push_back(e);
     }
-    const double pack_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const size_t group = std::max<size_t>(1, ((size_t)64 << 20) / chunk);  // chunks per expansion launch
+    uint64_t issued = 0, completed = 0;     // copies (packed or plain), in stream order
+    uint64_t bytes_issued = 0, bytes_completed = 0;
+    uint64_t copy_len[kCopyEvents];
+    // plain chunks are added while less than this is queued (~110 us of PCIe work: longer than a
+    // sleep of this thread, so the copy engine does not run dry)
+    const uint64_t queue_low = 6ull << 20;
+    std::vector<uint64_t> seq(slots ? slots : 1, 0);  // copy number of the chunk that last used a staging slot
+    size_t sent_chunks = 0, released = 0, expanded_chunks = 0;
+    uint64_t plain_bytes = 0;
+    bool clean = true, expanded = false;
+    auto poll = [&]() {
+      while (completed < issued && cudaEventQuery(copy_ev_[completed % kCopyEvents]) == cudaSuccess)
+        bytes_completed += copy_len[completed++ % kCopyEvents];
+      while (released < sent_chunks && seq[released % slots] < completed) released++;
+      if (ring) pool_->release(released);
+    };
+    auto issue = [&](void* to, const void* from, size_t len) {
+      if (issued - completed >= kCopyEvents) {  // the oldest tracked copy frees its event
+        SB_CUDA(cudaEventSynchronize(copy_ev_[completed % kCopyEvents]));
+        poll();
+      }
+      SB_CUDA(cudaMemcpyAsync(to, from, len, cudaMemcpyHostToDevice, stream_));
+      SB_CUDA(cudaEventRecord(copy_ev_[issued % kCopyEvents], stream_));
+      copy_len[issued % kCopyEvents] = len;
+      bytes_issued += len;
+      issued++;
+    };
+    auto expand_upto = [&](size_t upto_chunk) {  // chunks [expanded_chunks, upto_chunk)
+      if (upto_chunk <= expanded_chunks) return;
+      const uint64_t char0 = (uint64_t)expanded_chunks * chunk;
+      const uint64_t chars = std::min<uint64_t>((uint64_t)upto_chunk * chunk, n) - char0;
+      cudaEvent_t e = copy_ev_[kCopyEvents];
+      SB_CUDA(cudaEventRecord(e, stream_));
+      SB_CUDA(cudaStreamWaitEvent(unpack_stream_, e, 0));
+      SB_CUDA(launch_unpack_dna(d_pack_.as<uint8_t>() + char0 / 4, dst + char0, chars, unpack_stream_));
+      expanded_chunks = upto_chunk;
+      expanded = true;
+    };
+#if defined(__linux__)
+    // short sleeps of this thread must be short: the default timer slack adds 50 us to each
+    const int slack = prctl(PR_GET_TIMERSLACK);
+    prctl(PR_SET_TIMERSLACK, 1000UL);
+#endif
+    pool_->start(host, h_pack_, n, chunk, ring ? slots : 0);
+    try {
+    for (;;) {
+      poll();
+      const size_t packed_end = pool_->packed_end();
+      if (sent_chunks >= packed_end) break;
+      const int st = pool_->chunk_state(sent_chunks);
+      if (st != 0) {
+        if (st != 1) {
+          clean = false;
+          break;
+        }
+        const size_t c = sent_chunks;
+        const uint64_t chars = std::min<uint64_t>(chunk, n - (uint64_t)c * chunk);
+        const size_t len = (size_t)((chars + 63) / 64 * 16);
+        issue(d_pack_.as<uint8_t>() + c * (chunk / 4), h_pack_ + (c % slots) * (chunk / 4), len);
+        seq[c % slots] = issued - 1;
+        sent_chunks++;
+        if (sent_chunks % group == 0) expand_upto(sent_chunks);
+        continue;
+      }
+      size_t t;
+      if (pinned && bytes_issued - bytes_completed < queue_low && pool_->claim_tail(&t)) {
+        const uint64_t off = (uint64_t)t * chunk;
+        const uint64_t len = std::min<uint64_t>(chunk, n - off);
+        issue(dst + off, host + off, (size_t)len);
+        plain_bytes += len;
+        continue;
+      }
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+    } catch (...) {  // a failed CUDA call: the workers must be idle before the pool is used again
+      pool_->cancel();
+      pool_->finish();
+      throw;
+    }
+    if (!clean) pool_->cancel();
     pool_->finish();
+#if defined(__linux__)
+    if (slack > 0) prctl(PR_SET_TIMERSLACK, (unsigned long)slack);
+#endif
+    if (clean) expand_upto(sent_chunks);
     if (expanded) {  // everything later in stream_ (also the byte copies of a fallback) follows the expansion
-      cudaEvent_t e = next_event();
+      cudaEvent_t e = copy_ev_[kCopyEvents + 1];
       SB_CUDA(cudaEventRecord(e, unpack_stream_));
       SB_CUDA(cudaStreamWaitEvent(stream_, e, 0));
     }
     if (clean) {
-      if (pack_s > 1e-4) pack_gbps_ = 0.5 * pack_gbps_ + 0.5 * ((double)n_packed / pack_s / 1e9);
       // the expansion wrote whole groups of 64: clear what lies beyond the text
       SB_CUDA(cudaMemsetAsync(dst + n, 0, pad, stream_));
-      transfer_packed_ = true;
-      transfer_bytes_ = packed_bytes + (n - n_packed);
+      const uint64_t packed_chars = std::min<uint64_t>((uint64_t)sent_chunks * chunk, n);
+      transfer_packed_ = sent_chunks > 0;
+      transfer_bytes_ = (packed_chars + 63) / 64 * 16 + plain_bytes;
       sent = true;
     }
   }

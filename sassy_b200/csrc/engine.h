@@ -191,13 +191,11 @@ class Engine {
   uint64_t transfer_bytes_ = 0;
   bool transfer_packed_ = false;
   PackPool* pool_ = nullptr;
-  double pack_gbps_ = 40.0;  // measured host packing rate (characters/s), refined per transfer
-  double pcie_gbps_ = 52.0;  // pinned host->device copy rate assumed for the split
   uint8_t* h_pack_ = nullptr;  // pinned staging of the packed text
   size_t h_pack_cap_ = 0;
   DevBuf d_pack_;
   cudaStream_t unpack_stream_ = nullptr;  // expansion of the packed text, group by group behind the copies
-  std::vector<cudaEvent_t> unpack_ev_;
+  std::vector<cudaEvent_t> copy_ev_;      // one per host->device copy in flight (+ 2 for the expansion hand-over)
   int sm_count_ = 148;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

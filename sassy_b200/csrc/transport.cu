@@ -37,7 +37,7 @@ namespace sb {
 
 namespace {
 
-bool pack_range(const uint8_t* src, uint8_t* dst, size_t n) { return dna_pack(src, dst, n); }
+bool pack_range(const uint8_t* src, uint8_t* dst, size_t n, bool stream) { return dna_pack(src, dst, n, -1, stream); }
 
 }  // namespace
 
@@ -48,8 +48,11 @@ struct PackPool::Impl {
   // current job
   const uint8_t* src = nullptr;
   uint8_t* dst = nullptr;
-  size_t n = 0, chunk = 0, nchunks = 0;
-  std::atomic<size_t> next{0};
+  size_t n = 0, chunk = 0, nchunks = 0, ring = 0;
+  // unclaimed chunks [lo, hi): lo in the low 32 bits (workers take from the front), hi in the
+  // high 32 bits (the caller takes from the back)
+  std::atomic<uint64_t> range{0};
+  std::atomic<size_t> released{0};
   std::unique_ptr<std::atomic<uint8_t>[]> done;  // per chunk: 0 pending, 1 ok, 2 saw a foreign byte
   uint64_t generation = 0;
   size_t active = 0;
@@ -72,13 +75,31 @@ struct PackPool::Impl {
     }
   }
 
-  void run_chunks() {
+  bool take_front(size_t& c) {
+    uint64_t r = range.load(std::memory_order_relaxed);
     for (;;) {
-      const size_t c = next.fetch_add(1, std::memory_order_relaxed);
-      if (c >= nchunks) return;
+      const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+      if (lo >= hi) return false;
+      if (range.compare_exchange_weak(r, (r & 0xFFFFFFFF00000000ull) | (uint64_t)(lo + 1), std::memory_order_relaxed)) {
+        c = lo;
+        return true;
+      }
+    }
+  }
+
+  void run_chunks() {
+    size_t c;
+    while (take_front(c)) {
+      if (ring) {
+        // the previous user of this slot must have been copied out; cancel() empties the range and
+        // releases everything
+        while (c >= released.load(std::memory_order_acquire) + ring)
+          std::this_thread::sleep_for(std::chrono::microseconds(10));
+      }
       const size_t off = c * chunk;
       const size_t len = off + chunk <= n ? chunk : n - off;
-      const bool ok = pack_range(src + off, dst + (off >> 2), len);
+      const size_t slot = ring ? c % ring : c;
+      const bool ok = pack_range(src + off, dst + slot * (chunk >> 2), len, /*stream=*/ring == 0);
       done[c].store(ok ? 1 : 2, std::memory_order_release);
     }
   }
@@ -121,12 +142,13 @@ PackPool::~PackPool() {
 
 int PackPool::threads() const { return (int)impl_->workers.size(); }
 
-void PackPool::start(const uint8_t* src, uint8_t* dst, size_t n, size_t chunk) {
+void PackPool::start(const uint8_t* src, uint8_t* dst, size_t n, size_t chunk, size_t ring) {
   Impl& s = *impl_;
   std::lock_guard<std::mutex> lk(s.mu);
-  s.src = src, s.dst = dst, s.n = n, s.chunk = chunk;
+  s.src = src, s.dst = dst, s.n = n, s.chunk = chunk, s.ring = ring;
   s.nchunks = (n + chunk - 1) / chunk;
-  s.next.store(0);
+  s.range.store((uint64_t)s.nchunks << 32);
+  s.released.store(0);
   s.done.reset(new std::atomic<uint8_t>[s.nchunks ? s.nchunks : 1]);
   for (size_t c = 0; c < s.nchunks; c++) s.done[c].store(0);
   s.active = s.workers.size();
@@ -136,12 +158,41 @@ void PackPool::start(const uint8_t* src, uint8_t* dst, size_t n, size_t chunk) {
 
 size_t PackPool::chunks() const { return impl_->nchunks; }
 
+size_t PackPool::packed_end() const { return (size_t)(impl_->range.load(std::memory_order_acquire) >> 32); }
+
+int PackPool::chunk_state(size_t c) const { return impl_->done[c].load(std::memory_order_acquire); }
+
 bool PackPool::wait_chunk(size_t c) {
   uint8_t v;
   // sleep rather than spin: the workers own every core
   while ((v = impl_->done[c].load(std::memory_order_acquire)) == 0)
     std::this_thread::sleep_for(std::chrono::microseconds(30));
   return v == 1;
+}
+
+bool PackPool::claim_tail(size_t* c) {
+  uint64_t r = impl_->range.load(std::memory_order_relaxed);
+  for (;;) {
+    const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+    if (lo >= hi) return false;
+    if (impl_->range.compare_exchange_weak(r, ((uint64_t)(hi - 1) << 32) | lo, std::memory_order_acq_rel)) {
+      *c = hi - 1;
+      return true;
+    }
+  }
+}
+
+void PackPool::release(size_t upto) {
+  if (upto > impl_->released.load(std::memory_order_relaxed)) impl_->released.store(upto, std::memory_order_release);
+}
+
+void PackPool::cancel() {
+  uint64_t r = impl_->range.load(std::memory_order_relaxed);
+  for (;;) {
+    const uint32_t lo = (uint32_t)r;
+    if (impl_->range.compare_exchange_weak(r, ((uint64_t)lo << 32) | lo, std::memory_order_acq_rel)) break;
+  }
+  impl_->released.store(~(size_t)0 >> 1, std::memory_order_release);
 }
 
 void PackPool::finish() {
