@@ -802,8 +802,9 @@ def main():
             tables = est["words"] * 4 * {"dna": 4, "iupac": 32, "ascii": 256}[profile] * nq_local
             rec["e2e"] = {"value": n * e_steps / e["el"] / 1e9, "unit": "GB/s",
                           "h2d_bytes_per_step": est["transfer_bytes"] + tables + len(pats) * m,
-                          "transport": ("head of the text at 2 bits per character (packed by host threads inside the "
-                                        "timed region), tail as bytes, split so that packing and PCIe finish together")
+                          "transport": ("text at 2 bits per character (packed by host threads inside the timed region "
+                                        "into a cache-resident staging ring); while the copy engine would run dry, chunks "
+                                        "from the back of the text cross as plain bytes")
                           if est["transfer_packed"] else "bytes",
                           "transfer_ms": est["transfer_ms"],
                           "d2h_bytes_per_step": len(matches) * (24 + 4 * ((m + k + 1 + 15) // 16)) + 16,

@@ -55,16 +55,19 @@ if __name__ == "__main__":
         sys.exit(0)
     settings = [
         {},
-        {"SASSY_B200_PACK_RING": "0", "SASSY_B200_PACK_CHUNK": str(8 << 20)},
-        {"SASSY_B200_PACK_RING": "0"},
-        {"SASSY_B200_PACK_RING": "24"},
-        {"SASSY_B200_PACK_RING": "96"},
-        {"SASSY_B200_PACK_CHUNK": str(1 << 20), "SASSY_B200_PACK_RING": "96"},
-        {"SASSY_B200_PACK_CHUNK": str(4 << 20), "SASSY_B200_PACK_RING": "24"},
+        {"SASSY_B200_PACK_MERGE": "1"},
+        {"SASSY_B200_PACK_MERGE": "4"},
+        {"SASSY_B200_PACK_MERGE": "16"},
         {"SASSY_B200_PACK_THREADS": "15"},
         {"SASSY_B200_PACK_THREADS": "14"},
+        {"SASSY_B200_PACK_THREADS": "12"},
+        {"SASSY_B200_PACK_RING": "32"},
+        {"SASSY_B200_PACK_RING": "64"},
+        {"SASSY_B200_PACK_CHUNK": str(1 << 20), "SASSY_B200_PACK_RING": "96", "SASSY_B200_PACK_MERGE": "16"},
+        {"SASSY_B200_PACK_CHUNK": str(1 << 19), "SASSY_B200_PACK_RING": "192", "SASSY_B200_PACK_MERGE": "32"},
         {"SASSY_B200_PACK_AHEAD": "8192"},
-        {"SASSY_B200_PACK_AHEAD": "32768"},
+        {"SASSY_B200_PACK_THREADS": "15", "SASSY_B200_PACK_AHEAD": "8192"},
+        {"SASSY_B200_PACK_RING": "0", "SASSY_B200_PACK_CHUNK": str(8 << 20)},
     ]
     for env in settings:
         e = dict(os.environ)
