@@ -59,7 +59,7 @@ def test_sharded_search_equals_unsharded():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, patterns, text, k, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=60)
+    got = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -110,7 +110,7 @@ def test_gather_matchlists_and_rank_tags():
     procs = [ctx.Process(target=_worker_ml, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = q.get(timeout=120)
+    out = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
