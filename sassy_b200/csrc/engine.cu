@@ -1257,7 +1257,16 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
     meta[ntexts + i] = lens[i];
     total += (lens[i] + 15) & ~15ull;
   }
-  const size_t text_bytes = (size_t)total + 64;
+  // Enough work for the row-tiled kernels: the texts are scanned as ONE concatenated text, all
+  // queries at once (2 T lane-steps/s instead of the 0.25 T of one thread per (text, query) pair
+  // walking its text alone); see the candidate section below.  SASSY_B200_TEXTS_CONCAT: 0 never,
+  // 2 always (tests).
+  int concat_mode = 1;
+  if (const char* e = getenv("SASSY_B200_TEXTS_CONCAT")) concat_mode = atoi(e);
+  const bool concat = concat_mode != 0 && !(opts.alpha >= 0.f) && m > k && total > 0 &&
+                      (concat_mode == 2 || total >= (1ull << 20));
+  // the concatenation is tiled like any text: room for one extra row of any tiling behind it
+  const size_t text_bytes = concat ? padded_alloc(total) : (size_t)total + 64;
   const size_t meta_off = (text_bytes + 255) & ~(size_t)255;
   const size_t packed_bytes = meta_off + meta.size() * sizeof(uint64_t);
   // staged in PINNED memory (kept between calls) by a few threads: hundreds of megabytes of reads
@@ -1339,14 +1348,74 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
 
   unsigned long long h_counts[4] = {0, 0, 0, 0};
   uint64_t ncand = 0;
+  // Concatenated scan: a cost <= k inside a text can only be LOWERED by what the scan carries over
+  // from the previous text (the fresh state D[j][0] = j is the largest possible column), and only
+  // within the first m + k end positions of the text (an alignment of cost <= k spans at most
+  // m + k characters).  So: the row-tiled scan reports every candidate of the concatenation into a
+  // raw list; concat_remap_kernel keeps those beyond the first m + k end positions of their text
+  // (as (text, query) slots, text-relative positions) and texts_kernel computes the first m + k end
+  // positions of every text from a fresh state.  Both directions: "first" is in scan direction.
+  uint32_t nfwd = 0;
+  while (nfwd < nq && !queries[nfwd].rev) nfwd++;
+  DeviceText ctext;
+  ScanGeom cg;
+  CUtensorMap ctmap;
+  memset(&ctmap, 0, sizeof ctmap);
+  if (concat) {
+    for (uint32_t q = nfwd; q < nq; q++)
+      if (!queries[q].rev) throw CudaError("forward queries must precede reversed ones");
+    ctext.d = d_texts_.as<uint8_t>();
+    ctext.n = total;
+    ctext.alloc = text_bytes;
+    ctext.owned = false;
+    const int occ = scan_blocks_per_sm(W, false, variant_, nrows_);
+    cg = choose_geom(total, m, k, nq, occ * sm_count_);
+    if ((uint64_t)cg.rows * cg.ltot > ctext.alloc) throw CudaError("internal: text padding too small for tiling");
+    if (variant_ == kVariantTma) make_tensor_map(&ctmap, ctext, cg);
+    stats_.ltot = cg.ltot;
+    stats_.blocks_per_sm = (uint32_t)occ;
+  }
   for (int attempt = 0;; attempt++) {
     keys_.ensure(cand_cap_ * sizeof(uint64_t));
     cost_.ensure(cand_cap_ * sizeof(uint32_t));
     a.cand_keys = keys_.as<uint64_t>();
     a.cand_cost = cost_.as<uint32_t>();
     a.cand_cap = cand_cap_;
-    if (attempt > 0) SB_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long), stream_));
+    if (attempt > 0) SB_CUDA(cudaMemsetAsync(d_counts, 0, 4 * sizeof(unsigned long long), stream_));
     SB_CUDA(cudaEventRecord(ev_[1], stream_));
+    if (concat) {
+      keys2_.ensure(cand_cap_ * sizeof(uint64_t));
+      cost2_.ensure(cand_cap_ * sizeof(uint32_t));
+      ScanArgs c = a;  // the concatenation as one text; raw candidates, counted in d_counts[2]
+      c.text = ctext.d;
+      c.n = total;
+      c.g = cg;
+      c.cand_keys = keys2_.as<uint64_t>();
+      c.cand_cost = cost2_.as<uint32_t>();
+      c.cand_count = d_counts + 2;
+      if (nfwd) {
+        c.reset_idx = 0, c.nq = nfwd, c.qs_base = 0, c.eq = d_eq;
+        if (W == 1 && nfwd >= 2 && scan2_)
+          SB_CUDA(launch_scan2(false, variant_, &ctmap, c, stream_));
+        else
+          SB_CUDA(launch_scan(W, false, variant_, &ctmap, c, stream_));
+        stats_.scan_launches++;
+      }
+      if (nq > nfwd) {
+        c.reset_idx = total - 1, c.nq = nq - nfwd, c.qs_base = nfwd, c.eq = d_eq + (size_t)nfwd * nrows_ * W;
+        if (W == 1 && nq - nfwd >= 2 && scan2_)
+          SB_CUDA(launch_scan2(true, variant_, &ctmap, c, stream_));
+        else
+          SB_CUDA(launch_scan(W, true, variant_, &ctmap, c, stream_));
+        stats_.scan_launches++;
+      }
+      stats_.swar_lanes = (W == 1 && scan2_ && (nfwd >= 2 || nq - nfwd >= 2)) ? 2u : 1u;
+      const uint64_t skip = (uint64_t)m + (uint64_t)k;
+      SB_CUDA(launch_concat_remap(keys2_.as<uint64_t>(), cost2_.as<uint32_t>(), d_counts + 2, cand_cap_, a, t, total,
+                                  skip, stream_));
+      stats_.aux_launches++;
+      t.prefix = (uint32_t)skip;
+    }
     SB_CUDA(launch_texts(W, a, t, stream_));
     stats_.scan_launches++;
     if (ov) {
@@ -1359,12 +1428,13 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
     float ms = 0;
     SB_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2]));
     stats_.scan_ms += ms;
-    if (h_counts[0] <= cand_cap_) {
+    const unsigned long long most = std::max(h_counts[0], concat ? h_counts[2] : 0ull);
+    if (most <= cand_cap_) {
       ncand = h_counts[0];
       break;
     }
     if (attempt >= 3) throw CudaError("candidate buffer overflow after retries");
-    cand_cap_ = (size_t)(h_counts[0] + h_counts[0] / 8 + 1024);
+    cand_cap_ = (size_t)(most + most / 8 + 1024);
     stats_.retries++;
   }
   stats_.candidates = ncand;

@@ -69,8 +69,17 @@ struct TextsArgs {
   uint32_t ntexts, nq;
   uint32_t include_pos0;
   uint32_t overhang;  // 1: positions <= min(n, m+k) of every text are left to the edge kernel
+  uint32_t prefix;    // > 0: only the first `prefix` end positions (scan direction) of every text
 };
 cudaError_t launch_texts(int W, const ScanArgs& a, const TextsArgs& t, cudaStream_t stream);
+// Many texts scanned as ONE concatenated text by the row-tiled kernels (Engine::search_texts):
+// candidates (query, end position in the concatenation) become (text * nq + query, end position
+// in the text); those in the padding between texts and those within the first `skip` end
+// positions of their text -- where the state carried over from the previous text can lower a
+// cost; texts_kernel with `prefix` owns them -- are dropped.
+cudaError_t launch_concat_remap(const uint64_t* raw_keys, const uint32_t* raw_cost, const unsigned long long* raw_count,
+                                uint64_t raw_cap, const ScanArgs& out, const TextsArgs& t, uint64_t total,
+                                uint64_t skip, cudaStream_t stream);
 
 // Overhang: the end positions that the overhang changes -- 0..min(n, m+k) (cheap left column)
 // and n+1..n+steps (wildcard columns beyond the text, + floor(alpha * overshoot)) -- are

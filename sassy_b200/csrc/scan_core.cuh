@@ -877,6 +877,24 @@ SB_HD void verify_hit(const ScanArgs& a, const uint32_t* eq /*[nrows][W] of this
   }
 }
 
+// Concatenated texts (offs ascending, every text followed by padding): the text that holds the
+// end position `pos` (scan direction over `total` bytes) of a candidate, and the end position
+// inside that text, again in scan direction.  False for positions in the padding.
+SB_HD bool concat_locate(uint64_t pos, bool rev, uint64_t total, const uint64_t* offs, const uint64_t* lens,
+                         uint32_t ntexts, uint32_t& ti, uint64_t& local) {
+  if (pos == 0 || pos > total || ntexts == 0) return false;
+  const uint64_t g = rev ? total - pos : pos - 1;  // forward index of the last character consumed
+  uint32_t lo = 0, hi = ntexts;                    // last text with offs <= g
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if (offs[mid] <= g) lo = mid; else hi = mid;
+  }
+  if (offs[lo] > g || g >= offs[lo] + lens[lo]) return false;
+  ti = lo;
+  local = rev ? offs[lo] + lens[lo] - g : g - offs[lo] + 1;
+  return true;
+}
+
 // True when the stage starting at forward index stage_idx holds the restart index.
 SB_HD bool stage_is_special(const ScanArgs& a, uint64_t stage_idx) {
   return (a.reset_idx - stage_idx) < (uint64_t)kStageBytes;  // unsigned wrap-around intended

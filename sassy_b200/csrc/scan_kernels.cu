@@ -679,8 +679,28 @@ __global__ void __launch_bounds__(128)
       continue;
     }
     if (t.include_pos0 && a.m <= a.k) emit_candidate(a, (uint32_t)slot, 0, a.m);
+    const int64_t stop = (t.prefix && (int64_t)t.prefix < n) ? (int64_t)t.prefix : n;
     scan_window<W>(a, a.eq + (size_t)q * a.nrows * W, (uint32_t)slot, t.rev_flags[q] != 0, t.base + t.offs[ti], n, 0,
-                   n, 0);
+                   stop, 0);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    concat_remap_kernel(const uint64_t* __restrict__ raw_keys, const uint32_t* __restrict__ raw_cost,
+                        const unsigned long long* __restrict__ raw_count, uint64_t raw_cap,
+                        const __grid_constant__ ScanArgs out, const __grid_constant__ TextsArgs t, uint64_t total,
+                        uint64_t skip) {
+  unsigned long long n = *raw_count;
+  if (n > raw_cap) n = raw_cap;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint64_t key = raw_keys[i];
+    const uint32_t q = key_qs(key);
+    uint32_t ti;
+    uint64_t local;
+    if (!concat_locate(key_pos(key), t.rev_flags[q] != 0, total, t.offs, t.lens, t.ntexts, ti, local)) continue;
+    if (local <= skip) continue;
+    emit_candidate(out, ti * t.nq + q, local, (int)raw_cost[i]);
   }
 }
 
@@ -1363,6 +1383,13 @@ cudaError_t launch_overhang_edges(int W, const ScanArgs& a, const OverhangArgs& 
 #undef SB_OCALL
     default: return cudaErrorInvalidValue;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_concat_remap(const uint64_t* raw_keys, const uint32_t* raw_cost, const unsigned long long* raw_count,
+                                uint64_t raw_cap, const ScanArgs& out, const TextsArgs& t, uint64_t total,
+                                uint64_t skip, cudaStream_t stream) {
+  concat_remap_kernel<<<148 * 4, 256, 0, stream>>>(raw_keys, raw_cost, raw_count, raw_cap, out, t, total, skip);
   return cudaGetLastError();
 }
 

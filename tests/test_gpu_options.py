@@ -106,10 +106,14 @@ def test_gpu_encoded_max_n_frac():
             assert sorted(map(kk, got)) == sorted(map(kk, want))
 
 
+@pytest.mark.parametrize("concat", ["0", "2"], ids=["thread-per-pair", "concatenated"])
 @pytest.mark.parametrize("alphabet", ["dna", "iupac"])
-def test_gpu_search_many_fuzz(alphabet):
+def test_gpu_search_many_fuzz(alphabet, concat, monkeypatch):
     """Mirrors the reference's search_many_fuzz (src/search.rs:3624-3730): random pattern and
-    text sets, all three modes, against pattern-by-text single searches (the oracle)."""
+    text sets, all three modes, against pattern-by-text single searches (the oracle).  Both
+    many-text routes of Engine::search_texts: one thread per (text, query) pair, and the texts
+    scanned as one concatenated text by the row-tiled kernels."""
+    monkeypatch.setenv("SASSY_B200_TEXTS_CONCAT", concat)
     rng = random.Random(33)
     s = mk(alphabet, True)
     fwd = mk(alphabet, False)
@@ -131,6 +135,45 @@ def test_gpu_search_many_fuzz(alphabet):
         for mode in ("single", "batch_patterns", "batch_texts"):
             got = srch.search_many(pats, texts, k, 0, mode)
             assert list(map(key, got)) == list(map(key, want)), (it, mode, m, k, rc)
+
+
+@pytest.mark.parametrize("alphabet", ["dna", "iupac", "ascii"])
+def test_gpu_search_many_reads(alphabet):
+    """The nanopore-barcode shape at a size that takes the concatenated route by itself (> 1 MiB of
+    reads): barcodes planted at the very start and the very end of reads (where the state carried
+    over from the neighbouring read must not leak in), reads shorter than m + k, empty reads, a
+    read that ends with the start of a barcode and is followed by one that continues it."""
+    rng = random.Random(35)
+    rc = alphabet != "ascii"
+    s = mk(alphabet, rc)
+    m, k = 24, 3
+    sigma = b"ACGT" if alphabet != "ascii" else b"abcdefghijklmnop"
+    seq = lambda n: bytes(rng.choice(sigma) for _ in range(n))
+    pats = [seq(m) for _ in range(24)]
+    reads = []
+    total = 0
+    while total < (1 << 20) + 50_000:
+        ln = rng.choice([0, 5, 20, 27, 30, 64]) if rng.random() < 0.1 else rng.randrange(200, 3000)
+        r = bytearray(seq(ln))
+        if ln >= 100 and rng.random() < 0.6:
+            bc = bytearray(rng.choice(pats))
+            for _ in range(rng.randrange(0, k + 1)):
+                bc[rng.randrange(m)] = rng.choice(sigma)
+            where = rng.choice(["start", "end", "mid"])
+            pos = 0 if where == "start" else (ln - m if where == "end" else rng.randrange(0, ln - m))
+            pos = max(0, min(ln - m, pos + rng.randrange(-2, 3)))
+            r[pos:pos + m] = bc
+        reads.append(bytes(r))
+        total += ln
+    # a barcode split over two neighbouring reads must not be found
+    p0 = pats[0]
+    reads.append(seq(500) + p0[:12])
+    reads.append(p0[12:] + seq(500))
+    want = oracle.search_many(alphabet, pats, reads, k, rc=rc)
+    got = s.search_many(pats, reads, k)
+    assert list(map(key, got)) == list(map(key, want))
+    assert len(want) > 100
+    assert s.stats()["swar_lanes"] == 2  # the two-pattern row-tiled scan ran
 
 
 def test_gpu_search_many_mixed_lengths_and_long_text():
