@@ -384,17 +384,17 @@ std::vector<Match> Searcher::collected_v1(PeerGather& pg, size_t m, bool* comple
   return out;
 }
 
-std::vector<Match> Searcher::flush_sharded(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs,
-                                           size_t n_slabs, uint64_t n_global, int* state) {
+void Searcher::flush_sharded(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
+                             uint64_t n_global, int* state, FlatMatches& merged) {
   engine_->flush_gather(pg);
   *state = 1;
   if (!pg.pipelined() || !pg.has_result()) {
     *state = 2;
-    return {};
+    return;
   }
   if (!pg.ok())
     throw std::runtime_error("pipelined gather: some rank's result did not fit the exchange; use the lock-step mode");
-  return merge_collected(pg, m, all_minima, slabs, n_slabs, n_global);
+  merge_collected(pg, m, all_minima, slabs, n_slabs, n_global, merged);
 }
 
 std::vector<Match> Searcher::flush_gathered(PeerGather& pg, size_t m, int* state) {
@@ -406,7 +406,7 @@ std::vector<Match> Searcher::flush_gathered(PeerGather& pg, size_t m, int* state
 std::vector<Match> Searcher::search_sharded_gathered(PeerGather& pg, const uint8_t* pattern, size_t m,
                                                      const DeviceText& window, size_t k, bool all_minima,
                                                      const SlabInfo* slabs, size_t n_slabs, uint64_t n_global,
-                                                     bool* complete) {
+                                                     bool* complete, FlatMatches& merged) {
   // search_all of the window; in lock-step mode the records of THIS search are in the host mirror
   // afterwards, in pipelined mode those of the previous one
   engine_->set_gather(&pg, 1);
@@ -434,15 +434,16 @@ std::vector<Match> Searcher::search_sharded_gathered(PeerGather& pg, const uint8
       return convert_v1(ms_, 1, m, [wn](size_t) { return wn; });
     }
   }
-  return merge_collected(pg, m, all_minima, slabs, n_slabs, n_global);
+  merge_collected(pg, m, all_minima, slabs, n_slabs, n_global, merged);
+  return {};
 }
 
 // Ownership filter + local-minima rule on the RAW records of the collected step (scan-direction
 // coordinates, 32 bytes each); only the selected records are turned into Matches (CIGAR strings).
 // Every rank merges all ranks' search_all records every step: this is the host cost of a sharded
 // search, so it avoids per-record allocations.
-std::vector<Match> Searcher::merge_collected(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs,
-                                             size_t n_slabs, uint64_t n_global) {
+void Searcher::merge_collected(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
+                               uint64_t n_global, FlatMatches& merged) {
   struct Item {
     uint64_t key;
     uint32_t cost, rank, idx;
@@ -485,27 +486,43 @@ std::vector<Match> Searcher::merge_collected(PeerGather& pg, size_t m, bool all_
   std::vector<uint64_t> keys(items.size());
   std::vector<uint32_t> cost(items.size());
   for (size_t i = 0; i < items.size(); i++) keys[i] = items[i].key, cost[i] = items[i].cost;
-  // the kept records as one MatchSet whose "text index" is the source rank
-  MatchSet kept;
-  std::vector<uint32_t> kept_rank;
+  // the kept records straight into flat C records (as Searcher::convert_v1 + to_result would)
+  merged.m.clear();
+  merged.ops.clear();
   for (size_t i = 0; i < items.size(); i++) {
     if (!select_candidate(keys.data(), cost.data(), i, items.size(), all_minima)) continue;
-    const PeerGather::Slot sl = pg.slot((int)items[i].rank);
-    if (kept.m.empty()) kept.ops_words = sl.ops_words;
-    GpuMatch g = sl.records[items[i].idx];
-    g.qs = (uint32_t)(items[i].rank * nq + g.qs % nq);
-    kept.m.push_back(g);
-    kept.ops.insert(kept.ops.end(), sl.ops + (size_t)items[i].idx * sl.ops_words,
-                    sl.ops + (size_t)(items[i].idx + 1) * sl.ops_words);
+    const int r = (int)items[i].rank;
+    const PeerGather::Slot sl = pg.slot(r);
+    const GpuMatch& g = sl.records[items[i].idx];
+    if (g.failed & 1u) throw std::runtime_error("Trace failed (text contains bytes outside the profile's alphabet?)");
+    const SlabInfo& sb_ = slabs[r];
+    const uint64_t wn = sl.text_n;
+    sassy_gpu_Match o;
+    memset(&o, 0, sizeof o);
+    o.pattern_idx = 0;
+    o.text_idx = 0;
+    o.cost = g.cost;
+    o.pattern_start = without_trace_ ? ~0ull : (uint64_t)((g.failed >> 8) & 0xFFFu);
+    o.pattern_end = m - (uint64_t)(g.failed >> 20);
+    if (g.qs % nq == 0) {
+      o.strand = (uint8_t)kFwd;
+      o.text_start = sb_.window_off + g.text_start;
+      o.text_end = sb_.window_off + g.text_end;
+    } else {
+      o.strand = (uint8_t)kRc;
+      o.text_start = sb_.window_off + (wn - g.text_end);
+      o.text_end = without_trace_ ? ~0ull : sb_.window_off + (wn - g.text_start);
+    }
+    o.ops_off = merged.ops.size();
+    if (!without_trace_) {
+      const uint32_t* w = sl.ops + (size_t)items[i].idx * sl.ops_words;
+      o.ops_len = g.nops;
+      const size_t off = merged.ops.size();
+      merged.ops.resize(off + g.nops);
+      for (uint32_t a = 0; a < g.nops; a++) merged.ops[off + a] = kOpChars[(w[a >> 4] >> ((a & 15) * 2)) & 3u];
+    }
+    merged.m.push_back(o);
   }
-  std::vector<Match> out = convert_v1(kept, 1, m, [&](size_t ti) { return (uint64_t)pg.slot((int)ti).text_n; });
-  for (auto& mm : out) {
-    const SlabInfo& sb_ = slabs[mm.text_idx];
-    mm.text_start += sb_.window_off;
-    mm.text_end += sb_.window_off;
-    mm.text_idx = 0;
-  }
-  return out;
 }
 
 std::vector<Match> Searcher::merge_gathered(std::vector<Match>& all, bool all_minima, const SlabInfo* slabs,
@@ -1021,12 +1038,17 @@ sassy_gpu_Result* sassy_gpu_search_text_sharded(sassy_SearcherType* searcher, sa
     for (size_t i = 0; i < n_slabs; i++) info[i] = sb::SlabInfo{slabs[i].window_off, slabs[i].own_lo, slabs[i].own_hi};
     bool ok = false;
     const bool primed = !gather->g.pipelined() || gather->g.has_result() || false;
+    sb::Searcher::FlatMatches merged;
     auto v = searcher->s.search_sharded_gathered(gather->g, pattern, pattern_len, *window->t, k, all != 0, info.data(),
-                                                 n_slabs, n_global, &ok);
+                                                 n_slabs, n_global, &ok, merged);
     (void)primed;
     *complete = ok ? 1 : 0;
     if (gather->g.pipelined() && !gather->g.has_result()) *complete = 2;  // pipeline priming: no result yet
-    return to_result(v);
+    if (!ok) return to_result(v);  // this rank's unmerged matches for the caller's own collective
+    sassy_gpu_Result* r = new sassy_gpu_Result;
+    r->m.swap(merged.m);
+    r->ops.swap(merged.ops);
+    return r;
   });
 }
 
@@ -1045,8 +1067,12 @@ sassy_gpu_Result* sassy_gpu_text_sharded_flush(sassy_SearcherType* searcher, sas
     if (!searcher || !gather || !slabs || !state) throw std::invalid_argument("null pointer");
     std::vector<sb::SlabInfo> info(n_slabs);
     for (size_t i = 0; i < n_slabs; i++) info[i] = sb::SlabInfo{slabs[i].window_off, slabs[i].own_lo, slabs[i].own_hi};
-    auto merged = searcher->s.flush_sharded(gather->g, pattern_len, all != 0, info.data(), n_slabs, n_global, state);
-    return to_result(merged);
+    sb::Searcher::FlatMatches merged;
+    searcher->s.flush_sharded(gather->g, pattern_len, all != 0, info.data(), n_slabs, n_global, state, merged);
+    sassy_gpu_Result* r = new sassy_gpu_Result;
+    r->m.swap(merged.m);
+    r->ops.swap(merged.ops);
+    return r;
   });
 }
 

@@ -113,20 +113,26 @@ class Searcher {
   // gather and the ownership filter + local-minima rule run on the merged list.  *complete = false:
   // this rank's unmerged search_all matches (window coordinates) are returned for the caller's own
   // collective + sassy_gpu_merge_slabs.
+  // The merged result is written as flat C records (`merged`; no per-match allocation: every rank
+  // merges all ranks' records every step); the returned vector only holds the fallback's matches.
+  struct FlatMatches {
+    std::vector<sassy_gpu_Match> m;
+    std::string ops;
+  };
   std::vector<Match> search_sharded_gathered(PeerGather& pg, const uint8_t* pattern, size_t m,
                                              const DeviceText& window, size_t k, bool all_minima,
                                              const SlabInfo* slabs, size_t n_slabs, uint64_t n_global,
-                                             bool* complete);
+                                             bool* complete, FlatMatches& merged);
 
   // Pipelined PeerGather: the records of the collected (previous) step / of the last pushed step.
   std::vector<Match> collected_v1(PeerGather& pg, size_t m, bool* complete, int* state = nullptr);
   std::vector<Match> flush_gathered(PeerGather& pg, size_t m, int* state);
   std::vector<Match> merge_gathered(std::vector<Match>& all, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
                                     uint64_t n_global);
-  std::vector<Match> merge_collected(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
-                                     uint64_t n_global);
-  std::vector<Match> flush_sharded(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
-                                   uint64_t n_global, int* state);
+  void merge_collected(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
+                       uint64_t n_global, FlatMatches& merged);
+  void flush_sharded(PeerGather& pg, size_t m, bool all_minima, const SlabInfo* slabs, size_t n_slabs,
+                     uint64_t n_global, int* state, FlatMatches& merged);
 
   void validate_pattern(const uint8_t* p, size_t m) const;
 
