@@ -90,6 +90,35 @@ Engine::Engine(int profile, int device) : profile_(profile), device_(device), va
   if (!encode_tiled_ && variant_ == kVariantTma) throw CudaError("cuTensorMapEncodeTiled not available");
 }
 
+namespace {
+struct HostTimerState {
+  double acc[HostTimers::kCount] = {};
+  unsigned long long n[HostTimers::kCount] = {};
+  bool on = false;
+  HostTimerState() {
+    const char* e = getenv("SASSY_B200_HOST_TIMING");
+    on = e && atoi(e) != 0;
+  }
+  ~HostTimerState() {
+    if (!on) return;
+    static const char* names[HostTimers::kCount] = {"entry -> parameters uploaded", "launches + wait for the GPU",
+                                                    "after the last synchronisation", "merge of gathered records",
+                                                    "whole C call (sharded search)"};
+    for (int i = 0; i < HostTimers::kCount; i++)
+      if (n[i]) fprintf(stderr, "[sassy_b200 host timing] %-34s %9.1f us avg over %llu calls\n", names[i], acc[i] / n[i], n[i]);
+  }
+};
+HostTimerState g_host_timers;
+}  // namespace
+bool HostTimers::on() { return g_host_timers.on; }
+void HostTimers::add(int which, double us) {
+  g_host_timers.acc[which] += us;
+  g_host_timers.n[which]++;
+}
+double HostTimers::now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
@@ -617,6 +646,8 @@ uint64_t Engine::post_process(const PostCtx& c, const SearchOpts& opts, uint64_t
 void Engine::search(const DeviceText& text, const std::vector<Query>& queries, int m, int k, const SearchOpts& opts,
                     MatchSet& out) {
   const bool all_minima = opts.all_minima, include_pos0 = opts.include_pos0;
+  const bool timing = HostTimers::on();
+  const double t_entry = timing ? HostTimers::now_us() : 0.0;
   SB_CUDA(cudaSetDevice(device_));
   cudaGetLastError();  // a stale error left by another library in this thread is not ours to report
   stats_ = SearchStats();
@@ -676,6 +707,9 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   const bool pair = profile_ == kDna && WT <= pair_max_words_;
   const size_t tab_words = pair ? (size_t)kPairTableWords * WT : (size_t)256 * WT;
   upload_params(queries, m, W, fp, pair, fused, qgram ? &qp : nullptr);
+  const double t_uploaded = timing ? HostTimers::now_us() : 0.0;
+  if (timing) HostTimers::add(HostTimers::kPre, t_uploaded - t_entry);
+  double t_last_sync = t_uploaded;
   uint8_t* dst = d_stage_.as<uint8_t>();
   unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(dst + off_counts_);
   unsigned long long* d_cand_count = d_counts;      // [0] candidates
@@ -746,6 +780,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
   auto read_counts = [&]() {
     SB_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, stream_));
     SB_CUDA(cudaStreamSynchronize(stream_));
+    if (timing) t_last_sync = HostTimers::now_us();
   };
   auto elapsed = [&](cudaEvent_t e0, cudaEvent_t e1) {
     float ms = 0;
@@ -795,6 +830,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
                          pg_user_, stream_));
     stats_.aux_launches += 2;
   };
+  bool tail_event = false;
   auto queue_small_tail = [&]() {
     if (!small_path) {
       pg_exchange(true);
@@ -836,6 +872,9 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     SB_CUDA(launch_trace(t, stream_));
     stats_.aux_launches += 2;
     pg_exchange(!small_in_slot);
+    // end of the search when this tail completes it: the caller synchronises right behind it
+    SB_CUDA(cudaEventRecord(ev_[3], stream_));
+    tail_event = true;
   };
   // after the synchronisation that follows a tail: did every rank deliver a complete result?
   auto pg_check = [&]() {
@@ -1201,12 +1240,19 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
     c.end_bit = end_bit;
     nsel = post_process(c, opts, ncand, out);
   }
-  SB_CUDA(cudaEventRecord(ev_[3], stream_));
-  SB_CUDA(cudaStreamSynchronize(stream_));
+  if (!(small_done && tail_event)) {  // (the fast tail recorded the end and was synchronised already)
+    SB_CUDA(cudaEventRecord(ev_[3], stream_));
+    SB_CUDA(cudaStreamSynchronize(stream_));
+  }
   float total = 0;
   SB_CUDA(cudaEventElapsedTime(&total, ev_[0], ev_[3]));
   stats_.total_ms = total;
   stats_.matches = nsel;
+  if (timing) {
+    const double t_end = HostTimers::now_us();
+    HostTimers::add(HostTimers::kGpuWait, t_last_sync - t_uploaded);
+    HostTimers::add(HostTimers::kPost, t_end - t_last_sync);
+  }
   if (transfer_pending_) {  // the text of this search came from the host just before it
     SB_CUDA(cudaEventElapsedTime(&transfer_ms_, ev_[5], ev_[6]));
     transfer_pending_ = false;

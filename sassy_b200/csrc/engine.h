@@ -23,6 +23,15 @@ struct CudaError : std::runtime_error {
 };
 // A size limit of this implementation (not an error of the reference): the C ABI's search()
 // reports it without aborting the process (include/sassy.h).
+// Host-side phase timers of the search entry points (SASSY_B200_HOST_TIMING=1 prints the averages
+// to stderr at exit; profiling aid, not part of the product path's behaviour).
+struct HostTimers {
+  enum { kPre, kGpuWait, kPost, kMerge, kSearchCall, kCount };
+  static bool on();
+  static void add(int which, double us);
+  static double now_us();
+};
+
 struct CapacityError : CudaError {
   using CudaError::CudaError;
 };

@@ -434,7 +434,9 @@ std::vector<Match> Searcher::search_sharded_gathered(PeerGather& pg, const uint8
       return convert_v1(ms_, 1, m, [wn](size_t) { return wn; });
     }
   }
+  const double t0 = HostTimers::on() ? HostTimers::now_us() : 0.0;
   merge_collected(pg, m, all_minima, slabs, n_slabs, n_global, merged);
+  if (HostTimers::on()) HostTimers::add(HostTimers::kMerge, HostTimers::now_us() - t0);
   return {};
 }
 
@@ -1038,6 +1040,13 @@ sassy_gpu_Result* sassy_gpu_search_text_sharded(sassy_SearcherType* searcher, sa
     for (size_t i = 0; i < n_slabs; i++) info[i] = sb::SlabInfo{slabs[i].window_off, slabs[i].own_lo, slabs[i].own_hi};
     bool ok = false;
     const bool primed = !gather->g.pipelined() || gather->g.has_result() || false;
+    const double t_call = sb::HostTimers::on() ? sb::HostTimers::now_us() : 0.0;
+    struct CallTimer {
+      double t0;
+      ~CallTimer() {
+        if (sb::HostTimers::on()) sb::HostTimers::add(sb::HostTimers::kSearchCall, sb::HostTimers::now_us() - t0);
+      }
+    } call_timer{t_call};
     sb::Searcher::FlatMatches merged;
     auto v = searcher->s.search_sharded_gathered(gather->g, pattern, pattern_len, *window->t, k, all != 0, info.data(),
                                                  n_slabs, n_global, &ok, merged);
