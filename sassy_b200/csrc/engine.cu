@@ -924,7 +924,7 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
       gf.rows = (uint32_t)((n + gf.ltot - 1) / gf.ltot);
       gf.nstage = gf.ltot / kStageBytes;
     }
-    const bool qseq = qgram && variant_ == kVariantTma && qgram_seq_ && n < (1ull << 36);
+    const bool qseq = qgram && variant_ == kVariantTma && qgram_seq_ && n < (1ull << 36) && kStageBytes == 64;
     CUtensorMap ftmap;
     memset(&ftmap, 0, sizeof ftmap);
     if (variant_ == kVariantTma && !qseq) make_tensor_map(&ftmap, text, gf);

@@ -435,7 +435,8 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
   __shared__ uint32_t hit_n[kWarpsPerBlock];
   constexpr uint32_t kTabWords = (1u << (2 * Q)) / 32;
   __shared__ __align__(16) uint32_t bitmap[kTabWords];
-  static_assert(kStageBytes == 64, "tiles are 32 x 64 bytes");
+  // tiles are 32 x 64 bytes: builds with another stage size (tiling experiments) run the row-tiled kernel
+  if (kStageBytes != 64) return;
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t qs = a.qs_base;
   HitQueue hq;
