@@ -238,6 +238,47 @@ def test_dna_packed_transport(tma):
     assert s2.stats()["transfer_packed"] == 0
 
 
+def test_dna_packed_transport_pinned_ring(tma):
+    """A pinned host text longer than the staging ring (48 x 2 Mi characters): ring slots are
+    re-used, chunks from the back of the text cross as plain bytes, matches straddle chunk borders
+    and the packed / plain border; a foreign byte late in the text (after most of it has been
+    expanded on the device) falls back to the byte transport with the same result."""
+    import sassy_b200
+    rng = random.Random(28)
+    chunk = 2 << 20
+    n = 120 * chunk + 4099
+    table = bytes(b"ACGTacgt"[c & 7] for c in range(256))
+    t = bytearray(rng.randbytes(n).translate(table))
+    p = rand_seq(rng, 32)
+    spots = [0, chunk - 16, 47 * chunk - 5, 48 * chunk - 31, 49 * chunk + 1, 90 * chunk - 16, 100 * chunk - 1,
+             110 * chunk - 17, 119 * chunk - 3, n - 32]
+    for pos in spots:
+        t[pos:pos + 32] = p
+    addr = sassy_b200.host_alloc(n)
+    try:
+        ctypes.memmove(addr, bytes(t), n)
+        s = sassy_b200.Searcher("dna", rc=True)
+        s.set_transport("bytes")
+        want = s.search(p, (addr, n), 3)
+        assert s.stats()["transfer_packed"] == 0
+        assert sorted(m.text_start for m in want if m.cost == 0 and m.strand == "+") == sorted(spots)
+        s.set_transport("packed")
+        for _ in range(3):  # the split between packed and plain bytes differs from call to call
+            got = s.search(p, (addr, n), 3)
+            st = s.stats()
+            assert st["transfer_packed"] == 1 and st["transfer_bytes"] < n
+            assert got == want
+        ctypes.memset(addr + 117 * chunk + 12345, ord("N"), 1)
+        t[117 * chunk + 12345] = ord("N")
+        s.set_transport("bytes")
+        want2 = s.search(p, (addr, n), 3)
+        s.set_transport("packed")
+        got2 = s.search(p, (addr, n), 3)
+        assert s.stats()["transfer_packed"] == 0 and got2 == want2
+    finally:
+        sassy_b200.host_free(addr)
+
+
 def test_c_abi_search_symbol():
     """The reference's own entry points (include/sassy.h), called as c/example.c does."""
     from sassy_b200 import _native
