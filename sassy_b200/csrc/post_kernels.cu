@@ -210,6 +210,9 @@ constexpr int kTraceWideWindow = 1280;  // characters of a traceback window stag
 template <int P, int WL>
 __global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const __grid_constant__ TraceArgs t) {
   __shared__ uint8_t win[kTraceWideWarps][kTraceWideWindow];
+  // column stores of the block's warps when they fit (launch_trace sets smem_cols): the walk of
+  // lane 0 reads two or three words per step, each a round trip to L2 otherwise
+  extern __shared__ __align__(16) uint32_t trace_cols[];
   uint64_t count = t.count;
   if (t.count_dev) {
     const unsigned long long total = *t.count_dev;
@@ -236,7 +239,8 @@ __global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const 
     // contiguous column store per match: the 4 fields of a word are 16 adjacent bytes, the words of a
     // column adjacent lines, so the walk touches one new 128-byte line per step
     ColStore cs;
-    cs.base = t.scratch + (li % nwarps) * trace_words_per_match(m, k, W);
+    cs.base = t.smem_cols ? trace_cols + (threadIdx.x >> 5) * trace_words_per_match(m, k, W)
+                          : t.scratch + (li % nwarps) * trace_words_per_match(m, k, W);
     cs.stride = 1;
     const uint64_t fill = (uint64_t)m + (uint64_t)k;
     const uint64_t off = end > fill ? end - fill : 0;
@@ -383,13 +387,17 @@ cudaError_t launch_trace(const TraceArgs& t0, cudaStream_t stream) {
   if (trace_is_wide(t)) {
     // the scratch holds trace_threads(count) column stores, the warps in flight need fewer
     const unsigned blocks = (unsigned)(trace_wide_warps(t.count) / kTraceWideWarps);
+    // column stores in shared memory when the block's four fit 40 KB (e.g. m = 100, k = 8: 7 KB each)
+    const size_t cols_bytes = (size_t)trace_words_per_match(t.m, t.k, t.W) * sizeof(uint32_t) * kTraceWideWarps;
+    t.smem_cols = cols_bytes <= 40 * 1024 ? 1 : 0;
+    const size_t dyn = t.smem_cols ? cols_bytes : 0;
 #define SB_TW(PP)                                                                                     \
   if (t.W <= 32)                                                                                      \
-    trace_wide_kernel<PP, 1><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t);                         \
+    trace_wide_kernel<PP, 1><<<blocks, 32 * kTraceWideWarps, dyn, stream>>>(t);                       \
   else if (t.W == 64)                                                                                 \
-    trace_wide_kernel<PP, 2><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t);                         \
+    trace_wide_kernel<PP, 2><<<blocks, 32 * kTraceWideWarps, dyn, stream>>>(t);                       \
   else if (t.W == 128)                                                                                \
-    trace_wide_kernel<PP, 4><<<blocks, 32 * kTraceWideWarps, 0, stream>>>(t);                         \
+    trace_wide_kernel<PP, 4><<<blocks, 32 * kTraceWideWarps, dyn, stream>>>(t);                       \
   else                                                                                                \
     return cudaErrorInvalidValue;
     switch (t.profile) {

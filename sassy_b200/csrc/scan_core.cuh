@@ -89,6 +89,7 @@ struct ScanArgs {
   uint32_t hit_exact;       // 1: hit keys hold a nominal END POSITION (scan direction) instead of a 16-byte chunk
   const uint32_t* hit_span; // hit_exact: per entry, how many positions beyond the nominal one the entry covers
   uint32_t max_span;        // upper bound of hit_span (sizes the window staging of the wide re-scan kernel)
+  uint32_t wide_few;        // launch_verify: both re-scan kernels run, the device-side entry count picks one
   // Regional fallback of the prefilter routes.  A tile = the kScanThreads rows of one block of the
   // scan geometry.  Tiles with so many hits that re-scanning their neighbourhoods would cost more
   // than scanning the tile (repeats, low-complexity sequence) are marked dense: their hits are
@@ -692,6 +693,14 @@ SB_HD uint32_t pack4_classes(uint32_t x) {
   return umulhi32(x & 0x06060606u, 0x82082000u);
 }
 
+SB_HD int first_bit(uint32_t x) {  // index of the lowest set bit, x != 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
+
 SB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // low word of (hi:lo) >> sh, sh in [0, 32)
 #if defined(__CUDA_ARCH__)
   return __funnelshift_r(lo, hi, sh);
@@ -785,15 +794,34 @@ SB_HD bool refine_hit(const ScanArgs& a, uint32_t qs, bool rev, uint64_t base, i
     c[j] = code;
   }
   const uint32_t* conf = a.qconf + (size_t)qs * a.qnp * kConfWords;
+  // vals[i] = the 16 characters of alignment i (the alignment starts at character 32 + rel0 + i of the
+  // window: 4 .. 47).  All shares of the q-gram route have the same rel0, so the 16 funnel shifts
+  // are done once per hit and a share costs 16 compares (statically indexed registers throughout).
+  uint32_t vals[16];
+  int32_t vals_rel0 = 1 << 30;
   for (uint32_t p = 0; p < a.qnp; p++) {
     const uint32_t code = conf[p * kConfWords], mask = conf[p * kConfWords + 1];
     const int32_t rel0 = (int32_t)conf[p * kConfWords + 2];
     const uint32_t off = conf[p * kConfWords + 3], len = conf[p * kConfWords + 4];
-    for (int i = 0; i < 16; i++) {
-      const uint32_t o = (uint32_t)(32 + rel0 + i);  // start of the alignment relative to base - 32: 4 .. 47
-      const uint32_t w0 = c[o >> 4], w1 = (o >> 4) < 3 ? c[(o >> 4) + 1] : 0u;
-      const uint32_t val = funnel_r(w0, w1, 2 * (o & 15u));
-      if (((val ^ code) & mask) != 0) continue;
+    if (rel0 != vals_rel0) {
+      vals_rel0 = rel0;
+      const uint32_t o0 = (uint32_t)(32 + rel0);
+      const uint32_t wi = o0 >> 4, sh = o0 & 15u;
+      const uint32_t w0 = wi == 0 ? c[0] : (wi == 1 ? c[1] : c[2]);
+      const uint32_t w1 = wi == 0 ? c[1] : (wi == 1 ? c[2] : c[3]);
+      const uint32_t w2 = wi == 0 ? c[2] : (wi == 1 ? c[3] : 0u);
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const uint32_t x = sh + (uint32_t)i;  // 0 .. 30
+        vals[i] = x < 16 ? funnel_r(w0, w1, 2 * x) : funnel_r(w1, w2, 2 * (x - 16));
+      }
+    }
+    uint32_t cand = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) cand |= (uint32_t)(((vals[i] ^ code) & mask) == 0) << i;
+    while (cand) {
+      const int i = first_bit(cand);
+      cand &= cand - 1;
       const int64_t start = (int64_t)base + rel0 + i;  // forward index of the first character of F
       if (start < 0 || start + (int64_t)len > (int64_t)a.n) continue;
       // An intact copy of the pattern matches with ALL its shares, on one diagonal, and every share
@@ -1077,7 +1105,8 @@ struct ColStore {
   // hint: the line holding `slot` will be read a few steps from now (device only)
   SB_HD void prefetch(uint32_t slot) const {
 #if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (uint64_t)slot * stride));
+    // generic address: a column store in shared memory makes this a no-op
+    asm volatile("prefetch.L1 [%0];" ::"l"(base + (uint64_t)slot * stride));
 #else
     (void)slot;
 #endif

@@ -539,12 +539,17 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
 // computation, after an L2 prefetch of the whole window: thousands of resident threads
 // each touching 2-3 lines would otherwise evict each other's lines from L1 between two
 // consecutive byte loads.
+// Refined entries of patterns of 3 .. 7 words: up to this many entries the warp-per-entry kernel
+// takes them (launch_verify launches both kernels, each tests the device-side count).
+constexpr unsigned long long kWideFewEntries = 148ull * 64;  // one wave of warps
+
 template <int W>
 __global__ void __launch_bounds__(128)
     verify_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags) {
   if (a.guard_limit && *a.guard_count > a.guard_limit) return;  // too many hits: the regional pass follows
   unsigned long long nhits = *a.hit_count;
   if (nhits > a.hit_cap) nhits = a.hit_cap;
+  if (a.wide_few && nhits <= kWideFewEntries) return;  // verify_wide_kernel has them
   const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nhits; i += nthreads)
     verify_one<W>(a, rev_flags, i);
@@ -1095,6 +1100,10 @@ __global__ void __launch_bounds__(32 * kWideWarps)
   if (a.guard_limit && *a.guard_count > a.guard_limit) return;  // too many hits: the regional pass follows
   unsigned long long nhits = *a.hit_count;
   if (nhits > a.hit_cap) nhits = a.hit_cap;
+  // 3 .. 7 words: a warp per entry pays off while the entries fit one wave of warps (latency of the
+  // word chain: 4x shorter per step); longer lists belong to the one-thread-per-entry kernel, which
+  // is launched next to this one and applies the opposite test
+  if (W < 8 && nhits > kWideFewEntries) return;
   const unsigned long long nwarps = (unsigned long long)gridDim.x * kWideWarps;
   const int pad = 32 * W - a.m;
   const int nl = W / WL;                 // active lanes
@@ -1277,6 +1286,24 @@ cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cu
   // (refined entries: warm-up m + k, 2k + 1 end positions, and a span of at most 16 + m on repetitive text)
   const int64_t window = a.hit_exact ? 2 * (int64_t)a.m + 3 * (int64_t)a.k + 18
                                      : 2 * ((int64_t)a.m + a.k) + kHitChars + (int64_t)a.rev_lead;
+  // few refined entries of 3 .. 7 words: both kernels, the device-side count decides which one works
+  const bool few_route = a.hit_exact && W >= 3 && W < 8 && window <= kWideWindow;
+  if (few_route) {
+    static size_t trf[64] = {};
+    const size_t smem = (size_t)kWideWarps * (size_t)kWideWindow;
+    cudaError_t e = ensure_smem(verify_wide_kernel<1>, smem, trf);
+    if (e != cudaSuccess) return e;
+    ScanArgs b = a;
+    b.wide_few = 1;
+    verify_wide_kernel<1><<<148 * 8, 32 * kWideWarps, smem, stream>>>(b, rev_flags, W, kWideWindow);
+    switch (W) {
+#define SB_VCALL(WW) case WW: verify_kernel<WW><<<blocks, threads, 0, stream>>>(b, rev_flags); break;
+      SB_VCALL(3) SB_VCALL(4) SB_VCALL(6)
+#undef SB_VCALL
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
   if (W >= 8 && (window <= kWideWindow || W > 32)) {
     const unsigned wblocks = 148 * 8;
     // window staging per warp: the fixed 2304 bytes up to 32 words, the longest window beyond
