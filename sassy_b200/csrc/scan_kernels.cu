@@ -539,9 +539,10 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
 // computation, after an L2 prefetch of the whole window: thousands of resident threads
 // each touching 2-3 lines would otherwise evict each other's lines from L1 between two
 // consecutive byte loads.
-// Refined entries of patterns of 3 .. 7 words: up to this many entries the warp-per-entry kernel
-// takes them (launch_verify launches both kernels, each tests the device-side count).
-constexpr unsigned long long kWideFewEntries = 148ull * 64;  // one wave of warps
+// Refined entries of patterns of 3 .. 7 words: up to this many entries the warp-systolic kernel
+// takes them, 4 or 8 lanes per entry (launch_verify launches both kernels, each tests the
+// device-side count; beyond, one thread per entry hides its latency by itself).
+constexpr unsigned long long kWideFewEntries = 32768;
 
 template <int W>
 __global__ void __launch_bounds__(128)
@@ -736,6 +737,11 @@ cudaError_t ensure_smem(Kern kern, size_t smem, size_t (&set_dev)[64]) {
   return cudaSuccess;
 }
 
+template <int WL>
+size_t (&wide_smem_tracker())[64] {  // one per kernel: the attribute only ever grows
+  static size_t t[64] = {};
+  return t;
+}
 template <int W, bool REV, int VARIANT>
 size_t (&scan_smem_tracker())[64] {
   static size_t t[64] = {};
@@ -1093,54 +1099,69 @@ constexpr int kWideWindow = 2304;    // >= 2 (m + k) + 16 + piece length for m +
 template <int WL>
 __global__ void __launch_bounds__(32 * kWideWarps)
     verify_wide_kernel(const __grid_constant__ ScanArgs a, const uint8_t* __restrict__ rev_flags, const int W,
-                       const int32_t wcap) {
+                       const int32_t wcap, const uint32_t G) {
+  // G = lanes per entry (a power of two >= W / WL): a warp re-scans 32 / G entries side by side, so
+  // the instructions of a step are shared by that many entries (4 words: 8 entries per warp)
   extern __shared__ uint8_t win_dyn[];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* const win = win_dyn + (size_t)warp * (size_t)wcap;
+  const uint32_t gl = lane & (G - 1);  // lane inside its group
+  const uint32_t grp = lane / G, ngrp = 32u / G;
+  uint8_t* const win = win_dyn + ((size_t)warp * ngrp + grp) * (size_t)wcap;
   if (a.guard_limit && *a.guard_count > a.guard_limit) return;  // too many hits: the regional pass follows
   unsigned long long nhits = *a.hit_count;
   if (nhits > a.hit_cap) nhits = a.hit_cap;
-  // 3 .. 7 words: a warp per entry pays off while the entries fit one wave of warps (latency of the
-  // word chain: 4x shorter per step); longer lists belong to the one-thread-per-entry kernel, which
-  // is launched next to this one and applies the opposite test
-  if (W < 8 && nhits > kWideFewEntries) return;
+  // 3 .. 7 words: the lane groups pay off while the entries are few (latency of the word chain: 4x
+  // shorter per step); long lists belong to the one-thread-per-entry kernel, which is launched
+  // next to this one and applies the opposite test
+  if (a.wide_few && nhits > kWideFewEntries) return;
   const unsigned long long nwarps = (unsigned long long)gridDim.x * kWideWarps;
   const int pad = 32 * W - a.m;
-  const int nl = W / WL;                 // active lanes
-  const int w_first = (int)lane * WL;    // first word of this lane
-  for (unsigned long long h = (unsigned long long)blockIdx.x * kWideWarps + warp; h < nhits; h += nwarps) {
-    const uint64_t key = a.hit_keys[h];
-    const uint32_t qs = key_qs(key);
-    const bool rev = rev_flags[qs] != 0;
-    const uint32_t* __restrict__ eq = a.eq + (size_t)qs * a.nrows * W;
-    const int64_t n = (int64_t)a.n;
-    int64_t w0, end, emit_from;
-    if (a.hit_exact) {
-      hit_window_exact(a, key_pos(key), a.hit_span ? a.hit_span[h] : 0u, w0, end, emit_from);
-    } else {
-      const int64_t base = (int64_t)(key_pos(key) * kHitChars);
-      if (hit_in_dense_tile(a, (uint64_t)base)) continue;  // its tile is scanned whole (warp-uniform)
-      const int64_t g0 = rev ? n - kHitChars - base : base;
-      const int64_t span = (int64_t)a.m + (int64_t)a.k;
-      w0 = g0 - span;
-      if (w0 < 0) w0 = 0;
-      end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
-      if (end > n) end = n;
-      emit_from = g0 < 0 ? 0 : g0;
+  const int nl = W / WL;               // lanes of a group that hold words
+  const int w_first = (int)gl * WL;    // first word of this lane
+  const bool word_lane = (int)gl < nl;
+  const int64_t n = (int64_t)a.n;
+  for (unsigned long long base = ((unsigned long long)blockIdx.x * kWideWarps + warp) * ngrp; base < nhits;
+       base += nwarps * ngrp) {
+    // every lane of a group derives the same window; a group without an entry idles (the warp stays
+    // converged: the carries travel by shuffle)
+    const unsigned long long h = base + grp;
+    bool valid = h < nhits;
+    uint32_t qs = 0;
+    bool rev = false;
+    int64_t w0 = 0, end = 0, emit_from = 0;
+    if (valid) {
+      const uint64_t key = a.hit_keys[h];
+      qs = key_qs(key);
+      rev = rev_flags[qs] != 0;
+      if (a.hit_exact) {
+        hit_window_exact(a, key_pos(key), a.hit_span ? a.hit_span[h] : 0u, w0, end, emit_from);
+      } else {
+        const int64_t hb = (int64_t)(key_pos(key) * kHitChars);
+        if (hit_in_dense_tile(a, (uint64_t)hb)) valid = false;  // its tile is scanned whole
+        const int64_t g0 = rev ? n - kHitChars - hb : hb;
+        const int64_t span = (int64_t)a.m + (int64_t)a.k;
+        w0 = g0 - span;
+        if (w0 < 0) w0 = 0;
+        end = g0 + kHitChars + span + (rev ? (int64_t)a.rev_lead : 0);
+        if (end > n) end = n;
+        emit_from = g0 < 0 ? 0 : g0;
+      }
+      if (end <= w0) valid = false;
     }
-    if (end <= w0) continue;
-    const int32_t L = (int32_t)(end - w0);
-    // stage the window in scan order (launch_verify sizes wcap for the longest possible window)
+    const uint32_t* __restrict__ eq = a.eq + (size_t)qs * a.nrows * W;
+    const int32_t L = valid ? (int32_t)(end - w0) : 0;
+    const int32_t Lc = L < wcap ? L : wcap;  // (launch_verify sizes wcap for the longest possible window)
+    // stage the group's window in scan order
     __syncwarp();
-    for (int32_t i = (int32_t)lane; i < L && i < wcap; i += 32)
+    for (int32_t i = (int32_t)gl; i < Lc; i += (int32_t)G)
       win[i] = text_at_dir(a.text, (uint64_t)n, rev, (uint64_t)(w0 + i));
     __syncwarp();
-    const int32_t Lc = L < wcap ? L : wcap;
+    const int32_t steps = (int32_t)__reduce_max_sync(0xFFFFFFFFu, Lc > 0 ? Lc + nl - 1 : 0);
     uint32_t pv[WL], mv[WL];
 #pragma unroll
     for (int j = 0; j < WL; j++) {
       pv[j] = mv[j] = 0;
-      if ((int)lane < nl) {
+      if (word_lane) {
         const int lo = pad - 32 * (w_first + j);
         pv[j] = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
       }
@@ -1153,34 +1174,34 @@ __global__ void __launch_bounds__(32 * kWideWarps)
     auto fetch = [&](int32_t idx, uint32_t (&e)[WL]) {
 #pragma unroll
       for (int j = 0; j < WL; j++) e[j] = 0u;
-      if ((int)lane >= nl || idx < 0 || idx >= Lc) return;
+      if (!word_lane || idx < 0 || idx >= Lc) return;
       const uint32_t row = ((uint32_t)win[idx] >> a.sh0) & (a.msk0 & 0xFFu);
 #pragma unroll
       for (int j = 0; j < WL; j++) e[j] = __ldg(eq + row * W + w_first + j);
     };
     uint32_t eq_next[WL];
-    fetch(-(int32_t)lane, eq_next);
-    for (int32_t t = 0; t < Lc + nl - 1; t++) {
-      const int32_t idx = t - (int32_t)lane;
+    fetch(-(int32_t)gl, eq_next);
+    for (int32_t t = 0; t < steps; t++) {
+      const int32_t idx = t - (int32_t)gl;
       uint32_t eq_cur[WL];
 #pragma unroll
       for (int j = 0; j < WL; j++) eq_cur[j] = eq_next[j];
       fetch(idx + 1, eq_next);
       uint32_t cout = 0;
-      if ((int)lane < nl && idx >= 0 && idx < Lc) {
+      if (word_lane && idx >= 0 && idx < Lc) {
         uint32_t c = carry, ph = 0, mh = 0;
 #pragma unroll
         for (int j = 0; j < WL; j++) {
           myers_word(pv[j], mv[j], eq_cur[j], c, cout, ph, mh);
           c = cout;
         }
-        if ((int)lane == nl - 1) {
+        if ((int)gl == nl - 1) {
           score += (int)(ph >> 31) - (int)(mh >> 31);
           if (idx >= emit_rel && score <= a.k) emit_candidate(a, qs, (uint64_t)(w0 + idx) + 1, score);
         }
       }
       carry = __shfl_up_sync(0xFFFFFFFFu, cout, 1);
-      if (lane == 0) carry = 0;
+      if (gl == 0) carry = 0;
     }
   }
 }
@@ -1286,16 +1307,31 @@ cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cu
   // (refined entries: warm-up m + k, 2k + 1 end positions, and a span of at most 16 + m on repetitive text)
   const int64_t window = a.hit_exact ? 2 * (int64_t)a.m + 3 * (int64_t)a.k + 18
                                      : 2 * ((int64_t)a.m + a.k) + kHitChars + (int64_t)a.rev_lead;
+  // lanes per entry of the warp-systolic kernel: the smallest power of two that holds the words
+  uint32_t G = 32;
+  if (W <= 16) G = 16;
+  if (W <= 8) G = 8;
+  if (W <= 4) G = 4;
+  // window staging per entry: the longest window (<= 2304 bytes up to 32 words)
+  auto window_cap = [&]() -> int32_t {
+    if (W > 32) {
+      // warm-up m + k, 2k + 1 end positions, the span (refined hits: at most 16 + m; cover: the stride)
+      const int64_t longest = a.hit_exact ? (int64_t)a.m + 3 * (int64_t)a.k + 2 + std::max<int64_t>(a.max_span, a.m + 16)
+                                          : window;
+      return (int32_t)((longest + 64 + 127) / 128 * 128);
+    }
+    return (int32_t)((window + 127) / 128 * 128);
+  };
   // few refined entries of 3 .. 7 words: both kernels, the device-side count decides which one works
   const bool few_route = a.hit_exact && W >= 3 && W < 8 && window <= kWideWindow;
   if (few_route) {
-    static size_t trf[64] = {};
-    const size_t smem = (size_t)kWideWarps * (size_t)kWideWindow;
-    cudaError_t e = ensure_smem(verify_wide_kernel<1>, smem, trf);
+    const int32_t wcap = window_cap();
+    const size_t smem = (size_t)kWideWarps * (32u / G) * (size_t)wcap;
+    cudaError_t e = ensure_smem(verify_wide_kernel<1>, smem, wide_smem_tracker<1>());
     if (e != cudaSuccess) return e;
     ScanArgs b = a;
     b.wide_few = 1;
-    verify_wide_kernel<1><<<148 * 8, 32 * kWideWarps, smem, stream>>>(b, rev_flags, W, kWideWindow);
+    verify_wide_kernel<1><<<148 * 8, 32 * kWideWarps, smem, stream>>>(b, rev_flags, W, wcap, G);
     switch (W) {
 #define SB_VCALL(WW) case WW: verify_kernel<WW><<<blocks, threads, 0, stream>>>(b, rev_flags); break;
       SB_VCALL(3) SB_VCALL(4) SB_VCALL(6)
@@ -1306,27 +1342,19 @@ cudaError_t launch_verify(int W, const ScanArgs& a, const uint8_t* rev_flags, cu
   }
   if (W >= 8 && (window <= kWideWindow || W > 32)) {
     const unsigned wblocks = 148 * 8;
-    // window staging per warp: the fixed 2304 bytes up to 32 words, the longest window beyond
-    int32_t wcap = kWideWindow;
-    if (W > 32) {
-      // warm-up m + k, 2k + 1 end positions, the span (refined hits: at most 16 + m; cover: the stride)
-      const int64_t longest = a.hit_exact ? (int64_t)a.m + 3 * (int64_t)a.k + 2 + std::max<int64_t>(a.max_span, a.m + 16)
-                                          : window;
-      wcap = (int32_t)((longest + 64 + 127) / 128 * 128);
-    }
-    const size_t smem = (size_t)kWideWarps * (size_t)wcap;
+    const int32_t wcap = window_cap();
+    const size_t smem = (size_t)kWideWarps * (32u / G) * (size_t)wcap;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    static size_t tr1[64] = {}, tr2[64] = {}, tr4[64] = {};
     cudaError_t e = cudaSuccess;
     if (W <= 32) {
-      e = ensure_smem(verify_wide_kernel<1>, smem, tr1);
-      if (e == cudaSuccess) verify_wide_kernel<1><<<wblocks, 32 * kWideWarps, smem, stream>>>(a, rev_flags, W, wcap);
+      e = ensure_smem(verify_wide_kernel<1>, smem, wide_smem_tracker<1>());
+      if (e == cudaSuccess) verify_wide_kernel<1><<<wblocks, 32 * kWideWarps, smem, stream>>>(a, rev_flags, W, wcap, G);
     } else if (W == 64) {
-      e = ensure_smem(verify_wide_kernel<2>, smem, tr2);
-      if (e == cudaSuccess) verify_wide_kernel<2><<<wblocks, 32 * kWideWarps, smem, stream>>>(a, rev_flags, W, wcap);
+      e = ensure_smem(verify_wide_kernel<2>, smem, wide_smem_tracker<2>());
+      if (e == cudaSuccess) verify_wide_kernel<2><<<wblocks, 32 * kWideWarps, smem, stream>>>(a, rev_flags, W, wcap, 32u);
     } else if (W == 128) {
-      e = ensure_smem(verify_wide_kernel<4>, smem, tr4);
-      if (e == cudaSuccess) verify_wide_kernel<4><<<wblocks, 32 * kWideWarps, smem, stream>>>(a, rev_flags, W, wcap);
+      e = ensure_smem(verify_wide_kernel<4>, smem, wide_smem_tracker<4>());
+      if (e == cudaSuccess) verify_wide_kernel<4><<<wblocks, 32 * kWideWarps, smem, stream>>>(a, rev_flags, W, wcap, 32u);
     } else {
       return cudaErrorInvalidValue;
     }

@@ -268,13 +268,17 @@ def test_dna_packed_transport_pinned_ring(tma):
             st = s.stats()
             assert st["transfer_packed"] == 1 and st["transfer_bytes"] < n
             assert got == want
-        ctypes.memset(addr + 117 * chunk + 12345, ord("N"), 1)
-        t[117 * chunk + 12345] = ord("N")
-        s.set_transport("bytes")
-        want2 = s.search(p, (addr, n), 3)
-        s.set_transport("packed")
-        got2 = s.search(p, (addr, n), 3)
-        assert s.stats()["transfer_packed"] == 0 and got2 == want2
+        # a foreign byte near the end: its chunk usually crosses as plain bytes (no fall-back needed);
+        # one in the first half is met by the packer, and the whole text is sent as bytes
+        for at, must_fall_back in ((117 * chunk + 12345, False), (30 * chunk + 777, True)):
+            ctypes.memset(addr + at, ord("N"), 1)
+            s.set_transport("bytes")
+            want2 = s.search(p, (addr, n), 3)
+            s.set_transport("packed")
+            got2 = s.search(p, (addr, n), 3)
+            assert got2 == want2
+            if must_fall_back:
+                assert s.stats()["transfer_packed"] == 0
     finally:
         sassy_b200.host_free(addr)
 
