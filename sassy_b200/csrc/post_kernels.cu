@@ -200,6 +200,7 @@ __device__ __forceinline__ void trace_word(uint32_t& pv, uint32_t& mv, uint32_t 
 
 constexpr int kTraceWideWarps = 4;
 constexpr int kTraceWideWindow = 1280;  // characters of a traceback window staged in shared memory
+constexpr int kTraceWidePattern = 1024; // pattern characters staged next to it
 
 // Traceback for patterns of many words (W >= 8): ONE WARP per match.  The column store is filled
 // systolically -- word w in lane w, lane w one column behind lane w-1, carries by shuffle -- in
@@ -210,6 +211,7 @@ constexpr int kTraceWideWindow = 1280;  // characters of a traceback window stag
 template <int P, int WL>
 __global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const __grid_constant__ TraceArgs t) {
   __shared__ uint8_t win[kTraceWideWarps][kTraceWideWindow];
+  __shared__ uint8_t pat_s[kTraceWideWarps][kTraceWidePattern];
   // column stores of the block's warps when they fit (launch_trace sets smem_cols): the walk of
   // lane 0 reads two or three words per step, each a round trip to L2 otherwise
   extern __shared__ __align__(16) uint32_t trace_cols[];
@@ -248,9 +250,16 @@ __global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const 
     // stage the window's characters (scan order): the fill reads one per lane and step
     const bool staged = wlen <= (uint32_t)kTraceWideWindow;
     uint8_t* wbuf = win[threadIdx.x >> 5];
+    // the pattern too (the walk compares one pattern character per step)
+    const uint8_t* pat = t.patterns + (size_t)q * m;
+    uint8_t* pbuf = pat_s[threadIdx.x >> 5];
     __syncwarp();
     if (staged)
       for (uint32_t i = lane; i < wlen; i += 32) wbuf[i] = text_at_dir(text, n, rev, off + i);
+    if (m <= kTraceWidePattern) {
+      for (int i = (int)lane; i < m; i += 32) pbuf[i] = pat[i];
+      pat = pbuf;
+    }
     __syncwarp();
     uint32_t pv[WL], mv[WL];
 #pragma unroll
@@ -301,8 +310,8 @@ __global__ void __launch_bounds__(32 * kTraceWideWarps) trace_wide_kernel(const 
     __syncwarp();  // the column store written by all lanes is read by lane 0
     if (lane == 0) {
       TraceOut out;
-      trace_walk<P>(text, n, rev, t.patterns + (size_t)q * m, m, W, off, wlen, end, cs, t.ops + gi * t.ops_words,
-                    t.ops_words, out);
+      trace_walk<P>(text, n, rev, pat, m, W, off, wlen, end, cs, t.ops + gi * t.ops_words, t.ops_words, out,
+                    staged ? wbuf : nullptr);
       GpuMatch gm;
       gm.qs = qs;
       gm.text_start = out.text_start;
@@ -387,9 +396,9 @@ cudaError_t launch_trace(const TraceArgs& t0, cudaStream_t stream) {
   if (trace_is_wide(t)) {
     // the scratch holds trace_threads(count) column stores, the warps in flight need fewer
     const unsigned blocks = (unsigned)(trace_wide_warps(t.count) / kTraceWideWarps);
-    // column stores in shared memory when the block's four fit 40 KB (e.g. m = 100, k = 8: 7 KB each)
+    // column stores in shared memory when the block's four fit 36 KB (e.g. m = 100, k = 8: 7 KB each)
     const size_t cols_bytes = (size_t)trace_words_per_match(t.m, t.k, t.W) * sizeof(uint32_t) * kTraceWideWarps;
-    t.smem_cols = cols_bytes <= 40 * 1024 ? 1 : 0;
+    t.smem_cols = cols_bytes <= 36 * 1024 ? 1 : 0;
     const size_t dyn = t.smem_cols ? cols_bytes : 0;
 #define SB_TW(PP)                                                                                     \
   if (t.W <= 32)                                                                                      \

@@ -1133,20 +1133,24 @@ SB_HD int delta_at(uint32_t p, uint32_t mn, int bit) { return (int)((p >> bit) &
 
 // The greedy walk of src/trace.rs:314-388 over a filled column store (columns 0..wlen of the
 // window starting at `off`): '=' > 'X' > 'D' (text only) > 'I' (pattern only).
+// `win`: the window's characters in scan order when the caller has them at hand (shared memory),
+// else nullptr (they are read from the text).
 template <int P>
 SB_HD void trace_walk(const uint8_t* text, uint64_t n, bool rev, const uint8_t* pattern, int m, int W, uint64_t off,
                       uint32_t wlen, uint64_t end, const ColStore& cs, uint32_t* ops_out, uint32_t ops_words,
-                      TraceOut& out) {
+                      TraceOut& out, const uint8_t* win = nullptr) {
   const int pad = 32 * W - m;
   const int F = trace_fields(W);
   const bool wide = F == 4;
-  // The op codes are built (and reversed) in a local buffer and written out once: `ops_out` may be
-  // pinned host memory (the single-synchronisation tail writes results over PCIe), where every
-  // read-modify-write of a word would cost a round trip.
-  constexpr uint32_t kLocalOpsWords = 80;  // 1280 ops: any m + k the wide kernels accept
+  const bool unit = cs.stride == 1;  // the warp-per-match kernels: the fields of a word are 16 adjacent bytes
+  // The op codes are built in a local buffer and written out once: `ops_out` may be pinned host
+  // memory (the single-synchronisation tail writes results over PCIe), where every
+  // read-modify-write of a word would cost a round trip.  The walk produces the ops back to front
+  // (src/trace.rs:393 reverses them): they are written downwards from the top of the buffer, 16
+  // per word through a register, and moved to the front with one funnel shift per word at the end.
+  constexpr uint32_t kLocalOpsWords = 80;  // 1280 ops: any m + k up to 1024 + 255
   uint32_t local_ops[kLocalOpsWords];
   uint32_t* const ops = ops_words <= kLocalOpsWords ? local_ops : ops_out;
-  for (uint32_t w = 0; w < ops_words; w++) ops[w] = 0;
   // D[j][i] for the narrow layout: column 0 is j, row 0 is 0, else the sum of the vertical deltas
   auto cost = [&](int j, uint32_t i) -> int {
     if (j == 0) return 0;
@@ -1159,18 +1163,6 @@ SB_HD void trace_walk(const uint8_t* text, uint64_t n, bool rev, const uint8_t* 
     }
     return v;
   };
-  // neighbours of (j, i) with value g (wide layout): single-bit reads
-  //   left  D[j][i-1]   = g - h(j, i)
-  //   up    D[j-1][i]   = g - v(j, i)
-  //   diag  D[j-1][i-1] = left - v(j, i-1)
-  auto vdelta = [&](int j, uint32_t i) -> int {  // D[j][i] - D[j-1][i]
-    const int b = pad + j - 1;
-    return delta_at(cs.at((i * W + (b >> 5)) * F), cs.at((i * W + (b >> 5)) * F + 1), b & 31);
-  };
-  auto hdelta = [&](int j, uint32_t i) -> int {  // D[j][i] - D[j][i-1], i >= 1
-    const int b = pad + j - 1;
-    return delta_at(cs.at((i * W + (b >> 5)) * F + 2), cs.at((i * W + (b >> 5)) * F + 3), b & 31);
-  };
   int j = m;
   uint32_t i = wlen;
   int g = cost(j, i);
@@ -1178,15 +1170,42 @@ SB_HD void trace_walk(const uint8_t* text, uint64_t n, bool rev, const uint8_t* 
   out.failed = 0;
   uint32_t nops = 0;
   const uint32_t max_ops = ops_words * 16;
+  uint32_t cur = 0;  // the word that holds op number max_ops - 1 - nops
   while (j > 0) {
     int diag, left, up;
     if (wide) {
-      // the walk moves one column per step at most: fetch the words around the path 6 columns ahead
-      if (i >= 6) cs.prefetch(((i - 6) * W + ((pad + j - 1) >> 5)) * F);
-      up = g - vdelta(j, i);
+      // neighbours of (j, i) with value g: single-bit reads of word (pad + j - 1) / 32
+      //   up    D[j-1][i]   = g - v(j, i)
+      //   left  D[j][i-1]   = g - h(j, i)
+      //   diag  D[j-1][i-1] = left - v(j, i-1)
+      const int b = pad + j - 1;
+      const int bit = b & 31;
+      const uint32_t slot = (i * (uint32_t)W + (uint32_t)(b >> 5)) * 4u;
+      uint32_t pv_i, mv_i, ph_i = 0, mh_i = 0, pv_p = 0, mv_p = 0;
+#if defined(__CUDA_ARCH__)
+      if (unit) {
+        // the walk moves one column per step at most: fetch the words around the path 6 columns ahead
+        if (i >= 6) cs.prefetch(slot - 6u * (uint32_t)W * 4u);
+        const uint4 f = *reinterpret_cast<const uint4*>(cs.base + slot);
+        pv_i = f.x, mv_i = f.y, ph_i = f.z, mh_i = f.w;
+        if (i > 0) {
+          const uint2 f2 = *reinterpret_cast<const uint2*>(cs.base + (slot - (uint32_t)W * 4u));
+          pv_p = f2.x, mv_p = f2.y;
+        }
+      } else
+#endif
+      {
+        (void)unit;
+        pv_i = cs.at(slot), mv_i = cs.at(slot + 1);
+        if (i > 0) {
+          ph_i = cs.at(slot + 2), mh_i = cs.at(slot + 3);
+          pv_p = cs.at(slot - (uint32_t)W * 4u), mv_p = cs.at(slot - (uint32_t)W * 4u + 1);
+        }
+      }
+      up = g - delta_at(pv_i, mv_i, bit);
       if (i > 0) {
-        left = g - hdelta(j, i);
-        diag = left - vdelta(j, i - 1);
+        left = g - delta_at(ph_i, mh_i, bit);
+        diag = left - delta_at(pv_p, mv_p, bit);
       } else {
         left = diag = 0;
       }
@@ -1196,7 +1215,8 @@ SB_HD void trace_walk(const uint8_t* text, uint64_t n, bool rev, const uint8_t* 
       diag = i > 0 ? cost(j - 1, i - 1) : 0;
     }
     uint32_t op;
-    if (i > 0 && diag == g && trace_match<P>(pattern[j - 1], text_at_dir(text, n, rev, off + i - 1))) {
+    const uint8_t tc = i > 0 ? (win ? win[i - 1] : text_at_dir(text, n, rev, off + i - 1)) : (uint8_t)0;
+    if (i > 0 && diag == g && trace_match<P>(pattern[j - 1], tc)) {
       op = kOpEq;
       j--, i--;
     } else {
@@ -1215,22 +1235,34 @@ SB_HD void trace_walk(const uint8_t* text, uint64_t n, bool rev, const uint8_t* 
         break;
       }
     }
-    if (nops < max_ops) ops[nops >> 4] |= op << ((nops & 15) * 2);
+    if (nops >= max_ops) {  // more ops than the record holds: cannot happen for cost <= k
+      out.failed = 1;
+      break;
+    }
+    const uint32_t pos = max_ops - 1 - nops;
+    cur |= op << ((pos & 15u) * 2);
+    if ((pos & 15u) == 0) {
+      ops[pos >> 4] = cur;
+      cur = 0;
+    }
     nops++;
   }
-  if (nops > max_ops) {
-    out.failed = 1;
-    nops = max_ops;
+  // ops[first_pos ..] hold the ops in pattern direction: move them to position 0
+  const uint32_t first_pos = max_ops - nops;
+  if (first_pos & 15u) ops[first_pos >> 4] = cur;  // the partly filled word
+  const uint32_t w0 = first_pos >> 4, sh = (first_pos & 15u) * 2;
+  const uint32_t nwords = (nops + 15) / 16;
+  for (uint32_t w = 0; w < ops_words; w++) {
+    uint32_t v = 0;
+    if (w < nwords) {
+      const uint32_t lo = ops[w0 + w];
+      const uint32_t hi = (w0 + w + 1 < ops_words) ? ops[w0 + w + 1] : 0u;
+      v = sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+      const uint32_t valid = nops - w * 16;  // ops in this word
+      if (valid < 16) v &= (1u << (2 * valid)) - 1u;
+    }
+    ops_out[w] = v;
   }
-  // reverse into pattern direction (src/trace.rs:393)
-  for (uint32_t a = 0, b = nops; a + 1 < b; a++, b--) {
-    const uint32_t oa = (ops[a >> 4] >> ((a & 15) * 2)) & 3u;
-    const uint32_t ob = (ops[(b - 1) >> 4] >> (((b - 1) & 15) * 2)) & 3u;
-    ops[a >> 4] = (ops[a >> 4] & ~(3u << ((a & 15) * 2))) | (ob << ((a & 15) * 2));
-    ops[(b - 1) >> 4] = (ops[(b - 1) >> 4] & ~(3u << (((b - 1) & 15) * 2))) | (oa << (((b - 1) & 15) * 2));
-  }
-  if (ops != ops_out)
-    for (uint32_t w = 0; w < ops_words; w++) ops_out[w] = ops[w];
   out.text_start = off + i;
   out.text_end = end;
   out.nops = nops;
