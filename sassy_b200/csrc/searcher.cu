@@ -145,6 +145,65 @@ std::vector<Match> Searcher::search(const uint8_t* pattern, size_t m, const uint
   return search_with_pam(pattern, m, text, n, k, all_minima, nullptr, 0);
 }
 
+// As convert_v1 (one pattern, one text) + the C ABI's record layout, in one pass.
+void Searcher::search_flat(const uint8_t* pattern, size_t m, const DeviceText& text, size_t k, bool all_minima,
+                           const uint8_t* pam, size_t pam_len, FlatMatches& out) {
+  raw_only_ = true;
+  try {
+    search_with_pam(pattern, m, text, k, all_minima, pam, pam_len);
+  } catch (...) {
+    raw_only_ = false;
+    throw;
+  }
+  raw_only_ = false;
+  const MatchSet& ms = ms_;
+  const size_t nq = rc_ ? 2 : 1;
+  const uint64_t n = text.n;
+  const size_t cnt = ms.m.size();
+  out.m.resize(cnt);
+  size_t total = 0;
+  for (size_t i = 0; i < cnt; i++) {
+    if (ms.m[i].failed & 1u) throw std::runtime_error("Trace failed (text contains bytes outside the profile's alphabet?)");
+    total += without_trace_ ? 0 : ms.m[i].nops;
+  }
+  out.ops.resize(total);
+  char* ops = total ? &out.ops[0] : nullptr;
+  size_t off = 0;
+  for (size_t i = 0; i < cnt; i++) {
+    const GpuMatch& g = ms.m[i];
+    sassy_gpu_Match& o = out.m[i];
+    memset(&o, 0, sizeof o);
+    const size_t q = g.qs % nq;
+    o.cost = g.cost;
+    o.pattern_start = without_trace_ ? ~0ull : (uint64_t)((g.failed >> 8) & 0xFFFu);
+    o.pattern_end = m - (uint64_t)(g.failed >> 20);
+    if (q == 0) {
+      o.strand = (uint8_t)kFwd;
+      o.text_start = g.text_start;
+      o.text_end = g.text_end;
+    } else {
+      o.strand = (uint8_t)kRc;
+      o.text_start = n - g.text_end;
+      o.text_end = without_trace_ ? ~0ull : n - g.text_start;
+    }
+    o.ops_off = off;
+    if (!without_trace_) {
+      o.ops_len = g.nops;
+      const uint32_t* w = &ms.ops[i * ms.ops_words];
+      for (uint32_t a = 0; a < g.nops; a++) ops[off + a] = kOpChars[(w[a >> 4] >> ((a & 15) * 2)) & 3u];
+      off += g.nops;
+    }
+  }
+}
+
+void Searcher::search_flat(const uint8_t* pattern, size_t m, const uint8_t* text, size_t n, size_t k, bool all_minima,
+                           const uint8_t* pam, size_t pam_len, FlatMatches& out) {
+  if (m == 0) throw std::invalid_argument("empty pattern");
+  validate_pattern(pattern, m);
+  DeviceText* t = engine_->stage_text(text, n);
+  search_flat(pattern, m, *t, k, all_minima, pam, pam_len, out);
+}
+
 std::vector<Match> Searcher::search_with_pam(const uint8_t* pattern, size_t m, const uint8_t* text, size_t n,
                                              size_t k, bool all_minima, const uint8_t* pam, size_t pam_len) {
   if (m == 0) throw std::invalid_argument("empty pattern");
@@ -629,6 +688,13 @@ sassy_gpu_Result* to_result(const std::vector<sb::Match>& v) {
   return r;
 }
 
+sassy_gpu_Result* flat_result(sb::Searcher::FlatMatches& f) {
+  sassy_gpu_Result* r = new sassy_gpu_Result;
+  r->m.swap(f.m);
+  r->ops.swap(f.ops);
+  return r;
+}
+
 // v2 records -> flat C result in one pass (no per-match heap allocation): same mapping as
 // Searcher::convert_v2.
 sassy_gpu_Result* to_result_v2(const sb::MatchSet& ms, size_t n_patterns, int m) {
@@ -864,7 +930,9 @@ sassy_gpu_Result* sassy_gpu_search(sassy_SearcherType* searcher, const uint8_t* 
                                    const uint8_t* text, size_t text_len, size_t k, int all) {
   return guarded([&]() -> sassy_gpu_Result* {
     if (!searcher || !pattern || (!text && text_len)) throw std::invalid_argument("null pointer");
-    return to_result(searcher->s.search(pattern, pattern_len, text, text_len, k, all != 0));
+    sb::Searcher::FlatMatches f;
+    searcher->s.search_flat(pattern, pattern_len, text, text_len, k, all != 0, nullptr, 0, f);
+    return flat_result(f);
   });
 }
 
@@ -872,7 +940,9 @@ sassy_gpu_Result* sassy_gpu_search_text(sassy_SearcherType* searcher, const uint
                                         const sassy_gpu_Text* text, size_t k, int all) {
   return guarded([&]() -> sassy_gpu_Result* {
     if (!searcher || !pattern || !text) throw std::invalid_argument("null pointer");
-    return to_result(searcher->s.search(pattern, pattern_len, *text->t, k, all != 0));
+    sb::Searcher::FlatMatches f;
+    searcher->s.search_flat(pattern, pattern_len, *text->t, k, all != 0, nullptr, 0, f);
+    return flat_result(f);
   });
 }
 
@@ -905,7 +975,9 @@ sassy_gpu_Result* sassy_gpu_search_pam(sassy_SearcherType* searcher, const uint8
                                        size_t pam_len) {
   return guarded([&]() -> sassy_gpu_Result* {
     if (!searcher || !pattern || (!text && text_len) || (!pam && pam_len)) throw std::invalid_argument("null pointer");
-    return to_result(searcher->s.search_with_pam(pattern, pattern_len, text, text_len, k, all != 0, pam, pam_len));
+    sb::Searcher::FlatMatches f;
+    searcher->s.search_flat(pattern, pattern_len, text, text_len, k, all != 0, pam, pam_len, f);
+    return flat_result(f);
   });
 }
 
@@ -914,7 +986,9 @@ sassy_gpu_Result* sassy_gpu_search_pam_text(sassy_SearcherType* searcher, const 
                                             size_t pam_len) {
   return guarded([&]() -> sassy_gpu_Result* {
     if (!searcher || !pattern || !text || (!pam && pam_len)) throw std::invalid_argument("null pointer");
-    return to_result(searcher->s.search_with_pam(pattern, pattern_len, *text->t, k, all != 0, pam, pam_len));
+    sb::Searcher::FlatMatches f;
+    searcher->s.search_flat(pattern, pattern_len, *text->t, k, all != 0, pam, pam_len, f);
+    return flat_result(f);
   });
 }
 

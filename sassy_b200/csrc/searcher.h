@@ -85,6 +85,16 @@ class Searcher {
                                      bool all_minima, const uint8_t* pam, size_t pam_len);
   std::vector<Match> search_with_pam(const uint8_t* pattern, size_t m, const uint8_t* text, size_t n, size_t k,
                                      bool all_minima, const uint8_t* pam, size_t pam_len);
+  // The same searches with the result written as flat C records (one pass over the device records,
+  // no per-match allocation: result sets of 10^5..10^6 matches are bound by this conversion).
+  struct FlatMatches {
+    std::vector<sassy_gpu_Match> m;
+    std::string ops;
+  };
+  void search_flat(const uint8_t* pattern, size_t m, const DeviceText& text, size_t k, bool all_minima,
+                   const uint8_t* pam, size_t pam_len, FlatMatches& out);
+  void search_flat(const uint8_t* pattern, size_t m, const uint8_t* text, size_t n, size_t k, bool all_minima,
+                   const uint8_t* pam, size_t pam_len, FlatMatches& out);
 
   // search_patterns (src/search.rs:648-683): equal-length patterns against one text (v1
   // semantics per pattern, pattern_idx set).
@@ -115,10 +125,6 @@ class Searcher {
   // collective + sassy_gpu_merge_slabs.
   // The merged result is written as flat C records (`merged`; no per-match allocation: every rank
   // merges all ranks' records every step); the returned vector only holds the fallback's matches.
-  struct FlatMatches {
-    std::vector<sassy_gpu_Match> m;
-    std::string ops;
-  };
   std::vector<Match> search_sharded_gathered(PeerGather& pg, const uint8_t* pattern, size_t m,
                                              const DeviceText& window, size_t k, bool all_minima,
                                              const SlabInfo* slabs, size_t n_slabs, uint64_t n_global,
