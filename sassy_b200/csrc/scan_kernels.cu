@@ -529,9 +529,9 @@ __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
   flush_hits(a, hq, lane);
 }
 
-template <int W>
+template <int W, bool SM>
 __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __restrict__ rev_flags,
-                                           unsigned long long i);
+                                           unsigned long long i, uint32_t tab_saddr);
 
 // One thread per prefilter hit: exact recurrences over the hit's neighbourhood
 // (same window and emission rule as verify_hit in scan_core.cuh, which the host emulator
@@ -543,6 +543,7 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
 // takes them, 4 or 8 lanes per entry (launch_verify launches both kernels, each tests the
 // device-side count; beyond, one thread per entry hides its latency by itself).
 constexpr unsigned long long kWideFewEntries = 32768;
+constexpr uint32_t kVerifyEqWords = 2048;  // shared-memory copy of the equality tables in verify_kernel
 
 template <int W>
 __global__ void __launch_bounds__(128)
@@ -552,18 +553,41 @@ __global__ void __launch_bounds__(128)
   if (nhits > a.hit_cap) nhits = a.hit_cap;
   if (a.wide_few && nhits <= kWideFewEntries) return;  // verify_wide_kernel has them
   const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+  // the equality tables of all query slots in shared memory when they fit (one pattern: 4 .. 256 words)
+  __shared__ uint32_t eq_s[kVerifyEqWords];
+  const uint32_t tab_words = a.nq * a.nrows * (uint32_t)W;
+  if (a.nq <= kVerifyEqWords && tab_words <= kVerifyEqWords) {
+    if ((unsigned long long)blockIdx.x * blockDim.x >= nhits) return;  // (block-uniform)
+    for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) eq_s[i] = a.eq[i];
+    __syncthreads();
+    const uint32_t saddr = smem_u32(eq_s);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nhits; i += nthreads)
+      verify_one<W, true>(a, rev_flags, i, saddr);
+    return;
+  }
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nhits; i += nthreads)
-    verify_one<W>(a, rev_flags, i);
+    verify_one<W, false>(a, rev_flags, i, 0u);
 }
 
 // Exact recurrences over scan-direction positions [w0, end) of one text, emitting every end
 // position > emit_from with score <= k under query slot `qs`.  `text` must be 16-byte aligned
 // and padded to a multiple of 16 bytes.
-template <int W>
+// SM: the query's equality table lies in shared memory (`tab`; PRMT + IMAD + LDS per look-up instead of
+// a 64-bit address computation + LDG), else it is read through `eq`.
+template <int W, bool SM = false>
 __device__ __forceinline__ void scan_window(const ScanArgs& a, const uint32_t* __restrict__ eq, uint32_t qs, bool rev,
                                             const uint8_t* __restrict__ text, int64_t n, int64_t w0, int64_t end,
-                                            int64_t emit_from) {
+                                            int64_t emit_from, EqTab tab = EqTab()) {
   if (end <= w0) return;
+  auto step = [&](Lane<W>& st, uint32_t pre, int b) {
+    if (SM) {
+      uint32_t e[W];
+      load_eq<W>(e, tab, pre, b);
+      myers_step<W>(st, e);
+    } else {
+      myers_step<W>(st, eq + ((pre >> (8 * b)) & 0xFFu) * W);
+    }
+  };
   // forward byte range [lo, hi) of the window and its aligned 16-byte chunks
   const int64_t lo = rev ? n - end : w0, hi = rev ? n - w0 : end;
   const int64_t c_lo = lo >> 4, c_hi = (hi + 15) >> 4;  // chunk indices [c_lo, c_hi)
@@ -599,20 +623,20 @@ __device__ __forceinline__ void scan_window(const ScanArgs& a, const uint32_t* _
       const bool inside = wlen >= 4u && (uint32_t)srel0 <= wlen - 4u;
       if (inside && srel0 + 4 <= emit_rel) {  // warm-up: no position of this word can be reported
 #pragma unroll
-        for (int b = 0; b < 4; b++) myers_step<W>(s, eq + ((pre >> (8 * b)) & 0xFFu) * W);
+        for (int b = 0; b < 4; b++) step(s, pre, b);
       } else if (inside && srel0 >= emit_rel) {
         // emit zone: the score moves by at most 1 per character, so a position of this word can
         // only be <= k if score_before + score_after <= 2k + 4 (as fast_group in scan_core.cuh)
         if (prev < 0) prev = lane_score<W>(s);
         const Lane<W> saved = s;
 #pragma unroll
-        for (int b = 0; b < 4; b++) myers_step<W>(s, eq + ((pre >> (8 * b)) & 0xFFu) * W);
+        for (int b = 0; b < 4; b++) step(s, pre, b);
         const int score = lane_score<W>(s);
         if (prev + score <= 2 * a.k + 4) {
           s = saved;
 #pragma unroll 1
           for (int b = 0; b < 4; b++) {
-            myers_step<W>(s, eq + ((pre >> (8 * b)) & 0xFFu) * W);
+            step(s, pre, b);
             const int sc = lane_score<W>(s);
             if (sc <= a.k) emit_candidate(a, qs, (uint64_t)(w0 + srel0 + b) + 1, sc);
           }
@@ -623,7 +647,7 @@ __device__ __forceinline__ void scan_window(const ScanArgs& a, const uint32_t* _
         for (int b = 0; b < 4; b++) {
           const int32_t srel = srel0 + b;
           if ((uint32_t)srel < wlen) {
-            myers_step<W>(s, eq + ((pre >> (8 * b)) & 0xFFu) * W);
+            step(s, pre, b);
             if (srel >= emit_rel) {
               const int sc = lane_score<W>(s);
               if (sc <= a.k) emit_candidate(a, qs, (uint64_t)(w0 + srel) + 1, sc);
@@ -638,9 +662,9 @@ __device__ __forceinline__ void scan_window(const ScanArgs& a, const uint32_t* _
   }
 }
 
-template <int W>
+template <int W, bool SM>
 __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __restrict__ rev_flags,
-                                           unsigned long long i) {
+                                           unsigned long long i, uint32_t tab_saddr) {
   const uint64_t key = a.hit_keys[i];
   const uint32_t qs = key_qs(key);
   const bool rev = rev_flags[qs] != 0;
@@ -661,7 +685,11 @@ __device__ __forceinline__ void verify_one(const ScanArgs& a, const uint8_t* __r
     if (end > n) end = n;
     emit_from = g0 < 0 ? 0 : g0;
   }
-  scan_window<W>(a, eq, qs, rev, a.text, n, w0, end, emit_from);
+  EqTab tab;
+  tab.p = nullptr;
+  tab.rowbytes = (uint32_t)W * 4u;
+  tab.saddr = tab_saddr + qs * a.nrows * (uint32_t)W * 4u;
+  scan_window<W, SM>(a, eq, qs, rev, a.text, n, w0, end, emit_from, tab);
 }
 
 // search_texts / search_many: many short texts, one thread per (text, query) pair runs the
