@@ -762,6 +762,12 @@ void emu_dna_unpack(const uint8_t* packed, size_t n, uint8_t* out) {
   }
 }
 
+// Many texts scanned as one concatenation (Engine::search_texts): candidate position -> (text, position in the text).
+int emu_concat_locate(uint64_t pos, int rev, uint64_t total, const uint64_t* offs, const uint64_t* lens, uint32_t ntexts,
+                      uint32_t* ti, uint64_t* local) {
+  return concat_locate(pos, rev != 0, total, offs, lens, ntexts, *ti, *local) ? 1 : 0;
+}
+
 size_t emu_len(const EmuResult* r) { return r->m.size(); }
 const GpuMatch* emu_matches(const EmuResult* r) { return r->m.data(); }
 const uint32_t* emu_ops(const EmuResult* r) { return r->ops.data(); }

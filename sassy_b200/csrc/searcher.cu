@@ -1113,7 +1113,6 @@ sassy_gpu_Result* sassy_gpu_search_text_sharded(sassy_SearcherType* searcher, sa
     std::vector<sb::SlabInfo> info(n_slabs);
     for (size_t i = 0; i < n_slabs; i++) info[i] = sb::SlabInfo{slabs[i].window_off, slabs[i].own_lo, slabs[i].own_hi};
     bool ok = false;
-    const bool primed = !gather->g.pipelined() || gather->g.has_result() || false;
     const double t_call = sb::HostTimers::on() ? sb::HostTimers::now_us() : 0.0;
     struct CallTimer {
       double t0;
@@ -1124,7 +1123,6 @@ sassy_gpu_Result* sassy_gpu_search_text_sharded(sassy_SearcherType* searcher, sa
     sb::Searcher::FlatMatches merged;
     auto v = searcher->s.search_sharded_gathered(gather->g, pattern, pattern_len, *window->t, k, all != 0, info.data(),
                                                  n_slabs, n_global, &ok, merged);
-    (void)primed;
     *complete = ok ? 1 : 0;
     if (gather->g.pipelined() && !gather->g.has_result()) *complete = 2;  // pipeline priming: no result yet
     if (!ok) return to_result(v);  // this rank's unmerged matches for the caller's own collective

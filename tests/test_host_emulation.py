@@ -441,3 +441,44 @@ def test_dna_transport_encoding():
                 for level in range(best + 1):
                     dst = ctypes.create_string_buffer(size + 64)
                     assert lib.emu_dna_pack(level, t2, n, dst) == 0, (n, level, bad, pos)
+
+
+def test_concat_locate():
+    """Many texts scanned as one concatenated text (Engine::search_texts): a candidate's end position
+    in the concatenation maps to (text, end position in the text) in scan direction, positions in the
+    padding between texts map to nothing; empty texts never own a position."""
+    import ctypes
+    from tests.emu_backend import _lib
+    lib = _lib()
+    lib.emu_concat_locate.restype = ctypes.c_int
+    lib.emu_concat_locate.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64),
+                                      ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint32,
+                                      ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint64)]
+    rng = random.Random(91)
+    for _ in range(30):
+        nt = rng.randrange(1, 40)
+        lens = [rng.choice([0, 0, 1, 5, 15, 16, 17, 100]) for _ in range(nt)]
+        offs, total = [], 0
+        for ln in lens:  # as Engine::search_texts: every text starts on a 16-byte boundary
+            offs.append(total)
+            total += (ln + 15) & ~15
+        if total == 0:
+            continue
+        owner = [None] * total  # forward index -> (text, index in the text)
+        for t, (o, ln) in enumerate(zip(offs, lens)):
+            for i in range(ln):
+                owner[o + i] = (t, i)
+        c_offs = (ctypes.c_uint64 * nt)(*offs)
+        c_lens = (ctypes.c_uint64 * nt)(*lens)
+        ti, local = ctypes.c_uint32(0), ctypes.c_uint64(0)
+        for pos in range(0, total + 2):
+            for rev in (0, 1):
+                ok = lib.emu_concat_locate(pos, rev, total, c_offs, c_lens, nt, ctypes.byref(ti), ctypes.byref(local))
+                g = (total - pos) if rev else (pos - 1)  # forward index of the last character consumed
+                want = owner[g] if 1 <= pos <= total else None
+                if want is None:
+                    assert ok == 0, (pos, rev)
+                else:
+                    t, i = want
+                    assert ok == 1 and ti.value == t, (pos, rev, offs, lens)
+                    assert local.value == ((lens[t] - i) if rev else (i + 1)), (pos, rev)
