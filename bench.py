@@ -276,6 +276,38 @@ class ClockSampler:
         self.sm.clear(), self.power.clear(), self.reasons.clear()
         self._last = 0.0
 
+    # Timed regions are sampled from a background thread (an NVML query can take a good part of a
+    # millisecond: inside the step loop it would be charged to the steps it lands in).  The thread
+    # only records while a timed region is open.
+    def start_thread(self, period=0.005):
+        import threading
+        if self.h is None or getattr(self, "_thread", None) is not None:
+            return
+        self._open = False
+        self._stop = False
+
+        def loop():
+            while not self._stop:
+                if self._open:
+                    self.sample(min_gap=0.0)
+                time.sleep(period)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
+
+    def region(self, is_open: bool):
+        if getattr(self, "_thread", None) is not None:
+            self._open = is_open
+
+    def threaded(self):
+        return getattr(self, "_thread", None) is not None
+
+    def stop_thread(self):
+        if getattr(self, "_thread", None) is not None:
+            self._stop = True
+            self._thread.join(timeout=1.0)
+            self._thread = None
+
     def result(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "source": "nvml"}
         if self.sm:
@@ -520,6 +552,7 @@ def main():
     if sampler is not None:  # the first NVML queries of a process can take long: not inside a timed region
         sampler.sample()
         sampler.reset()
+        sampler.start_thread()
 
     def barrier():
         if world > 1:
@@ -598,11 +631,13 @@ def main():
             ms = fn()
         barrier()
         scan_ms, total_ms, walls, launches = [], [], [], 0
+        if sampler is not None:
+            sampler.region(True)
         t0 = time.perf_counter()
         tp = t0
         for it in range(steps):
             ms = fn()
-            if sampler is not None:
+            if sampler is not None and not sampler.threaded():
                 sampler.sample()
             tn = time.perf_counter()
             walls.append((tn - tp) * 1e3)
@@ -614,7 +649,10 @@ def main():
         if finish is not None:
             ms = finish()
         barrier()
-        el = max_over_ranks(time.perf_counter() - t0)
+        t_end = time.perf_counter()
+        if sampler is not None:
+            sampler.region(False)
+        el = max_over_ranks(t_end - t0)
         launches_total[0] += launches
         return {"el": el, "matches": ms, "scan_ms": scan_ms, "total_ms": total_ms, "walls": sorted(walls),
                 "launches": launches, "stats": s.stats()}
@@ -901,6 +939,8 @@ def main():
     if world == 1 and args.workload == "c2" and args.sub in ("auto", "np") or "np" in args.sub.split(","):
         if rank == 0 and need_text0:
             sub_recs["nanopore"] = run_nanopore()
+    if sampler is not None:
+        sampler.stop_thread()
     clocks = sampler.result() if rank == 0 else None
 
     if rank != 0:
