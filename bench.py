@@ -252,8 +252,10 @@ class ClockSampler:
             self.h = None
             self.err = str(e)
 
-    def sample(self, min_gap=0.01):
-        # NVML queries cost up to a millisecond: at most one sample per 10 ms of wall time
+    def sample(self, min_gap=0.05):
+        # One sample (three NVML queries) costs the calling thread ~0.3 ms: at most one per 50 ms of wall
+        # time, i.e. the first step of every timed region and then <= 0.6 % of a long one.  (Sampling from
+        # a background thread was tried: the hand-overs of the interpreter lock cost every step ~40 us.)
         now = time.perf_counter()
         if self.h is None or now - getattr(self, "_last", 0.0) < min_gap:
             return
@@ -275,38 +277,6 @@ class ClockSampler:
     def reset(self):
         self.sm.clear(), self.power.clear(), self.reasons.clear()
         self._last = 0.0
-
-    # Timed regions are sampled from a background thread (an NVML query can take a good part of a
-    # millisecond: inside the step loop it would be charged to the steps it lands in).  The thread
-    # only records while a timed region is open.
-    def start_thread(self, period=0.005):
-        import threading
-        if self.h is None or getattr(self, "_thread", None) is not None:
-            return
-        self._open = False
-        self._stop = False
-
-        def loop():
-            while not self._stop:
-                if self._open:
-                    self.sample(min_gap=0.0)
-                time.sleep(period)
-
-        self._thread = threading.Thread(target=loop, daemon=True)
-        self._thread.start()
-
-    def region(self, is_open: bool):
-        if getattr(self, "_thread", None) is not None:
-            self._open = is_open
-
-    def threaded(self):
-        return getattr(self, "_thread", None) is not None
-
-    def stop_thread(self):
-        if getattr(self, "_thread", None) is not None:
-            self._stop = True
-            self._thread.join(timeout=1.0)
-            self._thread = None
 
     def result(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "source": "nvml"}
@@ -552,7 +522,6 @@ def main():
     if sampler is not None:  # the first NVML queries of a process can take long: not inside a timed region
         sampler.sample()
         sampler.reset()
-        sampler.start_thread()
 
     def barrier():
         if world > 1:
@@ -631,13 +600,11 @@ def main():
             ms = fn()
         barrier()
         scan_ms, total_ms, walls, launches = [], [], [], 0
-        if sampler is not None:
-            sampler.region(True)
         t0 = time.perf_counter()
         tp = t0
         for it in range(steps):
             ms = fn()
-            if sampler is not None and not sampler.threaded():
+            if sampler is not None:
                 sampler.sample()
             tn = time.perf_counter()
             walls.append((tn - tp) * 1e3)
@@ -649,10 +616,7 @@ def main():
         if finish is not None:
             ms = finish()
         barrier()
-        t_end = time.perf_counter()
-        if sampler is not None:
-            sampler.region(False)
-        el = max_over_ranks(t_end - t0)
+        el = max_over_ranks(time.perf_counter() - t0)
         launches_total[0] += launches
         return {"el": el, "matches": ms, "scan_ms": scan_ms, "total_ms": total_ms, "walls": sorted(walls),
                 "launches": launches, "stats": s.stats()}
@@ -939,8 +903,6 @@ def main():
     if world == 1 and args.workload == "c2" and args.sub in ("auto", "np") or "np" in args.sub.split(","):
         if rank == 0 and need_text0:
             sub_recs["nanopore"] = run_nanopore()
-    if sampler is not None:
-        sampler.stop_thread()
     clocks = sampler.result() if rank == 0 else None
 
     if rank != 0:
