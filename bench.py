@@ -253,9 +253,10 @@ class ClockSampler:
             self.err = str(e)
 
     def sample(self, min_gap=0.05):
-        # One sample (three NVML queries) costs the calling thread ~0.3 ms: at most one per 50 ms of wall
-        # time, i.e. the first step of every timed region and then <= 0.6 % of a long one.  (Sampling from
-        # a background thread was tried: the hand-overs of the interpreter lock cost every step ~40 us.)
+        # One sample (three NVML queries) costs the calling thread ~40 us on an idle host and up to a
+        # millisecond while every core is packing a text (e2e leg): at most one per 50 ms of wall time,
+        # i.e. the first step of every timed region and then <= 2 % of a long one.  (Sampling from a
+        # background thread was tried: the hand-overs of the interpreter lock cost EVERY step ~40 us.)
         now = time.perf_counter()
         if self.h is None or now - getattr(self, "_last", 0.0) < min_gap:
             return
