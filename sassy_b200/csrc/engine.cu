@@ -280,8 +280,15 @@ void Engine::send_text(uint8_t* dst, size_t dst_alloc, const uint8_t* host, uint
     uint64_t plain_bytes = 0;
     bool clean = true, expanded = false;
     auto poll = [&]() {
-      while (completed < issued && cudaEventQuery(copy_ev_[completed % kCopyEvents]) == cudaSuccess)
+      while (completed < issued) {
+        const cudaError_t q = cudaEventQuery(copy_ev_[completed % kCopyEvents]);
+        if (q == cudaErrorNotReady) {
+          cudaGetLastError();  // "not ready" is an answer, not an error to be found by a later check
+          break;
+        }
+        SB_CUDA(q);
         bytes_completed += copy_len[completed++ % kCopyEvents];
+      }
       while (released < sent_chunks && seq[released % slots] < completed) released++;
       if (ring) pool_->release(released);
     };
