@@ -103,7 +103,8 @@ struct HostTimerState {
     if (!on) return;
     static const char* names[HostTimers::kCount] = {"entry -> parameters uploaded", "launches + wait for the GPU",
                                                     "after the last synchronisation", "merge of gathered records",
-                                                    "whole C call (sharded search)"};
+                                                    "whole C call (sharded search)", "many texts: staging (host copies)",
+                                                    "many texts: upload + kernels + tail", "many texts: records -> matches"};
     for (int i = 0; i < HostTimers::kCount; i++)
       if (n[i]) fprintf(stderr, "[sassy_b200 host timing] %-34s %9.1f us avg over %llu calls\n", names[i], acc[i] / n[i], n[i]);
   }
@@ -1302,6 +1303,7 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
   if (nslots >= (1ull << (64 - kPosBits))) throw CudaError("too many (text, query) pairs in one search");
 
   // ---- pack and upload the texts -------------------------------------------------------------
+  const double t_stage0 = HostTimers::on() ? HostTimers::now_us() : 0.0;
   std::vector<uint64_t> meta(2 * ntexts);
   uint64_t total = 0;
   for (size_t i = 0; i < ntexts; i++) {
@@ -1354,6 +1356,8 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
   }
   memcpy(packed + meta_off, meta.data(), meta.size() * sizeof(uint64_t));
   d_texts_.ensure(packed_bytes);
+  const double t_stage1 = HostTimers::on() ? HostTimers::now_us() : 0.0;
+  if (HostTimers::on()) HostTimers::add(HostTimers::kTextsStage, t_stage1 - t_stage0);
   SB_CUDA(cudaEventRecord(ev_[0], stream_));
   SB_CUDA(cudaMemcpyAsync(d_texts_.p, packed, packed_bytes, cudaMemcpyHostToDevice, stream_));
   const uint8_t* d_base = d_texts_.as<uint8_t>();
@@ -1511,6 +1515,7 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
   stats_.total_ms = total_ms;
   stats_.matches = nsel;
   stats_.rows = (uint32_t)ntexts;
+  if (HostTimers::on()) HostTimers::add(HostTimers::kTextsGpu, HostTimers::now_us() - t_stage1);
 }
 
 }  // namespace sb

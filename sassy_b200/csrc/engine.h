@@ -26,7 +26,7 @@ struct CudaError : std::runtime_error {
 // Host-side phase timers of the search entry points (SASSY_B200_HOST_TIMING=1 prints the averages
 // to stderr at exit; profiling aid, not part of the product path's behaviour).
 struct HostTimers {
-  enum { kPre, kGpuWait, kPost, kMerge, kSearchCall, kCount };
+  enum { kPre, kGpuWait, kPost, kMerge, kSearchCall, kTextsStage, kTextsGpu, kTextsConvert, kCount };
   static bool on();
   static void add(int which, double us);
   static double now_us();

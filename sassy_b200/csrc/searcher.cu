@@ -256,9 +256,11 @@ std::vector<Match> Searcher::search_group(const uint8_t* const* patterns, size_t
   for (size_t first = 0; first < sp.size(); first += max_texts) {
     const size_t cnt = std::min(max_texts, sp.size() - first);
     engine_->search_texts(sp.data() + first, sl.data() + first, cnt, qs, (int)m, kk, o, ms_);
+    const double t0 = HostTimers::on() ? HostTimers::now_us() : 0.0;
     std::vector<Match> part = convert_v1(ms_, n_pat, m, [&](size_t ti) { return sl[first + ti]; });
     for (auto& mm : part) mm.text_idx = sidx[first + mm.text_idx];
     out.insert(out.end(), std::make_move_iterator(part.begin()), std::make_move_iterator(part.end()));
+    if (HostTimers::on()) HostTimers::add(HostTimers::kTextsConvert, HostTimers::now_us() - t0);
   }
   return out;
 }
