@@ -1334,8 +1334,14 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
     h_texts_cap_ = packed_bytes + packed_bytes / 4;
   }
   uint8_t* packed = h_texts_;
+  d_texts_.ensure(packed_bytes);
+  SB_CUDA(cudaEventRecord(ev_[0], stream_));
   {
-    const size_t nthreads = total > (8u << 20) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    // The texts are separate host buffers: a few threads copy them range by range (consecutive
+    // texts, ~8 MB each) into the pinned staging buffer, and every finished range is handed to the
+    // copy engine at once, so the upload runs behind the host copies instead of after them.
+    const size_t nthreads =
+        total > (8u << 20) ? std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
     auto copy_range = [&](size_t t0, size_t t1) {
       for (size_t i = t0; i < t1; i++) {
         if (lens[i]) memcpy(packed + meta[i], texts[i], lens[i]);
@@ -1346,20 +1352,50 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
     };
     if (nthreads == 1) {
       copy_range(0, ntexts);
+      if (meta_off > text_bytes) memset(packed + text_bytes, 0, meta_off - text_bytes);
+      memcpy(packed + meta_off, meta.data(), meta.size() * sizeof(uint64_t));
+      SB_CUDA(cudaMemcpyAsync(d_texts_.p, packed, packed_bytes, cudaMemcpyHostToDevice, stream_));
     } else {
+      // ranges of consecutive texts with about the same number of bytes
+      const size_t nranges = std::min<size_t>(ntexts, std::max<size_t>(nthreads * 2, (size_t)(total >> 23)));
+      std::vector<size_t> first(nranges + 1, ntexts);
+      first[0] = 0;
+      {
+        size_t r = 1;
+        for (size_t i = 0; i < ntexts && r < nranges; i++)
+          if (meta[i] >= total / nranges * r) first[r++] = i;
+      }
+      std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[nranges]);
+      for (size_t r = 0; r < nranges; r++) done[r].store(0);
+      std::atomic<size_t> next_range{0};
       std::vector<std::thread> th;
       for (size_t t = 0; t < nthreads; t++)
-        th.emplace_back(copy_range, ntexts * t / nthreads, ntexts * (t + 1) / nthreads);
+        th.emplace_back([&] {
+          for (;;) {
+            const size_t r = next_range.fetch_add(1);
+            if (r >= nranges) return;
+            copy_range(first[r], first[r + 1]);
+            done[r].store(1, std::memory_order_release);
+          }
+        });
+      cudaError_t err = cudaSuccess;
+      for (size_t r = 0; r < nranges; r++) {
+        while (done[r].load(std::memory_order_acquire) == 0) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        const uint64_t b0 = first[r] < ntexts ? meta[first[r]] : text_bytes;
+        const uint64_t b1 = first[r + 1] < ntexts ? meta[first[r + 1]] : text_bytes;
+        if (b1 > b0 && err == cudaSuccess)
+          err = cudaMemcpyAsync(d_texts_.as<uint8_t>() + b0, packed + b0, b1 - b0, cudaMemcpyHostToDevice, stream_);
+      }
       for (auto& x : th) x.join();
+      SB_CUDA(err);
+      if (meta_off > text_bytes) memset(packed + text_bytes, 0, meta_off - text_bytes);
+      memcpy(packed + meta_off, meta.data(), meta.size() * sizeof(uint64_t));
+      SB_CUDA(cudaMemcpyAsync(d_texts_.as<uint8_t>() + text_bytes, packed + text_bytes, packed_bytes - text_bytes,
+                              cudaMemcpyHostToDevice, stream_));
     }
-    if (meta_off > text_bytes) memset(packed + text_bytes, 0, meta_off - text_bytes);
   }
-  memcpy(packed + meta_off, meta.data(), meta.size() * sizeof(uint64_t));
-  d_texts_.ensure(packed_bytes);
   const double t_stage1 = HostTimers::on() ? HostTimers::now_us() : 0.0;
   if (HostTimers::on()) HostTimers::add(HostTimers::kTextsStage, t_stage1 - t_stage0);
-  SB_CUDA(cudaEventRecord(ev_[0], stream_));
-  SB_CUDA(cudaMemcpyAsync(d_texts_.p, packed, packed_bytes, cudaMemcpyHostToDevice, stream_));
   const uint8_t* d_base = d_texts_.as<uint8_t>();
   const uint64_t* d_offs = reinterpret_cast<const uint64_t*>(d_base + meta_off);
   const uint64_t* d_lens = d_offs + ntexts;
