@@ -144,3 +144,65 @@ def test_overhang_is_plain_search_away_from_the_ends():
         inner = lambda ms: [x for x in ms if x.text_start > m + k and x.text_end < n - (m + k) and x.pattern_start == 0
                             and x.pattern_end == m]
         assert inner(a) == inner(b)
+
+
+def test_concatenated_texts_argument():
+    """The argument behind the many-text route of the GPU engine (Engine::search_texts, DESIGN 4.6):
+    scanning texts as ONE concatenation gives, beyond the first m + k end positions of a text (in scan
+    direction), exactly the end positions and costs <= k of a search of that text alone -- whatever
+    precedes it -- and the first m + k end positions only need the text's own first m + k characters."""
+    import random
+    from tests.test_oracle_props import mutate, rand_seq
+    rng = random.Random(123)
+    seen_deep, seen_head, seen_rc = 0, 0, 0
+    for alphabet in ("dna", "iupac"):
+        for it in range(25):
+            m = rng.randrange(4, 40)
+            k = rng.randrange(0, max(1, m // 3))
+            p = rand_seq(rng, m)
+            texts = []
+            for _ in range(rng.randrange(2, 9)):
+                ln = rng.choice([0, 1, m - 1, m + k, m + k + 1, 3 * m, 200])
+                t = bytearray(rand_seq(rng, ln))
+                if ln >= m and rng.random() < 0.8:  # a copy at the very start / end / somewhere
+                    q = mutate(rng, p, rng.randrange(0, k + 1))[:ln]
+                    pos = rng.choice([0, max(0, ln - len(q)), rng.randrange(0, ln - len(q) + 1)])
+                    t[pos:pos + len(q)] = q
+                texts.append(bytes(t))
+            # as the engine stages them: every text on a 16-byte boundary, zero bytes in between
+            offs, cat = [], bytearray()
+            for t in texts:
+                offs.append(len(cat))
+                cat += t + bytes((-len(t)) % 16)
+            cat = bytes(cat)
+            total = len(cat)
+            if total == 0:
+                continue
+
+            def ends(ms, n):  # (strand, end position in scan direction, cost)
+                return {(x.strand, x.text_end if x.strand == "+" else n - x.text_start, x.cost) for x in ms}
+
+            # (costs and end positions only: the padding bytes are outside the alphabet, a traceback
+            #  over them is the reference's "Trace failed" panic; the engine traces per text)
+            whole = ends(oracle.search(alphabet, p, cat, k, rc=True, all_minima=True, without_trace=True), total)
+            for t, off in zip(texts, offs):
+                n = len(t)
+                own = ends(oracle.search(alphabet, p, t, k, rc=True, all_minima=True, without_trace=True), n)
+                # the concatenation's candidates that fall into this text, in text coordinates
+                got = set()
+                for strand, e, c in whole:
+                    g = e - 1 if strand == "+" else total - e  # forward index of the last character consumed
+                    if off <= g < off + n:
+                        local = g - off + 1 if strand == "+" else off + n - g
+                        if local > m + k:
+                            got.add((strand, local, c))
+                assert got == {x for x in own if x[1] > m + k}, (alphabet, p, texts, k)
+                seen_deep += len(got)
+                seen_rc += sum(1 for x in got if x[0] == "-")
+                # the first m + k end positions from the text's own first (scan direction) m + k characters
+                head_f = ends(oracle.search(alphabet, p, t[:m + k], k, rc=False, all_minima=True, without_trace=True),
+                              min(n, m + k))
+                want_f = {x for x in own if x[0] == "+" and x[1] <= m + k}
+                assert {x for x in head_f if x[1] <= m + k} == want_f, (alphabet, p, t, k)
+                seen_head += len(want_f)
+    assert seen_deep > 100 and seen_head > 20, (seen_deep, seen_head, seen_rc)
