@@ -730,7 +730,10 @@ void Engine::search(const DeviceText& text, const std::vector<Query>& queries, i
 
   const int occ = scan_blocks_per_sm(std::min(W, kMaxScanWords), false, variant_, nrows_);
   stats_.blocks_per_sm = (uint32_t)occ;
-  const ScanGeom g = choose_geom(n, m, k, nq, occ * sm_count_);
+  // blocks per tile of one scan launch: the queries of a direction (pairs of them in scan2_kernel)
+  auto launch_cols = [&](uint32_t cnt) { return (W == 1 && cnt >= 2 && scan2_) ? (cnt + 1) / 2 : cnt; };
+  const uint32_t cols = std::max<uint32_t>(1, std::max(launch_cols(nfwd), launch_cols(nq - nfwd)));
+  const ScanGeom g = choose_geom(n, m, k, cols, occ * sm_count_);
   if ((uint64_t)g.rows * g.ltot > text.alloc) throw CudaError("internal: text padding too small for tiling");
   stats_.ltot = g.ltot;
   stats_.rows = g.rows;
@@ -1462,7 +1465,9 @@ void Engine::search_texts(const uint8_t* const* texts, const uint64_t* lens, siz
     ctext.alloc = text_bytes;
     ctext.owned = false;
     const int occ = scan_blocks_per_sm(W, false, variant_, nrows_);
-    cg = choose_geom(total, m, k, nq, occ * sm_count_);
+    auto launch_cols = [&](uint32_t cnt) { return (W == 1 && cnt >= 2 && scan2_) ? (cnt + 1) / 2 : cnt; };
+    cg = choose_geom(total, m, k, std::max<uint32_t>(1, std::max(launch_cols(nfwd), launch_cols(nq - nfwd))),
+                     occ * sm_count_);
     if ((uint64_t)cg.rows * cg.ltot > ctext.alloc) throw CudaError("internal: text padding too small for tiling");
     if (variant_ == kVariantTma) make_tensor_map(&ctmap, ctext, cg);
     stats_.ltot = cg.ltot;

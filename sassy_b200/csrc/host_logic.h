@@ -72,6 +72,8 @@ inline void build_eq_table(int profile, const uint8_t* p, int m, int W, uint32_t
 // block, one block per (tile, query).  ltot is as long as possible (the
 // per-row warm-up costs nwarm*128 bytes) subject to filling the GPU with a
 // whole number of waves when the grid is small.  bpw = resident blocks per wave.
+// nq = blocks per tile of ONE launch (the queries of a direction; half of them, rounded up, when two
+// patterns share a thread): a launch then fills whole waves.
 inline ScanGeom choose_geom(uint64_t n, int m, int k, uint32_t nq, int bpw) {
   ScanGeom g;
   g.nwarm = (uint32_t)((m + k + kStageBytes - 1) / kStageBytes);
@@ -82,9 +84,9 @@ inline ScanGeom choose_geom(uint64_t n, int m, int k, uint32_t nq, int bpw) {
   const uint64_t fill = ((uint64_t)bpw + nq - 1) / nq;  // tiles needed to give every SM slot a block
   tiles = std::max(tiles, fill);
   uint64_t blocks = tiles * nq;
-  if (blocks < 16ull * bpw) {  // few waves: round up to whole waves
+  if (blocks < 16ull * bpw) {  // few waves: whole waves (never more blocks than they hold: tiles round down)
     blocks = (blocks + bpw - 1) / bpw * bpw;
-    tiles = (blocks + nq - 1) / nq;
+    tiles = std::max<uint64_t>(tiles, blocks / nq);
   }
   uint64_t ltot = (n + tiles * kScanThreads - 1) / (tiles * kScanThreads);
   ltot = (ltot + kRowAlign - 1) / kRowAlign * kRowAlign;
